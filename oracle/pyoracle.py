@@ -1,0 +1,158 @@
+"""ctypes binding of oracle/liboracle.so and a runner for oracle/_ref/ref_harness.
+
+TEST INFRASTRUCTURE ONLY (see oracle/dmx_oracle.h): imported by tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / --impl reference legs -- never by demuxlet_b200/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liboracle.so")
+REF_BIN = os.path.join(HERE, "_ref", "ref_harness")
+
+
+class OrcInput(C.Structure):
+    _fields_ = [
+        ("nv", C.c_int32), ("n_alpha", C.c_int32), ("alpha", C.POINTER(C.c_double)),
+        ("doublet_prior", C.c_double),
+        ("min_total", C.c_int32), ("min_uniq", C.c_int32), ("min_snp", C.c_int32),
+        ("nsnps", C.c_int64), ("gp", C.POINTER(C.c_float)),
+        ("ncells", C.c_int64), ("cell_ptr", C.POINTER(C.c_int64)), ("ent_snp", C.POINTER(C.c_int32)),
+        ("ent_ptr", C.POINTER(C.c_int64)), ("reads", C.POINTER(C.c_uint16)),
+        ("totl", C.POINTER(C.c_int32)), ("npass", C.POINTER(C.c_int32)), ("uniq", C.POINTER(C.c_int32)),
+    ]
+
+
+BEST_DTYPE = np.dtype([
+    ("skipped", "<i4"), ("n_snp", "<i4"), ("i_sing1", "<i4"), ("i_sing2", "<i4"),
+    ("j_best", "<i4"), ("k_best", "<i4"), ("a_best", "<i4"), ("call", "<i4"),
+    ("max_llk", "<f8"), ("sum_single", "<f8"), ("sum_double", "<f8"),
+    ("sing_llk1", "<f8"), ("sing_llk2", "<f8"), ("sing_llk0", "<f8"),
+    ("pair_llk12", "<f8"), ("pair_llk1", "<f8"), ("pair_llk2", "<f8"),
+    ("pair_llk10", "<f8"), ("pair_llk20", "<f8"), ("pair_llk00", "<f8"),
+    ("post_doublet", "<f8"), ("post_singlet", "<f8"),
+], align=True)
+
+_lib = None
+
+
+def build() -> None:
+    subprocess.run(["make", "-C", HERE, "all"], check=True, stdout=subprocess.DEVNULL)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        _lib = C.CDLL(LIB_PATH)
+        _lib.orc_time_cells.restype = C.c_double
+        _lib.orc_pass2_one.restype = C.c_double
+        _lib.orc_count_asym.restype = C.c_int64
+        _lib.orc_write_all.restype = C.c_int
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class Oracle:
+    """Holds an orc_input over a Pileup (keeps the numpy arrays alive)."""
+
+    def __init__(self, plp, alphas=(0.0, 0.5), doublet_prior=0.5, min_total=0, min_uniq=0, min_snp=0):
+        self.plp = plp
+        self.alpha = np.ascontiguousarray(alphas, dtype=np.float64)
+        self.inp = OrcInput(
+            plp.nv, len(self.alpha), _p(self.alpha, C.c_double), doublet_prior,
+            min_total, min_uniq, min_snp, plp.nsnps, _p(plp.gp, C.c_float), plp.ncells,
+            _p(plp.cell_ptr, C.c_int64), _p(plp.ent_snp, C.c_int32), _p(plp.ent_ptr, C.c_int64),
+            _p(plp.reads, C.c_uint16), _p(plp.totl, C.c_int32), _p(plp.npass, C.c_int32),
+            _p(plp.uniq, C.c_int32))
+        assert BEST_DTYPE.itemsize == 8 * 4 + 14 * 8
+        self.nv, self.nA = plp.nv, len(self.alpha)
+
+    def gp0(self):
+        out = np.zeros((self.plp.nsnps, 3))
+        lib().orc_gp0(C.byref(self.inp), _p(out, C.c_double))
+        return out
+
+    def run(self, nthreads=1, want_pass1=True):
+        n, nv, nA = self.plp.ncells, self.nv, self.nA
+        best = np.zeros(n, dtype=BEST_DTYPE)
+        sing = np.zeros((n, nv)); l00 = np.zeros((n, nA))
+        p1 = np.zeros((n, nv)); p10 = np.zeros(n)
+        lib().orc_run(C.byref(self.inp), C.c_int32(nthreads), best.ctypes.data_as(C.c_void_p),
+                      _p(sing, C.c_double), _p(l00, C.c_double),
+                      _p(p1, C.c_double) if want_pass1 else None,
+                      _p(p10, C.c_double) if want_pass1 else None)
+        return dict(best=best, sing=sing, l00=l00, p1=p1, p1_0=p10)
+
+    def pass2_cell(self, cell, gp0=None):
+        nv, nA = self.nv, self.nA
+        if gp0 is None:
+            gp0 = self.gp0()
+        AB = np.zeros((nv, nv, nA)); A0 = np.zeros((nv, nA)); L00 = np.zeros(nA)
+        lib().orc_pass2_cell(C.byref(self.inp), _p(gp0, C.c_double), C.c_int64(cell),
+                             _p(AB, C.c_double), _p(A0, C.c_double), _p(L00, C.c_double))
+        return AB, A0, L00
+
+    def pass2_one(self, cell, j, k, n):
+        return lib().orc_pass2_one(C.byref(self.inp), C.c_int64(cell), C.c_int32(j), C.c_int32(k),
+                                   C.c_int32(n))
+
+    def count_asym(self, AB, n):
+        AB = np.ascontiguousarray(AB)
+        return int(lib().orc_count_asym(C.byref(self.inp), _p(AB, C.c_double), C.c_int32(n)))
+
+    def time_cells(self, cells, nthreads=1, with_pass1=True):
+        cells = np.ascontiguousarray(cells, dtype=np.int64)
+        return float(lib().orc_time_cells(C.byref(self.inp), _p(cells, C.c_int64),
+                                          C.c_int64(len(cells)), C.c_int32(nthreads),
+                                          C.c_int32(1 if with_pass1 else 0)))
+
+    def write_all(self, prefix, write_pair=False):
+        bcs = (C.c_char_p * self.plp.ncells)(*[b.encode() for b in self.plp.barcodes])
+        sms = (C.c_char_p * self.nv)(*[s.encode() for s in self.plp.samples])
+        rc = lib().orc_write_all(C.byref(self.inp), bcs, sms, prefix.encode(), C.c_int32(1 if write_pair else 0))
+        if rc != 0:
+            raise OSError("orc_write_all failed for %s" % prefix)
+
+
+def ref_available() -> bool:
+    return os.path.exists(REF_BIN) and os.access(REF_BIN, os.X_OK)
+
+
+def run_ref(plp, prefix, alphas=None, write_pair=False, doublet_prior=None, min_total=0, min_uniq=0,
+            min_snp=0, plp_path=None):
+    """Run the reference's own lines 386-881 (oracle/_ref/ref_harness) on a Pileup; writes
+    <prefix>.single/.sing2/.best[/.pair]; returns the harness' timing dict."""
+    if not ref_available():
+        raise FileNotFoundError(REF_BIN)
+    tmp = None
+    if plp_path is None:
+        tmp = tempfile.NamedTemporaryFile(suffix=".dmxp", delete=False)
+        tmp.close()
+        plp_path = tmp.name
+        plp.save(plp_path)
+    cmd = [REF_BIN, plp_path, prefix]
+    for a in (alphas or []):
+        cmd += ["--alpha", repr(float(a))]
+    if write_pair:
+        cmd.append("--write-pair")
+    if doublet_prior is not None:
+        cmd += ["--doublet-prior", repr(float(doublet_prior))]
+    cmd += ["--min-total", str(min_total), "--min-uniq", str(min_uniq), "--min-snp", str(min_snp)]
+    try:
+        out = subprocess.run(cmd, check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
+    finally:
+        if tmp is not None:
+            os.unlink(plp_path)
+    return json.loads(out.stdout.decode().strip().splitlines()[-1])
