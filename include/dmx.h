@@ -1,0 +1,161 @@
+/*
+ * dmx.h -- C ABI of libdmx: the B200 (sm_100a) implementation of demuxlet's per-barcode
+ * genotype-likelihood / doublet-pair scan.
+ *
+ * The reference has no plugin or FFI boundary for this path: the whole computation is a code
+ * region of main() (/root/reference/cmd_cram_demuxlet.cpp:386-875) that consumes the in-memory
+ * pileup `sc_dropseq_lib_t scl` (/root/reference/sc_drop_seq.h:34-58), the per-SNP genotype
+ * probabilities `scl.snps[i].gps`, `gridAlpha`, `doublet_prior` and the three min-filters, and
+ * prints four TSV files.  This header is the boundary a maintainer would cut there
+ * (INTEGRATION.md shows the call site): flat arrays in, fixed-size records out, plain pointers and
+ * sizes, no C++/CUDA/torch types.  Each entry point cites the reference lines it replaces.
+ *
+ * Conventions: every function returns 0 (DMX_OK) or a negative dmx_status and never throws or
+ * aborts; the caller owns all host buffers (the library copies what it keeps unless
+ * DMX_BORROW_INPUTS is set); a dmx_ctx is bound to one CUDA device and is not thread-safe;
+ * multi-GPU runs use one ctx (one process) per device over disjoint cell ranges -- cells are
+ * independent in the reference (:576-875), cf. its --group-list sharding (:68).
+ */
+#ifndef DMX_H
+#define DMX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMX_ABI_VERSION 1
+#define DMX_MAX_ALPHA 16
+
+typedef enum {
+  DMX_OK = 0,
+  DMX_E_INVALID = -1,      /* bad argument (nv < 2, n_alpha < 2, null pointer, unsorted CSR ...) */
+  DMX_E_CUDA = -2,         /* CUDA runtime error; dmx_last_error() has the text                   */
+  DMX_E_NODEVICE = -3,     /* no usable sm_100 device: the library has NO CPU fallback           */
+  DMX_E_STATE = -4,        /* call order: gp/pileup not set, run not done                        */
+  DMX_E_NOMEM = -5,
+  DMX_E_IO = -6,           /* output file cannot be created (:409, :535)                         */
+  DMX_E_UNSUPPORTED = -7
+} dmx_status;
+
+/* dmx_config.flags */
+#define DMX_EXACT_TIES    0x1u  /* re-score near-tied candidates with the reference's exact double
+                                   arithmetic so BEST / SNG.1ST / DBL.1ST are bit-identical (default on
+                                   through dmx_config_default) */
+#define DMX_BORROW_INPUTS 0x2u  /* dmx_set_gp/dmx_set_pileup keep the caller's pointers (which must
+                                   stay valid and unchanged until the ctx is destroyed or re-set)
+                                   instead of copying; use with dmx_alloc_host for pinned transfers */
+#define DMX_FP32_PAIRS    0x4u  /* pair scan accumulates in fp32 (faster, ~1e-6 LLK error) instead
+                                   of fp64; singlet, pass-1 and all re-scored values stay fp64      */
+
+typedef struct {
+  int32_t nv;                  /* number of VCF samples, >= 2 (:180)                   */
+  int32_t n_alpha;             /* alpha grid size, >= 2, <= DMX_MAX_ALPHA (:348)                   */
+  const double* alpha;         /* gridAlpha (:54, :78-90); alpha[0] is the "singlet" slot (Q3)     */
+  double doublet_prior;        /* --doublet-prior (:56)                                            */
+  int32_t min_total, min_uniq, min_snp;   /* --min-total/--min-uniq/--min-snp (:69-71, :581)       */
+  int32_t device;              /* CUDA device ordinal                                              */
+  uint32_t flags;
+  int32_t n_host_threads;      /* threads of the tie finaliser; 0 = hardware concurrency           */
+} dmx_config;
+
+/* one row of <out>.best (:816-874), fixed size POD */
+typedef struct {
+  int32_t status;              /* 0 row present; 1 dropped by the min-filters (:581); 2 no SNP (:592) */
+  int32_t n_snp;               /* N.SNP = covered SNPs incl. all-allele-2 ones (:835)               */
+  int32_t sng1, sng2;          /* iSing1, iSing2 (:746-758)                                         */
+  int32_t dbl1, dbl2, alpha_idx; /* jBest, kBest, alphaBest (:799-814)                              */
+  int32_t call;                /* 0 DBL, 1 SNG, 2 AMB (:837-857)                                    */
+  double sng_llk1, sng_llk2, sng_llk0;                 /* :816-820 */
+  double llk12, llk1, llk2, llk10, llk20, llk00;       /* :821-826 */
+  double prb_dbl, prb_sng1;                            /* :827-828 */
+  double max_llk, sum_single, sum_double;              /* :713-734 */
+  int32_t n_rescored;          /* hypotheses the tie finaliser re-scored exactly for this cell      */
+  uint32_t exact_mask;         /* DMX_X_* : which LLK fields carry reference-exact bits             */
+} dmx_best_rec;
+
+#define DMX_X_SNG1  0x01u
+#define DMX_X_SNG2  0x02u
+#define DMX_X_LLK12 0x04u
+#define DMX_X_LLK1  0x08u
+#define DMX_X_LLK2  0x10u
+#define DMX_X_FULLCELL 0x80u   /* whole cell recomputed exactly (candidate list overflowed)         */
+
+typedef struct {
+  double h2d_ms, prep_ms, kernel_ms, d2h_ms, finalise_ms, total_ms;  /* last dmx_run / dmx_compute */
+  int64_t h2d_bytes, d2h_bytes;
+  int64_t n_entries, n_reads, n_tasks;
+  int64_t gpu_launches;        /* kernels launched by the last run                                 */
+  int64_t n_rescored;          /* hypotheses re-scored exactly                                     */
+  int64_t n_fullcell;          /* cells recomputed exactly in full                                 */
+  double algo_bytes;           /* SURVEY 8(d) gather-model bytes of the pair kernel, last run      */
+  double pair_kernel_ms;       /* CUDA-event time of the pair-scan kernel(s) alone                 */
+} dmx_stats;
+
+typedef struct dmx_ctx dmx_ctx;
+
+/* defaults of the reference CLI: doublet_prior 0.5 (:29), filters 0 (:31-33), alpha {0, 0.5}
+ * must still be supplied by the caller; flags = DMX_EXACT_TIES */
+void dmx_config_default(dmx_config* cfg);
+
+/* number of CUDA devices this library can run on (compute capability 10.x); 0 if none */
+int dmx_device_count(void);
+
+int dmx_create(dmx_ctx** out, const dmx_config* cfg);
+void dmx_destroy(dmx_ctx* ctx);
+
+/* gp[nsnps][nv][3], genotype fastest: exactly the floats the reference widens into
+ * scl.snps[i].gps (:181-184, :227-231).  Also computes the cohort mean gp0s (:391-401) on device. */
+int dmx_set_gp(dmx_ctx* ctx, const float* gp, int64_t nsnps);
+
+/* CSR flattening of sc_dropseq_lib_t (sc_drop_seq.h:34-58):
+ *   cell_ptr[ncells+1]  into entries, cells in cell-id (first-seen) order
+ *   ent_snp[E]          SNP id, strictly ascending inside a cell (std::map<int32_t,..> order)
+ *   ent_ptr[E+1]        into reads
+ *   reads[R]            allele<<8 | bq, in UMI-string order inside an entry (std::map<std::string,..>),
+ *                       allele 0 ref / 1 alt / 2 other (:322), bq already capped (:323)
+ *   totl/pass/uniq[ncells]  cell_totl_reads / cell_pass_reads / cell_uniq_reads */
+int dmx_set_pileup(dmx_ctx* ctx, int64_t ncells, const int64_t* cell_ptr, const int32_t* ent_snp,
+                   const int64_t* ent_ptr, const uint16_t* reads, const int32_t* totl,
+                   const int32_t* pass, const int32_t* uniq);
+
+/* dmx_run = dmx_upload (host->device copies) + dmx_compute (kernels, record read-back, tie finaliser).
+ * Replaces cmd_cram_demuxlet.cpp:412-461 (pass 1) and :539-734, :746-758, :799-828 (pass 2). */
+int dmx_upload(dmx_ctx* ctx);
+int dmx_compute(dmx_ctx* ctx);
+int dmx_run(dmx_ctx* ctx);
+
+/* results, valid after dmx_run/dmx_compute; arrays are in cell-id order */
+int dmx_get_best(dmx_ctx* ctx, dmx_best_rec* out /* [ncells] */);
+/* pass 1 (:455-459): llk[ncells][nv] = llks, llk0[ncells] = llk0s */
+int dmx_get_single(dmx_ctx* ctx, double* llk, double* llk0);
+/* :760-769: llk_j00[ncells][nv] = llksAB[j][0][0]; llk00[ncells][n_alpha] = llks00 */
+int dmx_get_sing2(dmx_ctx* ctx, double* llk_j00, double* llk00);
+/* dense llksAB[cell][j][k][n] for cells [cell_lo, cell_hi) (what --write-pair prints, :772-797);
+ * re-runs the pair scan for that range with dense stores */
+int dmx_get_pair(dmx_ctx* ctx, int64_t cell_lo, int64_t cell_hi, double* llkAB);
+
+/* exact (reference-arithmetic) value of one hypothesis, as the tie finaliser computes it */
+int dmx_rescore(dmx_ctx* ctx, int64_t cell, int32_t j, int32_t k, int32_t n, double* out);
+
+/* writers with the reference's formats: <prefix>.single (:470,:506), .sing2 (:533,:760),
+ * .best (:571,:830-874) and, if write_pair, .pair (:570,:774-792).  Rows in barcode
+ * lexicographic order (std::map iteration, :472,:576). */
+int dmx_write_outputs(dmx_ctx* ctx, const char* const* barcodes /* [ncells] */,
+                      const char* const* samples /* [nv] */, const char* prefix, int write_pair);
+
+int dmx_get_stats(dmx_ctx* ctx, dmx_stats* out);
+
+/* pinned host memory for DMX_BORROW_INPUTS callers */
+void* dmx_alloc_host(int64_t bytes);
+void dmx_free_host(void* p);
+
+const char* dmx_strerror(int status);
+const char* dmx_last_error(void);      /* text of the last DMX_E_CUDA on this thread */
+int dmx_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
