@@ -1,0 +1,254 @@
+"""ctypes binding of libdmx.so (include/dmx.h) and the host-side driver object.
+
+`Demuxlet` mirrors what the reference's main() does after the pileup is built
+(/root/reference/cmd_cram_demuxlet.cpp:386-875): it takes the flat pileup (demuxlet_b200.plp.Pileup),
+the alpha grid / doublet prior / min-filters of the reference CLI (:54-56, :69-71), runs the likelihood
+scan on the GPU and writes <out>.single/.sing2/.best[/.pair].  There is no CPU fallback: a missing
+library or a machine without an sm_100 GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .plp import Pileup
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdmx.so")
+
+DMX_EXACT_TIES = 0x1
+DMX_BORROW_INPUTS = 0x2
+DMX_FP32_PAIRS = 0x4
+DMX_SKIP_SINGLE = 0x8
+DMX_TRUST_INPUTS = 0x10
+
+# every symbol include/dmx.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = [
+    "dmx_config_default", "dmx_device_count", "dmx_create", "dmx_destroy", "dmx_set_gp", "dmx_set_pileup",
+    "dmx_upload", "dmx_compute", "dmx_run", "dmx_get_best", "dmx_get_single", "dmx_get_sing2", "dmx_get_pair",
+    "dmx_rescore", "dmx_write_outputs", "dmx_get_stats", "dmx_alloc_host", "dmx_free_host", "dmx_strerror",
+    "dmx_last_error", "dmx_abi_version",
+]
+
+
+class DmxConfig(C.Structure):
+    _fields_ = [
+        ("nv", C.c_int32), ("n_alpha", C.c_int32), ("alpha", C.POINTER(C.c_double)),
+        ("doublet_prior", C.c_double),
+        ("min_total", C.c_int32), ("min_uniq", C.c_int32), ("min_snp", C.c_int32),
+        ("device", C.c_int32), ("flags", C.c_uint32), ("n_host_threads", C.c_int32),
+    ]
+
+
+BEST_DTYPE = np.dtype([
+    ("status", "<i4"), ("n_snp", "<i4"), ("sng1", "<i4"), ("sng2", "<i4"),
+    ("dbl1", "<i4"), ("dbl2", "<i4"), ("alpha_idx", "<i4"), ("call", "<i4"),
+    ("sng_llk1", "<f8"), ("sng_llk2", "<f8"), ("sng_llk0", "<f8"),
+    ("llk12", "<f8"), ("llk1", "<f8"), ("llk2", "<f8"), ("llk10", "<f8"), ("llk20", "<f8"), ("llk00", "<f8"),
+    ("prb_dbl", "<f8"), ("prb_sng1", "<f8"),
+    ("max_llk", "<f8"), ("sum_single", "<f8"), ("sum_double", "<f8"),
+    ("n_rescored", "<i4"), ("exact_mask", "<u4"),
+], align=True)
+
+
+class DmxStats(C.Structure):
+    _fields_ = [
+        ("h2d_ms", C.c_double), ("prep_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double),
+        ("finalise_ms", C.c_double), ("total_ms", C.c_double),
+        ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+        ("n_entries", C.c_int64), ("n_reads", C.c_int64), ("n_tasks", C.c_int64),
+        ("gpu_launches", C.c_int64), ("n_rescored", C.c_int64), ("n_fullcell", C.c_int64),
+        ("algo_bytes", C.c_double), ("pair_kernel_ms", C.c_double),
+    ]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class DmxError(RuntimeError):
+    def __init__(self, status: int, where: str, detail: str = ""):
+        self.status = status
+        super().__init__("%s failed: %s (%d)%s" % (where, _strerror(status), status, (" -- " + detail) if detail else ""))
+
+
+_lib = None
+
+
+def load_library(path: Optional[str] = None):
+    """dlopen libdmx.so; raises OSError if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    lib = C.CDLL(path or LIB_PATH)
+    lib.dmx_strerror.restype = C.c_char_p
+    lib.dmx_last_error.restype = C.c_char_p
+    lib.dmx_alloc_host.restype = C.c_void_p
+    lib.dmx_alloc_host.argtypes = [C.c_int64]
+    lib.dmx_free_host.argtypes = [C.c_void_p]
+    lib.dmx_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(DmxConfig)]
+    lib.dmx_destroy.argtypes = [C.c_void_p]
+    lib.dmx_destroy.restype = None
+    lib.dmx_set_gp.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    lib.dmx_set_pileup.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7
+    for f in ("dmx_upload", "dmx_compute", "dmx_run"):
+        getattr(lib, f).argtypes = [C.c_void_p]
+    lib.dmx_get_best.argtypes = [C.c_void_p, C.c_void_p]
+    lib.dmx_get_single.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.dmx_get_sing2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.dmx_get_pair.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+    lib.dmx_rescore.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double)]
+    lib.dmx_write_outputs.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_char_p, C.c_int]
+    lib.dmx_get_stats.argtypes = [C.c_void_p, C.POINTER(DmxStats)]
+    lib.dmx_config_default.argtypes = [C.POINTER(DmxConfig)]
+    lib.dmx_config_default.restype = None
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _strerror(status: int) -> str:
+    try:
+        return load_library().dmx_strerror(status).decode()
+    except OSError:
+        return "status %d" % status
+
+
+def device_count() -> int:
+    return int(load_library().dmx_device_count())
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """numpy array over cudaMallocHost memory (for DMX_BORROW_INPUTS); freed with the array."""
+    lib = load_library()
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    ptr = lib.dmx_alloc_host(max(n, 1))
+    if not ptr:
+        raise MemoryError("dmx_alloc_host(%d)" % n)
+    buf = (C.c_char * max(n, 1)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED[ptr] = buf
+    import weakref
+    weakref.finalize(buf, lib.dmx_free_host, ptr)
+    return arr
+
+
+_PINNED: dict = {}
+
+
+class Demuxlet:
+    """The likelihood scan of one pileup on one GPU.
+
+    alphas        --alpha (multi-valued; default {0, 0.5}, cmd_cram_demuxlet.cpp:78-90)
+    doublet_prior --doublet-prior (:56)
+    min_total/min_uniq/min_snp  --min-total/--min-uniq/--min-snp (:69-71)
+    """
+
+    def __init__(self, nv: int, alphas: Sequence[float] = (0.0, 0.5), doublet_prior: float = 0.5,
+                 min_total: int = 0, min_uniq: int = 0, min_snp: int = 0, device: int = 0,
+                 exact_ties: bool = True, borrow: bool = False, fp32_pairs: bool = False,
+                 skip_single: bool = False, trust_inputs: bool = False, host_threads: int = 0):
+        self.lib = load_library()
+        self.nv = int(nv)
+        self.alpha = np.ascontiguousarray(alphas, dtype=np.float64)
+        self.nA = int(self.alpha.shape[0])
+        flags = ((DMX_EXACT_TIES if exact_ties else 0) | (DMX_BORROW_INPUTS if borrow else 0) |
+                 (DMX_FP32_PAIRS if fp32_pairs else 0) | (DMX_SKIP_SINGLE if skip_single else 0) |
+                 (DMX_TRUST_INPUTS if trust_inputs else 0))
+        self.cfg = DmxConfig(self.nv, self.nA, self.alpha.ctypes.data_as(C.POINTER(C.c_double)), doublet_prior,
+                             min_total, min_uniq, min_snp, device, flags, host_threads)
+        self._h = C.c_void_p()
+        self._chk(self.lib.dmx_create(C.byref(self._h), C.byref(self.cfg)), "dmx_create")
+        self._keep = []
+        self.ncells = 0
+        self.plp: Optional[Pileup] = None
+
+    def _chk(self, rc: int, where: str):
+        if rc != 0:
+            raise DmxError(rc, where, self.lib.dmx_last_error().decode() if rc == -2 else "")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.dmx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- inputs -----------------------------------------------------------------------------------
+    def set_gp(self, gp: np.ndarray):
+        assert gp.dtype == np.float32 and gp.flags.c_contiguous and gp.shape[1:] == (self.nv, 3)
+        self._gp = gp
+        self._chk(self.lib.dmx_set_gp(self._h, gp.ctypes.data, gp.shape[0]), "dmx_set_gp")
+
+    def set_pileup_arrays(self, cell_ptr, ent_snp, ent_ptr, reads, totl, npass, uniq):
+        self._keep = [cell_ptr, ent_snp, ent_ptr, reads, totl, npass, uniq]
+        self.ncells = int(cell_ptr.shape[0] - 1)
+        self._chk(self.lib.dmx_set_pileup(self._h, self.ncells, cell_ptr.ctypes.data, ent_snp.ctypes.data,
+                                          ent_ptr.ctypes.data, reads.ctypes.data, totl.ctypes.data,
+                                          npass.ctypes.data, uniq.ctypes.data), "dmx_set_pileup")
+
+    def set_pileup(self, plp: Pileup):
+        assert plp.nv == self.nv
+        self.plp = plp
+        self.set_gp(plp.gp)
+        self.set_pileup_arrays(plp.cell_ptr, plp.ent_snp, plp.ent_ptr, plp.reads, plp.totl, plp.npass, plp.uniq)
+
+    # ---- run --------------------------------------------------------------------------------------
+    def upload(self):
+        self._chk(self.lib.dmx_upload(self._h), "dmx_upload")
+
+    def compute(self):
+        self._chk(self.lib.dmx_compute(self._h), "dmx_compute")
+
+    def run(self):
+        self._chk(self.lib.dmx_run(self._h), "dmx_run")
+
+    # ---- results ----------------------------------------------------------------------------------
+    def best(self) -> np.ndarray:
+        out = np.zeros(self.ncells, dtype=BEST_DTYPE)
+        self._chk(self.lib.dmx_get_best(self._h, out.ctypes.data), "dmx_get_best")
+        return out
+
+    def single(self):
+        llk = np.zeros((self.ncells, self.nv))
+        llk0 = np.zeros(self.ncells)
+        self._chk(self.lib.dmx_get_single(self._h, llk.ctypes.data, llk0.ctypes.data), "dmx_get_single")
+        return llk, llk0
+
+    def sing2(self):
+        a = np.zeros((self.ncells, self.nv))
+        b = np.zeros((self.ncells, self.nA))
+        self._chk(self.lib.dmx_get_sing2(self._h, a.ctypes.data, b.ctypes.data), "dmx_get_sing2")
+        return a, b
+
+    def pair(self, lo: int, hi: int) -> np.ndarray:
+        out = np.zeros((hi - lo, self.nv, self.nv, self.nA))
+        self._chk(self.lib.dmx_get_pair(self._h, lo, hi, out.ctypes.data), "dmx_get_pair")
+        return out
+
+    def rescore(self, cell: int, j: int, k: int, n: int) -> float:
+        v = C.c_double()
+        self._chk(self.lib.dmx_rescore(self._h, cell, j, k, n, C.byref(v)), "dmx_rescore")
+        return v.value
+
+    def stats(self) -> dict:
+        st = DmxStats()
+        self._chk(self.lib.dmx_get_stats(self._h, C.byref(st)), "dmx_get_stats")
+        return st.asdict()
+
+    def write_outputs(self, prefix: str, barcodes: Optional[Sequence[str]] = None,
+                      samples: Optional[Sequence[str]] = None, write_pair: bool = False):
+        barcodes = barcodes if barcodes is not None else self.plp.barcodes
+        samples = samples if samples is not None else self.plp.samples
+        assert len(barcodes) == self.ncells and len(samples) == self.nv
+        bcs = (C.c_char_p * self.ncells)(*[b.encode() for b in barcodes])
+        sms = (C.c_char_p * self.nv)(*[s.encode() for s in samples])
+        self._chk(self.lib.dmx_write_outputs(self._h, bcs, sms, prefix.encode(), 1 if write_pair else 0),
+                  "dmx_write_outputs")

@@ -1,0 +1,819 @@
+// dmx_api.cu -- the C ABI of include/dmx.h: context, uploads, kernel orchestration, read-back,
+// tie finaliser threads and the TSV writers.  No CPU fallback: without an sm_100 device dmx_create
+// fails with DMX_E_NODEVICE.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "dmx_host.h"
+#include "dmx_internal.h"
+
+using namespace dmx;
+
+namespace {
+thread_local std::string g_last_error;
+
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;   // elements
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+template <class T>
+struct PinBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMallocHost((void**)&p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+}  // namespace
+
+struct dmx_ctx {
+  dmx_config cfg;
+  std::vector<double> alpha;
+  PGrid pg;
+  int UQ = 0;
+  std::vector<TaskType> tt;
+  double err256[256];
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+
+  // inputs (host): borrowed or owned
+  int nvp = 0;
+  int64_t nsnps = 0, ncells = 0, E = 0, R = 0;
+  const float* h_gp = nullptr;
+  const int64_t* h_cell_ptr = nullptr;
+  const int32_t* h_ent_snp = nullptr;
+  const int64_t* h_ent_ptr = nullptr;
+  const uint16_t* h_reads = nullptr;
+  PinBuf<float> o_gp;
+  PinBuf<int64_t> o_cell_ptr, o_ent_ptr;
+  PinBuf<int32_t> o_ent_snp;
+  PinBuf<uint16_t> o_reads;
+  std::vector<int32_t> totl, npass, uniq;
+  bool have_gp = false, have_plp = false, gp_dirty = true, plp_dirty = true, uploaded = false, computed = false;
+
+  // device
+  DevBuf<float> d_gp;
+  DevBuf<double> d_gp0, d_entq, d_row0, d_singA, d_lb, d_p1, d_p1_0, d_l00, d_sing, d_dense;
+  DevBuf<int64_t> d_cell_ptr, d_ent_ptr;
+  DevBuf<int32_t> d_ent_snp, d_order;
+  DevBuf<uint16_t> d_reads;
+  DevBuf<TaskType> d_tt;
+  DevBuf<Part> d_parts;
+  DevBuf<CellOut> d_out;
+
+  // schedule
+  std::vector<int32_t> order;       // active cells, largest first
+  std::vector<int32_t> status;      // per cell: 0 active, 1 filtered, 2 empty
+
+  // read-back (pinned)
+  PinBuf<CellOut> r_out;
+  PinBuf<double> r_sing, r_row0, r_l00, r_p1, r_p1_0, r_dense;
+
+  std::vector<dmx_best_rec> best;
+  dmx_stats st;
+};
+
+namespace {
+
+int fail_cuda(cudaError_t e, const char* what) {
+  g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return DMX_E_CUDA;
+}
+#define CU(x)                                                  \
+  do {                                                         \
+    cudaError_t e__ = (cudaError_t)(x);                        \
+    if (e__ != cudaSuccess) return fail_cuda(e__, #x);         \
+  } while (0)
+
+void build_tasks(dmx_ctx* c) {
+  const int nA = c->cfg.n_alpha, nvp = c->nvp;
+  const PGrid& g = c->pg;
+  c->tt.clear();
+  int fd = -1;
+  for (int n = 0; n < nA; ++n)
+    if (g.mode[n] != PM_SEP) { fd = n; break; }
+  const int nblk = (nvp + BLK - 1) / BLK;
+  for (int n = 0; n < nA; ++n) {
+    if (g.mode[n] == PM_SEP) continue;
+    const bool sym = g.mode[n] == PM_SYM;
+    bool first = true;
+    auto push = [&](int j0, int nj, int k0, int nk, uint32_t fl) {
+      TaskType t;
+      memset(&t, 0, sizeof(t));
+      t.n = (int16_t)n;
+      t.j0 = (int16_t)j0; t.nj = (int16_t)nj; t.k0 = (int16_t)k0; t.nk = (int16_t)nk;
+      t.flags = fl | (sym ? TF_SYM : 0u) | (n == 0 ? TF_NOARG : 0u);
+      if (first) {
+        t.flags |= TF_L00;
+        if (n == fd) t.flags |= TF_SCALARS;
+        first = false;
+      }
+      for (int i = 0; i < 9; ++i) t.qidx[i] = g.umap[n * 9 + i];
+      c->tt.push_back(t);
+    };
+    for (int jb = 0; jb < nblk; ++jb) {
+      const int j0 = jb * BLK, nj = std::min(BLK, nvp - j0);
+      if (sym) {
+        push(j0, nj, j0, nj, TF_TRI | (n == fd ? TF_EXTRAS : 0u));
+        for (int k0 = j0 + BLK; k0 < nvp; k0 += BLK_RECT_K) push(j0, nj, k0, std::min(BLK_RECT_K, nvp - k0), 0u);
+      } else {
+        for (int k0 = 0; k0 < nvp; k0 += BLK_RECT_K)
+          push(j0, nj, k0, std::min(BLK_RECT_K, nvp - k0), (n == fd && jb == 0) ? TF_EXTRAS : 0u);
+      }
+    }
+  }
+}
+
+template <class F>
+void parallel_for(int64_t n, int nthreads, F f) {
+  if (nthreads <= 1 || n < 2) {
+    for (int64_t i = 0; i < n; ++i) f(i, 0);
+    return;
+  }
+  std::atomic<int64_t> next(0);
+  std::vector<std::thread> th;
+  const int64_t chunk = std::max<int64_t>(1, n / (nthreads * 16));
+  for (int t = 0; t < nthreads; ++t)
+    th.emplace_back([&, t]() {
+      for (;;) {
+        const int64_t lo = next.fetch_add(chunk);
+        if (lo >= n) break;
+        const int64_t hi = std::min(n, lo + chunk);
+        for (int64_t i = lo; i < hi; ++i) f(i, t);
+      }
+    });
+  for (auto& x : th) x.join();
+}
+
+int host_threads(const dmx_ctx* c) {
+  int n = c->cfg.n_host_threads;
+  if (n <= 0) n = (int)std::thread::hardware_concurrency();
+  return std::max(1, n);
+}
+
+HostView host_view(const dmx_ctx* c) {
+  HostView hv;
+  hv.nv = c->cfg.nv; hv.nA = c->cfg.n_alpha; hv.alpha = c->alpha.data();
+  hv.gp = c->h_gp; hv.nsnps = c->nsnps; hv.ncells = c->ncells;
+  hv.cell_ptr = c->h_cell_ptr; hv.ent_snp = c->h_ent_snp; hv.ent_ptr = c->h_ent_ptr; hv.reads = c->h_reads;
+  return hv;
+}
+
+void fill_scan_params(dmx_ctx* c, ScanParams* p) {
+  memset(p, 0, sizeof(*p));
+  p->nv = c->cfg.nv; p->nvp = c->nvp; p->nA = c->cfg.n_alpha; p->U = c->pg.U; p->UQ = c->UQ;
+  p->sep0 = c->pg.sep0; p->T = (int)c->tt.size();
+  p->want_single = (c->cfg.flags & DMX_SKIP_SINGLE) ? 0 : 1;
+  for (int l = 0; l < 3; ++l) p->fidx[l] = c->pg.umap[l * 3];
+  p->eps_rel = (c->cfg.flags & DMX_FP32_PAIRS) ? 1e-4 : 1e-9;
+  p->gp = c->d_gp.p; p->gp0 = c->d_gp0.p; p->ent_snp = c->d_ent_snp.p; p->entq = c->d_entq.p;
+  p->cell_ptr = c->d_cell_ptr.p; p->cell_order = c->d_order.p; p->tt = c->d_tt.p; p->parts = c->d_parts.p;
+  p->row0 = c->d_row0.p; p->singA = c->d_singA.p; p->lb = c->d_lb.p; p->p1 = c->d_p1.p;
+  p->p1_0 = c->d_p1_0.p; p->l00 = c->d_l00.p; p->dense = nullptr;
+}
+
+// candidate list of a cell -> ordered hypotheses in (j,k,n) lexicographic order
+void expand_cands(const dmx_ctx* c, const CellOut& co, std::vector<Hyp>* out) {
+  out->clear();
+  const int nc = std::min<int>(co.ncand, MAX_CAND);
+  for (int i = 0; i < nc; ++i) {
+    const int j = co.cand[i] & 0xfff, k = (co.cand[i] >> 12) & 0xfff, n = co.cand[i] >> 24;
+    out->push_back(Hyp{j, k, n});
+    if (c->pg.mode[n] == PM_SYM) out->push_back(Hyp{k, j, n});
+  }
+  std::sort(out->begin(), out->end(), [](const Hyp& a, const Hyp& b) {
+    return a.j != b.j ? a.j < b.j : (a.k != b.k ? a.k < b.k : a.n < b.n);
+  });
+}
+
+// dense llksAB for a list of active cells (device order buffer is temporarily replaced)
+int dense_scan(dmx_ctx* c, const std::vector<int32_t>& cells, double* host_out /* [n][nv][nv][nA] */) {
+  const int nv = c->cfg.nv, nA = c->cfg.n_alpha;
+  const size_t per = (size_t)nv * nv * nA;
+  const size_t max_batch = std::max<size_t>(1, ((size_t)1 << 30) / (per * sizeof(double)));
+  DevBuf<int32_t> d_cells;
+  DevBuf<Part> d_parts;
+  CU(d_cells.reserve(std::min(cells.size(), max_batch)));
+  CU(d_parts.reserve(std::min(cells.size(), max_batch) * c->tt.size()));
+  CU(c->d_dense.reserve(std::min(cells.size(), max_batch) * per));
+  for (size_t lo = 0; lo < cells.size(); lo += max_batch) {
+    const size_t n = std::min(max_batch, cells.size() - lo);
+    CU(cudaMemcpyAsync(d_cells.p, cells.data() + lo, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    ScanParams p;
+    fill_scan_params(c, &p);
+    p.cell_order = d_cells.p;
+    p.parts = d_parts.p;
+    p.dense = c->d_dense.p;
+    CU(launch_pair_scan(p, (int64_t)n, false, c->stream));
+    CU(launch_fill_sep_dense(p, (int64_t)n, c->stream));
+    c->st.gpu_launches += 1 + (p.sep0 ? 1 : 0);
+    CU(cudaMemcpyAsync(host_out + lo * per, c->d_dense.p, n * per * sizeof(double), cudaMemcpyDeviceToHost,
+                       c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  d_cells.release();
+  d_parts.release();
+  return DMX_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int dmx_abi_version(void) { return DMX_ABI_VERSION; }
+
+const char* dmx_strerror(int s) {
+  switch (s) {
+    case DMX_OK: return "ok";
+    case DMX_E_INVALID: return "invalid argument";
+    case DMX_E_CUDA: return "CUDA error";
+    case DMX_E_NODEVICE: return "no sm_100 CUDA device (libdmx has no CPU fallback)";
+    case DMX_E_STATE: return "call order violated";
+    case DMX_E_NOMEM: return "out of memory";
+    case DMX_E_IO: return "cannot create output file";
+    case DMX_E_UNSUPPORTED: return "unsupported configuration";
+    default: return "unknown status";
+  }
+}
+
+const char* dmx_last_error(void) { return g_last_error.c_str(); }
+
+void dmx_config_default(dmx_config* cfg) {
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->doublet_prior = 0.5;          // cmd_cram_demuxlet.cpp:29
+  cfg->flags = DMX_EXACT_TIES;
+}
+
+int dmx_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ++ok;
+  }
+  return ok;
+}
+
+void* dmx_alloc_host(int64_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, (size_t)std::max<int64_t>(bytes, 1)) != cudaSuccess) return nullptr;
+  return p;
+}
+void dmx_free_host(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int dmx_create(dmx_ctx** out, const dmx_config* cfg) {
+  if (!out || !cfg || !cfg->alpha) return DMX_E_INVALID;
+  *out = nullptr;
+  // the reference indexes out of bounds for nv < 2 or n_alpha < 2
+  if (cfg->nv < 2 || cfg->nv > 4095 || cfg->n_alpha < 2 || cfg->n_alpha > DMX_MAX_ALPHA) return DMX_E_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg->device < 0 || cfg->device >= ndev) {
+    g_last_error = "no CUDA device";
+    return DMX_E_NODEVICE;
+  }
+  int major = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, cfg->device);
+  if (major != 10) {
+    g_last_error = "device is not compute capability 10.x";
+    return DMX_E_NODEVICE;
+  }
+  CU(cudaSetDevice(cfg->device));
+  dmx_ctx* c = new (std::nothrow) dmx_ctx();
+  if (!c) return DMX_E_NOMEM;
+  c->cfg = *cfg;
+  c->alpha.assign(cfg->alpha, cfg->alpha + cfg->n_alpha);
+  c->cfg.alpha = c->alpha.data();
+  memset(&c->st, 0, sizeof(c->st));
+  build_pgrid(c->alpha.data(), cfg->n_alpha, &c->pg);
+  c->UQ = (c->pg.U + 3 + 1) & ~1;
+  c->nvp = (cfg->nv + TILE - 1) / TILE * TILE;
+  build_tasks(c);
+  for (int i = 0; i <= 255; ++i) c->err256[i] = (i > 1) ? pow(0.1, i * 0.1) : 0.75;   // PhredHelper.cpp:30
+  cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
+  if (e == cudaSuccess) e = (cudaError_t)set_err_table(c->err256);
+  if (e == cudaSuccess) e = (cudaError_t)pair_scan_init();
+  if (e == cudaSuccess) e = c->d_tt.reserve(c->tt.size());
+  if (e == cudaSuccess)
+    e = cudaMemcpy(c->d_tt.p, c->tt.data(), c->tt.size() * sizeof(TaskType), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    dmx_destroy(c);
+    return fail_cuda(e, "dmx_create");
+  }
+  *out = c;
+  return DMX_OK;
+}
+
+void dmx_destroy(dmx_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->cfg.device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  c->d_gp.release(); c->d_gp0.release(); c->d_entq.release(); c->d_row0.release(); c->d_singA.release();
+  c->d_lb.release(); c->d_p1.release(); c->d_p1_0.release(); c->d_l00.release(); c->d_sing.release();
+  c->d_dense.release(); c->d_cell_ptr.release(); c->d_ent_ptr.release(); c->d_ent_snp.release();
+  c->d_order.release(); c->d_reads.release(); c->d_tt.release(); c->d_parts.release(); c->d_out.release();
+  c->o_gp.release(); c->o_cell_ptr.release(); c->o_ent_ptr.release(); c->o_ent_snp.release(); c->o_reads.release();
+  c->r_out.release(); c->r_sing.release(); c->r_row0.release(); c->r_l00.release(); c->r_p1.release();
+  c->r_p1_0.release(); c->r_dense.release();
+  for (int i = 0; i < 6; ++i)
+    if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int dmx_set_gp(dmx_ctx* c, const float* gp, int64_t nsnps) {
+  if (!c || !gp || nsnps < 0) return DMX_E_INVALID;
+  CU(cudaSetDevice(c->cfg.device));
+  c->nsnps = nsnps;
+  const size_t n = (size_t)nsnps * c->cfg.nv * 3;
+  if (c->cfg.flags & DMX_BORROW_INPUTS) {
+    c->h_gp = gp;
+  } else {
+    CU(c->o_gp.reserve(n));
+    memcpy(c->o_gp.p, gp, n * sizeof(float));
+    c->h_gp = c->o_gp.p;
+  }
+  c->have_gp = true;
+  c->gp_dirty = true;
+  c->uploaded = false;
+  c->computed = false;
+  return DMX_OK;
+}
+
+int dmx_set_pileup(dmx_ctx* c, int64_t ncells, const int64_t* cell_ptr, const int32_t* ent_snp,
+                   const int64_t* ent_ptr, const uint16_t* reads, const int32_t* totl, const int32_t* pass,
+                   const int32_t* uniq) {
+  if (!c || ncells < 0 || !cell_ptr || !ent_ptr || !totl || !pass || !uniq) return DMX_E_INVALID;
+  if (ncells > 0x7fffffffLL) return DMX_E_UNSUPPORTED;
+  if (cell_ptr[0] != 0) return DMX_E_INVALID;
+  const int64_t E = cell_ptr[ncells];
+  if (E < 0 || (E > 0 && (!ent_snp))) return DMX_E_INVALID;
+  if (ent_ptr[0] != 0) return DMX_E_INVALID;
+  const int64_t R = ent_ptr[E];
+  if (R < 0 || (R > 0 && !reads)) return DMX_E_INVALID;
+  for (int64_t i = 0; i < ncells; ++i)
+    if (cell_ptr[i + 1] < cell_ptr[i]) return DMX_E_INVALID;
+  CU(cudaSetDevice(c->cfg.device));
+  c->ncells = ncells; c->E = E; c->R = R;
+  if (c->cfg.flags & DMX_BORROW_INPUTS) {
+    c->h_cell_ptr = cell_ptr; c->h_ent_snp = ent_snp; c->h_ent_ptr = ent_ptr; c->h_reads = reads;
+  } else {
+    CU(c->o_cell_ptr.reserve(ncells + 1)); CU(c->o_ent_snp.reserve(E)); CU(c->o_ent_ptr.reserve(E + 1));
+    CU(c->o_reads.reserve(R));
+    memcpy(c->o_cell_ptr.p, cell_ptr, (ncells + 1) * sizeof(int64_t));
+    if (E) memcpy(c->o_ent_snp.p, ent_snp, E * sizeof(int32_t));
+    memcpy(c->o_ent_ptr.p, ent_ptr, (E + 1) * sizeof(int64_t));
+    if (R) memcpy(c->o_reads.p, reads, R * sizeof(uint16_t));
+    c->h_cell_ptr = c->o_cell_ptr.p; c->h_ent_snp = c->o_ent_snp.p; c->h_ent_ptr = c->o_ent_ptr.p;
+    c->h_reads = c->o_reads.p;
+  }
+  c->totl.assign(totl, totl + ncells);
+  c->npass.assign(pass, pass + ncells);
+  c->uniq.assign(uniq, uniq + ncells);
+  // schedule: drop filtered (:581) and empty (:592) cells, largest cells first
+  c->status.assign(ncells, 0);
+  c->order.clear();
+  for (int64_t i = 0; i < ncells; ++i) {
+    const int64_t ns = cell_ptr[i + 1] - cell_ptr[i];
+    if (totl[i] < c->cfg.min_total || uniq[i] < c->cfg.min_uniq || ns < c->cfg.min_snp) c->status[i] = 1;
+    else if (ns == 0) c->status[i] = 2;
+    else c->order.push_back((int32_t)i);
+  }
+  std::stable_sort(c->order.begin(), c->order.end(), [&](int32_t a, int32_t b) {
+    return (cell_ptr[a + 1] - cell_ptr[a]) > (cell_ptr[b + 1] - cell_ptr[b]);
+  });
+  c->have_plp = true;
+  c->plp_dirty = true;
+  c->uploaded = false;
+  c->computed = false;
+  return DMX_OK;
+}
+
+int dmx_upload(dmx_ctx* c) {
+  if (!c) return DMX_E_INVALID;
+  if (!c->have_gp || !c->have_plp) return DMX_E_STATE;
+  CU(cudaSetDevice(c->cfg.device));
+  const double t0 = now_ms();
+  const int nv = c->cfg.nv, nvp = c->nvp;
+  int64_t bytes = 0;
+  if (c->E > 0 && !(c->cfg.flags & DMX_TRUST_INPUTS)) {
+    // SNP ids must index the GP matrix
+    // (checked lazily here rather than in dmx_set_pileup so either setter can come first)
+    int32_t mx = -1, mn = 0;
+    for (int64_t e = 0; e < c->E; ++e) {
+      mx = std::max(mx, c->h_ent_snp[e]);
+      mn = std::min(mn, c->h_ent_snp[e]);
+    }
+    if (mn < 0 || mx >= c->nsnps) return DMX_E_INVALID;
+  }
+  if (c->gp_dirty) {
+    CU(c->d_gp.reserve((size_t)c->nsnps * nvp * 3 + 4));
+    CU(c->d_gp0.reserve((size_t)c->nsnps * 4 + 4));
+    if (nvp == nv) {
+      CU(cudaMemcpyAsync(c->d_gp.p, c->h_gp, (size_t)c->nsnps * nv * 3 * sizeof(float), cudaMemcpyHostToDevice,
+                         c->stream));
+    } else {
+      CU(cudaMemsetAsync(c->d_gp.p, 0, (size_t)c->nsnps * nvp * 3 * sizeof(float), c->stream));
+      CU(cudaMemcpy2DAsync(c->d_gp.p, (size_t)nvp * 12, c->h_gp, (size_t)nv * 12, (size_t)nv * 12,
+                           (size_t)c->nsnps, cudaMemcpyHostToDevice, c->stream));
+    }
+    bytes += c->nsnps * nv * 3 * (int64_t)sizeof(float);
+    c->gp_dirty = false;
+  }
+  if (c->plp_dirty) {
+    CU(c->d_cell_ptr.reserve(c->ncells + 1)); CU(c->d_ent_snp.reserve(c->E + 1)); CU(c->d_ent_ptr.reserve(c->E + 1));
+    CU(c->d_reads.reserve(c->R + 1)); CU(c->d_order.reserve(c->order.size() + 1));
+    CU(cudaMemcpyAsync(c->d_cell_ptr.p, c->h_cell_ptr, (c->ncells + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    if (c->E) CU(cudaMemcpyAsync(c->d_ent_snp.p, c->h_ent_snp, c->E * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_ent_ptr.p, c->h_ent_ptr, (c->E + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    if (c->R) CU(cudaMemcpyAsync(c->d_reads.p, c->h_reads, c->R * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+    if (!c->order.empty())
+      CU(cudaMemcpyAsync(c->d_order.p, c->order.data(), c->order.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    bytes += (c->ncells + 1) * 8 + c->E * 4 + (c->E + 1) * 8 + c->R * 2 + (int64_t)c->order.size() * 4;
+    c->plp_dirty = false;
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  c->st.h2d_ms = now_ms() - t0;
+  c->st.h2d_bytes = bytes;
+  c->uploaded = true;
+  c->computed = false;
+  return DMX_OK;
+}
+
+int dmx_compute(dmx_ctx* c) {
+  if (!c) return DMX_E_INVALID;
+  if (!c->uploaded) return DMX_E_STATE;
+  CU(cudaSetDevice(c->cfg.device));
+  const double t0 = now_ms();
+  const int nv = c->cfg.nv, nA = c->cfg.n_alpha;
+  const int64_t nc = c->ncells, nact = (int64_t)c->order.size();
+  const int T = (int)c->tt.size();
+  c->st.gpu_launches = 0;
+  c->st.n_rescored = 0;
+  c->st.n_fullcell = 0;
+
+  CU(c->d_entq.reserve((size_t)c->E * c->UQ + 2));
+  CU(c->d_parts.reserve((size_t)nact * T + 1));
+  CU(c->d_row0.reserve((size_t)nc * nA * nv + 1)); CU(c->d_singA.reserve((size_t)nc * nv + 1));
+  CU(c->d_lb.reserve((size_t)nc * nv + 1)); CU(c->d_p1.reserve((size_t)nc * nv + 1));
+  CU(c->d_p1_0.reserve(nc + 1)); CU(c->d_l00.reserve((size_t)nc * nA + 1));
+  CU(c->d_sing.reserve((size_t)nc * nv + 1)); CU(c->d_out.reserve(nc + 1));
+  CU(c->r_out.reserve(nc + 1)); CU(c->r_sing.reserve((size_t)nc * nv + 1));
+  CU(c->r_row0.reserve((size_t)nc * nA * nv + 1)); CU(c->r_l00.reserve((size_t)nc * nA + 1));
+  CU(c->r_p1.reserve((size_t)nc * nv + 1)); CU(c->r_p1_0.reserve(nc + 1));
+
+  CU(cudaEventRecord(c->ev[0], c->stream));
+  // outputs of cells that are never scheduled stay zero (the reference prints zeros for them in .single)
+  CU(cudaMemsetAsync(c->d_p1.p, 0, (size_t)nc * nv * sizeof(double), c->stream));
+  CU(cudaMemsetAsync(c->d_p1_0.p, 0, (size_t)nc * sizeof(double), c->stream));
+  CU(cudaMemsetAsync(c->d_sing.p, 0, (size_t)nc * nv * sizeof(double), c->stream));
+  CU(cudaMemsetAsync(c->d_l00.p, 0, (size_t)nc * nA * sizeof(double), c->stream));
+  CU(cudaMemsetAsync(c->d_row0.p, 0, (size_t)nc * nA * nv * sizeof(double), c->stream));
+  CU(cudaMemsetAsync(c->d_out.p, 0, (size_t)nc * sizeof(CellOut), c->stream));
+  CU(launch_gp0(c->d_gp.p, c->d_gp0.p, c->nsnps, nv, c->nvp, c->stream));
+  EntqParams eq;
+  eq.U = c->pg.U; eq.UQ = c->UQ; eq.E = c->E; eq.ent_ptr = c->d_ent_ptr.p; eq.reads = c->d_reads.p;
+  eq.entq = c->d_entq.p;
+  memcpy(eq.pu, c->pg.pu, sizeof(double) * c->pg.U);
+  CU(launch_entq(eq, c->stream));
+  CU(cudaEventRecord(c->ev[1], c->stream));
+  ScanParams sp;
+  fill_scan_params(c, &sp);
+  CU(launch_pair_scan(sp, nact, (c->cfg.flags & DMX_FP32_PAIRS) != 0, c->stream));
+  CU(cudaEventRecord(c->ev[2], c->stream));
+  MergeParams mp;
+  memset(&mp, 0, sizeof(mp));
+  mp.nv = nv; mp.nA = nA; mp.T = T; mp.sep0 = c->pg.sep0; mp.eps_rel = sp.eps_rel;
+  mp.w_single = (1. - c->cfg.doublet_prior) / nv;
+  for (int n = 0; n < nA; ++n)
+    mp.w_double[n] = c->cfg.doublet_prior / nv / (nv - 1) / (nA - 1) / (c->alpha[n] == 0.5 ? 2.0 : 1.0);
+  mp.cell_order = c->d_order.p; mp.tt = c->d_tt.p; mp.parts = c->d_parts.p; mp.row0 = c->d_row0.p;
+  mp.singA = c->d_singA.p; mp.lb = c->d_lb.p; mp.sing = c->d_sing.p; mp.out = c->d_out.p;
+  CU(launch_merge(mp, nact, c->stream));
+  c->st.gpu_launches += (c->nsnps ? 1 : 0) + (c->E ? 1 : 0) + (nact ? 2 : 0);
+  CU(cudaEventRecord(c->ev[3], c->stream));
+  CU(cudaMemcpyAsync(c->r_out.p, c->d_out.p, nc * sizeof(CellOut), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(c->r_sing.p, c->d_sing.p, (size_t)nc * nv * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(c->r_row0.p, c->d_row0.p, (size_t)nc * nA * nv * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(c->r_l00.p, c->d_l00.p, (size_t)nc * nA * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (sp.want_single) {
+    CU(cudaMemcpyAsync(c->r_p1.p, c->d_p1.p, (size_t)nc * nv * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->r_p1_0.p, c->d_p1_0.p, (size_t)nc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU(cudaEventRecord(c->ev[4], c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->st.d2h_bytes = nc * (int64_t)sizeof(CellOut) + (int64_t)nc * nv * 8 * (1 + nA + (sp.want_single ? 1 : 0)) +
+                    nc * nA * 8 + (sp.want_single ? nc * 8 : 0);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->st.prep_ms = ms;
+  cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->st.pair_kernel_ms = ms;
+  cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]); c->st.kernel_ms = ms;
+  cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); c->st.d2h_ms = ms;
+
+  // ---- finalise -----------------------------------------------------------------------------------
+  const double tf0 = now_ms();
+  c->best.assign(nc, dmx_best_rec());
+  const HostView hv = host_view(c);
+  const ExactScorer scorer(hv, c->err256);
+  const bool exact = (c->cfg.flags & DMX_EXACT_TIES) != 0;
+  const int nth = host_threads(c);
+  std::vector<std::vector<int32_t>> overflow(nth);
+  std::vector<int64_t> resc(nth, 0);
+  auto do_cell = [&](int64_t cell, const std::vector<Hyp>& cands, int tid) {
+    dmx_best_rec* r = &c->best[cell];
+    CellGpu g;
+    g.co = &c->r_out.p[cell];
+    g.sing = c->r_sing.p + (size_t)cell * nv;
+    g.row0 = c->r_row0.p + (size_t)cell * nA * nv;
+    g.l00 = c->r_l00.p + (size_t)cell * nA;
+    finalise_cell(hv, scorer, cell, g, cands, c->cfg.doublet_prior, sp.eps_rel, exact, r);
+    resc[tid] += r->n_rescored;
+  };
+  parallel_for(nc, nth, [&](int64_t cell, int tid) {
+    dmx_best_rec* r = &c->best[cell];
+    memset(r, 0, sizeof(*r));
+    r->status = c->status[cell];
+    r->n_snp = (int32_t)(c->h_cell_ptr[cell + 1] - c->h_cell_ptr[cell]);
+    if (r->status != 0) return;
+    const CellOut& co = c->r_out.p[cell];
+    if (co.ncand > MAX_CAND) { overflow[tid].push_back((int32_t)cell); return; }
+    std::vector<Hyp> cands;
+    expand_cands(c, co, &cands);
+    do_cell(cell, cands, tid);
+  });
+  std::vector<int32_t> ov;
+  for (auto& v : overflow) ov.insert(ov.end(), v.begin(), v.end());
+  if (!ov.empty()) {
+    // candidate list overflow (massive exact ties, e.g. GT-field genotypes on a handful of SNPs): take the
+    // candidates from a dense llksAB scan of just those cells
+    const size_t per = (size_t)nv * nv * nA;
+    const size_t batch = std::max<size_t>(1, ((size_t)256 << 20) / (per * sizeof(double)));
+    CU(c->r_dense.reserve(std::min(batch, ov.size()) * per));
+    for (size_t lo = 0; lo < ov.size(); lo += batch) {
+      const size_t n = std::min(batch, ov.size() - lo);
+      std::vector<int32_t> cells(ov.begin() + lo, ov.begin() + lo + n);
+      int rc = dense_scan(c, cells, c->r_dense.p);
+      if (rc != DMX_OK) return rc;
+      parallel_for((int64_t)n, nth, [&](int64_t i, int tid) {
+        std::vector<Hyp> cands;
+        candidates_from_dense(c->r_dense.p + (size_t)i * per, nv, nA, 1, sp.eps_rel, &cands);
+        do_cell(cells[i], cands, tid);
+        c->best[cells[i]].exact_mask |= DMX_X_FULLCELL;
+      });
+    }
+    c->st.n_fullcell = (int64_t)ov.size();
+  }
+  for (int t = 0; t < nth; ++t) c->st.n_rescored += resc[t];
+  c->st.finalise_ms = now_ms() - tf0;
+  c->st.n_entries = c->E;
+  c->st.n_reads = c->R;
+  c->st.n_tasks = nact * T;
+  // SURVEY 8(d) gather model: per entry 12*nv (GP row) + 12 (gp0 row) + 4 (snp id) + 2*reads
+  c->st.algo_bytes = 0;
+  for (int64_t i = 0; i < nact; ++i) {
+    const int32_t cell = c->order[i];
+    const int64_t e0 = c->h_cell_ptr[cell], e1 = c->h_cell_ptr[cell + 1];
+    c->st.algo_bytes += (double)(e1 - e0) * (12.0 * nv + 16.0) + 2.0 * (double)(c->h_ent_ptr[e1] - c->h_ent_ptr[e0]) +
+                        8.0 + 200.0 + 8.0 * nv;
+  }
+  c->st.total_ms = now_ms() - t0;
+  c->computed = true;
+  return DMX_OK;
+}
+
+int dmx_run(dmx_ctx* c) {
+  if (!c) return DMX_E_INVALID;
+  int rc = dmx_upload(c);
+  if (rc != DMX_OK) return rc;
+  const double up = c->st.h2d_ms;
+  rc = dmx_compute(c);
+  if (rc == DMX_OK) c->st.total_ms += up;
+  return rc;
+}
+
+int dmx_get_best(dmx_ctx* c, dmx_best_rec* out) {
+  if (!c || !out) return DMX_E_INVALID;
+  if (!c->computed) return DMX_E_STATE;
+  if (c->ncells) memcpy(out, c->best.data(), c->ncells * sizeof(dmx_best_rec));
+  return DMX_OK;
+}
+
+int dmx_get_single(dmx_ctx* c, double* llk, double* llk0) {
+  if (!c || !llk || !llk0) return DMX_E_INVALID;
+  if (!c->computed) return DMX_E_STATE;
+  if (c->cfg.flags & DMX_SKIP_SINGLE) return DMX_E_STATE;
+  memcpy(llk, c->r_p1.p, (size_t)c->ncells * c->cfg.nv * sizeof(double));
+  memcpy(llk0, c->r_p1_0.p, (size_t)c->ncells * sizeof(double));
+  return DMX_OK;
+}
+
+int dmx_get_sing2(dmx_ctx* c, double* llk_j00, double* llk00) {
+  if (!c || !llk_j00 || !llk00) return DMX_E_INVALID;
+  if (!c->computed) return DMX_E_STATE;
+  memcpy(llk_j00, c->r_sing.p, (size_t)c->ncells * c->cfg.nv * sizeof(double));
+  memcpy(llk00, c->r_l00.p, (size_t)c->ncells * c->cfg.n_alpha * sizeof(double));
+  return DMX_OK;
+}
+
+int dmx_get_pair(dmx_ctx* c, int64_t cell_lo, int64_t cell_hi, double* llkAB) {
+  if (!c || !llkAB || cell_lo < 0 || cell_hi > c->ncells || cell_lo > cell_hi) return DMX_E_INVALID;
+  if (!c->computed) return DMX_E_STATE;
+  CU(cudaSetDevice(c->cfg.device));
+  const size_t per = (size_t)c->cfg.nv * c->cfg.nv * c->cfg.n_alpha;
+  std::vector<int32_t> cells;
+  for (int64_t i = cell_lo; i < cell_hi; ++i)
+    if (c->status[i] == 0) cells.push_back((int32_t)i);
+  memset(llkAB, 0, (size_t)(cell_hi - cell_lo) * per * sizeof(double));
+  if (cells.empty()) return DMX_OK;
+  std::vector<double> tmp(cells.size() * per);
+  int rc = dense_scan(c, cells, tmp.data());
+  if (rc != DMX_OK) return rc;
+  for (size_t i = 0; i < cells.size(); ++i)
+    memcpy(llkAB + (size_t)(cells[i] - cell_lo) * per, tmp.data() + i * per, per * sizeof(double));
+  return DMX_OK;
+}
+
+int dmx_rescore(dmx_ctx* c, int64_t cell, int32_t j, int32_t k, int32_t n, double* out) {
+  if (!c || !out || !c->have_gp || !c->have_plp) return DMX_E_STATE;
+  if (cell < 0 || cell >= c->ncells || j < 0 || j >= c->cfg.nv || k < 0 || k >= c->cfg.nv || n < 0 ||
+      n >= c->cfg.n_alpha)
+    return DMX_E_INVALID;
+  const HostView hv = host_view(c);
+  const ExactScorer scorer(hv, c->err256);
+  Hyp h{j, k, n};
+  scorer.eval(cell, &h, 1, out);
+  return DMX_OK;
+}
+
+int dmx_get_stats(dmx_ctx* c, dmx_stats* out) {
+  if (!c || !out) return DMX_E_INVALID;
+  *out = c->st;
+  return DMX_OK;
+}
+
+// ---- writers ---------------------------------------------------------------------------------------
+int dmx_write_outputs(dmx_ctx* c, const char* const* barcodes, const char* const* samples, const char* prefix,
+                      int write_pair) {
+  if (!c || !barcodes || !samples || !prefix) return DMX_E_INVALID;
+  if (!c->computed) return DMX_E_STATE;
+  const int nv = c->cfg.nv, nA = c->cfg.n_alpha;
+  const double dp = c->cfg.doublet_prior;
+  const int64_t nc = c->ncells;
+  // std::map<std::string,int32_t> iteration order (:472, :576)
+  std::vector<int32_t> ord(nc);
+  for (int64_t i = 0; i < nc; ++i) ord[i] = (int32_t)i;
+  std::sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) { return std::string(barcodes[a]) < std::string(barcodes[b]); });
+  const std::string pre(prefix);
+  FILE* ws = nullptr;
+  if (!(c->cfg.flags & DMX_SKIP_SINGLE)) {
+    ws = fopen((pre + ".single").c_str(), "w");
+    if (!ws) return DMX_E_IO;                                           // :409
+    fprintf(ws, "BARCODE\tSM_ID\tRD.TOTL\tRD.PASS\tRD.UNIQ\tN.SNP\tLLK1\tLLK0\tPOSTPRB\n");   // :470
+    for (int64_t oi = 0; oi < nc; ++oi) {
+      const int32_t i = ord[oi];
+      if (c->status[i] == 1) continue;                                  // :480
+      const double* llks = c->r_p1.p + (size_t)i * nv;
+      double sumLLK = -1e300;                                           // :478-489
+      for (int j = 0; j < nv; ++j) {
+        const double cur = llks[j];
+        if (sumLLK > cur) sumLLK = sumLLK + log(1.0 + exp(cur - sumLLK));
+        else sumLLK = cur + log(1.0 + exp(sumLLK - cur));
+      }
+      const int nsnp = (int)(c->h_cell_ptr[i + 1] - c->h_cell_ptr[i]);
+      for (int j = 0; j < nv; ++j)                                      // :506
+        fprintf(ws, "%s\t%s\t%d\t%d\t%d\t%d\t%.5lf\t%.5lf\t%.3lg\n", barcodes[i], samples[j], c->totl[i],
+                c->npass[i], c->uniq[i], nsnp, llks[j], c->r_p1_0.p[i], exp(llks[j] - sumLLK));
+    }
+    fclose(ws);
+  }
+  FILE* w2 = fopen((pre + ".sing2").c_str(), "w");
+  FILE* wb = fopen((pre + ".best").c_str(), "w");
+  FILE* wp = write_pair ? fopen((pre + ".pair").c_str(), "w") : nullptr;
+  if (!w2 || !wb || (write_pair && !wp)) {                              // :535
+    if (w2) fclose(w2);
+    if (wb) fclose(wb);
+    if (wp) fclose(wp);
+    return DMX_E_IO;
+  }
+  fprintf(w2, "BARCODE\tSM_ID\tRD.TOTL\tRD.PASS\tRD.UNIQ\tN.SNP\tLLK1\tLLK0\tPOSTPRB\n");     // :533
+  if (wp) fprintf(wp, "BARCODE\tSM1.ID\tSM2.ID\tLLK12\tPOSTPRB\n");                           // :570
+  fprintf(wb,
+          "BARCODE\tRD.TOTL\tRD.PASS\tRD.UNIQ\tN.SNP\tBEST\tSNG.1ST\tSNG.LLK1\tSNG.2ND\tSNG.LLK2\tSNG.LLK0\tDBL.1ST\t"
+          "DBL.2ND\tALPHA\tLLK12\tLLK1\tLLK2\tLLK10\tLLK20\tLLK00\tPRB.DBL\tPRB.SNG1\n");      // :571
+  const size_t per = (size_t)nv * nv * nA;
+  std::vector<double> dense;
+  const int64_t pair_batch = std::max<int64_t>(1, ((int64_t)64 << 20) / (int64_t)(per * sizeof(double)));
+  int64_t dense_lo = 0, dense_hi = 0;   // positions in `ord` covered by `dense`
+  int rc = DMX_OK;
+  for (int64_t oi = 0; oi < nc && rc == DMX_OK; ++oi) {
+    const int32_t i = ord[oi];
+    if (c->status[i] != 0) continue;                                    // :581, :592
+    const dmx_best_rec& b = c->best[i];
+    const double* sing = c->r_sing.p + (size_t)i * nv;
+    const double l00_0 = c->r_l00.p[(size_t)i * nA];
+    // exact values where the finaliser produced them
+    auto sv = [&](int j) {
+      if (j == b.sng1) return b.sng_llk1;
+      if (j == b.sng2) return b.sng_llk2;
+      if (j == b.dbl1) return b.llk1;
+      if (j == b.dbl2) return b.llk2;
+      return sing[j];
+    };
+    for (int j = 0; j < nv; ++j)                                        // :760-769
+      fprintf(w2, "%s\t%s\t%d\t%d\t%d\t%d\t%.4lf\t%.4lf\t%.3lg\n", barcodes[i], samples[j], c->totl[i], c->npass[i],
+              c->uniq[i], b.n_snp, sv(j), l00_0, exp(sv(j) - b.max_llk) * (1. - dp) / nv / b.sum_single);
+    if (wp) {                                                           // :772-797
+      if (oi >= dense_hi) {
+        // next batch of cells in output order
+        std::vector<int32_t> cells;
+        dense_lo = oi;
+        int64_t o2 = oi;
+        for (; o2 < nc && (int64_t)cells.size() < pair_batch; ++o2)
+          if (c->status[ord[o2]] == 0) cells.push_back(ord[o2]);
+        dense_hi = o2;
+        dense.resize(cells.size() * per);
+        rc = dense_scan(c, cells, dense.data());
+        if (rc != DMX_OK) break;
+      }
+      size_t pos = 0;
+      for (int64_t o2 = dense_lo; o2 < oi; ++o2)
+        if (c->status[ord[o2]] == 0) ++pos;
+      const double* AB = dense.data() + pos * per;
+      for (int j = 0; j < nv; ++j) {
+        fprintf(wp, "%s\t%s\t%s\t%.3lf\t%.5lf\t%.5lg\n", barcodes[i], samples[j], samples[j], c->alpha[0], sv(j),
+                exp(sv(j) - b.max_llk) * (1. - dp) / nv / (b.sum_single + b.sum_double));
+        for (int k = 0; k < nv; ++k)
+          for (int n = 0; n < nA; ++n)
+            if (n > 0 && j != k) {
+              if (j > k && c->alpha[n] == 0.5) continue;                // :785
+              double v = AB[((size_t)j * nv + k) * nA + n];
+              if (j == b.dbl1 && k == b.dbl2 && n == b.alpha_idx) v = b.llk12;
+              fprintf(wp, "%s\t%s\t%s\t%.3lf\t%.5lf\t%.5lg\n", barcodes[i], samples[j], samples[k], c->alpha[n], v,
+                      exp(v - b.max_llk) * dp / nv / (nv - 1) / (nA - 1) / (b.sum_single + b.sum_double));
+            }
+      }
+    }
+    fprintf(wb, "%s\t%d\t%d\t%d\t%d\t", barcodes[i], c->totl[i], c->npass[i], c->uniq[i], b.n_snp);   // :830
+    if (b.call == 0)
+      fprintf(wb, "DBL-%s-%s-%.3lf", samples[b.dbl1], samples[b.dbl2], c->alpha[b.alpha_idx]);       // :838
+    else if (b.call == 1)
+      fprintf(wb, "SNG-%s", samples[b.sng1]);                                                          // :845
+    else
+      fprintf(wb, "AMB-%s-%s-%s/%s", samples[b.sng1], samples[b.sng2], samples[b.dbl1], samples[b.dbl2]);   // :851
+    fprintf(wb, "\t%s\t%.4lf", samples[b.sng1], b.sng_llk1);
+    fprintf(wb, "\t%s\t%.4lf\t%.4lf", samples[b.sng2], b.sng_llk2, b.sng_llk0);
+    fprintf(wb, "\t%s\t%s\t%.3lf\t%.4lf\t%.4lf\t%.4lf\t%.4lf\t%.4lf\t%.4lf\t%.3lg\t%.3lg\n", samples[b.dbl1],
+            samples[b.dbl2], c->alpha[b.alpha_idx], b.llk12, b.llk1, b.llk2, b.llk10, b.llk20, b.llk00, b.prb_dbl,
+            b.prb_sng1);
+  }
+  fclose(w2);
+  fclose(wb);
+  if (wp) fclose(wp);
+  return rc;
+}
+
+}  // extern "C"

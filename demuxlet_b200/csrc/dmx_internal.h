@@ -8,46 +8,51 @@ namespace dmx {
 
 // ---- geometry of the pair scan ---------------------------------------------------------------
 constexpr int TILE = 4;        // each consumer lane owns a TILE x TILE block of (j,k) hypotheses
-constexpr int BLK = 64;        // samples per block side (16 tiles); nv > 64 is tiled over blocks
+constexpr int BLK = 64;        // samples per task side (16 tiles); nv > 64 is tiled over tasks
+constexpr int BLK_RECT_K = 32; // k-side samples of a rectangular task (16 x 8 tiles = 128 lanes)
 constexpr int NB = 8;          // pileup entries per pipeline stage
-constexpr int S_PROC = 3;      // stages of the processed (a, w) ring: producers -> consumers
-constexpr int S_RAW = 4;       // stages of the raw ring: TMA bulk copies -> producers
-constexpr int NPW = 2;         // producer warps (read likelihood + per-sample projections)
+constexpr int S_RAW = 4;       // stages of the raw ring: bulk (TMA) copies -> transform warps
+constexpr int S_PROC = 2;      // stages of the processed (a, w) ring: transform -> consumer warps
+constexpr int NCW = 5;         // consumer warps (136 tiles of the 64 x 64 upper triangle -> 160 lanes)
+constexpr int NTW = 2;         // transform warps (one lane per sample of each side)
+constexpr int NTHREADS = (NCW + NTW + 1) * 32;   // + 1 loader warp
+constexpr int GRP_DBL = 14;    // doubles per 4-sample group in the processed ring (12 + 2 pad: 112 B
+                               // stride spreads 16-byte lane loads over all banks)
+constexpr int GRP_F32 = 12;    // floats per 4-sample group in the fp32 processed ring (48 B stride)
+constexpr int FLUSH_STAGES = 2;   // exponent renormalisation period (stages)
 constexpr int MAX_CAND = 8;    // near-tie candidates kept per task / per cell
-constexpr int MAX_U = DMX_MAX_ALPHA * 9;   // distinct mixing proportions p(n,l,m)
+constexpr int MAX_U = DMX_MAX_ALPHA * 6 + 3;   // distinct mixing proportions p(n,l,m)
 
-// ---- device layout of one (cell, snp) pileup entry: 16 bytes ------------------------------------
-// Built on device by pack_entries_kernel from the CSR arrays of dmx_set_pileup.  Reads with
-// allele == 2 carry no likelihood (cmd_cram_demuxlet.cpp:435,:604) and are dropped here; entries
-// with more than 3 informative reads keep a pointer into the raw reads array instead.
-struct PackedEnt {
-  int32_t snp;
-  uint16_t nreads;     // informative reads stored inline in r[] (0..3), or 0xFFFF = external
-  uint16_t r[3];       // allele<<8 | bq      (external: r[0] | r[1]<<16 = raw read count)
-  uint32_t roff;       // external: offset of the entry's first raw read
+// plane modes
+enum : uint8_t {
+  PM_SEP = 0,   // alpha == 0 at index 0: S[j][k] = A_j * B_k, no pair work
+  PM_SYM = 1,   // alpha == 0.5: S[j][k] == S[k][j], only j <= k is computed
+  PM_FULL = 2,  // everything else: all nv x nv ordered pairs
 };
-static_assert(sizeof(PackedEnt) == 16, "PackedEnt must be 16 bytes");
 
 // ---- work decomposition -------------------------------------------------------------------------
-// One CTA per task = (cell, alpha index n, sample block jb x kb).
+// One CTA per task = (cell, task type); a task type = (alpha index n, sample block j0.. x k0..).
 enum : uint32_t {
-  TF_SYM = 1u,       // alpha_n == 0.5: S[j][k] == S[k][j], only tiles with tj <= tk on diagonal blocks
-  TF_DIAG = 2u,      // jb == kb
-  TF_EXTRAS = 4u,    // also accumulate, for the samples of this block: singlet product of the
-                     // separable n = 0 plane and the pass-1 likelihood (cmd_cram_demuxlet.cpp:455-458)
-  TF_SCALARS = 8u,   // also llk0s (:459), llks00[0] when n = 0 is separable, and the k = 0 row-sum factor
-  TF_L00 = 16u,      // also llks00[n] for this task's n (:700-709)
-  TF_N0 = 32u,       // n == 0 handled densely (alpha[0] != 0): excluded from argmax / sumDouble
+  TF_TRI = 1u,       // 64 x 64 diagonal block of a PM_SYM plane: tiles with tj <= tk only
+  TF_SYM = 2u,       // plane is PM_SYM (unordered pairs count twice in sumDouble)
+  TF_EXTRAS = 4u,    // transform lanes also accumulate, for the k-side samples of this task: the singlet
+                     // factor of the separable n = 0 plane, the row sum factor, and the pass-1
+                     // likelihood (cmd_cram_demuxlet.cpp:455-458)
+  TF_SCALARS = 8u,   // also llk0s (:459) and llks00[0] of a separable plane 0
+  TF_L00 = 16u,      // also llks00[n] for this task's plane (:700-709)
+  TF_NOARG = 32u,    // plane is alpha index 0 handled densely (alpha[0] != 0): excluded from the
+                     // best-pair argmax and from sumDouble (:728,:805 start at n = 1)
 };
 
-struct Task {
-  int32_t cell;
-  int16_t n;           // alpha index
-  uint8_t jb, kb;      // block coordinates (units of BLK samples)
+struct TaskType {
+  int16_t n;           // alpha index of the plane
+  int16_t j0, k0;      // first sample of each side
+  int16_t nj, nk;      // samples on each side, padded to a multiple of TILE
+  int16_t pad;
   uint32_t flags;
-  int32_t part;        // index of this task's Part record
+  uint8_t qidx[12];    // index into the entry's q[] for Q'[n][l][m] (9 used)
 };
-static_assert(sizeof(Task) == 16, "Task must be 16 bytes");
+static_assert(sizeof(TaskType) == 28, "TaskType layout");
 
 // partial reduction of one task over its hypotheses
 struct Part {
@@ -56,55 +61,75 @@ struct Part {
   double best_v;       // max llk over j != k
   int32_t ncand;       // hypotheses within eps of best_v (may exceed MAX_CAND: overflow)
   int32_t pad;
-  uint32_t cand[MAX_CAND];   // j | k << 12 (global sample ids; unordered j < k for TF_SYM)
+  uint32_t cand[MAX_CAND];   // j | k << 12 (global sample ids; j < k stands for both orders if TF_SYM)
 };
 static_assert(sizeof(Part) == 64, "Part must be 64 bytes");
 
 // per-cell result of merge_kernel
 struct CellOut {
   double max_llk, sum_single, sum_double, best_v;
-  int32_t ncand;       // > MAX_CAND: overflow, the finaliser recomputes the cell exactly
-  int32_t status;      // 0 ok, 1 filtered, 2 empty
+  int32_t ncand;       // > MAX_CAND: overflow, the finaliser re-derives the candidates from a dense scan
+  int32_t pad;
   uint32_t cand[MAX_CAND];   // j | k << 12 | n << 24
 };
 static_assert(sizeof(CellOut) == 72, "CellOut must be 72 bytes");
 
-struct Params {
-  int32_t nv, nvp, nA, nu;
-  int32_t sep0;                // alpha[0] == 0: the n = 0 plane is separable (SURVEY Q3)
-  int32_t first_dense;         // first alpha index handled densely
-  double eps;                  // candidate window
-  double w_single;             // (1 - doublet_prior) / nv
-  double w_double[DMX_MAX_ALPHA];   // doublet_prior / nv / (nv-1) / (nA-1) / (alpha == 0.5 ? 2 : 1)
-  const float* gp;             // [nsnps][nvp*3], rows zero padded to a multiple of 16 bytes
-  const double* gp0;           // [nsnps][4]: cohort mean (x, y, z) and the row sum of sample 0
-  const PackedEnt* ent;
-  const uint16_t* reads;
-  const int64_t* cell_ptr;
-  const Task* tasks;
-  Part* parts;
-  double* row0;                // [ncells][nA][nv]  llksAB[j][0][n]
+struct ScanParams {
+  int32_t nv, nvp, nA, U, UQ;
+  int32_t sep0;                // alpha[0] == 0: the n = 0 plane is separable
+  int32_t T;                   // task types per cell
+  int32_t want_single;         // accumulate pass 1
+  int32_t fidx[3];             // q index of Q'[0][l][.] for the separable plane
+  double eps_rel;              // candidate window, relative to max(1, |best|)
+  const float* gp;             // [nsnps][nvp*3], rows zero padded
+  const double* gp0;           // [nsnps][4]: cohort mean (x, y, z), 0
+  const int32_t* ent_snp;      // [E]
+  const double* entq;          // [E][UQ]: U distinct Q' values, then the 3 pass-1 GLs
+  const int64_t* cell_ptr;     // [ncells+1]
+  const int32_t* cell_order;   // [nactive] cell ids, scheduled order
+  const TaskType* tt;          // [T]
+  Part* parts;                 // [nactive][T]
+  double* row0;                // [ncells][nA][nv]  llksAB[j][0][n] of dense planes
+  double* singA;               // [ncells][nv]      separable plane: sum log A_j
+  double* lb;                  // [ncells][nv]      separable plane: sum log B_k (row sums)
   double* p1;                  // [ncells][nv]      pass-1 llks
   double* p1_0;                // [ncells]          pass-1 llk0s
   double* l00;                 // [ncells][nA]      llks00
-  double* lb0;                 // [ncells]          sum log(row sum of sample 0) (n = 0 factor, Q3)
-  double* dense;               // optional [cells][nv][nv][nA]
-  int64_t dense_cell_lo;
-  double pu[MAX_U];            // distinct p values
-  uint8_t umap[DMX_MAX_ALPHA * 9];  // (n*9 + l*3 + m) -> index into pu
+  double* dense;               // optional [nactive][nv][nv][nA]
 };
 
-// host-callable launchers (dmx_kernels.cu)
-struct LaunchCfg { int ncw; bool fp32; };
+struct MergeParams {
+  int32_t nv, nA, T, sep0;
+  double eps_rel;
+  double w_single;             // (1 - doublet_prior) / nv
+  double w_double[DMX_MAX_ALPHA];   // doublet_prior / nv / (nv-1) / (nA-1) / (alpha == 0.5 ? 2 : 1)
+  const int32_t* cell_order;
+  const TaskType* tt;
+  const Part* parts;
+  const double* row0;
+  const double* singA;
+  const double* lb;
+  double* sing;                // [ncells][nv] out: llksAB[j][0][0]
+  CellOut* out;                // [ncells]
+};
+
+struct EntqParams {
+  int32_t U, UQ;
+  int64_t E;
+  const int64_t* ent_ptr;
+  const uint16_t* reads;
+  double* entq;
+  double pu[MAX_U];            // distinct p values (cmd_cram_demuxlet.cpp:613)
+};
+
+// host-callable launchers (dmx_kernels.cu); all return a cudaError_t as int
 int launch_gp0(const float* gp, double* gp0, int64_t nsnps, int nv, int nvp, void* stream);
-int launch_pack(const int32_t* ent_snp, const int64_t* ent_ptr, const uint16_t* reads, PackedEnt* out,
-                int64_t E, void* stream);
-int launch_pair_scan(const Params& p, int64_t task_lo, int64_t ntasks, int ncw, bool fp32, bool offdiag,
-                     void* stream);
-int launch_merge(const Params& p, const int64_t* cell_task_ptr, const int32_t* totl, const int32_t* uniq,
-                 int32_t min_total, int32_t min_uniq, int32_t min_snp, CellOut* out, int64_t ncells,
-                 void* stream);
+int launch_entq(const EntqParams& p, void* stream);
+int launch_pair_scan(const ScanParams& p, int64_t nactive, bool fp32, void* stream);
+int launch_merge(const MergeParams& p, int64_t nactive, void* stream);
+int launch_fill_sep_dense(const ScanParams& p, int64_t nactive, void* stream);
 int set_err_table(const double* err256);
-size_t pair_scan_smem_bytes(bool fp32, bool offdiag);
+int pair_scan_init();          // func attributes (max dynamic smem)
+size_t pair_scan_smem_bytes(const ScanParams& p, bool fp32);
 
 }  // namespace dmx

@@ -46,6 +46,8 @@ typedef enum {
 #define DMX_BORROW_INPUTS 0x2u  /* dmx_set_gp/dmx_set_pileup keep the caller's pointers (which must
                                    stay valid and unchanged until the ctx is destroyed or re-set)
                                    instead of copying; use with dmx_alloc_host for pinned transfers */
+#define DMX_SKIP_SINGLE   0x8u  /* do not compute pass 1 (.single, :412-461); dmx_get_single then fails   */
+#define DMX_TRUST_INPUTS  0x10u /* skip the host-side range check of ent_snp against nsnps in dmx_upload  */
 #define DMX_FP32_PAIRS    0x4u  /* pair scan accumulates in fp32 (faster, ~1e-6 LLK error) instead
                                    of fp64; singlet, pass-1 and all re-scored values stay fp64      */
 

@@ -1,0 +1,82 @@
+"""GPU parity: libdmx (through the C ABI) against the CPU oracle on the same seeded pileups."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.util import compare, diff_tsv, run_both
+
+pytestmark = pytest.mark.gpu
+
+BEST_EXACT = {"BARCODE", "RD.TOTL", "RD.PASS", "RD.UNIQ", "N.SNP", "BEST", "SNG.1ST", "SNG.2ND", "DBL.1ST",
+              "DBL.2ND", "ALPHA"}
+ROW_EXACT = {"BARCODE", "SM_ID", "SM1.ID", "SM2.ID", "RD.TOTL", "RD.PASS", "RD.UNIQ", "N.SNP"}
+
+
+def synth(*a, **k):
+    from demuxlet_b200.synth import make_synth
+    return make_synth(*a, **k)
+
+
+@pytest.mark.parametrize("ncells,nv,nsnps,field,alphas", [
+    (300, 8, 2000, "GP", (0.0, 0.5)),            # C2-like
+    (200, 64, 5000, "GP", (0.0, 0.5)),           # C3-like (headline shape, fewer cells)
+    (500, 2, 54000, "GT", (0.0, 0.5)),           # C1' (tutorial shape: 2 samples, GT field)
+    (150, 6, 3000, "GP", (0.0, 0.25, 0.5)),      # a non-symmetric plane
+    (150, 5, 3000, "GP", (0.1, 0.5)),            # alpha[0] != 0: "singlet" is pair (j, 0, alpha_0)
+    (60, 70, 4000, "GP", (0.0, 0.5)),            # nv > 64, not a multiple of 4: multi-block tasks
+    (40, 12, 3000, "PL", tuple(round(0.05 * i, 2) for i in range(11))),   # C5-like grid
+    (200, 16, 300, "GT", (0.0, 0.5)),            # GT field, low coverage: massive exact ties
+])
+def test_records_match_oracle(ncells, nv, nsnps, field, alphas):
+    p = synth(ncells, nv, nsnps, field, seed=11 + nv)
+    orc, ref, d = run_both(p, alphas)
+    worst = compare(ref, d)
+    st = d.stats()
+    assert st["gpu_launches"] >= 4
+    print("max LLK err %.3g rescored %d fullcell %d" % (worst, st["n_rescored"], st["n_fullcell"]))
+
+
+def test_filters_and_empty_cells():
+    p = synth(120, 8, 1500, "GP", seed=5)
+    # make a few cells empty
+    keep = np.ones(p.ncells, dtype=bool)
+    keep[[3, 50, 119]] = False
+    from demuxlet_b200.plp import Pileup
+    n_e = np.diff(p.cell_ptr)
+    n_e2 = np.where(keep, n_e, 0)
+    sub = p.subset_cells(np.nonzero(keep)[0])
+    cell_ptr = np.concatenate([[0], np.cumsum(n_e2)])
+    q = Pileup(p.gp, cell_ptr, sub.ent_snp, sub.ent_ptr, sub.reads, p.totl, p.npass, p.uniq, p.barcodes, p.samples)
+    orc, ref, d = run_both(q, min_total=int(np.median(q.totl)), min_uniq=5, min_snp=3)
+    compare(ref, d)
+    st = d.best()["status"]
+    assert (st == 1).any() and (st == 0).any()
+
+
+def test_output_files(tmp_path):
+    p = synth(80, 6, 2500, "GP", seed=3)
+    orc, ref, d = run_both(p)
+    orc.write_all(str(tmp_path / "orc"), write_pair=True)
+    d.write_outputs(str(tmp_path / "gpu"), write_pair=True)
+    diff_tsv(tmp_path / "orc.best", tmp_path / "gpu.best", BEST_EXACT)
+    for ext in ("single", "sing2", "pair"):
+        diff_tsv(tmp_path / ("orc." + ext), tmp_path / ("gpu." + ext), ROW_EXACT)
+
+
+def test_dense_pair_block_matches_oracle():
+    p = synth(30, 10, 2000, "GP", seed=9)
+    alphas = (0.0, 0.3, 0.5)
+    orc, ref, d = run_both(p, alphas)
+    AB = d.pair(0, p.ncells)
+    gp0 = orc.gp0()
+    for c in (0, 7, 29):
+        oAB, _, _ = orc.pass2_cell(c, gp0)
+        assert np.abs(AB[c] - oAB).max() < 1e-8
+
+
+def test_rescore_is_bit_exact():
+    p = synth(20, 6, 1500, "GP", seed=4)
+    orc, ref, d = run_both(p)
+    for (c, j, k, n) in [(0, 1, 2, 1), (5, 2, 1, 1), (19, 0, 0, 0), (7, 3, 0, 0)]:
+        assert d.rescore(c, j, k, n) == orc.pass2_one(c, j, k, n)
