@@ -24,6 +24,7 @@ DMX_BORROW_INPUTS = 0x2
 DMX_FP32_PAIRS = 0x4
 DMX_SKIP_SINGLE = 0x8
 DMX_TRUST_INPUTS = 0x10
+DMX_HOST_FINALISE = 0x20
 
 # every symbol include/dmx.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
@@ -61,6 +62,7 @@ class DmxStats(C.Structure):
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("n_entries", C.c_int64), ("n_reads", C.c_int64), ("n_tasks", C.c_int64),
         ("gpu_launches", C.c_int64), ("n_rescored", C.c_int64), ("n_fullcell", C.c_int64),
+        ("n_rescored_gpu", C.c_int64), ("gpu_exact", C.c_int32), ("pad_", C.c_int32),
         ("algo_bytes", C.c_double), ("pair_kernel_ms", C.c_double),
     ]
 
@@ -150,14 +152,15 @@ class Demuxlet:
     def __init__(self, nv: int, alphas: Sequence[float] = (0.0, 0.5), doublet_prior: float = 0.5,
                  min_total: int = 0, min_uniq: int = 0, min_snp: int = 0, device: int = 0,
                  exact_ties: bool = True, borrow: bool = False, fp32_pairs: bool = False,
-                 skip_single: bool = False, trust_inputs: bool = False, host_threads: int = 0):
+                 skip_single: bool = False, trust_inputs: bool = False, host_threads: int = 0,
+                 host_finalise: bool = False):
         self.lib = load_library()
         self.nv = int(nv)
         self.alpha = np.ascontiguousarray(alphas, dtype=np.float64)
         self.nA = int(self.alpha.shape[0])
         flags = ((DMX_EXACT_TIES if exact_ties else 0) | (DMX_BORROW_INPUTS if borrow else 0) |
                  (DMX_FP32_PAIRS if fp32_pairs else 0) | (DMX_SKIP_SINGLE if skip_single else 0) |
-                 (DMX_TRUST_INPUTS if trust_inputs else 0))
+                 (DMX_TRUST_INPUTS if trust_inputs else 0) | (DMX_HOST_FINALISE if host_finalise else 0))
         self.cfg = DmxConfig(self.nv, self.nA, self.alpha.ctypes.data_as(C.POINTER(C.c_double)), doublet_prior,
                              min_total, min_uniq, min_snp, device, flags, host_threads)
         self._h = C.c_void_p()

@@ -71,6 +71,7 @@ struct dmx_ctx {
   std::vector<double> alpha;
   PGrid pg;
   int UQ = 0;
+  int dense_idx[DMX_MAX_ALPHA];
   std::vector<TaskType> tt;
   double err256[256];
   cudaStream_t stream = nullptr;
@@ -100,6 +101,9 @@ struct dmx_ctx {
   DevBuf<TaskType> d_tt;
   DevBuf<Part> d_parts;
   DevBuf<CellOut> d_out;
+  DevBuf<RescList> d_lists;
+  PinBuf<RescList> r_lists;
+  bool gpu_exact = false;          // device log() verified bit-identical to the host libm
 
   // schedule
   std::vector<int32_t> order;       // active cells, largest first
@@ -125,10 +129,66 @@ int fail_cuda(cudaError_t e, const char* what) {
     if (e__ != cudaSuccess) return fail_cuda(e__, #x);         \
   } while (0)
 
+// Upload the host libm's log table and check the device transcription of glibc's log() against the
+// host's own log() on a large sample of the values the path produces (S in (1e-7, 1.1]) plus every
+// table-interval boundary.  Only a 100 % bit-exact match enables the device re-scorer.
+int verify_device_log(dmx_ctx* c) {
+  c->gpu_exact = false;
+  double tab[18 + 256];
+  if (!find_libm_log_table(tab)) return DMX_OK;
+  CU(set_log_table(tab));
+  const int64_t N = 1 << 19;
+  std::vector<double> x(N), y(N);
+  uint64_t st = 0x9E3779B97F4A7C15ull;
+  auto rnd = [&]() {
+    st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+    return (double)(st >> 11) * (1.0 / 9007199254740992.0);
+  };
+  int64_t i = 0;
+  for (int t = 0; t < 128; ++t)               // interval boundaries of the 128-entry table, +- a few ulps
+    for (int d = -4; d <= 4; ++d) {
+      uint64_t bits = 0x3fe6000000000000ull + ((uint64_t)t << 45) + (uint64_t)(int64_t)d;
+      double v;
+      memcpy(&v, &bits, 8);
+      x[i++] = v;
+      x[i++] = v * 0.0009765625;
+    }
+  for (int d = -2000; d <= 2000; ++d) {       // both edges of the near-1 branch
+    uint64_t b0 = 0x3fee000000000000ull + (uint64_t)(int64_t)d, b1 = 0x3ff1090000000000ull + (uint64_t)(int64_t)d,
+             b2 = 0x3ff0000000000000ull + (uint64_t)(int64_t)d;
+    memcpy(&x[i++], &b0, 8); memcpy(&x[i++], &b1, 8); memcpy(&x[i++], &b2, 8);
+  }
+  for (; i < N; ++i) {
+    const int kind = (int)(i & 3);
+    if (kind == 0) x[i] = exp(-16.2 * rnd());                 // log-uniform down to 1e-7
+    else if (kind == 1) x[i] = 0.9 + 0.2 * rnd();             // around 1
+    else if (kind == 2) x[i] = 1.0 - 1e-5 * rnd() + 3e-7;     // the uninformative-entry cluster
+    else x[i] = 1e-6 * (1.0 + 50.0 * rnd());                  // the floor cluster
+  }
+  DevBuf<double> dx, dy;
+  CU(dx.reserve(N)); CU(dy.reserve(N));
+  CU(cudaMemcpyAsync(dx.p, x.data(), N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(launch_logtest(dx.p, dy.p, N, c->stream));
+  CU(cudaMemcpyAsync(y.data(), dy.p, N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  dx.release(); dy.release();
+  bool same = true;
+  for (int64_t q = 0; q < N && same; ++q) {
+    volatile double xv = x[q];
+    const double h = log(xv);
+    if (memcmp(&h, &y[q], 8) != 0) same = false;
+  }
+  c->gpu_exact = same;
+  return DMX_OK;
+}
+
 void build_tasks(dmx_ctx* c) {
   const int nA = c->cfg.n_alpha, nvp = c->nvp;
   const PGrid& g = c->pg;
   c->tt.clear();
+  int nd = 0;
+  for (int n = 0; n < nA; ++n) c->dense_idx[n] = (g.mode[n] == PM_SEP) ? -1 : nd++;
+  c->UQ = QHEAD + QPLANE * nd;
   int fd = -1;
   for (int n = 0; n < nA; ++n)
     if (g.mode[n] != PM_SEP) { fd = n; break; }
@@ -148,7 +208,7 @@ void build_tasks(dmx_ctx* c) {
         if (n == fd) t.flags |= TF_SCALARS;
         first = false;
       }
-      for (int i = 0; i < 9; ++i) t.qidx[i] = g.umap[n * 9 + i];
+      t.qoff = (int16_t)(QHEAD + QPLANE * c->dense_idx[n]);
       c->tt.push_back(t);
     };
     for (int jb = 0; jb < nblk; ++jb) {
@@ -201,10 +261,10 @@ HostView host_view(const dmx_ctx* c) {
 
 void fill_scan_params(dmx_ctx* c, ScanParams* p) {
   memset(p, 0, sizeof(*p));
-  p->nv = c->cfg.nv; p->nvp = c->nvp; p->nA = c->cfg.n_alpha; p->U = c->pg.U; p->UQ = c->UQ;
+  p->nv = c->cfg.nv; p->nvp = c->nvp; p->nA = c->cfg.n_alpha; p->UQ = c->UQ;
   p->sep0 = c->pg.sep0; p->T = (int)c->tt.size();
   p->want_single = (c->cfg.flags & DMX_SKIP_SINGLE) ? 0 : 1;
-  for (int l = 0; l < 3; ++l) p->fidx[l] = c->pg.umap[l * 3];
+  p->ntasks = (int64_t)c->order.size() * p->T;
   p->eps_rel = (c->cfg.flags & DMX_FP32_PAIRS) ? 1e-4 : 1e-9;
   p->gp = c->d_gp.p; p->gp0 = c->d_gp0.p; p->ent_snp = c->d_ent_snp.p; p->entq = c->d_entq.p;
   p->cell_ptr = c->d_cell_ptr.p; p->cell_order = c->d_order.p; p->tt = c->d_tt.p; p->parts = c->d_parts.p;
@@ -244,7 +304,8 @@ int dense_scan(dmx_ctx* c, const std::vector<int32_t>& cells, double* host_out /
     p.cell_order = d_cells.p;
     p.parts = d_parts.p;
     p.dense = c->d_dense.p;
-    CU(launch_pair_scan(p, (int64_t)n, false, c->stream));
+    p.ntasks = (int64_t)n * p.T;
+    CU(launch_pair_scan(p, false, c->stream));
     CU(launch_fill_sep_dense(p, (int64_t)n, c->stream));
     c->st.gpu_launches += 1 + (p.sep0 ? 1 : 0);
     CU(cudaMemcpyAsync(host_out + lo * per, c->d_dense.p, n * per * sizeof(double), cudaMemcpyDeviceToHost,
@@ -329,7 +390,6 @@ int dmx_create(dmx_ctx** out, const dmx_config* cfg) {
   c->cfg.alpha = c->alpha.data();
   memset(&c->st, 0, sizeof(c->st));
   build_pgrid(c->alpha.data(), cfg->n_alpha, &c->pg);
-  c->UQ = (c->pg.U + 3 + 1) & ~1;
   c->nvp = (cfg->nv + TILE - 1) / TILE * TILE;
   build_tasks(c);
   for (int i = 0; i <= 255; ++i) c->err256[i] = (i > 1) ? pow(0.1, i * 0.1) : 0.75;   // PhredHelper.cpp:30
@@ -344,6 +404,13 @@ int dmx_create(dmx_ctx** out, const dmx_config* cfg) {
     dmx_destroy(c);
     return fail_cuda(e, "dmx_create");
   }
+  if (cfg->flags & DMX_EXACT_TIES) {
+    const int rc = verify_device_log(c);
+    if (rc != DMX_OK) {
+      dmx_destroy(c);
+      return rc;
+    }
+  }
   *out = c;
   return DMX_OK;
 }
@@ -356,6 +423,7 @@ void dmx_destroy(dmx_ctx* c) {
   c->d_lb.release(); c->d_p1.release(); c->d_p1_0.release(); c->d_l00.release(); c->d_sing.release();
   c->d_dense.release(); c->d_cell_ptr.release(); c->d_ent_ptr.release(); c->d_ent_snp.release();
   c->d_order.release(); c->d_reads.release(); c->d_tt.release(); c->d_parts.release(); c->d_out.release();
+  c->d_lists.release(); c->r_lists.release();
   c->o_gp.release(); c->o_cell_ptr.release(); c->o_ent_ptr.release(); c->o_ent_snp.release(); c->o_reads.release();
   c->r_out.release(); c->r_sing.release(); c->r_row0.release(); c->r_l00.release(); c->r_p1.release();
   c->r_p1_0.release(); c->r_dense.release();
@@ -519,11 +587,27 @@ int dmx_compute(dmx_ctx* c) {
   eq.U = c->pg.U; eq.UQ = c->UQ; eq.E = c->E; eq.ent_ptr = c->d_ent_ptr.p; eq.reads = c->d_reads.p;
   eq.entq = c->d_entq.p;
   memcpy(eq.pu, c->pg.pu, sizeof(double) * c->pg.U);
+  {
+    // record layout: GL[3] (written by the kernel), f[3] = Q'[0][l][0] of a separable plane 0, then per dense
+    // plane 9 values Q'[n][l][m] (+1 pad); oslot lists, per distinct p value, the record slots it feeds
+    std::vector<std::vector<int>> slots(c->pg.U);
+    if (c->pg.sep0)
+      for (int l = 0; l < 3; ++l) slots[c->pg.umap[l * 3]].push_back(3 + l);
+    for (int n = 0; n < nA; ++n)
+      if (c->dense_idx[n] >= 0)
+        for (int i = 0; i < 9; ++i) slots[c->pg.umap[n * 9 + i]].push_back(QHEAD + QPLANE * c->dense_idx[n] + i);
+    int o = 0;
+    for (int u2 = 0; u2 < c->pg.U; ++u2) {
+      eq.oslot_ptr[u2] = (uint8_t)o;
+      for (int sl : slots[u2]) eq.oslot[o++] = (uint8_t)sl;
+    }
+    eq.oslot_ptr[c->pg.U] = (uint8_t)o;
+  }
   CU(launch_entq(eq, c->stream));
   CU(cudaEventRecord(c->ev[1], c->stream));
   ScanParams sp;
   fill_scan_params(c, &sp);
-  CU(launch_pair_scan(sp, nact, (c->cfg.flags & DMX_FP32_PAIRS) != 0, c->stream));
+  CU(launch_pair_scan(sp, (c->cfg.flags & DMX_FP32_PAIRS) != 0, c->stream));
   CU(cudaEventRecord(c->ev[2], c->stream));
   MergeParams mp;
   memset(&mp, 0, sizeof(mp));
@@ -533,8 +617,25 @@ int dmx_compute(dmx_ctx* c) {
     mp.w_double[n] = c->cfg.doublet_prior / nv / (nv - 1) / (nA - 1) / (c->alpha[n] == 0.5 ? 2.0 : 1.0);
   mp.cell_order = c->d_order.p; mp.tt = c->d_tt.p; mp.parts = c->d_parts.p; mp.row0 = c->d_row0.p;
   mp.singA = c->d_singA.p; mp.lb = c->d_lb.p; mp.sing = c->d_sing.p; mp.out = c->d_out.p;
+  const bool exact = (c->cfg.flags & DMX_EXACT_TIES) != 0;
+  const bool dev_rescore = exact && c->gpu_exact && !(c->cfg.flags & DMX_HOST_FINALISE);
+  if (dev_rescore) {
+    CU(c->d_lists.reserve(nc + 1));
+    CU(c->r_lists.reserve(nc + 1));
+    mp.lists = c->d_lists.p;
+    for (int n = 0; n < nA; ++n) mp.mode[n] = c->pg.mode[n];
+  }
   CU(launch_merge(mp, nact, c->stream));
-  c->st.gpu_launches += (c->nsnps ? 1 : 0) + (c->E ? 1 : 0) + (nact ? 2 : 0);
+  if (dev_rescore) {
+    RescoreParams rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.nv = nv; rp.nvp = c->nvp; rp.nA = nA; rp.UQ = c->UQ; rp.sep0 = c->pg.sep0;
+    for (int n = 0; n < nA; ++n) rp.dense_idx[n] = (int8_t)c->dense_idx[n];
+    rp.gp = c->d_gp.p; rp.ent_snp = c->d_ent_snp.p; rp.entq = c->d_entq.p; rp.cell_ptr = c->d_cell_ptr.p;
+    rp.cell_order = c->d_order.p; rp.lists = c->d_lists.p;
+    CU(launch_rescore(rp, nact, c->stream));
+  }
+  c->st.gpu_launches += (c->nsnps ? 1 : 0) + (c->E ? 1 : 0) + (nact ? 2 : 0) + ((nact && dev_rescore) ? 1 : 0);
   CU(cudaEventRecord(c->ev[3], c->stream));
   CU(cudaMemcpyAsync(c->r_out.p, c->d_out.p, nc * sizeof(CellOut), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(c->r_sing.p, c->d_sing.p, (size_t)nc * nv * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -544,9 +645,11 @@ int dmx_compute(dmx_ctx* c) {
     CU(cudaMemcpyAsync(c->r_p1.p, c->d_p1.p, (size_t)nc * nv * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(c->r_p1_0.p, c->d_p1_0.p, (size_t)nc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   }
+  if (dev_rescore && nc)
+    CU(cudaMemcpyAsync(c->r_lists.p, c->d_lists.p, nc * sizeof(RescList), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaEventRecord(c->ev[4], c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  c->st.d2h_bytes = nc * (int64_t)sizeof(CellOut) + (int64_t)nc * nv * 8 * (1 + nA + (sp.want_single ? 1 : 0)) +
+  c->st.d2h_bytes = nc * (int64_t)(sizeof(CellOut) + (dev_rescore ? sizeof(RescList) : 0)) + (int64_t)nc * nv * 8 * (1 + nA + (sp.want_single ? 1 : 0)) +
                     nc * nA * 8 + (sp.want_single ? nc * 8 : 0);
   float ms = 0;
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->st.prep_ms = ms;
@@ -559,10 +662,9 @@ int dmx_compute(dmx_ctx* c) {
   c->best.assign(nc, dmx_best_rec());
   const HostView hv = host_view(c);
   const ExactScorer scorer(hv, c->err256);
-  const bool exact = (c->cfg.flags & DMX_EXACT_TIES) != 0;
   const int nth = host_threads(c);
   std::vector<std::vector<int32_t>> overflow(nth);
-  std::vector<int64_t> resc(nth, 0);
+  std::vector<int64_t> resc(nth, 0), resc_gpu(nth, 0);
   auto do_cell = [&](int64_t cell, const std::vector<Hyp>& cands, int tid) {
     dmx_best_rec* r = &c->best[cell];
     CellGpu g;
@@ -570,8 +672,11 @@ int dmx_compute(dmx_ctx* c) {
     g.sing = c->r_sing.p + (size_t)cell * nv;
     g.row0 = c->r_row0.p + (size_t)cell * nA * nv;
     g.l00 = c->r_l00.p + (size_t)cell * nA;
-    finalise_cell(hv, scorer, cell, g, cands, c->cfg.doublet_prior, sp.eps_rel, exact, r);
+    int32_t from_gpu = 0;
+    finalise_cell(hv, scorer, cell, g, cands, c->cfg.doublet_prior, sp.eps_rel, exact,
+                  dev_rescore ? &c->r_lists.p[cell] : nullptr, r, &from_gpu);
     resc[tid] += r->n_rescored;
+    resc_gpu[tid] += from_gpu;
   };
   parallel_for(nc, nth, [&](int64_t cell, int tid) {
     dmx_best_rec* r = &c->best[cell];
@@ -607,7 +712,9 @@ int dmx_compute(dmx_ctx* c) {
     }
     c->st.n_fullcell = (int64_t)ov.size();
   }
-  for (int t = 0; t < nth; ++t) c->st.n_rescored += resc[t];
+  c->st.n_rescored_gpu = 0;
+  for (int t = 0; t < nth; ++t) { c->st.n_rescored += resc[t]; c->st.n_rescored_gpu += resc_gpu[t]; }
+  c->st.gpu_exact = c->gpu_exact ? 1 : 0;
   c->st.finalise_ms = now_ms() - tf0;
   c->st.n_entries = c->E;
   c->st.n_reads = c->R;

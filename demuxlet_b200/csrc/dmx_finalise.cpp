@@ -167,7 +167,7 @@ inline bool near(double a, double b, double eps_rel) {
 
 void finalise_cell(const HostView& hv, const ExactScorer& sc, int64_t cell, const CellGpu& g,
                    const std::vector<Hyp>& cands, double doublet_prior, double eps_rel, bool exact,
-                   dmx_best_rec* rec) {
+                   const RescList* gl, dmx_best_rec* rec, int32_t* n_from_gpu) {
   const int nv = hv.nv;
   std::vector<double> vals(g.sing, g.sing + nv);
   std::vector<uint8_t> is_exact(nv, 0);
@@ -196,7 +196,25 @@ void finalise_cell(const HostView& hv, const ExactScorer& sc, int64_t cell, cons
   auto run_batch = [&](std::vector<Hyp>& hs) {
     if (hs.empty()) return;
     std::vector<double> out(hs.size());
-    sc.eval(cell, hs.data(), (int)hs.size(), out.data());
+    // values the device re-scorer already produced (bit-identical to the host arithmetic, verified at
+    // dmx_create); the rest is scored here
+    std::vector<Hyp> miss;
+    std::vector<size_t> miss_at;
+    for (size_t i = 0; i < hs.size(); ++i) {
+      bool hit = false;
+      if (gl && gl->n > 0) {
+        const uint32_t key = (uint32_t)hs[i].j | ((uint32_t)hs[i].k << 12) | ((uint32_t)hs[i].n << 24);
+        for (int q = 0; q < gl->n; ++q)
+          if (gl->hyp[q] == key) { out[i] = gl->val[q]; hit = true; break; }
+      }
+      if (hit) ++*n_from_gpu;
+      else { miss.push_back(hs[i]); miss_at.push_back(i); }
+    }
+    if (!miss.empty()) {
+      std::vector<double> mo(miss.size());
+      sc.eval(cell, miss.data(), (int)miss.size(), mo.data());
+      for (size_t i = 0; i < miss.size(); ++i) out[miss_at[i]] = mo[i];
+    }
     for (size_t i = 0; i < hs.size(); ++i) {
       cache.h.push_back(hs[i]);
       cache.v.push_back(out[i]);
@@ -296,4 +314,62 @@ void finalise_cell(const HostView& hv, const ExactScorer& sc, int64_t cell, cons
     rec->call = 2;
 }
 
+}  // namespace dmx
+
+// ---- locating the host libm's log table -------------------------------------------------------------
+#include <stdio.h>
+namespace dmx {
+bool find_libm_log_table(double out[18 + 256]) {
+  // path of the libm this process has mapped
+  std::string path;
+  if (FILE* m = fopen("/proc/self/maps", "r")) {
+    char line[1024];
+    while (fgets(line, sizeof(line), m)) {
+      const char* p = strstr(line, "/");
+      if (p && strstr(p, "libm.so")) {
+        path = p;
+        while (!path.empty() && (path.back() == '\n' || path.back() == ' ')) path.pop_back();
+        break;
+      }
+    }
+    fclose(m);
+  }
+  const char* fallbacks[] = {"/lib/x86_64-linux-gnu/libm.so.6", "/usr/lib/x86_64-linux-gnu/libm.so.6",
+                             "/lib64/libm.so.6", "/usr/lib64/libm.so.6"};
+  std::vector<std::string> tries;
+  if (!path.empty()) tries.push_back(path);
+  for (const char* fb : fallbacks) tries.push_back(fb);
+  // struct log_data starts with ln2hi, ln2lo (N = 128 variant), then poly[0] ~ -0.5, ...
+  const double ln2hi = 0x1.62e42fefa3800p-1, ln2lo = 0x1.ef35793c76730p-45;
+  for (const std::string& t : tries) {
+    FILE* fp = fopen(t.c_str(), "rb");
+    if (!fp) continue;
+    std::vector<unsigned char> buf;
+    unsigned char chunk[65536];
+    size_t n;
+    while ((n = fread(chunk, 1, sizeof(chunk), fp)) > 0) buf.insert(buf.end(), chunk, chunk + n);
+    fclose(fp);
+    const size_t need = (18 + 256) * sizeof(double);
+    for (size_t off = 0; off + need <= buf.size(); off += 8) {
+      double a, b;
+      memcpy(&a, &buf[off], 8);
+      if (a != ln2hi) continue;
+      memcpy(&b, &buf[off + 8], 8);
+      if (b != ln2lo) continue;
+      double tab[18 + 256];
+      memcpy(tab, &buf[off], need);
+      // sanity: polynomial heads and a monotone invc column that brackets [1/1.42, 1/0.69]
+      bool ok = fabs(tab[2] + 0.5) < 1e-9 && tab[7] == -0.5 && fabs(tab[8] - 1.0 / 3) < 1e-9;
+      for (int i = 0; ok && i < 128; ++i) {
+        const double invc = tab[18 + 2 * i], logc = tab[19 + 2 * i];
+        if (!(invc > 0.69 && invc < 1.46) || fabs(logc + log(invc)) > 1e-9) ok = false;
+      }
+      if (ok) {
+        memcpy(out, tab, need);
+        return true;
+      }
+    }
+  }
+  return false;
+}
 }  // namespace dmx

@@ -65,6 +65,10 @@ void candidates_from_dense(const double* dense, int nv, int nA, int first_arg_pl
 // within the window of the GPU's best pair.
 void finalise_cell(const HostView& hv, const ExactScorer& sc, int64_t cell, const CellGpu& g,
                    const std::vector<Hyp>& cands, double doublet_prior, double eps_rel, bool exact,
-                   dmx_best_rec* rec);
+                   const RescList* gpu_exact, dmx_best_rec* rec, int32_t* n_from_gpu);
+
+// the host libm's __log_data (ln2hi, ln2lo, poly[5], poly1[11], tab[128]{invc, logc}) read from the
+// libm.so.6 image this process has loaded; false if it cannot be located
+bool find_libm_log_table(double out[18 + 256]);
 
 }  // namespace dmx

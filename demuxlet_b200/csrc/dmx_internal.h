@@ -13,9 +13,12 @@ constexpr int BLK_RECT_K = 32; // k-side samples of a rectangular task (16 x 8 t
 constexpr int NB = 8;          // pileup entries per pipeline stage
 constexpr int S_RAW = 4;       // stages of the raw ring: bulk (TMA) copies -> transform warps
 constexpr int S_PROC = 2;      // stages of the processed (a, w) ring: transform -> consumer warps
-constexpr int NCW = 5;         // consumer warps (136 tiles of the 64 x 64 upper triangle -> 160 lanes)
-constexpr int NTW = 2;         // transform warps (one lane per sample of each side)
-constexpr int NTHREADS = (NCW + NTW + 1) * 32;   // + 1 loader warp
+constexpr int NCW = 5;         // consumer warps per slot (136 tiles of the 64 x 64 upper triangle -> 160 lanes)
+constexpr int NTW = 2;         // transform warps per slot (one lane per sample of each side)
+constexpr int NSLOT = 2;       // independent task pipelines per CTA (one persistent CTA per SM)
+constexpr int NTHREADS = NSLOT * (NCW + NTW + 1) * 32;   // + 1 loader warp per slot = 512
+constexpr int QHEAD = 6;       // entry record head: 3 pass-1 GLs, 3 values of the separable plane
+constexpr int QPLANE = 10;     // doubles per dense plane in the entry record (9 + 1 pad: 80 B, 16-B aligned)
 constexpr int GRP_DBL = 14;    // doubles per 4-sample group in the processed ring (12 + 2 pad: 112 B
                                // stride spreads 16-byte lane loads over all banks)
 constexpr int GRP_F32 = 12;    // floats per 4-sample group in the fp32 processed ring (48 B stride)
@@ -48,11 +51,10 @@ struct TaskType {
   int16_t n;           // alpha index of the plane
   int16_t j0, k0;      // first sample of each side
   int16_t nj, nk;      // samples on each side, padded to a multiple of TILE
-  int16_t pad;
+  int16_t qoff;        // offset (doubles) of the plane's 9 Q' values inside the entry record
   uint32_t flags;
-  uint8_t qidx[12];    // index into the entry's q[] for Q'[n][l][m] (9 used)
 };
-static_assert(sizeof(TaskType) == 28, "TaskType layout");
+static_assert(sizeof(TaskType) == 16, "TaskType layout");
 
 // partial reduction of one task over its hypotheses
 struct Part {
@@ -75,16 +77,16 @@ struct CellOut {
 static_assert(sizeof(CellOut) == 72, "CellOut must be 72 bytes");
 
 struct ScanParams {
-  int32_t nv, nvp, nA, U, UQ;
+  int32_t nv, nvp, nA, UQ;
   int32_t sep0;                // alpha[0] == 0: the n = 0 plane is separable
   int32_t T;                   // task types per cell
   int32_t want_single;         // accumulate pass 1
-  int32_t fidx[3];             // q index of Q'[0][l][.] for the separable plane
+  int64_t ntasks;              // nactive * T
   double eps_rel;              // candidate window, relative to max(1, |best|)
   const float* gp;             // [nsnps][nvp*3], rows zero padded
   const double* gp0;           // [nsnps][4]: cohort mean (x, y, z), 0
   const int32_t* ent_snp;      // [E]
-  const double* entq;          // [E][UQ]: U distinct Q' values, then the 3 pass-1 GLs
+  const double* entq;          // [E][UQ]: GL[3], sep-plane f[3], then QPLANE doubles per dense plane
   const int64_t* cell_ptr;     // [ncells+1]
   const int32_t* cell_order;   // [nactive] cell ids, scheduled order
   const TaskType* tt;          // [T]
@@ -96,6 +98,27 @@ struct ScanParams {
   double* p1_0;                // [ncells]          pass-1 llk0s
   double* l00;                 // [ncells][nA]      llks00
   double* dense;               // optional [nactive][nv][nv][nA]
+};
+
+// exact re-scoring requests of one cell (built by merge_kernel, filled by rescore_kernel)
+constexpr int RMAX = 32;
+struct RescList {
+  int32_t n;                   // hypotheses listed; -1: too many (the host scorer handles the cell)
+  int32_t pad;
+  uint32_t hyp[RMAX];          // j | k << 12 | n << 24
+  double val[RMAX];            // llksAB[j][k][n] in the reference's arithmetic
+};
+static_assert(sizeof(RescList) == 392, "RescList layout");
+
+struct RescoreParams {
+  int32_t nv, nvp, nA, UQ, sep0;
+  int8_t dense_idx[DMX_MAX_ALPHA];
+  const float* gp;
+  const int32_t* ent_snp;
+  const double* entq;
+  const int64_t* cell_ptr;
+  const int32_t* cell_order;
+  RescList* lists;             // [ncells]
 };
 
 struct MergeParams {
@@ -111,6 +134,8 @@ struct MergeParams {
   const double* lb;
   double* sing;                // [ncells][nv] out: llksAB[j][0][0]
   CellOut* out;                // [ncells]
+  RescList* lists;             // [ncells] or null: exact re-scoring requests
+  uint8_t mode[DMX_MAX_ALPHA]; // PM_* per alpha index
 };
 
 struct EntqParams {
@@ -120,15 +145,20 @@ struct EntqParams {
   const uint16_t* reads;
   double* entq;
   double pu[MAX_U];            // distinct p values (cmd_cram_demuxlet.cpp:613)
+  uint8_t oslot_ptr[MAX_U + 1];   // CSR: record slots fed by distinct value u
+  uint8_t oslot[QHEAD + QPLANE * DMX_MAX_ALPHA];
 };
 
 // host-callable launchers (dmx_kernels.cu); all return a cudaError_t as int
 int launch_gp0(const float* gp, double* gp0, int64_t nsnps, int nv, int nvp, void* stream);
 int launch_entq(const EntqParams& p, void* stream);
-int launch_pair_scan(const ScanParams& p, int64_t nactive, bool fp32, void* stream);
+int launch_pair_scan(const ScanParams& p, bool fp32, void* stream);
 int launch_merge(const MergeParams& p, int64_t nactive, void* stream);
 int launch_fill_sep_dense(const ScanParams& p, int64_t nactive, void* stream);
+int launch_rescore(const RescoreParams& p, int64_t nactive, void* stream);
 int set_err_table(const double* err256);
+int set_log_table(const double* tab274);          // glibc __log_data: ln2hi, ln2lo, A[5], B[11], tab[128][2]
+int launch_logtest(const double* x, double* y, int64_t n, void* stream);
 int pair_scan_init();          // func attributes (max dynamic smem)
 size_t pair_scan_smem_bytes(const ScanParams& p, bool fp32);
 

@@ -26,6 +26,84 @@
 namespace dmx {
 
 __constant__ double c_err[256];   // phred2Err, PhredHelper.cpp:30-32 (computed on the host with libm pow)
+__constant__ double c_logtab[18 + 256];   // the host libm's __log_data (read from the loaded libm.so.6 at run time)
+
+// Bit-for-bit transcription of the x86-64 FMA build of glibc's log() (sysdeps/ieee754/dbl-64/e_log.c as
+// compiled into libm.so.6 2.3x: instruction sequence of __log_fma, table __log_data).  IEEE fma/mul/add are
+// exact on both machines, so with the host's own table this returns the very double the reference's
+// `log(sumPs)` (cmd_cram_demuxlet.cpp:683) yields on an FMA-capable x86 host.  dmx_create verifies that
+// claim against the host libm on a large sample before the device re-scorer is trusted.
+__device__ __forceinline__ double glibc_log_fma(double x) {
+  const double* T = c_logtab;
+  unsigned long long ix = (unsigned long long)__double_as_longlong(x);
+  if (ix - 0x3fee000000000000ull <= 0x308ffffffffffull) {          // 1 - 2^-4 <= x < 1 + 0x1.09p-4
+    if (ix == 0x3ff0000000000000ull) return 0.0;
+    const double r = __dadd_rn(x, -1.0);
+    double p1 = __fma_rn(r, T[9], T[8]);
+    double p2 = __fma_rn(r, T[12], T[11]);
+    const double r2 = __dmul_rn(r, r);
+    double p3 = __fma_rn(r, T[15], T[14]);
+    p1 = __fma_rn(r2, T[10], p1);
+    p2 = __fma_rn(r2, T[13], p2);
+    const double r3 = __dmul_rn(r, r2);
+    p3 = __fma_rn(r2, T[16], p3);
+    p3 = __fma_rn(r3, T[17], p3);
+    const double q = __fma_rn(p3, r3, p2);
+    const double poly = __fma_rn(q, r3, p1);
+    const double t = __fma_rn(r, 134217728.0, r);
+    const double rhi = __fma_rn(-134217728.0, r, t);
+    const double rhi2 = __dmul_rn(rhi, rhi);
+    const double rlo = __dsub_rn(r, rhi);
+    const double hi = __fma_rn(rhi2, T[7], r);
+    double lo = __fma_rn(rhi2, T[7], __dsub_rn(r, hi));
+    const double s = __dadd_rn(r, rhi);
+    const double b = __dmul_rn(T[7], rlo);
+    lo = __fma_rn(b, s, lo);
+    const double y = __fma_rn(poly, r3, lo);
+    return __dadd_rn(hi, y);
+  }
+  const unsigned top = (unsigned)(ix >> 48);
+  if (top - 0x10u > 0x7fdfu) {
+    if (ix * 2 == 0) return -INFINITY;                              // log(+-0)
+    if (ix == 0x7ff0000000000000ull) return x;                      // log(inf)
+    if ((top & 0x8000u) || (top & 0x7ff0u) == 0x7ff0u) return __longlong_as_double(0x7ff8000000000000ll);
+    ix = (unsigned long long)__double_as_longlong(__dmul_rn(x, 4503599627370496.0));   // subnormal
+    ix -= 52ull << 52;
+  }
+  const unsigned long long tmp = ix - 0x3fe6000000000000ull;
+  const int i = (int)((tmp >> 45) & 127);
+  const int k = (int)((long long)tmp >> 52);
+  const unsigned long long iz = ix - (tmp & 0xfff0000000000000ull);
+  const double invc = T[18 + 2 * i], logc = T[19 + 2 * i];
+  const double z = __longlong_as_double((long long)iz);
+  const double kd = (double)k;
+  const double w = __fma_rn(kd, T[0], logc);
+  const double r = __fma_rn(z, invc, -1.0);
+  const double t1 = __fma_rn(r, T[4], T[3]);
+  const double hi = __dadd_rn(r, w);
+  const double r2 = __dmul_rn(r, r);
+  double lo = __dadd_rn(__dsub_rn(w, hi), r);
+  lo = __fma_rn(kd, T[1], lo);
+  const double r3 = __dmul_rn(r, r2);
+  const double t2 = __fma_rn(r, T[6], T[5]);
+  lo = __fma_rn(r2, T[2], lo);
+  const double t3 = __fma_rn(t2, r2, t1);
+  const double y = __fma_rn(r3, t3, lo);
+  return __dadd_rn(y, hi);
+}
+
+__global__ void logtest_kernel(const double* __restrict__ x, double* __restrict__ y, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = glibc_log_fma(x[i]);
+}
+int launch_logtest(const double* x, double* y, int64_t n, void* stream) {
+  if (n == 0) return 0;
+  logtest_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, y, n);
+  return (int)cudaGetLastError();
+}
+int set_log_table(const double* tab274) {
+  return (int)cudaMemcpyToSymbol(c_logtab, tab274, (18 + 256) * sizeof(double));
+}
 
 // ---------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + bulk async copy (TMA 1-D)
@@ -65,8 +143,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
-__device__ __forceinline__ void consumer_bar_sync() {
-  asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory");
+__device__ __forceinline__ void consumer_bar_sync(int slot) {
+  asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "n"(NCW * 32) : "memory");
 }
 
 // peel the binary exponent of a positive double into an integer accumulator; mantissa stays in [1,2)
@@ -169,16 +247,19 @@ __global__ void __launch_bounds__(256) entq_kernel(const __grid_constant__ EntqP
   double* out = p.entq + e * p.UQ;
 #pragma unroll
   for (int v = 0; v < VPL; ++v)
-    if (ok[v]) out[sub + v * LPE] = __ddiv_rn(P[v], mx);                     // :656-663
+    if (ok[v]) {
+      const int u = sub + v * LPE;
+      const double val = __ddiv_rn(P[v], mx);                                // :656-663
+      for (int o = p.oslot_ptr[u]; o < p.oslot_ptr[u + 1]; ++o) out[p.oslot[o]] = val;
+    }
   if (sub == 0) {
     G0 = __dadd_rn(G0, 1e-6);                                                // :446-452
     G1 = __dadd_rn(G1, 1e-6);
     G2 = __dadd_rn(G2, 1e-6);
     const double sm = __dadd_rn(__dadd_rn(G0, G1), G2);
-    out[p.U] = __ddiv_rn(G0, sm);
-    out[p.U + 1] = __ddiv_rn(G1, sm);
-    out[p.U + 2] = __ddiv_rn(G2, sm);
-    if (p.U + 3 < p.UQ) out[p.U + 3] = 0.0;
+    out[0] = __ddiv_rn(G0, sm);
+    out[1] = __ddiv_rn(G1, sm);
+    out[2] = __ddiv_rn(G2, sm);
   }
 }
 
@@ -199,365 +280,433 @@ int set_err_table(const double* err256) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// pair scan
+// pair scan: persistent kernel, one 512-thread CTA per SM, two independent task pipelines ("slots")
 // ---------------------------------------------------------------------------------------------
-struct SmemLayout {
-  uint32_t rowj_bytes, rowk_bytes;      // GP row slices per entry
-  uint32_t off_gpj, off_gpk, off_gp0, off_q, raw_slot_bytes;
-  uint32_t ent_a_dbl, ent_w_dbl;        // doubles per entry in the processed ring
-  uint32_t off_raw, off_proc, proc_slot_bytes, total;
-};
+// Warp roles.  SM sub-partition = warp id % 4; the FP64 pipe is the bound, so the consumer warps (C,
+// 64 DFMA/DMUL per lane and entry) are spread 3/3/2/2 over the four sub-partitions and the lighter
+// transform (T) and loader (L) warps fill the rest:
+//   wid  0  1  2  3 |  4  5  6  7 |  8  9 10 11 | 12 13 14 15
+//        CA CA CA CA| CA CB CB CB | CB CB TA TA | LA LB TB TB        (A, B = slot)
+namespace {
+constexpr uint32_t ROWJ_STRIDE = BLK * 12;          // bytes per entry, j-side GP row slice
+constexpr uint32_t ROWK_STRIDE = BLK_RECT_K * 12;   // bytes per entry, k-side slice of a rectangular task
+constexpr uint32_t Q_STRIDE = (QHEAD + QPLANE) * 8; // 128 B: head (48) + one plane (80)
+constexpr uint32_t OFF_GPJ = 0;
+constexpr uint32_t OFF_GPK = OFF_GPJ + NB * ROWJ_STRIDE;
+constexpr uint32_t OFF_GP0 = OFF_GPK + NB * ROWK_STRIDE;
+constexpr uint32_t OFF_Q = OFF_GP0 + NB * 32;
+constexpr uint32_t RAW_SLOT = OFF_Q + NB * Q_STRIDE;                 // 10496 B
+constexpr uint32_t ENT_DBL = (BLK / TILE) * GRP_DBL;                 // doubles per entry and side (224)
+constexpr uint32_t PROC_SLOT = NB * 2 * ENT_DBL * 8;                 // 28672 B
+constexpr uint32_t SLOT_CTRL = 512;                                  // barriers + epilogue scratch
+constexpr uint32_t SLOT_BYTES = SLOT_CTRL + S_RAW * RAW_SLOT + S_PROC * PROC_SLOT;
+static_assert(RAW_SLOT % 128 == 0 && PROC_SLOT % 128 == 0 && SLOT_BYTES % 128 == 0, "alignment");
 
-__host__ __device__ inline SmemLayout make_layout(int nj, int nk, bool same, int UQ) {
-  SmemLayout L;
-  L.rowj_bytes = (uint32_t)nj * 12u;
-  L.rowk_bytes = same ? 0u : (uint32_t)nk * 12u;
-  L.off_gpj = 0;
-  L.off_gpk = L.off_gpj + NB * L.rowj_bytes;
-  L.off_gp0 = L.off_gpk + NB * L.rowk_bytes;
-  L.off_q = L.off_gp0 + NB * 32u;
-  L.raw_slot_bytes = L.off_q + NB * (uint32_t)UQ * 8u;
-  L.ent_a_dbl = (uint32_t)(nj / TILE) * GRP_DBL;
-  L.ent_w_dbl = (uint32_t)(nk / TILE) * GRP_DBL;
-  L.off_raw = 512;   // barriers + epilogue scratch
-  L.off_proc = L.off_raw + S_RAW * L.raw_slot_bytes;
-  L.proc_slot_bytes = NB * (L.ent_a_dbl + L.ent_w_dbl) * 8u;
-  L.total = L.off_proc + S_PROC * L.proc_slot_bytes;
-  return L;
-}
-
-struct Scratch {                     // lives at smem offset 128
+struct Scratch {                     // at slot offset 128
   double red[2][NCW];
-  double bcast[2];
+  double red2[NCW];
   int ncand;
   uint32_t cand[MAX_CAND];
 };
+static_assert(sizeof(Scratch) + 128 <= SLOT_CTRL, "scratch");
 
-__global__ void __launch_bounds__(NTHREADS, 2) pair_scan_kernel(const __grid_constant__ ScanParams p) {
+struct TaskInfo {
+  int64_t aidx;
+  int tti, cell, nst;
+  int64_t e0, e1;
+};
+
+__device__ __forceinline__ bool next_task(const ScanParams& p, int r, int u, int NS, TaskInfo* t) {
+  const int64_t g = (int64_t)r * NS + ((r & 1) ? (NS - 1 - u) : u);   // snake order over size-sorted tasks
+  if (g >= p.ntasks) return false;
+  t->aidx = g / p.T;
+  t->tti = (int)(g - t->aidx * p.T);
+  t->cell = __ldg(p.cell_order + t->aidx);
+  t->e0 = __ldg(p.cell_ptr + t->cell);
+  t->e1 = __ldg(p.cell_ptr + t->cell + 1);
+  t->nst = (int)((t->e1 - t->e0 + NB - 1) / NB);
+  return true;
+}
+
+// one stage of the transform for lane `tl` (sample slot on each side)
+template <bool SAME, bool FULL>
+__device__ __forceinline__ void transform_stage(const unsigned char* __restrict__ rs, double* __restrict__ pa,
+                                                int tl, int nvalid, bool do_j, bool do_k, bool extras, bool sep0,
+                                                bool want_single, double& PA, double& PB, double& P1) {
+  const int grp = tl >> 2, pos = tl & 3;
+  double* ad = pa + grp * GRP_DBL + pos * 3;
+  double* wd = ad + NB * ENT_DBL;
+  const float* gj = reinterpret_cast<const float*>(rs + OFF_GPJ) + tl * 3;
+  const float* gk = SAME ? gj : reinterpret_cast<const float*>(rs + OFF_GPK) + tl * 3;
+  constexpr int GK_STRIDE = SAME ? ROWJ_STRIDE / 4 : ROWK_STRIDE / 4;
+  const double2* q2 = reinterpret_cast<const double2*>(rs + OFF_Q);
+#pragma unroll
+  for (int e = 0; e < NB; ++e) {
+    if (FULL || e < nvalid) {
+      double g0 = 0, g1 = 0, g2 = 0;
+      if (do_k) {
+        g0 = (double)gk[e * GK_STRIDE];
+        g1 = (double)gk[e * GK_STRIDE + 1];
+        g2 = (double)gk[e * GK_STRIDE + 2];
+        const double2 qa = q2[e * 8 + 3], qb = q2[e * 8 + 4], qc = q2[e * 8 + 5], qd = q2[e * 8 + 6];
+        const double q22 = reinterpret_cast<const double*>(q2 + e * 8 + 7)[0];
+        // Q'[l][m] row-major: qa = (00, 01), qb = (02, 10), qc = (11, 12), qd = (20, 21), q22
+        wd[e * ENT_DBL + 0] = fma(qb.x, g2, fma(qa.y, g1, qa.x * g0));
+        wd[e * ENT_DBL + 1] = fma(qc.y, g2, fma(qc.x, g1, qb.y * g0));
+        wd[e * ENT_DBL + 2] = fma(q22, g2, fma(qd.y, g1, qd.x * g0));
+        if (extras) {
+          const double2 h0 = q2[e * 8], h1 = q2[e * 8 + 1], h2 = q2[e * 8 + 2];   // GL0 GL1 | GL2 f0 | f1 f2
+          if (sep0) PA *= fma(h2.y, g2, fma(h2.x, g1, h1.y * g0));
+          PB *= (g0 + g1) + g2;
+          if (want_single) P1 *= fma(h1.x, g2, fma(h0.y, g1, h0.x * g0));
+        }
+      }
+      if (do_j) {
+        if (SAME) {
+          ad[e * ENT_DBL + 0] = g0; ad[e * ENT_DBL + 1] = g1; ad[e * ENT_DBL + 2] = g2;
+        } else {
+          ad[e * ENT_DBL + 0] = (double)gj[e * (ROWJ_STRIDE / 4)];
+          ad[e * ENT_DBL + 1] = (double)gj[e * (ROWJ_STRIDE / 4) + 1];
+          ad[e * ENT_DBL + 2] = (double)gj[e * (ROWJ_STRIDE / 4) + 2];
+        }
+      }
+    } else {   // identity entry: S = 1 for every hypothesis
+      if (do_k) { wd[e * ENT_DBL + 0] = 1.0; wd[e * ENT_DBL + 1] = 0.0; wd[e * ENT_DBL + 2] = 0.0; }
+      if (do_j) { ad[e * ENT_DBL + 0] = 1.0; ad[e * ENT_DBL + 1] = 0.0; ad[e * ENT_DBL + 2] = 0.0; }
+    }
+  }
+}
+}  // namespace
+
+__global__ void __launch_bounds__(NTHREADS, 1) pair_scan_kernel(const __grid_constant__ ScanParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  uint64_t* raw_full = reinterpret_cast<uint64_t*>(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // role decode (see table above)
+  int role, slot, rw;   // role 0 consumer, 1 transform, 2 loader; rw = warp index inside the role
+  if (warp < 5) { role = 0; slot = 0; rw = warp; }
+  else if (warp < 10) { role = 0; slot = 1; rw = warp - 5; }
+  else if (warp < 12) { role = 1; slot = 0; rw = warp - 10; }
+  else if (warp < 14) { role = 2; slot = warp - 12; rw = 0; }
+  else { role = 1; slot = 1; rw = warp - 14; }
+
+  unsigned char* sb = smem + (size_t)slot * SLOT_BYTES;
+  uint64_t* raw_full = reinterpret_cast<uint64_t*>(sb);
   uint64_t* raw_empty = raw_full + S_RAW;
   uint64_t* proc_full = raw_empty + S_RAW;
   uint64_t* proc_empty = proc_full + S_PROC;
-  Scratch* scr = reinterpret_cast<Scratch*>(smem + 128);
+  Scratch* scr = reinterpret_cast<Scratch*>(sb + 128);
+  unsigned char* raw_base = sb + SLOT_CTRL;
+  unsigned char* proc_base = raw_base + S_RAW * RAW_SLOT;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t aidx = blockIdx.x / p.T;
-  const int tti = blockIdx.x - (int)(aidx * p.T);
-  const TaskType tt = p.tt[tti];
-  const int cell = p.cell_order[aidx];
-  const int64_t e0 = p.cell_ptr[cell], e1 = p.cell_ptr[cell + 1];
-  const int nst = (int)((e1 - e0 + NB - 1) / NB);
-  const bool tri = tt.flags & TF_TRI;
-  const bool same = tri;
-  const int nj = tt.nj, nk = tt.nk;
-  const SmemLayout L = make_layout(nj, nk, same, p.UQ);
-  const int ntj = nj / TILE, ntk = nk / TILE;
-  const int ntiles = tri ? ntj * (ntj + 1) / 2 : ntj * ntk;
-  const int ncw_active = (ntiles + 31) / 32;
-
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < NSLOT) {
+    unsigned char* b = smem + (size_t)threadIdx.x * SLOT_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b);
     for (int s = 0; s < S_RAW; ++s) {
-      mbar_init(&raw_full[s], 1);
-      mbar_init(&raw_empty[s], NTW);
+      mbar_init(&bars[s], 1);
+      mbar_init(&bars[S_RAW + s], NTW);
     }
     for (int s = 0; s < S_PROC; ++s) {
-      mbar_init(&proc_full[s], NTW);
-      mbar_init(&proc_empty[s], ncw_active);
+      mbar_init(&bars[2 * S_RAW + s], NTW);
+      mbar_init(&bars[2 * S_RAW + S_PROC + s], NCW);
     }
-    scr->ncand = 0;
+    reinterpret_cast<Scratch*>(b + 128)->ncand = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
 
-  unsigned char* raw_base = smem + L.off_raw;
-  unsigned char* proc_base = smem + L.off_proc;
+  const int NS = (int)gridDim.x * NSLOT;
+  const int u = (int)blockIdx.x * NSLOT + slot;
+  uint32_t git = 0;   // stages issued so far in this slot (same sequence in every role)
+  TaskInfo ti;
 
-  if (warp == NCW + NTW) {
+  if (role == 2) {
     // =============================== loader warp ===============================================
-    const uint32_t per_entry = L.rowj_bytes + L.rowk_bytes + 32u + (uint32_t)p.UQ * 8u;
+    const int sub = lane & 7, kind = lane >> 3;   // kind 0: GP rows + gp0, 1: record head, 2: record plane
     const int64_t rowstride = (int64_t)p.nvp * 3;   // floats
-    for (int it = 0; it < nst; ++it) {
-      const int slot = it % S_RAW;
-      const uint32_t ph = (uint32_t)(it / S_RAW) & 1u;
-      const int64_t eb = e0 + (int64_t)it * NB;
-      const int nvalid = (int)min((int64_t)NB, e1 - eb);
-      int snp = 0;
-      if (lane < nvalid) snp = __ldg(p.ent_snp + eb + lane);
-      mbar_wait(&raw_empty[slot], ph ^ 1u);
-      unsigned char* rs = raw_base + (size_t)slot * L.raw_slot_bytes;
-      if (lane == 0) mbar_expect_tx(&raw_full[slot], (uint32_t)nvalid * per_entry);
-      __syncwarp();
-      if (lane < nvalid) {
-        const float* row = p.gp + (int64_t)snp * rowstride;
-        bulk_g2s(rs + L.off_gpj + lane * L.rowj_bytes, row + tt.j0 * 3, L.rowj_bytes, &raw_full[slot]);
-        if (!same)
-          bulk_g2s(rs + L.off_gpk + lane * L.rowk_bytes, row + tt.k0 * 3, L.rowk_bytes, &raw_full[slot]);
-        bulk_g2s(rs + L.off_gp0 + lane * 32, p.gp0 + (int64_t)snp * 4, 32u, &raw_full[slot]);
-      }
-      if (lane == 0)
-        bulk_g2s(rs + L.off_q, p.entq + eb * p.UQ, (uint32_t)nvalid * (uint32_t)p.UQ * 8u, &raw_full[slot]);
-    }
-  } else if (warp >= NCW) {
-    // =============================== transform warps ===========================================
-    const int tl = (warp - NCW) * 32 + lane;        // sample slot on each side
-    const bool do_j = tl < nj, do_k = tl < nk;
-    const bool extras = (tt.flags & TF_EXTRAS) && do_k;
-    const bool scal = (tt.flags & (TF_SCALARS | TF_L00)) && tl == 0;
-    const bool k_valid = (tt.k0 + tl) < p.nv;
-    double PA = 1.0, PB = 1.0, P1 = 1.0;            // running products (extras)
-    int eA = 0, eB = 0, e1x = 0;
-    double PS0 = 1.0, PS1 = 1.0, PS2 = 1.0;         // scalars: llk0s, llks00[sep], llks00[n]
-    int eS0 = 0, eS1 = 0, eS2 = 0;
-    int nflush = 0;
-    const int gj = tl >> 2, pj = tl & 3;
-    for (int it = 0; it < nst; ++it) {
-      const int rslot = it % S_RAW, pslot = it % S_PROC;
-      const uint32_t rph = (uint32_t)(it / S_RAW) & 1u, pph = (uint32_t)(it / S_PROC) & 1u;
-      const int nvalid = (int)min((int64_t)NB, e1 - (e0 + (int64_t)it * NB));
-      mbar_wait(&raw_full[rslot], rph);
-      mbar_wait(&proc_empty[pslot], pph ^ 1u);
-      const unsigned char* rs = raw_base + (size_t)rslot * L.raw_slot_bytes;
-      double* pa = reinterpret_cast<double*>(proc_base + (size_t)pslot * L.proc_slot_bytes);
-      double* pw = pa + NB * L.ent_a_dbl;
-#pragma unroll 2
-      for (int e = 0; e < NB; ++e) {
-        double* ad = pa + e * L.ent_a_dbl + gj * GRP_DBL + pj * 3;
-        double* wd = pw + e * L.ent_w_dbl + gj * GRP_DBL + pj * 3;
-        if (e < nvalid) {
-          const double* q = reinterpret_cast<const double*>(rs + L.off_q) + e * p.UQ;
-          const float* gkf = reinterpret_cast<const float*>(rs + (same ? L.off_gpj : L.off_gpk) +
-                                                            e * (same ? L.rowj_bytes : L.rowk_bytes));
-          double g0 = 0, g1 = 0, g2 = 0;
-          if (do_k) {
-            g0 = (double)gkf[tl * 3];
-            g1 = (double)gkf[tl * 3 + 1];
-            g2 = (double)gkf[tl * 3 + 2];
-            const double q00 = q[tt.qidx[0]], q01 = q[tt.qidx[1]], q02 = q[tt.qidx[2]];
-            const double q10 = q[tt.qidx[3]], q11 = q[tt.qidx[4]], q12 = q[tt.qidx[5]];
-            const double q20 = q[tt.qidx[6]], q21 = q[tt.qidx[7]], q22 = q[tt.qidx[8]];
-            wd[0] = fma(q02, g2, fma(q01, g1, q00 * g0));
-            wd[1] = fma(q12, g2, fma(q11, g1, q10 * g0));
-            wd[2] = fma(q22, g2, fma(q21, g1, q20 * g0));
+    for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
+      const TaskType tt = p.tt[ti.tti];
+      const bool same = tt.flags & TF_TRI;
+      const bool need_head = tt.flags & (TF_EXTRAS | TF_SCALARS);
+      const bool need_z = tt.flags & (TF_SCALARS | TF_L00);
+      const uint32_t rowj = (uint32_t)tt.nj * 12u, rowk = same ? 0u : (uint32_t)tt.nk * 12u;
+      const uint32_t per_entry = rowj + rowk + (need_z ? 32u : 0u) + (need_head ? 48u : 0u) + 80u;
+      for (int it = 0; it < ti.nst; ++it, ++git) {
+        const int rslot = git % S_RAW;
+        const uint32_t ph = (git / S_RAW) & 1u;
+        const int64_t eb = ti.e0 + (int64_t)it * NB;
+        const int nvalid = (int)min((int64_t)NB, ti.e1 - eb);
+        const bool mine = sub < nvalid && kind < 3;
+        int snp = 0;
+        if (mine && kind == 0) snp = __ldg(p.ent_snp + eb + sub);
+        mbar_wait(&raw_empty[rslot], ph ^ 1u);
+        unsigned char* rs = raw_base + (size_t)rslot * RAW_SLOT;
+        if (lane == 0) mbar_expect_tx(&raw_full[rslot], (uint32_t)nvalid * per_entry);
+        __syncwarp();
+        if (mine) {
+          if (kind == 0) {
+            const float* row = p.gp + (int64_t)snp * rowstride;
+            bulk_g2s(rs + OFF_GPJ + sub * ROWJ_STRIDE, row + tt.j0 * 3, rowj, &raw_full[rslot]);
+            if (!same) bulk_g2s(rs + OFF_GPK + sub * ROWK_STRIDE, row + tt.k0 * 3, rowk, &raw_full[rslot]);
+            if (need_z) bulk_g2s(rs + OFF_GP0 + sub * 32, p.gp0 + (int64_t)snp * 4, 32u, &raw_full[rslot]);
+          } else if (kind == 1) {
+            if (need_head) bulk_g2s(rs + OFF_Q + sub * Q_STRIDE, p.entq + (eb + sub) * p.UQ, 48u, &raw_full[rslot]);
+          } else {
+            bulk_g2s(rs + OFF_Q + sub * Q_STRIDE + 48, p.entq + (eb + sub) * p.UQ + tt.qoff, 80u, &raw_full[rslot]);
           }
-          if (do_j) {
-            if (same) {
-              ad[0] = g0; ad[1] = g1; ad[2] = g2;
-            } else {
-              const float* gjf = reinterpret_cast<const float*>(rs + L.off_gpj + e * L.rowj_bytes);
-              ad[0] = (double)gjf[tl * 3];
-              ad[1] = (double)gjf[tl * 3 + 1];
-              ad[2] = (double)gjf[tl * 3 + 2];
-            }
-          }
-          if (extras && k_valid) {
-            if (p.sep0) PA *= fma(q[p.fidx[2]], g2, fma(q[p.fidx[1]], g1, q[p.fidx[0]] * g0));
-            PB *= (g0 + g1) + g2;
-            if (p.want_single) P1 *= fma(q[p.U + 2], g2, fma(q[p.U + 1], g1, q[p.U] * g0));
-          }
-          if (scal) {
-            const double* z = reinterpret_cast<const double*>(rs + L.off_gp0) + e * 4;
-            const double z0 = z[0], z1 = z[1], z2 = z[2];
-            if (tt.flags & TF_SCALARS) {
-              if (p.want_single) PS0 *= fma(q[p.U + 2], z2, fma(q[p.U + 1], z1, q[p.U] * z0));   // :459
-              if (p.sep0)
-                PS1 *= fma(q[p.fidx[2]], z2, fma(q[p.fidx[1]], z1, q[p.fidx[0]] * z0)) * ((z0 + z1) + z2);
-            }
-            if (tt.flags & TF_L00) {                                                            // :700-709
-              const double t0 = fma(q[tt.qidx[2]], z2, fma(q[tt.qidx[1]], z1, q[tt.qidx[0]] * z0));
-              const double t1 = fma(q[tt.qidx[5]], z2, fma(q[tt.qidx[4]], z1, q[tt.qidx[3]] * z0));
-              const double t2 = fma(q[tt.qidx[8]], z2, fma(q[tt.qidx[7]], z1, q[tt.qidx[6]] * z0));
-              PS2 *= fma(z2, t2, fma(z1, t1, z0 * t0));
-            }
-          }
-        } else {   // identity entry: S = 1 for every hypothesis
-          if (do_k) { wd[0] = 1.0; wd[1] = 0.0; wd[2] = 0.0; }
-          if (do_j) { ad[0] = 1.0; ad[1] = 0.0; ad[2] = 0.0; }
         }
       }
-      if ((it % FLUSH_STAGES) == FLUSH_STAGES - 1) {
-        peel(PA, eA); peel(PB, eB); peel(P1, e1x);
-        peel(PS0, eS0); peel(PS1, eS1); peel(PS2, eS2);
-        ++nflush;
-      }
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&proc_full[pslot]);
-        mbar_arrive(&raw_empty[rslot]);
-      }
     }
-    if (extras && k_valid) {
-      const int k = tt.k0 + tl;
-      if (p.sep0) p.singA[(int64_t)cell * p.nv + k] = unpeel_log(PA, eA, nflush);
-      p.lb[(int64_t)cell * p.nv + k] = unpeel_log(PB, eB, nflush);
-      if (p.want_single) p.p1[(int64_t)cell * p.nv + k] = unpeel_log(P1, e1x, nflush);
-    }
-    if (scal) {
-      if (tt.flags & TF_SCALARS) {
-        if (p.want_single) p.p1_0[cell] = unpeel_log(PS0, eS0, nflush);
-        if (p.sep0) p.l00[(int64_t)cell * p.nA] = unpeel_log(PS1, eS1, nflush);
+  } else if (role == 1) {
+    // =============================== transform warps ===========================================
+    const int tl = rw * 32 + lane;        // sample slot on each side
+    for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
+      const TaskType tt = p.tt[ti.tti];
+      const bool same = tt.flags & TF_TRI;
+      const bool do_j = tl < tt.nj, do_k = tl < tt.nk;
+      const bool k_valid = (tt.k0 + tl) < p.nv;
+      const bool extras = (tt.flags & TF_EXTRAS) && do_k && k_valid;
+      const bool scal = (tt.flags & (TF_SCALARS | TF_L00)) && rw == 0 && lane < NB;
+      double PA = 1.0, PB = 1.0, P1 = 1.0;            // running products (extras)
+      int eA = 0, eB = 0, e1x = 0;
+      double PS0 = 1.0, PS1 = 1.0, PS2 = 1.0;         // scalars: llk0s, llks00[sep], llks00[n]; lane = entry slot
+      int eS0 = 0, eS1 = 0, eS2 = 0;
+      int nflush = 0;
+      for (int it = 0; it < ti.nst; ++it, ++git) {
+        const int rslot = git % S_RAW, pslot = git % S_PROC;
+        const uint32_t rph = (git / S_RAW) & 1u, pph = (git / S_PROC) & 1u;
+        const int nvalid = (int)min((int64_t)NB, ti.e1 - (ti.e0 + (int64_t)it * NB));
+        mbar_wait(&raw_full[rslot], rph);
+        mbar_wait(&proc_empty[pslot], pph ^ 1u);
+        const unsigned char* rs = raw_base + (size_t)rslot * RAW_SLOT;
+        double* pa = reinterpret_cast<double*>(proc_base + (size_t)pslot * PROC_SLOT);
+        if (nvalid == NB) {
+          if (same) transform_stage<true, true>(rs, pa, tl, nvalid, do_j, do_k, extras, p.sep0, p.want_single, PA, PB, P1);
+          else transform_stage<false, true>(rs, pa, tl, nvalid, do_j, do_k, extras, p.sep0, p.want_single, PA, PB, P1);
+        } else {
+          if (same) transform_stage<true, false>(rs, pa, tl, nvalid, do_j, do_k, extras, p.sep0, p.want_single, PA, PB, P1);
+          else transform_stage<false, false>(rs, pa, tl, nvalid, do_j, do_k, extras, p.sep0, p.want_single, PA, PB, P1);
+        }
+        if (scal && lane < nvalid) {
+          const double* z = reinterpret_cast<const double*>(rs + OFF_GP0) + lane * 4;
+          const double* q = reinterpret_cast<const double*>(rs + OFF_Q) + lane * (QHEAD + QPLANE);
+          const double z0 = z[0], z1 = z[1], z2 = z[2];
+          if (tt.flags & TF_SCALARS) {
+            if (p.want_single) PS0 *= fma(q[2], z2, fma(q[1], z1, q[0] * z0));                       // :459
+            if (p.sep0) PS1 *= fma(q[5], z2, fma(q[4], z1, q[3] * z0)) * ((z0 + z1) + z2);
+          }
+          if (tt.flags & TF_L00) {                                                                   // :700-709
+            const double t0 = fma(q[8], z2, fma(q[7], z1, q[6] * z0));
+            const double t1 = fma(q[11], z2, fma(q[10], z1, q[9] * z0));
+            const double t2 = fma(q[14], z2, fma(q[13], z1, q[12] * z0));
+            PS2 *= fma(z2, t2, fma(z1, t1, z0 * t0));
+          }
+        }
+        if ((it % FLUSH_STAGES) == FLUSH_STAGES - 1) {
+          peel(PA, eA); peel(PB, eB); peel(P1, e1x);
+          peel(PS0, eS0); peel(PS1, eS1); peel(PS2, eS2);
+          ++nflush;
+        }
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&proc_full[pslot]);
+          mbar_arrive(&raw_empty[rslot]);
+        }
       }
-      if (tt.flags & TF_L00) p.l00[(int64_t)cell * p.nA + tt.n] = unpeel_log(PS2, eS2, nflush);
+      if (extras) {
+        const int k = tt.k0 + tl;
+        if (p.sep0) p.singA[(int64_t)ti.cell * p.nv + k] = unpeel_log(PA, eA, nflush);
+        p.lb[(int64_t)ti.cell * p.nv + k] = unpeel_log(PB, eB, nflush);
+        if (p.want_single) p.p1[(int64_t)ti.cell * p.nv + k] = unpeel_log(P1, e1x, nflush);
+      }
+      if ((tt.flags & (TF_SCALARS | TF_L00)) && rw == 0) {
+        // each of the first NB lanes holds the product over "its" entries of every stage
+        double s0 = scal ? unpeel_log(PS0, eS0, nflush) : 0.0;
+        double s1 = scal ? unpeel_log(PS1, eS1, nflush) : 0.0;
+        double s2 = scal ? unpeel_log(PS2, eS2, nflush) : 0.0;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+          s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (lane == 0) {
+          if (tt.flags & TF_SCALARS) {
+            if (p.want_single) p.p1_0[ti.cell] = s0;
+            if (p.sep0) p.l00[(int64_t)ti.cell * p.nA] = s1;
+          }
+          if (tt.flags & TF_L00) p.l00[(int64_t)ti.cell * p.nA + tt.n] = s2;
+        }
+      }
     }
   } else {
     // =============================== consumer warps ============================================
-    const int t = warp * 32 + lane;
-    const bool lane_active = t < ntiles;
-    int tj = 0, tk = 0;
-    if (lane_active) {
-      if (tri) {
-        int rem = t, row = 0;
-        while (rem >= ntj - row) { rem -= ntj - row; ++row; }
-        tj = row; tk = row + rem;
-      } else {
-        tj = t / ntk; tk = t - tj * ntk;
-      }
-    }
-    double acc[TILE][TILE];
-    int es[TILE][TILE];
-#pragma unroll
-    for (int a = 0; a < TILE; ++a)
-#pragma unroll
-      for (int b = 0; b < TILE; ++b) { acc[a][b] = 1.0; es[a][b] = 0; }
-    int nflush = 0;
-    if (warp < ncw_active) {
-      for (int it = 0; it < nst; ++it) {
-        const int pslot = it % S_PROC;
-        const uint32_t pph = (uint32_t)(it / S_PROC) & 1u;
-        mbar_wait(&proc_full[pslot], pph);
-        const double* pa = reinterpret_cast<const double*>(proc_base + (size_t)pslot * L.proc_slot_bytes);
-        const double* pw = pa + NB * L.ent_a_dbl;
-        const double* ap = pa + tj * GRP_DBL;
-        const double* wp = pw + tk * GRP_DBL;
-#pragma unroll 2
-        for (int e = 0; e < NB; ++e) {
-          double a[12], w[12];
-          const double2* a2 = reinterpret_cast<const double2*>(ap + e * L.ent_a_dbl);
-          const double2* w2 = reinterpret_cast<const double2*>(wp + e * L.ent_w_dbl);
-#pragma unroll
-          for (int i = 0; i < 6; ++i) {
-            const double2 x = a2[i], y = w2[i];
-            a[2 * i] = x.x; a[2 * i + 1] = x.y;
-            w[2 * i] = y.x; w[2 * i + 1] = y.y;
-          }
-#pragma unroll
-          for (int jj = 0; jj < TILE; ++jj)
-#pragma unroll
-            for (int kk = 0; kk < TILE; ++kk) {
-              const double s = fma(a[jj * 3 + 2], w[kk * 3 + 2],
-                                   fma(a[jj * 3 + 1], w[kk * 3 + 1], a[jj * 3] * w[kk * 3]));
-              acc[jj][kk] *= s;
-            }
+    const int t = rw * 32 + lane;
+    for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
+      const TaskType tt = p.tt[ti.tti];
+      const bool tri = tt.flags & TF_TRI;
+      const int ntj = tt.nj / TILE, ntk = tt.nk / TILE;
+      const int ntiles = tri ? ntj * (ntj + 1) / 2 : ntj * ntk;
+      const bool lane_active = t < ntiles;
+      const bool warp_active = rw * 32 < ntiles;
+      int tj = 0, tk = 0;
+      if (lane_active) {
+        if (tri) {
+          int rem = t, row = 0;
+          while (rem >= ntj - row) { rem -= ntj - row; ++row; }
+          tj = row; tk = row + rem;
+        } else {
+          tj = t / ntk; tk = t - tj * ntk;
         }
-        if ((it % FLUSH_STAGES) == FLUSH_STAGES - 1) {
+      }
+      double acc[TILE][TILE];
+      int es[TILE][TILE];
 #pragma unroll
-          for (int jj = 0; jj < TILE; ++jj)
+      for (int a = 0; a < TILE; ++a)
 #pragma unroll
-            for (int kk = 0; kk < TILE; ++kk) peel(acc[jj][kk], es[jj][kk]);
-          ++nflush;
+        for (int b = 0; b < TILE; ++b) { acc[a][b] = 1.0; es[a][b] = 0; }
+      int nflush = 0;
+      for (int it = 0; it < ti.nst; ++it, ++git) {
+        const int pslot = git % S_PROC;
+        const uint32_t pph = (git / S_PROC) & 1u;
+        mbar_wait(&proc_full[pslot], pph);
+        if (warp_active) {
+          const double* pa = reinterpret_cast<const double*>(proc_base + (size_t)pslot * PROC_SLOT);
+          const double* ap = pa + tj * GRP_DBL;
+          const double* wp = pa + NB * ENT_DBL + tk * GRP_DBL;
+#pragma unroll 2
+          for (int e = 0; e < NB; ++e) {
+            double a[12], w[12];
+            const double2* a2 = reinterpret_cast<const double2*>(ap + e * ENT_DBL);
+            const double2* w2 = reinterpret_cast<const double2*>(wp + e * ENT_DBL);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+              const double2 x = a2[i], y = w2[i];
+              a[2 * i] = x.x; a[2 * i + 1] = x.y;
+              w[2 * i] = y.x; w[2 * i + 1] = y.y;
+            }
+#pragma unroll
+            for (int jj = 0; jj < TILE; ++jj)
+#pragma unroll
+              for (int kk = 0; kk < TILE; ++kk) {
+                const double s = fma(a[jj * 3 + 2], w[kk * 3 + 2],
+                                     fma(a[jj * 3 + 1], w[kk * 3 + 1], a[jj * 3] * w[kk * 3]));
+                acc[jj][kk] *= s;
+              }
+          }
+          if ((it % FLUSH_STAGES) == FLUSH_STAGES - 1) {
+#pragma unroll
+            for (int jj = 0; jj < TILE; ++jj)
+#pragma unroll
+              for (int kk = 0; kk < TILE; ++kk) peel(acc[jj][kk], es[jj][kk]);
+            ++nflush;
+          }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&proc_empty[pslot]);
       }
-    }
-    // ---- per-task reductions (:712-734, :799-814) ---------------------------------------------
-    const bool sym = tt.flags & TF_SYM;
-    const bool noarg = tt.flags & TF_NOARG;
-    double v[TILE][TILE];
-    uint32_t vmask = 0;
-    double m_all = -INFINITY, best = -INFINITY;
+      // ---- per-task reductions (:712-734, :799-814) ---------------------------------------------
+      const bool sym = tt.flags & TF_SYM;
+      const bool noarg = tt.flags & TF_NOARG;
+      double v[TILE][TILE];
+      uint32_t vmask = 0;
+      double m_all = -INFINITY, best = -INFINITY;
 #pragma unroll
-    for (int jj = 0; jj < TILE; ++jj)
+      for (int jj = 0; jj < TILE; ++jj)
 #pragma unroll
-      for (int kk = 0; kk < TILE; ++kk) {
-        const int j = tt.j0 + tj * TILE + jj, k = tt.k0 + tk * TILE + kk;
-        const bool valid = lane_active && j < p.nv && k < p.nv && (!tri || tj < tk || jj <= kk);
-        const double x = valid ? unpeel_log(acc[jj][kk], es[jj][kk], nflush) : -INFINITY;
-        v[jj][kk] = x;
-        if (valid) vmask |= 1u << (jj * TILE + kk);
-        m_all = fmax(m_all, x);
-        if (j != k) best = fmax(best, x);
+        for (int kk = 0; kk < TILE; ++kk) {
+          const int j = tt.j0 + tj * TILE + jj, k = tt.k0 + tk * TILE + kk;
+          const bool valid = lane_active && j < p.nv && k < p.nv && (!tri || tj < tk || jj <= kk);
+          const double x = valid ? unpeel_log(acc[jj][kk], es[jj][kk], nflush) : -INFINITY;
+          v[jj][kk] = x;
+          if (valid) vmask |= 1u << (jj * TILE + kk);
+          m_all = fmax(m_all, x);
+          if (j != k) best = fmax(best, x);
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        m_all = fmax(m_all, __shfl_xor_sync(0xffffffffu, m_all, o));
+        best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
       }
+      if (lane == 0) { scr->red[0][rw] = m_all; scr->red[1][rw] = best; }
+      consumer_bar_sync(slot);
+      m_all = scr->red[0][0]; best = scr->red[1][0];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      m_all = fmax(m_all, __shfl_xor_sync(0xffffffffu, m_all, o));
-      best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
-    }
-    if (lane == 0) { scr->red[0][warp] = m_all; scr->red[1][warp] = best; }
-    consumer_bar_sync();
-    m_all = scr->red[0][0]; best = scr->red[1][0];
+      for (int wq = 1; wq < NCW; ++wq) {
+        m_all = fmax(m_all, scr->red[0][wq]);
+        best = fmax(best, scr->red[1][wq]);
+      }
+      const double thr = best - p.eps_rel * fmax(1.0, fabs(best));
+      double sd = 0.0;
 #pragma unroll
-    for (int wq = 1; wq < NCW; ++wq) {
-      m_all = fmax(m_all, scr->red[0][wq]);
-      best = fmax(best, scr->red[1][wq]);
-    }
-    const double thr = best - p.eps_rel * fmax(1.0, fabs(best));
-    double sd = 0.0;
+      for (int jj = 0; jj < TILE; ++jj)
 #pragma unroll
-    for (int jj = 0; jj < TILE; ++jj)
-#pragma unroll
-      for (int kk = 0; kk < TILE; ++kk) {
-        if (!(vmask & (1u << (jj * TILE + kk)))) continue;
-        const int j = tt.j0 + tj * TILE + jj, k = tt.k0 + tk * TILE + kk;
-        const double x = v[jj][kk];
-        if (j != k) {
-          sd += exp(x - m_all);
-          if (!noarg && x >= thr) {
-            const int slot = atomicAdd(&scr->ncand, 1);
-            if (slot < MAX_CAND) scr->cand[slot] = (uint32_t)j | ((uint32_t)k << 12);
+        for (int kk = 0; kk < TILE; ++kk) {
+          if (!(vmask & (1u << (jj * TILE + kk)))) continue;
+          const int j = tt.j0 + tj * TILE + jj, k = tt.k0 + tk * TILE + kk;
+          const double x = v[jj][kk];
+          if (j != k) {
+            sd += exp(x - m_all);
+            if (!noarg && x >= thr) {
+              const int cs = atomicAdd(&scr->ncand, 1);
+              if (cs < MAX_CAND) scr->cand[cs] = (uint32_t)j | ((uint32_t)k << 12);
+            }
+          }
+          // row k = 0 of the plane (LLK10 / LLK20, :824-825; singlets when plane 0 is dense)
+          if (sym) {
+            if (j == 0) p.row0[((int64_t)ti.cell * p.nA + tt.n) * p.nv + k] = x;
+          } else if (k == 0) {
+            p.row0[((int64_t)ti.cell * p.nA + tt.n) * p.nv + j] = x;
+          }
+          if (p.dense) {
+            double* d = p.dense + ti.aidx * p.nv * p.nv * p.nA;
+            d[((int64_t)j * p.nv + k) * p.nA + tt.n] = x;
+            if (sym) d[((int64_t)k * p.nv + j) * p.nA + tt.n] = x;
           }
         }
-        // row k = 0 of the plane (LLK10 / LLK20, :824-825; singlets when plane 0 is dense)
-        if (sym) {
-          if (j == 0) p.row0[((int64_t)cell * p.nA + tt.n) * p.nv + k] = x;
-        } else if (k == 0) {
-          p.row0[((int64_t)cell * p.nA + tt.n) * p.nv + j] = x;
-        }
-        if (p.dense) {
-          double* d = p.dense + (int64_t)aidx * p.nv * p.nv * p.nA;
-          d[((int64_t)j * p.nv + k) * p.nA + tt.n] = x;
-          if (sym) d[((int64_t)k * p.nv + j) * p.nA + tt.n] = x;
-        }
-      }
-    if (sym) sd *= 2.0;
+      if (sym) sd *= 2.0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
-    consumer_bar_sync();   // everyone has read red[] before it is reused
-    if (lane == 0) scr->red[0][warp] = sd;
-    consumer_bar_sync();
-    if (t == 0) {
-      double tot = 0.0;
-      for (int wq = 0; wq < NCW; ++wq) tot += scr->red[0][wq];
-      Part* out = p.parts + aidx * p.T + tti;
-      out->m_all = m_all;
-      out->sd = tot;
-      out->best_v = best;
-      out->ncand = scr->ncand;
-      out->pad = 0;
-      for (int c = 0; c < MAX_CAND; ++c) out->cand[c] = scr->cand[c];
+      for (int o = 16; o > 0; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
+      if (lane == 0) scr->red2[rw] = sd;
+      consumer_bar_sync(slot);
+      if (t == 0) {
+        double tot = 0.0;
+        for (int wq = 0; wq < NCW; ++wq) tot += scr->red2[wq];
+        Part* out = p.parts + ti.aidx * p.T + ti.tti;
+        out->m_all = m_all;
+        out->sd = tot;
+        out->best_v = best;
+        out->ncand = scr->ncand;
+        out->pad = 0;
+        for (int c = 0; c < MAX_CAND; ++c) out->cand[c] = scr->cand[c];
+        scr->ncand = 0;
+      }
+      consumer_bar_sync(slot);
     }
   }
 }
 
-size_t pair_scan_smem_bytes(const ScanParams& p, bool /*fp32*/) {
-  // worst case over the two task shapes (tri 64 x 64 and rect 64 x 32), clipped to nvp
-  const int nj = p.nvp < BLK ? p.nvp : BLK;
-  const int nk = p.nvp < BLK_RECT_K ? p.nvp : BLK_RECT_K;
-  const SmemLayout a = make_layout(nj, nj, true, p.UQ);
-  const SmemLayout b = make_layout(nj, nk, false, p.UQ);
-  return a.total > b.total ? a.total : b.total;
-}
+size_t pair_scan_smem_bytes(const ScanParams& /*p*/, bool /*fp32*/) { return (size_t)NSLOT * SLOT_BYTES; }
 
+static int g_num_sms = 0;
 int pair_scan_init() {
-  return (int)cudaFuncSetAttribute(pair_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(pair_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NSLOT * SLOT_BYTES);
+  return (int)e;
 }
 
-int launch_pair_scan(const ScanParams& p, int64_t nactive, bool fp32, void* stream) {
-  if (nactive == 0) return 0;
+int launch_pair_scan(const ScanParams& p, bool fp32, void* stream) {
+  if (p.ntasks == 0) return 0;
+  if (g_num_sms == 0) {
+    int rc = pair_scan_init();
+    if (rc) return rc;
+  }
   const size_t smem = pair_scan_smem_bytes(p, fp32);
-  const int64_t grid = nactive * p.T;
-  if (grid > 0x7fffffffLL) return (int)cudaErrorInvalidConfiguration;
+  int64_t grid = (p.ntasks + NSLOT - 1) / NSLOT;
+  if (grid > g_num_sms) grid = g_num_sms;
   pair_scan_kernel<<<(unsigned)grid, NTHREADS, smem, (cudaStream_t)stream>>>(p);
   return (int)cudaGetLastError();
 }
@@ -614,6 +763,40 @@ __global__ void merge_kernel(const __grid_constant__ MergeParams p, int64_t nact
   o.sum_double = sdb;
   o.best_v = best;
   p.out[cell] = o;
+  if (p.lists) {
+    // hypotheses whose reference-exact value decides an output: every ordered candidate pair, and the
+    // singlets if the top two are too close to call (same windows as the host finaliser)
+    RescList* L = p.lists + cell;
+    int n = 0;
+    bool over = o.ncand > MAX_CAND;
+    if (!over && o.ncand > 1 - 1) {
+      int pairs = 0;
+      for (int c = 0; c < o.ncand; ++c) pairs += (p.mode[o.cand[c] >> 24] == PM_SYM) ? 2 : 1;
+      if (pairs > 1)
+        for (int c = 0; c < o.ncand; ++c) {
+          const uint32_t h = o.cand[c];
+          L->hyp[n++] = h;
+          if (p.mode[h >> 24] == PM_SYM) L->hyp[n++] = ((h >> 12) & 0xfffu) | ((h & 0xfffu) << 12) | (h & 0xff000000u);
+        }
+    }
+    int i1 = 0;
+    for (int j = 1; j < nv; ++j)
+      if (sing[j] > sing[i1]) i1 = j;
+    double m2 = -INFINITY;
+    for (int j = 0; j < nv; ++j)
+      if (j != i1) m2 = fmax(m2, sing[j]);
+    const double w = 2.0 * p.eps_rel * fmax(1.0, fabs(m2));
+    int close2 = 0;
+    for (int j = 0; j < nv; ++j)
+      if (j != i1 && sing[j] >= m2 - w) ++close2;
+    if (sing[i1] - m2 <= w || close2 >= 2)
+      for (int j = 0; j < nv; ++j)
+        if (sing[j] >= m2 - w) {
+          if (n < RMAX) L->hyp[n] = (uint32_t)j;   // (j, 0, 0)
+          ++n;
+        }
+    L->n = (over || n > RMAX) ? -1 : n;
+  }
 }
 
 int launch_merge(const MergeParams& p, int64_t nactive, void* stream) {
@@ -638,6 +821,78 @@ int launch_fill_sep_dense(const ScanParams& p, int64_t nactive, void* stream) {
   if (nactive == 0 || !p.sep0 || !p.dense) return 0;
   const int64_t n = nactive * p.nv * p.nv;
   fill_sep_dense_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, nactive);
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// rescore: the listed hypotheses of every cell in the reference's exact arithmetic
+// (cmd_cram_demuxlet.cpp:671-684: gpAB product, (l,m) row-major sum, log, SNP-ascending accumulation).
+// One warp per cell: lanes take 32 consecutive entries and evaluate log(S) for every listed hypothesis,
+// then lane h adds column h in entry order.
+// ---------------------------------------------------------------------------------------------
+constexpr int RESC_WARPS = 4;
+__global__ void __launch_bounds__(RESC_WARPS * 32) rescore_kernel(const __grid_constant__ RescoreParams p,
+                                                                   int64_t nactive) {
+  __shared__ double logs[RESC_WARPS][32][RMAX + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t aidx = (int64_t)blockIdx.x * RESC_WARPS + warp;
+  if (aidx >= nactive) return;
+  const int cell = p.cell_order[aidx];
+  RescList* L = p.lists + cell;
+  const int H = L->n;
+  if (H <= 0) return;
+  const uint32_t myh = lane < H ? L->hyp[lane] : 0u;
+  double acc = 0.0;
+  const int64_t e0 = p.cell_ptr[cell], e1 = p.cell_ptr[cell + 1];
+  for (int64_t base = e0; base < e1; base += 32) {
+    const int64_t e = base + lane;
+    const int cnt = (int)min((int64_t)32, e1 - base);
+    const bool valid = lane < cnt;
+    const float* g = p.gp;
+    const double* q = p.entq;
+    if (valid) {
+      g += (int64_t)__ldg(p.ent_snp + e) * p.nvp * 3;
+      q += e * p.UQ;
+    }
+    for (int h = 0; h < H; ++h) {
+      const uint32_t hy = __shfl_sync(0xffffffffu, myh, h);
+      if (valid) {
+        const int j = hy & 0xfff, k = (hy >> 12) & 0xfff, n = hy >> 24;
+        const double gj0 = (double)__ldg(g + 3 * j), gj1 = (double)__ldg(g + 3 * j + 1), gj2 = (double)__ldg(g + 3 * j + 2);
+        const double gk0 = (double)__ldg(g + 3 * k), gk1 = (double)__ldg(g + 3 * k + 1), gk2 = (double)__ldg(g + 3 * k + 2);
+        double Q[9];
+        if (p.dense_idx[n] < 0) {   // separable plane 0: Q'[0][l][m] = f[l]
+#pragma unroll
+          for (int l = 0; l < 3; ++l) Q[l * 3] = Q[l * 3 + 1] = Q[l * 3 + 2] = q[3 + l];
+        } else {
+          const double* qp = q + QHEAD + QPLANE * p.dense_idx[n];
+#pragma unroll
+          for (int i = 0; i < 9; ++i) Q[i] = qp[i];
+        }
+        double s = 0.0;
+        s = __dadd_rn(s, __dmul_rn(__dmul_rn(gj0, gk0), Q[0]));
+        s = __dadd_rn(s, __dmul_rn(__dmul_rn(gj0, gk1), Q[1]));
+        s = __dadd_rn(s, __dmul_rn(__dmul_rn(gj0, gk2), Q[2]));
+        s = __dadd_rn(s, __dmul_rn(__dmul_rn(gj1, gk0), Q[3]));
+        s = __dadd_rn(s, __dmul_rn(__dmul_rn(gj1, gk1), Q[4]));
+        s = __dadd_rn(s, __dmul_rn(__dmul_rn(gj1, gk2), Q[5]));
+        s = __dadd_rn(s, __dmul_rn(__dmul_rn(gj2, gk0), Q[6]));
+        s = __dadd_rn(s, __dmul_rn(__dmul_rn(gj2, gk1), Q[7]));
+        s = __dadd_rn(s, __dmul_rn(__dmul_rn(gj2, gk2), Q[8]));
+        logs[warp][lane][h] = glibc_log_fma(s);
+      }
+    }
+    __syncwarp();
+    if (lane < H)
+      for (int i = 0; i < cnt; ++i) acc = __dadd_rn(acc, logs[warp][i][lane]);
+    __syncwarp();
+  }
+  if (lane < H) L->val[lane] = acc;
+}
+
+int launch_rescore(const RescoreParams& p, int64_t nactive, void* stream) {
+  if (nactive == 0) return 0;
+  rescore_kernel<<<(unsigned)((nactive + RESC_WARPS - 1) / RESC_WARPS), RESC_WARPS * 32, 0, (cudaStream_t)stream>>>(p, nactive);
   return (int)cudaGetLastError();
 }
 

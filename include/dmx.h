@@ -48,6 +48,8 @@ typedef enum {
                                    instead of copying; use with dmx_alloc_host for pinned transfers */
 #define DMX_SKIP_SINGLE   0x8u  /* do not compute pass 1 (.single, :412-461); dmx_get_single then fails   */
 #define DMX_TRUST_INPUTS  0x10u /* skip the host-side range check of ent_snp against nsnps in dmx_upload  */
+#define DMX_HOST_FINALISE 0x20u /* re-score near ties on the host (libm log) even when the device re-scorer
+                                   has verified itself bit-identical to the host libm                    */
 #define DMX_FP32_PAIRS    0x4u  /* pair scan accumulates in fp32 (faster, ~1e-6 LLK error) instead
                                    of fp64; singlet, pass-1 and all re-scored values stay fp64      */
 
@@ -90,7 +92,10 @@ typedef struct {
   int64_t n_entries, n_reads, n_tasks;
   int64_t gpu_launches;        /* kernels launched by the last run                                 */
   int64_t n_rescored;          /* hypotheses re-scored exactly                                     */
-  int64_t n_fullcell;          /* cells recomputed exactly in full                                 */
+  int64_t n_fullcell;          /* cells whose candidate list overflowed (dense re-scan)            */
+  int64_t n_rescored_gpu;      /* ... of n_rescored, by the device re-scorer                       */
+  int32_t gpu_exact;           /* 1: device log() verified bit-identical to the host libm          */
+  int32_t pad_;
   double algo_bytes;           /* SURVEY 8(d) gather-model bytes of the pair kernel, last run      */
   double pair_kernel_ms;       /* CUDA-event time of the pair-scan kernel(s) alone                 */
 } dmx_stats;

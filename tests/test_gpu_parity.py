@@ -80,3 +80,23 @@ def test_rescore_is_bit_exact():
     orc, ref, d = run_both(p)
     for (c, j, k, n) in [(0, 1, 2, 1), (5, 2, 1, 1), (19, 0, 0, 0), (7, 3, 0, 0)]:
         assert d.rescore(c, j, k, n) == orc.pass2_one(c, j, k, n)
+
+
+def test_device_rescorer_matches_host_libm():
+    """the device transcription of glibc log() must be verified bit-identical to the host libm on this box,
+    and the device re-scorer must then return the very bits the host scorer (and the oracle) computes"""
+    from demuxlet_b200.api import Demuxlet
+    p = synth(300, 16, 3000, "GP", seed=21)
+    orc, ref, d = run_both(p)
+    st = d.stats()
+    assert st["gpu_exact"] == 1, "device log() differs from the host libm: device re-scorer disabled"
+    assert st["n_rescored_gpu"] == st["n_rescored"] and st["n_rescored"] >= 2 * 300
+    h = Demuxlet(p.nv, (0.0, 0.5), host_finalise=True)
+    h.set_pileup(p)
+    h.run()
+    assert h.stats()["n_rescored_gpu"] == 0
+    a, b = d.best(), h.best()
+    for f in ("sng1", "sng2", "dbl1", "dbl2", "alpha_idx", "call"):
+        assert np.array_equal(a[f], b[f]), f
+    assert np.array_equal(a["llk12"], b["llk12"])          # bit-identical doubles
+    assert np.array_equal(a["llk12"], ref["best"]["pair_llk12"])   # ... and equal to the oracle's bits
