@@ -296,8 +296,12 @@ constexpr uint32_t OFF_GPK = OFF_GPJ + NB * ROWJ_STRIDE;
 constexpr uint32_t OFF_GP0 = OFF_GPK + NB * ROWK_STRIDE;
 constexpr uint32_t OFF_Q = OFF_GP0 + NB * 32;
 constexpr uint32_t RAW_SLOT = OFF_Q + NB * Q_STRIDE;                 // 10496 B
-constexpr uint32_t ENT_DBL = (BLK / TILE) * GRP_DBL;                 // doubles per entry and side (224)
-constexpr uint32_t PROC_SLOT = NB * 2 * ENT_DBL * 8;                 // 28672 B
+// processed ring: per entry and side a 64 x 4 matrix (sample x genotype, 4th column zero) stored as 8 blocks of
+// 8 samples; inside a block the layout is column-major with the column index XOR-swizzled by the block parity,
+// so that both the transform's stores (one column, 32 consecutive samples) and the consumers' DMMA fragment
+// loads (lane -> row lane/4, column lane%4 of one block) are bank-conflict free.
+constexpr uint32_t SIDE_DBL = BLK * 4;                               // doubles per entry and side (256)
+constexpr uint32_t PROC_SLOT = NB * 2 * SIDE_DBL * 8;                // 32768 B
 constexpr uint32_t SLOT_CTRL = 512;                                  // barriers + epilogue scratch
 constexpr uint32_t SLOT_BYTES = SLOT_CTRL + S_RAW * RAW_SLOT + S_PROC * PROC_SLOT;
 static_assert(RAW_SLOT % 128 == 0 && PROC_SLOT % 128 == 0 && SLOT_BYTES % 128 == 0, "alignment");
@@ -328,53 +332,101 @@ __device__ __forceinline__ bool next_task(const ScanParams& p, int r, int u, int
   return true;
 }
 
-// one stage of the transform for lane `tl` (sample slot on each side)
-template <bool SAME, bool FULL>
+// one stage of the transform for lane `tl` (sample slot on each side).  No lane-dependent branches: lanes
+// beyond the task's sample count work on padding (their ring slots are never read), so the compiler can
+// batch the shared-memory loads of several entries.
+template <bool SAME, bool FULL, bool EXTRAS>
 __device__ __forceinline__ void transform_stage(const unsigned char* __restrict__ rs, double* __restrict__ pa,
-                                                int tl, int nvalid, bool do_j, bool do_k, bool extras, bool sep0,
-                                                bool want_single, double& PA, double& PB, double& P1) {
-  const int grp = tl >> 2, pos = tl & 3;
-  double* ad = pa + grp * GRP_DBL + pos * 3;
-  double* wd = ad + NB * ENT_DBL;
+                                                int tl, int nvalid, double& PA, double& PB, double& P1) {
+  const int blk = tl >> 3, sw = blk & 1;
+  double* ad = pa + blk * 32 + (tl & 7);
+  double* wd = ad + NB * SIDE_DBL;
+  const int c0 = (0 ^ sw) * 8, c1 = (1 ^ sw) * 8, c2 = (2 ^ sw) * 8;
   const float* gj = reinterpret_cast<const float*>(rs + OFF_GPJ) + tl * 3;
-  const float* gk = SAME ? gj : reinterpret_cast<const float*>(rs + OFF_GPK) + tl * 3;
+  const float* gk = SAME ? gj : reinterpret_cast<const float*>(rs + OFF_GPK) + (tl & (BLK_RECT_K - 1)) * 3;
   constexpr int GK_STRIDE = SAME ? ROWJ_STRIDE / 4 : ROWK_STRIDE / 4;
   const double2* q2 = reinterpret_cast<const double2*>(rs + OFF_Q);
 #pragma unroll
   for (int e = 0; e < NB; ++e) {
     if (FULL || e < nvalid) {
-      double g0 = 0, g1 = 0, g2 = 0;
-      if (do_k) {
-        g0 = (double)gk[e * GK_STRIDE];
-        g1 = (double)gk[e * GK_STRIDE + 1];
-        g2 = (double)gk[e * GK_STRIDE + 2];
-        const double2 qa = q2[e * 8 + 3], qb = q2[e * 8 + 4], qc = q2[e * 8 + 5], qd = q2[e * 8 + 6];
-        const double q22 = reinterpret_cast<const double*>(q2 + e * 8 + 7)[0];
-        // Q'[l][m] row-major: qa = (00, 01), qb = (02, 10), qc = (11, 12), qd = (20, 21), q22
-        wd[e * ENT_DBL + 0] = fma(qb.x, g2, fma(qa.y, g1, qa.x * g0));
-        wd[e * ENT_DBL + 1] = fma(qc.y, g2, fma(qc.x, g1, qb.y * g0));
-        wd[e * ENT_DBL + 2] = fma(q22, g2, fma(qd.y, g1, qd.x * g0));
-        if (extras) {
-          const double2 h0 = q2[e * 8], h1 = q2[e * 8 + 1], h2 = q2[e * 8 + 2];   // GL0 GL1 | GL2 f0 | f1 f2
-          if (sep0) PA *= fma(h2.y, g2, fma(h2.x, g1, h1.y * g0));
-          PB *= (g0 + g1) + g2;
-          if (want_single) P1 *= fma(h1.x, g2, fma(h0.y, g1, h0.x * g0));
-        }
+      const double g0 = (double)gk[e * GK_STRIDE];
+      const double g1 = (double)gk[e * GK_STRIDE + 1];
+      const double g2 = (double)gk[e * GK_STRIDE + 2];
+      const double2 qa = q2[e * 8 + 3], qb = q2[e * 8 + 4], qc = q2[e * 8 + 5], qd = q2[e * 8 + 6];
+      const double q22 = reinterpret_cast<const double*>(q2 + e * 8 + 7)[0];
+      // Q'[l][m] row-major: qa = (00, 01), qb = (02, 10), qc = (11, 12), qd = (20, 21), q22
+      wd[e * SIDE_DBL + c0] = fma(qb.x, g2, fma(qa.y, g1, qa.x * g0));
+      wd[e * SIDE_DBL + c1] = fma(qc.y, g2, fma(qc.x, g1, qb.y * g0));
+      wd[e * SIDE_DBL + c2] = fma(q22, g2, fma(qd.y, g1, qd.x * g0));
+      if (EXTRAS) {
+        const double2 h0 = q2[e * 8], h1 = q2[e * 8 + 1], h2 = q2[e * 8 + 2];   // GL0 GL1 | GL2 f0 | f1 f2
+        PA *= fma(h2.y, g2, fma(h2.x, g1, h1.y * g0));
+        PB *= (g0 + g1) + g2;
+        P1 *= fma(h1.x, g2, fma(h0.y, g1, h0.x * g0));
       }
-      if (do_j) {
-        if (SAME) {
-          ad[e * ENT_DBL + 0] = g0; ad[e * ENT_DBL + 1] = g1; ad[e * ENT_DBL + 2] = g2;
-        } else {
-          ad[e * ENT_DBL + 0] = (double)gj[e * (ROWJ_STRIDE / 4)];
-          ad[e * ENT_DBL + 1] = (double)gj[e * (ROWJ_STRIDE / 4) + 1];
-          ad[e * ENT_DBL + 2] = (double)gj[e * (ROWJ_STRIDE / 4) + 2];
-        }
+      if (SAME) {
+        ad[e * SIDE_DBL + c0] = g0; ad[e * SIDE_DBL + c1] = g1; ad[e * SIDE_DBL + c2] = g2;
+      } else {
+        ad[e * SIDE_DBL + c0] = (double)gj[e * (ROWJ_STRIDE / 4)];
+        ad[e * SIDE_DBL + c1] = (double)gj[e * (ROWJ_STRIDE / 4) + 1];
+        ad[e * SIDE_DBL + c2] = (double)gj[e * (ROWJ_STRIDE / 4) + 2];
       }
     } else {   // identity entry: S = 1 for every hypothesis
-      if (do_k) { wd[e * ENT_DBL + 0] = 1.0; wd[e * ENT_DBL + 1] = 0.0; wd[e * ENT_DBL + 2] = 0.0; }
-      if (do_j) { ad[e * ENT_DBL + 0] = 1.0; ad[e * ENT_DBL + 1] = 0.0; ad[e * ENT_DBL + 2] = 0.0; }
+      wd[e * SIDE_DBL + c0] = 1.0; wd[e * SIDE_DBL + c1] = 0.0; wd[e * SIDE_DBL + c2] = 0.0;
+      ad[e * SIDE_DBL + c0] = 1.0; ad[e * SIDE_DBL + c1] = 0.0; ad[e * SIDE_DBL + c2] = 0.0;
     }
   }
+}
+
+// D (8 x 8) = A (8 x 4, row) * B (4 x 8, col) in FP64 on the tensor cores (SASS: DMMA.8x8x4).  Fragments: lane
+// holds A[lane/4][lane%4], B[lane%4][lane/4], D[lane/4][2*(lane%4) + {0,1}].
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+               : "=d"(d0), "=d"(d1)
+               : "d"(a), "d"(b), "d"(0.0), "d"(0.0));
+}
+
+// Consumer tile shapes: a warp owns 8 tiles of 8 x 8 hypotheses built from <= 4 row blocks and <= 4 column blocks.
+//   shape 0: 2 row blocks x 4 col blocks      tile t -> (A[t >> 2], B[t & 3])
+//   shape 1: 4 row blocks x 2 col blocks      tile t -> (A[t >> 1], B[t & 1])
+//   shape 2: two groups of 2 x 2              tile t -> (A[2g + ((t >> 1) & 1)], B[2g + (t & 1)]), g = t >> 2
+template <int SHAPE> __device__ __forceinline__ constexpr int tile_ia(int t) {
+  return SHAPE == 0 ? (t >> 2) : SHAPE == 1 ? (t >> 1) : (2 * (t >> 2) + ((t >> 1) & 1));
+}
+template <int SHAPE> __device__ __forceinline__ constexpr int tile_ib(int t) {
+  return SHAPE == 0 ? (t & 3) : SHAPE == 1 ? (t & 1) : (2 * (t >> 2) + (t & 1));
+}
+constexpr int NTILE = 8;
+
+template <int SHAPE>
+__device__ __forceinline__ void consume_stage(const double* __restrict__ pa, const int (&aoff)[4], const int (&boff)[4],
+                                              uint32_t tmask, double (&acc)[NTILE][2]) {
+  constexpr int NA = SHAPE == 0 ? 2 : 4, NBF = SHAPE == 1 ? 2 : 4;
+  const double* pw = pa + NB * SIDE_DBL;
+#pragma unroll 2
+  for (int e = 0; e < NB; ++e) {
+    double af[4], bf[4];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) af[i] = pa[e * SIDE_DBL + aoff[i]];
+#pragma unroll
+    for (int i = 0; i < NBF; ++i) bf[i] = pw[e * SIDE_DBL + boff[i]];
+#pragma unroll
+    for (int t = 0; t < NTILE; ++t) {
+      if (tmask & (1u << t)) {
+        double s0, s1;
+        dmma884(s0, s1, af[tile_ia<SHAPE>(t)], bf[tile_ib<SHAPE>(t)]);
+        acc[t][0] *= s0;
+        acc[t][1] *= s1;
+      }
+    }
+  }
+}
+
+template <bool SAME, bool EXTRAS>
+__device__ __forceinline__ void transform_dispatch(const unsigned char* rs, double* pa, int tl, int nvalid,
+                                                   double& PA, double& PB, double& P1) {
+  if (nvalid == NB) transform_stage<SAME, true, EXTRAS>(rs, pa, tl, nvalid, PA, PB, P1);
+  else transform_stage<SAME, false, EXTRAS>(rs, pa, tl, nvalid, PA, PB, P1);
 }
 }  // namespace
 
@@ -412,6 +464,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_scan_kernel(const __grid_con
     reinterpret_cast<Scratch*>(b + 128)->ncand = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  // the 4th (padding) column of every A / B matrix must be 0: it is never written again
+  for (int sl = 0; sl < NSLOT; ++sl) {
+    double* pr = reinterpret_cast<double*>(smem + (size_t)sl * SLOT_BYTES + SLOT_CTRL + S_RAW * RAW_SLOT);
+    for (uint32_t i = threadIdx.x; i < S_PROC * PROC_SLOT / 8; i += NTHREADS) pr[i] = 0.0;
   }
   __syncthreads();
 
@@ -480,12 +537,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_scan_kernel(const __grid_con
         mbar_wait(&proc_empty[pslot], pph ^ 1u);
         const unsigned char* rs = raw_base + (size_t)rslot * RAW_SLOT;
         double* pa = reinterpret_cast<double*>(proc_base + (size_t)pslot * PROC_SLOT);
-        if (nvalid == NB) {
-          if (same) transform_stage<true, true>(rs, pa, tl, nvalid, do_j, do_k, extras, p.sep0, p.want_single, PA, PB, P1);
-          else transform_stage<false, true>(rs, pa, tl, nvalid, do_j, do_k, extras, p.sep0, p.want_single, PA, PB, P1);
+        if (same) {
+          if (tt.flags & TF_EXTRAS) transform_dispatch<true, true>(rs, pa, tl, nvalid, PA, PB, P1);
+          else transform_dispatch<true, false>(rs, pa, tl, nvalid, PA, PB, P1);
         } else {
-          if (same) transform_stage<true, false>(rs, pa, tl, nvalid, do_j, do_k, extras, p.sep0, p.want_single, PA, PB, P1);
-          else transform_stage<false, false>(rs, pa, tl, nvalid, do_j, do_k, extras, p.sep0, p.want_single, PA, PB, P1);
+          if (tt.flags & TF_EXTRAS) transform_dispatch<false, true>(rs, pa, tl, nvalid, PA, PB, P1);
+          else transform_dispatch<false, false>(rs, pa, tl, nvalid, PA, PB, P1);
         }
         if (scal && lane < nvalid) {
           const double* z = reinterpret_cast<const double*>(rs + OFF_GP0) + lane * 4;
@@ -541,64 +598,57 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_scan_kernel(const __grid_con
     }
   } else {
     // =============================== consumer warps ============================================
-    const int t = rw * 32 + lane;
+    const int lr = lane >> 2, lc = lane & 3;
     for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
       const TaskType tt = p.tt[ti.tti];
       const bool tri = tt.flags & TF_TRI;
-      const int ntj = tt.nj / TILE, ntk = tt.nk / TILE;
-      const int ntiles = tri ? ntj * (ntj + 1) / 2 : ntj * ntk;
-      const bool lane_active = t < ntiles;
-      const bool warp_active = rw * 32 < ntiles;
-      int tj = 0, tk = 0;
-      if (lane_active) {
-        if (tri) {
-          int rem = t, row = 0;
-          while (rem >= ntj - row) { rem -= ntj - row; ++row; }
-          tj = row; tk = row + rem;
-        } else {
-          tj = t / ntk; tk = t - tj * ntk;
-        }
+      const int nbj = (tt.nj + 7) >> 3, nbk = (tt.nk + 7) >> 3;   // 8-sample blocks on each side
+      // tile cover of the task (see the shape comment above)
+      int shape = 0, ar[4] = {0, 0, 0, 0}, bc[4] = {0, 0, 0, 0};
+      if (tri) {
+        if (rw == 0) { ar[0] = 0; ar[1] = 1; bc[0] = 0; bc[1] = 1; bc[2] = 2; bc[3] = 3; }
+        else if (rw == 1) { ar[0] = 0; ar[1] = 1; bc[0] = 4; bc[1] = 5; bc[2] = 6; bc[3] = 7; }
+        else if (rw == 2) { ar[0] = 2; ar[1] = 3; bc[0] = 2; bc[1] = 3; bc[2] = 4; bc[3] = 5; }
+        else if (rw == 3) { shape = 1; ar[0] = 2; ar[1] = 3; ar[2] = 4; ar[3] = 5; bc[0] = 6; bc[1] = 7; }
+        else { shape = 2; ar[0] = 4; ar[1] = 5; ar[2] = 6; ar[3] = 7; bc[0] = 4; bc[1] = 5; bc[2] = 6; bc[3] = 7; }
+      } else {
+        ar[0] = 2 * rw; ar[1] = 2 * rw + 1; bc[0] = 0; bc[1] = 1; bc[2] = 2; bc[3] = 3;
       }
-      double acc[TILE][TILE];
-      int es[TILE][TILE];
+      int trow[NTILE], tcol[NTILE];
+      uint32_t tmask = 0;
 #pragma unroll
-      for (int a = 0; a < TILE; ++a)
+      for (int t = 0; t < NTILE; ++t) {
+        const int ia = shape == 0 ? (t >> 2) : shape == 1 ? (t >> 1) : (2 * (t >> 2) + ((t >> 1) & 1));
+        const int ib = shape == 0 ? (t & 3) : shape == 1 ? (t & 1) : (2 * (t >> 2) + (t & 1));
+        trow[t] = ar[ia];
+        tcol[t] = bc[ib];
+        const bool ok = trow[t] < nbj && tcol[t] < nbk && (!tri || tcol[t] >= trow[t]) && (tri || rw < 4);
+        if (ok) tmask |= 1u << t;
+      }
+      // fragment offsets (doubles) inside one entry's side matrix: block * 32 + swizzled column * 8 + row
+      int aoff[4], boff[4];
 #pragma unroll
-        for (int b = 0; b < TILE; ++b) { acc[a][b] = 1.0; es[a][b] = 0; }
+      for (int i = 0; i < 4; ++i) {
+        aoff[i] = ar[i] * 32 + ((lc ^ (ar[i] & 1)) << 3) + lr;
+        boff[i] = bc[i] * 32 + ((lc ^ (bc[i] & 1)) << 3) + lr;
+      }
+      double acc[NTILE][2];
+      int es[NTILE][2];
+#pragma unroll
+      for (int t = 0; t < NTILE; ++t) { acc[t][0] = acc[t][1] = 1.0; es[t][0] = es[t][1] = 0; }
       int nflush = 0;
       for (int it = 0; it < ti.nst; ++it, ++git) {
         const int pslot = git % S_PROC;
         const uint32_t pph = (git / S_PROC) & 1u;
         mbar_wait(&proc_full[pslot], pph);
-        if (warp_active) {
+        if (tmask) {
           const double* pa = reinterpret_cast<const double*>(proc_base + (size_t)pslot * PROC_SLOT);
-          const double* ap = pa + tj * GRP_DBL;
-          const double* wp = pa + NB * ENT_DBL + tk * GRP_DBL;
-#pragma unroll 2
-          for (int e = 0; e < NB; ++e) {
-            double a[12], w[12];
-            const double2* a2 = reinterpret_cast<const double2*>(ap + e * ENT_DBL);
-            const double2* w2 = reinterpret_cast<const double2*>(wp + e * ENT_DBL);
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
-              const double2 x = a2[i], y = w2[i];
-              a[2 * i] = x.x; a[2 * i + 1] = x.y;
-              w[2 * i] = y.x; w[2 * i + 1] = y.y;
-            }
-#pragma unroll
-            for (int jj = 0; jj < TILE; ++jj)
-#pragma unroll
-              for (int kk = 0; kk < TILE; ++kk) {
-                const double s = fma(a[jj * 3 + 2], w[kk * 3 + 2],
-                                     fma(a[jj * 3 + 1], w[kk * 3 + 1], a[jj * 3] * w[kk * 3]));
-                acc[jj][kk] *= s;
-              }
-          }
+          if (shape == 0) consume_stage<0>(pa, aoff, boff, tmask, acc);
+          else if (shape == 1) consume_stage<1>(pa, aoff, boff, tmask, acc);
+          else consume_stage<2>(pa, aoff, boff, tmask, acc);
           if ((it % FLUSH_STAGES) == FLUSH_STAGES - 1) {
 #pragma unroll
-            for (int jj = 0; jj < TILE; ++jj)
-#pragma unroll
-              for (int kk = 0; kk < TILE; ++kk) peel(acc[jj][kk], es[jj][kk]);
+            for (int t = 0; t < NTILE; ++t) { peel(acc[t][0], es[t][0]); peel(acc[t][1], es[t][1]); }
             ++nflush;
           }
         }
@@ -608,18 +658,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_scan_kernel(const __grid_con
       // ---- per-task reductions (:712-734, :799-814) ---------------------------------------------
       const bool sym = tt.flags & TF_SYM;
       const bool noarg = tt.flags & TF_NOARG;
-      double v[TILE][TILE];
+      double v[NTILE][2];
       uint32_t vmask = 0;
       double m_all = -INFINITY, best = -INFINITY;
 #pragma unroll
-      for (int jj = 0; jj < TILE; ++jj)
+      for (int t = 0; t < NTILE; ++t)
 #pragma unroll
-        for (int kk = 0; kk < TILE; ++kk) {
-          const int j = tt.j0 + tj * TILE + jj, k = tt.k0 + tk * TILE + kk;
-          const bool valid = lane_active && j < p.nv && k < p.nv && (!tri || tj < tk || jj <= kk);
-          const double x = valid ? unpeel_log(acc[jj][kk], es[jj][kk], nflush) : -INFINITY;
-          v[jj][kk] = x;
-          if (valid) vmask |= 1u << (jj * TILE + kk);
+        for (int i = 0; i < 2; ++i) {
+          const int j = tt.j0 + trow[t] * 8 + lr, k = tt.k0 + tcol[t] * 8 + 2 * lc + i;
+          const bool valid = ((tmask >> t) & 1u) && j < p.nv && k < p.nv && (!tri || j <= k);
+          const double x = valid ? unpeel_log(acc[t][i], es[t][i], nflush) : -INFINITY;
+          v[t][i] = x;
+          if (valid) vmask |= 1u << (t * 2 + i);
           m_all = fmax(m_all, x);
           if (j != k) best = fmax(best, x);
         }
@@ -639,12 +689,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_scan_kernel(const __grid_con
       const double thr = best - p.eps_rel * fmax(1.0, fabs(best));
       double sd = 0.0;
 #pragma unroll
-      for (int jj = 0; jj < TILE; ++jj)
+      for (int t = 0; t < NTILE; ++t)
 #pragma unroll
-        for (int kk = 0; kk < TILE; ++kk) {
-          if (!(vmask & (1u << (jj * TILE + kk)))) continue;
-          const int j = tt.j0 + tj * TILE + jj, k = tt.k0 + tk * TILE + kk;
-          const double x = v[jj][kk];
+        for (int i = 0; i < 2; ++i) {
+          if (!(vmask & (1u << (t * 2 + i)))) continue;
+          const int j = tt.j0 + trow[t] * 8 + lr, k = tt.k0 + tcol[t] * 8 + 2 * lc + i;
+          const double x = v[t][i];
           if (j != k) {
             sd += exp(x - m_all);
             if (!noarg && x >= thr) {
@@ -669,7 +719,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_scan_kernel(const __grid_con
       for (int o = 16; o > 0; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
       if (lane == 0) scr->red2[rw] = sd;
       consumer_bar_sync(slot);
-      if (t == 0) {
+      if (rw == 0 && lane == 0) {
         double tot = 0.0;
         for (int wq = 0; wq < NCW; ++wq) tot += scr->red2[wq];
         Part* out = p.parts + ti.aidx * p.T + ti.tti;
