@@ -10,7 +10,7 @@ namespace dmx {
 constexpr int TILE = 4;        // each consumer lane owns a TILE x TILE block of (j,k) hypotheses
 constexpr int BLK = 64;        // samples per task side (16 tiles); nv > 64 is tiled over tasks
 constexpr int BLK_RECT_K = 32; // k-side samples of a rectangular task (16 x 8 tiles = 128 lanes)
-constexpr int NB = 8;          // pileup entries per pipeline stage
+constexpr int NB = 8;          // pileup entries per pipeline stage (power of two, <= 8)
 constexpr int S_RAW = 4;       // stages of the raw ring: bulk (TMA) copies -> transform warps
 constexpr int S_PROC = 2;      // stages of the processed (a, w) ring: transform -> consumer warps
 constexpr int NCW = 5;         // consumer warps per slot (136 tiles of the 64 x 64 upper triangle -> 160 lanes)
@@ -22,7 +22,7 @@ constexpr int QPLANE = 10;     // doubles per dense plane in the entry record (9
 constexpr int GRP_DBL = 14;    // doubles per 4-sample group in the processed ring (12 + 2 pad: 112 B
                                // stride spreads 16-byte lane loads over all banks)
 constexpr int GRP_F32 = 12;    // floats per 4-sample group in the fp32 processed ring (48 B stride)
-constexpr int FLUSH_STAGES = 2;   // exponent renormalisation period (stages)
+constexpr int FLUSH_STAGES = 16 / NB;   // exponent renormalisation period (stages): every 16 entries
 constexpr int MAX_CAND = 8;    // near-tie candidates kept per task / per cell
 constexpr int MAX_U = DMX_MAX_ALPHA * 6 + 3;   // distinct mixing proportions p(n,l,m)
 

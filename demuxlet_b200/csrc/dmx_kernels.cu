@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_scan_kernel(const __grid_con
 
   if (role == 2) {
     // =============================== loader warp ===============================================
-    const int sub = lane & 7, kind = lane >> 3;   // kind 0: GP rows + gp0, 1: record head, 2: record plane
+    const int sub = lane % NB, kind = lane / NB;   // kind 0: GP rows + gp0, 1: record head, 2: record plane
     const int64_t rowstride = (int64_t)p.nvp * 3;   // floats
     for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
       const TaskType tt = p.tt[ti.tti];
@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_scan_kernel(const __grid_con
     for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
       const TaskType tt = p.tt[ti.tti];
       const bool same = tt.flags & TF_TRI;
-      const bool do_j = tl < tt.nj, do_k = tl < tt.nk;
+      const bool do_k = tl < tt.nk;
       const bool k_valid = (tt.k0 + tl) < p.nv;
       const bool extras = (tt.flags & TF_EXTRAS) && do_k && k_valid;
       const bool scal = (tt.flags & (TF_SCALARS | TF_L00)) && rw == 0 && lane < NB;
@@ -582,7 +582,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_scan_kernel(const __grid_con
         double s1 = scal ? unpeel_log(PS1, eS1, nflush) : 0.0;
         double s2 = scal ? unpeel_log(PS2, eS2, nflush) : 0.0;
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
+        for (int o = NB / 2; o > 0; o >>= 1) {
           s0 += __shfl_xor_sync(0xffffffffu, s0, o);
           s1 += __shfl_xor_sync(0xffffffffu, s1, o);
           s2 += __shfl_xor_sync(0xffffffffu, s2, o);
