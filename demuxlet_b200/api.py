@@ -30,7 +30,7 @@ DMX_HOST_FINALISE = 0x20
 ABI_SYMBOLS = [
     "dmx_config_default", "dmx_device_count", "dmx_create", "dmx_destroy", "dmx_set_gp", "dmx_set_pileup",
     "dmx_upload", "dmx_compute", "dmx_run", "dmx_get_best", "dmx_get_single", "dmx_get_sing2", "dmx_get_pair",
-    "dmx_rescore", "dmx_write_outputs", "dmx_get_stats", "dmx_alloc_host", "dmx_free_host", "dmx_strerror",
+    "dmx_rescore", "dmx_exact_llk", "dmx_write_outputs", "dmx_get_stats", "dmx_alloc_host", "dmx_free_host", "dmx_strerror",
     "dmx_last_error", "dmx_abi_version",
 ]
 
@@ -120,6 +120,21 @@ def _strerror(status: int) -> str:
 
 def device_count() -> int:
     return int(load_library().dmx_device_count())
+
+
+def exact_llk(plp: Pileup, alphas: Sequence[float], cell: int, j: int, k: int, n: int) -> float:
+    """llksAB[j][k][n] of one cell in the reference's exact arithmetic (host only; needs no GPU)"""
+    lib = load_library()
+    al = np.ascontiguousarray(alphas, dtype=np.float64)
+    out = C.c_double()
+    lib.dmx_exact_llk.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double)]
+    rc = lib.dmx_exact_llk(plp.nv, len(al), al.ctypes.data, plp.gp.ctypes.data, plp.cell_ptr.ctypes.data,
+                           plp.ent_snp.ctypes.data, plp.ent_ptr.ctypes.data, plp.reads.ctypes.data, cell, j, k, n,
+                           C.byref(out))
+    if rc != 0:
+        raise DmxError(rc, "dmx_exact_llk")
+    return out.value
 
 
 def pinned_empty(shape, dtype) -> np.ndarray:

@@ -796,6 +796,23 @@ int dmx_rescore(dmx_ctx* c, int64_t cell, int32_t j, int32_t k, int32_t n, doubl
   return DMX_OK;
 }
 
+int dmx_exact_llk(int32_t nv, int32_t n_alpha, const double* alpha, const float* gp, const int64_t* cell_ptr,
+                  const int32_t* ent_snp, const int64_t* ent_ptr, const uint16_t* reads, int64_t cell, int32_t j,
+                  int32_t k, int32_t n, double* out) {
+  if (!alpha || !gp || !cell_ptr || !ent_ptr || !out || nv < 1 || n_alpha < 1 || n_alpha > DMX_MAX_ALPHA || cell < 0 ||
+      j < 0 || j >= nv || k < 0 || k >= nv || n < 0 || n >= n_alpha)
+    return DMX_E_INVALID;
+  HostView hv;
+  hv.nv = nv; hv.nA = n_alpha; hv.alpha = alpha; hv.gp = gp;
+  hv.cell_ptr = cell_ptr; hv.ent_snp = ent_snp; hv.ent_ptr = ent_ptr; hv.reads = reads;
+  double err256[256];
+  for (int i = 0; i <= 255; ++i) err256[i] = (i > 1) ? pow(0.1, i * 0.1) : 0.75;   // PhredHelper.cpp:30
+  const ExactScorer scorer(hv, err256);
+  Hyp h{j, k, n};
+  scorer.eval(cell, &h, 1, out);
+  return DMX_OK;
+}
+
 int dmx_get_stats(dmx_ctx* c, dmx_stats* out) {
   if (!c || !out) return DMX_E_INVALID;
   *out = c->st;

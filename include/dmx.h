@@ -152,6 +152,12 @@ int dmx_rescore(dmx_ctx* ctx, int64_t cell, int32_t j, int32_t k, int32_t n, dou
 int dmx_write_outputs(dmx_ctx* ctx, const char* const* barcodes /* [ncells] */,
                       const char* const* samples /* [nv] */, const char* prefix, int write_pair);
 
+/* host-only utility (needs no device, no ctx): llksAB[j][k][n] of one cell in the reference's exact arithmetic
+ * (cmd_cram_demuxlet.cpp:597-684), from the same flat arrays dmx_set_gp / dmx_set_pileup take */
+int dmx_exact_llk(int32_t nv, int32_t n_alpha, const double* alpha, const float* gp, const int64_t* cell_ptr,
+                  const int32_t* ent_snp, const int64_t* ent_ptr, const uint16_t* reads, int64_t cell, int32_t j,
+                  int32_t k, int32_t n, double* out);
+
 int dmx_get_stats(dmx_ctx* ctx, dmx_stats* out);
 
 /* pinned host memory for DMX_BORROW_INPUTS callers */
