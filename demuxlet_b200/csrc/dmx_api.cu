@@ -1,6 +1,7 @@
 // dmx_api.cu -- the C ABI of include/dmx.h: context, uploads, kernel orchestration, read-back,
 // tie finaliser threads and the TSV writers.  No CPU fallback: without an sm_100 device dmx_create
 // fails with DMX_E_NODEVICE.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -115,6 +116,7 @@ struct dmx_ctx {
 
   std::vector<dmx_best_rec> best;
   dmx_stats st;
+  ScanMaps maps;                    // TMA descriptors of d_gp / d_gp0 / d_entq (encode_maps)
 };
 
 namespace {
@@ -180,6 +182,61 @@ int verify_device_log(dmx_ctx* c) {
   }
   c->gpu_exact = same;
   return DMX_OK;
+}
+
+// ---- TMA descriptors ----------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled lives in libcuda; it is looked up through the runtime so the library needs no -lcuda.
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+encode_tiled_fn get_encoder() {
+  static encode_tiled_fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (encode_tiled_fn)p;
+  }
+  return fn;
+}
+
+int encode_2d(CUtensorMap* m, CUtensorMapDataType dt, size_t esize, void* base, uint64_t cols, uint64_t rows,
+              uint32_t box_cols, uint32_t box_rows) {
+  encode_tiled_fn enc = get_encoder();
+  if (!enc) {
+    g_last_error = "cuTensorMapEncodeTiled not available";
+    return DMX_E_CUDA;
+  }
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * esize};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(m, dt, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    g_last_error = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
+    return DMX_E_CUDA;
+  }
+  return DMX_OK;
+}
+
+// descriptors of the pair scan's inputs; call after d_gp / d_gp0 / d_entq have their final addresses
+int encode_maps(dmx_ctx* c) {
+  memset(&c->maps, 0, sizeof(c->maps));
+  if (c->nsnps == 0 || c->E == 0) return DMX_OK;   // nothing is launched
+  int rc = encode_2d(&c->maps.gp, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c->d_gp.p, (uint64_t)c->nvp * 3,
+                     (uint64_t)c->nsnps, 96, 1);
+  if (rc == DMX_OK)
+    rc = encode_2d(&c->maps.gp0, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, c->d_gp0.p, 4, (uint64_t)c->nsnps, 4, 1);
+  if (rc == DMX_OK)
+    rc = encode_2d(&c->maps.qh, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, c->d_entq.p, (uint64_t)c->UQ, (uint64_t)c->E,
+                   QHEAD, NB);
+  if (rc == DMX_OK)
+    rc = encode_2d(&c->maps.qp, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, c->d_entq.p, (uint64_t)c->UQ, (uint64_t)c->E,
+                   QPLANE, NB);
+  return rc;
 }
 
 void build_tasks(dmx_ctx* c) {
@@ -265,7 +322,9 @@ void fill_scan_params(dmx_ctx* c, ScanParams* p) {
   p->sep0 = c->pg.sep0; p->T = (int)c->tt.size();
   p->want_single = (c->cfg.flags & DMX_SKIP_SINGLE) ? 0 : 1;
   p->ntasks = (int64_t)c->order.size() * p->T;
-  p->eps_rel = (c->cfg.flags & DMX_FP32_PAIRS) ? 1e-4 : 1e-9;
+  p->eps_rel = 1e-9;
+  // fp32 pair scan: |error of a llk| <= entries * (a few fp32 ulps); 2^-20 per entry leaves a wide margin
+  p->eps_ent = (c->cfg.flags & DMX_FP32_PAIRS) ? 0x1p-20 : 0.0;
   p->gp = c->d_gp.p; p->gp0 = c->d_gp0.p; p->ent_snp = c->d_ent_snp.p; p->entq = c->d_entq.p;
   p->cell_ptr = c->d_cell_ptr.p; p->cell_order = c->d_order.p; p->tt = c->d_tt.p; p->parts = c->d_parts.p;
   p->row0 = c->d_row0.p; p->singA = c->d_singA.p; p->lb = c->d_lb.p; p->p1 = c->d_p1.p;
@@ -305,7 +364,7 @@ int dense_scan(dmx_ctx* c, const std::vector<int32_t>& cells, double* host_out /
     p.parts = d_parts.p;
     p.dense = c->d_dense.p;
     p.ntasks = (int64_t)n * p.T;
-    CU(launch_pair_scan(p, false, c->stream));
+    CU(launch_pair_scan(p, c->maps, (c->cfg.flags & DMX_FP32_PAIRS) != 0, c->stream));
     CU(launch_fill_sep_dense(p, (int64_t)n, c->stream));
     c->st.gpu_launches += 1 + (p.sep0 ? 1 : 0);
     CU(cudaMemcpyAsync(host_out + lo * per, c->d_dense.p, n * per * sizeof(double), cudaMemcpyDeviceToHost,
@@ -607,11 +666,15 @@ int dmx_compute(dmx_ctx* c) {
   CU(cudaEventRecord(c->ev[1], c->stream));
   ScanParams sp;
   fill_scan_params(c, &sp);
-  CU(launch_pair_scan(sp, (c->cfg.flags & DMX_FP32_PAIRS) != 0, c->stream));
+  {
+    const int rc = encode_maps(c);
+    if (rc != DMX_OK) return rc;
+  }
+  CU(launch_pair_scan(sp, c->maps, (c->cfg.flags & DMX_FP32_PAIRS) != 0, c->stream));
   CU(cudaEventRecord(c->ev[2], c->stream));
   MergeParams mp;
   memset(&mp, 0, sizeof(mp));
-  mp.nv = nv; mp.nA = nA; mp.T = T; mp.sep0 = c->pg.sep0; mp.eps_rel = sp.eps_rel;
+  mp.nv = nv; mp.nA = nA; mp.T = T; mp.sep0 = c->pg.sep0; mp.eps_rel = sp.eps_rel; mp.eps_ent = sp.eps_ent; mp.cell_ptr = c->d_cell_ptr.p;
   mp.w_single = (1. - c->cfg.doublet_prior) / nv;
   for (int n = 0; n < nA; ++n)
     mp.w_double[n] = c->cfg.doublet_prior / nv / (nv - 1) / (nA - 1) / (c->alpha[n] == 0.5 ? 2.0 : 1.0);
@@ -673,7 +736,8 @@ int dmx_compute(dmx_ctx* c) {
     g.row0 = c->r_row0.p + (size_t)cell * nA * nv;
     g.l00 = c->r_l00.p + (size_t)cell * nA;
     int32_t from_gpu = 0;
-    finalise_cell(hv, scorer, cell, g, cands, c->cfg.doublet_prior, sp.eps_rel, exact,
+    const double eps_abs = sp.eps_ent * (double)(c->h_cell_ptr[cell + 1] - c->h_cell_ptr[cell]);
+    finalise_cell(hv, scorer, cell, g, cands, c->cfg.doublet_prior, sp.eps_rel, eps_abs, exact,
                   dev_rescore ? &c->r_lists.p[cell] : nullptr, r, &from_gpu);
     resc[tid] += r->n_rescored;
     resc_gpu[tid] += from_gpu;
@@ -705,7 +769,9 @@ int dmx_compute(dmx_ctx* c) {
       if (rc != DMX_OK) return rc;
       parallel_for((int64_t)n, nth, [&](int64_t i, int tid) {
         std::vector<Hyp> cands;
-        candidates_from_dense(c->r_dense.p + (size_t)i * per, nv, nA, 1, sp.eps_rel, &cands);
+        const int64_t cl = cells[i];
+        candidates_from_dense(c->r_dense.p + (size_t)i * per, nv, nA, 1, sp.eps_rel,
+                              sp.eps_ent * (double)(c->h_cell_ptr[cl + 1] - c->h_cell_ptr[cl]), &cands);
         do_cell(cells[i], cands, tid);
         c->best[cells[i]].exact_mask |= DMX_X_FULLCELL;
       });

@@ -132,7 +132,7 @@ void ExactScorer::eval(int64_t cell, const Hyp* hyps, int nh, double* out) const
   }
 }
 
-void candidates_from_dense(const double* dense, int nv, int nA, int first_arg_plane, double eps_rel,
+void candidates_from_dense(const double* dense, int nv, int nA, int first_arg_plane, double eps_rel, double eps_abs,
                            std::vector<Hyp>* out) {
   out->clear();
   double best = -INFINITY;
@@ -141,7 +141,7 @@ void candidates_from_dense(const double* dense, int nv, int nA, int first_arg_pl
       if (j == k) continue;
       for (int n = first_arg_plane; n < nA; ++n) best = fmax(best, dense[((size_t)j * nv + k) * nA + n]);
     }
-  const double thr = best - eps_rel * fmax(1.0, fabs(best));
+  const double thr = best - (eps_rel * fmax(1.0, fabs(best)) + eps_abs);
   for (int j = 0; j < nv; ++j)
     for (int k = 0; k < nv; ++k) {
       if (j == k) continue;
@@ -160,13 +160,13 @@ struct ExactCache {
     return false;
   }
 };
-inline bool near(double a, double b, double eps_rel) {
-  return fabs(a - b) <= eps_rel * (fmax(1.0, fabs(a)) + fmax(1.0, fabs(b)));
+inline bool near(double a, double b, double eps_rel, double eps_abs) {
+  return fabs(a - b) <= eps_rel * (fmax(1.0, fabs(a)) + fmax(1.0, fabs(b))) + 2.0 * eps_abs;
 }
 }  // namespace
 
 void finalise_cell(const HostView& hv, const ExactScorer& sc, int64_t cell, const CellGpu& g,
-                   const std::vector<Hyp>& cands, double doublet_prior, double eps_rel, bool exact,
+                   const std::vector<Hyp>& cands, double doublet_prior, double eps_rel, double eps_abs, bool exact,
                    const RescList* gl, dmx_best_rec* rec, int32_t* n_from_gpu) {
   const int nv = hv.nv;
   std::vector<double> vals(g.sing, g.sing + nv);
@@ -182,7 +182,7 @@ void finalise_cell(const HostView& hv, const ExactScorer& sc, int64_t cell, cons
     double m2 = -INFINITY;
     for (int j = 0; j < nv; ++j)
       if (j != i1) m2 = fmax(m2, vals[j]);
-    const double w = 2.0 * eps_rel * fmax(1.0, fabs(m2));
+    const double w = 2.0 * (eps_rel * fmax(1.0, fabs(m2)) + eps_abs);
     int close2 = 0;
     for (int j = 0; j < nv; ++j)
       if (j != i1 && vals[j] >= m2 - w) ++close2;
@@ -266,10 +266,10 @@ void finalise_cell(const HostView& hv, const ExactScorer& sc, int64_t cell, cons
   if (exact) {
     const double s1 = vals[iS1], s2 = vals[iS2], l1 = vals[jB], l2 = vals[kB];
     bool want12 = false;
-    if (near(llk12, l1, eps_rel)) { want12 = true; exactify_sing(jB); }
-    if (near(llk12, l2, eps_rel)) { want12 = true; exactify_sing(kB); }
-    if (near(llk12, s1 + 2, eps_rel)) { want12 = true; exactify_sing(iS1); }
-    if (near(s1, s2 + 2, eps_rel)) { exactify_sing(iS1); exactify_sing(iS2); }
+    if (near(llk12, l1, eps_rel, eps_abs)) { want12 = true; exactify_sing(jB); }
+    if (near(llk12, l2, eps_rel, eps_abs)) { want12 = true; exactify_sing(kB); }
+    if (near(llk12, s1 + 2, eps_rel, eps_abs)) { want12 = true; exactify_sing(iS1); }
+    if (near(s1, s2 + 2, eps_rel, eps_abs)) { exactify_sing(iS1); exactify_sing(iS2); }
     if (want12 && !llk12_exact) need.push_back(Hyp{jB, kB, nB});
     // de-duplicate
     std::sort(need.begin(), need.end(), [](const Hyp& a, const Hyp& b) {

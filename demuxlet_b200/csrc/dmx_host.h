@@ -58,13 +58,14 @@ struct CellGpu {
 };
 
 // candidate pairs of a cell whose GPU candidate list overflowed: taken from a dense llksAB block
-void candidates_from_dense(const double* dense, int nv, int nA, int first_arg_plane, double eps_rel,
+void candidates_from_dense(const double* dense, int nv, int nA, int first_arg_plane, double eps_rel, double eps_abs,
                            std::vector<Hyp>* out);
 
 // :746-758, :799-857 with near-ties resolved by ExactScorer.  `cands` = ordered candidate hypotheses
-// within the window of the GPU's best pair.
+// within the window of the GPU's best pair.  Window of a value x: eps_rel * max(1, |x|) + eps_abs, where eps_abs is
+// the cell's absolute error allowance (entries x per-entry bound of the fp32 pair scan; 0 for the fp64 scan).
 void finalise_cell(const HostView& hv, const ExactScorer& sc, int64_t cell, const CellGpu& g,
-                   const std::vector<Hyp>& cands, double doublet_prior, double eps_rel, bool exact,
+                   const std::vector<Hyp>& cands, double doublet_prior, double eps_rel, double eps_abs, bool exact,
                    const RescList* gpu_exact, dmx_best_rec* rec, int32_t* n_from_gpu);
 
 // the host libm's __log_data (ln2hi, ln2lo, poly[5], poly1[11], tab[128]{invc, logc}) read from the

@@ -2,6 +2,7 @@
 // sm_100a kernels (dmx_kernels.cu).  Not part of the ABI.
 #pragma once
 #include <stdint.h>
+#include <cuda.h>   // CUtensorMap (type only; the encoder is looked up at run time)
 #include "../../include/dmx.h"
 
 namespace dmx {
@@ -23,6 +24,14 @@ constexpr int GRP_DBL = 14;    // doubles per 4-sample group in the processed ri
                                // stride spreads 16-byte lane loads over all banks)
 constexpr int GRP_F32 = 12;    // floats per 4-sample group in the fp32 processed ring (48 B stride)
 constexpr int FLUSH_STAGES = 16 / NB;   // exponent renormalisation period (stages): every 16 entries
+// fp32 pair scan (pair_scan_f32_kernel): one task pipeline per CTA; a consumer thread owns an 8 x 8 tile of
+// hypotheses for ONE of the NB entries of a stage (lane & 7 = entry, lane >> 3 = tile position inside the warp)
+constexpr int F_NCW = 9;       // consumer warps: 36 tile positions of the 64 x 64 upper triangle x 8 entry lanes
+constexpr int F_NTW = 2;       // transform warps: a lane = one entry slot x eight samples
+constexpr int F_S_RAW = 6;     // stages of the raw ring
+constexpr int F_S_PROC = 4;    // stages of the processed ring
+constexpr int F_NTHREADS = (F_NCW + F_NTW + 1) * 32;   // 448
+constexpr int F_PEEL_STAGES = 4;   // underflow check period (stages = entries per thread)
 constexpr int MAX_CAND = 8;    // near-tie candidates kept per task / per cell
 constexpr int MAX_U = DMX_MAX_ALPHA * 6 + 3;   // distinct mixing proportions p(n,l,m)
 
@@ -82,7 +91,8 @@ struct ScanParams {
   int32_t T;                   // task types per cell
   int32_t want_single;         // accumulate pass 1
   int64_t ntasks;              // nactive * T
-  double eps_rel;              // candidate window, relative to max(1, |best|)
+  double eps_rel;              // candidate window, relative to max(1, |best|) ...
+  double eps_ent;              // ... plus this much per pileup entry of the cell (fp32 pair scan error bound)
   const float* gp;             // [nsnps][nvp*3], rows zero padded
   const double* gp0;           // [nsnps][4]: cohort mean (x, y, z), 0
   const int32_t* ent_snp;      // [E]
@@ -98,6 +108,14 @@ struct ScanParams {
   double* p1_0;                // [ncells]          pass-1 llk0s
   double* l00;                 // [ncells][nA]      llks00
   double* dense;               // optional [nactive][nv][nv][nA]
+};
+
+// TMA descriptors of the pair scan's inputs (built by dmx_api.cu:encode_maps, passed as a __grid_constant__)
+struct ScanMaps {
+  CUtensorMap gp;    // float32 [nsnps][nvp*3], box {96, 1}: tile::gather4 of 4 SNP rows x 32 samples
+  CUtensorMap gp0;   // float64 [nsnps][4],     box {4, 1}:  tile::gather4
+  CUtensorMap qh;    // float64 [E][UQ],        box {QHEAD, NB}:  record heads of NB consecutive entries
+  CUtensorMap qp;    // float64 [E][UQ],        box {QPLANE, NB}: one plane of NB consecutive entries
 };
 
 // exact re-scoring requests of one cell (built by merge_kernel, filled by rescore_kernel)
@@ -123,7 +141,8 @@ struct RescoreParams {
 
 struct MergeParams {
   int32_t nv, nA, T, sep0;
-  double eps_rel;
+  double eps_rel, eps_ent;     // candidate window: eps_rel * max(1, |x|) + eps_ent * entries of the cell
+  const int64_t* cell_ptr;
   double w_single;             // (1 - doublet_prior) / nv
   double w_double[DMX_MAX_ALPHA];   // doublet_prior / nv / (nv-1) / (nA-1) / (alpha == 0.5 ? 2 : 1)
   const int32_t* cell_order;
@@ -152,7 +171,7 @@ struct EntqParams {
 // host-callable launchers (dmx_kernels.cu); all return a cudaError_t as int
 int launch_gp0(const float* gp, double* gp0, int64_t nsnps, int nv, int nvp, void* stream);
 int launch_entq(const EntqParams& p, void* stream);
-int launch_pair_scan(const ScanParams& p, bool fp32, void* stream);
+int launch_pair_scan(const ScanParams& p, const ScanMaps& tm, bool fp32, void* stream);
 int launch_merge(const MergeParams& p, int64_t nactive, void* stream);
 int launch_fill_sep_dense(const ScanParams& p, int64_t nactive, void* stream);
 int launch_rescore(const RescoreParams& p, int64_t nactive, void* stream);

@@ -143,8 +143,22 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
-__device__ __forceinline__ void consumer_bar_sync(int slot) {
-  asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "n"(NCW * 32) : "memory");
+
+// TMA tensor copies (descriptors built on the host, dmx_api.cu:encode_maps)
+__device__ __forceinline__ void tma_gather4(void* dst, const CUtensorMap* map, int col, int r0, int r1, int r2, int r3,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, "
+      "%5, %6}], [%7];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_tile2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
 }
 
 // peel the binary exponent of a positive double into an integer accumulator; mantissa stays in [1,2)
@@ -280,39 +294,56 @@ int set_err_table(const double* err256) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// pair scan: persistent kernel, one 512-thread CTA per SM, two independent task pipelines ("slots")
+// pair scan: persistent kernels.  Two variants share the loader and transform roles:
+//   pair_scan_kernel      fp64 hypotheses on the FP64 tensor path (DMMA), two task pipelines per CTA
+//   pair_scan_f32_kernel  fp32 hypotheses (3 FFMA + 1 FMUL per hypothesis and entry), one pipeline per CTA
 // ---------------------------------------------------------------------------------------------
-// Warp roles.  SM sub-partition = warp id % 4; the FP64 pipe is the bound, so the consumer warps (C,
-// 64 DFMA/DMUL per lane and entry) are spread 3/3/2/2 over the four sub-partitions and the lighter
-// transform (T) and loader (L) warps fill the rest:
-//   wid  0  1  2  3 |  4  5  6  7 |  8  9 10 11 | 12 13 14 15
-//        CA CA CA CA| CA CB CB CB | CB CB TA TA | LA LB TB TB        (A, B = slot)
 namespace {
-constexpr uint32_t ROWJ_STRIDE = BLK * 12;          // bytes per entry, j-side GP row slice
-constexpr uint32_t ROWK_STRIDE = BLK_RECT_K * 12;   // bytes per entry, k-side slice of a rectangular task
-constexpr uint32_t Q_STRIDE = (QHEAD + QPLANE) * 8; // 128 B: head (48) + one plane (80)
+// raw ring stage (what the TMA unit writes).  GP rows arrive through tile::gather4 copies of 4 rows x 32 samples
+// (384 B per row): the j side as [half of 32 samples][entry][384 B], the k side of a rectangular task as
+// [entry][384 B]; gp0 rows as [entry][32 B]; the entry records through two tiled 2-D copies of 8 consecutive
+// entries: heads [entry][48 B] and the task's plane [entry][80 B].
+constexpr uint32_t GROW = 32 * 12;                  // bytes of one gathered row slice (32 samples)
+constexpr uint32_t GATHER_BYTES = 4 * GROW;         // one gather4
 constexpr uint32_t OFF_GPJ = 0;
-constexpr uint32_t OFF_GPK = OFF_GPJ + NB * ROWJ_STRIDE;
-constexpr uint32_t OFF_GP0 = OFF_GPK + NB * ROWK_STRIDE;
-constexpr uint32_t OFF_Q = OFF_GP0 + NB * 32;
-constexpr uint32_t RAW_SLOT = OFF_Q + NB * Q_STRIDE;                 // 10496 B
-// processed ring: per entry and side a 64 x 4 matrix (sample x genotype, 4th column zero) stored as 8 blocks of
-// 8 samples; inside a block the layout is column-major with the column index XOR-swizzled by the block parity,
+constexpr uint32_t HALF_BYTES = NB * GROW;          // 3072: one 32-sample half of the j side, all entries
+constexpr uint32_t OFF_GPK = OFF_GPJ + (BLK / 32) * HALF_BYTES;
+constexpr uint32_t OFF_GP0 = OFF_GPK + HALF_BYTES;
+constexpr uint32_t OFF_QH = OFF_GP0 + NB * 32;
+constexpr uint32_t OFF_QP = OFF_QH + NB * QHEAD * 8;
+constexpr uint32_t RAW_SLOT = OFF_QP + NB * QPLANE * 8;              // 10496 B
+static_assert(OFF_GPK % 128 == 0 && OFF_GP0 % 128 == 0 && OFF_QH % 128 == 0 && OFF_QP % 128 == 0, "TMA alignment");
+static_assert(BLK_RECT_K == 32 && BLK % 32 == 0, "gather geometry");
+// fp64 processed ring: per entry and side a 64 x 4 matrix (sample x genotype, 4th column zero) stored as 8 blocks
+// of 8 samples; inside a block the layout is column-major with the column index XOR-swizzled by the block parity,
 // so that both the transform's stores (one column, 32 consecutive samples) and the consumers' DMMA fragment
 // loads (lane -> row lane/4, column lane%4 of one block) are bank-conflict free.
 constexpr uint32_t SIDE_DBL = BLK * 4;                               // doubles per entry and side (256)
 constexpr uint32_t PROC_SLOT = NB * 2 * SIDE_DBL * 8;                // 32768 B
-constexpr uint32_t SLOT_CTRL = 512;                                  // barriers + epilogue scratch
+constexpr uint32_t SLOT_CTRL = 1024;                                 // barriers + epilogue scratch
 constexpr uint32_t SLOT_BYTES = SLOT_CTRL + S_RAW * RAW_SLOT + S_PROC * PROC_SLOT;
 static_assert(RAW_SLOT % 128 == 0 && PROC_SLOT % 128 == 0 && SLOT_BYTES % 128 == 0, "alignment");
+// fp32 processed ring: per side 16 blocks of 4 samples; a block holds, for each of the NB entries of the stage,
+// the 12 floats (4 samples x 3 genotypes) a consumer thread fetches with three LDS.128.  Entry stride 48 B makes
+// the 8 entry lanes of a quarter warp conflict free; block stride 432 B (= 12 words mod 32) makes the transform's
+// stores (lane = sample, 3 words apart) conflict free as well.
+constexpr uint32_t F_BLK4_FLT = NB * 12 + 12;                        // 108 floats
+constexpr uint32_t F_SIDE_FLT = (BLK / 4) * F_BLK4_FLT;              // 1728 floats
+constexpr uint32_t F_PROC_SLOT = 2 * F_SIDE_FLT * 4;                 // 13824 B
+constexpr uint32_t F_ES_STRIDE = F_NCW * 32;                         // ints between the exponents of one thread
+constexpr uint32_t F_ES_BYTES = 64 * F_ES_STRIDE * 4;                // 73728 B
+constexpr uint32_t F_SMEM_NOTS = SLOT_CTRL + F_S_RAW * RAW_SLOT + F_S_PROC * F_PROC_SLOT + F_ES_BYTES;   // + TScratch
+static_assert(F_PROC_SLOT % 128 == 0 && NB == 8, "fp32 scan geometry");
+static_assert(2 * F_S_RAW + 2 * F_S_PROC <= 32 && 2 * S_RAW + 2 * S_PROC <= 32, "barriers must fit below the scratch area");
 
-struct Scratch {                     // at slot offset 128
-  double red[2][NCW];
-  double red2[NCW];
+constexpr uint32_t SCRATCH_OFF = 256;   // barriers live below
+struct Scratch {                     // at slot offset SCRATCH_OFF
+  double red[2][16];
+  double red2[16];
   int ncand;
   uint32_t cand[MAX_CAND];
 };
-static_assert(sizeof(Scratch) + 128 <= SLOT_CTRL, "scratch");
+static_assert(sizeof(Scratch) + SCRATCH_OFF <= SLOT_CTRL, "scratch");
 
 struct TaskInfo {
   int64_t aidx;
@@ -332,50 +363,548 @@ __device__ __forceinline__ bool next_task(const ScanParams& p, int r, int u, int
   return true;
 }
 
-// one stage of the transform for lane `tl` (sample slot on each side).  No lane-dependent branches: lanes
-// beyond the task's sample count work on padding (their ring slots are never read), so the compiler can
-// batch the shared-memory loads of several entries.
-template <bool SAME, bool FULL, bool EXTRAS>
-__device__ __forceinline__ void transform_stage(const unsigned char* __restrict__ rs, double* __restrict__ pa,
-                                                int tl, int nvalid, double& PA, double& PB, double& P1) {
+template <int NTHR>
+__device__ __forceinline__ void consumer_bar_sync(int id) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id + 1), "n"(NTHR) : "memory");
+}
+
+// one stage of the transform for lane `tl` (sample slot on each side).  The fp64 variant has no lane-dependent
+// branches: lanes beyond the task's sample count work on padding (their ring slots are never read), so the
+// compiler can batch the shared-memory loads of several entries.  The fp32 variant writes neutral vectors
+// (1, 0, 0) for such lanes because an 8-sample tile may straddle the end of the sample range.
+template <bool SAME, bool FULL, bool EXTRAS, bool F32>
+__device__ __forceinline__ void transform_stage(const unsigned char* __restrict__ rs, void* __restrict__ pav,
+                                                int tl, int nvalid, bool jv, bool kv, double& PA, double& PB,
+                                                double& P1) {
   const int blk = tl >> 3, sw = blk & 1;
-  double* ad = pa + blk * 32 + (tl & 7);
+  double* ad = reinterpret_cast<double*>(pav) + blk * 32 + (tl & 7);
   double* wd = ad + NB * SIDE_DBL;
+  float* af = reinterpret_cast<float*>(pav) + (tl >> 2) * F_BLK4_FLT + (tl & 3) * 3;
+  float* wf = af + F_SIDE_FLT;
   const int c0 = (0 ^ sw) * 8, c1 = (1 ^ sw) * 8, c2 = (2 ^ sw) * 8;
-  const float* gj = reinterpret_cast<const float*>(rs + OFF_GPJ) + tl * 3;
-  const float* gk = SAME ? gj : reinterpret_cast<const float*>(rs + OFF_GPK) + (tl & (BLK_RECT_K - 1)) * 3;
-  constexpr int GK_STRIDE = SAME ? ROWJ_STRIDE / 4 : ROWK_STRIDE / 4;
-  const double2* q2 = reinterpret_cast<const double2*>(rs + OFF_Q);
+  const float* gj = reinterpret_cast<const float*>(rs + OFF_GPJ + (tl >> 5) * HALF_BYTES) + (tl & 31) * 3;
+  const float* gk = SAME ? gj : reinterpret_cast<const float*>(rs + OFF_GPK) + (tl & 31) * 3;
+  constexpr int GK_STRIDE = GROW / 4, GJ_STRIDE = GROW / 4;
+  const double2* qh = reinterpret_cast<const double2*>(rs + OFF_QH);   // 3 double2 per entry
+  const double2* qp = reinterpret_cast<const double2*>(rs + OFF_QP);   // 5 double2 per entry
 #pragma unroll
   for (int e = 0; e < NB; ++e) {
     if (FULL || e < nvalid) {
-      const double g0 = (double)gk[e * GK_STRIDE];
-      const double g1 = (double)gk[e * GK_STRIDE + 1];
-      const double g2 = (double)gk[e * GK_STRIDE + 2];
-      const double2 qa = q2[e * 8 + 3], qb = q2[e * 8 + 4], qc = q2[e * 8 + 5], qd = q2[e * 8 + 6];
-      const double q22 = reinterpret_cast<const double*>(q2 + e * 8 + 7)[0];
+      const float f0 = gk[e * GK_STRIDE], f1 = gk[e * GK_STRIDE + 1], f2 = gk[e * GK_STRIDE + 2];
+      const double g0 = (double)f0, g1 = (double)f1, g2 = (double)f2;
+      const double2 qa = qp[e * 5], qb = qp[e * 5 + 1], qc = qp[e * 5 + 2], qd = qp[e * 5 + 3];
+      const double q22 = reinterpret_cast<const double*>(qp + e * 5 + 4)[0];
       // Q'[l][m] row-major: qa = (00, 01), qb = (02, 10), qc = (11, 12), qd = (20, 21), q22
-      wd[e * SIDE_DBL + c0] = fma(qb.x, g2, fma(qa.y, g1, qa.x * g0));
-      wd[e * SIDE_DBL + c1] = fma(qc.y, g2, fma(qc.x, g1, qb.y * g0));
-      wd[e * SIDE_DBL + c2] = fma(q22, g2, fma(qd.y, g1, qd.x * g0));
+      const double w0 = fma(qb.x, g2, fma(qa.y, g1, qa.x * g0));
+      const double w1 = fma(qc.y, g2, fma(qc.x, g1, qb.y * g0));
+      const double w2 = fma(q22, g2, fma(qd.y, g1, qd.x * g0));
       if (EXTRAS) {
-        const double2 h0 = q2[e * 8], h1 = q2[e * 8 + 1], h2 = q2[e * 8 + 2];   // GL0 GL1 | GL2 f0 | f1 f2
+        const double2 h0 = qh[e * 3], h1 = qh[e * 3 + 1], h2 = qh[e * 3 + 2];   // GL0 GL1 | GL2 f0 | f1 f2
         PA *= fma(h2.y, g2, fma(h2.x, g1, h1.y * g0));
         PB *= (g0 + g1) + g2;
         P1 *= fma(h1.x, g2, fma(h0.y, g1, h0.x * g0));
       }
-      if (SAME) {
-        ad[e * SIDE_DBL + c0] = g0; ad[e * SIDE_DBL + c1] = g1; ad[e * SIDE_DBL + c2] = g2;
+      if (F32) {
+        wf[e * 12 + 0] = kv ? (float)w0 : 1.0f;
+        wf[e * 12 + 1] = kv ? (float)w1 : 0.0f;
+        wf[e * 12 + 2] = kv ? (float)w2 : 0.0f;
+        float a0 = f0, a1 = f1, a2 = f2;
+        if (!SAME) {
+          a0 = gj[e * (GJ_STRIDE)]; a1 = gj[e * (GJ_STRIDE) + 1]; a2 = gj[e * (GJ_STRIDE) + 2];
+        }
+        af[e * 12 + 0] = jv ? a0 : 1.0f;
+        af[e * 12 + 1] = jv ? a1 : 0.0f;
+        af[e * 12 + 2] = jv ? a2 : 0.0f;
       } else {
-        ad[e * SIDE_DBL + c0] = (double)gj[e * (ROWJ_STRIDE / 4)];
-        ad[e * SIDE_DBL + c1] = (double)gj[e * (ROWJ_STRIDE / 4) + 1];
-        ad[e * SIDE_DBL + c2] = (double)gj[e * (ROWJ_STRIDE / 4) + 2];
+        wd[e * SIDE_DBL + c0] = w0;
+        wd[e * SIDE_DBL + c1] = w1;
+        wd[e * SIDE_DBL + c2] = w2;
+        if (SAME) {
+          ad[e * SIDE_DBL + c0] = g0; ad[e * SIDE_DBL + c1] = g1; ad[e * SIDE_DBL + c2] = g2;
+        } else {
+          ad[e * SIDE_DBL + c0] = (double)gj[e * (GJ_STRIDE)];
+          ad[e * SIDE_DBL + c1] = (double)gj[e * (GJ_STRIDE) + 1];
+          ad[e * SIDE_DBL + c2] = (double)gj[e * (GJ_STRIDE) + 2];
+        }
       }
-    } else {   // identity entry: S = 1 for every hypothesis
+    } else if (F32) {   // identity entry: S = 1 for every hypothesis
+      wf[e * 12 + 0] = 1.0f; wf[e * 12 + 1] = 0.0f; wf[e * 12 + 2] = 0.0f;
+      af[e * 12 + 0] = 1.0f; af[e * 12 + 1] = 0.0f; af[e * 12 + 2] = 0.0f;
+    } else {
       wd[e * SIDE_DBL + c0] = 1.0; wd[e * SIDE_DBL + c1] = 0.0; wd[e * SIDE_DBL + c2] = 0.0;
       ad[e * SIDE_DBL + c0] = 1.0; ad[e * SIDE_DBL + c1] = 0.0; ad[e * SIDE_DBL + c2] = 0.0;
     }
   }
+}
+
+template <bool SAME, bool EXTRAS, bool F32>
+__device__ __forceinline__ void transform_dispatch(const unsigned char* rs, void* pa, int tl, int nvalid, bool jv,
+                                                   bool kv, double& PA, double& PB, double& P1) {
+  if (nvalid == NB) transform_stage<SAME, true, EXTRAS, F32>(rs, pa, tl, nvalid, jv, kv, PA, PB, P1);
+  else transform_stage<SAME, false, EXTRAS, F32>(rs, pa, tl, nvalid, jv, kv, PA, PB, P1);
+}
+
+// ring pointers of one task pipeline
+struct Pipe {
+  uint64_t *raw_full, *raw_empty, *proc_full, *proc_empty;
+  unsigned char *raw_base, *proc_base;
+};
+
+// =============================== loader warp =====================================================
+// Per stage of NB entries one elected lane issues the TMA copies: tile::gather4 for the GP row slices (4 SNP rows
+// x 32 samples per instruction) and the gp0 rows, and two tiled 2-D copies for the heads and the task's plane of
+// the NB consecutive entry records.  Every stage moves the same number of bytes: entries beyond the cell's last one
+// gather row 0 / the next cell's records (rows beyond the table are zero filled by the TMA unit), and the transform
+// ignores them.  SNP ids are fetched one stage ahead.
+template <int SRAW>
+__device__ __forceinline__ void loader_role(const ScanParams& p, const ScanMaps& tm, const Pipe& pp, int lane, int u,
+                                            int NS) {
+  uint32_t git = 0;
+  TaskInfo ti;
+  for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
+    const TaskType tt = p.tt[ti.tti];
+    const bool same = tt.flags & TF_TRI;
+    const bool need_head = tt.flags & (TF_EXTRAS | TF_SCALARS);
+    const bool need_z = tt.flags & (TF_SCALARS | TF_L00);
+    const int nh = (tt.nj + 31) >> 5;     // 32-sample halves of the j side
+    const uint32_t bytes = (uint32_t)NB * ((uint32_t)nh * GROW + (same ? 0u : GROW) + (need_z ? 32u : 0u) +
+                                           (need_head ? (uint32_t)QHEAD * 8u : 0u) + (uint32_t)QPLANE * 8u);
+    int snp_next = (lane < NB && ti.e0 + lane < ti.e1) ? __ldg(p.ent_snp + ti.e0 + lane) : 0;
+    for (int it = 0; it < ti.nst; ++it, ++git) {
+      const int rslot = git % SRAW;
+      const uint32_t ph = (git / SRAW) & 1u;
+      const int64_t eb = ti.e0 + (int64_t)it * NB;
+      const int snp = snp_next;
+      snp_next = (lane < NB && eb + NB + lane < ti.e1) ? __ldg(p.ent_snp + eb + NB + lane) : 0;
+      int s[NB];
+#pragma unroll
+      for (int i = 0; i < NB; ++i) s[i] = __shfl_sync(0xffffffffu, snp, i);
+      mbar_wait(&pp.raw_empty[rslot], ph ^ 1u);
+      if (lane == 0) {
+        unsigned char* rs = pp.raw_base + (size_t)rslot * RAW_SLOT;
+        uint64_t* bar = &pp.raw_full[rslot];
+        mbar_expect_tx(bar, bytes);
+#pragma unroll
+        for (int g = 0; g < NB / 4; ++g) {
+          for (int h = 0; h < nh; ++h)
+            tma_gather4(rs + OFF_GPJ + h * HALF_BYTES + g * GATHER_BYTES, &tm.gp, (tt.j0 + 32 * h) * 3, s[4 * g],
+                        s[4 * g + 1], s[4 * g + 2], s[4 * g + 3], bar);
+          if (!same)
+            tma_gather4(rs + OFF_GPK + g * GATHER_BYTES, &tm.gp, tt.k0 * 3, s[4 * g], s[4 * g + 1], s[4 * g + 2],
+                        s[4 * g + 3], bar);
+          if (need_z)
+            tma_gather4(rs + OFF_GP0 + g * 128, &tm.gp0, 0, s[4 * g], s[4 * g + 1], s[4 * g + 2], s[4 * g + 3], bar);
+        }
+        if (need_head) tma_tile2d(rs + OFF_QH, &tm.qh, 0, (int)eb, bar);
+        tma_tile2d(rs + OFF_QP, &tm.qp, tt.qoff, (int)eb, bar);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// =============================== transform warps =================================================
+// one lane per sample: GP row -> (a, w) vectors in the processed ring; the lanes also carry the per-sample
+// "extras" (separable-plane factor, row-sum factor, pass-1 llks) and, in NB lanes, the scalars llk0s / llks00
+template <bool F32, int SRAW, int SPROC, uint32_t PSLOT_BYTES>
+__device__ __forceinline__ void transform_role(const ScanParams& p, const Pipe& pp, int rw, int lane, int u, int NS) {
+  const int tl = rw * 32 + lane;        // sample slot on each side
+  uint32_t git = 0;
+  TaskInfo ti;
+  for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
+    const TaskType tt = p.tt[ti.tti];
+    const bool same = tt.flags & TF_TRI;
+    const bool do_k = tl < tt.nk;
+    const bool k_valid = (tt.k0 + tl) < p.nv;
+    const bool extras = (tt.flags & TF_EXTRAS) && do_k && k_valid;
+    const bool scal = (tt.flags & (TF_SCALARS | TF_L00)) && rw == 0 && lane < NB;
+    const bool jv = tl < tt.nj;
+    const bool kv = same ? jv : ((tl & (BLK_RECT_K - 1)) < tt.nk);
+    double PA = 1.0, PB = 1.0, P1 = 1.0;            // running products (extras)
+    int eA = 0, eB = 0, e1x = 0;
+    double PS0 = 1.0, PS1 = 1.0, PS2 = 1.0;         // scalars: llk0s, llks00[sep], llks00[n]; lane = entry slot
+    int eS0 = 0, eS1 = 0, eS2 = 0;
+    int nflush = 0;
+    for (int it = 0; it < ti.nst; ++it, ++git) {
+      const int rslot = git % SRAW, pslot = git % SPROC;
+      const uint32_t rph = (git / SRAW) & 1u, pph = (git / SPROC) & 1u;
+      const int nvalid = (int)min((int64_t)NB, ti.e1 - (ti.e0 + (int64_t)it * NB));
+      mbar_wait(&pp.raw_full[rslot], rph);
+      mbar_wait(&pp.proc_empty[pslot], pph ^ 1u);
+      const unsigned char* rs = pp.raw_base + (size_t)rslot * RAW_SLOT;
+      void* pa = pp.proc_base + (size_t)pslot * PSLOT_BYTES;
+      if (same) {
+        if (tt.flags & TF_EXTRAS) transform_dispatch<true, true, F32>(rs, pa, tl, nvalid, jv, kv, PA, PB, P1);
+        else transform_dispatch<true, false, F32>(rs, pa, tl, nvalid, jv, kv, PA, PB, P1);
+      } else {
+        if (tt.flags & TF_EXTRAS) transform_dispatch<false, true, F32>(rs, pa, tl, nvalid, jv, kv, PA, PB, P1);
+        else transform_dispatch<false, false, F32>(rs, pa, tl, nvalid, jv, kv, PA, PB, P1);
+      }
+      if (scal && lane < nvalid) {
+        const double* z = reinterpret_cast<const double*>(rs + OFF_GP0) + lane * 4;
+        const double* hq = reinterpret_cast<const double*>(rs + OFF_QH) + lane * QHEAD;
+        const double* q = reinterpret_cast<const double*>(rs + OFF_QP) + lane * QPLANE;
+        const double z0 = z[0], z1 = z[1], z2 = z[2];
+        if (tt.flags & TF_SCALARS) {
+          if (p.want_single) PS0 *= fma(hq[2], z2, fma(hq[1], z1, hq[0] * z0));                    // :459
+          if (p.sep0) PS1 *= fma(hq[5], z2, fma(hq[4], z1, hq[3] * z0)) * ((z0 + z1) + z2);
+        }
+        if (tt.flags & TF_L00) {                                                                   // :700-709
+          const double t0 = fma(q[2], z2, fma(q[1], z1, q[0] * z0));
+          const double t1 = fma(q[5], z2, fma(q[4], z1, q[3] * z0));
+          const double t2 = fma(q[8], z2, fma(q[7], z1, q[6] * z0));
+          PS2 *= fma(z2, t2, fma(z1, t1, z0 * t0));
+        }
+      }
+      if ((it % FLUSH_STAGES) == FLUSH_STAGES - 1) {
+        peel(PA, eA); peel(PB, eB); peel(P1, e1x);
+        peel(PS0, eS0); peel(PS1, eS1); peel(PS2, eS2);
+        ++nflush;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&pp.proc_full[pslot]);
+        mbar_arrive(&pp.raw_empty[rslot]);
+      }
+    }
+    if (extras) {
+      const int k = tt.k0 + tl;
+      if (p.sep0) p.singA[(int64_t)ti.cell * p.nv + k] = unpeel_log(PA, eA, nflush);
+      p.lb[(int64_t)ti.cell * p.nv + k] = unpeel_log(PB, eB, nflush);
+      if (p.want_single) p.p1[(int64_t)ti.cell * p.nv + k] = unpeel_log(P1, e1x, nflush);
+    }
+    if ((tt.flags & (TF_SCALARS | TF_L00)) && rw == 0) {
+      // each of the first NB lanes holds the product over "its" entries of every stage
+      double s0 = scal ? unpeel_log(PS0, eS0, nflush) : 0.0;
+      double s1 = scal ? unpeel_log(PS1, eS1, nflush) : 0.0;
+      double s2 = scal ? unpeel_log(PS2, eS2, nflush) : 0.0;
+#pragma unroll
+      for (int o = NB / 2; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      if (lane == 0) {
+        if (tt.flags & TF_SCALARS) {
+          if (p.want_single) p.p1_0[ti.cell] = s0;
+          if (p.sep0) p.l00[(int64_t)ti.cell * p.nA] = s1;
+        }
+        if (tt.flags & TF_L00) p.l00[(int64_t)ti.cell * p.nA + tt.n] = s2;
+      }
+    }
+  }
+}
+
+// =============================== fp32 transform warps ============================================
+// F_NTW = 2 warps.  A lane serves ONE entry slot of every stage (e = 4 * warp + lane / 8) and EIGHT samples of each
+// side (8 * (lane & 7) ...), so that everything moves as 16-byte vectors: the 24 floats of its samples' GP rows
+// (6 LDS.128), and the (a, w) vectors of two 4-sample blocks per side (12 STS.128).  Lanes 4..7 of a quarter warp
+// visit their two blocks in the opposite order, which makes both access patterns bank-conflict free.
+// w_k[l] = sum_m Q'[l][m] gp_k[m] is evaluated in fp32 (Q' rounded to fp32 once per lane and stage); the per-sample
+// extras (singlet factor of the separable plane, row sums, pass 1) and the scalars stay in fp64 running products,
+// one set per lane = per entry slot, folded over the eight entry slots at the end of a task.
+struct TScratch {
+  double xfer[2][3][BLK];            // [task parity][PA, PB, P1][sample]: partial logs of warp 1
+  double xs[2][4];                   // [task parity][s0, s1, s2]
+};
+constexpr uint32_t F_TS_BYTES = (sizeof(TScratch) + 127) / 128 * 128;
+
+template <bool SAME, bool EXTRAS>
+__device__ __forceinline__ void transform_entry_f32(const unsigned char* __restrict__ rs, float* __restrict__ pf, int e,
+                                                    int sgrp, uint32_t jm, uint32_t km, double (&PA)[8], double (&PB)[8],
+                                                    double (&P1)[8]) {
+  const int flip = sgrp >> 2;
+  // Q'[l][m] of this entry, row-major, rounded to fp32
+  const double2* qp = reinterpret_cast<const double2*>(rs + OFF_QP) + e * (QPLANE / 2);
+  const double2 qa = qp[0], qb = qp[1], qc = qp[2], qd = qp[3];
+  const float q00 = (float)qa.x, q01 = (float)qa.y, q02 = (float)qb.x, q10 = (float)qb.y, q11 = (float)qc.x,
+              q12 = (float)qc.y, q20 = (float)qd.x, q21 = (float)qd.y, q22 = (float)qp[4].x;
+  double h[6];
+  if (EXTRAS) {
+    const double2* qh = reinterpret_cast<const double2*>(rs + OFF_QH) + e * (QHEAD / 2);
+    const double2 h0 = qh[0], h1 = qh[1], h2 = qh[2];   // GL0 GL1 | GL2 f0 | f1 f2
+    h[0] = h0.x; h[1] = h0.y; h[2] = h1.x; h[3] = h1.y; h[4] = h2.x; h[5] = h2.y;
+  }
+  const int s0 = 8 * sgrp;
+  const unsigned char* rk = SAME ? rs + OFF_GPJ + (s0 >> 5) * HALF_BYTES + e * GROW + (s0 & 31) * 12
+                                 : rs + OFF_GPK + e * GROW + (s0 & 31) * 12;
+  const unsigned char* rj = rs + OFF_GPJ + (s0 >> 5) * HALF_BYTES + e * GROW + (s0 & 31) * 12;
+  float* af = pf + (2 * sgrp) * F_BLK4_FLT + e * 12;
+  float* wf = af + F_SIDE_FLT;
+#pragma unroll
+  for (int hb = 0; hb < 2; ++hb) {
+    const int b = hb ^ flip;                      // 4-sample block of this lane's eight samples
+    float g[12];
+    if (SAME || sgrp < 4) {
+      const float4* src = reinterpret_cast<const float4*>(rk + b * 48);
+      const float4 x = src[0], y = src[1], z = src[2];
+      g[0] = x.x; g[1] = x.y; g[2] = x.z; g[3] = x.w; g[4] = y.x; g[5] = y.y; g[6] = y.z; g[7] = y.w;
+      g[8] = z.x; g[9] = z.y; g[10] = z.z; g[11] = z.w;
+      float w[12];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float f0 = g[3 * i], f1 = g[3 * i + 1], f2 = g[3 * i + 2];
+        const bool kv = (km >> (4 * b + i)) & 1u;
+        w[3 * i + 0] = kv ? fmaf(q02, f2, fmaf(q01, f1, q00 * f0)) : 1.0f;
+        w[3 * i + 1] = kv ? fmaf(q12, f2, fmaf(q11, f1, q10 * f0)) : 0.0f;
+        w[3 * i + 2] = kv ? fmaf(q22, f2, fmaf(q21, f1, q20 * f0)) : 0.0f;
+        if (EXTRAS) {
+          const double g0 = (double)f0, g1 = (double)f1, g2 = (double)f2;
+          PA[4 * hb + i] *= fma(h[5], g2, fma(h[4], g1, h[3] * g0));
+          PB[4 * hb + i] *= (g0 + g1) + g2;
+          P1[4 * hb + i] *= fma(h[2], g2, fma(h[1], g1, h[0] * g0));
+        }
+      }
+      float4* dw = reinterpret_cast<float4*>(wf + b * F_BLK4_FLT);
+      dw[0] = make_float4(w[0], w[1], w[2], w[3]);
+      dw[1] = make_float4(w[4], w[5], w[6], w[7]);
+      dw[2] = make_float4(w[8], w[9], w[10], w[11]);
+    }
+    if (!SAME) {
+      const float4* src = reinterpret_cast<const float4*>(rj + b * 48);
+      const float4 x = src[0], y = src[1], z = src[2];
+      g[0] = x.x; g[1] = x.y; g[2] = x.z; g[3] = x.w; g[4] = y.x; g[5] = y.y; g[6] = y.z; g[7] = y.w;
+      g[8] = z.x; g[9] = z.y; g[10] = z.z; g[11] = z.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const bool jv = (jm >> (4 * b + i)) & 1u;
+      g[3 * i] = jv ? g[3 * i] : 1.0f;
+      g[3 * i + 1] = jv ? g[3 * i + 1] : 0.0f;
+      g[3 * i + 2] = jv ? g[3 * i + 2] : 0.0f;
+    }
+    float4* da = reinterpret_cast<float4*>(af + b * F_BLK4_FLT);
+    da[0] = make_float4(g[0], g[1], g[2], g[3]);
+    da[1] = make_float4(g[4], g[5], g[6], g[7]);
+    da[2] = make_float4(g[8], g[9], g[10], g[11]);
+  }
+}
+
+__device__ __forceinline__ void transform_role_f32(const ScanParams& p, const Pipe& pp, TScratch* ts, int tw, int lane,
+                                                   int u, int NS) {
+  const int sgrp = lane & 7, e = tw * 4 + (lane >> 3);
+  const int flip = sgrp >> 2, s0 = 8 * sgrp;
+  uint32_t git = 0;
+  TaskInfo ti;
+  for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
+    const TaskType tt = p.tt[ti.tti];
+    const bool same = tt.flags & TF_TRI;
+    const bool extras_t = tt.flags & TF_EXTRAS;
+    const bool scal_t = tt.flags & (TF_SCALARS | TF_L00);
+    const bool scal = scal_t && sgrp == 0;            // this lane also carries the scalars of its entry slot
+    // validity masks of this lane's eight samples on each side (bit = 4 * block + i)
+    uint32_t jm = 0, km = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (s0 + i < tt.nj) jm |= 1u << i;
+      if (same ? (s0 + i < tt.nj) : (s0 + i < tt.nk)) km |= 1u << i;
+    }
+    double PA[8], PB[8], P1[8];                       // running products (extras), slot h = 4 * hb + i
+    int eA[8], eB[8], e1x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { PA[i] = PB[i] = P1[i] = 1.0; eA[i] = eB[i] = e1x[i] = 0; }
+    double PS0 = 1.0, PS1 = 1.0, PS2 = 1.0;           // scalars: llk0s, llks00[sep], llks00[n]
+    int eS0 = 0, eS1 = 0, eS2 = 0;
+    int nflush = 0;
+    for (int it = 0; it < ti.nst; ++it, ++git) {
+      const int rslot = git % F_S_RAW, pslot = git % F_S_PROC;
+      const uint32_t rph = (git / F_S_RAW) & 1u, pph = (git / F_S_PROC) & 1u;
+      const int nvalid = (int)min((int64_t)NB, ti.e1 - (ti.e0 + (int64_t)it * NB));
+      mbar_wait(&pp.raw_full[rslot], rph);
+      mbar_wait(&pp.proc_empty[pslot], pph ^ 1u);
+      const unsigned char* rs = pp.raw_base + (size_t)rslot * RAW_SLOT;
+      float* pf = reinterpret_cast<float*>(pp.proc_base + (size_t)pslot * F_PROC_SLOT);
+      if (e < nvalid) {
+        if (same) {
+          if (extras_t) transform_entry_f32<true, true>(rs, pf, e, sgrp, jm, km, PA, PB, P1);
+          else transform_entry_f32<true, false>(rs, pf, e, sgrp, jm, km, PA, PB, P1);
+        } else {
+          if (extras_t) transform_entry_f32<false, true>(rs, pf, e, sgrp, jm, km, PA, PB, P1);
+          else transform_entry_f32<false, false>(rs, pf, e, sgrp, jm, km, PA, PB, P1);
+        }
+        if (scal) {
+          const double* z = reinterpret_cast<const double*>(rs + OFF_GP0) + e * 4;
+          const double* hq = reinterpret_cast<const double*>(rs + OFF_QH) + e * QHEAD;
+          const double* q = reinterpret_cast<const double*>(rs + OFF_QP) + e * QPLANE;
+          const double z0 = z[0], z1 = z[1], z2 = z[2];
+          if (tt.flags & TF_SCALARS) {
+            if (p.want_single) PS0 *= fma(hq[2], z2, fma(hq[1], z1, hq[0] * z0));                    // :459
+            if (p.sep0) PS1 *= fma(hq[5], z2, fma(hq[4], z1, hq[3] * z0)) * ((z0 + z1) + z2);
+          }
+          if (tt.flags & TF_L00) {                                                                   // :700-709
+            const double t0 = fma(q[2], z2, fma(q[1], z1, q[0] * z0));
+            const double t1 = fma(q[5], z2, fma(q[4], z1, q[3] * z0));
+            const double t2 = fma(q[8], z2, fma(q[7], z1, q[6] * z0));
+            PS2 *= fma(z2, t2, fma(z1, t1, z0 * t0));
+          }
+        }
+      } else {   // identity entry: S = 1 for every hypothesis
+        float* af = pf + (2 * sgrp) * F_BLK4_FLT + e * 12;
+        const float4 i0 = make_float4(1.f, 0.f, 0.f, 1.f), i1 = make_float4(0.f, 0.f, 1.f, 0.f),
+                     i2 = make_float4(0.f, 1.f, 0.f, 0.f);
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+          const int b = hb ^ flip;
+          float4* da = reinterpret_cast<float4*>(af + b * F_BLK4_FLT);
+          float4* dw = reinterpret_cast<float4*>(af + F_SIDE_FLT + b * F_BLK4_FLT);
+          da[0] = i0; da[1] = i1; da[2] = i2;
+          dw[0] = i0; dw[1] = i1; dw[2] = i2;
+        }
+      }
+      if ((it & 15) == 15) {   // every 16 entries of this lane
+        if (extras_t) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { peel(PA[i], eA[i]); peel(PB[i], eB[i]); peel(P1[i], e1x[i]); }
+        }
+        peel(PS0, eS0); peel(PS1, eS1); peel(PS2, eS2);
+        ++nflush;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&pp.proc_full[pslot]);
+        mbar_arrive(&pp.raw_empty[rslot]);
+      }
+    }
+    if (!(extras_t || scal_t)) continue;   // uniform over the transform warps
+    const int buf = r & 1;
+    // fold the four entry slots of this warp (lanes 8 apart), then the two warps through shared memory
+    double la[8], lbv[8], l1[8];
+    if (extras_t) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        la[i] = p.sep0 ? unpeel_log(PA[i], eA[i], nflush) : 0.0;
+        lbv[i] = unpeel_log(PB[i], eB[i], nflush);
+        l1[i] = p.want_single ? unpeel_log(P1[i], e1x[i], nflush) : 0.0;
+#pragma unroll
+        for (int o = 8; o < 32; o <<= 1) {
+          la[i] += __shfl_xor_sync(0xffffffffu, la[i], o);
+          lbv[i] += __shfl_xor_sync(0xffffffffu, lbv[i], o);
+          l1[i] += __shfl_xor_sync(0xffffffffu, l1[i], o);
+        }
+      }
+    }
+    double s0v = 0.0, s1v = 0.0, s2v = 0.0;
+    if (scal_t) {
+      s0v = scal ? unpeel_log(PS0, eS0, nflush) : 0.0;
+      s1v = scal ? unpeel_log(PS1, eS1, nflush) : 0.0;
+      s2v = scal ? unpeel_log(PS2, eS2, nflush) : 0.0;
+#pragma unroll
+      for (int o = 8; o < 32; o <<= 1) {
+        s0v += __shfl_xor_sync(0xffffffffu, s0v, o);
+        s1v += __shfl_xor_sync(0xffffffffu, s1v, o);
+        s2v += __shfl_xor_sync(0xffffffffu, s2v, o);
+      }
+    }
+    if (tw == 1 && lane < 8) {
+      if (extras_t) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int smp = s0 + 4 * ((i >> 2) ^ flip) + (i & 3);
+          ts->xfer[buf][0][smp] = la[i];
+          ts->xfer[buf][1][smp] = lbv[i];
+          ts->xfer[buf][2][smp] = l1[i];
+        }
+      }
+      if (scal_t && lane == 0) { ts->xs[buf][0] = s0v; ts->xs[buf][1] = s1v; ts->xs[buf][2] = s2v; }
+    }
+    asm volatile("bar.sync 2, %0;" ::"n"(F_NTW * 32) : "memory");
+    if (tw == 0 && lane < 8) {
+      if (extras_t) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int smp = s0 + 4 * ((i >> 2) ^ flip) + (i & 3);
+          const int k = tt.k0 + smp;
+          if (smp < tt.nk && k < p.nv) {
+            if (p.sep0) p.singA[(int64_t)ti.cell * p.nv + k] = la[i] + ts->xfer[buf][0][smp];
+            p.lb[(int64_t)ti.cell * p.nv + k] = lbv[i] + ts->xfer[buf][1][smp];
+            if (p.want_single) p.p1[(int64_t)ti.cell * p.nv + k] = l1[i] + ts->xfer[buf][2][smp];
+          }
+        }
+      }
+      if (scal_t && lane == 0) {
+        if (tt.flags & TF_SCALARS) {
+          if (p.want_single) p.p1_0[ti.cell] = s0v + ts->xs[buf][0];
+          if (p.sep0) p.l00[(int64_t)ti.cell * p.nA] = s1v + ts->xs[buf][1];
+        }
+        if (tt.flags & TF_L00) p.l00[(int64_t)ti.cell * p.nA + tt.n] = s2v + ts->xs[buf][2];
+      }
+    }
+  }
+}
+
+// =============================== per-task reductions (:712-734, :799-814) ==========================
+// Every consumer thread brings NV llk values with their (j, k); the block of NW consumer warps reduces them to
+// the task's Part (max, sum of exp, best pair value, near-tie candidates) and stores row 0 / the dense block.
+template <int NV, int NW>
+__device__ __forceinline__ void task_epilogue(const ScanParams& p, const TaskInfo& ti, const TaskType& tt, Scratch* scr,
+                                              int bar_id, int rw, int lane, const double (&v)[NV], const int (&vj)[NV],
+                                              const int (&vk)[NV], uint32_t vmask) {
+  const bool sym = tt.flags & TF_SYM;
+  const bool noarg = tt.flags & TF_NOARG;
+  double m_all = -INFINITY, best = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const double x = (vmask >> i) & 1u ? v[i] : -INFINITY;
+    m_all = fmax(m_all, x);
+    if (vj[i] != vk[i]) best = fmax(best, x);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m_all = fmax(m_all, __shfl_xor_sync(0xffffffffu, m_all, o));
+    best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+  }
+  if (lane == 0) { scr->red[0][rw] = m_all; scr->red[1][rw] = best; }
+  consumer_bar_sync<NW * 32>(bar_id);
+  m_all = scr->red[0][0]; best = scr->red[1][0];
+#pragma unroll
+  for (int wq = 1; wq < NW; ++wq) {
+    m_all = fmax(m_all, scr->red[0][wq]);
+    best = fmax(best, scr->red[1][wq]);
+  }
+  const double thr = best - (p.eps_rel * fmax(1.0, fabs(best)) + p.eps_ent * (double)(ti.e1 - ti.e0));
+  double sd = 0.0;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (!((vmask >> i) & 1u)) continue;
+    const int j = vj[i], k = vk[i];
+    const double x = v[i];
+    if (j != k) {
+      sd += exp(x - m_all);
+      if (!noarg && x >= thr) {
+        const int cs = atomicAdd(&scr->ncand, 1);
+        if (cs < MAX_CAND) scr->cand[cs] = (uint32_t)j | ((uint32_t)k << 12);
+      }
+    }
+    // row k = 0 of the plane (LLK10 / LLK20, :824-825; singlets when plane 0 is dense)
+    if (sym) {
+      if (j == 0) p.row0[((int64_t)ti.cell * p.nA + tt.n) * p.nv + k] = x;
+    } else if (k == 0) {
+      p.row0[((int64_t)ti.cell * p.nA + tt.n) * p.nv + j] = x;
+    }
+    if (p.dense) {
+      double* d = p.dense + ti.aidx * p.nv * p.nv * p.nA;
+      d[((int64_t)j * p.nv + k) * p.nA + tt.n] = x;
+      if (sym) d[((int64_t)k * p.nv + j) * p.nA + tt.n] = x;
+    }
+  }
+  if (sym) sd *= 2.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
+  if (lane == 0) scr->red2[rw] = sd;
+  consumer_bar_sync<NW * 32>(bar_id);
+  if (rw == 0 && lane == 0) {
+    double tot = 0.0;
+    for (int wq = 0; wq < NW; ++wq) tot += scr->red2[wq];
+    Part* out = p.parts + ti.aidx * p.T + ti.tti;
+    out->m_all = m_all;
+    out->sd = tot;
+    out->best_v = best;
+    out->ncand = scr->ncand;
+    out->pad = 0;
+    for (int c = 0; c < MAX_CAND; ++c) out->cand[c] = scr->cand[c];
+    scr->ncand = 0;
+  }
+  consumer_bar_sync<NW * 32>(bar_id);
 }
 
 // D (8 x 8) = A (8 x 4, row) * B (4 x 8, col) in FP64 on the tensor cores (SASS: DMMA.8x8x4).  Fragments: lane
@@ -421,16 +950,15 @@ __device__ __forceinline__ void consume_stage(const double* __restrict__ pa, con
     }
   }
 }
-
-template <bool SAME, bool EXTRAS>
-__device__ __forceinline__ void transform_dispatch(const unsigned char* rs, double* pa, int tl, int nvalid,
-                                                   double& PA, double& PB, double& P1) {
-  if (nvalid == NB) transform_stage<SAME, true, EXTRAS>(rs, pa, tl, nvalid, PA, PB, P1);
-  else transform_stage<SAME, false, EXTRAS>(rs, pa, tl, nvalid, PA, PB, P1);
-}
 }  // namespace
 
-__global__ void __launch_bounds__(NTHREADS, 1) pair_scan_kernel(const __grid_constant__ ScanParams p) {
+// Warp roles of the fp64 kernel.  SM sub-partition = warp id % 4; the FP64 pipe is the bound, so the consumer
+// warps (C) are spread 3/3/2/2 over the four sub-partitions and the lighter transform (T) and loader (L) warps
+// fill the rest:
+//   wid  0  1  2  3 |  4  5  6  7 |  8  9 10 11 | 12 13 14 15
+//        CA CA CA CA| CA CB CB CB | CB CB TA TA | LA LB TB TB        (A, B = slot)
+__global__ void __launch_bounds__(NTHREADS, 1) pair_scan_kernel(const __grid_constant__ ScanParams p,
+                                                                const __grid_constant__ ScanMaps tm) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // role decode (see table above)
@@ -442,13 +970,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_scan_kernel(const __grid_con
   else { role = 1; slot = 1; rw = warp - 14; }
 
   unsigned char* sb = smem + (size_t)slot * SLOT_BYTES;
-  uint64_t* raw_full = reinterpret_cast<uint64_t*>(sb);
-  uint64_t* raw_empty = raw_full + S_RAW;
-  uint64_t* proc_full = raw_empty + S_RAW;
-  uint64_t* proc_empty = proc_full + S_PROC;
-  Scratch* scr = reinterpret_cast<Scratch*>(sb + 128);
-  unsigned char* raw_base = sb + SLOT_CTRL;
-  unsigned char* proc_base = raw_base + S_RAW * RAW_SLOT;
+  Pipe pp;
+  pp.raw_full = reinterpret_cast<uint64_t*>(sb);
+  pp.raw_empty = pp.raw_full + S_RAW;
+  pp.proc_full = pp.raw_empty + S_RAW;
+  pp.proc_empty = pp.proc_full + S_PROC;
+  Scratch* scr = reinterpret_cast<Scratch*>(sb + SCRATCH_OFF);
+  pp.raw_base = sb + SLOT_CTRL;
+  pp.proc_base = pp.raw_base + S_RAW * RAW_SLOT;
 
   if (threadIdx.x < NSLOT) {
     unsigned char* b = smem + (size_t)threadIdx.x * SLOT_BYTES;
@@ -461,7 +990,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_scan_kernel(const __grid_con
       mbar_init(&bars[2 * S_RAW + s], NTW);
       mbar_init(&bars[2 * S_RAW + S_PROC + s], NCW);
     }
-    reinterpret_cast<Scratch*>(b + 128)->ncand = 0;
+    reinterpret_cast<Scratch*>(b + SCRATCH_OFF)->ncand = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -474,130 +1003,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_scan_kernel(const __grid_con
 
   const int NS = (int)gridDim.x * NSLOT;
   const int u = (int)blockIdx.x * NSLOT + slot;
-  uint32_t git = 0;   // stages issued so far in this slot (same sequence in every role)
-  TaskInfo ti;
 
   if (role == 2) {
-    // =============================== loader warp ===============================================
-    const int sub = lane % NB, kind = lane / NB;   // kind 0: GP rows + gp0, 1: record head, 2: record plane
-    const int64_t rowstride = (int64_t)p.nvp * 3;   // floats
-    for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
-      const TaskType tt = p.tt[ti.tti];
-      const bool same = tt.flags & TF_TRI;
-      const bool need_head = tt.flags & (TF_EXTRAS | TF_SCALARS);
-      const bool need_z = tt.flags & (TF_SCALARS | TF_L00);
-      const uint32_t rowj = (uint32_t)tt.nj * 12u, rowk = same ? 0u : (uint32_t)tt.nk * 12u;
-      const uint32_t per_entry = rowj + rowk + (need_z ? 32u : 0u) + (need_head ? 48u : 0u) + 80u;
-      for (int it = 0; it < ti.nst; ++it, ++git) {
-        const int rslot = git % S_RAW;
-        const uint32_t ph = (git / S_RAW) & 1u;
-        const int64_t eb = ti.e0 + (int64_t)it * NB;
-        const int nvalid = (int)min((int64_t)NB, ti.e1 - eb);
-        const bool mine = sub < nvalid && kind < 3;
-        int snp = 0;
-        if (mine && kind == 0) snp = __ldg(p.ent_snp + eb + sub);
-        mbar_wait(&raw_empty[rslot], ph ^ 1u);
-        unsigned char* rs = raw_base + (size_t)rslot * RAW_SLOT;
-        if (lane == 0) mbar_expect_tx(&raw_full[rslot], (uint32_t)nvalid * per_entry);
-        __syncwarp();
-        if (mine) {
-          if (kind == 0) {
-            const float* row = p.gp + (int64_t)snp * rowstride;
-            bulk_g2s(rs + OFF_GPJ + sub * ROWJ_STRIDE, row + tt.j0 * 3, rowj, &raw_full[rslot]);
-            if (!same) bulk_g2s(rs + OFF_GPK + sub * ROWK_STRIDE, row + tt.k0 * 3, rowk, &raw_full[rslot]);
-            if (need_z) bulk_g2s(rs + OFF_GP0 + sub * 32, p.gp0 + (int64_t)snp * 4, 32u, &raw_full[rslot]);
-          } else if (kind == 1) {
-            if (need_head) bulk_g2s(rs + OFF_Q + sub * Q_STRIDE, p.entq + (eb + sub) * p.UQ, 48u, &raw_full[rslot]);
-          } else {
-            bulk_g2s(rs + OFF_Q + sub * Q_STRIDE + 48, p.entq + (eb + sub) * p.UQ + tt.qoff, 80u, &raw_full[rslot]);
-          }
-        }
-      }
-    }
+    loader_role<S_RAW>(p, tm, pp, lane, u, NS);
   } else if (role == 1) {
-    // =============================== transform warps ===========================================
-    const int tl = rw * 32 + lane;        // sample slot on each side
-    for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
-      const TaskType tt = p.tt[ti.tti];
-      const bool same = tt.flags & TF_TRI;
-      const bool do_k = tl < tt.nk;
-      const bool k_valid = (tt.k0 + tl) < p.nv;
-      const bool extras = (tt.flags & TF_EXTRAS) && do_k && k_valid;
-      const bool scal = (tt.flags & (TF_SCALARS | TF_L00)) && rw == 0 && lane < NB;
-      double PA = 1.0, PB = 1.0, P1 = 1.0;            // running products (extras)
-      int eA = 0, eB = 0, e1x = 0;
-      double PS0 = 1.0, PS1 = 1.0, PS2 = 1.0;         // scalars: llk0s, llks00[sep], llks00[n]; lane = entry slot
-      int eS0 = 0, eS1 = 0, eS2 = 0;
-      int nflush = 0;
-      for (int it = 0; it < ti.nst; ++it, ++git) {
-        const int rslot = git % S_RAW, pslot = git % S_PROC;
-        const uint32_t rph = (git / S_RAW) & 1u, pph = (git / S_PROC) & 1u;
-        const int nvalid = (int)min((int64_t)NB, ti.e1 - (ti.e0 + (int64_t)it * NB));
-        mbar_wait(&raw_full[rslot], rph);
-        mbar_wait(&proc_empty[pslot], pph ^ 1u);
-        const unsigned char* rs = raw_base + (size_t)rslot * RAW_SLOT;
-        double* pa = reinterpret_cast<double*>(proc_base + (size_t)pslot * PROC_SLOT);
-        if (same) {
-          if (tt.flags & TF_EXTRAS) transform_dispatch<true, true>(rs, pa, tl, nvalid, PA, PB, P1);
-          else transform_dispatch<true, false>(rs, pa, tl, nvalid, PA, PB, P1);
-        } else {
-          if (tt.flags & TF_EXTRAS) transform_dispatch<false, true>(rs, pa, tl, nvalid, PA, PB, P1);
-          else transform_dispatch<false, false>(rs, pa, tl, nvalid, PA, PB, P1);
-        }
-        if (scal && lane < nvalid) {
-          const double* z = reinterpret_cast<const double*>(rs + OFF_GP0) + lane * 4;
-          const double* q = reinterpret_cast<const double*>(rs + OFF_Q) + lane * (QHEAD + QPLANE);
-          const double z0 = z[0], z1 = z[1], z2 = z[2];
-          if (tt.flags & TF_SCALARS) {
-            if (p.want_single) PS0 *= fma(q[2], z2, fma(q[1], z1, q[0] * z0));                       // :459
-            if (p.sep0) PS1 *= fma(q[5], z2, fma(q[4], z1, q[3] * z0)) * ((z0 + z1) + z2);
-          }
-          if (tt.flags & TF_L00) {                                                                   // :700-709
-            const double t0 = fma(q[8], z2, fma(q[7], z1, q[6] * z0));
-            const double t1 = fma(q[11], z2, fma(q[10], z1, q[9] * z0));
-            const double t2 = fma(q[14], z2, fma(q[13], z1, q[12] * z0));
-            PS2 *= fma(z2, t2, fma(z1, t1, z0 * t0));
-          }
-        }
-        if ((it % FLUSH_STAGES) == FLUSH_STAGES - 1) {
-          peel(PA, eA); peel(PB, eB); peel(P1, e1x);
-          peel(PS0, eS0); peel(PS1, eS1); peel(PS2, eS2);
-          ++nflush;
-        }
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&proc_full[pslot]);
-          mbar_arrive(&raw_empty[rslot]);
-        }
-      }
-      if (extras) {
-        const int k = tt.k0 + tl;
-        if (p.sep0) p.singA[(int64_t)ti.cell * p.nv + k] = unpeel_log(PA, eA, nflush);
-        p.lb[(int64_t)ti.cell * p.nv + k] = unpeel_log(PB, eB, nflush);
-        if (p.want_single) p.p1[(int64_t)ti.cell * p.nv + k] = unpeel_log(P1, e1x, nflush);
-      }
-      if ((tt.flags & (TF_SCALARS | TF_L00)) && rw == 0) {
-        // each of the first NB lanes holds the product over "its" entries of every stage
-        double s0 = scal ? unpeel_log(PS0, eS0, nflush) : 0.0;
-        double s1 = scal ? unpeel_log(PS1, eS1, nflush) : 0.0;
-        double s2 = scal ? unpeel_log(PS2, eS2, nflush) : 0.0;
-#pragma unroll
-        for (int o = NB / 2; o > 0; o >>= 1) {
-          s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-        }
-        if (lane == 0) {
-          if (tt.flags & TF_SCALARS) {
-            if (p.want_single) p.p1_0[ti.cell] = s0;
-            if (p.sep0) p.l00[(int64_t)ti.cell * p.nA] = s1;
-          }
-          if (tt.flags & TF_L00) p.l00[(int64_t)ti.cell * p.nA + tt.n] = s2;
-        }
-      }
-    }
+    transform_role<false, S_RAW, S_PROC, PROC_SLOT>(p, pp, rw, lane, u, NS);
   } else {
     // =============================== consumer warps ============================================
+    uint32_t git = 0;   // stages consumed so far in this slot (same sequence in every role)
+    TaskInfo ti;
     const int lr = lane >> 2, lc = lane & 3;
     for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
       const TaskType tt = p.tt[ti.tti];
@@ -640,9 +1054,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_scan_kernel(const __grid_con
       for (int it = 0; it < ti.nst; ++it, ++git) {
         const int pslot = git % S_PROC;
         const uint32_t pph = (git / S_PROC) & 1u;
-        mbar_wait(&proc_full[pslot], pph);
+        mbar_wait(&pp.proc_full[pslot], pph);
         if (tmask) {
-          const double* pa = reinterpret_cast<const double*>(proc_base + (size_t)pslot * PROC_SLOT);
+          const double* pa = reinterpret_cast<const double*>(pp.proc_base + (size_t)pslot * PROC_SLOT);
           if (shape == 0) consume_stage<0>(pa, aoff, boff, tmask, acc);
           else if (shape == 1) consume_stage<1>(pa, aoff, boff, tmask, acc);
           else consume_stage<2>(pa, aoff, boff, tmask, acc);
@@ -653,90 +1067,204 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_scan_kernel(const __grid_con
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&proc_empty[pslot]);
+        if (lane == 0) mbar_arrive(&pp.proc_empty[pslot]);
       }
-      // ---- per-task reductions (:712-734, :799-814) ---------------------------------------------
-      const bool sym = tt.flags & TF_SYM;
-      const bool noarg = tt.flags & TF_NOARG;
-      double v[NTILE][2];
+      double v[NTILE * 2];
+      int vj[NTILE * 2], vk[NTILE * 2];
       uint32_t vmask = 0;
-      double m_all = -INFINITY, best = -INFINITY;
 #pragma unroll
       for (int t = 0; t < NTILE; ++t)
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const int j = tt.j0 + trow[t] * 8 + lr, k = tt.k0 + tcol[t] * 8 + 2 * lc + i;
           const bool valid = ((tmask >> t) & 1u) && j < p.nv && k < p.nv && (!tri || j <= k);
-          const double x = valid ? unpeel_log(acc[t][i], es[t][i], nflush) : -INFINITY;
-          v[t][i] = x;
+          v[t * 2 + i] = valid ? unpeel_log(acc[t][i], es[t][i], nflush) : -INFINITY;
+          vj[t * 2 + i] = j;
+          vk[t * 2 + i] = k;
           if (valid) vmask |= 1u << (t * 2 + i);
-          m_all = fmax(m_all, x);
-          if (j != k) best = fmax(best, x);
         }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        m_all = fmax(m_all, __shfl_xor_sync(0xffffffffu, m_all, o));
-        best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
-      }
-      if (lane == 0) { scr->red[0][rw] = m_all; scr->red[1][rw] = best; }
-      consumer_bar_sync(slot);
-      m_all = scr->red[0][0]; best = scr->red[1][0];
-#pragma unroll
-      for (int wq = 1; wq < NCW; ++wq) {
-        m_all = fmax(m_all, scr->red[0][wq]);
-        best = fmax(best, scr->red[1][wq]);
-      }
-      const double thr = best - p.eps_rel * fmax(1.0, fabs(best));
-      double sd = 0.0;
-#pragma unroll
-      for (int t = 0; t < NTILE; ++t)
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          if (!(vmask & (1u << (t * 2 + i)))) continue;
-          const int j = tt.j0 + trow[t] * 8 + lr, k = tt.k0 + tcol[t] * 8 + 2 * lc + i;
-          const double x = v[t][i];
-          if (j != k) {
-            sd += exp(x - m_all);
-            if (!noarg && x >= thr) {
-              const int cs = atomicAdd(&scr->ncand, 1);
-              if (cs < MAX_CAND) scr->cand[cs] = (uint32_t)j | ((uint32_t)k << 12);
-            }
-          }
-          // row k = 0 of the plane (LLK10 / LLK20, :824-825; singlets when plane 0 is dense)
-          if (sym) {
-            if (j == 0) p.row0[((int64_t)ti.cell * p.nA + tt.n) * p.nv + k] = x;
-          } else if (k == 0) {
-            p.row0[((int64_t)ti.cell * p.nA + tt.n) * p.nv + j] = x;
-          }
-          if (p.dense) {
-            double* d = p.dense + ti.aidx * p.nv * p.nv * p.nA;
-            d[((int64_t)j * p.nv + k) * p.nA + tt.n] = x;
-            if (sym) d[((int64_t)k * p.nv + j) * p.nA + tt.n] = x;
-          }
-        }
-      if (sym) sd *= 2.0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
-      if (lane == 0) scr->red2[rw] = sd;
-      consumer_bar_sync(slot);
-      if (rw == 0 && lane == 0) {
-        double tot = 0.0;
-        for (int wq = 0; wq < NCW; ++wq) tot += scr->red2[wq];
-        Part* out = p.parts + ti.aidx * p.T + ti.tti;
-        out->m_all = m_all;
-        out->sd = tot;
-        out->best_v = best;
-        out->ncand = scr->ncand;
-        out->pad = 0;
-        for (int c = 0; c < MAX_CAND; ++c) out->cand[c] = scr->cand[c];
-        scr->ncand = 0;
-      }
-      consumer_bar_sync(slot);
+      task_epilogue<NTILE * 2, NCW>(p, ti, tt, scr, slot, rw, lane, v, vj, vk, vmask);
     }
   }
 }
 
-size_t pair_scan_smem_bytes(const ScanParams& /*p*/, bool /*fp32*/) { return (size_t)NSLOT * SLOT_BYTES; }
+// ---------------------------------------------------------------------------------------------
+// fp32 pair scan.  Warps 0..8 consumers, 9..10 transform, 11 loader (SM sub-partition = warp % 4: 3 / 2+T / 2+T /
+// 2+L).  A consumer thread owns the 8 x 8 tile (bj, bk) of hypotheses for the entries e = lane & 7 of every
+// stage: per entry 12 LDS.128 (two 4-sample blocks of a, two of w), 64 x (FMUL + 2 FFMA) for S[j][k] and 64 FMUL
+// into the running products.  Every F_PEEL_STAGES entries the warp checks for products about to leave the fp32
+// range and, if any, peels all exponents into per-thread integer accumulators in shared memory.  At the end of a
+// task the eight entry lanes of a tile multiply their products together (in fp64, butterfly shuffles) and lane e
+// takes the log of column e.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(F_NTHREADS, 1) pair_scan_f32_kernel(const __grid_constant__ ScanParams p,
+                                                                    const __grid_constant__ ScanMaps tm) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Pipe pp;
+  pp.raw_full = reinterpret_cast<uint64_t*>(smem);
+  pp.raw_empty = pp.raw_full + F_S_RAW;
+  pp.proc_full = pp.raw_empty + F_S_RAW;
+  pp.proc_empty = pp.proc_full + F_S_PROC;
+  Scratch* scr = reinterpret_cast<Scratch*>(smem + SCRATCH_OFF);
+  pp.raw_base = smem + SLOT_CTRL;
+  pp.proc_base = pp.raw_base + F_S_RAW * RAW_SLOT;
+  int* es_base = reinterpret_cast<int*>(pp.proc_base + F_S_PROC * F_PROC_SLOT);
+  TScratch* ts = reinterpret_cast<TScratch*>(smem + F_SMEM_NOTS);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < F_S_RAW; ++s) {
+      mbar_init(&pp.raw_full[s], 1);
+      mbar_init(&pp.raw_empty[s], F_NTW);
+    }
+    for (int s = 0; s < F_S_PROC; ++s) {
+      mbar_init(&pp.proc_full[s], F_NTW);
+      mbar_init(&pp.proc_empty[s], F_NCW);
+    }
+    scr->ncand = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  // rings start from finite values: padding lanes of the transform may read slots no copy has written yet
+  for (uint32_t i = threadIdx.x; i < (F_S_RAW * RAW_SLOT + F_S_PROC * F_PROC_SLOT) / 4; i += F_NTHREADS)
+    reinterpret_cast<uint32_t*>(pp.raw_base)[i] = 0u;
+  __syncthreads();
+
+  const int NS = (int)gridDim.x, u = (int)blockIdx.x;
+  // warps 0..8 consumers (sub-partitions 0,1,2,3,0,1,2,3,0), 9..10 transform, 11 loader
+  if (warp == F_NCW + F_NTW) {
+    loader_role<F_S_RAW>(p, tm, pp, lane, u, NS);
+  } else if (warp >= F_NCW) {
+    transform_role_f32(p, pp, ts, warp - F_NCW, lane, u, NS);
+  } else {
+    // =============================== consumer warps ============================================
+    const int rw = warp, el = lane & 7;
+    const int pos = rw * 4 + (lane >> 3);
+    int* es = es_base + rw * 32 + lane;           // es[h * F_ES_STRIDE]: exponent sum of hypothesis h of this thread
+    uint32_t git = 0;
+    TaskInfo ti;
+    for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
+      const TaskType tt = p.tt[ti.tti];
+      const bool tri = tt.flags & TF_TRI;
+      const int nbj = (tt.nj + 7) >> 3, nbk = (tt.nk + 7) >> 3;   // 8-sample blocks on each side
+      int bj, bk;
+      if (tri) {   // row-major walk of the upper triangle of 8 x 8 blocks
+        int q = pos;
+        bj = 0;
+        while (q >= 8 - bj) { q -= 8 - bj; ++bj; }
+        bk = bj + q;
+      } else {
+        bj = pos >> 2;
+        bk = pos & 3;
+      }
+      const bool active = (tri || pos < 32) && bj < nbj && bk < nbk;
+      const uint32_t aoff = (uint32_t)(2 * bj) * F_BLK4_FLT + (uint32_t)el * 12u;                 // floats
+      const uint32_t woff = F_SIDE_FLT + (uint32_t)(2 * bk) * F_BLK4_FLT + (uint32_t)el * 12u;
+      float acc[64];
+#pragma unroll
+      for (int h = 0; h < 64; ++h) acc[h] = 1.0f;
+      int npeel = 0;
+      for (int it = 0; it < ti.nst; ++it, ++git) {
+        const int pslot = git % F_S_PROC;
+        const uint32_t pph = (git / F_S_PROC) & 1u;
+        mbar_wait(&pp.proc_full[pslot], pph);
+        if (active) {
+          const float* pf = reinterpret_cast<const float*>(pp.proc_base + (size_t)pslot * F_PROC_SLOT);
+          float a[8][3], w[8][3];
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {
+            const float4 x = *reinterpret_cast<const float4*>(pf + aoff + (q / 3) * F_BLK4_FLT + (q % 3) * 4);
+            const float4 y = *reinterpret_cast<const float4*>(pf + woff + (q / 3) * F_BLK4_FLT + (q % 3) * 4);
+            const float xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int f = (q % 3) * 4 + c;   // float index inside the 4-sample block
+              a[(q / 3) * 4 + f / 3][f % 3] = xs[c];
+              w[(q / 3) * 4 + f / 3][f % 3] = ys[c];
+            }
+          }
+          // one tile row at a time, eight independent chains in flight (source order = issue order for ptxas)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float s[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) s[c] = a[i][0] * w[c][0];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) s[c] = fmaf(a[i][1], w[c][1], s[c]);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) s[c] = fmaf(a[i][2], w[c][2], s[c]);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[i * 8 + c] *= s[c];
+          }
+        }
+        if ((it % F_PEEL_STAGES) == F_PEEL_STAGES - 1) {
+          float mn = 1.0f;
+#pragma unroll
+          for (int h = 0; h < 64; h += 2) mn = fminf(mn, fminf(acc[h], acc[h + 1]));
+          // the next F_PEEL_STAGES factors are >= (1e-6)^4 ~ 2^-80 in total: stay above 2^-126
+          if (__any_sync(0xffffffffu, active && mn < 0x1p-46f)) {
+            if (active) {
+#pragma unroll
+              for (int h = 0; h < 64; ++h) {
+                float x = acc[h];
+                uint32_t b = __float_as_uint(x);
+                int e = 0;
+                if (b < 0x00800000u) {          // zero stays zero (llk = -inf); a denormal is renormalised first
+                  x *= 0x1p64f;
+                  b = __float_as_uint(x);
+                  e = -64;
+                }
+                if (b != 0u) {
+                  e += (int)(b >> 23);
+                  acc[h] = __uint_as_float((b & 0x007fffffu) | 0x3f800000u);
+                } else {
+                  e = 127;
+                }
+                if (npeel == 0) es[h * F_ES_STRIDE] = e;
+                else es[h * F_ES_STRIDE] += e;
+              }
+            }
+            ++npeel;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pp.proc_empty[pslot]);
+      }
+      // ---- fold the eight entry lanes of each tile: lane e keeps column e ------------------------------
+      double dcol[8];
+      int ecol[8];
+#pragma unroll
+      for (int h = 0; h < 64; ++h) {
+        double dm = (double)acc[h];
+        int ee = npeel ? es[h * F_ES_STRIDE] : 0;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          dm *= __shfl_xor_sync(0xffffffffu, dm, o);
+          if (npeel) ee += __shfl_xor_sync(0xffffffffu, ee, o);
+        }
+        if ((h & 7) == el) { dcol[h >> 3] = dm; ecol[h >> 3] = ee; }
+      }
+      double v[8];
+      int vj[8], vk[8];
+      uint32_t vmask = 0;
+      const int ebias = 127 * 8 * npeel;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int j = tt.j0 + bj * 8 + i, k = tt.k0 + bk * 8 + el;
+        const bool valid = active && j < p.nv && k < p.nv && (!tri || j <= k);
+        v[i] = valid ? (double)(ecol[i] - ebias) * 0.693147180559945309417232121458 + log(dcol[i]) : -INFINITY;
+        vj[i] = j;
+        vk[i] = k;
+        if (valid) vmask |= 1u << i;
+      }
+      task_epilogue<8, F_NCW>(p, ti, tt, scr, 0, rw, lane, v, vj, vk, vmask);
+    }
+  }
+}
+
+size_t pair_scan_smem_bytes(const ScanParams& /*p*/, bool fp32) {
+  return fp32 ? (size_t)(F_SMEM_NOTS + F_TS_BYTES) : (size_t)NSLOT * SLOT_BYTES;
+}
 
 static int g_num_sms = 0;
 int pair_scan_init() {
@@ -745,19 +1273,27 @@ int pair_scan_init() {
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(pair_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NSLOT * SLOT_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(pair_scan_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_NOTS + F_TS_BYTES);
   return (int)e;
 }
 
-int launch_pair_scan(const ScanParams& p, bool fp32, void* stream) {
+int launch_pair_scan(const ScanParams& p, const ScanMaps& tm, bool fp32, void* stream) {
   if (p.ntasks == 0) return 0;
   if (g_num_sms == 0) {
     int rc = pair_scan_init();
     if (rc) return rc;
   }
   const size_t smem = pair_scan_smem_bytes(p, fp32);
-  int64_t grid = (p.ntasks + NSLOT - 1) / NSLOT;
-  if (grid > g_num_sms) grid = g_num_sms;
-  pair_scan_kernel<<<(unsigned)grid, NTHREADS, smem, (cudaStream_t)stream>>>(p);
+  if (fp32) {
+    int64_t grid = p.ntasks;
+    if (grid > g_num_sms) grid = g_num_sms;
+    pair_scan_f32_kernel<<<(unsigned)grid, F_NTHREADS, smem, (cudaStream_t)stream>>>(p, tm);
+  } else {
+    int64_t grid = (p.ntasks + NSLOT - 1) / NSLOT;
+    if (grid > g_num_sms) grid = g_num_sms;
+    pair_scan_kernel<<<(unsigned)grid, NTHREADS, smem, (cudaStream_t)stream>>>(p, tm);
+  }
   return (int)cudaGetLastError();
 }
 
@@ -792,7 +1328,8 @@ __global__ void merge_kernel(const __grid_constant__ MergeParams p, int64_t nact
   }
   double ss = 0.0, sdb = 0.0;
   for (int j = 0; j < nv; ++j) ss += exp(sing[j] - mx) * p.w_single;
-  const double thr = best - p.eps_rel * fmax(1.0, fabs(best));
+  const double eps_abs = p.eps_ent * (double)(p.cell_ptr[cell + 1] - p.cell_ptr[cell]);
+  const double thr = best - (p.eps_rel * fmax(1.0, fabs(best)) + eps_abs);
   CellOut o;
   o.ncand = 0;
   o.pad = 0;
@@ -835,7 +1372,7 @@ __global__ void merge_kernel(const __grid_constant__ MergeParams p, int64_t nact
     double m2 = -INFINITY;
     for (int j = 0; j < nv; ++j)
       if (j != i1) m2 = fmax(m2, sing[j]);
-    const double w = 2.0 * p.eps_rel * fmax(1.0, fabs(m2));
+    const double w = 2.0 * (p.eps_rel * fmax(1.0, fabs(m2)) + eps_abs);
     int close2 = 0;
     for (int j = 0; j < nv; ++j)
       if (j != i1 && sing[j] >= m2 - w) ++close2;

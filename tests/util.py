@@ -21,7 +21,7 @@ def run_both(plp, alphas=(0.0, 0.5), doublet_prior=0.5, min_total=0, min_uniq=0,
     return orc, ref, d
 
 
-def compare(ref, d, tol=LLK_TOL, check_single=True):
+def compare(ref, d, tol=LLK_TOL, check_single=True, prb_rtol=1e-6):
     """ref: oracle.run() dict; d: Demuxlet after run().  Returns max abs LLK error."""
     ob, gb = ref["best"], d.best()
     assert np.array_equal(ob["skipped"] != 0, gb["status"] != 0)
@@ -37,7 +37,7 @@ def compare(ref, d, tol=LLK_TOL, check_single=True):
             worst = max(worst, float(err.max()))
             assert err.max() <= tol, "%s max err %g" % (gf, err.max())
     for of, gf in PRB_FIELDS:
-        assert np.allclose(ob[of][live], gb[gf][live], rtol=1e-6, atol=1e-12), gf
+        assert np.allclose(ob[of][live], gb[gf][live], rtol=prb_rtol, atol=1e-12), gf
     sing, l00 = d.sing2()
     err = np.abs(sing - ref["sing"])[live]
     if err.size:
