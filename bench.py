@@ -94,8 +94,23 @@ class ClockSampler:
 
 
 def make_workload(name: str, rank: int, scale: float):
-    from demuxlet_b200.synth import make_config
-    return make_config(name, scale=scale, seed_offset=1000 * rank)
+    """synth-v1 workload of this rank; generation takes about a minute at the headline shape, so the flat
+    pileup is cached under $TMPDIR for repeated runs on the same box"""
+    from demuxlet_b200.synth import make_config, CONFIGS
+    from demuxlet_b200.plp import Pileup
+    path = os.path.join(tempfile.gettempdir(), "dmx_synth_%s_%g_%d.dmxp" % (name, scale, rank))
+    if os.path.exists(path):
+        try:
+            return Pileup.load(path), CONFIGS[name]["alphas"]
+        except Exception:
+            pass
+    plp, alphas = make_config(name, scale=scale, seed_offset=1000 * rank)
+    try:
+        plp.save(path + ".tmp%d" % os.getpid())
+        os.replace(path + ".tmp%d" % os.getpid(), path)
+    except Exception:
+        pass
+    return plp, alphas
 
 
 # -------------------------------------------------------------------------------------------------

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -94,8 +95,9 @@ struct dmx_ctx {
   bool have_gp = false, have_plp = false, gp_dirty = true, plp_dirty = true, uploaded = false, computed = false;
 
   // device
-  DevBuf<float> d_gp;
-  DevBuf<double> d_gp0, d_entq, d_row0, d_singA, d_lb, d_p1, d_p1_0, d_l00, d_sing, d_dense;
+  DevBuf<float> d_gp;              // uploaded [nsnps][nvp*3]
+  DevBuf<float> d_gprow;           // [nsnps][8 + nvp*3]: gp0 | samples (gprow_kernel)
+  DevBuf<double> d_entq, d_row0, d_singA, d_lb, d_p1, d_p1_0, d_l00, d_sing, d_dense;
   DevBuf<int64_t> d_cell_ptr, d_ent_ptr;
   DevBuf<int32_t> d_ent_snp, d_order;
   DevBuf<uint16_t> d_reads;
@@ -116,7 +118,8 @@ struct dmx_ctx {
 
   std::vector<dmx_best_rec> best;
   dmx_stats st;
-  ScanMaps maps;                    // TMA descriptors of d_gp / d_gp0 / d_entq (encode_maps)
+  DevBuf<long long> d_dbg;
+  ScanMaps maps;                    // TMA descriptors of d_gprow / d_entq (encode_maps)
 };
 
 namespace {
@@ -222,14 +225,19 @@ int encode_2d(CUtensorMap* m, CUtensorMapDataType dt, size_t esize, void* base, 
   return DMX_OK;
 }
 
-// descriptors of the pair scan's inputs; call after d_gp / d_gp0 / d_entq have their final addresses
+// descriptors of the pair scan's inputs; call after d_gprow / d_entq have their final addresses
 int encode_maps(dmx_ctx* c) {
   memset(&c->maps, 0, sizeof(c->maps));
   if (c->nsnps == 0 || c->E == 0) return DMX_OK;   // nothing is launched
-  int rc = encode_2d(&c->maps.gp, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c->d_gp.p, (uint64_t)c->nvp * 3,
-                     (uint64_t)c->nsnps, 96, 1);
+  const uint64_t rowlen = (uint64_t)c->nvp * 3 + 8;
+  int rc = encode_2d(&c->maps.gpj, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c->d_gprow.p, rowlen, (uint64_t)c->nsnps,
+                     8 + BLK * 3, 1);
   if (rc == DMX_OK)
-    rc = encode_2d(&c->maps.gp0, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, c->d_gp0.p, 4, (uint64_t)c->nsnps, 4, 1);
+    rc = encode_2d(&c->maps.gpk, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c->d_gprow.p, rowlen, (uint64_t)c->nsnps,
+                   8 + BLK_RECT_K * 3, 1);
+  if (rc == DMX_OK && c->UQ == QHEAD + QPLANE)
+    rc = encode_2d(&c->maps.q, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, c->d_entq.p, (uint64_t)c->UQ, (uint64_t)c->E,
+                   QHEAD + QPLANE, NB);
   if (rc == DMX_OK)
     rc = encode_2d(&c->maps.qh, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, c->d_entq.p, (uint64_t)c->UQ, (uint64_t)c->E,
                    QHEAD, NB);
@@ -325,7 +333,15 @@ void fill_scan_params(dmx_ctx* c, ScanParams* p) {
   p->eps_rel = 1e-9;
   // fp32 pair scan: |error of a llk| <= entries * (a few fp32 ulps); 2^-20 per entry leaves a wide margin
   p->eps_ent = (c->cfg.flags & DMX_FP32_PAIRS) ? 0x1p-20 : 0.0;
-  p->gp = c->d_gp.p; p->gp0 = c->d_gp0.p; p->ent_snp = c->d_ent_snp.p; p->entq = c->d_entq.p;
+  if (c->UQ == QHEAD + QPLANE) { p->q_hp = (QHEAD + QPLANE) * 8; p->q_po = QHEAD * 8; p->q_pp = (QHEAD + QPLANE) * 8; }
+  else { p->q_hp = QHEAD * 8; p->q_po = NB * QHEAD * 8; p->q_pp = QPLANE * 8; }
+  p->gp_stride = c->nvp * 3 + 8;
+  p->dbg = getenv("DMX_DEBUG") ? atoi(getenv("DMX_DEBUG")) : 0;
+  if (p->dbg & 8) {
+    c->d_dbg.reserve(272 * 8);
+    p->dbgbuf = c->d_dbg.p;
+  }
+  p->gp = c->d_gprow.p + 8; p->ent_snp = c->d_ent_snp.p; p->entq = c->d_entq.p;
   p->cell_ptr = c->d_cell_ptr.p; p->cell_order = c->d_order.p; p->tt = c->d_tt.p; p->parts = c->d_parts.p;
   p->row0 = c->d_row0.p; p->singA = c->d_singA.p; p->lb = c->d_lb.p; p->p1 = c->d_p1.p;
   p->p1_0 = c->d_p1_0.p; p->l00 = c->d_l00.p; p->dense = nullptr;
@@ -478,7 +494,7 @@ void dmx_destroy(dmx_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  c->d_gp.release(); c->d_gp0.release(); c->d_entq.release(); c->d_row0.release(); c->d_singA.release();
+  c->d_gp.release(); c->d_gprow.release(); c->d_entq.release(); c->d_row0.release(); c->d_singA.release();
   c->d_lb.release(); c->d_p1.release(); c->d_p1_0.release(); c->d_l00.release(); c->d_sing.release();
   c->d_dense.release(); c->d_cell_ptr.release(); c->d_ent_ptr.release(); c->d_ent_snp.release();
   c->d_order.release(); c->d_reads.release(); c->d_tt.release(); c->d_parts.release(); c->d_out.release();
@@ -579,7 +595,7 @@ int dmx_upload(dmx_ctx* c) {
   }
   if (c->gp_dirty) {
     CU(c->d_gp.reserve((size_t)c->nsnps * nvp * 3 + 4));
-    CU(c->d_gp0.reserve((size_t)c->nsnps * 4 + 4));
+    CU(c->d_gprow.reserve((size_t)c->nsnps * (nvp * 3 + 8) + 256));
     if (nvp == nv) {
       CU(cudaMemcpyAsync(c->d_gp.p, c->h_gp, (size_t)c->nsnps * nv * 3 * sizeof(float), cudaMemcpyHostToDevice,
                          c->stream));
@@ -623,7 +639,7 @@ int dmx_compute(dmx_ctx* c) {
   c->st.n_rescored = 0;
   c->st.n_fullcell = 0;
 
-  CU(c->d_entq.reserve((size_t)c->E * c->UQ + 2));
+  CU(c->d_entq.reserve((size_t)c->E * c->UQ + (size_t)NB * c->UQ + 2));   // slack: a stage always reads NB records
   CU(c->d_parts.reserve((size_t)nact * T + 1));
   CU(c->d_row0.reserve((size_t)nc * nA * nv + 1)); CU(c->d_singA.reserve((size_t)nc * nv + 1));
   CU(c->d_lb.reserve((size_t)nc * nv + 1)); CU(c->d_p1.reserve((size_t)nc * nv + 1));
@@ -641,9 +657,11 @@ int dmx_compute(dmx_ctx* c) {
   CU(cudaMemsetAsync(c->d_l00.p, 0, (size_t)nc * nA * sizeof(double), c->stream));
   CU(cudaMemsetAsync(c->d_row0.p, 0, (size_t)nc * nA * nv * sizeof(double), c->stream));
   CU(cudaMemsetAsync(c->d_out.p, 0, (size_t)nc * sizeof(CellOut), c->stream));
-  CU(launch_gp0(c->d_gp.p, c->d_gp0.p, c->nsnps, nv, c->nvp, c->stream));
+  CU(launch_gprow(c->d_gp.p, c->d_gprow.p, c->nsnps, nv, c->nvp, c->stream));
   EntqParams eq;
-  eq.U = c->pg.U; eq.UQ = c->UQ; eq.E = c->E; eq.ent_ptr = c->d_ent_ptr.p; eq.reads = c->d_reads.p;
+  eq.U = c->pg.U; eq.UQ = c->UQ; eq.E = c->E;
+  eq.nd = (c->UQ - QHEAD) / QPLANE; eq.sep0 = c->pg.sep0; eq.gp_stride = c->nvp * 3 + 8; eq.gprow = c->d_gprow.p;
+  eq.ent_snp = c->d_ent_snp.p; eq.ent_ptr = c->d_ent_ptr.p; eq.reads = c->d_reads.p;
   eq.entq = c->d_entq.p;
   memcpy(eq.pu, c->pg.pu, sizeof(double) * c->pg.U);
   {
@@ -672,6 +690,18 @@ int dmx_compute(dmx_ctx* c) {
   }
   CU(launch_pair_scan(sp, c->maps, (c->cfg.flags & DMX_FP32_PAIRS) != 0, c->stream));
   CU(cudaEventRecord(c->ev[2], c->stream));
+  if ((sp.dbg & 8) && getenv("DMX_TRACE")) {
+    std::vector<long long> tb(272 * 8);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(tb.data(), c->d_dbg.p, tb.size() * 8, cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(getenv("DMX_TRACE"), "w")) {
+      for (int i = 0; i < 272; ++i) {
+        for (int k = 0; k < 8; ++k) fprintf(f, "%lld ", tb[i * 8 + k]);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+  }
   MergeParams mp;
   memset(&mp, 0, sizeof(mp));
   mp.nv = nv; mp.nA = nA; mp.T = T; mp.sep0 = c->pg.sep0; mp.eps_rel = sp.eps_rel; mp.eps_ent = sp.eps_ent; mp.cell_ptr = c->d_cell_ptr.p;
@@ -692,9 +722,9 @@ int dmx_compute(dmx_ctx* c) {
   if (dev_rescore) {
     RescoreParams rp;
     memset(&rp, 0, sizeof(rp));
-    rp.nv = nv; rp.nvp = c->nvp; rp.nA = nA; rp.UQ = c->UQ; rp.sep0 = c->pg.sep0;
+    rp.nv = nv; rp.gp_stride = c->nvp * 3 + 8; rp.nA = nA; rp.UQ = c->UQ; rp.sep0 = c->pg.sep0;
     for (int n = 0; n < nA; ++n) rp.dense_idx[n] = (int8_t)c->dense_idx[n];
-    rp.gp = c->d_gp.p; rp.ent_snp = c->d_ent_snp.p; rp.entq = c->d_entq.p; rp.cell_ptr = c->d_cell_ptr.p;
+    rp.gp = c->d_gprow.p + 8; rp.ent_snp = c->d_ent_snp.p; rp.entq = c->d_entq.p; rp.cell_ptr = c->d_cell_ptr.p;
     rp.cell_order = c->d_order.p; rp.lists = c->d_lists.p;
     CU(launch_rescore(rp, nact, c->stream));
   }

@@ -18,8 +18,9 @@ constexpr int NCW = 5;         // consumer warps per slot (136 tiles of the 64 x
 constexpr int NTW = 2;         // transform warps per slot (one lane per sample of each side)
 constexpr int NSLOT = 2;       // independent task pipelines per CTA (one persistent CTA per SM)
 constexpr int NTHREADS = NSLOT * (NCW + NTW + 1) * 32;   // + 1 loader warp per slot = 512
-constexpr int QHEAD = 6;       // entry record head: 3 pass-1 GLs, 3 values of the separable plane
-constexpr int QPLANE = 10;     // doubles per dense plane in the entry record (9 + 1 pad: 80 B, 16-B aligned)
+constexpr int QHEAD = 8;       // entry record head: 3 pass-1 GLs, 3 values of the separable plane, the entry's llk0s
+                               // factor, its llks00 factor of a separable plane 0
+constexpr int QPLANE = 10;     // doubles per dense plane in the entry record: 9 Q' values + the entry's llks00[n] factor
 constexpr int GRP_DBL = 14;    // doubles per 4-sample group in the processed ring (12 + 2 pad: 112 B
                                // stride spreads 16-byte lane loads over all banks)
 constexpr int GRP_F32 = 12;    // floats per 4-sample group in the fp32 processed ring (48 B stride)
@@ -31,6 +32,7 @@ constexpr int F_NTW = 2;       // transform warps: a lane = one entry slot x eig
 constexpr int F_S_RAW = 6;     // stages of the raw ring
 constexpr int F_S_PROC = 4;    // stages of the processed ring
 constexpr int F_NTHREADS = (F_NCW + F_NTW + 1) * 32;   // 448
+constexpr bool F_TMA_LOADER = true;    // fp32 kernel: gather through TMA tile::gather4 (true) or per-lane cp.async
 constexpr int F_PEEL_STAGES = 4;   // underflow check period (stages = entries per thread)
 constexpr int MAX_CAND = 8;    // near-tie candidates kept per task / per cell
 constexpr int MAX_U = DMX_MAX_ALPHA * 6 + 3;   // distinct mixing proportions p(n,l,m)
@@ -90,11 +92,14 @@ struct ScanParams {
   int32_t sep0;                // alpha[0] == 0: the n = 0 plane is separable
   int32_t T;                   // task types per cell
   int32_t want_single;         // accumulate pass 1
+  int32_t q_hp, q_po, q_pp;    // raw-stage layout of the entry records: head pitch, plane offset, plane pitch (bytes)
+  long long* dbgbuf;           // DMX_DEBUG & 8: [256][8] clock64 stamps of block 0, second task
+  int32_t dbg;                 // DMX_DEBUG: timing experiments (1: skip consumer math, 2: skip transform math)
+  int32_t gp_stride;           // floats per GP row in HBM (8 + nvp*3); gp points at the first sample of row 0
   int64_t ntasks;              // nactive * T
   double eps_rel;              // candidate window, relative to max(1, |best|) ...
   double eps_ent;              // ... plus this much per pileup entry of the cell (fp32 pair scan error bound)
-  const float* gp;             // [nsnps][nvp*3], rows zero padded
-  const double* gp0;           // [nsnps][4]: cohort mean (x, y, z), 0
+  const float* gp;             // [nsnps][gp_stride] (first sample of row 0); the 3 doubles in front of a row are gp0
   const int32_t* ent_snp;      // [E]
   const double* entq;          // [E][UQ]: GL[3], sep-plane f[3], then QPLANE doubles per dense plane
   const int64_t* cell_ptr;     // [ncells+1]
@@ -110,12 +115,14 @@ struct ScanParams {
   double* dense;               // optional [nactive][nv][nv][nA]
 };
 
-// TMA descriptors of the pair scan's inputs (built by dmx_api.cu:encode_maps, passed as a __grid_constant__)
+// TMA descriptors of the pair scan's inputs (built by dmx_api.cu:encode_maps, passed as a __grid_constant__).
+// A GP row in HBM is [gp0: 3 doubles + 8 B pad][nvp x 3 floats] (gprow_kernel).
 struct ScanMaps {
-  CUtensorMap gp;    // float32 [nsnps][nvp*3], box {96, 1}: tile::gather4 of 4 SNP rows x 32 samples
-  CUtensorMap gp0;   // float64 [nsnps][4],     box {4, 1}:  tile::gather4
-  CUtensorMap qh;    // float64 [E][UQ],        box {QHEAD, NB}:  record heads of NB consecutive entries
-  CUtensorMap qp;    // float64 [E][UQ],        box {QPLANE, NB}: one plane of NB consecutive entries
+  CUtensorMap gpj;   // float32 [nsnps][8 + nvp*3], box {200, 1}: tile::gather4 of 4 SNP rows x (gp0 | 64 samples)
+  CUtensorMap gpk;   // same tensor, box {104, 1}: 4 SNP rows x (8 floats | 32 samples), k side of rectangular tasks
+  CUtensorMap q;     // float64 [E][UQ], box {16, NB}: whole records (single dense plane)
+  CUtensorMap qh;    // float64 [E][UQ], box {QHEAD, NB}:  record heads of NB consecutive entries
+  CUtensorMap qp;    // float64 [E][UQ], box {QPLANE, NB}: one plane of NB consecutive entries
 };
 
 // exact re-scoring requests of one cell (built by merge_kernel, filled by rescore_kernel)
@@ -129,7 +136,7 @@ struct RescList {
 static_assert(sizeof(RescList) == 392, "RescList layout");
 
 struct RescoreParams {
-  int32_t nv, nvp, nA, UQ, sep0;
+  int32_t nv, gp_stride, nA, UQ, sep0;
   int8_t dense_idx[DMX_MAX_ALPHA];
   const float* gp;
   const int32_t* ent_snp;
@@ -159,6 +166,10 @@ struct MergeParams {
 
 struct EntqParams {
   int32_t U, UQ;
+  int32_t nd, sep0;            // dense planes; alpha[0] == 0
+  int32_t gp_stride;           // floats per GP row
+  const float* gprow;          // GP rows with the gp0 prefix (gprow_kernel)
+  const int32_t* ent_snp;
   int64_t E;
   const int64_t* ent_ptr;
   const uint16_t* reads;
@@ -169,7 +180,7 @@ struct EntqParams {
 };
 
 // host-callable launchers (dmx_kernels.cu); all return a cudaError_t as int
-int launch_gp0(const float* gp, double* gp0, int64_t nsnps, int nv, int nvp, void* stream);
+int launch_gprow(const float* gp_flat, float* gp_rows, int64_t nsnps, int nv, int nvp, void* stream);
 int launch_entq(const EntqParams& p, void* stream);
 int launch_pair_scan(const ScanParams& p, const ScanMaps& tm, bool fp32, void* stream);
 int launch_merge(const MergeParams& p, int64_t nactive, void* stream);

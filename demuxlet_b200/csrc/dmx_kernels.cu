@@ -19,6 +19,7 @@
 // 5 consumer warps each own 4 x 4 tiles of hypotheses in registers.  Rings are mbarrier pipelines.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <math.h>
 
 #include "dmx_internal.h"
@@ -144,20 +145,33 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
       : "memory");
 }
 
-// TMA tensor copies (descriptors built on the host, dmx_api.cu:encode_maps)
-__device__ __forceinline__ void tma_gather4(void* dst, const CUtensorMap* map, int col, int r0, int r1, int r2, int r3,
-                                            uint64_t* bar) {
+// TMA tensor copies (descriptors built on the host, dmx_api.cu:encode_maps).  The *_elect forms are executed by a
+// converged warp with warp-uniform operands; elect.sync picks the one lane that issues.
+__device__ __forceinline__ void tma_gather4_elect(uint32_t dst, const CUtensorMap* map, int col, int r0, int r1, int r2,
+                                                  int r3, uint32_t bar) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, "
-      "%5, %6}], [%7];" ::"r"(smem_u32(dst)),
-      "l"(map), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_u32(bar))
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "@p cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, "
+      "%4, %5, %6}], [%7];\n\t}" ::"r"(dst),
+      "l"(map), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar)
       : "memory");
 }
-__device__ __forceinline__ void tma_tile2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+__device__ __forceinline__ void tma_tile2d_elect(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "@p cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n\t}" ::
+          "r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_elect(uint32_t bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar),
+      "r"(bytes)
       : "memory");
 }
 
@@ -167,33 +181,49 @@ __device__ __forceinline__ void peel(double& x, int& esum) {
   esum += hi >> 20;
   x = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(x));
 }
+// fp32 flavour; a zero (or denormal) product is left alone: its log is -inf whatever the exponent sum says
+__device__ __forceinline__ void peelf(float& x, int& esum) {
+  const uint32_t b = __float_as_uint(x);
+  if (b >= 0x00800000u) {
+    esum += (int)(b >> 23);
+    x = __uint_as_float((b & 0x007fffffu) | 0x3f800000u);
+  } else {
+    esum += 127;
+  }
+}
+__device__ __forceinline__ double unpeelf_log(float x, int esum, int nflush) {
+  return (double)(esum - 127 * nflush) * 0.693147180559945309417232121458 + log((double)x);
+}
 __device__ __forceinline__ double unpeel_log(double x, int esum, int nflush) {
   return (double)(esum - 1023 * nflush) * 0.693147180559945309417232121458 + log(x);
 }
 
 // ---------------------------------------------------------------------------------------------
-// gp0: cohort mean GP per SNP, cmd_cram_demuxlet.cpp:391-401 (ascending-j double sums, then / nv)
+// gprow: builds the GP rows the TMA gathers read, [gp0: 3 doubles, 8 B pad][nvp x 3 floats], from the uploaded
+// [nsnps][nvp*3] matrix.  gp0 = cohort mean GP per SNP, cmd_cram_demuxlet.cpp:391-401 (ascending-j double sums, then
+// / nv): lanes 0..2 of the row's warp sum one genotype each while the other lanes copy the row.
 // ---------------------------------------------------------------------------------------------
-__global__ void gp0_kernel(const float* __restrict__ gp, double* __restrict__ gp0, int64_t nsnps, int nv,
-                           int nvp) {
-  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) gprow_kernel(const float* __restrict__ gp, float* __restrict__ rows, int64_t nsnps,
+                                                    int nv, int nvp) {
+  const int lane = threadIdx.x & 31;
+  const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (s >= nsnps) return;
-  const float* g = gp + s * (int64_t)nvp * 3;
-  double a = 0, b = 0, c = 0;
-  for (int j = 0; j < nv; ++j) {
-    a = __dadd_rn(a, (double)g[3 * j]);
-    b = __dadd_rn(b, (double)g[3 * j + 1]);
-    c = __dadd_rn(c, (double)g[3 * j + 2]);
+  const int n3 = nvp * 3;
+  const float* g = gp + s * (int64_t)n3;
+  float* out = rows + s * (int64_t)(n3 + 8);
+  for (int i = lane; i < n3; i += 32) out[8 + i] = g[i];
+  if (lane < 3) {
+    double a = 0;
+    for (int j = 0; j < nv; ++j) a = __dadd_rn(a, (double)g[3 * j + lane]);
+    reinterpret_cast<double*>(out)[lane] = __ddiv_rn(a, (double)nv);
+  } else if (lane == 3) {
+    reinterpret_cast<double*>(out)[3] = 0.0;
   }
-  gp0[s * 4 + 0] = __ddiv_rn(a, (double)nv);
-  gp0[s * 4 + 1] = __ddiv_rn(b, (double)nv);
-  gp0[s * 4 + 2] = __ddiv_rn(c, (double)nv);
-  gp0[s * 4 + 3] = 0.0;
 }
 
-int launch_gp0(const float* gp, double* gp0, int64_t nsnps, int nv, int nvp, void* stream) {
+int launch_gprow(const float* gp_flat, float* gp_rows, int64_t nsnps, int nv, int nvp, void* stream) {
   if (nsnps == 0) return 0;
-  gp0_kernel<<<(unsigned)((nsnps + 255) / 256), 256, 0, (cudaStream_t)stream>>>(gp, gp0, nsnps, nv, nvp);
+  gprow_kernel<<<(unsigned)((nsnps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(gp_flat, gp_rows, nsnps, nv, nvp);
   return (int)cudaGetLastError();
 }
 
@@ -275,6 +305,29 @@ __global__ void __launch_bounds__(256) entq_kernel(const __grid_constant__ EntqP
     out[1] = __ddiv_rn(G1, sm);
     out[2] = __ddiv_rn(G2, sm);
   }
+  // per-entry factors of the three sample-independent likelihoods (they need only this record and the cohort mean
+  // gp0 of the entry's SNP): llk0s (:459) -> head[6], llks00 of a separable plane 0 -> head[7], llks00[n] (:700-709)
+  // -> slot 9 of each dense plane.  The pair scan just multiplies them up per cell.
+  __syncwarp(gmask);
+  if (sub == 0) {
+    const double* z = reinterpret_cast<const double*>(p.gprow + (int64_t)__ldg(p.ent_snp + e) * p.gp_stride);
+    const double z0 = __ldg(z), z1 = __ldg(z + 1), z2 = __ldg(z + 2);
+    const double g0 = __ldcg(out), g1 = __ldcg(out + 1), g2 = __ldcg(out + 2);
+    out[6] = fma(g2, z2, fma(g1, z1, g0 * z0));
+    if (p.sep0) {
+      const double f0 = __ldcg(out + 3), f1 = __ldcg(out + 4), f2 = __ldcg(out + 5);
+      out[7] = fma(f2, z2, fma(f1, z1, f0 * z0)) * ((z0 + z1) + z2);
+    } else {
+      out[7] = 1.0;
+    }
+    for (int d = 0; d < p.nd; ++d) {
+      double* q = out + QHEAD + QPLANE * d;
+      const double t0 = fma(__ldcg(q + 2), z2, fma(__ldcg(q + 1), z1, __ldcg(q) * z0));
+      const double t1 = fma(__ldcg(q + 5), z2, fma(__ldcg(q + 4), z1, __ldcg(q + 3) * z0));
+      const double t2 = fma(__ldcg(q + 8), z2, fma(__ldcg(q + 7), z1, __ldcg(q + 6) * z0));
+      q[9] = fma(z2, t2, fma(z1, t1, z0 * t0));
+    }
+  }
 }
 
 int launch_entq(const EntqParams& p, void* stream) {
@@ -299,21 +352,22 @@ int set_err_table(const double* err256) {
 //   pair_scan_f32_kernel  fp32 hypotheses (3 FFMA + 1 FMUL per hypothesis and entry), one pipeline per CTA
 // ---------------------------------------------------------------------------------------------
 namespace {
-// raw ring stage (what the TMA unit writes).  GP rows arrive through tile::gather4 copies of 4 rows x 32 samples
-// (384 B per row): the j side as [half of 32 samples][entry][384 B], the k side of a rectangular task as
-// [entry][384 B]; gp0 rows as [entry][32 B]; the entry records through two tiled 2-D copies of 8 consecutive
-// entries: heads [entry][48 B] and the task's plane [entry][80 B].
-constexpr uint32_t GROW = 32 * 12;                  // bytes of one gathered row slice (32 samples)
-constexpr uint32_t GATHER_BYTES = 4 * GROW;         // one gather4
+// raw ring stage (what the TMA unit writes).  A GP row in HBM is [gp0: 3 doubles + pad = 8 floats][nvp x 3 floats]
+// (gprow_kernel), so one tile::gather4 of 4 SNP rows x 200 floats brings gp0 and 64 samples of each row: the j side
+// is [entry][800 B], samples from byte 32 (gp0 in front is valid for tasks with j0 = 0).  The k side of a
+// rectangular task is [entry][416 B] (8 + 96 floats).  The records of the NB consecutive entries arrive as one tiled
+// 2-D copy [entry][128 B] when there is a single dense plane, else as heads [entry][48 B] + planes [entry][80 B]
+// (ScanParams::q_hp / q_po / q_pp give the pitches).
+constexpr uint32_t GPFX = 8;                        // floats in front of the samples of a GP row
+constexpr uint32_t GROWJ = (GPFX + BLK * 3) * 4;    // 800 B: smem pitch of a j-side row
+constexpr uint32_t GROWK = (GPFX + BLK_RECT_K * 3) * 4;   // 416 B: k-side row of a rectangular task
 constexpr uint32_t OFF_GPJ = 0;
-constexpr uint32_t HALF_BYTES = NB * GROW;          // 3072: one 32-sample half of the j side, all entries
-constexpr uint32_t OFF_GPK = OFF_GPJ + (BLK / 32) * HALF_BYTES;
-constexpr uint32_t OFF_GP0 = OFF_GPK + HALF_BYTES;
-constexpr uint32_t OFF_QH = OFF_GP0 + NB * 32;
-constexpr uint32_t OFF_QP = OFF_QH + NB * QHEAD * 8;
-constexpr uint32_t RAW_SLOT = OFF_QP + NB * QPLANE * 8;              // 10496 B
-static_assert(OFF_GPK % 128 == 0 && OFF_GP0 % 128 == 0 && OFF_QH % 128 == 0 && OFF_QP % 128 == 0, "TMA alignment");
-static_assert(BLK_RECT_K == 32 && BLK % 32 == 0, "gather geometry");
+constexpr uint32_t OFF_GPK = OFF_GPJ + NB * GROWJ;
+constexpr uint32_t OFF_Q = OFF_GPK + NB * GROWK;
+constexpr uint32_t RAW_SLOT = OFF_Q + NB * (QHEAD + QPLANE) * 8;     // 10752 B
+static_assert((4 * GROWJ) % 128 == 0 && (4 * GROWK) % 128 == 0 && OFF_GPK % 128 == 0 && OFF_Q % 128 == 0,
+              "TMA alignment");
+static_assert(BLK_RECT_K == 32 && BLK == 64 && NB == 8, "gather geometry");
 // fp64 processed ring: per entry and side a 64 x 4 matrix (sample x genotype, 4th column zero) stored as 8 blocks
 // of 8 samples; inside a block the layout is column-major with the column index XOR-swizzled by the block parity,
 // so that both the transform's stores (one column, 32 consecutive samples) and the consumers' DMMA fragment
@@ -372,8 +426,10 @@ __device__ __forceinline__ void consumer_bar_sync(int id) {
 // branches: lanes beyond the task's sample count work on padding (their ring slots are never read), so the
 // compiler can batch the shared-memory loads of several entries.  The fp32 variant writes neutral vectors
 // (1, 0, 0) for such lanes because an 8-sample tile may straddle the end of the sample range.
+struct QLay { uint32_t hp, po, pp; };   // byte pitches of the record heads / planes in a raw stage
+
 template <bool SAME, bool FULL, bool EXTRAS, bool F32>
-__device__ __forceinline__ void transform_stage(const unsigned char* __restrict__ rs, void* __restrict__ pav,
+__device__ __forceinline__ void transform_stage(const unsigned char* __restrict__ rs, void* __restrict__ pav, QLay ql,
                                                 int tl, int nvalid, bool jv, bool kv, double& PA, double& PB,
                                                 double& P1) {
   const int blk = tl >> 3, sw = blk & 1;
@@ -382,24 +438,26 @@ __device__ __forceinline__ void transform_stage(const unsigned char* __restrict_
   float* af = reinterpret_cast<float*>(pav) + (tl >> 2) * F_BLK4_FLT + (tl & 3) * 3;
   float* wf = af + F_SIDE_FLT;
   const int c0 = (0 ^ sw) * 8, c1 = (1 ^ sw) * 8, c2 = (2 ^ sw) * 8;
-  const float* gj = reinterpret_cast<const float*>(rs + OFF_GPJ + (tl >> 5) * HALF_BYTES) + (tl & 31) * 3;
-  const float* gk = SAME ? gj : reinterpret_cast<const float*>(rs + OFF_GPK) + (tl & 31) * 3;
-  constexpr int GK_STRIDE = GROW / 4, GJ_STRIDE = GROW / 4;
-  const double2* qh = reinterpret_cast<const double2*>(rs + OFF_QH);   // 3 double2 per entry
-  const double2* qp = reinterpret_cast<const double2*>(rs + OFF_QP);   // 5 double2 per entry
+  const float* gj = reinterpret_cast<const float*>(rs + OFF_GPJ) + GPFX + tl * 3;
+  const float* gk = SAME ? gj : reinterpret_cast<const float*>(rs + OFF_GPK) + GPFX + (tl & 31) * 3;
+  constexpr int GK_STRIDE = SAME ? GROWJ / 4 : GROWK / 4, GJ_STRIDE = GROWJ / 4;
+  const unsigned char* qhb = rs + OFF_Q;                 // head of entry e at qhb + e * ql.hp
+  const unsigned char* qpb = rs + OFF_Q + ql.po;         // plane of entry e at qpb + e * ql.pp
 #pragma unroll
   for (int e = 0; e < NB; ++e) {
     if (FULL || e < nvalid) {
       const float f0 = gk[e * GK_STRIDE], f1 = gk[e * GK_STRIDE + 1], f2 = gk[e * GK_STRIDE + 2];
       const double g0 = (double)f0, g1 = (double)f1, g2 = (double)f2;
-      const double2 qa = qp[e * 5], qb = qp[e * 5 + 1], qc = qp[e * 5 + 2], qd = qp[e * 5 + 3];
-      const double q22 = reinterpret_cast<const double*>(qp + e * 5 + 4)[0];
+      const double2* qp = reinterpret_cast<const double2*>(qpb + e * ql.pp);
+      const double2 qa = qp[0], qb = qp[1], qc = qp[2], qd = qp[3];
+      const double q22 = reinterpret_cast<const double*>(qp + 4)[0];
       // Q'[l][m] row-major: qa = (00, 01), qb = (02, 10), qc = (11, 12), qd = (20, 21), q22
       const double w0 = fma(qb.x, g2, fma(qa.y, g1, qa.x * g0));
       const double w1 = fma(qc.y, g2, fma(qc.x, g1, qb.y * g0));
       const double w2 = fma(q22, g2, fma(qd.y, g1, qd.x * g0));
       if (EXTRAS) {
-        const double2 h0 = qh[e * 3], h1 = qh[e * 3 + 1], h2 = qh[e * 3 + 2];   // GL0 GL1 | GL2 f0 | f1 f2
+        const double2* qh = reinterpret_cast<const double2*>(qhb + e * ql.hp);
+        const double2 h0 = qh[0], h1 = qh[1], h2 = qh[2];   // GL0 GL1 | GL2 f0 | f1 f2
         PA *= fma(h2.y, g2, fma(h2.x, g1, h1.y * g0));
         PB *= (g0 + g1) + g2;
         P1 *= fma(h1.x, g2, fma(h0.y, g1, h0.x * g0));
@@ -438,10 +496,10 @@ __device__ __forceinline__ void transform_stage(const unsigned char* __restrict_
 }
 
 template <bool SAME, bool EXTRAS, bool F32>
-__device__ __forceinline__ void transform_dispatch(const unsigned char* rs, void* pa, int tl, int nvalid, bool jv,
-                                                   bool kv, double& PA, double& PB, double& P1) {
-  if (nvalid == NB) transform_stage<SAME, true, EXTRAS, F32>(rs, pa, tl, nvalid, jv, kv, PA, PB, P1);
-  else transform_stage<SAME, false, EXTRAS, F32>(rs, pa, tl, nvalid, jv, kv, PA, PB, P1);
+__device__ __forceinline__ void transform_dispatch(const unsigned char* rs, void* pa, QLay ql, int tl, int nvalid,
+                                                   bool jv, bool kv, double& PA, double& PB, double& P1) {
+  if (nvalid == NB) transform_stage<SAME, true, EXTRAS, F32>(rs, pa, ql, tl, nvalid, jv, kv, PA, PB, P1);
+  else transform_stage<SAME, false, EXTRAS, F32>(rs, pa, ql, tl, nvalid, jv, kv, PA, PB, P1);
 }
 
 // ring pointers of one task pipeline
@@ -451,54 +509,137 @@ struct Pipe {
 };
 
 // =============================== loader warp =====================================================
-// Per stage of NB entries one elected lane issues the TMA copies: tile::gather4 for the GP row slices (4 SNP rows
-// x 32 samples per instruction) and the gp0 rows, and two tiled 2-D copies for the heads and the task's plane of
-// the NB consecutive entry records.  Every stage moves the same number of bytes: entries beyond the cell's last one
-// gather row 0 / the next cell's records (rows beyond the table are zero filled by the TMA unit), and the transform
-// ignores them.  SNP ids are fetched one stage ahead.
+// Per stage of NB entries the warp issues (one elected lane, straight-line code): two tile::gather4 copies for the j
+// side (4 SNP rows x [gp0 | 64 samples] each), two more for the k side of a rectangular task, and one tiled 2-D copy
+// of the NB consecutive entry records (two when there are several dense planes).  Every stage moves the same number
+// of bytes: entry slots beyond the cell's last entry gather row 0 / the next cell's records (rows beyond the table are
+// zero filled by the TMA unit) and the transform ignores them.  SNP ids are fetched one stage ahead.
 template <int SRAW>
 __device__ __forceinline__ void loader_role(const ScanParams& p, const ScanMaps& tm, const Pipe& pp, int lane, int u,
                                             int NS) {
+  const uint32_t raw0 = smem_u32(pp.raw_base), full0 = smem_u32(pp.raw_full);
+  const bool one_q = p.q_hp == (QHEAD + QPLANE) * 8;
   uint32_t git = 0;
   TaskInfo ti;
   for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
     const TaskType tt = p.tt[ti.tti];
     const bool same = tt.flags & TF_TRI;
     const bool need_head = tt.flags & (TF_EXTRAS | TF_SCALARS);
-    const bool need_z = tt.flags & (TF_SCALARS | TF_L00);
-    const int nh = (tt.nj + 31) >> 5;     // 32-sample halves of the j side
-    const uint32_t bytes = (uint32_t)NB * ((uint32_t)nh * GROW + (same ? 0u : GROW) + (need_z ? 32u : 0u) +
-                                           (need_head ? (uint32_t)QHEAD * 8u : 0u) + (uint32_t)QPLANE * 8u);
-    int snp_next = (lane < NB && ti.e0 + lane < ti.e1) ? __ldg(p.ent_snp + ti.e0 + lane) : 0;
+    const int colj = tt.j0 * 3, colk = tt.k0 * 3, qoff = tt.qoff;
+    const uint32_t bytes = (uint32_t)NB * (GROWJ + (same ? 0u : GROWK)) +
+                           (one_q ? (uint32_t)NB * (QHEAD + QPLANE) * 8u
+                                  : (uint32_t)NB * ((need_head ? (uint32_t)QHEAD * 8u : 0u) + (uint32_t)QPLANE * 8u));
+    // SNP ids are fetched 32 entries (4 stages) at a time, one block ahead: the global-load latency of the ids must
+    // not sit on the per-stage critical path
+    int snp_cur = (ti.e0 + lane < ti.e1) ? __ldg(p.ent_snp + ti.e0 + lane) : 0;
+    int snp_nxt = (ti.e0 + 32 + lane < ti.e1) ? __ldg(p.ent_snp + ti.e0 + 32 + lane) : 0;
     for (int it = 0; it < ti.nst; ++it, ++git) {
-      const int rslot = git % SRAW;
+      const uint32_t rslot = git % SRAW;
       const uint32_t ph = (git / SRAW) & 1u;
       const int64_t eb = ti.e0 + (int64_t)it * NB;
-      const int snp = snp_next;
-      snp_next = (lane < NB && eb + NB + lane < ti.e1) ? __ldg(p.ent_snp + eb + NB + lane) : 0;
+      if (it && (it & 3) == 0) {
+        snp_cur = snp_nxt;
+        snp_nxt = (eb + 32 + lane < ti.e1) ? __ldg(p.ent_snp + eb + 32 + lane) : 0;
+      }
       int s[NB];
 #pragma unroll
-      for (int i = 0; i < NB; ++i) s[i] = __shfl_sync(0xffffffffu, snp, i);
+      for (int i = 0; i < NB; ++i) s[i] = __shfl_sync(0xffffffffu, snp_cur, (it & 3) * NB + i);
+      const long long tl0 = clock64();
       mbar_wait(&pp.raw_empty[rslot], ph ^ 1u);
-      if (lane == 0) {
-        unsigned char* rs = pp.raw_base + (size_t)rslot * RAW_SLOT;
-        uint64_t* bar = &pp.raw_full[rslot];
-        mbar_expect_tx(bar, bytes);
-#pragma unroll
-        for (int g = 0; g < NB / 4; ++g) {
-          for (int h = 0; h < nh; ++h)
-            tma_gather4(rs + OFF_GPJ + h * HALF_BYTES + g * GATHER_BYTES, &tm.gp, (tt.j0 + 32 * h) * 3, s[4 * g],
-                        s[4 * g + 1], s[4 * g + 2], s[4 * g + 3], bar);
-          if (!same)
-            tma_gather4(rs + OFF_GPK + g * GATHER_BYTES, &tm.gp, tt.k0 * 3, s[4 * g], s[4 * g + 1], s[4 * g + 2],
-                        s[4 * g + 3], bar);
-          if (need_z)
-            tma_gather4(rs + OFF_GP0 + g * 128, &tm.gp0, 0, s[4 * g], s[4 * g + 1], s[4 * g + 2], s[4 * g + 3], bar);
-        }
-        if (need_head) tma_tile2d(rs + OFF_QH, &tm.qh, 0, (int)eb, bar);
-        tma_tile2d(rs + OFF_QP, &tm.qp, tt.qoff, (int)eb, bar);
+      if ((p.dbg & 8) && blockIdx.x == 0 && lane == 0 && r == 1 && it < 256) { p.dbgbuf[it * 8 + 0] = tl0; p.dbgbuf[it * 8 + 1] = clock64(); }
+      const uint32_t rs = raw0 + rslot * RAW_SLOT, bar = full0 + rslot * 8u;
+      mbar_expect_tx_elect(bar, bytes);
+      tma_gather4_elect(rs + OFF_GPJ, &tm.gpj, colj, s[0], s[1], s[2], s[3], bar);
+      tma_gather4_elect(rs + OFF_GPJ + 4 * GROWJ, &tm.gpj, colj, s[4], s[5], s[6], s[7], bar);
+      if (!same) {
+        tma_gather4_elect(rs + OFF_GPK, &tm.gpk, colk, s[0], s[1], s[2], s[3], bar);
+        tma_gather4_elect(rs + OFF_GPK + 4 * GROWK, &tm.gpk, colk, s[4], s[5], s[6], s[7], bar);
       }
-      __syncwarp();
+      if (one_q) {
+        tma_tile2d_elect(rs + OFF_Q, &tm.q, 0, (int)eb, bar);
+      } else {
+        if (need_head) tma_tile2d_elect(rs + OFF_Q, &tm.qh, 0, (int)eb, bar);
+        tma_tile2d_elect(rs + OFF_Q + NB * QHEAD * 8, &tm.qp, qoff, (int)eb, bar);
+      }
+    }
+  }
+}
+
+// =============================== loader warp, cp.async flavour ====================================
+// Measured on B200: one warp cannot issue the TMA copies of a stage (two gather4 + one tile, ~20 dependent
+// uniform-datapath instructions each) faster than about 1000 cycles per stage, which caps the whole pipeline.  The
+// gather of 8 arbitrary 800-byte rows is therefore also available as per-lane 16-byte cp.async copies (SASS LDGSTS):
+// four lanes per SNP row, immediate offsets, no address arithmetic per copy; completion is tracked on the same
+// mbarrier through cp.async.mbarrier.arrive.noinc (32 asynchronous arrivals per stage).  Same raw-stage layout.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+template <int SRAW>
+__device__ __forceinline__ void loader_role_cpasync(const ScanParams& p, const Pipe& pp, int lane, int u, int NS) {
+  const uint32_t raw0 = smem_u32(pp.raw_base), full0 = smem_u32(pp.raw_full);
+  const int row = lane >> 2, q = lane & 3;            // 4 lanes per gathered row
+  const char* gbase = reinterpret_cast<const char*>(p.gp) - GPFX * 4;   // start of GP row 0 (gp0 prefix)
+  const int64_t rowbytes = (int64_t)p.gp_stride * 4;
+  const int recbytes = p.UQ * 8;
+  const bool one_q = p.q_hp == (QHEAD + QPLANE) * 8;
+  uint32_t git = 0;
+  TaskInfo ti;
+  for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
+    const TaskType tt = p.tt[ti.tti];
+    const bool same = tt.flags & TF_TRI;
+    const bool need_head = tt.flags & (TF_EXTRAS | TF_SCALARS);
+    const int ncj = (GPFX * 4 + tt.nj * 12 + 15) >> 4;               // 16-byte chunks of a j-side row
+    const int nck = same ? 0 : (GPFX * 4 + tt.nk * 12 + 15) >> 4;
+    const int64_t colj = (int64_t)tt.j0 * 12, colk = (int64_t)tt.k0 * 12;
+    // SNP ids are fetched 32 entries (4 stages) at a time, one block ahead
+    int snp_cur = (ti.e0 + lane < ti.e1) ? __ldg(p.ent_snp + ti.e0 + lane) : 0;
+    int snp_nxt = (ti.e0 + 32 + lane < ti.e1) ? __ldg(p.ent_snp + ti.e0 + 32 + lane) : 0;
+    for (int it = 0; it < ti.nst; ++it, ++git) {
+      const uint32_t rslot = git % SRAW;
+      const uint32_t ph = (git / SRAW) & 1u;
+      const int64_t eb = ti.e0 + (int64_t)it * NB;
+      if (it && (it & 3) == 0) {
+        snp_cur = snp_nxt;
+        snp_nxt = (eb + 32 + lane < ti.e1) ? __ldg(p.ent_snp + eb + 32 + lane) : 0;
+      }
+      const int snp = __shfl_sync(0xffffffffu, snp_cur, (it & 3) * NB + row);
+      const char* src = gbase + (int64_t)snp * rowbytes;
+      const long long tl0 = clock64();
+      mbar_wait(&pp.raw_empty[rslot], ph ^ 1u);
+      if ((p.dbg & 8) && blockIdx.x == 0 && lane == 0 && r == 1 && it < 256) { p.dbgbuf[it * 8 + 0] = tl0; p.dbgbuf[it * 8 + 1] = clock64(); }
+      const uint32_t rs = raw0 + rslot * RAW_SLOT, bar = full0 + rslot * 8u;
+      {
+        const uint32_t d = rs + OFF_GPJ + row * GROWJ + q * 16;
+        const char* sj = src + colj + q * 16;
+#pragma unroll
+        for (int k = 0; k < (int)(GROWJ / 64) + 1; ++k)
+          if (q + 4 * k < ncj) cp_async16(d + k * 64, sj + k * 64);
+      }
+      if (!same) {
+        const uint32_t d = rs + OFF_GPK + row * GROWK + q * 16;
+        const char* sk = src + colk + q * 16;
+#pragma unroll
+        for (int k = 0; k < (int)(GROWK / 64) + 1; ++k)
+          if (q + 4 * k < nck) cp_async16(d + k * 64, sk + k * 64);
+      }
+      // records of the NB consecutive entries (rows beyond the table: the buffer has slack, dmx_api.cu)
+      if (one_q) {
+        const char* sq = reinterpret_cast<const char*>(p.entq) + eb * recbytes + lane * 16;
+        for (int c = lane; c < NB * (QHEAD + QPLANE) / 2; c += 32) cp_async16(rs + OFF_Q + c * 16, sq + (c - lane) * 16);
+      } else {
+        // heads [entry][48 B] (3 chunks each) and planes [entry][80 B] (5 chunks each)
+        if (need_head)   // QHEAD * 8 = 64 B = 4 chunks per entry
+          cp_async16(rs + OFF_Q + lane * 16,
+                     reinterpret_cast<const char*>(p.entq) + (eb + lane / 4) * recbytes + (lane % 4) * 16);
+        for (int c = lane; c < NB * 5; c += 32)
+          cp_async16(rs + OFF_Q + NB * QHEAD * 8 + c * 16,
+                     reinterpret_cast<const char*>(p.entq) + (eb + c / 5) * recbytes + tt.qoff * 8 + (c % 5) * 16);
+      }
+      cp_async_arrive_noinc(bar);
     }
   }
 }
@@ -509,6 +650,7 @@ __device__ __forceinline__ void loader_role(const ScanParams& p, const ScanMaps&
 template <bool F32, int SRAW, int SPROC, uint32_t PSLOT_BYTES>
 __device__ __forceinline__ void transform_role(const ScanParams& p, const Pipe& pp, int rw, int lane, int u, int NS) {
   const int tl = rw * 32 + lane;        // sample slot on each side
+  const QLay ql = {(uint32_t)p.q_hp, (uint32_t)p.q_po, (uint32_t)p.q_pp};
   uint32_t git = 0;
   TaskInfo ti;
   for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
@@ -534,27 +676,21 @@ __device__ __forceinline__ void transform_role(const ScanParams& p, const Pipe& 
       const unsigned char* rs = pp.raw_base + (size_t)rslot * RAW_SLOT;
       void* pa = pp.proc_base + (size_t)pslot * PSLOT_BYTES;
       if (same) {
-        if (tt.flags & TF_EXTRAS) transform_dispatch<true, true, F32>(rs, pa, tl, nvalid, jv, kv, PA, PB, P1);
-        else transform_dispatch<true, false, F32>(rs, pa, tl, nvalid, jv, kv, PA, PB, P1);
+        if (tt.flags & TF_EXTRAS) transform_dispatch<true, true, F32>(rs, pa, ql, tl, nvalid, jv, kv, PA, PB, P1);
+        else transform_dispatch<true, false, F32>(rs, pa, ql, tl, nvalid, jv, kv, PA, PB, P1);
       } else {
-        if (tt.flags & TF_EXTRAS) transform_dispatch<false, true, F32>(rs, pa, tl, nvalid, jv, kv, PA, PB, P1);
-        else transform_dispatch<false, false, F32>(rs, pa, tl, nvalid, jv, kv, PA, PB, P1);
+        if (tt.flags & TF_EXTRAS) transform_dispatch<false, true, F32>(rs, pa, ql, tl, nvalid, jv, kv, PA, PB, P1);
+        else transform_dispatch<false, false, F32>(rs, pa, ql, tl, nvalid, jv, kv, PA, PB, P1);
       }
       if (scal && lane < nvalid) {
-        const double* z = reinterpret_cast<const double*>(rs + OFF_GP0) + lane * 4;
-        const double* hq = reinterpret_cast<const double*>(rs + OFF_QH) + lane * QHEAD;
-        const double* q = reinterpret_cast<const double*>(rs + OFF_QP) + lane * QPLANE;
-        const double z0 = z[0], z1 = z[1], z2 = z[2];
+        // per-entry factors precomputed by entq_kernel
+        const double* hq = reinterpret_cast<const double*>(rs + OFF_Q + lane * ql.hp);
+        const double* q = reinterpret_cast<const double*>(rs + OFF_Q + ql.po + lane * ql.pp);
         if (tt.flags & TF_SCALARS) {
-          if (p.want_single) PS0 *= fma(hq[2], z2, fma(hq[1], z1, hq[0] * z0));                    // :459
-          if (p.sep0) PS1 *= fma(hq[5], z2, fma(hq[4], z1, hq[3] * z0)) * ((z0 + z1) + z2);
+          if (p.want_single) PS0 *= hq[6];                                                          // :459
+          if (p.sep0) PS1 *= hq[7];
         }
-        if (tt.flags & TF_L00) {                                                                   // :700-709
-          const double t0 = fma(q[2], z2, fma(q[1], z1, q[0] * z0));
-          const double t1 = fma(q[5], z2, fma(q[4], z1, q[3] * z0));
-          const double t2 = fma(q[8], z2, fma(q[7], z1, q[6] * z0));
-          PS2 *= fma(z2, t2, fma(z1, t1, z0 * t0));
-        }
+        if (tt.flags & TF_L00) PS2 *= q[9];                                                         // :700-709
       }
       if ((it % FLUSH_STAGES) == FLUSH_STAGES - 1) {
         peel(PA, eA); peel(PB, eB); peel(P1, e1x);
@@ -610,25 +746,25 @@ struct TScratch {
 constexpr uint32_t F_TS_BYTES = (sizeof(TScratch) + 127) / 128 * 128;
 
 template <bool SAME, bool EXTRAS>
-__device__ __forceinline__ void transform_entry_f32(const unsigned char* __restrict__ rs, float* __restrict__ pf, int e,
-                                                    int sgrp, uint32_t jm, uint32_t km, double (&PA)[8], double (&PB)[8],
-                                                    double (&P1)[8]) {
+__device__ __forceinline__ void transform_entry_f32(const unsigned char* __restrict__ rs, float* __restrict__ pf, QLay ql,
+                                                    int e, int sgrp, uint32_t jm, uint32_t km, float (&PA)[8], float (&PB)[8],
+                                                    float (&P1)[8]) {
   const int flip = sgrp >> 2;
   // Q'[l][m] of this entry, row-major, rounded to fp32
-  const double2* qp = reinterpret_cast<const double2*>(rs + OFF_QP) + e * (QPLANE / 2);
+  const double2* qp = reinterpret_cast<const double2*>(rs + OFF_Q + ql.po + e * ql.pp);
   const double2 qa = qp[0], qb = qp[1], qc = qp[2], qd = qp[3];
   const float q00 = (float)qa.x, q01 = (float)qa.y, q02 = (float)qb.x, q10 = (float)qb.y, q11 = (float)qc.x,
               q12 = (float)qc.y, q20 = (float)qd.x, q21 = (float)qd.y, q22 = (float)qp[4].x;
-  double h[6];
+  float h[6];
   if (EXTRAS) {
-    const double2* qh = reinterpret_cast<const double2*>(rs + OFF_QH) + e * (QHEAD / 2);
+    const double2* qh = reinterpret_cast<const double2*>(rs + OFF_Q + e * ql.hp);
     const double2 h0 = qh[0], h1 = qh[1], h2 = qh[2];   // GL0 GL1 | GL2 f0 | f1 f2
-    h[0] = h0.x; h[1] = h0.y; h[2] = h1.x; h[3] = h1.y; h[4] = h2.x; h[5] = h2.y;
+    h[0] = (float)h0.x; h[1] = (float)h0.y; h[2] = (float)h1.x; h[3] = (float)h1.y; h[4] = (float)h2.x;
+    h[5] = (float)h2.y;
   }
   const int s0 = 8 * sgrp;
-  const unsigned char* rk = SAME ? rs + OFF_GPJ + (s0 >> 5) * HALF_BYTES + e * GROW + (s0 & 31) * 12
-                                 : rs + OFF_GPK + e * GROW + (s0 & 31) * 12;
-  const unsigned char* rj = rs + OFF_GPJ + (s0 >> 5) * HALF_BYTES + e * GROW + (s0 & 31) * 12;
+  const unsigned char* rj = rs + OFF_GPJ + e * GROWJ + GPFX * 4 + s0 * 12;
+  const unsigned char* rk = SAME ? rj : rs + OFF_GPK + e * GROWK + GPFX * 4 + (s0 & 31) * 12;
   float* af = pf + (2 * sgrp) * F_BLK4_FLT + e * 12;
   float* wf = af + F_SIDE_FLT;
 #pragma unroll
@@ -649,10 +785,9 @@ __device__ __forceinline__ void transform_entry_f32(const unsigned char* __restr
         w[3 * i + 1] = kv ? fmaf(q12, f2, fmaf(q11, f1, q10 * f0)) : 0.0f;
         w[3 * i + 2] = kv ? fmaf(q22, f2, fmaf(q21, f1, q20 * f0)) : 0.0f;
         if (EXTRAS) {
-          const double g0 = (double)f0, g1 = (double)f1, g2 = (double)f2;
-          PA[4 * hb + i] *= fma(h[5], g2, fma(h[4], g1, h[3] * g0));
-          PB[4 * hb + i] *= (g0 + g1) + g2;
-          P1[4 * hb + i] *= fma(h[2], g2, fma(h[1], g1, h[0] * g0));
+          PA[4 * hb + i] *= fmaf(h[5], f2, fmaf(h[4], f1, h[3] * f0));
+          PB[4 * hb + i] *= (f0 + f1) + f2;
+          P1[4 * hb + i] *= fmaf(h[2], f2, fmaf(h[1], f1, h[0] * f0));
         }
       }
       float4* dw = reinterpret_cast<float4*>(wf + b * F_BLK4_FLT);
@@ -684,13 +819,14 @@ __device__ __forceinline__ void transform_role_f32(const ScanParams& p, const Pi
                                                    int u, int NS) {
   const int sgrp = lane & 7, e = tw * 4 + (lane >> 3);
   const int flip = sgrp >> 2, s0 = 8 * sgrp;
+  const QLay ql = {(uint32_t)p.q_hp, (uint32_t)p.q_po, (uint32_t)p.q_pp};
   uint32_t git = 0;
   TaskInfo ti;
   for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
     const TaskType tt = p.tt[ti.tti];
     const bool same = tt.flags & TF_TRI;
-    const bool extras_t = tt.flags & TF_EXTRAS;
-    const bool scal_t = tt.flags & (TF_SCALARS | TF_L00);
+    const bool extras_t = (tt.flags & TF_EXTRAS) && !(p.dbg & 16);
+    const bool scal_t = (tt.flags & (TF_SCALARS | TF_L00)) && !(p.dbg & 32);
     const bool scal = scal_t && sgrp == 0;            // this lane also carries the scalars of its entry slot
     // validity masks of this lane's eight samples on each side (bit = 4 * block + i)
     uint32_t jm = 0, km = 0;
@@ -699,10 +835,11 @@ __device__ __forceinline__ void transform_role_f32(const ScanParams& p, const Pi
       if (s0 + i < tt.nj) jm |= 1u << i;
       if (same ? (s0 + i < tt.nj) : (s0 + i < tt.nk)) km |= 1u << i;
     }
-    double PA[8], PB[8], P1[8];                       // running products (extras), slot h = 4 * hb + i
+    float PA[8], PB[8], P1[8];                        // running fp32 products (extras), slot h = 4 * hb + i
     int eA[8], eB[8], e1x[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { PA[i] = PB[i] = P1[i] = 1.0; eA[i] = eB[i] = e1x[i] = 0; }
+    for (int i = 0; i < 8; ++i) { PA[i] = PB[i] = P1[i] = 1.0f; eA[i] = eB[i] = e1x[i] = 0; }
+    int nflush_x = 0;
     double PS0 = 1.0, PS1 = 1.0, PS2 = 1.0;           // scalars: llk0s, llks00[sep], llks00[n]
     int eS0 = 0, eS1 = 0, eS2 = 0;
     int nflush = 0;
@@ -710,33 +847,31 @@ __device__ __forceinline__ void transform_role_f32(const ScanParams& p, const Pi
       const int rslot = git % F_S_RAW, pslot = git % F_S_PROC;
       const uint32_t rph = (git / F_S_RAW) & 1u, pph = (git / F_S_PROC) & 1u;
       const int nvalid = (int)min((int64_t)NB, ti.e1 - (ti.e0 + (int64_t)it * NB));
+      const long long tt0 = clock64();
       mbar_wait(&pp.raw_full[rslot], rph);
+      const long long tt1 = clock64();
       mbar_wait(&pp.proc_empty[pslot], pph ^ 1u);
+      if ((p.dbg & 8) && blockIdx.x == 0 && lane == 0 && tw == 0 && r == 1 && it < 256) { p.dbgbuf[it * 8 + 2] = tt0; p.dbgbuf[it * 8 + 3] = tt1; p.dbgbuf[it * 8 + 4] = clock64(); }
       const unsigned char* rs = pp.raw_base + (size_t)rslot * RAW_SLOT;
       float* pf = reinterpret_cast<float*>(pp.proc_base + (size_t)pslot * F_PROC_SLOT);
-      if (e < nvalid) {
+      if (p.dbg & 2) {
+      } else if (e < nvalid) {
         if (same) {
-          if (extras_t) transform_entry_f32<true, true>(rs, pf, e, sgrp, jm, km, PA, PB, P1);
-          else transform_entry_f32<true, false>(rs, pf, e, sgrp, jm, km, PA, PB, P1);
+          if (extras_t) transform_entry_f32<true, true>(rs, pf, ql, e, sgrp, jm, km, PA, PB, P1);
+          else transform_entry_f32<true, false>(rs, pf, ql, e, sgrp, jm, km, PA, PB, P1);
         } else {
-          if (extras_t) transform_entry_f32<false, true>(rs, pf, e, sgrp, jm, km, PA, PB, P1);
-          else transform_entry_f32<false, false>(rs, pf, e, sgrp, jm, km, PA, PB, P1);
+          if (extras_t) transform_entry_f32<false, true>(rs, pf, ql, e, sgrp, jm, km, PA, PB, P1);
+          else transform_entry_f32<false, false>(rs, pf, ql, e, sgrp, jm, km, PA, PB, P1);
         }
         if (scal) {
-          const double* z = reinterpret_cast<const double*>(rs + OFF_GP0) + e * 4;
-          const double* hq = reinterpret_cast<const double*>(rs + OFF_QH) + e * QHEAD;
-          const double* q = reinterpret_cast<const double*>(rs + OFF_QP) + e * QPLANE;
-          const double z0 = z[0], z1 = z[1], z2 = z[2];
+          // per-entry factors precomputed by entq_kernel
+          const double* hq = reinterpret_cast<const double*>(rs + OFF_Q + e * ql.hp);
+          const double* q = reinterpret_cast<const double*>(rs + OFF_Q + ql.po + e * ql.pp);
           if (tt.flags & TF_SCALARS) {
-            if (p.want_single) PS0 *= fma(hq[2], z2, fma(hq[1], z1, hq[0] * z0));                    // :459
-            if (p.sep0) PS1 *= fma(hq[5], z2, fma(hq[4], z1, hq[3] * z0)) * ((z0 + z1) + z2);
+            if (p.want_single) PS0 *= hq[6];                                                          // :459
+            if (p.sep0) PS1 *= hq[7];
           }
-          if (tt.flags & TF_L00) {                                                                   // :700-709
-            const double t0 = fma(q[2], z2, fma(q[1], z1, q[0] * z0));
-            const double t1 = fma(q[5], z2, fma(q[4], z1, q[3] * z0));
-            const double t2 = fma(q[8], z2, fma(q[7], z1, q[6] * z0));
-            PS2 *= fma(z2, t2, fma(z1, t1, z0 * t0));
-          }
+          if (tt.flags & TF_L00) PS2 *= q[9];                                                         // :700-709
         }
       } else {   // identity entry: S = 1 for every hypothesis
         float* af = pf + (2 * sgrp) * F_BLK4_FLT + e * 12;
@@ -751,11 +886,13 @@ __device__ __forceinline__ void transform_role_f32(const ScanParams& p, const Pi
           dw[0] = i0; dw[1] = i1; dw[2] = i2;
         }
       }
-      if ((it & 15) == 15) {   // every 16 entries of this lane
-        if (extras_t) {
+      if ((p.dbg & 8) && blockIdx.x == 0 && lane == 0 && tw == 0 && r == 1 && it < 256) p.dbgbuf[it * 8 + 7] = clock64();
+      if (extras_t && (it & 3) == 3) {   // fp32 products: every 4 entries of this lane (factors >= 1e-6 each)
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { peel(PA[i], eA[i]); peel(PB[i], eB[i]); peel(P1[i], e1x[i]); }
-        }
+        for (int i = 0; i < 8; ++i) { peelf(PA[i], eA[i]); peelf(PB[i], eB[i]); peelf(P1[i], e1x[i]); }
+        ++nflush_x;
+      }
+      if ((it & 15) == 15) {   // fp64 scalars: every 16 entries of this lane
         peel(PS0, eS0); peel(PS1, eS1); peel(PS2, eS2);
         ++nflush;
       }
@@ -772,9 +909,9 @@ __device__ __forceinline__ void transform_role_f32(const ScanParams& p, const Pi
     if (extras_t) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        la[i] = p.sep0 ? unpeel_log(PA[i], eA[i], nflush) : 0.0;
-        lbv[i] = unpeel_log(PB[i], eB[i], nflush);
-        l1[i] = p.want_single ? unpeel_log(P1[i], e1x[i], nflush) : 0.0;
+        la[i] = p.sep0 ? unpeelf_log(PA[i], eA[i], nflush_x) : 0.0;
+        lbv[i] = unpeelf_log(PB[i], eB[i], nflush_x);
+        l1[i] = p.want_single ? unpeelf_log(P1[i], e1x[i], nflush_x) : 0.0;
 #pragma unroll
         for (int o = 8; o < 32; o <<= 1) {
           la[i] += __shfl_xor_sync(0xffffffffu, la[i], o);
@@ -1088,6 +1225,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_scan_kernel(const __grid_con
   }
 }
 
+// S[i][c] = a_i . w_c and acc *= S for one 8 x 8 tile and one entry, a tile row at a time (eight independent chains);
+// a diagonal tile of a triangular task skips the hypotheses below the diagonal
+template <bool DIAG>
+__device__ __forceinline__ void tile_math(const float (&a)[8][3], const float (&w)[8][3], float (&acc)[64]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float s[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (!DIAG || c >= i) s[c] = a[i][0] * w[c][0];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (!DIAG || c >= i) s[c] = fmaf(a[i][1], w[c][1], s[c]);
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (!DIAG || c >= i) s[c] = fmaf(a[i][2], w[c][2], s[c]);
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (!DIAG || c >= i) acc[i * 8 + c] *= s[c];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // fp32 pair scan.  Warps 0..8 consumers, 9..10 transform, 11 loader (SM sub-partition = warp % 4: 3 / 2+T / 2+T /
 // 2+L).  A consumer thread owns the 8 x 8 tile (bj, bk) of hypotheses for the entries e = lane & 7 of every
@@ -1114,7 +1273,7 @@ __global__ void __launch_bounds__(F_NTHREADS, 1) pair_scan_f32_kernel(const __gr
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < F_S_RAW; ++s) {
-      mbar_init(&pp.raw_full[s], 1);
+      mbar_init(&pp.raw_full[s], (F_TMA_LOADER || (p.dbg & 4)) ? 1 : 32);
       mbar_init(&pp.raw_empty[s], F_NTW);
     }
     for (int s = 0; s < F_S_PROC; ++s) {
@@ -1133,7 +1292,8 @@ __global__ void __launch_bounds__(F_NTHREADS, 1) pair_scan_f32_kernel(const __gr
   const int NS = (int)gridDim.x, u = (int)blockIdx.x;
   // warps 0..8 consumers (sub-partitions 0,1,2,3,0,1,2,3,0), 9..10 transform, 11 loader
   if (warp == F_NCW + F_NTW) {
-    loader_role<F_S_RAW>(p, tm, pp, lane, u, NS);
+    if (F_TMA_LOADER || (p.dbg & 4)) loader_role<F_S_RAW>(p, tm, pp, lane, u, NS);
+    else loader_role_cpasync<F_S_RAW>(p, pp, lane, u, NS);
   } else if (warp >= F_NCW) {
     transform_role_f32(p, pp, ts, warp - F_NCW, lane, u, NS);
   } else {
@@ -1147,12 +1307,19 @@ __global__ void __launch_bounds__(F_NTHREADS, 1) pair_scan_f32_kernel(const __gr
       const TaskType tt = p.tt[ti.tti];
       const bool tri = tt.flags & TF_TRI;
       const int nbj = (tt.nj + 7) >> 3, nbk = (tt.nk + 7) >> 3;   // 8-sample blocks on each side
+      // tile positions of a triangular task: 0..27 the off-diagonal tiles (bj < bk, row-major) on warps 0..6, 28..35 the
+      // diagonal tiles on warps 7 and 8, which evaluate only the 36 hypotheses with j <= k of their tile
       int bj, bk;
-      if (tri) {   // row-major walk of the upper triangle of 8 x 8 blocks
-        int q = pos;
-        bj = 0;
-        while (q >= 8 - bj) { q -= 8 - bj; ++bj; }
-        bk = bj + q;
+      const bool diag = tri && pos >= 28;
+      if (tri) {
+        if (diag) {
+          bj = bk = pos - 28;
+        } else {
+          int q = pos;
+          bj = 0;
+          while (q >= 7 - bj) { q -= 7 - bj; ++bj; }
+          bk = bj + 1 + q;
+        }
       } else {
         bj = pos >> 2;
         bk = pos & 3;
@@ -1167,8 +1334,11 @@ __global__ void __launch_bounds__(F_NTHREADS, 1) pair_scan_f32_kernel(const __gr
       for (int it = 0; it < ti.nst; ++it, ++git) {
         const int pslot = git % F_S_PROC;
         const uint32_t pph = (git / F_S_PROC) & 1u;
+        const long long tc0 = clock64();
         mbar_wait(&pp.proc_full[pslot], pph);
-        if (active) {
+        if ((p.dbg & 8) && blockIdx.x == 0 && lane == 0 && rw == 0 && r == 1 && it < 256) { p.dbgbuf[it * 8 + 5] = tc0; p.dbgbuf[it * 8 + 6] = clock64(); }
+        if ((p.dbg & 8) && blockIdx.x == 0 && lane == 0 && r == 1 && it >= 64 && it < 68) { p.dbgbuf[(256 + rw) * 8 + (it - 64) * 2] = tc0; p.dbgbuf[(256 + rw) * 8 + (it - 64) * 2 + 1] = clock64(); }
+        if (active && !(p.dbg & 1)) {
           const float* pf = reinterpret_cast<const float*>(pp.proc_base + (size_t)pslot * F_PROC_SLOT);
           float a[8][3], w[8][3];
 #pragma unroll
@@ -1183,19 +1353,8 @@ __global__ void __launch_bounds__(F_NTHREADS, 1) pair_scan_f32_kernel(const __gr
               w[(q / 3) * 4 + f / 3][f % 3] = ys[c];
             }
           }
-          // one tile row at a time, eight independent chains in flight (source order = issue order for ptxas)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float s[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) s[c] = a[i][0] * w[c][0];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) s[c] = fmaf(a[i][1], w[c][1], s[c]);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) s[c] = fmaf(a[i][2], w[c][2], s[c]);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) acc[i * 8 + c] *= s[c];
-          }
+          if (diag) tile_math<true>(a, w, acc);     // warp-uniform: rw >= 7
+          else tile_math<false>(a, w, acc);
         }
         if ((it % F_PEEL_STAGES) == F_PEEL_STAGES - 1) {
           float mn = 1.0f;
@@ -1438,7 +1597,7 @@ __global__ void __launch_bounds__(RESC_WARPS * 32) rescore_kernel(const __grid_c
     const float* g = p.gp;
     const double* q = p.entq;
     if (valid) {
-      g += (int64_t)__ldg(p.ent_snp + e) * p.nvp * 3;
+      g += (int64_t)__ldg(p.ent_snp + e) * p.gp_stride;
       q += e * p.UQ;
     }
     for (int h = 0; h < H; ++h) {

@@ -1,9 +1,8 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
-timeout 300 python bench.py --steps 5 --warmup 3 --fp32-pairs --no-cpu-baseline > gpurun_out/bench_f32b.json 2> gpurun_out/bench_f32b.err
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
+for m in "--fp32-pairs" ""; do
+timeout 300 python bench.py --steps 5 --warmup 3 $m --no-cpu-baseline > gpurun_out/bench_tmp.json 2> gpurun_out/bench_tmp.err
 python -c "
-import json;d=json.load(open('gpurun_out/bench_f32b.json'));print('f32',d['value'],d['e2e']['value'],d['breakdown_ms'])"
-timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_f64b.json 2> gpurun_out/bench_f64b.err
-python -c "
-import json;d=json.load(open('gpurun_out/bench_f64b.json'));print('f64',d['value'],d['e2e']['value'],d['breakdown_ms'])"
-tail -3 gpurun_out/bench_f32b.err gpurun_out/bench_f64b.err
+import json;d=json.load(open('gpurun_out/bench_tmp.json'));print('$m',d['value'],d['e2e']['value'],d['breakdown_ms'])"
+tail -n 3 gpurun_out/bench_tmp.err
+done
