@@ -98,6 +98,9 @@ struct dmx_ctx {
   DevBuf<float> d_gp;              // uploaded [nsnps][nvp*3]
   DevBuf<float> d_gprow;           // [nsnps][8 + nvp*3]: gp0 | samples (gprow_kernel)
   DevBuf<double> d_entq, d_row0, d_singA, d_lb, d_p1, d_p1_0, d_l00, d_sing, d_dense;
+  DevBuf<double> d_ents;           // [E][2 + nd] per-entry factors of llk0s / llks00 (entq -> cell_scalars)
+  DevBuf<float> d_entf_head, d_entf_plane;   // fp32 copies of the entry records (fp32 pair scan)
+  double err3_256[256];
   DevBuf<int64_t> d_cell_ptr, d_ent_ptr;
   DevBuf<int32_t> d_ent_snp, d_order;
   DevBuf<uint16_t> d_reads;
@@ -267,7 +270,7 @@ void build_tasks(dmx_ctx* c) {
       memset(&t, 0, sizeof(t));
       t.n = (int16_t)n;
       t.j0 = (int16_t)j0; t.nj = (int16_t)nj; t.k0 = (int16_t)k0; t.nk = (int16_t)nk;
-      t.flags = fl | (sym ? TF_SYM : 0u) | (n == 0 ? TF_NOARG : 0u);
+      t.flags = fl | (sym ? TF_SYM : 0u) | (n == 0 ? TF_NOARG : 0u) | ((sym ? j0 == 0 : k0 == 0) ? TF_ROW0 : 0u);
       if (first) {
         t.flags |= TF_L00;
         if (n == fd) t.flags |= TF_SCALARS;
@@ -342,6 +345,7 @@ void fill_scan_params(dmx_ctx* c, ScanParams* p) {
     p->dbgbuf = c->d_dbg.p;
   }
   p->gp = c->d_gprow.p + 8; p->ent_snp = c->d_ent_snp.p; p->entq = c->d_entq.p;
+  p->entf_head = c->d_entf_head.p; p->entf_plane = c->d_entf_plane.p; p->entf_pstride = (c->E + NB) * FPLANE;
   p->cell_ptr = c->d_cell_ptr.p; p->cell_order = c->d_order.p; p->tt = c->d_tt.p; p->parts = c->d_parts.p;
   p->row0 = c->d_row0.p; p->singA = c->d_singA.p; p->lb = c->d_lb.p; p->p1 = c->d_p1.p;
   p->p1_0 = c->d_p1_0.p; p->l00 = c->d_l00.p; p->dense = nullptr;
@@ -380,7 +384,9 @@ int dense_scan(dmx_ctx* c, const std::vector<int32_t>& cells, double* host_out /
     p.parts = d_parts.p;
     p.dense = c->d_dense.p;
     p.ntasks = (int64_t)n * p.T;
-    CU(launch_pair_scan(p, c->maps, (c->cfg.flags & DMX_FP32_PAIRS) != 0, c->stream));
+    // dense blocks always come from the fp64 scan: every hypothesis keeps its own exponent there, whereas the fp32
+    // scan lets hypotheses that are hopeless against the best of their tile underflow
+    CU(launch_pair_scan(p, c->maps, false, c->stream));
     CU(launch_fill_sep_dense(p, (int64_t)n, c->stream));
     c->st.gpu_launches += 1 + (p.sep0 ? 1 : 0);
     CU(cudaMemcpyAsync(host_out + lo * per, c->d_dense.p, n * per * sizeof(double), cudaMemcpyDeviceToHost,
@@ -470,7 +476,8 @@ int dmx_create(dmx_ctx** out, const dmx_config* cfg) {
   for (int i = 0; i <= 255; ++i) c->err256[i] = (i > 1) ? pow(0.1, i * 0.1) : 0.75;   // PhredHelper.cpp:30
   cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
-  if (e == cudaSuccess) e = (cudaError_t)set_err_table(c->err256);
+  for (int i = 0; i <= 255; ++i) c->err3_256[i] = c->err256[i] / 3.0;   // the quotient of :606-607
+  if (e == cudaSuccess) e = (cudaError_t)set_err_table(c->err256, c->err3_256);
   if (e == cudaSuccess) e = (cudaError_t)pair_scan_init();
   if (e == cudaSuccess) e = c->d_tt.reserve(c->tt.size());
   if (e == cudaSuccess)
@@ -494,6 +501,7 @@ void dmx_destroy(dmx_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  c->d_ents.release(); c->d_entf_head.release(); c->d_entf_plane.release();
   c->d_gp.release(); c->d_gprow.release(); c->d_entq.release(); c->d_row0.release(); c->d_singA.release();
   c->d_lb.release(); c->d_p1.release(); c->d_p1_0.release(); c->d_l00.release(); c->d_sing.release();
   c->d_dense.release(); c->d_cell_ptr.release(); c->d_ent_ptr.release(); c->d_ent_snp.release();
@@ -640,6 +648,14 @@ int dmx_compute(dmx_ctx* c) {
   c->st.n_fullcell = 0;
 
   CU(c->d_entq.reserve((size_t)c->E * c->UQ + (size_t)NB * c->UQ + 2));   // slack: a stage always reads NB records
+  const int nd = (c->UQ - QHEAD) / QPLANE;
+  const bool fp32 = (c->cfg.flags & DMX_FP32_PAIRS) != 0;
+  const int64_t pstride = (c->E + NB) * FPLANE;
+  CU(c->d_ents.reserve((size_t)c->E * (2 + nd) + 2));
+  if (fp32) {
+    CU(c->d_entf_head.reserve((size_t)(c->E + NB) * FHEAD));
+    CU(c->d_entf_plane.reserve((size_t)pstride * std::max(nd, 1)));
+  }
   CU(c->d_parts.reserve((size_t)nact * T + 1));
   CU(c->d_row0.reserve((size_t)nc * nA * nv + 1)); CU(c->d_singA.reserve((size_t)nc * nv + 1));
   CU(c->d_lb.reserve((size_t)nc * nv + 1)); CU(c->d_p1.reserve((size_t)nc * nv + 1));
@@ -663,6 +679,10 @@ int dmx_compute(dmx_ctx* c) {
   eq.nd = (c->UQ - QHEAD) / QPLANE; eq.sep0 = c->pg.sep0; eq.gp_stride = c->nvp * 3 + 8; eq.gprow = c->d_gprow.p;
   eq.ent_snp = c->d_ent_snp.p; eq.ent_ptr = c->d_ent_ptr.p; eq.reads = c->d_reads.p;
   eq.entq = c->d_entq.p;
+  eq.ents = c->d_ents.p;
+  eq.entf_head = fp32 ? c->d_entf_head.p : nullptr;
+  eq.entf_plane = fp32 ? c->d_entf_plane.p : nullptr;
+  eq.entf_pstride = pstride;
   memcpy(eq.pu, c->pg.pu, sizeof(double) * c->pg.U);
   {
     // record layout: GL[3] (written by the kernel), f[3] = Q'[0][l][0] of a separable plane 0, then per dense
@@ -674,13 +694,26 @@ int dmx_compute(dmx_ctx* c) {
       if (c->dense_idx[n] >= 0)
         for (int i = 0; i < 9; ++i) slots[c->pg.umap[n * 9 + i]].push_back(QHEAD + QPLANE * c->dense_idx[n] + i);
     int o = 0;
+    memset(eq.slot_u, 0, sizeof(eq.slot_u));
     for (int u2 = 0; u2 < c->pg.U; ++u2) {
       eq.oslot_ptr[u2] = (uint8_t)o;
-      for (int sl : slots[u2]) eq.oslot[o++] = (uint8_t)sl;
+      for (int sl : slots[u2]) { eq.oslot[o++] = (uint8_t)sl; eq.slot_u[sl] = (uint8_t)u2; }
     }
     eq.oslot_ptr[c->pg.U] = (uint8_t)o;
   }
   CU(launch_entq(eq, c->stream));
+  if (fp32) {
+    // the fp32 scan leaves the sample-independent likelihoods (llk0s, llks00) to their own small kernel
+    CellScalarParams cs;
+    memset(&cs, 0, sizeof(cs));
+    cs.nd = nd; cs.nA = nA; cs.sep0 = c->pg.sep0; cs.want_single = (c->cfg.flags & DMX_SKIP_SINGLE) ? 0 : 1;
+    for (int n = 0; n < nA; ++n)
+      if (c->dense_idx[n] >= 0) cs.plane_n[c->dense_idx[n]] = (int8_t)n;
+    cs.ents = c->d_ents.p; cs.cell_ptr = c->d_cell_ptr.p; cs.cell_order = c->d_order.p;
+    cs.p1_0 = c->d_p1_0.p; cs.l00 = c->d_l00.p;
+    CU(launch_cell_scalars(cs, nact, c->stream));
+    if (nact) c->st.gpu_launches += 1;
+  }
   CU(cudaEventRecord(c->ev[1], c->stream));
   ScanParams sp;
   fill_scan_params(c, &sp);

@@ -28,12 +28,13 @@ constexpr int FLUSH_STAGES = 16 / NB;   // exponent renormalisation period (stag
 // fp32 pair scan (pair_scan_f32_kernel): one task pipeline per CTA; a consumer thread owns an 8 x 8 tile of
 // hypotheses for ONE of the NB entries of a stage (lane & 7 = entry, lane >> 3 = tile position inside the warp)
 constexpr int F_NCW = 9;       // consumer warps: 36 tile positions of the 64 x 64 upper triangle x 8 entry lanes
-constexpr int F_NTW = 2;       // transform warps: a lane = one entry slot x eight samples
+constexpr int F_NTW = 4;       // transform warps: a lane = one entry slot x four samples
 constexpr int F_S_RAW = 6;     // stages of the raw ring
-constexpr int F_S_PROC = 4;    // stages of the processed ring
+constexpr int F_S_PROC = 8;    // stages of the processed ring
 constexpr int F_NTHREADS = (F_NCW + F_NTW + 1) * 32;   // 448
-constexpr bool F_TMA_LOADER = true;    // fp32 kernel: gather through TMA tile::gather4 (true) or per-lane cp.async
 constexpr int F_PEEL_STAGES = 4;   // underflow check period (stages = entries per thread)
+constexpr int FHEAD = 8;       // floats per entry in the fp32 head table: GL[3], f[3] (separable plane), 2 pad
+constexpr int FPLANE = 12;     // floats per entry and dense plane in the fp32 plane tables: Q'[3][3], 3 pad
 constexpr int MAX_CAND = 8;    // near-tie candidates kept per task / per cell
 constexpr int MAX_U = DMX_MAX_ALPHA * 6 + 3;   // distinct mixing proportions p(n,l,m)
 
@@ -56,6 +57,9 @@ enum : uint32_t {
   TF_L00 = 16u,      // also llks00[n] for this task's plane (:700-709)
   TF_NOARG = 32u,    // plane is alpha index 0 handled densely (alpha[0] != 0): excluded from the
                      // best-pair argmax and from sumDouble (:728,:805 start at n = 1)
+  TF_ROW0 = 64u,     // the task holds pairs with sample 0 (llksAB[x][0][n]: LLK10 / LLK20, :824-825, and the singlets of
+                     // a dense plane 0): symmetric planes as (0, x) in tasks with j0 == 0, full planes as (x, 0) in
+                     // tasks with k0 == 0.  The fp32 scan accumulates them in its transform warps.
 };
 
 struct TaskType {
@@ -102,6 +106,9 @@ struct ScanParams {
   const float* gp;             // [nsnps][gp_stride] (first sample of row 0); the 3 doubles in front of a row are gp0
   const int32_t* ent_snp;      // [E]
   const double* entq;          // [E][UQ]: GL[3], sep-plane f[3], then QPLANE doubles per dense plane
+  const float* entf_head;      // [E][FHEAD] fp32 copy of the record heads (fp32 pair scan)
+  const float* entf_plane;     // [nd][entf_pstride] fp32 copies of the dense planes, FPLANE floats per entry
+  int64_t entf_pstride;        // floats between consecutive planes
   const int64_t* cell_ptr;     // [ncells+1]
   const int32_t* cell_order;   // [nactive] cell ids, scheduled order
   const TaskType* tt;          // [T]
@@ -174,19 +181,36 @@ struct EntqParams {
   const int64_t* ent_ptr;
   const uint16_t* reads;
   double* entq;
+  float* entf_head;            // [E][FHEAD] or null
+  float* entf_plane;           // [nd][entf_pstride]
+  int64_t entf_pstride;
+  double* ents;                // [E][2 + nd]: the entry's factors of llk0s (:459), llks00 of a separable plane 0, and
+                               // llks00[n] of every dense plane (:700-709); summed per cell by cell_scalars_kernel
   double pu[MAX_U];            // distinct p values (cmd_cram_demuxlet.cpp:613)
   uint8_t oslot_ptr[MAX_U + 1];   // CSR: record slots fed by distinct value u
   uint8_t oslot[QHEAD + QPLANE * DMX_MAX_ALPHA];
+  uint8_t slot_u[QHEAD + QPLANE * DMX_MAX_ALPHA];   // inverse map: distinct value feeding record slot s
+};
+
+struct CellScalarParams {
+  int32_t nd, nA, sep0, want_single;
+  int8_t plane_n[DMX_MAX_ALPHA];   // alpha index of dense plane d
+  const double* ents;              // [E][2 + nd]
+  const int64_t* cell_ptr;
+  const int32_t* cell_order;
+  double* p1_0;                    // [ncells]
+  double* l00;                     // [ncells][nA]
 };
 
 // host-callable launchers (dmx_kernels.cu); all return a cudaError_t as int
 int launch_gprow(const float* gp_flat, float* gp_rows, int64_t nsnps, int nv, int nvp, void* stream);
 int launch_entq(const EntqParams& p, void* stream);
 int launch_pair_scan(const ScanParams& p, const ScanMaps& tm, bool fp32, void* stream);
+int launch_cell_scalars(const CellScalarParams& p, int64_t nactive, void* stream);
 int launch_merge(const MergeParams& p, int64_t nactive, void* stream);
 int launch_fill_sep_dense(const ScanParams& p, int64_t nactive, void* stream);
 int launch_rescore(const RescoreParams& p, int64_t nactive, void* stream);
-int set_err_table(const double* err256);
+int set_err_table(const double* err256, const double* err3_256);
 int set_log_table(const double* tab274);          // glibc __log_data: ln2hi, ln2lo, A[5], B[11], tab[128][2]
 int launch_logtest(const double* x, double* y, int64_t n, void* stream);
 int pair_scan_init();          // func attributes (max dynamic smem)

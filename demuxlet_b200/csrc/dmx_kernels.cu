@@ -27,6 +27,7 @@
 namespace dmx {
 
 __constant__ double c_err[256];   // phred2Err, PhredHelper.cpp:30-32 (computed on the host with libm pow)
+__constant__ double c_err3[256];  // phred2Err / 3.0, the quotient the reference forms at :606-607 (host-computed)
 __constant__ double c_logtab[18 + 256];   // the host libm's __log_data (read from the loaded libm.so.6 at run time)
 
 // Bit-for-bit transcription of the x86-64 FMA build of glibc's log() (sysdeps/ieee754/dbl-64/e_log.c as
@@ -228,10 +229,59 @@ int launch_gprow(const float* gp_flat, float* gp_rows, int64_t nsnps, int nv, in
 }
 
 // ---------------------------------------------------------------------------------------------
-// entq: per-entry read likelihood on the distinct p values (:597-663) and pass-1 GLs (:424-452).
-// LPE lanes cooperate on one entry; lane `sub` owns p values sub, sub+LPE, ...  The arithmetic is the
-// reference's (separately rounded mul/add/div, per-read max normalisation).
+// entq: per-entry read likelihood on the distinct p values (:597-663) and pass-1 GLs (:424-452), in the
+// reference's arithmetic (separately rounded mul/add/div, per-read max normalisation).  Outputs per entry:
+//   entq[e][UQ]        fp64 record: GL[3] | f[3] (separable plane) | llk0s factor | llks00 factor of a separable
+//                      plane 0 | per dense plane Q'[3][3] + its llks00 factor
+//   entf_head/_plane   the same values rounded to fp32 (what the fp32 pair scan streams)
+//   ents[e][2 + nd]    the three kinds of sample-independent factors (cell_scalars_kernel sums their logs per cell)
+// Two kernels: entq1 (one thread per entry, all distinct values in registers; U <= 8, the common grids) and
+// entq (LPE lanes per entry; lane `sub` owns p values sub, sub+LPE, ...) for long alpha grids.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void entq_emit(const EntqParams& p, int64_t e, double* __restrict__ out) {
+  // per-entry factors of the sample-independent likelihoods (they need only this record and the cohort mean gp0 of
+  // the entry's SNP): llk0s (:459) -> head[6], llks00 of a separable plane 0 -> head[7], llks00[n] (:700-709) -> slot 9
+  // of each dense plane; then the fp32 copies
+  const double* z = reinterpret_cast<const double*>(p.gprow + (int64_t)__ldg(p.ent_snp + e) * p.gp_stride);
+  const double z0 = __ldg(z), z1 = __ldg(z + 1), z2 = __ldg(z + 2);
+  const double g0 = __ldcg(out), g1 = __ldcg(out + 1), g2 = __ldcg(out + 2);
+  double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+  const double s0 = fma(g2, z2, fma(g1, z1, g0 * z0));
+  double s1 = 1.0;
+  if (p.sep0) {
+    f0 = __ldcg(out + 3); f1 = __ldcg(out + 4); f2 = __ldcg(out + 5);
+    s1 = fma(f2, z2, fma(f1, z1, f0 * z0)) * ((z0 + z1) + z2);
+  }
+  out[6] = s0;
+  out[7] = s1;
+  double* sc = p.ents + e * (2 + p.nd);
+  sc[0] = s0;
+  sc[1] = s1;
+  if (p.entf_head) {
+    float4* fh = reinterpret_cast<float4*>(p.entf_head + e * FHEAD);
+    fh[0] = make_float4((float)g0, (float)g1, (float)g2, (float)f0);
+    fh[1] = make_float4((float)f1, (float)f2, 0.f, 0.f);
+  }
+  for (int d = 0; d < p.nd; ++d) {
+    double* q = out + QHEAD + QPLANE * d;
+    double Q[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Q[i] = __ldcg(q + i);
+    const double t0 = fma(Q[2], z2, fma(Q[1], z1, Q[0] * z0));
+    const double t1 = fma(Q[5], z2, fma(Q[4], z1, Q[3] * z0));
+    const double t2 = fma(Q[8], z2, fma(Q[7], z1, Q[6] * z0));
+    const double s2 = fma(z2, t2, fma(z1, t1, z0 * t0));
+    q[9] = s2;
+    sc[2 + d] = s2;
+    if (p.entf_plane) {
+      float4* fp = reinterpret_cast<float4*>(p.entf_plane + d * p.entf_pstride + e * FPLANE);
+      fp[0] = make_float4((float)Q[0], (float)Q[1], (float)Q[2], (float)Q[3]);
+      fp[1] = make_float4((float)Q[4], (float)Q[5], (float)Q[6], (float)Q[7]);
+      fp[2] = make_float4((float)Q[8], 0.f, 0.f, 0.f);
+    }
+  }
+}
+
 template <int LPE, int VPL>
 __global__ void __launch_bounds__(256) entq_kernel(const __grid_constant__ EntqParams p) {
   const int lane = threadIdx.x & 31;
@@ -271,14 +321,15 @@ __global__ void __launch_bounds__(256) entq_kernel(const __grid_constant__ EntqP
     for (int o = LPE / 2; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(gmask, mx, o));
 #pragma unroll
     for (int v = 0; v < VPL; ++v) P[v] = __ddiv_rn(P[v], mx);               // :632-639
-    // pass-1 GLs, :437-443
-    G0 = __dmul_rn(G0, pR);
-    G1 = __dmul_rn(G1, __dsub_rn(0.5, e3));
-    G2 = __dmul_rn(G2, pA);
-    const double sm = __dadd_rn(__dadd_rn(G0, G1), G2);
-    G0 = __ddiv_rn(G0, sm);
-    G1 = __ddiv_rn(G1, sm);
-    G2 = __ddiv_rn(G2, sm);
+    if (sub == 0) {   // pass-1 GLs, :437-443
+      G0 = __dmul_rn(G0, pR);
+      G1 = __dmul_rn(G1, __dsub_rn(0.5, e3));
+      G2 = __dmul_rn(G2, pA);
+      const double sm = __dadd_rn(__dadd_rn(G0, G1), G2);
+      G0 = __ddiv_rn(G0, sm);
+      G1 = __ddiv_rn(G1, sm);
+      G2 = __ddiv_rn(G2, sm);
+    }
   }
   double mx = 0.0;
 #pragma unroll
@@ -305,36 +356,91 @@ __global__ void __launch_bounds__(256) entq_kernel(const __grid_constant__ EntqP
     out[1] = __ddiv_rn(G1, sm);
     out[2] = __ddiv_rn(G2, sm);
   }
-  // per-entry factors of the three sample-independent likelihoods (they need only this record and the cohort mean
-  // gp0 of the entry's SNP): llk0s (:459) -> head[6], llks00 of a separable plane 0 -> head[7], llks00[n] (:700-709)
-  // -> slot 9 of each dense plane.  The pair scan just multiplies them up per cell.
   __syncwarp(gmask);
-  if (sub == 0) {
-    const double* z = reinterpret_cast<const double*>(p.gprow + (int64_t)__ldg(p.ent_snp + e) * p.gp_stride);
-    const double z0 = __ldg(z), z1 = __ldg(z + 1), z2 = __ldg(z + 2);
-    const double g0 = __ldcg(out), g1 = __ldcg(out + 1), g2 = __ldcg(out + 2);
-    out[6] = fma(g2, z2, fma(g1, z1, g0 * z0));
-    if (p.sep0) {
-      const double f0 = __ldcg(out + 3), f1 = __ldcg(out + 4), f2 = __ldcg(out + 5);
-      out[7] = fma(f2, z2, fma(f1, z1, f0 * z0)) * ((z0 + z1) + z2);
-    } else {
-      out[7] = 1.0;
-    }
-    for (int d = 0; d < p.nd; ++d) {
-      double* q = out + QHEAD + QPLANE * d;
-      const double t0 = fma(__ldcg(q + 2), z2, fma(__ldcg(q + 1), z1, __ldcg(q) * z0));
-      const double t1 = fma(__ldcg(q + 5), z2, fma(__ldcg(q + 4), z1, __ldcg(q + 3) * z0));
-      const double t2 = fma(__ldcg(q + 8), z2, fma(__ldcg(q + 7), z1, __ldcg(q + 6) * z0));
-      q[9] = fma(z2, t2, fma(z1, t1, z0 * t0));
-    }
+  if (sub == 0) entq_emit(p, e, out);
+}
+
+// one thread per entry: the U <= UMAX distinct values live in registers (independent chains: the divisions of a read
+// overlap), the phred tables in shared memory (lanes index them with different qualities)
+template <int UMAX>
+__global__ void __launch_bounds__(128) entq1_kernel(const __grid_constant__ EntqParams p) {
+  __shared__ double s_err[256], s_err3[256];
+  __shared__ double s_val[UMAX][128];
+  for (int i = threadIdx.x; i < 256; i += 128) { s_err[i] = c_err[i]; s_err3[i] = c_err3[i]; }
+  __syncthreads();
+  const int64_t e = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (e >= p.E) return;
+  const int nu = p.U;
+  double P[UMAX], pu[UMAX], qu[UMAX];
+#pragma unroll
+  for (int v = 0; v < UMAX; ++v) {
+    pu[v] = v < nu ? p.pu[v] : 0.0;
+    qu[v] = __dsub_rn(1.0, pu[v]);
+    P[v] = 1.0;
   }
+  double G0 = 1.0, G1 = 1.0, G2 = 1.0;
+  const int64_t r0 = p.ent_ptr[e], r1 = p.ent_ptr[e + 1];
+  for (int64_t r = r0; r < r1; ++r) {
+    const uint32_t rd = p.reads[r];
+    const uint32_t al = rd >> 8, bq = rd & 0xff;
+    if (al == 2) continue;                                                  // :435, :604
+    const double err = s_err[bq];
+    const double e3 = s_err3[bq];                                           // err / 3 (same rounded quotient)
+    const double mat = __dsub_rn(1.0, err);
+    const double pR = (al == 0) ? mat : e3;                                 // :606
+    const double pA = (al == 1) ? mat : e3;                                 // :607
+    double mx = 0.0;
+#pragma unroll
+    for (int v = 0; v < UMAX; ++v) {
+      const double t = __dadd_rn(__dmul_rn(pR, qu[v]), __dmul_rn(pA, pu[v]));   // :625
+      P[v] = __dmul_rn(P[v], t);
+      if (v < nu) mx = fmax(mx, P[v]);
+    }
+#pragma unroll
+    for (int v = 0; v < UMAX; ++v) P[v] = __ddiv_rn(P[v], mx);              // :632-639
+    G0 = __dmul_rn(G0, pR);                                                 // pass-1 GLs, :437-443
+    G1 = __dmul_rn(G1, __dsub_rn(0.5, e3));
+    G2 = __dmul_rn(G2, pA);
+    const double sm = __dadd_rn(__dadd_rn(G0, G1), G2);
+    G0 = __ddiv_rn(G0, sm);
+    G1 = __ddiv_rn(G1, sm);
+    G2 = __ddiv_rn(G2, sm);
+  }
+  double mx = 0.0;
+#pragma unroll
+  for (int v = 0; v < UMAX; ++v) {
+    P[v] = __dadd_rn(P[v], 1e-6);                                           // :643-654
+    if (v < nu) mx = fmax(mx, P[v]);
+  }
+#pragma unroll
+  for (int v = 0; v < UMAX; ++v) s_val[v][threadIdx.x] = __ddiv_rn(P[v], mx);   // :656-663
+  double* out = p.entq + e * p.UQ;
+  {
+    G0 = __dadd_rn(G0, 1e-6);                                                // :446-452
+    G1 = __dadd_rn(G1, 1e-6);
+    G2 = __dadd_rn(G2, 1e-6);
+    const double sm = __dadd_rn(__dadd_rn(G0, G1), G2);
+    out[0] = __ddiv_rn(G0, sm);
+    out[1] = __ddiv_rn(G1, sm);
+    out[2] = __ddiv_rn(G2, sm);
+  }
+  if (p.sep0)
+    for (int s = 3; s < 6; ++s) out[s] = s_val[p.slot_u[s]][threadIdx.x];
+  for (int d = 0; d < p.nd; ++d)
+    for (int i = 0; i < 9; ++i) {
+      const int s = QHEAD + QPLANE * d + i;
+      out[s] = s_val[p.slot_u[s]][threadIdx.x];
+    }
+  entq_emit(p, e, out);
 }
 
 int launch_entq(const EntqParams& p, void* stream) {
   if (p.E == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   auto grid = [&](int lpe) { return (unsigned)((p.E * lpe + 255) / 256); };
-  if (p.U <= 8) entq_kernel<8, 1><<<grid(8), 256, 0, st>>>(p);
+  const unsigned g1 = (unsigned)((p.E + 127) / 128);
+  if (p.U <= 5) entq1_kernel<5><<<g1, 128, 0, st>>>(p);
+  else if (p.U <= 8) entq1_kernel<8><<<g1, 128, 0, st>>>(p);
   else if (p.U <= 16) entq_kernel<16, 1><<<grid(16), 256, 0, st>>>(p);
   else if (p.U <= 32) entq_kernel<32, 1><<<grid(32), 256, 0, st>>>(p);
   else if (p.U <= 64) entq_kernel<32, 2><<<grid(32), 256, 0, st>>>(p);
@@ -342,8 +448,47 @@ int launch_entq(const EntqParams& p, void* stream) {
   return (int)cudaGetLastError();
 }
 
-int set_err_table(const double* err256) {
-  return (int)cudaMemcpyToSymbol(c_err, err256, 256 * sizeof(double));
+int set_err_table(const double* err256, const double* err3_256) {
+  cudaError_t e = cudaMemcpyToSymbol(c_err, err256, 256 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_err3, err3_256, 256 * sizeof(double));
+  return (int)e;
+}
+
+// ---------------------------------------------------------------------------------------------
+// cell_scalars: llk0s (:459) and llks00[n] (:700-709) of a cell = sum over its entries of the log of the per-entry
+// factors entq wrote.  One warp per cell; running fp64 products with the exponent peeled every 16 factors, one log
+// per lane and scalar.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) cell_scalars_kernel(const __grid_constant__ CellScalarParams p, int64_t nactive) {
+  const int lane = threadIdx.x & 31;
+  const int64_t aidx = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (aidx >= nactive) return;
+  const int cell = p.cell_order[aidx];
+  const int64_t e0 = p.cell_ptr[cell], e1 = p.cell_ptr[cell + 1];
+  const int ns = 2 + p.nd;
+  for (int s = 0; s < ns; ++s) {
+    if ((s == 0 && !p.want_single) || (s == 1 && !p.sep0)) continue;
+    double prod = 1.0;
+    int es = 0, nfl = 0, cnt = 0;
+    for (int64_t e = e0 + lane; e < e1; e += 32) {
+      prod *= __ldg(p.ents + e * ns + s);
+      if (++cnt == 16) { peel(prod, es); ++nfl; cnt = 0; }
+    }
+    double v = unpeel_log(prod, es, nfl);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) {
+      if (s == 0) p.p1_0[cell] = v;
+      else if (s == 1) p.l00[(int64_t)cell * p.nA] = v;
+      else p.l00[(int64_t)cell * p.nA + p.plane_n[s - 2]] = v;
+    }
+  }
+}
+
+int launch_cell_scalars(const CellScalarParams& p, int64_t nactive, void* stream) {
+  if (nactive == 0) return 0;
+  cell_scalars_kernel<<<(unsigned)((nactive + 3) / 4), 128, 0, (cudaStream_t)stream>>>(p, nactive);
+  return (int)cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -384,9 +529,6 @@ static_assert(RAW_SLOT % 128 == 0 && PROC_SLOT % 128 == 0 && SLOT_BYTES % 128 ==
 constexpr uint32_t F_BLK4_FLT = NB * 12 + 12;                        // 108 floats
 constexpr uint32_t F_SIDE_FLT = (BLK / 4) * F_BLK4_FLT;              // 1728 floats
 constexpr uint32_t F_PROC_SLOT = 2 * F_SIDE_FLT * 4;                 // 13824 B
-constexpr uint32_t F_ES_STRIDE = F_NCW * 32;                         // ints between the exponents of one thread
-constexpr uint32_t F_ES_BYTES = 64 * F_ES_STRIDE * 4;                // 73728 B
-constexpr uint32_t F_SMEM_NOTS = SLOT_CTRL + F_S_RAW * RAW_SLOT + F_S_PROC * F_PROC_SLOT + F_ES_BYTES;   // + TScratch
 static_assert(F_PROC_SLOT % 128 == 0 && NB == 8, "fp32 scan geometry");
 static_assert(2 * F_S_RAW + 2 * F_S_PROC <= 32 && 2 * S_RAW + 2 * S_PROC <= 32, "barriers must fit below the scratch area");
 
@@ -422,21 +564,17 @@ __device__ __forceinline__ void consumer_bar_sync(int id) {
   asm volatile("bar.sync %0, %1;" ::"r"(id + 1), "n"(NTHR) : "memory");
 }
 
-// one stage of the transform for lane `tl` (sample slot on each side).  The fp64 variant has no lane-dependent
-// branches: lanes beyond the task's sample count work on padding (their ring slots are never read), so the
-// compiler can batch the shared-memory loads of several entries.  The fp32 variant writes neutral vectors
-// (1, 0, 0) for such lanes because an 8-sample tile may straddle the end of the sample range.
+// one stage of the fp64 transform for lane `tl` (sample slot on each side).  No lane-dependent branches: lanes beyond
+// the task's sample count work on padding (their ring slots are never read), so the compiler can batch the
+// shared-memory loads of several entries.
 struct QLay { uint32_t hp, po, pp; };   // byte pitches of the record heads / planes in a raw stage
 
-template <bool SAME, bool FULL, bool EXTRAS, bool F32>
+template <bool SAME, bool FULL, bool EXTRAS>
 __device__ __forceinline__ void transform_stage(const unsigned char* __restrict__ rs, void* __restrict__ pav, QLay ql,
-                                                int tl, int nvalid, bool jv, bool kv, double& PA, double& PB,
-                                                double& P1) {
+                                                int tl, int nvalid, double& PA, double& PB, double& P1) {
   const int blk = tl >> 3, sw = blk & 1;
   double* ad = reinterpret_cast<double*>(pav) + blk * 32 + (tl & 7);
   double* wd = ad + NB * SIDE_DBL;
-  float* af = reinterpret_cast<float*>(pav) + (tl >> 2) * F_BLK4_FLT + (tl & 3) * 3;
-  float* wf = af + F_SIDE_FLT;
   const int c0 = (0 ^ sw) * 8, c1 = (1 ^ sw) * 8, c2 = (2 ^ sw) * 8;
   const float* gj = reinterpret_cast<const float*>(rs + OFF_GPJ) + GPFX + tl * 3;
   const float* gk = SAME ? gj : reinterpret_cast<const float*>(rs + OFF_GPK) + GPFX + (tl & 31) * 3;
@@ -462,44 +600,28 @@ __device__ __forceinline__ void transform_stage(const unsigned char* __restrict_
         PB *= (g0 + g1) + g2;
         P1 *= fma(h1.x, g2, fma(h0.y, g1, h0.x * g0));
       }
-      if (F32) {
-        wf[e * 12 + 0] = kv ? (float)w0 : 1.0f;
-        wf[e * 12 + 1] = kv ? (float)w1 : 0.0f;
-        wf[e * 12 + 2] = kv ? (float)w2 : 0.0f;
-        float a0 = f0, a1 = f1, a2 = f2;
-        if (!SAME) {
-          a0 = gj[e * (GJ_STRIDE)]; a1 = gj[e * (GJ_STRIDE) + 1]; a2 = gj[e * (GJ_STRIDE) + 2];
-        }
-        af[e * 12 + 0] = jv ? a0 : 1.0f;
-        af[e * 12 + 1] = jv ? a1 : 0.0f;
-        af[e * 12 + 2] = jv ? a2 : 0.0f;
+      wd[e * SIDE_DBL + c0] = w0;
+      wd[e * SIDE_DBL + c1] = w1;
+      wd[e * SIDE_DBL + c2] = w2;
+      if (SAME) {
+        ad[e * SIDE_DBL + c0] = g0; ad[e * SIDE_DBL + c1] = g1; ad[e * SIDE_DBL + c2] = g2;
       } else {
-        wd[e * SIDE_DBL + c0] = w0;
-        wd[e * SIDE_DBL + c1] = w1;
-        wd[e * SIDE_DBL + c2] = w2;
-        if (SAME) {
-          ad[e * SIDE_DBL + c0] = g0; ad[e * SIDE_DBL + c1] = g1; ad[e * SIDE_DBL + c2] = g2;
-        } else {
-          ad[e * SIDE_DBL + c0] = (double)gj[e * (GJ_STRIDE)];
-          ad[e * SIDE_DBL + c1] = (double)gj[e * (GJ_STRIDE) + 1];
-          ad[e * SIDE_DBL + c2] = (double)gj[e * (GJ_STRIDE) + 2];
-        }
+        ad[e * SIDE_DBL + c0] = (double)gj[e * (GJ_STRIDE)];
+        ad[e * SIDE_DBL + c1] = (double)gj[e * (GJ_STRIDE) + 1];
+        ad[e * SIDE_DBL + c2] = (double)gj[e * (GJ_STRIDE) + 2];
       }
-    } else if (F32) {   // identity entry: S = 1 for every hypothesis
-      wf[e * 12 + 0] = 1.0f; wf[e * 12 + 1] = 0.0f; wf[e * 12 + 2] = 0.0f;
-      af[e * 12 + 0] = 1.0f; af[e * 12 + 1] = 0.0f; af[e * 12 + 2] = 0.0f;
-    } else {
+    } else {   // identity entry: S = 1 for every hypothesis
       wd[e * SIDE_DBL + c0] = 1.0; wd[e * SIDE_DBL + c1] = 0.0; wd[e * SIDE_DBL + c2] = 0.0;
       ad[e * SIDE_DBL + c0] = 1.0; ad[e * SIDE_DBL + c1] = 0.0; ad[e * SIDE_DBL + c2] = 0.0;
     }
   }
 }
 
-template <bool SAME, bool EXTRAS, bool F32>
+template <bool SAME, bool EXTRAS>
 __device__ __forceinline__ void transform_dispatch(const unsigned char* rs, void* pa, QLay ql, int tl, int nvalid,
-                                                   bool jv, bool kv, double& PA, double& PB, double& P1) {
-  if (nvalid == NB) transform_stage<SAME, true, EXTRAS, F32>(rs, pa, ql, tl, nvalid, jv, kv, PA, PB, P1);
-  else transform_stage<SAME, false, EXTRAS, F32>(rs, pa, ql, tl, nvalid, jv, kv, PA, PB, P1);
+                                                   double& PA, double& PB, double& P1) {
+  if (nvalid == NB) transform_stage<SAME, true, EXTRAS>(rs, pa, ql, tl, nvalid, PA, PB, P1);
+  else transform_stage<SAME, false, EXTRAS>(rs, pa, ql, tl, nvalid, PA, PB, P1);
 }
 
 // ring pointers of one task pipeline
@@ -544,9 +666,7 @@ __device__ __forceinline__ void loader_role(const ScanParams& p, const ScanMaps&
       int s[NB];
 #pragma unroll
       for (int i = 0; i < NB; ++i) s[i] = __shfl_sync(0xffffffffu, snp_cur, (it & 3) * NB + i);
-      const long long tl0 = clock64();
       mbar_wait(&pp.raw_empty[rslot], ph ^ 1u);
-      if ((p.dbg & 8) && blockIdx.x == 0 && lane == 0 && r == 1 && it < 256) { p.dbgbuf[it * 8 + 0] = tl0; p.dbgbuf[it * 8 + 1] = clock64(); }
       const uint32_t rs = raw0 + rslot * RAW_SLOT, bar = full0 + rslot * 8u;
       mbar_expect_tx_elect(bar, bytes);
       tma_gather4_elect(rs + OFF_GPJ, &tm.gpj, colj, s[0], s[1], s[2], s[3], bar);
@@ -565,89 +685,10 @@ __device__ __forceinline__ void loader_role(const ScanParams& p, const ScanMaps&
   }
 }
 
-// =============================== loader warp, cp.async flavour ====================================
-// Measured on B200: one warp cannot issue the TMA copies of a stage (two gather4 + one tile, ~20 dependent
-// uniform-datapath instructions each) faster than about 1000 cycles per stage, which caps the whole pipeline.  The
-// gather of 8 arbitrary 800-byte rows is therefore also available as per-lane 16-byte cp.async copies (SASS LDGSTS):
-// four lanes per SNP row, immediate offsets, no address arithmetic per copy; completion is tracked on the same
-// mbarrier through cp.async.mbarrier.arrive.noinc (32 asynchronous arrivals per stage).  Same raw-stage layout.
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-template <int SRAW>
-__device__ __forceinline__ void loader_role_cpasync(const ScanParams& p, const Pipe& pp, int lane, int u, int NS) {
-  const uint32_t raw0 = smem_u32(pp.raw_base), full0 = smem_u32(pp.raw_full);
-  const int row = lane >> 2, q = lane & 3;            // 4 lanes per gathered row
-  const char* gbase = reinterpret_cast<const char*>(p.gp) - GPFX * 4;   // start of GP row 0 (gp0 prefix)
-  const int64_t rowbytes = (int64_t)p.gp_stride * 4;
-  const int recbytes = p.UQ * 8;
-  const bool one_q = p.q_hp == (QHEAD + QPLANE) * 8;
-  uint32_t git = 0;
-  TaskInfo ti;
-  for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
-    const TaskType tt = p.tt[ti.tti];
-    const bool same = tt.flags & TF_TRI;
-    const bool need_head = tt.flags & (TF_EXTRAS | TF_SCALARS);
-    const int ncj = (GPFX * 4 + tt.nj * 12 + 15) >> 4;               // 16-byte chunks of a j-side row
-    const int nck = same ? 0 : (GPFX * 4 + tt.nk * 12 + 15) >> 4;
-    const int64_t colj = (int64_t)tt.j0 * 12, colk = (int64_t)tt.k0 * 12;
-    // SNP ids are fetched 32 entries (4 stages) at a time, one block ahead
-    int snp_cur = (ti.e0 + lane < ti.e1) ? __ldg(p.ent_snp + ti.e0 + lane) : 0;
-    int snp_nxt = (ti.e0 + 32 + lane < ti.e1) ? __ldg(p.ent_snp + ti.e0 + 32 + lane) : 0;
-    for (int it = 0; it < ti.nst; ++it, ++git) {
-      const uint32_t rslot = git % SRAW;
-      const uint32_t ph = (git / SRAW) & 1u;
-      const int64_t eb = ti.e0 + (int64_t)it * NB;
-      if (it && (it & 3) == 0) {
-        snp_cur = snp_nxt;
-        snp_nxt = (eb + 32 + lane < ti.e1) ? __ldg(p.ent_snp + eb + 32 + lane) : 0;
-      }
-      const int snp = __shfl_sync(0xffffffffu, snp_cur, (it & 3) * NB + row);
-      const char* src = gbase + (int64_t)snp * rowbytes;
-      const long long tl0 = clock64();
-      mbar_wait(&pp.raw_empty[rslot], ph ^ 1u);
-      if ((p.dbg & 8) && blockIdx.x == 0 && lane == 0 && r == 1 && it < 256) { p.dbgbuf[it * 8 + 0] = tl0; p.dbgbuf[it * 8 + 1] = clock64(); }
-      const uint32_t rs = raw0 + rslot * RAW_SLOT, bar = full0 + rslot * 8u;
-      {
-        const uint32_t d = rs + OFF_GPJ + row * GROWJ + q * 16;
-        const char* sj = src + colj + q * 16;
-#pragma unroll
-        for (int k = 0; k < (int)(GROWJ / 64) + 1; ++k)
-          if (q + 4 * k < ncj) cp_async16(d + k * 64, sj + k * 64);
-      }
-      if (!same) {
-        const uint32_t d = rs + OFF_GPK + row * GROWK + q * 16;
-        const char* sk = src + colk + q * 16;
-#pragma unroll
-        for (int k = 0; k < (int)(GROWK / 64) + 1; ++k)
-          if (q + 4 * k < nck) cp_async16(d + k * 64, sk + k * 64);
-      }
-      // records of the NB consecutive entries (rows beyond the table: the buffer has slack, dmx_api.cu)
-      if (one_q) {
-        const char* sq = reinterpret_cast<const char*>(p.entq) + eb * recbytes + lane * 16;
-        for (int c = lane; c < NB * (QHEAD + QPLANE) / 2; c += 32) cp_async16(rs + OFF_Q + c * 16, sq + (c - lane) * 16);
-      } else {
-        // heads [entry][48 B] (3 chunks each) and planes [entry][80 B] (5 chunks each)
-        if (need_head)   // QHEAD * 8 = 64 B = 4 chunks per entry
-          cp_async16(rs + OFF_Q + lane * 16,
-                     reinterpret_cast<const char*>(p.entq) + (eb + lane / 4) * recbytes + (lane % 4) * 16);
-        for (int c = lane; c < NB * 5; c += 32)
-          cp_async16(rs + OFF_Q + NB * QHEAD * 8 + c * 16,
-                     reinterpret_cast<const char*>(p.entq) + (eb + c / 5) * recbytes + tt.qoff * 8 + (c % 5) * 16);
-      }
-      cp_async_arrive_noinc(bar);
-    }
-  }
-}
-
 // =============================== transform warps =================================================
 // one lane per sample: GP row -> (a, w) vectors in the processed ring; the lanes also carry the per-sample
 // "extras" (separable-plane factor, row-sum factor, pass-1 llks) and, in NB lanes, the scalars llk0s / llks00
-template <bool F32, int SRAW, int SPROC, uint32_t PSLOT_BYTES>
+template <int SRAW, int SPROC, uint32_t PSLOT_BYTES>
 __device__ __forceinline__ void transform_role(const ScanParams& p, const Pipe& pp, int rw, int lane, int u, int NS) {
   const int tl = rw * 32 + lane;        // sample slot on each side
   const QLay ql = {(uint32_t)p.q_hp, (uint32_t)p.q_po, (uint32_t)p.q_pp};
@@ -660,8 +701,6 @@ __device__ __forceinline__ void transform_role(const ScanParams& p, const Pipe& 
     const bool k_valid = (tt.k0 + tl) < p.nv;
     const bool extras = (tt.flags & TF_EXTRAS) && do_k && k_valid;
     const bool scal = (tt.flags & (TF_SCALARS | TF_L00)) && rw == 0 && lane < NB;
-    const bool jv = tl < tt.nj;
-    const bool kv = same ? jv : ((tl & (BLK_RECT_K - 1)) < tt.nk);
     double PA = 1.0, PB = 1.0, P1 = 1.0;            // running products (extras)
     int eA = 0, eB = 0, e1x = 0;
     double PS0 = 1.0, PS1 = 1.0, PS2 = 1.0;         // scalars: llk0s, llks00[sep], llks00[n]; lane = entry slot
@@ -676,11 +715,11 @@ __device__ __forceinline__ void transform_role(const ScanParams& p, const Pipe& 
       const unsigned char* rs = pp.raw_base + (size_t)rslot * RAW_SLOT;
       void* pa = pp.proc_base + (size_t)pslot * PSLOT_BYTES;
       if (same) {
-        if (tt.flags & TF_EXTRAS) transform_dispatch<true, true, F32>(rs, pa, ql, tl, nvalid, jv, kv, PA, PB, P1);
-        else transform_dispatch<true, false, F32>(rs, pa, ql, tl, nvalid, jv, kv, PA, PB, P1);
+        if (tt.flags & TF_EXTRAS) transform_dispatch<true, true>(rs, pa, ql, tl, nvalid, PA, PB, P1);
+        else transform_dispatch<true, false>(rs, pa, ql, tl, nvalid, PA, PB, P1);
       } else {
-        if (tt.flags & TF_EXTRAS) transform_dispatch<false, true, F32>(rs, pa, ql, tl, nvalid, jv, kv, PA, PB, P1);
-        else transform_dispatch<false, false, F32>(rs, pa, ql, tl, nvalid, jv, kv, PA, PB, P1);
+        if (tt.flags & TF_EXTRAS) transform_dispatch<false, true>(rs, pa, ql, tl, nvalid, PA, PB, P1);
+        else transform_dispatch<false, false>(rs, pa, ql, tl, nvalid, PA, PB, P1);
       }
       if (scal && lane < nvalid) {
         // per-entry factors precomputed by entq_kernel
@@ -731,170 +770,249 @@ __device__ __forceinline__ void transform_role(const ScanParams& p, const Pipe& 
   }
 }
 
-// =============================== fp32 transform warps ============================================
-// F_NTW = 2 warps.  A lane serves ONE entry slot of every stage (e = 4 * warp + lane / 8) and EIGHT samples of each
-// side (8 * (lane & 7) ...), so that everything moves as 16-byte vectors: the 24 floats of its samples' GP rows
-// (6 LDS.128), and the (a, w) vectors of two 4-sample blocks per side (12 STS.128).  Lanes 4..7 of a quarter warp
-// visit their two blocks in the opposite order, which makes both access patterns bank-conflict free.
-// w_k[l] = sum_m Q'[l][m] gp_k[m] is evaluated in fp32 (Q' rounded to fp32 once per lane and stage); the per-sample
-// extras (singlet factor of the separable plane, row sums, pass 1) and the scalars stay in fp64 running products,
-// one set per lane = per entry slot, folded over the eight entry slots at the end of a task.
-struct TScratch {
-  double xfer[2][3][BLK];            // [task parity][PA, PB, P1][sample]: partial logs of warp 1
-  double xs[2][4];                   // [task parity][s0, s1, s2]
-};
-constexpr uint32_t F_TS_BYTES = (sizeof(TScratch) + 127) / 128 * 128;
+// =============================== fp32 pair scan: loader and transform ==============================
+// Raw stage of the fp32 scan: the gathered GP rows as in the fp64 scan, then the fp32 record heads and the task's
+// fp32 plane of the NB consecutive entries (two contiguous 1-D bulk copies: the tables are entry-major).
+constexpr uint32_t F_OFF_GPJ = 0;
+constexpr uint32_t F_OFF_GPK = F_OFF_GPJ + NB * GROWJ;
+constexpr uint32_t F_OFF_FH = F_OFF_GPK + NB * GROWK;
+constexpr uint32_t F_OFF_FP = F_OFF_FH + NB * FHEAD * 4;
+constexpr uint32_t F_RAW_SLOT = F_OFF_FP + NB * FPLANE * 4;   // 10368 B
+static_assert(F_OFF_GPK % 128 == 0 && F_OFF_FH % 128 == 0 && F_RAW_SLOT % 128 == 0 && (F_OFF_FP % 16) == 0, "alignment");
+constexpr uint32_t F_SMEM_NOTS = SLOT_CTRL + F_S_RAW * F_RAW_SLOT + F_S_PROC * F_PROC_SLOT;   // + TScratch
 
-template <bool SAME, bool EXTRAS>
-__device__ __forceinline__ void transform_entry_f32(const unsigned char* __restrict__ rs, float* __restrict__ pf, QLay ql,
-                                                    int e, int sgrp, uint32_t jm, uint32_t km, float (&PA)[8], float (&PB)[8],
-                                                    float (&P1)[8]) {
-  const int flip = sgrp >> 2;
-  // Q'[l][m] of this entry, row-major, rounded to fp32
-  const double2* qp = reinterpret_cast<const double2*>(rs + OFF_Q + ql.po + e * ql.pp);
-  const double2 qa = qp[0], qb = qp[1], qc = qp[2], qd = qp[3];
-  const float q00 = (float)qa.x, q01 = (float)qa.y, q02 = (float)qb.x, q10 = (float)qb.y, q11 = (float)qc.x,
-              q12 = (float)qc.y, q20 = (float)qd.x, q21 = (float)qd.y, q22 = (float)qp[4].x;
-  float h[6];
-  if (EXTRAS) {
-    const double2* qh = reinterpret_cast<const double2*>(rs + OFF_Q + e * ql.hp);
-    const double2 h0 = qh[0], h1 = qh[1], h2 = qh[2];   // GL0 GL1 | GL2 f0 | f1 f2
-    h[0] = (float)h0.x; h[1] = (float)h0.y; h[2] = (float)h1.x; h[3] = (float)h1.y; h[4] = (float)h2.x;
-    h[5] = (float)h2.y;
-  }
-  const int s0 = 8 * sgrp;
-  const unsigned char* rj = rs + OFF_GPJ + e * GROWJ + GPFX * 4 + s0 * 12;
-  const unsigned char* rk = SAME ? rj : rs + OFF_GPK + e * GROWK + GPFX * 4 + (s0 & 31) * 12;
-  float* af = pf + (2 * sgrp) * F_BLK4_FLT + e * 12;
-  float* wf = af + F_SIDE_FLT;
-#pragma unroll
-  for (int hb = 0; hb < 2; ++hb) {
-    const int b = hb ^ flip;                      // 4-sample block of this lane's eight samples
-    float g[12];
-    if (SAME || sgrp < 4) {
-      const float4* src = reinterpret_cast<const float4*>(rk + b * 48);
-      const float4 x = src[0], y = src[1], z = src[2];
-      g[0] = x.x; g[1] = x.y; g[2] = x.z; g[3] = x.w; g[4] = y.x; g[5] = y.y; g[6] = y.z; g[7] = y.w;
-      g[8] = z.x; g[9] = z.y; g[10] = z.z; g[11] = z.w;
-      float w[12];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float f0 = g[3 * i], f1 = g[3 * i + 1], f2 = g[3 * i + 2];
-        const bool kv = (km >> (4 * b + i)) & 1u;
-        w[3 * i + 0] = kv ? fmaf(q02, f2, fmaf(q01, f1, q00 * f0)) : 1.0f;
-        w[3 * i + 1] = kv ? fmaf(q12, f2, fmaf(q11, f1, q10 * f0)) : 0.0f;
-        w[3 * i + 2] = kv ? fmaf(q22, f2, fmaf(q21, f1, q20 * f0)) : 0.0f;
-        if (EXTRAS) {
-          PA[4 * hb + i] *= fmaf(h[5], f2, fmaf(h[4], f1, h[3] * f0));
-          PB[4 * hb + i] *= (f0 + f1) + f2;
-          P1[4 * hb + i] *= fmaf(h[2], f2, fmaf(h[1], f1, h[0] * f0));
-        }
-      }
-      float4* dw = reinterpret_cast<float4*>(wf + b * F_BLK4_FLT);
-      dw[0] = make_float4(w[0], w[1], w[2], w[3]);
-      dw[1] = make_float4(w[4], w[5], w[6], w[7]);
-      dw[2] = make_float4(w[8], w[9], w[10], w[11]);
-    }
-    if (!SAME) {
-      const float4* src = reinterpret_cast<const float4*>(rj + b * 48);
-      const float4 x = src[0], y = src[1], z = src[2];
-      g[0] = x.x; g[1] = x.y; g[2] = x.z; g[3] = x.w; g[4] = y.x; g[5] = y.y; g[6] = y.z; g[7] = y.w;
-      g[8] = z.x; g[9] = z.y; g[10] = z.z; g[11] = z.w;
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const bool jv = (jm >> (4 * b + i)) & 1u;
-      g[3 * i] = jv ? g[3 * i] : 1.0f;
-      g[3 * i + 1] = jv ? g[3 * i + 1] : 0.0f;
-      g[3 * i + 2] = jv ? g[3 * i + 2] : 0.0f;
-    }
-    float4* da = reinterpret_cast<float4*>(af + b * F_BLK4_FLT);
-    da[0] = make_float4(g[0], g[1], g[2], g[3]);
-    da[1] = make_float4(g[4], g[5], g[6], g[7]);
-    da[2] = make_float4(g[8], g[9], g[10], g[11]);
-  }
+__device__ __forceinline__ void bulk_g2s_elect(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
 }
 
-__device__ __forceinline__ void transform_role_f32(const ScanParams& p, const Pipe& pp, TScratch* ts, int tw, int lane,
-                                                   int u, int NS) {
-  const int sgrp = lane & 7, e = tw * 4 + (lane >> 3);
-  const int flip = sgrp >> 2, s0 = 8 * sgrp;
-  const QLay ql = {(uint32_t)p.q_hp, (uint32_t)p.q_po, (uint32_t)p.q_pp};
+__device__ __forceinline__ void loader_role_f32(const ScanParams& p, const ScanMaps& tm, const Pipe& pp, int lane, int u,
+                                                int NS) {
+  const uint32_t raw0 = smem_u32(pp.raw_base), full0 = smem_u32(pp.raw_full);
   uint32_t git = 0;
   TaskInfo ti;
   for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
     const TaskType tt = p.tt[ti.tti];
     const bool same = tt.flags & TF_TRI;
-    const bool extras_t = (tt.flags & TF_EXTRAS) && !(p.dbg & 16);
-    const bool scal_t = (tt.flags & (TF_SCALARS | TF_L00)) && !(p.dbg & 32);
-    const bool scal = scal_t && sgrp == 0;            // this lane also carries the scalars of its entry slot
-    // validity masks of this lane's eight samples on each side (bit = 4 * block + i)
-    uint32_t jm = 0, km = 0;
+    const int colj = tt.j0 * 3, colk = tt.k0 * 3;
+    const float* fplane = p.entf_plane + (int64_t)((tt.qoff - QHEAD) / QPLANE) * p.entf_pstride;
+    const uint32_t bytes = (uint32_t)NB * (GROWJ + (same ? 0u : GROWK)) + (uint32_t)NB * (FHEAD + FPLANE) * 4u;
+    // SNP ids are fetched 32 entries (4 stages) at a time, one block ahead: the global-load latency of the ids must
+    // not sit on the per-stage critical path
+    int snp_cur = (ti.e0 + lane < ti.e1) ? __ldg(p.ent_snp + ti.e0 + lane) : 0;
+    int snp_nxt = (ti.e0 + 32 + lane < ti.e1) ? __ldg(p.ent_snp + ti.e0 + 32 + lane) : 0;
+    for (int it = 0; it < ti.nst; ++it, ++git) {
+      const uint32_t rslot = git % F_S_RAW;
+      const uint32_t ph = (git / F_S_RAW) & 1u;
+      const int64_t eb = ti.e0 + (int64_t)it * NB;
+      if (it && (it & 3) == 0) {
+        snp_cur = snp_nxt;
+        snp_nxt = (eb + 32 + lane < ti.e1) ? __ldg(p.ent_snp + eb + 32 + lane) : 0;
+      }
+      int s[NB];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (s0 + i < tt.nj) jm |= 1u << i;
-      if (same ? (s0 + i < tt.nj) : (s0 + i < tt.nk)) km |= 1u << i;
+      for (int i = 0; i < NB; ++i) s[i] = __shfl_sync(0xffffffffu, snp_cur, (it & 3) * NB + i);
+      mbar_wait(&pp.raw_empty[rslot], ph ^ 1u);
+      const uint32_t rs = raw0 + rslot * F_RAW_SLOT, bar = full0 + rslot * 8u;
+      mbar_expect_tx_elect(bar, bytes);
+      tma_gather4_elect(rs + F_OFF_GPJ, &tm.gpj, colj, s[0], s[1], s[2], s[3], bar);
+      tma_gather4_elect(rs + F_OFF_GPJ + 4 * GROWJ, &tm.gpj, colj, s[4], s[5], s[6], s[7], bar);
+      if (!same) {
+        tma_gather4_elect(rs + F_OFF_GPK, &tm.gpk, colk, s[0], s[1], s[2], s[3], bar);
+        tma_gather4_elect(rs + F_OFF_GPK + 4 * GROWK, &tm.gpk, colk, s[4], s[5], s[6], s[7], bar);
+      }
+      // entry slots beyond the cell's last entry read the next cell's records (the tables have NB records of slack)
+      bulk_g2s_elect(rs + F_OFF_FH, p.entf_head + eb * FHEAD, NB * FHEAD * 4, bar);
+      bulk_g2s_elect(rs + F_OFF_FP, fplane + eb * FPLANE, NB * FPLANE * 4, bar);
     }
-    float PA[8], PB[8], P1[8];                        // running fp32 products (extras), slot h = 4 * hb + i
-    int eA[8], eB[8], e1x[8];
+  }
+}
+
+// F_NTW = 4 transform warps.  A lane serves ONE entry slot of every stage (e = 2 * warp + lane / 16) and one
+// 4-sample block q = lane % 16 of each side, so everything moves as 16-byte vectors: the 12 floats of its samples'
+// GP rows (3 LDS.128, 48-byte lane stride: conflict free), the entry's fp32 record (5 LDS.128, two distinct
+// addresses per warp), and the (a, w) blocks of the processed ring (3 + 3 STS.128, conflict free by the
+// F_BLK4_FLT padding).  w_k[l] = sum_m Q'[l][m] gp_k[m] in fp32.  The per-sample extras (singlet factor of the
+// separable plane, row sums, pass 1) are fp32 running products per lane = per (entry slot, sample); a product is
+// peeled into an integer exponent only when it gets small (checked every F_PEEL_STAGES stages), and the eight entry
+// slots of a sample are multiplied together in fp64 at the end of the task: one log per sample and quantity.
+struct TScratch {
+  double xm[2][F_NTW][4][BLK];       // [task parity][warp][PA, PB, P1, P0][sample]: mantissa products of the warp's slots
+  int xe[2][F_NTW][4][BLK];          // ... and their exponent sums
+};
+constexpr uint32_t F_TS_BYTES = (sizeof(TScratch) + 127) / 128 * 128;
+
+__device__ __forceinline__ void store_neutral_quad(float* dst) {   // four (1, 0, 0) vectors
+  float4* d = reinterpret_cast<float4*>(dst);
+  d[0] = make_float4(1.f, 0.f, 0.f, 1.f);
+  d[1] = make_float4(0.f, 0.f, 1.f, 0.f);
+  d[2] = make_float4(0.f, 1.f, 0.f, 0.f);
+}
+
+// ROW0: 0 none, 1 symmetric plane (P0 of k-sample x *= a_0 . w_x), 2 full plane (P0 of j-sample x *= a_x . w_0)
+template <bool SAME, bool EXTRAS, int ROW0>
+__device__ __forceinline__ void transform_quad_f32(const unsigned char* __restrict__ rs, float* __restrict__ pf, int e,
+                                                   int q, bool jq, bool kq, float (&PA)[4], float (&PB)[4],
+                                                   float (&P1)[4], float (&P0)[4]) {
+  float* af = pf + q * F_BLK4_FLT + e * 12;
+  float* wf = af + F_SIDE_FLT;
+  float g[12];
+  if (SAME || q < BLK_RECT_K / 4) {
+    if (kq) {
+      const float4* src = reinterpret_cast<const float4*>(
+          rs + (SAME ? F_OFF_GPJ + e * GROWJ : F_OFF_GPK + e * GROWK) + GPFX * 4 + q * 48);
+      const float4 x = src[0], y = src[1], z = src[2];
+      g[0] = x.x; g[1] = x.y; g[2] = x.z; g[3] = x.w; g[4] = y.x; g[5] = y.y; g[6] = y.z; g[7] = y.w;
+      g[8] = z.x; g[9] = z.y; g[10] = z.z; g[11] = z.w;
+      const float4* qp = reinterpret_cast<const float4*>(rs + F_OFF_FP + e * (FPLANE * 4));
+      const float4 qa = qp[0], qb = qp[1];       // Q'[l][m] row-major: (00 01 02 10) (11 12 20 21) (22 . . .)
+      const float q22 = reinterpret_cast<const float*>(qp + 2)[0];
+      float w[12];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { PA[i] = PB[i] = P1[i] = 1.0f; eA[i] = eB[i] = e1x[i] = 0; }
-    int nflush_x = 0;
-    double PS0 = 1.0, PS1 = 1.0, PS2 = 1.0;           // scalars: llk0s, llks00[sep], llks00[n]
-    int eS0 = 0, eS1 = 0, eS2 = 0;
-    int nflush = 0;
+      for (int i = 0; i < 4; ++i) {
+        const float f0 = g[3 * i], f1 = g[3 * i + 1], f2 = g[3 * i + 2];
+        w[3 * i + 0] = fmaf(qa.z, f2, fmaf(qa.y, f1, qa.x * f0));
+        w[3 * i + 1] = fmaf(qb.y, f2, fmaf(qb.x, f1, qa.w * f0));
+        w[3 * i + 2] = fmaf(q22, f2, fmaf(qb.w, f1, qb.z * f0));
+      }
+      if (EXTRAS) {
+        const float4* hp = reinterpret_cast<const float4*>(rs + F_OFF_FH + e * (FHEAD * 4));
+        const float4 h0 = hp[0];                  // GL0 GL1 GL2 f0
+        const float2 h1 = reinterpret_cast<const float2*>(hp + 1)[0];   // f1 f2
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float f0 = g[3 * i], f1 = g[3 * i + 1], f2 = g[3 * i + 2];
+          PA[i] *= fmaf(h1.y, f2, fmaf(h1.x, f1, h0.w * f0));
+          PB[i] *= (f0 + f1) + f2;
+          P1[i] *= fmaf(h0.z, f2, fmaf(h0.y, f1, h0.x * f0));
+        }
+      }
+      if (ROW0 == 1) {   // pairs (0, x): sample 0 is the first sample of the j-side row (j0 == 0)
+        const float* a0 = reinterpret_cast<const float*>(rs + F_OFF_GPJ + e * GROWJ + GPFX * 4);
+        const float a00 = a0[0], a01 = a0[1], a02 = a0[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) P0[i] *= fmaf(a02, w[3 * i + 2], fmaf(a01, w[3 * i + 1], a00 * w[3 * i]));
+      }
+      float4* dw = reinterpret_cast<float4*>(wf);
+      dw[0] = make_float4(w[0], w[1], w[2], w[3]);
+      dw[1] = make_float4(w[4], w[5], w[6], w[7]);
+      dw[2] = make_float4(w[8], w[9], w[10], w[11]);
+    } else {
+      store_neutral_quad(wf);
+    }
+  }
+  if (jq) {
+    if (!SAME) {
+      const float4* src = reinterpret_cast<const float4*>(rs + F_OFF_GPJ + e * GROWJ + GPFX * 4 + q * 48);
+      const float4 x = src[0], y = src[1], z = src[2];
+      float4* da = reinterpret_cast<float4*>(af);
+      da[0] = x; da[1] = y; da[2] = z;
+      if (ROW0 == 2) {   // pairs (x, 0): sample 0 is the first sample of the k-side row (k0 == 0)
+        const float* g0p = reinterpret_cast<const float*>(rs + F_OFF_GPK + e * GROWK + GPFX * 4);
+        const float f0 = g0p[0], f1 = g0p[1], f2 = g0p[2];
+        const float4* qp = reinterpret_cast<const float4*>(rs + F_OFF_FP + e * (FPLANE * 4));
+        const float4 qa = qp[0], qb = qp[1];
+        const float q22 = reinterpret_cast<const float*>(qp + 2)[0];
+        const float w0 = fmaf(qa.z, f2, fmaf(qa.y, f1, qa.x * f0));
+        const float w1 = fmaf(qb.y, f2, fmaf(qb.x, f1, qa.w * f0));
+        const float w2 = fmaf(q22, f2, fmaf(qb.w, f1, qb.z * f0));
+        P0[0] *= fmaf(x.z, w2, fmaf(x.y, w1, x.x * w0));
+        P0[1] *= fmaf(y.y, w2, fmaf(y.x, w1, x.w * w0));
+        P0[2] *= fmaf(z.x, w2, fmaf(y.w, w1, y.z * w0));
+        P0[3] *= fmaf(z.w, w2, fmaf(z.z, w1, z.y * w0));
+      }
+    } else {
+      float4* da = reinterpret_cast<float4*>(af);
+      da[0] = make_float4(g[0], g[1], g[2], g[3]);
+      da[1] = make_float4(g[4], g[5], g[6], g[7]);
+      da[2] = make_float4(g[8], g[9], g[10], g[11]);
+    }
+  } else {
+    store_neutral_quad(af);
+  }
+}
+
+// conditional peel of a running fp32 product: exponent into `es` (unbiased), mantissa back to [1, 2)
+__device__ __forceinline__ void peelf_unbiased(float& x, int& es) {
+  const uint32_t b = __float_as_uint(x);
+  if (b >= 0x00800000u) {
+    es += (int)(b >> 23) - 127;
+    x = __uint_as_float((b & 0x007fffffu) | 0x3f800000u);
+  }
+}
+
+__device__ __forceinline__ void transform_role_f32(const ScanParams& p, const Pipe& pp, TScratch* ts, int tw, int lane,
+                                                   int u, int NS) {
+  const int e = tw * 2 + (lane >> 4), q = lane & 15;
+  const int tl = tw * 32 + lane;
+  uint32_t git = 0;
+  TaskInfo ti;
+  for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
+    const TaskType tt = p.tt[ti.tti];
+    const bool same = tt.flags & TF_TRI;
+    const bool extras_t = (tt.flags & TF_EXTRAS) != 0;
+    const bool jq = 4 * q < tt.nj;                                  // nj, nk are multiples of 4
+    const bool kq = same ? jq : (4 * q < tt.nk);
+    // pairs with sample 0: on the k side of symmetric tasks, on the j side of the (rectangular) tasks of full planes
+    const int row0 = !(tt.flags & TF_ROW0) ? 0 : ((tt.flags & TF_SYM) ? 1 : (same ? 0 : 2));
+    const bool prods_t = extras_t || row0 != 0;
+    float PA[4], PB[4], P1[4], P0[4];                 // running fp32 products (extras) of this lane's samples
+    int eA[4], e1x[4], e0x[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { PA[i] = PB[i] = P1[i] = P0[i] = 1.0f; eA[i] = e1x[i] = e0x[i] = 0; }
     for (int it = 0; it < ti.nst; ++it, ++git) {
       const int rslot = git % F_S_RAW, pslot = git % F_S_PROC;
       const uint32_t rph = (git / F_S_RAW) & 1u, pph = (git / F_S_PROC) & 1u;
       const int nvalid = (int)min((int64_t)NB, ti.e1 - (ti.e0 + (int64_t)it * NB));
-      const long long tt0 = clock64();
       mbar_wait(&pp.raw_full[rslot], rph);
-      const long long tt1 = clock64();
       mbar_wait(&pp.proc_empty[pslot], pph ^ 1u);
-      if ((p.dbg & 8) && blockIdx.x == 0 && lane == 0 && tw == 0 && r == 1 && it < 256) { p.dbgbuf[it * 8 + 2] = tt0; p.dbgbuf[it * 8 + 3] = tt1; p.dbgbuf[it * 8 + 4] = clock64(); }
-      const unsigned char* rs = pp.raw_base + (size_t)rslot * RAW_SLOT;
+      const unsigned char* rs = pp.raw_base + (size_t)rslot * F_RAW_SLOT;
       float* pf = reinterpret_cast<float*>(pp.proc_base + (size_t)pslot * F_PROC_SLOT);
       if (p.dbg & 2) {
       } else if (e < nvalid) {
         if (same) {
-          if (extras_t) transform_entry_f32<true, true>(rs, pf, ql, e, sgrp, jm, km, PA, PB, P1);
-          else transform_entry_f32<true, false>(rs, pf, ql, e, sgrp, jm, km, PA, PB, P1);
-        } else {
-          if (extras_t) transform_entry_f32<false, true>(rs, pf, ql, e, sgrp, jm, km, PA, PB, P1);
-          else transform_entry_f32<false, false>(rs, pf, ql, e, sgrp, jm, km, PA, PB, P1);
-        }
-        if (scal) {
-          // per-entry factors precomputed by entq_kernel
-          const double* hq = reinterpret_cast<const double*>(rs + OFF_Q + e * ql.hp);
-          const double* q = reinterpret_cast<const double*>(rs + OFF_Q + ql.po + e * ql.pp);
-          if (tt.flags & TF_SCALARS) {
-            if (p.want_single) PS0 *= hq[6];                                                          // :459
-            if (p.sep0) PS1 *= hq[7];
+          if (extras_t) {
+            if (row0) transform_quad_f32<true, true, 1>(rs, pf, e, q, jq, kq, PA, PB, P1, P0);
+            else transform_quad_f32<true, true, 0>(rs, pf, e, q, jq, kq, PA, PB, P1, P0);
+          } else {
+            if (row0) transform_quad_f32<true, false, 1>(rs, pf, e, q, jq, kq, PA, PB, P1, P0);
+            else transform_quad_f32<true, false, 0>(rs, pf, e, q, jq, kq, PA, PB, P1, P0);
           }
-          if (tt.flags & TF_L00) PS2 *= q[9];                                                         // :700-709
+        } else {
+          if (extras_t) {
+            if (row0 == 2) transform_quad_f32<false, true, 2>(rs, pf, e, q, jq, kq, PA, PB, P1, P0);
+            else if (row0 == 1) transform_quad_f32<false, true, 1>(rs, pf, e, q, jq, kq, PA, PB, P1, P0);
+            else transform_quad_f32<false, true, 0>(rs, pf, e, q, jq, kq, PA, PB, P1, P0);
+          } else {
+            if (row0 == 2) transform_quad_f32<false, false, 2>(rs, pf, e, q, jq, kq, PA, PB, P1, P0);
+            else if (row0 == 1) transform_quad_f32<false, false, 1>(rs, pf, e, q, jq, kq, PA, PB, P1, P0);
+            else transform_quad_f32<false, false, 0>(rs, pf, e, q, jq, kq, PA, PB, P1, P0);
+          }
         }
       } else {   // identity entry: S = 1 for every hypothesis
-        float* af = pf + (2 * sgrp) * F_BLK4_FLT + e * 12;
-        const float4 i0 = make_float4(1.f, 0.f, 0.f, 1.f), i1 = make_float4(0.f, 0.f, 1.f, 0.f),
-                     i2 = make_float4(0.f, 1.f, 0.f, 0.f);
+        store_neutral_quad(pf + q * F_BLK4_FLT + e * 12);
+        store_neutral_quad(pf + F_SIDE_FLT + q * F_BLK4_FLT + e * 12);
+      }
+      if (prods_t && (it % F_PEEL_STAGES) == F_PEEL_STAGES - 1) {
+        // every factor is >= ~1e-6 (the +1e-6 floors of :446-452 and :643-663), so F_PEEL_STAGES more of them keep a
+        // product that is above 2^-46 now inside the fp32 range; exact zeros (padding samples) are left alone
+        float mn = 1.0f;
 #pragma unroll
-        for (int hb = 0; hb < 2; ++hb) {
-          const int b = hb ^ flip;
-          float4* da = reinterpret_cast<float4*>(af + b * F_BLK4_FLT);
-          float4* dw = reinterpret_cast<float4*>(af + F_SIDE_FLT + b * F_BLK4_FLT);
-          da[0] = i0; da[1] = i1; da[2] = i2;
-          dw[0] = i0; dw[1] = i1; dw[2] = i2;
+        for (int i = 0; i < 4; ++i) {
+          mn = fminf(mn, PA[i] > 0.f ? PA[i] : 1.0f);
+          mn = fminf(mn, P1[i] > 0.f ? P1[i] : 1.0f);
+          mn = fminf(mn, P0[i] > 0.f ? P0[i] : 1.0f);
         }
-      }
-      if ((p.dbg & 8) && blockIdx.x == 0 && lane == 0 && tw == 0 && r == 1 && it < 256) p.dbgbuf[it * 8 + 7] = clock64();
-      if (extras_t && (it & 3) == 3) {   // fp32 products: every 4 entries of this lane (factors >= 1e-6 each)
+        if (__any_sync(0xffffffffu, mn < 0x1p-46f)) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { peelf(PA[i], eA[i]); peelf(PB[i], eB[i]); peelf(P1[i], e1x[i]); }
-        ++nflush_x;
-      }
-      if ((it & 15) == 15) {   // fp64 scalars: every 16 entries of this lane
-        peel(PS0, eS0); peel(PS1, eS1); peel(PS2, eS2);
-        ++nflush;
+          for (int i = 0; i < 4; ++i) {
+            peelf_unbiased(PA[i], eA[i]); peelf_unbiased(P1[i], e1x[i]); peelf_unbiased(P0[i], e0x[i]);
+          }
+        }
       }
       __syncwarp();
       if (lane == 0) {
@@ -902,68 +1020,49 @@ __device__ __forceinline__ void transform_role_f32(const ScanParams& p, const Pi
         mbar_arrive(&pp.raw_empty[rslot]);
       }
     }
-    if (!(extras_t || scal_t)) continue;   // uniform over the transform warps
+    if (!prods_t) continue;   // uniform over the transform warps
     const int buf = r & 1;
-    // fold the four entry slots of this warp (lanes 8 apart), then the two warps through shared memory
-    double la[8], lbv[8], l1[8];
-    if (extras_t) {
+    // fold the two entry slots of this warp (lanes 16 apart), then the four warps through shared memory
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        la[i] = p.sep0 ? unpeelf_log(PA[i], eA[i], nflush_x) : 0.0;
-        lbv[i] = unpeelf_log(PB[i], eB[i], nflush_x);
-        l1[i] = p.want_single ? unpeelf_log(P1[i], e1x[i], nflush_x) : 0.0;
-#pragma unroll
-        for (int o = 8; o < 32; o <<= 1) {
-          la[i] += __shfl_xor_sync(0xffffffffu, la[i], o);
-          lbv[i] += __shfl_xor_sync(0xffffffffu, lbv[i], o);
-          l1[i] += __shfl_xor_sync(0xffffffffu, l1[i], o);
-        }
+    for (int i = 0; i < 4; ++i) {
+      double ma = (double)PA[i], mb = (double)PB[i], m1 = (double)P1[i], m0 = (double)P0[i];
+      int xa = eA[i], x1 = e1x[i], x0 = e0x[i];
+      ma *= __shfl_xor_sync(0xffffffffu, ma, 16);
+      mb *= __shfl_xor_sync(0xffffffffu, mb, 16);
+      m1 *= __shfl_xor_sync(0xffffffffu, m1, 16);
+      m0 *= __shfl_xor_sync(0xffffffffu, m0, 16);
+      xa += __shfl_xor_sync(0xffffffffu, xa, 16);
+      x1 += __shfl_xor_sync(0xffffffffu, x1, 16);
+      x0 += __shfl_xor_sync(0xffffffffu, x0, 16);
+      if (lane < 16) {
+        const int smp = 4 * q + i;
+        ts->xm[buf][tw][0][smp] = ma; ts->xe[buf][tw][0][smp] = xa;
+        ts->xm[buf][tw][1][smp] = mb; ts->xe[buf][tw][1][smp] = 0;
+        ts->xm[buf][tw][2][smp] = m1; ts->xe[buf][tw][2][smp] = x1;
+        ts->xm[buf][tw][3][smp] = m0; ts->xe[buf][tw][3][smp] = x0;
       }
-    }
-    double s0v = 0.0, s1v = 0.0, s2v = 0.0;
-    if (scal_t) {
-      s0v = scal ? unpeel_log(PS0, eS0, nflush) : 0.0;
-      s1v = scal ? unpeel_log(PS1, eS1, nflush) : 0.0;
-      s2v = scal ? unpeel_log(PS2, eS2, nflush) : 0.0;
-#pragma unroll
-      for (int o = 8; o < 32; o <<= 1) {
-        s0v += __shfl_xor_sync(0xffffffffu, s0v, o);
-        s1v += __shfl_xor_sync(0xffffffffu, s1v, o);
-        s2v += __shfl_xor_sync(0xffffffffu, s2v, o);
-      }
-    }
-    if (tw == 1 && lane < 8) {
-      if (extras_t) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int smp = s0 + 4 * ((i >> 2) ^ flip) + (i & 3);
-          ts->xfer[buf][0][smp] = la[i];
-          ts->xfer[buf][1][smp] = lbv[i];
-          ts->xfer[buf][2][smp] = l1[i];
-        }
-      }
-      if (scal_t && lane == 0) { ts->xs[buf][0] = s0v; ts->xs[buf][1] = s1v; ts->xs[buf][2] = s2v; }
     }
     asm volatile("bar.sync 2, %0;" ::"n"(F_NTW * 32) : "memory");
-    if (tw == 0 && lane < 8) {
-      if (extras_t) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int smp = s0 + 4 * ((i >> 2) ^ flip) + (i & 3);
-          const int k = tt.k0 + smp;
-          if (smp < tt.nk && k < p.nv) {
-            if (p.sep0) p.singA[(int64_t)ti.cell * p.nv + k] = la[i] + ts->xfer[buf][0][smp];
-            p.lb[(int64_t)ti.cell * p.nv + k] = lbv[i] + ts->xfer[buf][1][smp];
-            if (p.want_single) p.p1[(int64_t)ti.cell * p.nv + k] = l1[i] + ts->xfer[buf][2][smp];
-          }
-        }
+    // 4 x 64 (quantity, sample) results over the 128 transform lanes
+    for (int item = tl; item < 4 * BLK; item += F_NTW * 32) {
+      const int c = item >> 6, smp = item & (BLK - 1);
+      if (c < 3) {
+        if (!extras_t || smp >= tt.nk || tt.k0 + smp >= p.nv) continue;
+        if ((c == 0 && !p.sep0) || (c == 2 && !p.want_single)) continue;
+      } else {
+        if (row0 == 0) continue;
+        if (row0 == 1 ? (smp >= tt.nk || tt.k0 + smp >= p.nv) : (smp >= tt.nj || tt.j0 + smp >= p.nv)) continue;
       }
-      if (scal_t && lane == 0) {
-        if (tt.flags & TF_SCALARS) {
-          if (p.want_single) p.p1_0[ti.cell] = s0v + ts->xs[buf][0];
-          if (p.sep0) p.l00[(int64_t)ti.cell * p.nA] = s1v + ts->xs[buf][1];
-        }
-        if (tt.flags & TF_L00) p.l00[(int64_t)ti.cell * p.nA + tt.n] = s2v + ts->xs[buf][2];
+      double m = 1.0;
+      int ex = 0;
+#pragma unroll
+      for (int w = 0; w < F_NTW; ++w) { m *= ts->xm[buf][w][c][smp]; ex += ts->xe[buf][w][c][smp]; }
+      const double v = (double)ex * 0.693147180559945309417232121458 + log(m);
+      if (c < 3) {
+        double* dst = c == 0 ? p.singA : (c == 1 ? p.lb : p.p1);
+        dst[(int64_t)ti.cell * p.nv + tt.k0 + smp] = v;
+      } else {
+        p.row0[((int64_t)ti.cell * p.nA + tt.n) * p.nv + (row0 == 1 ? tt.k0 : tt.j0) + smp] = v;
       }
     }
   }
@@ -972,7 +1071,7 @@ __device__ __forceinline__ void transform_role_f32(const ScanParams& p, const Pi
 // =============================== per-task reductions (:712-734, :799-814) ==========================
 // Every consumer thread brings NV llk values with their (j, k); the block of NW consumer warps reduces them to
 // the task's Part (max, sum of exp, best pair value, near-tie candidates) and stores row 0 / the dense block.
-template <int NV, int NW>
+template <int NV, int NW, bool ROW0>
 __device__ __forceinline__ void task_epilogue(const ScanParams& p, const TaskInfo& ti, const TaskType& tt, Scratch* scr,
                                               int bar_id, int rw, int lane, const double (&v)[NV], const int (&vj)[NV],
                                               const int (&vk)[NV], uint32_t vmask) {
@@ -1013,10 +1112,12 @@ __device__ __forceinline__ void task_epilogue(const ScanParams& p, const TaskInf
       }
     }
     // row k = 0 of the plane (LLK10 / LLK20, :824-825; singlets when plane 0 is dense)
-    if (sym) {
-      if (j == 0) p.row0[((int64_t)ti.cell * p.nA + tt.n) * p.nv + k] = x;
-    } else if (k == 0) {
-      p.row0[((int64_t)ti.cell * p.nA + tt.n) * p.nv + j] = x;
+    if (ROW0) {
+      if (sym) {
+        if (j == 0) p.row0[((int64_t)ti.cell * p.nA + tt.n) * p.nv + k] = x;
+      } else if (k == 0) {
+        p.row0[((int64_t)ti.cell * p.nA + tt.n) * p.nv + j] = x;
+      }
     }
     if (p.dense) {
       double* d = p.dense + ti.aidx * p.nv * p.nv * p.nA;
@@ -1144,7 +1245,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_scan_kernel(const __grid_con
   if (role == 2) {
     loader_role<S_RAW>(p, tm, pp, lane, u, NS);
   } else if (role == 1) {
-    transform_role<false, S_RAW, S_PROC, PROC_SLOT>(p, pp, rw, lane, u, NS);
+    transform_role<S_RAW, S_PROC, PROC_SLOT>(p, pp, rw, lane, u, NS);
   } else {
     // =============================== consumer warps ============================================
     uint32_t git = 0;   // stages consumed so far in this slot (same sequence in every role)
@@ -1220,7 +1321,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_scan_kernel(const __grid_con
           vk[t * 2 + i] = k;
           if (valid) vmask |= 1u << (t * 2 + i);
         }
-      task_epilogue<NTILE * 2, NCW>(p, ti, tt, scr, slot, rw, lane, v, vj, vk, vmask);
+      task_epilogue<NTILE * 2, NCW, true>(p, ti, tt, scr, slot, rw, lane, v, vj, vk, vmask);
     }
   }
 }
@@ -1248,16 +1349,28 @@ __device__ __forceinline__ void tile_math(const float (&a)[8][3], const float (&
 }
 
 // ---------------------------------------------------------------------------------------------
-// fp32 pair scan.  Warps 0..8 consumers, 9..10 transform, 11 loader (SM sub-partition = warp % 4: 3 / 2+T / 2+T /
-// 2+L).  A consumer thread owns the 8 x 8 tile (bj, bk) of hypotheses for the entries e = lane & 7 of every
-// stage: per entry 12 LDS.128 (two 4-sample blocks of a, two of w), 64 x (FMUL + 2 FFMA) for S[j][k] and 64 FMUL
-// into the running products.  Every F_PEEL_STAGES entries the warp checks for products about to leave the fp32
-// range and, if any, peels all exponents into per-thread integer accumulators in shared memory.  At the end of a
-// task the eight entry lanes of a tile multiply their products together (in fp64, butterfly shuffles) and lane e
-// takes the log of column e.
+// fp32 pair scan: one task pipeline per CTA, 16 warps in four warpgroups.  SM sub-partition = warp id % 4; roles are
+// placed so that the issue load of the four sub-partitions is even (C = consumer, D = consumer of diagonal tiles:
+// 36 / 64 of the work, T = transform, L = loader, - = exits at once):
+//   wid   0  1  2  3 |  4  5  6  7 |  8  9 10 11 | 12 13 14 15
+//         D  C  C  C |  D  C  C  C |  C  T  T  T |  T  L  -  -
+// The last warpgroup gives registers back (setmaxnreg) so that the consumers' 64 accumulators + 48 operands fit.
+//
+// A consumer thread owns the 8 x 8 tile (bj, bk) of hypotheses for the entries e = lane & 7 of every stage: per
+// entry 12 LDS.128 (two 4-sample blocks of a, two of w), 64 x (FMUL + 2 FFMA) for S[j][k] and 64 FMUL into the
+// running products.  Range: a thread's 64 products share one integer exponent (block floating point): every
+// F_PEEL_STAGES entries the warp checks whether some thread's LARGEST product is about to leave the fp32 range and,
+// if so, every thread rescales its tile by a power of two.  A hypothesis more than ~2^-80 below the best of its own
+// tile underflows to zero (llk = -inf): it cannot be the best pair, a near tie or a visible term of sumDouble.  The
+// pairs with sample 0 that .best prints (LLK10 / LLK20) do not come from here but from the transform warps (TF_ROW0),
+// and dense llksAB blocks (--write-pair) from the fp64 scan.  At the end of a task the eight entry lanes of a tile
+// multiply their products together (fp64 reduce-scatter: lane e ends up with tile row e).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(F_NTHREADS, 1) pair_scan_f32_kernel(const __grid_constant__ ScanParams p,
-                                                                    const __grid_constant__ ScanMaps tm) {
+constexpr int F_LAUNCH_THREADS = 512;
+constexpr int F_REGS_HI = 136, F_REGS_LO = 104;   // (3 * 136 + 104) * 32 = 16384 registers per sub-partition
+
+__global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_f32_kernel(const __grid_constant__ ScanParams p,
+                                                                          const __grid_constant__ ScanMaps tm) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Pipe pp;
@@ -1267,13 +1380,12 @@ __global__ void __launch_bounds__(F_NTHREADS, 1) pair_scan_f32_kernel(const __gr
   pp.proc_empty = pp.proc_full + F_S_PROC;
   Scratch* scr = reinterpret_cast<Scratch*>(smem + SCRATCH_OFF);
   pp.raw_base = smem + SLOT_CTRL;
-  pp.proc_base = pp.raw_base + F_S_RAW * RAW_SLOT;
-  int* es_base = reinterpret_cast<int*>(pp.proc_base + F_S_PROC * F_PROC_SLOT);
+  pp.proc_base = pp.raw_base + F_S_RAW * F_RAW_SLOT;
   TScratch* ts = reinterpret_cast<TScratch*>(smem + F_SMEM_NOTS);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < F_S_RAW; ++s) {
-      mbar_init(&pp.raw_full[s], (F_TMA_LOADER || (p.dbg & 4)) ? 1 : 32);
+      mbar_init(&pp.raw_full[s], 1);
       mbar_init(&pp.raw_empty[s], F_NTW);
     }
     for (int s = 0; s < F_S_PROC; ++s) {
@@ -1284,31 +1396,33 @@ __global__ void __launch_bounds__(F_NTHREADS, 1) pair_scan_f32_kernel(const __gr
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  // rings start from finite values: padding lanes of the transform may read slots no copy has written yet
-  for (uint32_t i = threadIdx.x; i < (F_S_RAW * RAW_SLOT + F_S_PROC * F_PROC_SLOT) / 4; i += F_NTHREADS)
-    reinterpret_cast<uint32_t*>(pp.raw_base)[i] = 0u;
   __syncthreads();
 
   const int NS = (int)gridDim.x, u = (int)blockIdx.x;
-  // warps 0..8 consumers (sub-partitions 0,1,2,3,0,1,2,3,0), 9..10 transform, 11 loader
-  if (warp == F_NCW + F_NTW) {
-    if (F_TMA_LOADER || (p.dbg & 4)) loader_role<F_S_RAW>(p, tm, pp, lane, u, NS);
-    else loader_role_cpasync<F_S_RAW>(p, pp, lane, u, NS);
-  } else if (warp >= F_NCW) {
+  if (warp >= 12) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(F_REGS_LO));
+    if (warp == 12) transform_role_f32(p, pp, ts, F_NTW - 1, lane, u, NS);
+    else if (warp == 13) loader_role_f32(p, tm, pp, lane, u, NS);
+    return;
+  }
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(F_REGS_HI));
+  if (warp >= F_NCW) {
     transform_role_f32(p, pp, ts, warp - F_NCW, lane, u, NS);
   } else {
     // =============================== consumer warps ============================================
-    const int rw = warp, el = lane & 7;
+    // logical consumer index: 0..6 own the 28 off-diagonal tile positions of a triangular task, 7 and 8 (physical
+    // warps 0 and 4) the 8 diagonal ones
+    const int rw = warp == 0 ? 7 : (warp == 4 ? 8 : (warp < 4 ? warp - 1 : warp - 2));
+    const int el = lane & 7;
     const int pos = rw * 4 + (lane >> 3);
-    int* es = es_base + rw * 32 + lane;           // es[h * F_ES_STRIDE]: exponent sum of hypothesis h of this thread
     uint32_t git = 0;
     TaskInfo ti;
     for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
       const TaskType tt = p.tt[ti.tti];
       const bool tri = tt.flags & TF_TRI;
       const int nbj = (tt.nj + 7) >> 3, nbk = (tt.nk + 7) >> 3;   // 8-sample blocks on each side
-      // tile positions of a triangular task: 0..27 the off-diagonal tiles (bj < bk, row-major) on warps 0..6, 28..35 the
-      // diagonal tiles on warps 7 and 8, which evaluate only the 36 hypotheses with j <= k of their tile
+      // tile positions of a triangular task: 0..27 the off-diagonal tiles (bj < bk, row-major), 28..35 the diagonal
+      // tiles, which evaluate only the 36 hypotheses with j <= k of their tile
       int bj, bk;
       const bool diag = tri && pos >= 28;
       if (tri) {
@@ -1330,14 +1444,11 @@ __global__ void __launch_bounds__(F_NTHREADS, 1) pair_scan_f32_kernel(const __gr
       float acc[64];
 #pragma unroll
       for (int h = 0; h < 64; ++h) acc[h] = 1.0f;
-      int npeel = 0;
+      int ex = 0;                               // true products = acc * 2^ex
       for (int it = 0; it < ti.nst; ++it, ++git) {
         const int pslot = git % F_S_PROC;
         const uint32_t pph = (git / F_S_PROC) & 1u;
-        const long long tc0 = clock64();
         mbar_wait(&pp.proc_full[pslot], pph);
-        if ((p.dbg & 8) && blockIdx.x == 0 && lane == 0 && rw == 0 && r == 1 && it < 256) { p.dbgbuf[it * 8 + 5] = tc0; p.dbgbuf[it * 8 + 6] = clock64(); }
-        if ((p.dbg & 8) && blockIdx.x == 0 && lane == 0 && r == 1 && it >= 64 && it < 68) { p.dbgbuf[(256 + rw) * 8 + (it - 64) * 2] = tc0; p.dbgbuf[(256 + rw) * 8 + (it - 64) * 2 + 1] = clock64(); }
         if (active && !(p.dbg & 1)) {
           const float* pf = reinterpret_cast<const float*>(pp.proc_base + (size_t)pslot * F_PROC_SLOT);
           float a[8][3], w[8][3];
@@ -1353,70 +1464,72 @@ __global__ void __launch_bounds__(F_NTHREADS, 1) pair_scan_f32_kernel(const __gr
               w[(q / 3) * 4 + f / 3][f % 3] = ys[c];
             }
           }
-          if (diag) tile_math<true>(a, w, acc);     // warp-uniform: rw >= 7
+          if (diag) tile_math<true>(a, w, acc);     // warp-uniform (logical warps 7 and 8)
           else tile_math<false>(a, w, acc);
         }
         if ((it % F_PEEL_STAGES) == F_PEEL_STAGES - 1) {
-          float mn = 1.0f;
+          // a factor is >= ~2^-20 (the 1e-6 floors), so a tile whose largest product is above 2^-46 now keeps it
+          // inside the fp32 range for F_PEEL_STAGES more entries
+          float mx = 0.0f;
 #pragma unroll
-          for (int h = 0; h < 64; h += 2) mn = fminf(mn, fminf(acc[h], acc[h + 1]));
-          // the next F_PEEL_STAGES factors are >= (1e-6)^4 ~ 2^-80 in total: stay above 2^-126
-          if (__any_sync(0xffffffffu, active && mn < 0x1p-46f)) {
-            if (active) {
+          for (int h = 0; h < 64; h += 2) mx = fmaxf(mx, fmaxf(acc[h], acc[h + 1]));
+          if (__any_sync(0xffffffffu, active && mx < 0x1p-46f)) {
+            const uint32_t eb = __float_as_uint(mx) >> 23;            // biased exponent of the largest product
+            const float sc = __uint_as_float((254u - eb) << 23);      // 2^(127 - eb): brings it back to [1, 2)
+            ex += (int)eb - 127;
 #pragma unroll
-              for (int h = 0; h < 64; ++h) {
-                float x = acc[h];
-                uint32_t b = __float_as_uint(x);
-                int e = 0;
-                if (b < 0x00800000u) {          // zero stays zero (llk = -inf); a denormal is renormalised first
-                  x *= 0x1p64f;
-                  b = __float_as_uint(x);
-                  e = -64;
-                }
-                if (b != 0u) {
-                  e += (int)(b >> 23);
-                  acc[h] = __uint_as_float((b & 0x007fffffu) | 0x3f800000u);
-                } else {
-                  e = 127;
-                }
-                if (npeel == 0) es[h * F_ES_STRIDE] = e;
-                else es[h * F_ES_STRIDE] += e;
-              }
-            }
-            ++npeel;
+            for (int h = 0; h < 64; ++h) acc[h] *= sc;
           }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&pp.proc_empty[pslot]);
       }
-      // ---- fold the eight entry lanes of each tile: lane e keeps column e ------------------------------
-      double dcol[8];
-      int ecol[8];
+      // ---- fold the eight entry lanes of each tile (reduce-scatter over lane bits 2, 1, 0): lane e ends up with the
+      // products of tile row e.  Values of different lanes are multiplied in fp64 (no range problem).
+      double d3[8];
+      const bool b2 = el & 4, b1 = el & 2, b0 = el & 1;
 #pragma unroll
-      for (int h = 0; h < 64; ++h) {
-        double dm = (double)acc[h];
-        int ee = npeel ? es[h * F_ES_STRIDE] : 0;
+      for (int cg = 0; cg < 2; ++cg) {          // columns 4 cg .. 4 cg + 3
+        double d1[16];
 #pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-          dm *= __shfl_xor_sync(0xffffffffu, dm, o);
-          if (npeel) ee += __shfl_xor_sync(0xffffffffu, ee, o);
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float lo = acc[i * 8 + cg * 4 + c], hi = acc[(i + 4) * 8 + cg * 4 + c];
+            const double keep = (double)(b2 ? hi : lo), send = (double)(b2 ? lo : hi);
+            d1[i * 4 + c] = keep * __shfl_xor_sync(0xffffffffu, send, 4);
+          }
+        double d2[8];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const double lo = d1[i * 4 + c], hi = d1[(i + 2) * 4 + c];
+            d2[i * 4 + c] = (b1 ? hi : lo) * __shfl_xor_sync(0xffffffffu, b1 ? lo : hi, 2);
+          }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const double lo = d2[c], hi = d2[4 + c];
+          d3[cg * 4 + c] = (b0 ? hi : lo) * __shfl_xor_sync(0xffffffffu, b0 ? lo : hi, 1);
         }
-        if ((h & 7) == el) { dcol[h >> 3] = dm; ecol[h >> 3] = ee; }
       }
+      int exs = ex;
+      exs += __shfl_xor_sync(0xffffffffu, exs, 4);
+      exs += __shfl_xor_sync(0xffffffffu, exs, 2);
+      exs += __shfl_xor_sync(0xffffffffu, exs, 1);
       double v[8];
       int vj[8], vk[8];
       uint32_t vmask = 0;
-      const int ebias = 127 * 8 * npeel;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int j = tt.j0 + bj * 8 + i, k = tt.k0 + bk * 8 + el;
+      for (int c = 0; c < 8; ++c) {
+        const int j = tt.j0 + bj * 8 + el, k = tt.k0 + bk * 8 + c;
         const bool valid = active && j < p.nv && k < p.nv && (!tri || j <= k);
-        v[i] = valid ? (double)(ecol[i] - ebias) * 0.693147180559945309417232121458 + log(dcol[i]) : -INFINITY;
-        vj[i] = j;
-        vk[i] = k;
-        if (valid) vmask |= 1u << i;
+        v[c] = valid ? (double)exs * 0.693147180559945309417232121458 + log(d3[c]) : -INFINITY;
+        vj[c] = j;
+        vk[c] = k;
+        if (valid) vmask |= 1u << c;
       }
-      task_epilogue<8, F_NCW>(p, ti, tt, scr, 0, rw, lane, v, vj, vk, vmask);
+      task_epilogue<8, F_NCW, false>(p, ti, tt, scr, 0, rw, lane, v, vj, vk, vmask);
     }
   }
 }
@@ -1447,7 +1560,7 @@ int launch_pair_scan(const ScanParams& p, const ScanMaps& tm, bool fp32, void* s
   if (fp32) {
     int64_t grid = p.ntasks;
     if (grid > g_num_sms) grid = g_num_sms;
-    pair_scan_f32_kernel<<<(unsigned)grid, F_NTHREADS, smem, (cudaStream_t)stream>>>(p, tm);
+    pair_scan_f32_kernel<<<(unsigned)grid, F_LAUNCH_THREADS, smem, (cudaStream_t)stream>>>(p, tm);
   } else {
     int64_t grid = (p.ntasks + NSLOT - 1) / NSLOT;
     if (grid > g_num_sms) grid = g_num_sms;
