@@ -17,7 +17,7 @@ import numpy as np
 from .plp import Pileup
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdmx.so")
+LIB_PATH = os.environ.get("DMX_LIB") or os.path.join(HERE, "libdmx.so")   # DMX_LIB: experiment builds (tools/)
 
 DMX_EXACT_TIES = 0x1
 DMX_BORROW_INPUTS = 0x2

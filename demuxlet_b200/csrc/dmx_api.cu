@@ -98,6 +98,7 @@ struct dmx_ctx {
   DevBuf<float> d_gp;              // uploaded [nsnps][nvp*3]
   DevBuf<float> d_gprow;           // [nsnps][8 + nvp*3]: gp0 | samples (gprow_kernel)
   DevBuf<double> d_entq, d_row0, d_singA, d_lb, d_p1, d_p1_0, d_l00, d_sing, d_dense;
+  DevBuf<double> d_terms;          // [E][RESC_FAST] log terms of the two-phase exact re-scorer
   DevBuf<double> d_ents;           // [E][2 + nd] per-entry factors of llk0s / llks00 (entq -> cell_scalars)
   DevBuf<float> d_entf_head, d_entf_plane;   // fp32 copies of the entry records (fp32 pair scan)
   double err3_256[256];
@@ -501,7 +502,7 @@ void dmx_destroy(dmx_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  c->d_ents.release(); c->d_entf_head.release(); c->d_entf_plane.release();
+  c->d_terms.release(); c->d_ents.release(); c->d_entf_head.release(); c->d_entf_plane.release();
   c->d_gp.release(); c->d_gprow.release(); c->d_entq.release(); c->d_row0.release(); c->d_singA.release();
   c->d_lb.release(); c->d_p1.release(); c->d_p1_0.release(); c->d_l00.release(); c->d_sing.release();
   c->d_dense.release(); c->d_cell_ptr.release(); c->d_ent_ptr.release(); c->d_ent_snp.release();
@@ -759,7 +760,10 @@ int dmx_compute(dmx_ctx* c) {
     for (int n = 0; n < nA; ++n) rp.dense_idx[n] = (int8_t)c->dense_idx[n];
     rp.gp = c->d_gprow.p + 8; rp.ent_snp = c->d_ent_snp.p; rp.entq = c->d_entq.p; rp.cell_ptr = c->d_cell_ptr.p;
     rp.cell_order = c->d_order.p; rp.lists = c->d_lists.p;
+    CU(c->d_terms.reserve((size_t)c->E * RESC_FAST + 1));
+    rp.terms = c->d_terms.p;
     CU(launch_rescore(rp, nact, c->stream));
+    if (nact) c->st.gpu_launches += 2;
   }
   c->st.gpu_launches += (c->nsnps ? 1 : 0) + (c->E ? 1 : 0) + (nact ? 2 : 0) + ((nact && dev_rescore) ? 1 : 0);
   CU(cudaEventRecord(c->ev[3], c->stream));

@@ -29,7 +29,9 @@ constexpr int FLUSH_STAGES = 16 / NB;   // exponent renormalisation period (stag
 // hypotheses for ONE of the NB entries of a stage (lane & 7 = entry, lane >> 3 = tile position inside the warp)
 constexpr int F_NCW = 9;       // consumer warps: 36 tile positions of the 64 x 64 upper triangle x 8 entry lanes
 constexpr int F_NTW = 4;       // transform warps: a lane = one entry slot x four samples
-constexpr int F_S_RAW = 6;     // stages of the raw ring
+constexpr int F_S_RAW = 8;     // stages of the raw ring
+constexpr int F_NLOAD = 2;     // loader warps (stages round-robin); F_S_RAW % F_NLOAD == 0 and F_S_RAW % F_NTW == 0 keep one
+                               // producer and one consumer warp per ring slot (mbarrier parity waits must not alias)
 constexpr int F_S_PROC = 8;    // stages of the processed ring
 constexpr int F_NTHREADS = (F_NCW + F_NTW + 1) * 32;   // 448
 constexpr int F_PEEL_STAGES = 4;   // underflow check period (stages = entries per thread)
@@ -134,6 +136,7 @@ struct ScanMaps {
 
 // exact re-scoring requests of one cell (built by merge_kernel, filled by rescore_kernel)
 constexpr int RMAX = 32;
+constexpr int RESC_FAST = 4;   // cells listing at most this many hypotheses take the two-phase re-scorer
 struct RescList {
   int32_t n;                   // hypotheses listed; -1: too many (the host scorer handles the cell)
   int32_t pad;
@@ -151,6 +154,7 @@ struct RescoreParams {
   const int64_t* cell_ptr;
   const int32_t* cell_order;
   RescList* lists;             // [ncells]
+  double* terms;               // [E][RESC_FAST] log(S) terms of the two-phase re-scorer (null: one warp per cell only)
 };
 
 struct MergeParams {

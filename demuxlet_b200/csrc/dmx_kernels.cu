@@ -29,6 +29,8 @@ namespace dmx {
 __constant__ double c_err[256];   // phred2Err, PhredHelper.cpp:30-32 (computed on the host with libm pow)
 __constant__ double c_err3[256];  // phred2Err / 3.0, the quotient the reference forms at :606-607 (host-computed)
 __constant__ double c_logtab[18 + 256];   // the host libm's __log_data (read from the loaded libm.so.6 at run time)
+__device__ double g_logtab[18 + 256];     // same table in global memory: the per-interval entries are indexed
+                                          // differently by every lane (a constant-bank access would serialise)
 
 // Bit-for-bit transcription of the x86-64 FMA build of glibc's log() (sysdeps/ieee754/dbl-64/e_log.c as
 // compiled into libm.so.6 2.3x: instruction sequence of __log_fma, table __log_data).  IEEE fma/mul/add are
@@ -76,7 +78,7 @@ __device__ __forceinline__ double glibc_log_fma(double x) {
   const int i = (int)((tmp >> 45) & 127);
   const int k = (int)((long long)tmp >> 52);
   const unsigned long long iz = ix - (tmp & 0xfff0000000000000ull);
-  const double invc = T[18 + 2 * i], logc = T[19 + 2 * i];
+  const double invc = __ldg(&g_logtab[18 + 2 * i]), logc = __ldg(&g_logtab[19 + 2 * i]);
   const double z = __longlong_as_double((long long)iz);
   const double kd = (double)k;
   const double w = __fma_rn(kd, T[0], logc);
@@ -104,7 +106,9 @@ int launch_logtest(const double* x, double* y, int64_t n, void* stream) {
   return (int)cudaGetLastError();
 }
 int set_log_table(const double* tab274) {
-  return (int)cudaMemcpyToSymbol(c_logtab, tab274, (18 + 256) * sizeof(double));
+  cudaError_t e = cudaMemcpyToSymbol(c_logtab, tab274, (18 + 256) * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_logtab, tab274, (18 + 256) * sizeof(double));
+  return (int)e;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -127,7 +131,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
+#ifdef DMX_TEST_WAIT
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#else
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#endif
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
@@ -790,10 +798,13 @@ __device__ __forceinline__ void bulk_g2s_elect(uint32_t dst, const void* src, ui
       : "memory");
 }
 
+// F_NLOAD loader warps share the stages round-robin (stage g belongs to loader g % F_NLOAD): one warp's issue path
+// (barrier wait, eight shuffles, expect_tx, two to four gather4 and two bulk copies, all from one elected lane) takes
+// about 900 cycles per stage even on an otherwise idle SM, more than the consumers need for the stage's arithmetic.
 __device__ __forceinline__ void loader_role_f32(const ScanParams& p, const ScanMaps& tm, const Pipe& pp, int lane, int u,
-                                                int NS) {
+                                                int NS, int lid) {
   const uint32_t raw0 = smem_u32(pp.raw_base), full0 = smem_u32(pp.raw_full);
-  uint32_t git = 0;
+  uint32_t gbase = 0;   // stages of the tasks before this one
   TaskInfo ti;
   for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
     const TaskType tt = p.tt[ti.tti];
@@ -801,21 +812,26 @@ __device__ __forceinline__ void loader_role_f32(const ScanParams& p, const ScanM
     const int colj = tt.j0 * 3, colk = tt.k0 * 3;
     const float* fplane = p.entf_plane + (int64_t)((tt.qoff - QHEAD) / QPLANE) * p.entf_pstride;
     const uint32_t bytes = (uint32_t)NB * (GROWJ + (same ? 0u : GROWK)) + (uint32_t)NB * (FHEAD + FPLANE) * 4u;
-    // SNP ids are fetched 32 entries (4 stages) at a time, one block ahead: the global-load latency of the ids must
-    // not sit on the per-stage critical path
-    int snp_cur = (ti.e0 + lane < ti.e1) ? __ldg(p.ent_snp + ti.e0 + lane) : 0;
-    int snp_nxt = (ti.e0 + 32 + lane < ti.e1) ? __ldg(p.ent_snp + ti.e0 + 32 + lane) : 0;
-    for (int it = 0; it < ti.nst; ++it, ++git) {
+    int it = (int)((F_NLOAD + lid - gbase % F_NLOAD) % F_NLOAD);   // first stage of this task that is ours
+    // SNP ids of a stage are fetched by lanes 0..7 one own stage ahead
+    int snp_nxt = 0;
+    if (it < ti.nst) {
+      const int64_t e = ti.e0 + (int64_t)it * NB + lane;
+      snp_nxt = (lane < NB && e < ti.e1) ? __ldg(p.ent_snp + e) : 0;
+    }
+    for (; it < ti.nst; it += F_NLOAD) {
+      const uint32_t git = gbase + (uint32_t)it;
       const uint32_t rslot = git % F_S_RAW;
       const uint32_t ph = (git / F_S_RAW) & 1u;
       const int64_t eb = ti.e0 + (int64_t)it * NB;
-      if (it && (it & 3) == 0) {
-        snp_cur = snp_nxt;
-        snp_nxt = (eb + 32 + lane < ti.e1) ? __ldg(p.ent_snp + eb + 32 + lane) : 0;
+      const int snp_cur = snp_nxt;
+      if (it + F_NLOAD < ti.nst) {
+        const int64_t e = eb + (int64_t)F_NLOAD * NB + lane;
+        snp_nxt = (lane < NB && e < ti.e1) ? __ldg(p.ent_snp + e) : 0;
       }
       int s[NB];
 #pragma unroll
-      for (int i = 0; i < NB; ++i) s[i] = __shfl_sync(0xffffffffu, snp_cur, (it & 3) * NB + i);
+      for (int i = 0; i < NB; ++i) s[i] = __shfl_sync(0xffffffffu, snp_cur, i);
       mbar_wait(&pp.raw_empty[rslot], ph ^ 1u);
       const uint32_t rs = raw0 + rslot * F_RAW_SLOT, bar = full0 + rslot * 8u;
       mbar_expect_tx_elect(bar, bytes);
@@ -829,17 +845,18 @@ __device__ __forceinline__ void loader_role_f32(const ScanParams& p, const ScanM
       bulk_g2s_elect(rs + F_OFF_FH, p.entf_head + eb * FHEAD, NB * FHEAD * 4, bar);
       bulk_g2s_elect(rs + F_OFF_FP, fplane + eb * FPLANE, NB * FPLANE * 4, bar);
     }
+    gbase += (uint32_t)ti.nst;
   }
 }
 
-// F_NTW = 4 transform warps.  A lane serves ONE entry slot of every stage (e = 2 * warp + lane / 16) and one
-// 4-sample block q = lane % 16 of each side, so everything moves as 16-byte vectors: the 12 floats of its samples'
-// GP rows (3 LDS.128, 48-byte lane stride: conflict free), the entry's fp32 record (5 LDS.128, two distinct
-// addresses per warp), and the (a, w) blocks of the processed ring (3 + 3 STS.128, conflict free by the
-// F_BLK4_FLT padding).  w_k[l] = sum_m Q'[l][m] gp_k[m] in fp32.  The per-sample extras (singlet factor of the
-// separable plane, row sums, pass 1) are fp32 running products per lane = per (entry slot, sample); a product is
-// peeled into an integer exponent only when it gets small (checked every F_PEEL_STAGES stages), and the eight entry
-// slots of a sample are multiplied together in fp64 at the end of the task: one log per sample and quantity.
+// F_NTW = 4 transform warps, each owning every fourth stage.  A lane serves one 4-sample block q = lane % 16 of each
+// side for the four entries e = lane / 16 + {0, 2, 4, 6} of its stage, so everything moves as 16-byte vectors: the 12
+// floats of its samples' GP rows (3 LDS.128, 48-byte lane stride: conflict free), the entry's fp32 record (5
+// LDS.128, two distinct addresses per warp), and the (a, w) blocks of the processed ring (3 + 3 STS.128, conflict
+// free by the F_BLK4_FLT padding).  w_k[l] = sum_m Q'[l][m] gp_k[m] in fp32.  The per-sample extras (singlet factor
+// of the separable plane, row sums, pass 1, pairs with sample 0) are fp32 running products per lane; a product is
+// peeled into an integer exponent only when it gets small (checked after every stage), and the partial products of a
+// sample (2 lanes x 4 warps) are multiplied together in fp64 at the end of the task: one log per sample and quantity.
 struct TScratch {
   double xm[2][F_NTW][4][BLK];       // [task parity][warp][PA, PB, P1, P0][sample]: mantissa products of the warp's slots
   int xe[2][F_NTW][4][BLK];          // ... and their exponent sums
@@ -945,26 +962,46 @@ __device__ __forceinline__ void peelf_unbiased(float& x, int& es) {
   }
 }
 
+// all four entries of a lane in one stage: e = ebase + 2 i (independent work, interleaved by the compiler)
+template <bool SAME, bool EXTRAS, int ROW0>
+__device__ __forceinline__ void transform_stage_f32(const unsigned char* __restrict__ rs, float* __restrict__ pf,
+                                                    int ebase, int q, int nvalid, bool jq, bool kq, float (&PA)[4],
+                                                    float (&PB)[4], float (&P1)[4], float (&P0)[4]) {
+#pragma unroll
+  for (int i = 0; i < NB / 2; ++i) {
+    const int e = ebase + 2 * i;
+    if (e < nvalid) {
+      transform_quad_f32<SAME, EXTRAS, ROW0>(rs, pf, e, q, jq, kq, PA, PB, P1, P0);
+    } else {   // identity entry: S = 1 for every hypothesis
+      store_neutral_quad(pf + q * F_BLK4_FLT + e * 12);
+      store_neutral_quad(pf + F_SIDE_FLT + q * F_BLK4_FLT + e * 12);
+    }
+  }
+}
+
+// Transform warp tw owns the stages g with g % F_NTW == tw (whole stages: the four warps work on four different
+// stages at a time, which hides the latency of a stage's dependent load -> FMA -> store chain).
 __device__ __forceinline__ void transform_role_f32(const ScanParams& p, const Pipe& pp, TScratch* ts, int tw, int lane,
                                                    int u, int NS) {
-  const int e = tw * 2 + (lane >> 4), q = lane & 15;
+  const int ebase = lane >> 4, q = lane & 15;
   const int tl = tw * 32 + lane;
-  uint32_t git = 0;
+  uint32_t gbase = 0;   // stages of the tasks before this one
   TaskInfo ti;
   for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
     const TaskType tt = p.tt[ti.tti];
     const bool same = tt.flags & TF_TRI;
-    const bool extras_t = (tt.flags & TF_EXTRAS) != 0;
+    const bool extras_t = (tt.flags & TF_EXTRAS) != 0 && !(p.dbg & 4);
     const bool jq = 4 * q < tt.nj;                                  // nj, nk are multiples of 4
     const bool kq = same ? jq : (4 * q < tt.nk);
     // pairs with sample 0: on the k side of symmetric tasks, on the j side of the (rectangular) tasks of full planes
-    const int row0 = !(tt.flags & TF_ROW0) ? 0 : ((tt.flags & TF_SYM) ? 1 : (same ? 0 : 2));
+    const int row0 = (!(tt.flags & TF_ROW0) || (p.dbg & 16)) ? 0 : ((tt.flags & TF_SYM) ? 1 : (same ? 0 : 2));
     const bool prods_t = extras_t || row0 != 0;
     float PA[4], PB[4], P1[4], P0[4];                 // running fp32 products (extras) of this lane's samples
     int eA[4], e1x[4], e0x[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) { PA[i] = PB[i] = P1[i] = P0[i] = 1.0f; eA[i] = e1x[i] = e0x[i] = 0; }
-    for (int it = 0; it < ti.nst; ++it, ++git) {
+    for (int it = (int)((F_NTW + tw - gbase % F_NTW) % F_NTW); it < ti.nst; it += F_NTW) {
+      const uint32_t git = gbase + (uint32_t)it;
       const int rslot = git % F_S_RAW, pslot = git % F_S_PROC;
       const uint32_t rph = (git / F_S_RAW) & 1u, pph = (git / F_S_PROC) & 1u;
       const int nvalid = (int)min((int64_t)NB, ti.e1 - (ti.e0 + (int64_t)it * NB));
@@ -973,32 +1010,27 @@ __device__ __forceinline__ void transform_role_f32(const ScanParams& p, const Pi
       const unsigned char* rs = pp.raw_base + (size_t)rslot * F_RAW_SLOT;
       float* pf = reinterpret_cast<float*>(pp.proc_base + (size_t)pslot * F_PROC_SLOT);
       if (p.dbg & 2) {
-      } else if (e < nvalid) {
-        if (same) {
-          if (extras_t) {
-            if (row0) transform_quad_f32<true, true, 1>(rs, pf, e, q, jq, kq, PA, PB, P1, P0);
-            else transform_quad_f32<true, true, 0>(rs, pf, e, q, jq, kq, PA, PB, P1, P0);
-          } else {
-            if (row0) transform_quad_f32<true, false, 1>(rs, pf, e, q, jq, kq, PA, PB, P1, P0);
-            else transform_quad_f32<true, false, 0>(rs, pf, e, q, jq, kq, PA, PB, P1, P0);
-          }
+      } else if (same) {
+        if (extras_t) {
+          if (row0) transform_stage_f32<true, true, 1>(rs, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
+          else transform_stage_f32<true, true, 0>(rs, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
         } else {
-          if (extras_t) {
-            if (row0 == 2) transform_quad_f32<false, true, 2>(rs, pf, e, q, jq, kq, PA, PB, P1, P0);
-            else if (row0 == 1) transform_quad_f32<false, true, 1>(rs, pf, e, q, jq, kq, PA, PB, P1, P0);
-            else transform_quad_f32<false, true, 0>(rs, pf, e, q, jq, kq, PA, PB, P1, P0);
-          } else {
-            if (row0 == 2) transform_quad_f32<false, false, 2>(rs, pf, e, q, jq, kq, PA, PB, P1, P0);
-            else if (row0 == 1) transform_quad_f32<false, false, 1>(rs, pf, e, q, jq, kq, PA, PB, P1, P0);
-            else transform_quad_f32<false, false, 0>(rs, pf, e, q, jq, kq, PA, PB, P1, P0);
-          }
+          if (row0) transform_stage_f32<true, false, 1>(rs, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
+          else transform_stage_f32<true, false, 0>(rs, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
         }
-      } else {   // identity entry: S = 1 for every hypothesis
-        store_neutral_quad(pf + q * F_BLK4_FLT + e * 12);
-        store_neutral_quad(pf + F_SIDE_FLT + q * F_BLK4_FLT + e * 12);
+      } else {
+        if (extras_t) {
+          if (row0 == 2) transform_stage_f32<false, true, 2>(rs, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
+          else if (row0 == 1) transform_stage_f32<false, true, 1>(rs, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
+          else transform_stage_f32<false, true, 0>(rs, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
+        } else {
+          if (row0 == 2) transform_stage_f32<false, false, 2>(rs, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
+          else if (row0 == 1) transform_stage_f32<false, false, 1>(rs, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
+          else transform_stage_f32<false, false, 0>(rs, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
+        }
       }
-      if (prods_t && (it % F_PEEL_STAGES) == F_PEEL_STAGES - 1) {
-        // every factor is >= ~1e-6 (the +1e-6 floors of :446-452 and :643-663), so F_PEEL_STAGES more of them keep a
+      if (prods_t) {
+        // every factor is >= ~1e-6 (the +1e-6 floors of :446-452 and :643-663), so the four of the next stage keep a
         // product that is above 2^-46 now inside the fp32 range; exact zeros (padding samples) are left alone
         float mn = 1.0f;
 #pragma unroll
@@ -1020,6 +1052,7 @@ __device__ __forceinline__ void transform_role_f32(const ScanParams& p, const Pi
         mbar_arrive(&pp.raw_empty[rslot]);
       }
     }
+    gbase += (uint32_t)ti.nst;
     if (!prods_t) continue;   // uniform over the transform warps
     const int buf = r & 1;
     // fold the two entry slots of this warp (lanes 16 apart), then the four warps through shared memory
@@ -1351,9 +1384,9 @@ __device__ __forceinline__ void tile_math(const float (&a)[8][3], const float (&
 // ---------------------------------------------------------------------------------------------
 // fp32 pair scan: one task pipeline per CTA, 16 warps in four warpgroups.  SM sub-partition = warp id % 4; roles are
 // placed so that the issue load of the four sub-partitions is even (C = consumer, D = consumer of diagonal tiles:
-// 36 / 64 of the work, T = transform, L = loader, - = exits at once):
+// 36 / 64 of the work, T = transform, L = loader):
 //   wid   0  1  2  3 |  4  5  6  7 |  8  9 10 11 | 12 13 14 15
-//         D  C  C  C |  D  C  C  C |  C  T  T  T |  T  L  -  -
+//         D  C  C  C |  D  C  C  C |  C  T  T  T |  T  L  L  L
 // The last warpgroup gives registers back (setmaxnreg) so that the consumers' 64 accumulators + 48 operands fit.
 //
 // A consumer thread owns the 8 x 8 tile (bj, bk) of hypotheses for the entries e = lane & 7 of every stage: per
@@ -1367,6 +1400,7 @@ __device__ __forceinline__ void tile_math(const float (&a)[8][3], const float (&
 // multiply their products together (fp64 reduce-scatter: lane e ends up with tile row e).
 // ---------------------------------------------------------------------------------------------
 constexpr int F_LAUNCH_THREADS = 512;
+static_assert(F_S_RAW % F_NLOAD == 0 && F_S_RAW % F_NTW == 0 && F_S_PROC % F_NTW == 0 && F_NLOAD <= 3, "ring ownership");
 constexpr int F_REGS_HI = 136, F_REGS_LO = 104;   // (3 * 136 + 104) * 32 = 16384 registers per sub-partition
 
 __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_f32_kernel(const __grid_constant__ ScanParams p,
@@ -1386,10 +1420,10 @@ __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_f32_kernel(cons
   if (threadIdx.x == 0) {
     for (int s = 0; s < F_S_RAW; ++s) {
       mbar_init(&pp.raw_full[s], 1);
-      mbar_init(&pp.raw_empty[s], F_NTW);
+      mbar_init(&pp.raw_empty[s], 1);
     }
     for (int s = 0; s < F_S_PROC; ++s) {
-      mbar_init(&pp.proc_full[s], F_NTW);
+      mbar_init(&pp.proc_full[s], 1);
       mbar_init(&pp.proc_empty[s], F_NCW);
     }
     scr->ncand = 0;
@@ -1402,7 +1436,7 @@ __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_f32_kernel(cons
   if (warp >= 12) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(F_REGS_LO));
     if (warp == 12) transform_role_f32(p, pp, ts, F_NTW - 1, lane, u, NS);
-    else if (warp == 13) loader_role_f32(p, tm, pp, lane, u, NS);
+    else if (warp - 13 < F_NLOAD) loader_role_f32(p, tm, pp, lane, u, NS, warp - 13);
     return;
   }
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(F_REGS_HI));
@@ -1686,9 +1720,83 @@ int launch_fill_sep_dense(const ScanParams& p, int64_t nactive, void* stream) {
 // ---------------------------------------------------------------------------------------------
 // rescore: the listed hypotheses of every cell in the reference's exact arithmetic
 // (cmd_cram_demuxlet.cpp:671-684: gpAB product, (l,m) row-major sum, log, SNP-ascending accumulation).
-// One warp per cell: lanes take 32 consecutive entries and evaluate log(S) for every listed hypothesis,
-// then lane h adds column h in entry order.
+// Two phases for cells with at most RESC_FAST hypotheses (the common case: the two orders of the best pair):
+//   rescore_terms_kernel  one block per cell, one thread per entry: log(S) of every listed hypothesis -> terms[e][h]
+//   rescore_sum_kernel    one thread per (cell, hypothesis): the sequential sum in entry order (the chain of
+//                         dependent adds the reference's accumulation order demands), loads batched ahead of it
+// rescore_kernel (one warp per cell, any list length up to RMAX) handles the other cells.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double exact_term(const float* __restrict__ g, const double* __restrict__ q, uint32_t hy,
+                                             const int8_t* dense_idx) {
+  const int j = hy & 0xfff, k = (hy >> 12) & 0xfff, n = hy >> 24;
+  const double gj0 = (double)__ldg(g + 3 * j), gj1 = (double)__ldg(g + 3 * j + 1), gj2 = (double)__ldg(g + 3 * j + 2);
+  const double gk0 = (double)__ldg(g + 3 * k), gk1 = (double)__ldg(g + 3 * k + 1), gk2 = (double)__ldg(g + 3 * k + 2);
+  double Q[9];
+  if (dense_idx[n] < 0) {   // separable plane 0: Q'[0][l][m] = f[l]
+#pragma unroll
+    for (int l = 0; l < 3; ++l) Q[l * 3] = Q[l * 3 + 1] = Q[l * 3 + 2] = q[3 + l];
+  } else {
+    const double* qp = q + QHEAD + QPLANE * dense_idx[n];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Q[i] = qp[i];
+  }
+  double s = 0.0;
+  s = __dadd_rn(s, __dmul_rn(__dmul_rn(gj0, gk0), Q[0]));
+  s = __dadd_rn(s, __dmul_rn(__dmul_rn(gj0, gk1), Q[1]));
+  s = __dadd_rn(s, __dmul_rn(__dmul_rn(gj0, gk2), Q[2]));
+  s = __dadd_rn(s, __dmul_rn(__dmul_rn(gj1, gk0), Q[3]));
+  s = __dadd_rn(s, __dmul_rn(__dmul_rn(gj1, gk1), Q[4]));
+  s = __dadd_rn(s, __dmul_rn(__dmul_rn(gj1, gk2), Q[5]));
+  s = __dadd_rn(s, __dmul_rn(__dmul_rn(gj2, gk0), Q[6]));
+  s = __dadd_rn(s, __dmul_rn(__dmul_rn(gj2, gk1), Q[7]));
+  s = __dadd_rn(s, __dmul_rn(__dmul_rn(gj2, gk2), Q[8]));
+  return glibc_log_fma(s);
+}
+
+__global__ void __launch_bounds__(128) rescore_terms_kernel(const __grid_constant__ RescoreParams p, int64_t nactive) {
+  const int cell = p.cell_order[blockIdx.x];
+  const RescList* L = p.lists + cell;
+  const int H = L->n;
+  if (H <= 0 || H > RESC_FAST) return;
+  uint32_t hyp[RESC_FAST];
+#pragma unroll
+  for (int h = 0; h < RESC_FAST; ++h) hyp[h] = h < H ? L->hyp[h] : 0u;
+  const int64_t e0 = p.cell_ptr[cell], e1 = p.cell_ptr[cell + 1];
+  for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+    const float* g = p.gp + (int64_t)__ldg(p.ent_snp + e) * p.gp_stride;
+    const double* q = p.entq + e * p.UQ;
+#pragma unroll
+    for (int h = 0; h < RESC_FAST; ++h)
+      if (h < H) p.terms[e * RESC_FAST + h] = exact_term(g, q, hyp[h], p.dense_idx);
+  }
+}
+
+__global__ void __launch_bounds__(128) rescore_sum_kernel(const __grid_constant__ RescoreParams p, int64_t nactive) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t aidx = t / RESC_FAST;
+  const int h = (int)(t % RESC_FAST);
+  if (aidx >= nactive) return;
+  const int cell = p.cell_order[aidx];
+  RescList* L = p.lists + cell;
+  const int H = L->n;
+  if (H <= 0 || H > RESC_FAST || h >= H) return;
+  const int64_t e0 = p.cell_ptr[cell], e1 = p.cell_ptr[cell + 1];
+  const double* x = p.terms + e0 * RESC_FAST + h;
+  double acc = 0.0;
+  int64_t n = e1 - e0, i = 0;
+  for (; i + 8 <= n; i += 8) {
+    double v[8];
+#pragma unroll
+    for (int u2 = 0; u2 < 8; ++u2) v[u2] = __ldcg(x + (i + u2) * RESC_FAST);
+#pragma unroll
+    for (int u2 = 0; u2 < 8; ++u2) acc = __dadd_rn(acc, v[u2]);
+  }
+  for (; i < n; ++i) acc = __dadd_rn(acc, __ldcg(x + i * RESC_FAST));
+  L->val[h] = acc;
+}
+
+// One warp per cell: lanes take 32 consecutive entries and evaluate log(S) for every listed hypothesis, then lane h
+// adds column h in entry order.
 constexpr int RESC_WARPS = 4;
 __global__ void __launch_bounds__(RESC_WARPS * 32) rescore_kernel(const __grid_constant__ RescoreParams p,
                                                                    int64_t nactive) {
@@ -1699,7 +1807,7 @@ __global__ void __launch_bounds__(RESC_WARPS * 32) rescore_kernel(const __grid_c
   const int cell = p.cell_order[aidx];
   RescList* L = p.lists + cell;
   const int H = L->n;
-  if (H <= 0) return;
+  if (H <= 0 || (p.terms && H <= RESC_FAST)) return;
   const uint32_t myh = lane < H ? L->hyp[lane] : 0u;
   double acc = 0.0;
   const int64_t e0 = p.cell_ptr[cell], e1 = p.cell_ptr[cell + 1];
@@ -1715,31 +1823,7 @@ __global__ void __launch_bounds__(RESC_WARPS * 32) rescore_kernel(const __grid_c
     }
     for (int h = 0; h < H; ++h) {
       const uint32_t hy = __shfl_sync(0xffffffffu, myh, h);
-      if (valid) {
-        const int j = hy & 0xfff, k = (hy >> 12) & 0xfff, n = hy >> 24;
-        const double gj0 = (double)__ldg(g + 3 * j), gj1 = (double)__ldg(g + 3 * j + 1), gj2 = (double)__ldg(g + 3 * j + 2);
-        const double gk0 = (double)__ldg(g + 3 * k), gk1 = (double)__ldg(g + 3 * k + 1), gk2 = (double)__ldg(g + 3 * k + 2);
-        double Q[9];
-        if (p.dense_idx[n] < 0) {   // separable plane 0: Q'[0][l][m] = f[l]
-#pragma unroll
-          for (int l = 0; l < 3; ++l) Q[l * 3] = Q[l * 3 + 1] = Q[l * 3 + 2] = q[3 + l];
-        } else {
-          const double* qp = q + QHEAD + QPLANE * p.dense_idx[n];
-#pragma unroll
-          for (int i = 0; i < 9; ++i) Q[i] = qp[i];
-        }
-        double s = 0.0;
-        s = __dadd_rn(s, __dmul_rn(__dmul_rn(gj0, gk0), Q[0]));
-        s = __dadd_rn(s, __dmul_rn(__dmul_rn(gj0, gk1), Q[1]));
-        s = __dadd_rn(s, __dmul_rn(__dmul_rn(gj0, gk2), Q[2]));
-        s = __dadd_rn(s, __dmul_rn(__dmul_rn(gj1, gk0), Q[3]));
-        s = __dadd_rn(s, __dmul_rn(__dmul_rn(gj1, gk1), Q[4]));
-        s = __dadd_rn(s, __dmul_rn(__dmul_rn(gj1, gk2), Q[5]));
-        s = __dadd_rn(s, __dmul_rn(__dmul_rn(gj2, gk0), Q[6]));
-        s = __dadd_rn(s, __dmul_rn(__dmul_rn(gj2, gk1), Q[7]));
-        s = __dadd_rn(s, __dmul_rn(__dmul_rn(gj2, gk2), Q[8]));
-        logs[warp][lane][h] = glibc_log_fma(s);
-      }
+      if (valid) logs[warp][lane][h] = exact_term(g, q, hy, p.dense_idx);
     }
     __syncwarp();
     if (lane < H)
@@ -1751,7 +1835,12 @@ __global__ void __launch_bounds__(RESC_WARPS * 32) rescore_kernel(const __grid_c
 
 int launch_rescore(const RescoreParams& p, int64_t nactive, void* stream) {
   if (nactive == 0) return 0;
-  rescore_kernel<<<(unsigned)((nactive + RESC_WARPS - 1) / RESC_WARPS), RESC_WARPS * 32, 0, (cudaStream_t)stream>>>(p, nactive);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p.terms) {
+    rescore_terms_kernel<<<(unsigned)nactive, 128, 0, st>>>(p, nactive);
+    rescore_sum_kernel<<<(unsigned)((nactive * RESC_FAST + 127) / 128), 128, 0, st>>>(p, nactive);
+  }
+  rescore_kernel<<<(unsigned)((nactive + RESC_WARPS - 1) / RESC_WARPS), RESC_WARPS * 32, 0, st>>>(p, nactive);
   return (int)cudaGetLastError();
 }
 
