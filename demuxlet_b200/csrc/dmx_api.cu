@@ -763,7 +763,7 @@ int dmx_compute(dmx_ctx* c) {
     CU(c->d_terms.reserve((size_t)c->E * RESC_FAST + 1));
     rp.terms = c->d_terms.p;
     CU(launch_rescore(rp, nact, c->stream));
-    if (nact) c->st.gpu_launches += 2;
+    if (nact) c->st.gpu_launches += 2 * (RMAX / RESC_FAST) - 1;
   }
   c->st.gpu_launches += (c->nsnps ? 1 : 0) + (c->E ? 1 : 0) + (nact ? 2 : 0) + ((nact && dev_rescore) ? 1 : 0);
   CU(cudaEventRecord(c->ev[3], c->stream));

@@ -136,7 +136,7 @@ struct ScanMaps {
 
 // exact re-scoring requests of one cell (built by merge_kernel, filled by rescore_kernel)
 constexpr int RMAX = 32;
-constexpr int RESC_FAST = 4;   // cells listing at most this many hypotheses take the two-phase re-scorer
+constexpr int RESC_FAST = 8;   // hypotheses per cell and pass of the two-phase re-scorer
 struct RescList {
   int32_t n;                   // hypotheses listed; -1: too many (the host scorer handles the cell)
   int32_t pad;
@@ -154,7 +154,7 @@ struct RescoreParams {
   const int64_t* cell_ptr;
   const int32_t* cell_order;
   RescList* lists;             // [ncells]
-  double* terms;               // [E][RESC_FAST] log(S) terms of the two-phase re-scorer (null: one warp per cell only)
+  double* terms;               // per cell [RESC_FAST][entries] log(S) terms, cell block at e0 * RESC_FAST
 };
 
 struct MergeParams {

@@ -1720,11 +1720,10 @@ int launch_fill_sep_dense(const ScanParams& p, int64_t nactive, void* stream) {
 // ---------------------------------------------------------------------------------------------
 // rescore: the listed hypotheses of every cell in the reference's exact arithmetic
 // (cmd_cram_demuxlet.cpp:671-684: gpAB product, (l,m) row-major sum, log, SNP-ascending accumulation).
-// Two phases for cells with at most RESC_FAST hypotheses (the common case: the two orders of the best pair):
-//   rescore_terms_kernel  one block per cell, one thread per entry: log(S) of every listed hypothesis -> terms[e][h]
+// Two phases, RESC_FAST hypotheses of every cell per pass (the common list is the two orders of the best pair):
+//   rescore_terms_kernel  one block per cell, threads over its entries: log(S) of the listed hypotheses -> terms
 //   rescore_sum_kernel    one thread per (cell, hypothesis): the sequential sum in entry order (the chain of
-//                         dependent adds the reference's accumulation order demands), loads batched ahead of it
-// rescore_kernel (one warp per cell, any list length up to RMAX) handles the other cells.
+//                         dependent adds the reference's accumulation order demands), loads a batch ahead of it
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double exact_term(const float* __restrict__ g, const double* __restrict__ q, uint32_t hy,
                                              const int8_t* dense_idx) {
@@ -1753,94 +1752,69 @@ __device__ __forceinline__ double exact_term(const float* __restrict__ g, const 
   return glibc_log_fma(s);
 }
 
-__global__ void __launch_bounds__(128) rescore_terms_kernel(const __grid_constant__ RescoreParams p, int64_t nactive) {
+__global__ void __launch_bounds__(256) rescore_terms_kernel(const __grid_constant__ RescoreParams p, int64_t nactive,
+                                                            int pass) {
   const int cell = p.cell_order[blockIdx.x];
   const RescList* L = p.lists + cell;
-  const int H = L->n;
-  if (H <= 0 || H > RESC_FAST) return;
+  const int H = min(L->n - pass * RESC_FAST, RESC_FAST);   // hypotheses of this pass
+  if (H <= 0) return;
   uint32_t hyp[RESC_FAST];
 #pragma unroll
-  for (int h = 0; h < RESC_FAST; ++h) hyp[h] = h < H ? L->hyp[h] : 0u;
-  const int64_t e0 = p.cell_ptr[cell], e1 = p.cell_ptr[cell + 1];
-  for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+  for (int h = 0; h < RESC_FAST; ++h) hyp[h] = h < H ? L->hyp[pass * RESC_FAST + h] : 0u;
+  const int64_t e0 = p.cell_ptr[cell], n = p.cell_ptr[cell + 1] - e0;
+  double* out = p.terms + e0 * RESC_FAST;                  // this cell's block: [h][entry]
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const int64_t e = e0 + i;
     const float* g = p.gp + (int64_t)__ldg(p.ent_snp + e) * p.gp_stride;
     const double* q = p.entq + e * p.UQ;
 #pragma unroll
     for (int h = 0; h < RESC_FAST; ++h)
-      if (h < H) p.terms[e * RESC_FAST + h] = exact_term(g, q, hyp[h], p.dense_idx);
+      if (h < H) out[h * n + i] = exact_term(g, q, hyp[h], p.dense_idx);
   }
 }
 
-__global__ void __launch_bounds__(128) rescore_sum_kernel(const __grid_constant__ RescoreParams p, int64_t nactive) {
+__global__ void __launch_bounds__(128) rescore_sum_kernel(const __grid_constant__ RescoreParams p, int64_t nactive,
+                                                          int pass) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t aidx = t / RESC_FAST;
   const int h = (int)(t % RESC_FAST);
   if (aidx >= nactive) return;
   const int cell = p.cell_order[aidx];
   RescList* L = p.lists + cell;
-  const int H = L->n;
-  if (H <= 0 || H > RESC_FAST || h >= H) return;
-  const int64_t e0 = p.cell_ptr[cell], e1 = p.cell_ptr[cell + 1];
-  const double* x = p.terms + e0 * RESC_FAST + h;
-  double acc = 0.0;
-  int64_t n = e1 - e0, i = 0;
-  for (; i + 8 <= n; i += 8) {
-    double v[8];
+  if (L->n < 0 || pass * RESC_FAST + h >= L->n) return;
+  const int64_t e0 = p.cell_ptr[cell], n = p.cell_ptr[cell + 1] - e0;
+  const double* x = p.terms + e0 * RESC_FAST + h * n;
+  // the additions form one dependent chain in entry order; the loads run a batch ahead of it
+  constexpr int B = 16;
+  double cur[B], nxt[B];
 #pragma unroll
-    for (int u2 = 0; u2 < 8; ++u2) v[u2] = __ldcg(x + (i + u2) * RESC_FAST);
-#pragma unroll
-    for (int u2 = 0; u2 < 8; ++u2) acc = __dadd_rn(acc, v[u2]);
-  }
-  for (; i < n; ++i) acc = __dadd_rn(acc, __ldcg(x + i * RESC_FAST));
-  L->val[h] = acc;
-}
-
-// One warp per cell: lanes take 32 consecutive entries and evaluate log(S) for every listed hypothesis, then lane h
-// adds column h in entry order.
-constexpr int RESC_WARPS = 4;
-__global__ void __launch_bounds__(RESC_WARPS * 32) rescore_kernel(const __grid_constant__ RescoreParams p,
-                                                                   int64_t nactive) {
-  __shared__ double logs[RESC_WARPS][32][RMAX + 1];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t aidx = (int64_t)blockIdx.x * RESC_WARPS + warp;
-  if (aidx >= nactive) return;
-  const int cell = p.cell_order[aidx];
-  RescList* L = p.lists + cell;
-  const int H = L->n;
-  if (H <= 0 || (p.terms && H <= RESC_FAST)) return;
-  const uint32_t myh = lane < H ? L->hyp[lane] : 0u;
+  for (int u2 = 0; u2 < B; ++u2) cur[u2] = u2 < n ? __ldcg(x + u2) : 0.0;
   double acc = 0.0;
-  const int64_t e0 = p.cell_ptr[cell], e1 = p.cell_ptr[cell + 1];
-  for (int64_t base = e0; base < e1; base += 32) {
-    const int64_t e = base + lane;
-    const int cnt = (int)min((int64_t)32, e1 - base);
-    const bool valid = lane < cnt;
-    const float* g = p.gp;
-    const double* q = p.entq;
-    if (valid) {
-      g += (int64_t)__ldg(p.ent_snp + e) * p.gp_stride;
-      q += e * p.UQ;
+  for (int64_t i = 0; i < n; i += B) {
+#pragma unroll
+    for (int u2 = 0; u2 < B; ++u2) nxt[u2] = (i + B + u2 < n) ? __ldcg(x + i + B + u2) : 0.0;
+    if (i + B <= n) {
+#pragma unroll
+      for (int u2 = 0; u2 < B; ++u2) acc = __dadd_rn(acc, cur[u2]);
+    } else {
+#pragma unroll
+      for (int u2 = 0; u2 < B; ++u2)
+        if (i + u2 < n) acc = __dadd_rn(acc, cur[u2]);
     }
-    for (int h = 0; h < H; ++h) {
-      const uint32_t hy = __shfl_sync(0xffffffffu, myh, h);
-      if (valid) logs[warp][lane][h] = exact_term(g, q, hy, p.dense_idx);
-    }
-    __syncwarp();
-    if (lane < H)
-      for (int i = 0; i < cnt; ++i) acc = __dadd_rn(acc, logs[warp][i][lane]);
-    __syncwarp();
+#pragma unroll
+    for (int u2 = 0; u2 < B; ++u2) cur[u2] = nxt[u2];
   }
-  if (lane < H) L->val[lane] = acc;
+  L->val[pass * RESC_FAST + h] = acc;
 }
 
 int launch_rescore(const RescoreParams& p, int64_t nactive, void* stream) {
   if (nactive == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (p.terms) {
-    rescore_terms_kernel<<<(unsigned)nactive, 128, 0, st>>>(p, nactive);
-    rescore_sum_kernel<<<(unsigned)((nactive * RESC_FAST + 127) / 128), 128, 0, st>>>(p, nactive);
+  // lists longer than RESC_FAST take further passes over the same terms buffer (their blocks exit at once otherwise)
+  for (int pass = 0; pass * RESC_FAST < RMAX; ++pass) {
+    rescore_terms_kernel<<<(unsigned)nactive, 256, 0, st>>>(p, nactive, pass);
+    rescore_sum_kernel<<<(unsigned)((nactive * RESC_FAST + 127) / 128), 128, 0, st>>>(p, nactive, pass);
   }
-  rescore_kernel<<<(unsigned)((nactive + RESC_WARPS - 1) / RESC_WARPS), RESC_WARPS * 32, 0, st>>>(p, nactive);
   return (int)cudaGetLastError();
 }
 
