@@ -346,6 +346,9 @@ void fill_scan_params(dmx_ctx* c, ScanParams* p) {
     p->dbgbuf = c->d_dbg.p;
   }
   p->gp = c->d_gprow.p + 8; p->ent_snp = c->d_ent_snp.p; p->entq = c->d_entq.p;
+  p->has_rect = 0;
+  for (const TaskType& t : c->tt)
+    if (!(t.flags & TF_TRI)) p->has_rect = 1;
   p->entf_head = c->d_entf_head.p; p->entf_plane = c->d_entf_plane.p; p->entf_pstride = (c->E + NB) * FPLANE;
   p->cell_ptr = c->d_cell_ptr.p; p->cell_order = c->d_order.p; p->tt = c->d_tt.p; p->parts = c->d_parts.p;
   p->row0 = c->d_row0.p; p->singA = c->d_singA.p; p->lb = c->d_lb.p; p->p1 = c->d_p1.p;

@@ -28,12 +28,13 @@ constexpr int FLUSH_STAGES = 16 / NB;   // exponent renormalisation period (stag
 // fp32 pair scan (pair_scan_f32_kernel): one task pipeline per CTA; a consumer thread owns an 8 x 8 tile of
 // hypotheses for ONE of the NB entries of a stage (lane & 7 = entry, lane >> 3 = tile position inside the warp)
 constexpr int F_NCW = 9;       // consumer warps: 36 tile positions of the 64 x 64 upper triangle x 8 entry lanes
-constexpr int F_NTW = 4;       // transform warps: a lane = one entry slot x four samples
-constexpr int F_S_RAW = 8;     // stages of the raw ring
-constexpr int F_NLOAD = 2;     // loader warps (stages round-robin); F_S_RAW % F_NLOAD == 0 and F_S_RAW % F_NTW == 0 keep one
+#ifndef DMX_F_NTW
+#define DMX_F_NTW 4
+#endif
+constexpr int F_NTW = DMX_F_NTW;   // transform warps (whole stages, taken dynamically)
+constexpr int F_NLOAD = 2;     // loader warps (stages round-robin); the raw ring sizes are multiples of it, which keeps one
                                // producer and one consumer warp per ring slot (mbarrier parity waits must not alias)
 constexpr int F_S_PROC = 8;    // stages of the processed ring
-constexpr int F_NTHREADS = (F_NCW + F_NTW + 1) * 32;   // 448
 constexpr int F_PEEL_STAGES = 4;   // underflow check period (stages = entries per thread)
 constexpr int FHEAD = 8;       // floats per entry in the fp32 head table: GL[3], f[3] (separable plane), 2 pad
 constexpr int FPLANE = 12;     // floats per entry and dense plane in the fp32 plane tables: Q'[3][3], 3 pad
@@ -111,6 +112,8 @@ struct ScanParams {
   const float* entf_head;      // [E][FHEAD] fp32 copy of the record heads (fp32 pair scan)
   const float* entf_plane;     // [nd][entf_pstride] fp32 copies of the dense planes, FPLANE floats per entry
   int64_t entf_pstride;        // floats between consecutive planes
+  int32_t has_rect;            // the task list has rectangular tasks (k-side rows needed)
+  int32_t f_sraw, f_rawslot, f_off_fh;   // fp32 scan raw ring geometry (filled in by launch_pair_scan)
   const int64_t* cell_ptr;     // [ncells+1]
   const int32_t* cell_order;   // [nactive] cell ids, scheduled order
   const TaskType* tt;          // [T]

@@ -131,11 +131,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-#ifdef DMX_TEST_WAIT
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-#else
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-#endif
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 2000;\n\t"   // suspend-time hint (ns): fewer retry issues
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
@@ -538,9 +534,9 @@ constexpr uint32_t F_BLK4_FLT = NB * 12 + 12;                        // 108 floa
 constexpr uint32_t F_SIDE_FLT = (BLK / 4) * F_BLK4_FLT;              // 1728 floats
 constexpr uint32_t F_PROC_SLOT = 2 * F_SIDE_FLT * 4;                 // 13824 B
 static_assert(F_PROC_SLOT % 128 == 0 && NB == 8, "fp32 scan geometry");
-static_assert(2 * F_S_RAW + 2 * F_S_PROC <= 32 && 2 * S_RAW + 2 * S_PROC <= 32, "barriers must fit below the scratch area");
+static_assert(2 * 12 + 2 * F_S_PROC <= 64 && 2 * S_RAW + 2 * S_PROC <= 64, "barriers must fit below the scratch area");
 
-constexpr uint32_t SCRATCH_OFF = 256;   // barriers live below
+constexpr uint32_t SCRATCH_OFF = 512;   // barriers live below
 struct Scratch {                     // at slot offset SCRATCH_OFF
   double red[2][16];
   double red2[16];
@@ -781,13 +777,19 @@ __device__ __forceinline__ void transform_role(const ScanParams& p, const Pipe& 
 // =============================== fp32 pair scan: loader and transform ==============================
 // Raw stage of the fp32 scan: the gathered GP rows as in the fp64 scan, then the fp32 record heads and the task's
 // fp32 plane of the NB consecutive entries (two contiguous 1-D bulk copies: the tables are entry-major).
+// The k-side rows exist only when the task list has rectangular tasks (nv > 64 or a non-symmetric plane); without
+// them a stage is 7040 B instead of 10368 B and the same shared memory holds 12 raw stages instead of 8
+// (ScanParams::f_sraw / f_rawslot / f_off_fh, set by launch_pair_scan).
 constexpr uint32_t F_OFF_GPJ = 0;
 constexpr uint32_t F_OFF_GPK = F_OFF_GPJ + NB * GROWJ;
-constexpr uint32_t F_OFF_FH = F_OFF_GPK + NB * GROWK;
-constexpr uint32_t F_OFF_FP = F_OFF_FH + NB * FHEAD * 4;
-constexpr uint32_t F_RAW_SLOT = F_OFF_FP + NB * FPLANE * 4;   // 10368 B
-static_assert(F_OFF_GPK % 128 == 0 && F_OFF_FH % 128 == 0 && F_RAW_SLOT % 128 == 0 && (F_OFF_FP % 16) == 0, "alignment");
-constexpr uint32_t F_SMEM_NOTS = SLOT_CTRL + F_S_RAW * F_RAW_SLOT + F_S_PROC * F_PROC_SLOT;   // + TScratch
+constexpr uint32_t F_REC_BYTES = NB * (FHEAD + FPLANE) * 4;                    // 640
+constexpr uint32_t F_RAW_SLOT_RECT = F_OFF_GPK + NB * GROWK + F_REC_BYTES;     // 10368 B
+constexpr uint32_t F_RAW_SLOT_TRI = F_OFF_GPK + F_REC_BYTES;                   // 7040 B
+constexpr uint32_t F_S_RAW_RECT = 8, F_S_RAW_TRI = 12;
+constexpr uint32_t F_RAW_BYTES = F_S_RAW_TRI * F_RAW_SLOT_TRI;                 // 84480 B
+static_assert(F_OFF_GPK % 128 == 0 && F_RAW_SLOT_RECT % 128 == 0 && F_RAW_SLOT_TRI % 128 == 0 &&
+              F_S_RAW_RECT * F_RAW_SLOT_RECT <= F_RAW_BYTES && F_S_RAW_TRI <= 12, "raw ring layout");
+constexpr uint32_t F_SMEM_NOTS = SLOT_CTRL + F_RAW_BYTES + F_S_PROC * F_PROC_SLOT;   // + TScratch
 
 __device__ __forceinline__ void bulk_g2s_elect(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile(
@@ -804,6 +806,7 @@ __device__ __forceinline__ void bulk_g2s_elect(uint32_t dst, const void* src, ui
 __device__ __forceinline__ void loader_role_f32(const ScanParams& p, const ScanMaps& tm, const Pipe& pp, int lane, int u,
                                                 int NS, int lid) {
   const uint32_t raw0 = smem_u32(pp.raw_base), full0 = smem_u32(pp.raw_full);
+  const uint32_t sraw = (uint32_t)p.f_sraw, rawslot = (uint32_t)p.f_rawslot, off_fh = (uint32_t)p.f_off_fh;
   uint32_t gbase = 0;   // stages of the tasks before this one
   TaskInfo ti;
   for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
@@ -811,7 +814,7 @@ __device__ __forceinline__ void loader_role_f32(const ScanParams& p, const ScanM
     const bool same = tt.flags & TF_TRI;
     const int colj = tt.j0 * 3, colk = tt.k0 * 3;
     const float* fplane = p.entf_plane + (int64_t)((tt.qoff - QHEAD) / QPLANE) * p.entf_pstride;
-    const uint32_t bytes = (uint32_t)NB * (GROWJ + (same ? 0u : GROWK)) + (uint32_t)NB * (FHEAD + FPLANE) * 4u;
+    const uint32_t bytes = (uint32_t)NB * (GROWJ + (same ? 0u : GROWK)) + F_REC_BYTES;
     int it = (int)((F_NLOAD + lid - gbase % F_NLOAD) % F_NLOAD);   // first stage of this task that is ours
     // SNP ids of a stage are fetched by lanes 0..7 one own stage ahead
     int snp_nxt = 0;
@@ -821,8 +824,8 @@ __device__ __forceinline__ void loader_role_f32(const ScanParams& p, const ScanM
     }
     for (; it < ti.nst; it += F_NLOAD) {
       const uint32_t git = gbase + (uint32_t)it;
-      const uint32_t rslot = git % F_S_RAW;
-      const uint32_t ph = (git / F_S_RAW) & 1u;
+      const uint32_t rslot = git % sraw;
+      const uint32_t ph = (git / sraw) & 1u;
       const int64_t eb = ti.e0 + (int64_t)it * NB;
       const int snp_cur = snp_nxt;
       if (it + F_NLOAD < ti.nst) {
@@ -833,7 +836,7 @@ __device__ __forceinline__ void loader_role_f32(const ScanParams& p, const ScanM
 #pragma unroll
       for (int i = 0; i < NB; ++i) s[i] = __shfl_sync(0xffffffffu, snp_cur, i);
       mbar_wait(&pp.raw_empty[rslot], ph ^ 1u);
-      const uint32_t rs = raw0 + rslot * F_RAW_SLOT, bar = full0 + rslot * 8u;
+      const uint32_t rs = raw0 + rslot * rawslot, bar = full0 + rslot * 8u;
       mbar_expect_tx_elect(bar, bytes);
       tma_gather4_elect(rs + F_OFF_GPJ, &tm.gpj, colj, s[0], s[1], s[2], s[3], bar);
       tma_gather4_elect(rs + F_OFF_GPJ + 4 * GROWJ, &tm.gpj, colj, s[4], s[5], s[6], s[7], bar);
@@ -842,8 +845,8 @@ __device__ __forceinline__ void loader_role_f32(const ScanParams& p, const ScanM
         tma_gather4_elect(rs + F_OFF_GPK + 4 * GROWK, &tm.gpk, colk, s[4], s[5], s[6], s[7], bar);
       }
       // entry slots beyond the cell's last entry read the next cell's records (the tables have NB records of slack)
-      bulk_g2s_elect(rs + F_OFF_FH, p.entf_head + eb * FHEAD, NB * FHEAD * 4, bar);
-      bulk_g2s_elect(rs + F_OFF_FP, fplane + eb * FPLANE, NB * FPLANE * 4, bar);
+      bulk_g2s_elect(rs + off_fh, p.entf_head + eb * FHEAD, NB * FHEAD * 4, bar);
+      bulk_g2s_elect(rs + off_fh + NB * FHEAD * 4, fplane + eb * FPLANE, NB * FPLANE * 4, bar);
     }
     gbase += (uint32_t)ti.nst;
   }
@@ -860,6 +863,7 @@ __device__ __forceinline__ void loader_role_f32(const ScanParams& p, const ScanM
 struct TScratch {
   double xm[2][F_NTW][4][BLK];       // [task parity][warp][PA, PB, P1, P0][sample]: mantissa products of the warp's slots
   int xe[2][F_NTW][4][BLK];          // ... and their exponent sums
+  unsigned next_stage;               // stage counter of the CTA: transform warps take stages as they become free
 };
 constexpr uint32_t F_TS_BYTES = (sizeof(TScratch) + 127) / 128 * 128;
 
@@ -872,9 +876,10 @@ __device__ __forceinline__ void store_neutral_quad(float* dst) {   // four (1, 0
 
 // ROW0: 0 none, 1 symmetric plane (P0 of k-sample x *= a_0 . w_x), 2 full plane (P0 of j-sample x *= a_x . w_0)
 template <bool SAME, bool EXTRAS, int ROW0>
-__device__ __forceinline__ void transform_quad_f32(const unsigned char* __restrict__ rs, float* __restrict__ pf, int e,
-                                                   int q, bool jq, bool kq, float (&PA)[4], float (&PB)[4],
-                                                   float (&P1)[4], float (&P0)[4]) {
+__device__ __forceinline__ void transform_quad_f32(const unsigned char* __restrict__ rs, uint32_t off_fh,
+                                                   float* __restrict__ pf, int e, int q, bool jq, bool kq,
+                                                   float (&PA)[4], float (&PB)[4], float (&P1)[4], float (&P0)[4]) {
+  const uint32_t off_fp = off_fh + NB * FHEAD * 4;
   float* af = pf + q * F_BLK4_FLT + e * 12;
   float* wf = af + F_SIDE_FLT;
   float g[12];
@@ -885,7 +890,7 @@ __device__ __forceinline__ void transform_quad_f32(const unsigned char* __restri
       const float4 x = src[0], y = src[1], z = src[2];
       g[0] = x.x; g[1] = x.y; g[2] = x.z; g[3] = x.w; g[4] = y.x; g[5] = y.y; g[6] = y.z; g[7] = y.w;
       g[8] = z.x; g[9] = z.y; g[10] = z.z; g[11] = z.w;
-      const float4* qp = reinterpret_cast<const float4*>(rs + F_OFF_FP + e * (FPLANE * 4));
+      const float4* qp = reinterpret_cast<const float4*>(rs + off_fp + e * (FPLANE * 4));
       const float4 qa = qp[0], qb = qp[1];       // Q'[l][m] row-major: (00 01 02 10) (11 12 20 21) (22 . . .)
       const float q22 = reinterpret_cast<const float*>(qp + 2)[0];
       float w[12];
@@ -897,7 +902,7 @@ __device__ __forceinline__ void transform_quad_f32(const unsigned char* __restri
         w[3 * i + 2] = fmaf(q22, f2, fmaf(qb.w, f1, qb.z * f0));
       }
       if (EXTRAS) {
-        const float4* hp = reinterpret_cast<const float4*>(rs + F_OFF_FH + e * (FHEAD * 4));
+        const float4* hp = reinterpret_cast<const float4*>(rs + off_fh + e * (FHEAD * 4));
         const float4 h0 = hp[0];                  // GL0 GL1 GL2 f0
         const float2 h1 = reinterpret_cast<const float2*>(hp + 1)[0];   // f1 f2
 #pragma unroll
@@ -931,7 +936,7 @@ __device__ __forceinline__ void transform_quad_f32(const unsigned char* __restri
       if (ROW0 == 2) {   // pairs (x, 0): sample 0 is the first sample of the k-side row (k0 == 0)
         const float* g0p = reinterpret_cast<const float*>(rs + F_OFF_GPK + e * GROWK + GPFX * 4);
         const float f0 = g0p[0], f1 = g0p[1], f2 = g0p[2];
-        const float4* qp = reinterpret_cast<const float4*>(rs + F_OFF_FP + e * (FPLANE * 4));
+        const float4* qp = reinterpret_cast<const float4*>(rs + off_fp + e * (FPLANE * 4));
         const float4 qa = qp[0], qb = qp[1];
         const float q22 = reinterpret_cast<const float*>(qp + 2)[0];
         const float w0 = fmaf(qa.z, f2, fmaf(qa.y, f1, qa.x * f0));
@@ -963,15 +968,18 @@ __device__ __forceinline__ void peelf_unbiased(float& x, int& es) {
 }
 
 // all four entries of a lane in one stage: e = ebase + 2 i (independent work, interleaved by the compiler)
-template <bool SAME, bool EXTRAS, int ROW0>
-__device__ __forceinline__ void transform_stage_f32(const unsigned char* __restrict__ rs, float* __restrict__ pf,
-                                                    int ebase, int q, int nvalid, bool jq, bool kq, float (&PA)[4],
-                                                    float (&PB)[4], float (&P1)[4], float (&P0)[4]) {
-#pragma unroll
+template <bool SAME, bool EXTRAS, int ROW0, bool UNROLL>
+__device__ __forceinline__ void transform_stage_f32(const unsigned char* __restrict__ rs, uint32_t off_fh,
+                                                    float* __restrict__ pf, int ebase, int q, int nvalid, bool jq,
+                                                    bool kq, float (&PA)[4], float (&PB)[4], float (&P1)[4],
+                                                    float (&P0)[4]) {
+  // UNROLL: the four entries' loads and arithmetic interleave (needs ~130 registers); the rolled form is for the
+  // transform warp of the register-poor warpgroup
+#pragma unroll(UNROLL ? NB / 2 : 1)
   for (int i = 0; i < NB / 2; ++i) {
     const int e = ebase + 2 * i;
     if (e < nvalid) {
-      transform_quad_f32<SAME, EXTRAS, ROW0>(rs, pf, e, q, jq, kq, PA, PB, P1, P0);
+      transform_quad_f32<SAME, EXTRAS, ROW0>(rs, off_fh, pf, e, q, jq, kq, PA, PB, P1, P0);
     } else {   // identity entry: S = 1 for every hypothesis
       store_neutral_quad(pf + q * F_BLK4_FLT + e * 12);
       store_neutral_quad(pf + F_SIDE_FLT + q * F_BLK4_FLT + e * 12);
@@ -979,13 +987,23 @@ __device__ __forceinline__ void transform_stage_f32(const unsigned char* __restr
   }
 }
 
-// Transform warp tw owns the stages g with g % F_NTW == tw (whole stages: the four warps work on four different
-// stages at a time, which hides the latency of a stage's dependent load -> FMA -> store chain).
+// A transform warp takes whole stages from the CTA's stage counter, so the F_NTW warps work on different stages at a
+// time (which hides the latency of a stage's dependent load -> FMA -> store chain) and a warp that shares its
+// sub-partition with busier consumers simply takes fewer.  In-flight stages span at most F_NTW consecutive
+// indices, fewer than either ring has slots, so the parity waits below cannot alias.
+template <bool UNROLL>
 __device__ __forceinline__ void transform_role_f32(const ScanParams& p, const Pipe& pp, TScratch* ts, int tw, int lane,
                                                    int u, int NS) {
   const int ebase = lane >> 4, q = lane & 15;
   const int tl = tw * 32 + lane;
+  const uint32_t sraw = (uint32_t)p.f_sraw, rawslot = (uint32_t)p.f_rawslot, off_fh = (uint32_t)p.f_off_fh;
   uint32_t gbase = 0;   // stages of the tasks before this one
+  auto grab = [&]() -> uint32_t {
+    uint32_t g = 0;
+    if (lane == 0) g = atomicAdd(&ts->next_stage, 1u);
+    return __shfl_sync(0xffffffffu, g, 0);
+  };
+  uint32_t git = grab();
   TaskInfo ti;
   for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
     const TaskType tt = p.tt[ti.tti];
@@ -1000,33 +1018,33 @@ __device__ __forceinline__ void transform_role_f32(const ScanParams& p, const Pi
     int eA[4], e1x[4], e0x[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) { PA[i] = PB[i] = P1[i] = P0[i] = 1.0f; eA[i] = e1x[i] = e0x[i] = 0; }
-    for (int it = (int)((F_NTW + tw - gbase % F_NTW) % F_NTW); it < ti.nst; it += F_NTW) {
-      const uint32_t git = gbase + (uint32_t)it;
-      const int rslot = git % F_S_RAW, pslot = git % F_S_PROC;
-      const uint32_t rph = (git / F_S_RAW) & 1u, pph = (git / F_S_PROC) & 1u;
+    for (; git < gbase + (uint32_t)ti.nst; git = grab()) {
+      const int it = (int)(git - gbase);
+      const uint32_t rslot = git % sraw, pslot = git % F_S_PROC;
+      const uint32_t rph = (git / sraw) & 1u, pph = (git / F_S_PROC) & 1u;
       const int nvalid = (int)min((int64_t)NB, ti.e1 - (ti.e0 + (int64_t)it * NB));
       mbar_wait(&pp.raw_full[rslot], rph);
       mbar_wait(&pp.proc_empty[pslot], pph ^ 1u);
-      const unsigned char* rs = pp.raw_base + (size_t)rslot * F_RAW_SLOT;
+      const unsigned char* rs = pp.raw_base + (size_t)rslot * rawslot;
       float* pf = reinterpret_cast<float*>(pp.proc_base + (size_t)pslot * F_PROC_SLOT);
       if (p.dbg & 2) {
       } else if (same) {
         if (extras_t) {
-          if (row0) transform_stage_f32<true, true, 1>(rs, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
-          else transform_stage_f32<true, true, 0>(rs, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
+          if (row0) transform_stage_f32<true, true, 1, UNROLL>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
+          else transform_stage_f32<true, true, 0, UNROLL>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
         } else {
-          if (row0) transform_stage_f32<true, false, 1>(rs, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
-          else transform_stage_f32<true, false, 0>(rs, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
+          if (row0) transform_stage_f32<true, false, 1, UNROLL>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
+          else transform_stage_f32<true, false, 0, UNROLL>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
         }
       } else {
         if (extras_t) {
-          if (row0 == 2) transform_stage_f32<false, true, 2>(rs, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
-          else if (row0 == 1) transform_stage_f32<false, true, 1>(rs, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
-          else transform_stage_f32<false, true, 0>(rs, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
+          if (row0 == 2) transform_stage_f32<false, true, 2, UNROLL>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
+          else if (row0 == 1) transform_stage_f32<false, true, 1, UNROLL>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
+          else transform_stage_f32<false, true, 0, UNROLL>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
         } else {
-          if (row0 == 2) transform_stage_f32<false, false, 2>(rs, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
-          else if (row0 == 1) transform_stage_f32<false, false, 1>(rs, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
-          else transform_stage_f32<false, false, 0>(rs, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
+          if (row0 == 2) transform_stage_f32<false, false, 2, UNROLL>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
+          else if (row0 == 1) transform_stage_f32<false, false, 1, UNROLL>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
+          else transform_stage_f32<false, false, 0, UNROLL>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
         }
       }
       if (prods_t) {
@@ -1055,7 +1073,7 @@ __device__ __forceinline__ void transform_role_f32(const ScanParams& p, const Pi
     gbase += (uint32_t)ti.nst;
     if (!prods_t) continue;   // uniform over the transform warps
     const int buf = r & 1;
-    // fold the two entry slots of this warp (lanes 16 apart), then the four warps through shared memory
+    // fold the two entry slots of this warp (lanes 16 apart), then the warps through shared memory
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       double ma = (double)PA[i], mb = (double)PB[i], m1 = (double)P1[i], m0 = (double)P0[i];
@@ -1076,7 +1094,7 @@ __device__ __forceinline__ void transform_role_f32(const ScanParams& p, const Pi
       }
     }
     asm volatile("bar.sync 2, %0;" ::"n"(F_NTW * 32) : "memory");
-    // 4 x 64 (quantity, sample) results over the 128 transform lanes
+    // 4 x 64 (quantity, sample) results over the transform lanes
     for (int item = tl; item < 4 * BLK; item += F_NTW * 32) {
       const int c = item >> 6, smp = item & (BLK - 1);
       if (c < 3) {
@@ -1359,25 +1377,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_scan_kernel(const __grid_con
   }
 }
 
-// S[i][c] = a_i . w_c and acc *= S for one 8 x 8 tile and one entry, a tile row at a time (eight independent chains);
-// a diagonal tile of a triangular task skips the hypotheses below the diagonal
+// S[i][c] = a_i . w_c and acc *= S for one 8 x 8 tile and one entry, four columns of two tile rows at a time (eight
+// independent chains); the left half of the tile needs only the first of the two w blocks, so it can start while the
+// second block's loads are still in flight.  A diagonal tile of a triangular task skips the hypotheses below the
+// diagonal.
 template <bool DIAG>
 __device__ __forceinline__ void tile_math(const float (&a)[8][3], const float (&w)[8][3], float (&acc)[64]) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float s[8];
+  for (int half = 0; half < 2; ++half) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-      if (!DIAG || c >= i) s[c] = a[i][0] * w[c][0];
+    for (int i0 = 0; i0 < 8; i0 += 2) {
+      float s[2][4];
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-      if (!DIAG || c >= i) s[c] = fmaf(a[i][1], w[c][1], s[c]);
+      for (int r = 0; r < 2; ++r)
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-      if (!DIAG || c >= i) s[c] = fmaf(a[i][2], w[c][2], s[c]);
+        for (int c = 0; c < 4; ++c)
+          if (!DIAG || half * 4 + c >= i0 + r) s[r][c] = a[i0 + r][0] * w[half * 4 + c][0];
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-      if (!DIAG || c >= i) acc[i * 8 + c] *= s[c];
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (!DIAG || half * 4 + c >= i0 + r) s[r][c] = fmaf(a[i0 + r][1], w[half * 4 + c][1], s[r][c]);
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (!DIAG || half * 4 + c >= i0 + r) s[r][c] = fmaf(a[i0 + r][2], w[half * 4 + c][2], s[r][c]);
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (!DIAG || half * 4 + c >= i0 + r) acc[(i0 + r) * 8 + half * 4 + c] *= s[r][c];
+    }
   }
 }
 
@@ -1386,7 +1417,7 @@ __device__ __forceinline__ void tile_math(const float (&a)[8][3], const float (&
 // placed so that the issue load of the four sub-partitions is even (C = consumer, D = consumer of diagonal tiles:
 // 36 / 64 of the work, T = transform, L = loader):
 //   wid   0  1  2  3 |  4  5  6  7 |  8  9 10 11 | 12 13 14 15
-//         D  C  C  C |  D  C  C  C |  C  T  T  T |  T  L  L  L
+//         D  C  C  C |  D  C  C  C |  C  T  T  T |  T  L  L  T
 // The last warpgroup gives registers back (setmaxnreg) so that the consumers' 64 accumulators + 48 operands fit.
 //
 // A consumer thread owns the 8 x 8 tile (bj, bk) of hypotheses for the entries e = lane & 7 of every stage: per
@@ -1400,7 +1431,8 @@ __device__ __forceinline__ void tile_math(const float (&a)[8][3], const float (&
 // multiply their products together (fp64 reduce-scatter: lane e ends up with tile row e).
 // ---------------------------------------------------------------------------------------------
 constexpr int F_LAUNCH_THREADS = 512;
-static_assert(F_S_RAW % F_NLOAD == 0 && F_S_RAW % F_NTW == 0 && F_S_PROC % F_NTW == 0 && F_NLOAD <= 3, "ring ownership");
+static_assert(F_S_RAW_RECT % F_NLOAD == 0 && F_S_RAW_TRI % F_NLOAD == 0 && F_NLOAD == 2 && F_NTW <= 5 &&
+              F_NTW < (int)F_S_RAW_RECT && F_NTW < F_S_PROC, "ring ownership");
 constexpr int F_REGS_HI = 136, F_REGS_LO = 104;   // (3 * 136 + 104) * 32 = 16384 registers per sub-partition
 
 __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_f32_kernel(const __grid_constant__ ScanParams p,
@@ -1409,16 +1441,16 @@ __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_f32_kernel(cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Pipe pp;
   pp.raw_full = reinterpret_cast<uint64_t*>(smem);
-  pp.raw_empty = pp.raw_full + F_S_RAW;
-  pp.proc_full = pp.raw_empty + F_S_RAW;
+  pp.raw_empty = pp.raw_full + F_S_RAW_TRI;
+  pp.proc_full = pp.raw_empty + F_S_RAW_TRI;
   pp.proc_empty = pp.proc_full + F_S_PROC;
   Scratch* scr = reinterpret_cast<Scratch*>(smem + SCRATCH_OFF);
   pp.raw_base = smem + SLOT_CTRL;
-  pp.proc_base = pp.raw_base + F_S_RAW * F_RAW_SLOT;
+  pp.proc_base = pp.raw_base + F_RAW_BYTES;
   TScratch* ts = reinterpret_cast<TScratch*>(smem + F_SMEM_NOTS);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < F_S_RAW; ++s) {
+    for (int s = 0; s < (int)F_S_RAW_TRI; ++s) {
       mbar_init(&pp.raw_full[s], 1);
       mbar_init(&pp.raw_empty[s], 1);
     }
@@ -1427,6 +1459,7 @@ __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_f32_kernel(cons
       mbar_init(&pp.proc_empty[s], F_NCW);
     }
     scr->ncand = 0;
+    ts->next_stage = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -1435,13 +1468,14 @@ __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_f32_kernel(cons
   const int NS = (int)gridDim.x, u = (int)blockIdx.x;
   if (warp >= 12) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(F_REGS_LO));
-    if (warp == 12) transform_role_f32(p, pp, ts, F_NTW - 1, lane, u, NS);
-    else if (warp - 13 < F_NLOAD) loader_role_f32(p, tm, pp, lane, u, NS, warp - 13);
+    if (warp == 12) { if (F_NTW > 3) transform_role_f32<false>(p, pp, ts, 3, lane, u, NS); }
+    else if (warp == 15) { if (F_NTW > 4) transform_role_f32<false>(p, pp, ts, 4, lane, u, NS); }
+    else loader_role_f32(p, tm, pp, lane, u, NS, warp - 13);
     return;
   }
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(F_REGS_HI));
   if (warp >= F_NCW) {
-    transform_role_f32(p, pp, ts, warp - F_NCW, lane, u, NS);
+    transform_role_f32<true>(p, pp, ts, warp - F_NCW, lane, u, NS);
   } else {
     // =============================== consumer warps ============================================
     // logical consumer index: 0..6 own the 28 off-diagonal tile positions of a triangular task, 7 and 8 (physical
@@ -1486,10 +1520,17 @@ __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_f32_kernel(cons
         if (active && !(p.dbg & 1)) {
           const float* pf = reinterpret_cast<const float*>(pp.proc_base + (size_t)pslot * F_PROC_SLOT);
           float a[8][3], w[8][3];
+          float4 ld[12];   // issue order: first w block, the two a blocks, second w block
+#pragma unroll
+          for (int q = 0; q < 3; ++q) ld[q] = *reinterpret_cast<const float4*>(pf + woff + q * 4);
+#pragma unroll
+          for (int q = 0; q < 6; ++q)
+            ld[3 + q] = *reinterpret_cast<const float4*>(pf + aoff + (q / 3) * F_BLK4_FLT + (q % 3) * 4);
+#pragma unroll
+          for (int q = 0; q < 3; ++q) ld[9 + q] = *reinterpret_cast<const float4*>(pf + woff + F_BLK4_FLT + q * 4);
 #pragma unroll
           for (int q = 0; q < 6; ++q) {
-            const float4 x = *reinterpret_cast<const float4*>(pf + aoff + (q / 3) * F_BLK4_FLT + (q % 3) * 4);
-            const float4 y = *reinterpret_cast<const float4*>(pf + woff + (q / 3) * F_BLK4_FLT + (q % 3) * 4);
+            const float4 x = ld[3 + q], y = q < 3 ? ld[q] : ld[9 + q - 3];
             const float xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -1594,7 +1635,11 @@ int launch_pair_scan(const ScanParams& p, const ScanMaps& tm, bool fp32, void* s
   if (fp32) {
     int64_t grid = p.ntasks;
     if (grid > g_num_sms) grid = g_num_sms;
-    pair_scan_f32_kernel<<<(unsigned)grid, F_LAUNCH_THREADS, smem, (cudaStream_t)stream>>>(p, tm);
+    ScanParams q = p;
+    q.f_sraw = p.has_rect ? F_S_RAW_RECT : F_S_RAW_TRI;
+    q.f_rawslot = p.has_rect ? F_RAW_SLOT_RECT : F_RAW_SLOT_TRI;
+    q.f_off_fh = q.f_rawslot - F_REC_BYTES;
+    pair_scan_f32_kernel<<<(unsigned)grid, F_LAUNCH_THREADS, smem, (cudaStream_t)stream>>>(q, tm);
   } else {
     int64_t grid = (p.ntasks + NSLOT - 1) / NSLOT;
     if (grid > g_num_sms) grid = g_num_sms;
@@ -1754,22 +1799,24 @@ __device__ __forceinline__ double exact_term(const float* __restrict__ g, const 
 
 __global__ void __launch_bounds__(256) rescore_terms_kernel(const __grid_constant__ RescoreParams p, int64_t nactive,
                                                             int pass) {
-  const int cell = p.cell_order[blockIdx.x];
-  const RescList* L = p.lists + cell;
-  const int H = min(L->n - pass * RESC_FAST, RESC_FAST);   // hypotheses of this pass
-  if (H <= 0) return;
-  uint32_t hyp[RESC_FAST];
+  for (int64_t aidx = blockIdx.x; aidx < nactive; aidx += gridDim.x) {
+    const int cell = p.cell_order[aidx];
+    const RescList* L = p.lists + cell;
+    const int H = min(L->n - pass * RESC_FAST, RESC_FAST);   // hypotheses of this pass
+    if (H <= 0) continue;
+    uint32_t hyp[RESC_FAST];
 #pragma unroll
-  for (int h = 0; h < RESC_FAST; ++h) hyp[h] = h < H ? L->hyp[pass * RESC_FAST + h] : 0u;
-  const int64_t e0 = p.cell_ptr[cell], n = p.cell_ptr[cell + 1] - e0;
-  double* out = p.terms + e0 * RESC_FAST;                  // this cell's block: [h][entry]
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const int64_t e = e0 + i;
-    const float* g = p.gp + (int64_t)__ldg(p.ent_snp + e) * p.gp_stride;
-    const double* q = p.entq + e * p.UQ;
+    for (int h = 0; h < RESC_FAST; ++h) hyp[h] = h < H ? L->hyp[pass * RESC_FAST + h] : 0u;
+    const int64_t e0 = p.cell_ptr[cell], n = p.cell_ptr[cell + 1] - e0;
+    double* out = p.terms + e0 * RESC_FAST;                  // this cell's block: [h][entry]
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const int64_t e = e0 + i;
+      const float* g = p.gp + (int64_t)__ldg(p.ent_snp + e) * p.gp_stride;
+      const double* q = p.entq + e * p.UQ;
 #pragma unroll
-    for (int h = 0; h < RESC_FAST; ++h)
-      if (h < H) out[h * n + i] = exact_term(g, q, hyp[h], p.dense_idx);
+      for (int h = 0; h < RESC_FAST; ++h)
+        if (h < H) out[h * n + i] = exact_term(g, q, hyp[h], p.dense_idx);
+    }
   }
 }
 
@@ -1784,15 +1831,18 @@ __global__ void __launch_bounds__(128) rescore_sum_kernel(const __grid_constant_
   if (L->n < 0 || pass * RESC_FAST + h >= L->n) return;
   const int64_t e0 = p.cell_ptr[cell], n = p.cell_ptr[cell + 1] - e0;
   const double* x = p.terms + e0 * RESC_FAST + h * n;
-  // the additions form one dependent chain in entry order; the loads run a batch ahead of it
-  constexpr int B = 16;
+  // the additions form one dependent chain in entry order; the loads run a batch ahead of it and the lines they will
+  // touch are prefetched into L1 eight batches ahead (the terms were written by the previous launch)
+  constexpr int B = 16, PF = 8 * B;
   double cur[B], nxt[B];
+  for (int64_t i = 0; i < min(n, (int64_t)PF); i += B) asm volatile("prefetch.global.L1 [%0];" ::"l"(x + i));
 #pragma unroll
-  for (int u2 = 0; u2 < B; ++u2) cur[u2] = u2 < n ? __ldcg(x + u2) : 0.0;
+  for (int u2 = 0; u2 < B; ++u2) cur[u2] = u2 < n ? x[u2] : 0.0;
   double acc = 0.0;
   for (int64_t i = 0; i < n; i += B) {
+    if (i + PF < n) asm volatile("prefetch.global.L1 [%0];" ::"l"(x + i + PF));
 #pragma unroll
-    for (int u2 = 0; u2 < B; ++u2) nxt[u2] = (i + B + u2 < n) ? __ldcg(x + i + B + u2) : 0.0;
+    for (int u2 = 0; u2 < B; ++u2) nxt[u2] = (i + B + u2 < n) ? x[i + B + u2] : 0.0;
     if (i + B <= n) {
 #pragma unroll
       for (int u2 = 0; u2 < B; ++u2) acc = __dadd_rn(acc, cur[u2]);
@@ -1812,7 +1862,8 @@ int launch_rescore(const RescoreParams& p, int64_t nactive, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   // lists longer than RESC_FAST take further passes over the same terms buffer (their blocks exit at once otherwise)
   for (int pass = 0; pass * RESC_FAST < RMAX; ++pass) {
-    rescore_terms_kernel<<<(unsigned)nactive, 256, 0, st>>>(p, nactive, pass);
+    const int64_t grid = pass == 0 ? nactive : (nactive < 1184 ? nactive : 1184);
+    rescore_terms_kernel<<<(unsigned)grid, 256, 0, st>>>(p, nactive, pass);
     rescore_sum_kernel<<<(unsigned)((nactive * RESC_FAST + 127) / 128), 128, 0, st>>>(p, nactive, pass);
   }
   return (int)cudaGetLastError();
