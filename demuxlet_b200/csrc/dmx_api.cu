@@ -11,6 +11,9 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -68,6 +71,15 @@ struct PinBuf {
 };
 }  // namespace
 
+namespace {
+class WorkerPool;
+}
+
+struct Chunk {
+  int64_t c0, c1;   // cell ids [c0, c1)
+  int64_t o0, o1;   // its active cells, largest first: order[o0, o1)
+};
+
 struct dmx_ctx {
   dmx_config cfg;
   std::vector<double> alpha;
@@ -76,7 +88,14 @@ struct dmx_ctx {
   int dense_idx[DMX_MAX_ALPHA];
   std::vector<TaskType> tt;
   double err256[256];
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;   // kernels; host -> device copies of dmx_run;
+                                                                      // read back of finished chunks
+  std::vector<cudaEvent_t> cev;     // per-chunk events (run_path)
+  std::vector<Chunk> chunks;        // contiguous cell-id ranges, balanced by entries (dmx_set_pileup): one chunk for
+                                    // dmx_compute (inputs resident) ...
+  std::vector<Chunk> chunks_p;      // ... several for dmx_run, whose host -> device copies overlap the kernels
+  std::vector<int32_t> order_p;     // schedule of chunks_p
+  WorkerPool* pool = nullptr;       // host threads of the finaliser
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
   // inputs (host): borrowed or owned
@@ -136,6 +155,11 @@ int fail_cuda(cudaError_t e, const char* what) {
   do {                                                         \
     cudaError_t e__ = (cudaError_t)(x);                        \
     if (e__ != cudaSuccess) return fail_cuda(e__, #x);         \
+  } while (0)
+#define RC(x)                                                  \
+  do {                                                         \
+    const int rc__ = (x);                                      \
+    if (rc__ != DMX_OK) return rc__;                           \
   } while (0)
 
 // Upload the host libm's log table and check the device transcription of glibc's log() against the
@@ -293,26 +317,80 @@ void build_tasks(dmx_ctx* c) {
   }
 }
 
-template <class F>
-void parallel_for(int64_t n, int nthreads, F f) {
-  if (nthreads <= 1 || n < 2) {
-    for (int64_t i = 0; i < n; ++i) f(i, 0);
-    return;
+// Persistent host threads for the finaliser (a run calls parallel_for once per chunk: creating threads each time
+// would cost more than the work).
+class WorkerPool {
+ public:
+  ~WorkerPool() { stop(); }
+  void ensure(int nthreads) {
+    if ((int)th_.size() == nthreads - 1) return;
+    stop();
+    quit_ = false;
+    for (int t = 1; t < nthreads; ++t) th_.emplace_back([this, t]() { loop(t); });
   }
-  std::atomic<int64_t> next(0);
-  std::vector<std::thread> th;
-  const int64_t chunk = std::max<int64_t>(1, n / (nthreads * 16));
-  for (int t = 0; t < nthreads; ++t)
-    th.emplace_back([&, t]() {
-      for (;;) {
-        const int64_t lo = next.fetch_add(chunk);
-        if (lo >= n) break;
-        const int64_t hi = std::min(n, lo + chunk);
-        for (int64_t i = lo; i < hi; ++i) f(i, t);
+  // f(i, tid) for i in [0, n); the caller is worker 0
+  void run(int64_t n, int nthreads, const std::function<void(int64_t, int)>& f) {
+    if (nthreads <= 1 || n < 2) {
+      for (int64_t i = 0; i < n; ++i) f(i, 0);
+      return;
+    }
+    ensure(nthreads);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      fn_ = &f; n_ = n; next_.store(0);
+      chunk_ = std::max<int64_t>(1, n / (nthreads * 16));
+      pending_ = (int)th_.size();
+      ++gen_;
+    }
+    cv_.notify_all();
+    work(0);
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [this]() { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void work(int tid) {
+    for (;;) {
+      const int64_t lo = next_.fetch_add(chunk_);
+      if (lo >= n_) break;
+      const int64_t hi = std::min(n_, lo + chunk_);
+      for (int64_t i = lo; i < hi; ++i) (*fn_)(i, tid);
+    }
+  }
+  void loop(int tid) {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&]() { return quit_ || gen_ != seen; });
+        if (quit_) return;
+        seen = gen_;
       }
-    });
-  for (auto& x : th) x.join();
-}
+      work(tid);
+      std::lock_guard<std::mutex> lk(mu_);
+      if (--pending_ == 0) done_.notify_all();
+    }
+  }
+  void stop() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      quit_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+    th_.clear();
+  }
+  std::vector<std::thread> th_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int64_t, int)>* fn_ = nullptr;
+  std::atomic<int64_t> next_{0};
+  int64_t n_ = 0, chunk_ = 1;
+  int pending_ = 0;
+  uint64_t gen_ = 0;
+  bool quit_ = false;
+};
 
 int host_threads(const dmx_ctx* c) {
   int n = c->cfg.n_host_threads;
@@ -471,6 +549,7 @@ int dmx_create(dmx_ctx** out, const dmx_config* cfg) {
   dmx_ctx* c = new (std::nothrow) dmx_ctx();
   if (!c) return DMX_E_NOMEM;
   c->cfg = *cfg;
+  c->pool = new WorkerPool();
   c->alpha.assign(cfg->alpha, cfg->alpha + cfg->n_alpha);
   c->cfg.alpha = c->alpha.data();
   memset(&c->st, 0, sizeof(c->st));
@@ -479,6 +558,8 @@ int dmx_create(dmx_ctx** out, const dmx_config* cfg) {
   build_tasks(c);
   for (int i = 0; i <= 255; ++i) c->err256[i] = (i > 1) ? pow(0.1, i * 0.1) : 0.75;   // PhredHelper.cpp:30
   cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking);
   for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
   for (int i = 0; i <= 255; ++i) c->err3_256[i] = c->err256[i] / 3.0;   // the quotient of :606-607
   if (e == cudaSuccess) e = (cudaError_t)set_err_table(c->err256, c->err3_256);
@@ -516,6 +597,11 @@ void dmx_destroy(dmx_ctx* c) {
   c->r_p1_0.release(); c->r_dense.release();
   for (int i = 0; i < 6; ++i)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  delete c->pool;
+  for (cudaEvent_t e2 : c->cev)
+    if (e2) cudaEventDestroy(e2);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
+  if (c->stream3) cudaStreamDestroy(c->stream3);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -578,9 +664,35 @@ int dmx_set_pileup(dmx_ctx* c, int64_t ncells, const int64_t* cell_ptr, const in
     else if (ns == 0) c->status[i] = 2;
     else c->order.push_back((int32_t)i);
   }
-  std::stable_sort(c->order.begin(), c->order.end(), [&](int32_t a, int32_t b) {
-    return (cell_ptr[a + 1] - cell_ptr[a]) > (cell_ptr[b + 1] - cell_ptr[b]);
-  });
+  // chunks: contiguous cell-id ranges with about the same number of entries; inside a chunk the active cells are
+  // scheduled largest first.  Copies, kernels and the host finaliser of different chunks overlap (run_path).
+  int K = (E >= (2 << 20) && ncells >= 256) ? 3 : 1;
+  if (const char* ek = getenv("DMX_CHUNKS")) K = std::max(1, std::min(16, atoi(ek)));
+  auto build = [&](int nk, std::vector<int32_t>* ord, std::vector<Chunk>* chunks) {
+    chunks->clear();
+    int64_t cb = 0;
+    size_t ob = 0;
+    for (int k = 0; k < nk; ++k) {
+      Chunk ck;
+      ck.c0 = cb;
+      int64_t ce = cb;
+      if (k == nk - 1) ce = ncells;
+      else
+        while (ce < ncells && cell_ptr[ce] < (E * (k + 1)) / nk) ++ce;
+      ck.c1 = ce;
+      ck.o0 = (int64_t)ob;
+      while (ob < ord->size() && (*ord)[ob] < ce) ++ob;   // still in cell-id order here
+      ck.o1 = (int64_t)ob;
+      std::stable_sort(ord->begin() + ck.o0, ord->begin() + ck.o1, [&](int32_t a, int32_t b) {
+        return (cell_ptr[a + 1] - cell_ptr[a]) > (cell_ptr[b + 1] - cell_ptr[b]);
+      });
+      chunks->push_back(ck);
+      cb = ce;
+    }
+  };
+  c->order_p = c->order;
+  build(1, &c->order, &c->chunks);
+  build(K, &c->order_p, &c->chunks_p);
   c->have_plp = true;
   c->plp_dirty = true;
   c->uploaded = false;
@@ -588,13 +700,9 @@ int dmx_set_pileup(dmx_ctx* c, int64_t ncells, const int64_t* cell_ptr, const in
   return DMX_OK;
 }
 
-int dmx_upload(dmx_ctx* c) {
-  if (!c) return DMX_E_INVALID;
-  if (!c->have_gp || !c->have_plp) return DMX_E_STATE;
-  CU(cudaSetDevice(c->cfg.device));
-  const double t0 = now_ms();
-  const int nv = c->cfg.nv, nvp = c->nvp;
-  int64_t bytes = 0;
+namespace {
+// ---- host -> device copies: the inputs that every chunk needs, then one chunk's slices of the CSR arrays -----------
+int check_inputs(dmx_ctx* c) {
   if (c->E > 0 && !(c->cfg.flags & DMX_TRUST_INPUTS)) {
     // SNP ids must index the GP matrix
     // (checked lazily here rather than in dmx_set_pileup so either setter can come first)
@@ -605,82 +713,67 @@ int dmx_upload(dmx_ctx* c) {
     }
     if (mn < 0 || mx >= c->nsnps) return DMX_E_INVALID;
   }
-  if (c->gp_dirty) {
-    CU(c->d_gp.reserve((size_t)c->nsnps * nvp * 3 + 4));
-    CU(c->d_gprow.reserve((size_t)c->nsnps * (nvp * 3 + 8) + 256));
-    if (nvp == nv) {
-      CU(cudaMemcpyAsync(c->d_gp.p, c->h_gp, (size_t)c->nsnps * nv * 3 * sizeof(float), cudaMemcpyHostToDevice,
-                         c->stream));
-    } else {
-      CU(cudaMemsetAsync(c->d_gp.p, 0, (size_t)c->nsnps * nvp * 3 * sizeof(float), c->stream));
-      CU(cudaMemcpy2DAsync(c->d_gp.p, (size_t)nvp * 12, c->h_gp, (size_t)nv * 12, (size_t)nv * 12,
-                           (size_t)c->nsnps, cudaMemcpyHostToDevice, c->stream));
-    }
-    bytes += c->nsnps * nv * 3 * (int64_t)sizeof(float);
-    c->gp_dirty = false;
-  }
-  if (c->plp_dirty) {
-    CU(c->d_cell_ptr.reserve(c->ncells + 1)); CU(c->d_ent_snp.reserve(c->E + 1)); CU(c->d_ent_ptr.reserve(c->E + 1));
-    CU(c->d_reads.reserve(c->R + 1)); CU(c->d_order.reserve(c->order.size() + 1));
-    CU(cudaMemcpyAsync(c->d_cell_ptr.p, c->h_cell_ptr, (c->ncells + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
-    if (c->E) CU(cudaMemcpyAsync(c->d_ent_snp.p, c->h_ent_snp, c->E * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->d_ent_ptr.p, c->h_ent_ptr, (c->E + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
-    if (c->R) CU(cudaMemcpyAsync(c->d_reads.p, c->h_reads, c->R * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
-    if (!c->order.empty())
-      CU(cudaMemcpyAsync(c->d_order.p, c->order.data(), c->order.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-    bytes += (c->ncells + 1) * 8 + c->E * 4 + (c->E + 1) * 8 + c->R * 2 + (int64_t)c->order.size() * 4;
-    c->plp_dirty = false;
-  }
-  CU(cudaStreamSynchronize(c->stream));
-  c->st.h2d_ms = now_ms() - t0;
-  c->st.h2d_bytes = bytes;
-  c->uploaded = true;
-  c->computed = false;
   return DMX_OK;
 }
 
-int dmx_compute(dmx_ctx* c) {
-  if (!c) return DMX_E_INVALID;
-  if (!c->uploaded) return DMX_E_STATE;
-  CU(cudaSetDevice(c->cfg.device));
-  const double t0 = now_ms();
-  const int nv = c->cfg.nv, nA = c->cfg.n_alpha;
-  const int64_t nc = c->ncells, nact = (int64_t)c->order.size();
-  const int T = (int)c->tt.size();
-  c->st.gpu_launches = 0;
-  c->st.n_rescored = 0;
-  c->st.n_fullcell = 0;
+int reserve_inputs(dmx_ctx* c) {
+  const int nvp = c->nvp;
+  CU(c->d_gp.reserve((size_t)c->nsnps * nvp * 3 + 4));
+  CU(c->d_gprow.reserve((size_t)c->nsnps * (nvp * 3 + 8) + 256));
+  CU(c->d_cell_ptr.reserve(c->ncells + 1)); CU(c->d_ent_snp.reserve(c->E + 1)); CU(c->d_ent_ptr.reserve(c->E + 1));
+  CU(c->d_reads.reserve(c->R + 1)); CU(c->d_order.reserve(c->order.size() + 1));
+  return DMX_OK;
+}
 
-  CU(c->d_entq.reserve((size_t)c->E * c->UQ + (size_t)NB * c->UQ + 2));   // slack: a stage always reads NB records
+int upload_common(dmx_ctx* c, cudaStream_t st, int64_t* bytes, const std::vector<int32_t>& order) {
+  const int nv = c->cfg.nv, nvp = c->nvp;
+  if (c->gp_dirty) {
+    if (nvp == nv) {
+      CU(cudaMemcpyAsync(c->d_gp.p, c->h_gp, (size_t)c->nsnps * nv * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    } else {
+      CU(cudaMemsetAsync(c->d_gp.p, 0, (size_t)c->nsnps * nvp * 3 * sizeof(float), st));
+      CU(cudaMemcpy2DAsync(c->d_gp.p, (size_t)nvp * 12, c->h_gp, (size_t)nv * 12, (size_t)nv * 12, (size_t)c->nsnps,
+                           cudaMemcpyHostToDevice, st));
+    }
+    *bytes += c->nsnps * nv * 3 * (int64_t)sizeof(float);
+  }
+  if (c->plp_dirty) {
+    CU(cudaMemcpyAsync(c->d_cell_ptr.p, c->h_cell_ptr, (c->ncells + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    *bytes += (c->ncells + 1) * 8;
+  }
+  // the schedule goes with every run: dmx_compute and dmx_run use different ones
+  if (!order.empty())
+    CU(cudaMemcpyAsync(c->d_order.p, order.data(), order.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  *bytes += (int64_t)order.size() * 4;
+  return DMX_OK;
+}
+
+int upload_chunk(dmx_ctx* c, const Chunk& ck, cudaStream_t st, int64_t* bytes) {
+  if (!c->plp_dirty) return DMX_OK;
+  const int64_t e0 = c->h_cell_ptr[ck.c0], e1 = c->h_cell_ptr[ck.c1];
+  const int64_t r0 = c->h_ent_ptr[e0], r1 = c->h_ent_ptr[e1];
+  if (e1 > e0)
+    CU(cudaMemcpyAsync(c->d_ent_snp.p + e0, c->h_ent_snp + e0, (e1 - e0) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(c->d_ent_ptr.p + e0, c->h_ent_ptr + e0, (e1 - e0 + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  if (r1 > r0)
+    CU(cudaMemcpyAsync(c->d_reads.p + r0, c->h_reads + r0, (r1 - r0) * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+  *bytes += (e1 - e0) * 4 + (e1 - e0 + 1) * 8 + (r1 - r0) * 2;
+  return DMX_OK;
+}
+
+// ---- the kernels of one chunk (a contiguous cell-id range; its active cells are order[o0, o1)) ----------------------
+int enqueue_chunk(dmx_ctx* c, const Chunk& ck, const ScanParams& sp0, bool dev_rescore, cudaEvent_t* ev /* [4] */) {
+  const int nv = c->cfg.nv, nA = c->cfg.n_alpha;
+  const int T = (int)c->tt.size();
   const int nd = (c->UQ - QHEAD) / QPLANE;
   const bool fp32 = (c->cfg.flags & DMX_FP32_PAIRS) != 0;
   const int64_t pstride = (c->E + NB) * FPLANE;
-  CU(c->d_ents.reserve((size_t)c->E * (2 + nd) + 2));
-  if (fp32) {
-    CU(c->d_entf_head.reserve((size_t)(c->E + NB) * FHEAD));
-    CU(c->d_entf_plane.reserve((size_t)pstride * std::max(nd, 1)));
-  }
-  CU(c->d_parts.reserve((size_t)nact * T + 1));
-  CU(c->d_row0.reserve((size_t)nc * nA * nv + 1)); CU(c->d_singA.reserve((size_t)nc * nv + 1));
-  CU(c->d_lb.reserve((size_t)nc * nv + 1)); CU(c->d_p1.reserve((size_t)nc * nv + 1));
-  CU(c->d_p1_0.reserve(nc + 1)); CU(c->d_l00.reserve((size_t)nc * nA + 1));
-  CU(c->d_sing.reserve((size_t)nc * nv + 1)); CU(c->d_out.reserve(nc + 1));
-  CU(c->r_out.reserve(nc + 1)); CU(c->r_sing.reserve((size_t)nc * nv + 1));
-  CU(c->r_row0.reserve((size_t)nc * nA * nv + 1)); CU(c->r_l00.reserve((size_t)nc * nA + 1));
-  CU(c->r_p1.reserve((size_t)nc * nv + 1)); CU(c->r_p1_0.reserve(nc + 1));
-
-  CU(cudaEventRecord(c->ev[0], c->stream));
-  // outputs of cells that are never scheduled stay zero (the reference prints zeros for them in .single)
-  CU(cudaMemsetAsync(c->d_p1.p, 0, (size_t)nc * nv * sizeof(double), c->stream));
-  CU(cudaMemsetAsync(c->d_p1_0.p, 0, (size_t)nc * sizeof(double), c->stream));
-  CU(cudaMemsetAsync(c->d_sing.p, 0, (size_t)nc * nv * sizeof(double), c->stream));
-  CU(cudaMemsetAsync(c->d_l00.p, 0, (size_t)nc * nA * sizeof(double), c->stream));
-  CU(cudaMemsetAsync(c->d_row0.p, 0, (size_t)nc * nA * nv * sizeof(double), c->stream));
-  CU(cudaMemsetAsync(c->d_out.p, 0, (size_t)nc * sizeof(CellOut), c->stream));
-  CU(launch_gprow(c->d_gp.p, c->d_gprow.p, c->nsnps, nv, c->nvp, c->stream));
+  const int64_t e0 = c->h_cell_ptr[ck.c0], e1 = c->h_cell_ptr[ck.c1];
+  const int64_t nact = ck.o1 - ck.o0;
+  CU(cudaEventRecord(ev[0], c->stream));
   EntqParams eq;
-  eq.U = c->pg.U; eq.UQ = c->UQ; eq.E = c->E;
-  eq.nd = (c->UQ - QHEAD) / QPLANE; eq.sep0 = c->pg.sep0; eq.gp_stride = c->nvp * 3 + 8; eq.gprow = c->d_gprow.p;
+  eq.U = c->pg.U; eq.UQ = c->UQ; eq.E0 = e0; eq.E = e1;
+  eq.nd = nd; eq.sep0 = c->pg.sep0; eq.gp_stride = c->nvp * 3 + 8; eq.gprow = c->d_gprow.p;
   eq.ent_snp = c->d_ent_snp.p; eq.ent_ptr = c->d_ent_ptr.p; eq.reads = c->d_reads.p;
   eq.entq = c->d_entq.p;
   eq.ents = c->d_ents.p;
@@ -706,92 +799,166 @@ int dmx_compute(dmx_ctx* c) {
     eq.oslot_ptr[c->pg.U] = (uint8_t)o;
   }
   CU(launch_entq(eq, c->stream));
-  if (fp32) {
+  if (e1 > e0) c->st.gpu_launches += 1;
+  if (fp32 && nact) {
     // the fp32 scan leaves the sample-independent likelihoods (llk0s, llks00) to their own small kernel
     CellScalarParams cs;
     memset(&cs, 0, sizeof(cs));
     cs.nd = nd; cs.nA = nA; cs.sep0 = c->pg.sep0; cs.want_single = (c->cfg.flags & DMX_SKIP_SINGLE) ? 0 : 1;
     for (int n = 0; n < nA; ++n)
       if (c->dense_idx[n] >= 0) cs.plane_n[c->dense_idx[n]] = (int8_t)n;
-    cs.ents = c->d_ents.p; cs.cell_ptr = c->d_cell_ptr.p; cs.cell_order = c->d_order.p;
+    cs.ents = c->d_ents.p; cs.cell_ptr = c->d_cell_ptr.p; cs.cell_order = c->d_order.p + ck.o0;
     cs.p1_0 = c->d_p1_0.p; cs.l00 = c->d_l00.p;
     CU(launch_cell_scalars(cs, nact, c->stream));
-    if (nact) c->st.gpu_launches += 1;
+    c->st.gpu_launches += 1;
   }
-  CU(cudaEventRecord(c->ev[1], c->stream));
-  ScanParams sp;
-  fill_scan_params(c, &sp);
-  {
-    const int rc = encode_maps(c);
-    if (rc != DMX_OK) return rc;
-  }
-  CU(launch_pair_scan(sp, c->maps, (c->cfg.flags & DMX_FP32_PAIRS) != 0, c->stream));
-  CU(cudaEventRecord(c->ev[2], c->stream));
-  if ((sp.dbg & 8) && getenv("DMX_TRACE")) {
-    std::vector<long long> tb(272 * 8);
-    CU(cudaStreamSynchronize(c->stream));
-    CU(cudaMemcpy(tb.data(), c->d_dbg.p, tb.size() * 8, cudaMemcpyDeviceToHost));
-    if (FILE* f = fopen(getenv("DMX_TRACE"), "w")) {
-      for (int i = 0; i < 272; ++i) {
-        for (int k = 0; k < 8; ++k) fprintf(f, "%lld ", tb[i * 8 + k]);
-        fprintf(f, "\n");
-      }
-      fclose(f);
-    }
-  }
+  CU(cudaEventRecord(ev[1], c->stream));
+  ScanParams sp = sp0;
+  sp.cell_order = c->d_order.p + ck.o0;
+  sp.parts = c->d_parts.p + ck.o0 * T;
+  sp.ntasks = nact * T;
+  CU(launch_pair_scan(sp, c->maps, fp32, c->stream));
+  CU(cudaEventRecord(ev[2], c->stream));
   MergeParams mp;
   memset(&mp, 0, sizeof(mp));
   mp.nv = nv; mp.nA = nA; mp.T = T; mp.sep0 = c->pg.sep0; mp.eps_rel = sp.eps_rel; mp.eps_ent = sp.eps_ent; mp.cell_ptr = c->d_cell_ptr.p;
   mp.w_single = (1. - c->cfg.doublet_prior) / nv;
   for (int n = 0; n < nA; ++n)
     mp.w_double[n] = c->cfg.doublet_prior / nv / (nv - 1) / (nA - 1) / (c->alpha[n] == 0.5 ? 2.0 : 1.0);
-  mp.cell_order = c->d_order.p; mp.tt = c->d_tt.p; mp.parts = c->d_parts.p; mp.row0 = c->d_row0.p;
+  mp.cell_order = sp.cell_order; mp.tt = c->d_tt.p; mp.parts = sp.parts; mp.row0 = c->d_row0.p;
   mp.singA = c->d_singA.p; mp.lb = c->d_lb.p; mp.sing = c->d_sing.p; mp.out = c->d_out.p;
-  const bool exact = (c->cfg.flags & DMX_EXACT_TIES) != 0;
-  const bool dev_rescore = exact && c->gpu_exact && !(c->cfg.flags & DMX_HOST_FINALISE);
   if (dev_rescore) {
-    CU(c->d_lists.reserve(nc + 1));
-    CU(c->r_lists.reserve(nc + 1));
     mp.lists = c->d_lists.p;
     for (int n = 0; n < nA; ++n) mp.mode[n] = c->pg.mode[n];
   }
   CU(launch_merge(mp, nact, c->stream));
+  if (nact) c->st.gpu_launches += 2;
   if (dev_rescore) {
     RescoreParams rp;
     memset(&rp, 0, sizeof(rp));
     rp.nv = nv; rp.gp_stride = c->nvp * 3 + 8; rp.nA = nA; rp.UQ = c->UQ; rp.sep0 = c->pg.sep0;
     for (int n = 0; n < nA; ++n) rp.dense_idx[n] = (int8_t)c->dense_idx[n];
     rp.gp = c->d_gprow.p + 8; rp.ent_snp = c->d_ent_snp.p; rp.entq = c->d_entq.p; rp.cell_ptr = c->d_cell_ptr.p;
-    rp.cell_order = c->d_order.p; rp.lists = c->d_lists.p;
-    CU(c->d_terms.reserve((size_t)c->E * RESC_FAST + 1));
+    rp.cell_order = sp.cell_order; rp.lists = c->d_lists.p;
     rp.terms = c->d_terms.p;
     CU(launch_rescore(rp, nact, c->stream));
-    if (nact) c->st.gpu_launches += 2 * (RMAX / RESC_FAST) - 1;
+    if (nact) c->st.gpu_launches += 2 * (RMAX / RESC_FAST);
   }
-  c->st.gpu_launches += (c->nsnps ? 1 : 0) + (c->E ? 1 : 0) + (nact ? 2 : 0) + ((nact && dev_rescore) ? 1 : 0);
-  CU(cudaEventRecord(c->ev[3], c->stream));
-  CU(cudaMemcpyAsync(c->r_out.p, c->d_out.p, nc * sizeof(CellOut), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaMemcpyAsync(c->r_sing.p, c->d_sing.p, (size_t)nc * nv * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaMemcpyAsync(c->r_row0.p, c->d_row0.p, (size_t)nc * nA * nv * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaMemcpyAsync(c->r_l00.p, c->d_l00.p, (size_t)nc * nA * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  if (sp.want_single) {
-    CU(cudaMemcpyAsync(c->r_p1.p, c->d_p1.p, (size_t)nc * nv * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(c->r_p1_0.p, c->d_p1_0.p, (size_t)nc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaEventRecord(ev[3], c->stream));
+  // read back the chunk's records (all per-cell arrays are indexed by cell id: one contiguous slice each)
+  CU(cudaStreamWaitEvent(c->stream3, ev[3], 0));
+  const int64_t c0 = ck.c0, n = ck.c1 - ck.c0;
+  if (n > 0) {
+    CU(cudaMemcpyAsync(c->r_out.p + c0, c->d_out.p + c0, n * sizeof(CellOut), cudaMemcpyDeviceToHost, c->stream3));
+    CU(cudaMemcpyAsync(c->r_sing.p + c0 * nv, c->d_sing.p + c0 * nv, (size_t)n * nv * sizeof(double), cudaMemcpyDeviceToHost, c->stream3));
+    CU(cudaMemcpyAsync(c->r_row0.p + c0 * nA * nv, c->d_row0.p + c0 * nA * nv, (size_t)n * nA * nv * sizeof(double), cudaMemcpyDeviceToHost, c->stream3));
+    CU(cudaMemcpyAsync(c->r_l00.p + c0 * nA, c->d_l00.p + c0 * nA, (size_t)n * nA * sizeof(double), cudaMemcpyDeviceToHost, c->stream3));
+    if (sp.want_single) {
+      CU(cudaMemcpyAsync(c->r_p1.p + c0 * nv, c->d_p1.p + c0 * nv, (size_t)n * nv * sizeof(double), cudaMemcpyDeviceToHost, c->stream3));
+      CU(cudaMemcpyAsync(c->r_p1_0.p + c0, c->d_p1_0.p + c0, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream3));
+    }
+    if (dev_rescore)
+      CU(cudaMemcpyAsync(c->r_lists.p + c0, c->d_lists.p + c0, n * sizeof(RescList), cudaMemcpyDeviceToHost, c->stream3));
   }
-  if (dev_rescore && nc)
-    CU(cudaMemcpyAsync(c->r_lists.p, c->d_lists.p, nc * sizeof(RescList), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaEventRecord(c->ev[4], c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  c->st.d2h_bytes = nc * (int64_t)(sizeof(CellOut) + (dev_rescore ? sizeof(RescList) : 0)) + (int64_t)nc * nv * 8 * (1 + nA + (sp.want_single ? 1 : 0)) +
-                    nc * nA * 8 + (sp.want_single ? nc * 8 : 0);
-  float ms = 0;
-  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->st.prep_ms = ms;
-  cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->st.pair_kernel_ms = ms;
-  cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]); c->st.kernel_ms = ms;
-  cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); c->st.d2h_ms = ms;
+  return DMX_OK;
+}
 
-  // ---- finalise -----------------------------------------------------------------------------------
-  const double tf0 = now_ms();
+// The whole path.  `pipelined`: the host->device copies run on a second stream, chunk by chunk, under the kernels of
+// the previous chunks; in both modes the records of a chunk are read back and finalised on the host threads while the
+// device works on the next chunk.
+int run_path(dmx_ctx* c, bool pipelined) {
+  CU(cudaSetDevice(c->cfg.device));
+  const double t0 = now_ms();
+  const int nv = c->cfg.nv, nA = c->cfg.n_alpha;
+  const std::vector<int32_t>& order = pipelined ? c->order_p : c->order;
+  const std::vector<Chunk>& chunks = pipelined ? c->chunks_p : c->chunks;
+  const int64_t nc = c->ncells, nact = (int64_t)order.size();
+  const int T = (int)c->tt.size();
+  const int K = (int)chunks.size();
+  c->st.gpu_launches = 0;
+  c->st.n_rescored = 0;
+  c->st.n_fullcell = 0;
+
+  const int nd = (c->UQ - QHEAD) / QPLANE;
+  const bool fp32 = (c->cfg.flags & DMX_FP32_PAIRS) != 0;
+  const int64_t pstride = (c->E + NB) * FPLANE;
+  const bool exact = (c->cfg.flags & DMX_EXACT_TIES) != 0;
+  const bool dev_rescore = exact && c->gpu_exact && !(c->cfg.flags & DMX_HOST_FINALISE);
+  if (pipelined) {
+    const int rc = check_inputs(c);
+    if (rc != DMX_OK) return rc;
+    RC(reserve_inputs(c));
+  }
+  CU(c->d_entq.reserve((size_t)c->E * c->UQ + (size_t)NB * c->UQ + 2));   // slack: a stage always reads NB records
+  CU(c->d_ents.reserve((size_t)c->E * (2 + nd) + 2));
+  if (fp32) {
+    CU(c->d_entf_head.reserve((size_t)(c->E + NB) * FHEAD));
+    CU(c->d_entf_plane.reserve((size_t)pstride * std::max(nd, 1)));
+  }
+  CU(c->d_parts.reserve((size_t)nact * T + 1));
+  CU(c->d_row0.reserve((size_t)nc * nA * nv + 1)); CU(c->d_singA.reserve((size_t)nc * nv + 1));
+  CU(c->d_lb.reserve((size_t)nc * nv + 1)); CU(c->d_p1.reserve((size_t)nc * nv + 1));
+  CU(c->d_p1_0.reserve(nc + 1)); CU(c->d_l00.reserve((size_t)nc * nA + 1));
+  CU(c->d_sing.reserve((size_t)nc * nv + 1)); CU(c->d_out.reserve(nc + 1));
+  CU(c->r_out.reserve(nc + 1)); CU(c->r_sing.reserve((size_t)nc * nv + 1));
+  CU(c->r_row0.reserve((size_t)nc * nA * nv + 1)); CU(c->r_l00.reserve((size_t)nc * nA + 1));
+  CU(c->r_p1.reserve((size_t)nc * nv + 1)); CU(c->r_p1_0.reserve(nc + 1));
+  if (dev_rescore) {
+    CU(c->d_lists.reserve(nc + 1));
+    CU(c->r_lists.reserve(nc + 1));
+    CU(c->d_terms.reserve((size_t)c->E * RESC_FAST + 1));
+  }
+  if ((int)c->cev.size() < 6 * K + 4) {
+    const size_t old = c->cev.size();
+    c->cev.resize(6 * K + 4, nullptr);
+    for (size_t i = old; i < c->cev.size(); ++i) CU(cudaEventCreate(&c->cev[i]));
+  }
+  cudaEvent_t* ev_up = c->cev.data();            // [K + 2]: copies start, common inputs there, chunk k there
+  cudaEvent_t* ev_k = c->cev.data() + K + 2;     // [K][4] kernel phases, then [K] chunk read back
+  cudaEvent_t* ev_done = ev_k + 4 * K;
+  cudaEvent_t ev_first = c->cev[6 * K + 2], ev_last = c->cev[6 * K + 3];
+
+  int64_t h2d_bytes = 0;
+  if (pipelined) {
+    CU(cudaEventRecord(ev_up[0], c->stream2));
+    RC(upload_common(c, c->stream2, &h2d_bytes, order));
+    CU(cudaEventRecord(ev_up[1], c->stream2));
+    for (int k = 0; k < K; ++k) {
+      RC(upload_chunk(c, chunks[k], c->stream2, &h2d_bytes));
+      CU(cudaEventRecord(ev_up[2 + k], c->stream2));
+    }
+    c->gp_dirty = false;
+    c->plp_dirty = false;
+    c->uploaded = true;
+  }
+  if (!pipelined && !order.empty())   // dmx_run may have left its own schedule there
+    CU(cudaMemcpyAsync(c->d_order.p, order.data(), order.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaEventRecord(ev_first, c->stream));
+  // outputs of cells that are never scheduled stay zero (the reference prints zeros for them in .single)
+  CU(cudaMemsetAsync(c->d_p1.p, 0, (size_t)nc * nv * sizeof(double), c->stream));
+  CU(cudaMemsetAsync(c->d_p1_0.p, 0, (size_t)nc * sizeof(double), c->stream));
+  CU(cudaMemsetAsync(c->d_sing.p, 0, (size_t)nc * nv * sizeof(double), c->stream));
+  CU(cudaMemsetAsync(c->d_l00.p, 0, (size_t)nc * nA * sizeof(double), c->stream));
+  CU(cudaMemsetAsync(c->d_row0.p, 0, (size_t)nc * nA * nv * sizeof(double), c->stream));
+  CU(cudaMemsetAsync(c->d_out.p, 0, (size_t)nc * sizeof(CellOut), c->stream));
+  if (pipelined) CU(cudaStreamWaitEvent(c->stream, ev_up[1], 0));
+  CU(launch_gprow(c->d_gp.p, c->d_gprow.p, c->nsnps, nv, c->nvp, c->stream));
+  if (c->nsnps) c->st.gpu_launches += 1;
+  ScanParams sp;
+  fill_scan_params(c, &sp);
+  {
+    const int rc = encode_maps(c);
+    if (rc != DMX_OK) return rc;
+  }
+  for (int k = 0; k < K; ++k) {
+    if (pipelined) CU(cudaStreamWaitEvent(c->stream, ev_up[2 + k], 0));
+    const int rc = enqueue_chunk(c, chunks[k], sp, dev_rescore, ev_k + 4 * k);
+    if (rc != DMX_OK) return rc;
+    CU(cudaEventRecord(ev_done[k], c->stream3));
+  }
+  CU(cudaEventRecord(ev_last, c->stream));
+
+  // ---- finalise, chunk by chunk as the records arrive ---------------------------------------------------------
   c->best.assign(nc, dmx_best_rec());
   const HostView hv = host_view(c);
   const ExactScorer scorer(hv, c->err256);
@@ -812,18 +979,44 @@ int dmx_compute(dmx_ctx* c) {
     resc[tid] += r->n_rescored;
     resc_gpu[tid] += from_gpu;
   };
-  parallel_for(nc, nth, [&](int64_t cell, int tid) {
-    dmx_best_rec* r = &c->best[cell];
-    memset(r, 0, sizeof(*r));
-    r->status = c->status[cell];
-    r->n_snp = (int32_t)(c->h_cell_ptr[cell + 1] - c->h_cell_ptr[cell]);
-    if (r->status != 0) return;
-    const CellOut& co = c->r_out.p[cell];
-    if (co.ncand > MAX_CAND) { overflow[tid].push_back((int32_t)cell); return; }
-    std::vector<Hyp> cands;
-    expand_cands(c, co, &cands);
-    do_cell(cell, cands, tid);
-  });
+  double fin_ms = 0.0;
+  for (int k = 0; k < K; ++k) {
+    CU(cudaEventSynchronize(ev_done[k]));
+    const double tf0 = now_ms();
+    const int64_t c0 = chunks[k].c0, n = chunks[k].c1 - c0;
+    c->pool->run(n, nth, [&](int64_t i, int tid) {
+      const int64_t cell = c0 + i;
+      dmx_best_rec* r = &c->best[cell];
+      memset(r, 0, sizeof(*r));
+      r->status = c->status[cell];
+      r->n_snp = (int32_t)(c->h_cell_ptr[cell + 1] - c->h_cell_ptr[cell]);
+      if (r->status != 0) return;
+      const CellOut& co = c->r_out.p[cell];
+      if (co.ncand > MAX_CAND) { overflow[tid].push_back((int32_t)cell); return; }
+      std::vector<Hyp> cands;
+      expand_cands(c, co, &cands);
+      do_cell(cell, cands, tid);
+    });
+    fin_ms += now_ms() - tf0;
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaStreamSynchronize(c->stream3));
+  if (pipelined) CU(cudaStreamSynchronize(c->stream2));
+  c->st.d2h_bytes = nc * (int64_t)(sizeof(CellOut) + (dev_rescore ? sizeof(RescList) : 0)) + (int64_t)nc * nv * 8 * (1 + nA + (sp.want_single ? 1 : 0)) +
+                    nc * nA * 8 + (sp.want_single ? nc * 8 : 0);
+  float ms = 0;
+  c->st.prep_ms = 0; c->st.pair_kernel_ms = 0; c->st.d2h_ms = 0;
+  for (int k = 0; k < K; ++k) {
+    cudaEventElapsedTime(&ms, ev_k[4 * k], ev_k[4 * k + 1]); c->st.prep_ms += ms;
+    cudaEventElapsedTime(&ms, ev_k[4 * k + 1], ev_k[4 * k + 2]); c->st.pair_kernel_ms += ms;
+    cudaEventElapsedTime(&ms, ev_k[4 * k + 3], ev_done[k]); c->st.d2h_ms += ms;
+  }
+  cudaEventElapsedTime(&ms, ev_first, ev_last); c->st.kernel_ms = ms;   // first memset .. last kernel
+  if (pipelined) {
+    cudaEventElapsedTime(&ms, ev_up[0], ev_up[K + 1]); c->st.h2d_ms = ms;
+    c->st.h2d_bytes = h2d_bytes;
+  }
+  const double tf1 = now_ms();
   std::vector<int32_t> ov;
   for (auto& v : overflow) ov.insert(ov.end(), v.begin(), v.end());
   if (!ov.empty()) {
@@ -837,7 +1030,7 @@ int dmx_compute(dmx_ctx* c) {
       std::vector<int32_t> cells(ov.begin() + lo, ov.begin() + lo + n);
       int rc = dense_scan(c, cells, c->r_dense.p);
       if (rc != DMX_OK) return rc;
-      parallel_for((int64_t)n, nth, [&](int64_t i, int tid) {
+      c->pool->run((int64_t)n, nth, [&](int64_t i, int tid) {
         std::vector<Hyp> cands;
         const int64_t cl = cells[i];
         candidates_from_dense(c->r_dense.p + (size_t)i * per, nv, nA, 1, sp.eps_rel,
@@ -848,17 +1041,18 @@ int dmx_compute(dmx_ctx* c) {
     }
     c->st.n_fullcell = (int64_t)ov.size();
   }
+  fin_ms += now_ms() - tf1;
   c->st.n_rescored_gpu = 0;
   for (int t = 0; t < nth; ++t) { c->st.n_rescored += resc[t]; c->st.n_rescored_gpu += resc_gpu[t]; }
   c->st.gpu_exact = c->gpu_exact ? 1 : 0;
-  c->st.finalise_ms = now_ms() - tf0;
+  c->st.finalise_ms = fin_ms;
   c->st.n_entries = c->E;
   c->st.n_reads = c->R;
   c->st.n_tasks = nact * T;
   // SURVEY 8(d) gather model: per entry 12*nv (GP row) + 12 (gp0 row) + 4 (snp id) + 2*reads
   c->st.algo_bytes = 0;
   for (int64_t i = 0; i < nact; ++i) {
-    const int32_t cell = c->order[i];
+    const int32_t cell = order[i];
     const int64_t e0 = c->h_cell_ptr[cell], e1 = c->h_cell_ptr[cell + 1];
     c->st.algo_bytes += (double)(e1 - e0) * (12.0 * nv + 16.0) + 2.0 * (double)(c->h_ent_ptr[e1] - c->h_ent_ptr[e0]) +
                         8.0 + 200.0 + 8.0 * nv;
@@ -867,15 +1061,43 @@ int dmx_compute(dmx_ctx* c) {
   c->computed = true;
   return DMX_OK;
 }
+}  // namespace
 
+int dmx_upload(dmx_ctx* c) {
+  if (!c) return DMX_E_INVALID;
+  if (!c->have_gp || !c->have_plp) return DMX_E_STATE;
+  CU(cudaSetDevice(c->cfg.device));
+  const double t0 = now_ms();
+  int64_t bytes = 0;
+  {
+    const int rc = check_inputs(c);
+    if (rc != DMX_OK) return rc;
+  }
+  RC(reserve_inputs(c));
+  RC(upload_common(c, c->stream, &bytes, c->order));
+  for (const Chunk& ck : c->chunks) RC(upload_chunk(c, ck, c->stream, &bytes));
+  c->gp_dirty = false;
+  c->plp_dirty = false;
+  CU(cudaStreamSynchronize(c->stream));
+  c->st.h2d_ms = now_ms() - t0;
+  c->st.h2d_bytes = bytes;
+  c->uploaded = true;
+  c->computed = false;
+  return DMX_OK;
+}
+
+int dmx_compute(dmx_ctx* c) {
+  if (!c) return DMX_E_INVALID;
+  if (!c->uploaded) return DMX_E_STATE;
+  return run_path(c, false);
+}
+
+// host buffers in, records out: copies, kernels and the finaliser overlap chunk by chunk
 int dmx_run(dmx_ctx* c) {
   if (!c) return DMX_E_INVALID;
-  int rc = dmx_upload(c);
-  if (rc != DMX_OK) return rc;
-  const double up = c->st.h2d_ms;
-  rc = dmx_compute(c);
-  if (rc == DMX_OK) c->st.total_ms += up;
-  return rc;
+  if (!c->have_gp || !c->have_plp) return DMX_E_STATE;
+  if (!c->gp_dirty && !c->plp_dirty && c->uploaded) return run_path(c, false);
+  return run_path(c, true);
 }
 
 int dmx_get_best(dmx_ctx* c, dmx_best_rec* out) {

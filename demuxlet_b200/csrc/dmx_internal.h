@@ -184,7 +184,7 @@ struct EntqParams {
   int32_t gp_stride;           // floats per GP row
   const float* gprow;          // GP rows with the gp0 prefix (gprow_kernel)
   const int32_t* ent_snp;
-  int64_t E;
+  int64_t E0, E;               // entries [E0, E) of this launch
   const int64_t* ent_ptr;
   const uint16_t* reads;
   double* entq;

@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(256) entq_kernel(const __grid_constant__ EntqP
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPE;
   const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t e = gw * (32 / LPE) + lane / LPE;
+  const int64_t e = p.E0 + gw * (32 / LPE) + lane / LPE;
   if (e >= p.E) return;   // whole groups leave together
   const unsigned gmask = (LPE == 32) ? 0xffffffffu : (((1u << LPE) - 1u) << (lane - sub));
   double P[VPL], pu[VPL];
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(128) entq1_kernel(const __grid_constant__ Entq
   __shared__ double s_val[UMAX][128];
   for (int i = threadIdx.x; i < 256; i += 128) { s_err[i] = c_err[i]; s_err3[i] = c_err3[i]; }
   __syncthreads();
-  const int64_t e = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  const int64_t e = p.E0 + (int64_t)blockIdx.x * 128 + threadIdx.x;
   if (e >= p.E) return;
   const int nu = p.U;
   double P[UMAX], pu[UMAX], qu[UMAX];
@@ -439,10 +439,11 @@ __global__ void __launch_bounds__(128) entq1_kernel(const __grid_constant__ Entq
 }
 
 int launch_entq(const EntqParams& p, void* stream) {
-  if (p.E == 0) return 0;
+  const int64_t n = p.E - p.E0;
+  if (n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  auto grid = [&](int lpe) { return (unsigned)((p.E * lpe + 255) / 256); };
-  const unsigned g1 = (unsigned)((p.E + 127) / 128);
+  auto grid = [&](int lpe) { return (unsigned)((n * lpe + 255) / 256); };
+  const unsigned g1 = (unsigned)((n + 127) / 128);
   if (p.U <= 5) entq1_kernel<5><<<g1, 128, 0, st>>>(p);
   else if (p.U <= 8) entq1_kernel<8><<<g1, 128, 0, st>>>(p);
   else if (p.U <= 16) entq_kernel<16, 1><<<grid(16), 256, 0, st>>>(p);
