@@ -114,6 +114,24 @@ def make_workload(name: str, rank: int, scale: float):
 
 
 # -------------------------------------------------------------------------------------------------
+def fp_roofline(plp, alphas, pair_s, fp32, clocks):
+    """the pair scan against the arithmetic roofline that actually binds it: useful multiply-adds per second vs
+    the SM's issue peak (148 SMs x 128 FP32 or 64 FP64 lanes x 2 flop x SM clock)"""
+    nv = plp.nv
+    hyp = 0
+    for n, a in enumerate(alphas):
+        if n == 0 and a == 0.0:
+            continue                      # separable plane: no pair work
+        hyp += nv * (nv + 1) // 2 if a == 0.5 else nv * nv
+    flop = float(plp.n_entries) * hyp * 7.0          # 3 mul + 2 add for the dot, 1 mul into the product (+1 FMA slot)
+    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    peak = 148 * (128 if fp32 else 64) * 2 * mhz * 1e6 / 1e12
+    ach = flop / pair_s / 1e12
+    return {"bound": "fp32 pipe" if fp32 else "fp64 pipe", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+            "frac": ach / peak, "flop_per_launch": flop,
+            "note": "7 flop per hypothesis and pileup entry (4 issue slots); peak = 148 SMs x lanes x 2 x SM clock"}
+
+
 def cpu_baseline(plp, alphas, budget_s: float = 15.0):
     """the CPU oracle (restatement of the reference loop) on a bounded sample of the same cells"""
     from oracle import pyoracle as po
@@ -239,8 +257,8 @@ def run_ours(args):
     gp = pin(plp.gp)
     arrays = [pin(x) for x in (plp.cell_ptr, plp.ent_snp, plp.ent_ptr, plp.reads, plp.totl, plp.npass, plp.uniq)]
 
-    d = api.Demuxlet(plp.nv, alphas, device=local_rank, borrow=True, trust_inputs=True,
-                     fp32_pairs=args.fp32_pairs)
+    fp32 = not args.fp64_pairs
+    d = api.Demuxlet(plp.nv, alphas, device=local_rank, borrow=True, trust_inputs=True, fp32_pairs=fp32)
     d.set_gp(gp)
     d.set_pileup_arrays(*arrays)
 
@@ -331,7 +349,9 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32+f64" if args.fp32_pairs else "f64", "data": "synthetic (synth-v1, SURVEY 8d)",
+        "dtype": "f32 pair products + f64 logs / exact re-score" if fp32 else "f64", "data": "synthetic (synth-v1, SURVEY 8d)",
+        "timing": "host wall clock between device synchronisations (a step ends with the host-side tie finaliser), max "
+                  "over ranks; kernel times below from CUDA events on the library's own stream",
         "config": {"workload": workload_name(args), "alpha": list(map(float, alphas)),
                    "cells_per_gpu": ncells, "entries_per_gpu": int(plp.n_entries), "parallelism": "barcode shards x%d" % world,
                    "l2": "no flush: inputs larger than L2 (%.2f GB of CSR + entry tables streamed per step)" %
@@ -341,10 +361,14 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(st2["d2h_bytes"]) * world, "ms_per_step": dt2 / args.steps * 1e3,
                 "h2d_ms": st2["h2d_ms"], "kernel_ms": st2["kernel_ms"], "finalise_ms": st2["finalise_ms"]},
         "gpu_launches": int(st["gpu_launches"]) * args.steps,
-        "roofline": {"bound": "hbm", "kernel": "pair_scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "pair_scan_f32_kernel" if fp32 else "pair_scan_kernel",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algo_bytes_per_launch": st["algo_bytes"], "kernel_ms": pair_s * 1e3,
-                     "note": "FP64-pipe bound at nv=64 (SURVEY 8d): GP matrix is L2 resident, DRAM traffic << gather-model bytes"},
+                     "note": "gather-model bytes (SURVEY 8d) / CUDA-event time; at nv=64 the kernel is bound by the SM's "
+                             "%s issue rate, not by HBM: the 77 MB GP matrix is L2 resident, DRAM traffic << gather-model "
+                             "bytes (DESIGN.md 6)" % ("FP32" if fp32 else "FP64")},
+        "roofline_fp": fp_roofline(plp, alphas, pair_s, fp32, clocks),
         "breakdown_ms": {"prep": float(np.mean(prep_ms)), "pair_scan": float(np.mean(pair_ms)),
                          "all_kernels": float(np.mean(kern_ms)), "d2h": st["d2h_ms"], "finalise_host": float(np.mean(fin_ms)),
                          "rescored_hypotheses": int(st["n_rescored"]), "host_threads": os.cpu_count()},
@@ -366,7 +390,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the workload's barcodes (debug)")
-    ap.add_argument("--fp32-pairs", action="store_true")
+    ap.add_argument("--fp64-pairs", action="store_true",
+                    help="pair scan on the FP64 tensor path (DMMA) instead of fp32 products")
+    ap.add_argument("--fp32-pairs", action="store_true", help="(default; kept for old command lines)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
