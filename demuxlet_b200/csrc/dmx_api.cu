@@ -762,7 +762,7 @@ int upload_chunk(dmx_ctx* c, const Chunk& ck, cudaStream_t st, int64_t* bytes) {
 }
 
 // ---- the kernels of one chunk (a contiguous cell-id range; its active cells are order[o0, o1)) ----------------------
-int enqueue_chunk(dmx_ctx* c, const Chunk& ck, const ScanParams& sp0, bool dev_rescore, cudaEvent_t* ev /* [4] */) {
+int enqueue_chunk(dmx_ctx* c, const Chunk& ck, const ScanParams& sp0, bool dev_rescore, cudaEvent_t* ev /* [5] */) {
   const int nv = c->cfg.nv, nA = c->cfg.n_alpha;
   const int T = (int)c->tt.size();
   const int nd = (c->UQ - QHEAD) / QPLANE;
@@ -831,13 +831,31 @@ int enqueue_chunk(dmx_ctx* c, const Chunk& ck, const ScanParams& sp0, bool dev_r
     mp.lists = c->d_lists.p;
     for (int n = 0; n < nA; ++n) mp.mode[n] = c->pg.mode[n];
   }
+  // read back on the third stream as soon as each array is final (all per-cell arrays are indexed by cell id: one
+  // contiguous slice per chunk): the scan's outputs while merge and the re-scorer run, the rest after them
+  const int64_t c0 = ck.c0, n = ck.c1 - ck.c0;
+  if (n > 0) {
+    CU(cudaStreamWaitEvent(c->stream3, ev[2], 0));
+    CU(cudaMemcpyAsync(c->r_row0.p + c0 * nA * nv, c->d_row0.p + c0 * nA * nv, (size_t)n * nA * nv * sizeof(double), cudaMemcpyDeviceToHost, c->stream3));
+    CU(cudaMemcpyAsync(c->r_l00.p + c0 * nA, c->d_l00.p + c0 * nA, (size_t)n * nA * sizeof(double), cudaMemcpyDeviceToHost, c->stream3));
+    if (sp.want_single) {
+      CU(cudaMemcpyAsync(c->r_p1.p + c0 * nv, c->d_p1.p + c0 * nv, (size_t)n * nv * sizeof(double), cudaMemcpyDeviceToHost, c->stream3));
+      CU(cudaMemcpyAsync(c->r_p1_0.p + c0, c->d_p1_0.p + c0, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream3));
+    }
+  }
   CU(launch_merge(mp, nact, c->stream));
   if (nact) c->st.gpu_launches += 2;
+  CU(cudaEventRecord(ev[4], c->stream));
+  if (n > 0) {
+    CU(cudaStreamWaitEvent(c->stream3, ev[4], 0));
+    CU(cudaMemcpyAsync(c->r_sing.p + c0 * nv, c->d_sing.p + c0 * nv, (size_t)n * nv * sizeof(double), cudaMemcpyDeviceToHost, c->stream3));
+    CU(cudaMemcpyAsync(c->r_out.p + c0, c->d_out.p + c0, n * sizeof(CellOut), cudaMemcpyDeviceToHost, c->stream3));
+  }
   if (dev_rescore) {
     RescoreParams rp;
     memset(&rp, 0, sizeof(rp));
     rp.nv = nv; rp.gp_stride = c->nvp * 3 + 8; rp.nA = nA; rp.UQ = c->UQ; rp.sep0 = c->pg.sep0;
-    for (int n = 0; n < nA; ++n) rp.dense_idx[n] = (int8_t)c->dense_idx[n];
+    for (int n2 = 0; n2 < nA; ++n2) rp.dense_idx[n2] = (int8_t)c->dense_idx[n2];
     rp.gp = c->d_gprow.p + 8; rp.ent_snp = c->d_ent_snp.p; rp.entq = c->d_entq.p; rp.cell_ptr = c->d_cell_ptr.p;
     rp.cell_order = sp.cell_order; rp.lists = c->d_lists.p;
     rp.terms = c->d_terms.p;
@@ -845,20 +863,9 @@ int enqueue_chunk(dmx_ctx* c, const Chunk& ck, const ScanParams& sp0, bool dev_r
     if (nact) c->st.gpu_launches += 2 * (RMAX / RESC_FAST);
   }
   CU(cudaEventRecord(ev[3], c->stream));
-  // read back the chunk's records (all per-cell arrays are indexed by cell id: one contiguous slice each)
-  CU(cudaStreamWaitEvent(c->stream3, ev[3], 0));
-  const int64_t c0 = ck.c0, n = ck.c1 - ck.c0;
-  if (n > 0) {
-    CU(cudaMemcpyAsync(c->r_out.p + c0, c->d_out.p + c0, n * sizeof(CellOut), cudaMemcpyDeviceToHost, c->stream3));
-    CU(cudaMemcpyAsync(c->r_sing.p + c0 * nv, c->d_sing.p + c0 * nv, (size_t)n * nv * sizeof(double), cudaMemcpyDeviceToHost, c->stream3));
-    CU(cudaMemcpyAsync(c->r_row0.p + c0 * nA * nv, c->d_row0.p + c0 * nA * nv, (size_t)n * nA * nv * sizeof(double), cudaMemcpyDeviceToHost, c->stream3));
-    CU(cudaMemcpyAsync(c->r_l00.p + c0 * nA, c->d_l00.p + c0 * nA, (size_t)n * nA * sizeof(double), cudaMemcpyDeviceToHost, c->stream3));
-    if (sp.want_single) {
-      CU(cudaMemcpyAsync(c->r_p1.p + c0 * nv, c->d_p1.p + c0 * nv, (size_t)n * nv * sizeof(double), cudaMemcpyDeviceToHost, c->stream3));
-      CU(cudaMemcpyAsync(c->r_p1_0.p + c0, c->d_p1_0.p + c0, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream3));
-    }
-    if (dev_rescore)
-      CU(cudaMemcpyAsync(c->r_lists.p + c0, c->d_lists.p + c0, n * sizeof(RescList), cudaMemcpyDeviceToHost, c->stream3));
+  if (n > 0 && dev_rescore) {
+    CU(cudaStreamWaitEvent(c->stream3, ev[3], 0));
+    CU(cudaMemcpyAsync(c->r_lists.p + c0, c->d_lists.p + c0, n * sizeof(RescList), cudaMemcpyDeviceToHost, c->stream3));
   }
   return DMX_OK;
 }
@@ -908,15 +915,15 @@ int run_path(dmx_ctx* c, bool pipelined) {
     CU(c->r_lists.reserve(nc + 1));
     CU(c->d_terms.reserve((size_t)c->E * RESC_FAST + 1));
   }
-  if ((int)c->cev.size() < 6 * K + 4) {
+  if ((int)c->cev.size() < 7 * K + 4) {
     const size_t old = c->cev.size();
-    c->cev.resize(6 * K + 4, nullptr);
+    c->cev.resize(7 * K + 4, nullptr);
     for (size_t i = old; i < c->cev.size(); ++i) CU(cudaEventCreate(&c->cev[i]));
   }
   cudaEvent_t* ev_up = c->cev.data();            // [K + 2]: copies start, common inputs there, chunk k there
-  cudaEvent_t* ev_k = c->cev.data() + K + 2;     // [K][4] kernel phases, then [K] chunk read back
-  cudaEvent_t* ev_done = ev_k + 4 * K;
-  cudaEvent_t ev_first = c->cev[6 * K + 2], ev_last = c->cev[6 * K + 3];
+  cudaEvent_t* ev_k = c->cev.data() + K + 2;     // [K][5] kernel phases, then [K] chunk read back
+  cudaEvent_t* ev_done = ev_k + 5 * K;
+  cudaEvent_t ev_first = c->cev[7 * K + 2], ev_last = c->cev[7 * K + 3];
 
   int64_t h2d_bytes = 0;
   if (pipelined) {
@@ -952,7 +959,7 @@ int run_path(dmx_ctx* c, bool pipelined) {
   }
   for (int k = 0; k < K; ++k) {
     if (pipelined) CU(cudaStreamWaitEvent(c->stream, ev_up[2 + k], 0));
-    const int rc = enqueue_chunk(c, chunks[k], sp, dev_rescore, ev_k + 4 * k);
+    const int rc = enqueue_chunk(c, chunks[k], sp, dev_rescore, ev_k + 5 * k);
     if (rc != DMX_OK) return rc;
     CU(cudaEventRecord(ev_done[k], c->stream3));
   }
@@ -1007,9 +1014,9 @@ int run_path(dmx_ctx* c, bool pipelined) {
   float ms = 0;
   c->st.prep_ms = 0; c->st.pair_kernel_ms = 0; c->st.d2h_ms = 0;
   for (int k = 0; k < K; ++k) {
-    cudaEventElapsedTime(&ms, ev_k[4 * k], ev_k[4 * k + 1]); c->st.prep_ms += ms;
-    cudaEventElapsedTime(&ms, ev_k[4 * k + 1], ev_k[4 * k + 2]); c->st.pair_kernel_ms += ms;
-    cudaEventElapsedTime(&ms, ev_k[4 * k + 3], ev_done[k]); c->st.d2h_ms += ms;
+    cudaEventElapsedTime(&ms, ev_k[5 * k], ev_k[5 * k + 1]); c->st.prep_ms += ms;
+    cudaEventElapsedTime(&ms, ev_k[5 * k + 1], ev_k[5 * k + 2]); c->st.pair_kernel_ms += ms;
+    cudaEventElapsedTime(&ms, ev_k[5 * k + 3], ev_done[k]); c->st.d2h_ms += ms;   // read back not hidden by kernels
   }
   cudaEventElapsedTime(&ms, ev_first, ev_last); c->st.kernel_ms = ms;   // first memset .. last kernel
   if (pipelined) {

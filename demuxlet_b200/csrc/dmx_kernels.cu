@@ -1476,7 +1476,11 @@ __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_f32_kernel(cons
   }
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(F_REGS_HI));
   if (warp >= F_NCW) {
+#ifdef DMX_ROLLED
+    transform_role_f32<false>(p, pp, ts, warp - F_NCW, lane, u, NS);
+#else
     transform_role_f32<true>(p, pp, ts, warp - F_NCW, lane, u, NS);
+#endif
   } else {
     // =============================== consumer warps ============================================
     // logical consumer index: 0..6 own the 28 off-diagonal tile positions of a triangular task, 7 and 8 (physical

@@ -1,0 +1,205 @@
+// dmx_main.cpp -- command line driver of the hot path: demuxlet's options, libdmx underneath.
+//
+// The reference's main() (cmd_cram_demuxlet.cpp:15-883) reads a BAM and a VCF through htslib, builds the pileup
+// (sc_dropseq_lib_t) and then runs lines 386-881.  This driver keeps the option names and the four output files of
+// that program for the part that is in scope: it takes the finished pileup as a flat file (--plp, the .dmxp
+// container of demuxlet_b200/plp.py: GP matrix + CSR pileup + barcodes + sample ids, i.e. exactly what crosses the
+// C ABI) and calls dmx_set_gp / dmx_set_pileup / dmx_run / dmx_write_outputs.  --sam / --vcf are recognised and
+// refused with a clear message: BAM/VCF reading needs htslib, which is not part of this build.
+//
+//   dmx-demuxlet --plp in.dmxp --out prefix [--alpha A]... [--doublet-prior P] [--min-total N] [--min-uniq N]
+//                [--min-snp N] [--group-list FILE] [--write-pair] [--gpu D] [--fp64-pairs] [--verbose]
+//
+// Options and defaults follow cmd_cram_demuxlet.cpp:29-33,:54-56,:64-71,:78-90 (alpha grid {0, 0.5} when none is
+// given; barcodes restricted to --group-list like :68,:131-140).  Exit status 0 on success, 1 on error with the
+// reference's "[E:...]" style message on stderr (Error.cpp:27-41).
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/dmx.h"
+
+namespace {
+[[noreturn]] void die(const char* fmt, const char* a = "", const char* b = "") {
+  fprintf(stderr, "\nFATAL ERROR - \n[E:dmx-demuxlet] ");
+  fprintf(stderr, fmt, a, b);
+  fprintf(stderr, "\n");
+  exit(1);
+}
+
+struct Plp {
+  int64_t nv = 0, nsnps = 0, ncells = 0, E = 0, R = 0;
+  std::vector<float> gp;
+  std::vector<int64_t> cell_ptr, ent_ptr;
+  std::vector<int32_t> ent_snp, totl, npass, uniq;
+  std::vector<uint16_t> reads;
+  std::vector<std::string> barcodes, samples;
+};
+
+template <class T>
+void rd(FILE* f, std::vector<T>* v, size_t n, const char* path) {
+  v->resize(n);
+  if (n && fread(v->data(), sizeof(T), n, f) != n) die("Truncated pileup file %s", path);
+}
+
+void load_plp(const char* path, Plp* p) {
+  FILE* f = fopen(path, "rb");
+  if (!f) die("Cannot open file %s for reading", path);
+  char magic[8];
+  int64_t h[5];
+  if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "DMXPLP01", 8) != 0) die("%s is not a DMXPLP01 pileup file", path);
+  if (fread(h, 8, 5, f) != 5) die("Truncated pileup file %s", path);
+  p->nv = h[0]; p->nsnps = h[1]; p->ncells = h[2]; p->E = h[3]; p->R = h[4];
+  if (p->nv < 0 || p->nsnps < 0 || p->ncells < 0 || p->E < 0 || p->R < 0) die("Corrupt header in %s", path);
+  rd(f, &p->gp, (size_t)p->nsnps * p->nv * 3, path);
+  rd(f, &p->cell_ptr, (size_t)p->ncells + 1, path);
+  rd(f, &p->ent_snp, (size_t)p->E, path);
+  rd(f, &p->ent_ptr, (size_t)p->E + 1, path);
+  rd(f, &p->reads, (size_t)p->R, path);
+  rd(f, &p->totl, (size_t)p->ncells, path);
+  rd(f, &p->npass, (size_t)p->ncells, path);
+  rd(f, &p->uniq, (size_t)p->ncells, path);
+  std::string cur;
+  int c;
+  std::vector<std::string> names;
+  while ((c = fgetc(f)) != EOF) {
+    if (c == 0) { names.push_back(cur); cur.clear(); }
+    else cur.push_back((char)c);
+  }
+  fclose(f);
+  if ((int64_t)names.size() != p->ncells + p->nv) die("Barcode / sample id table of %s has the wrong length", path);
+  p->barcodes.assign(names.begin(), names.begin() + p->ncells);
+  p->samples.assign(names.begin() + p->ncells, names.end());
+}
+
+// --group-list (:68, :131-140): keep only the listed barcodes; cell order is preserved
+void restrict_to_groups(const char* path, Plp* p) {
+  FILE* f = fopen(path, "r");
+  if (!f) die("Cannot open file %s for reading", path);
+  std::set<std::string> keep;
+  char line[4096];
+  while (fgets(line, sizeof(line), f)) {
+    size_t n = strcspn(line, " \t\r\n");
+    if (n) keep.insert(std::string(line, n));
+  }
+  fclose(f);
+  Plp q;
+  q.nv = p->nv; q.nsnps = p->nsnps;
+  q.gp.swap(p->gp);
+  q.samples = p->samples;
+  q.cell_ptr.push_back(0);
+  q.ent_ptr.push_back(0);
+  for (int64_t i = 0; i < p->ncells; ++i) {
+    if (!keep.count(p->barcodes[i])) continue;
+    for (int64_t e = p->cell_ptr[i]; e < p->cell_ptr[i + 1]; ++e) {
+      q.ent_snp.push_back(p->ent_snp[e]);
+      for (int64_t r = p->ent_ptr[e]; r < p->ent_ptr[e + 1]; ++r) q.reads.push_back(p->reads[r]);
+      q.ent_ptr.push_back((int64_t)q.reads.size());
+    }
+    q.cell_ptr.push_back((int64_t)q.ent_snp.size());
+    q.totl.push_back(p->totl[i]); q.npass.push_back(p->npass[i]); q.uniq.push_back(p->uniq[i]);
+    q.barcodes.push_back(p->barcodes[i]);
+  }
+  q.ncells = (int64_t)q.barcodes.size();
+  q.E = (int64_t)q.ent_snp.size();
+  q.R = (int64_t)q.reads.size();
+  *p = std::move(q);
+}
+
+void usage() {
+  fprintf(stderr,
+          "dmx-demuxlet: demuxlet's genotype-likelihood scan on B200 (libdmx)\n"
+          "  --plp FILE          flat pileup (.dmxp): GP matrix + (barcode, snp, allele, BQ) table   [required]\n"
+          "  --out PREFIX        output prefix: PREFIX.best .single .sing2 [.pair]                     [required]\n"
+          "  --alpha A           grid of alpha, repeatable (default 0 and 0.5)\n"
+          "  --doublet-prior P   prior of doublet (default 0.5)\n"
+          "  --min-total N / --min-uniq N / --min-snp N   per-barcode filters (default 0)\n"
+          "  --group-list FILE   only the barcodes listed in FILE\n"
+          "  --write-pair        also write the (huge) PREFIX.pair\n"
+          "  --gpu D             CUDA device ordinal (default 0)\n"
+          "  --fp64-pairs        pair scan in fp64 (default: fp32 products, exact re-score of the decisive values)\n"
+          "  --sam / --vcf / --field ...   BAM/VCF input needs htslib and is not part of this build\n");
+}
+}  // namespace
+
+int main(int argc, char** argv) {
+  const char *plp_path = nullptr, *out = nullptr, *groups = nullptr;
+  std::vector<double> alpha;
+  double prior = 0.5;
+  int min_total = 0, min_uniq = 0, min_snp = 0, gpu = 0, write_pair = 0, verbose = 0, fp64 = 0;
+  for (int i = 1; i < argc; ++i) {
+    const std::string a = argv[i];
+    auto val = [&]() -> const char* {
+      if (i + 1 >= argc) die("Missing value for option %s", argv[i]);
+      return argv[++i];
+    };
+    if (a == "--plp") plp_path = val();
+    else if (a == "--out") out = val();
+    else if (a == "--alpha") alpha.push_back(atof(val()));
+    else if (a == "--doublet-prior") prior = atof(val());
+    else if (a == "--min-total") min_total = atoi(val());
+    else if (a == "--min-uniq") min_uniq = atoi(val());
+    else if (a == "--min-snp") min_snp = atoi(val());
+    else if (a == "--group-list") groups = val();
+    else if (a == "--write-pair") write_pair = 1;
+    else if (a == "--gpu") gpu = atoi(val());
+    else if (a == "--fp64-pairs") fp64 = 1;
+    else if (a == "--verbose") verbose = 1;
+    else if (a == "--help" || a == "-h") { usage(); return 0; }
+    else if (a == "--sam" || a == "--vcf" || a == "--field" || a == "--tag-group" || a == "--tag-UMI" || a == "--sm" ||
+             a == "--sm-list")
+      die("Option %s: BAM/VCF input is read through htslib, which this build does not have; build the pileup with "
+          "demuxlet's reader and pass it with --plp (INTEGRATION.md)", argv[i]);
+    else die("Unrecognized option %s", argv[i]);
+  }
+  if (!plp_path || !out) { usage(); die("--plp and --out are required"); }
+  if (alpha.empty()) { alpha.push_back(0.0); alpha.push_back(0.5); }   // :78-90
+
+  Plp p;
+  load_plp(plp_path, &p);
+  if (groups) restrict_to_groups(groups, &p);
+  if (verbose)
+    fprintf(stderr, "NOTICE - %lld droplets, %lld SNPs, %lld samples, %lld (droplet, SNP) entries, %lld reads\n",
+            (long long)p.ncells, (long long)p.nsnps, (long long)p.nv, (long long)p.E, (long long)p.R);
+
+  dmx_config cfg;
+  dmx_config_default(&cfg);
+  cfg.nv = (int32_t)p.nv;
+  cfg.n_alpha = (int32_t)alpha.size();
+  cfg.alpha = alpha.data();
+  cfg.doublet_prior = prior;
+  cfg.min_total = min_total; cfg.min_uniq = min_uniq; cfg.min_snp = min_snp;
+  cfg.device = gpu;
+  if (!fp64) cfg.flags |= DMX_FP32_PAIRS;
+  dmx_ctx* ctx = nullptr;
+  int rc = dmx_create(&ctx, &cfg);
+  if (rc == DMX_OK) rc = dmx_set_gp(ctx, p.gp.data(), p.nsnps);
+  if (rc == DMX_OK)
+    rc = dmx_set_pileup(ctx, p.ncells, p.cell_ptr.data(), p.ent_snp.data(), p.ent_ptr.data(), p.reads.data(),
+                        p.totl.data(), p.npass.data(), p.uniq.data());
+  if (rc == DMX_OK) rc = dmx_run(ctx);
+  if (rc == DMX_OK) {
+    std::vector<const char*> bcs(p.ncells), sms(p.nv);
+    for (int64_t i = 0; i < p.ncells; ++i) bcs[i] = p.barcodes[i].c_str();
+    for (int64_t j = 0; j < p.nv; ++j) sms[j] = p.samples[j].c_str();
+    rc = dmx_write_outputs(ctx, bcs.data(), sms.data(), out, write_pair);
+  }
+  if (rc != DMX_OK) {
+    const std::string why = std::string(dmx_strerror(rc)) + (rc == DMX_E_CUDA ? std::string(": ") + dmx_last_error() : "");
+    dmx_destroy(ctx);
+    die("libdmx: %s", why.c_str());
+  }
+  if (verbose) {
+    dmx_stats st;
+    dmx_get_stats(ctx, &st);
+    fprintf(stderr, "NOTICE - %lld kernel launches, copies %.2f ms, kernels %.2f ms (pair scan %.2f ms), finaliser %.2f ms\n",
+            (long long)st.gpu_launches, st.h2d_ms, st.kernel_ms, st.pair_kernel_ms, st.finalise_ms);
+  }
+  dmx_destroy(ctx);
+  return 0;
+}

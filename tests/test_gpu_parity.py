@@ -160,3 +160,41 @@ def test_full_size_properties():
         assert np.array_equal(ref[of], a[gf][cells]), gf
     assert np.array_equal(ref["pair_llk12"], a["llk12"][cells])
     assert np.abs(ref["pair_llk10"] - a["llk10"][cells]).max() < 1e-4
+
+
+@pytest.mark.parametrize("name", ["gp6", "gp6filt", "gt2"])
+def test_cli_reproduces_reference_files(name, tmp_path):
+    """dmx-demuxlet (C++ driver over the C ABI) with demuxlet's options on a golden pileup: the four files against
+    the ones the reference's code wrote; then --group-list keeps exactly the listed barcodes"""
+    import json
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = os.path.join(os.path.dirname(here), "demuxlet_b200", "dmx-demuxlet")
+    m = json.load(open(os.path.join(here, "golden", "manifest.json")))[name]
+    gold = os.path.join(here, "golden", name)
+    cmd = [exe, "--plp", gold + ".dmxp", "--out", str(tmp_path / "c"), "--write-pair", "--fp64-pairs"]
+    for a in m["alphas"]:
+        cmd += ["--alpha", repr(float(a))]
+    for opt, key in (("--doublet-prior", "doublet_prior"), ("--min-total", "min_total"), ("--min-uniq", "min_uniq"),
+                     ("--min-snp", "min_snp")):
+        if key in m:
+            cmd += [opt, str(m[key])]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    diff_tsv(gold + ".best", tmp_path / "c.best", BEST_EXACT)
+    for ext in ("single", "sing2", "pair"):
+        diff_tsv(gold + "." + ext, tmp_path / ("c." + ext), ROW_EXACT)
+    # --group-list: every second barcode of the .best file
+    rows = open(gold + ".best").read().splitlines()
+    bcs = [ln.split("\t")[0] for ln in rows[1:]][::2]
+    (tmp_path / "groups.txt").write_text("\n".join(bcs) + "\n")
+    r = subprocess.run(cmd[:4] + [str(tmp_path / "g")] + cmd[5:] + ["--group-list", str(tmp_path / "groups.txt")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = open(tmp_path / "g.best").read().splitlines()
+    want = [rows[0]] + [ln for ln in rows[1:] if ln.split("\t")[0] in set(bcs)]
+    assert [ln.split("\t")[0] for ln in got] == [ln.split("\t")[0] for ln in want]
+    for a, b in zip(got[1:], want[1:]):
+        fa, fb = a.split("\t"), b.split("\t")
+        for i in (0, 1, 2, 3, 4, 5, 6, 8, 11, 12, 13):   # identity columns incl. BEST / SNG.1ST / DBL.1ST / DBL.2ND / ALPHA
+            assert fa[i] == fb[i], (i, a, b)

@@ -115,3 +115,27 @@ def test_sharded_allgather_gloo_world2():
     out = mgr.dict()
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     assert out[0] and out[1]
+
+
+def _cli():
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return os.path.join(here, "demuxlet_b200", "dmx-demuxlet")
+
+
+def test_cli_option_handling_without_a_device():
+    """the command line driver keeps demuxlet's option names; BAM/VCF input (htslib) is refused with a message,
+    unknown options and a missing --plp/--out are errors (no GPU needed for any of this)"""
+    import subprocess
+    exe = _cli()
+    if not os.path.exists(exe):
+        pytest.skip("dmx-demuxlet not built")
+    r = subprocess.run([exe, "--help"], capture_output=True, text=True)
+    assert r.returncode == 0 and "--alpha" in r.stderr and "--group-list" in r.stderr and "--write-pair" in r.stderr
+    r = subprocess.run([exe, "--sam", "x.bam", "--vcf", "y.vcf", "--out", "o"], capture_output=True, text=True)
+    assert r.returncode == 1 and "htslib" in r.stderr
+    r = subprocess.run([exe, "--bogus"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Unrecognized option" in r.stderr
+    r = subprocess.run([exe, "--out", "o"], capture_output=True, text=True)
+    assert r.returncode == 1 and "--plp" in r.stderr
+    r = subprocess.run([exe, "--plp", "/nonexistent.dmxp", "--out", "o"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Cannot open" in r.stderr
