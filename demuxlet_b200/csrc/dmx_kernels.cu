@@ -1378,38 +1378,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_scan_kernel(const __grid_con
   }
 }
 
-// S[i][c] = a_i . w_c and acc *= S for one 8 x 8 tile and one entry, four columns of two tile rows at a time (eight
-// independent chains); the left half of the tile needs only the first of the two w blocks, so it can start while the
-// second block's loads are still in flight.  A diagonal tile of a triangular task skips the hypotheses below the
-// diagonal.
+// S[i][c] = a_i . w_c and acc *= S for one 8 x 8 tile and one entry, a few tile rows at a time (independent chains
+// that cover the 4-cycle FMA latency).  A diagonal tile of a triangular task skips the hypotheses below the diagonal.
 template <bool DIAG>
 __device__ __forceinline__ void tile_math(const float (&a)[8][3], const float (&w)[8][3], float (&acc)[64]) {
+#ifndef DMX_TILE_ROWS
+#define DMX_TILE_ROWS 2
+#endif
+  constexpr int R = DMX_TILE_ROWS;   // tile rows per pass: R x 8 independent chains
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
+  for (int i0 = 0; i0 < 8; i0 += R) {
+    float s[R][8];
 #pragma unroll
-    for (int i0 = 0; i0 < 8; i0 += 2) {
-      float s[2][4];
+    for (int r = 0; r < R; ++r)
 #pragma unroll
-      for (int r = 0; r < 2; ++r)
+      for (int c = 0; c < 8; ++c)
+        if (!DIAG || c >= i0 + r) s[r][c] = a[i0 + r][0] * w[c][0];
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (!DIAG || half * 4 + c >= i0 + r) s[r][c] = a[i0 + r][0] * w[half * 4 + c][0];
+    for (int r = 0; r < R; ++r)
 #pragma unroll
-      for (int r = 0; r < 2; ++r)
+      for (int c = 0; c < 8; ++c)
+        if (!DIAG || c >= i0 + r) s[r][c] = fmaf(a[i0 + r][1], w[c][1], s[r][c]);
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (!DIAG || half * 4 + c >= i0 + r) s[r][c] = fmaf(a[i0 + r][1], w[half * 4 + c][1], s[r][c]);
+    for (int r = 0; r < R; ++r)
 #pragma unroll
-      for (int r = 0; r < 2; ++r)
+      for (int c = 0; c < 8; ++c)
+        if (!DIAG || c >= i0 + r) s[r][c] = fmaf(a[i0 + r][2], w[c][2], s[r][c]);
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (!DIAG || half * 4 + c >= i0 + r) s[r][c] = fmaf(a[i0 + r][2], w[half * 4 + c][2], s[r][c]);
+    for (int r = 0; r < R; ++r)
 #pragma unroll
-      for (int r = 0; r < 2; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (!DIAG || half * 4 + c >= i0 + r) acc[(i0 + r) * 8 + half * 4 + c] *= s[r][c];
-    }
+      for (int c = 0; c < 8; ++c)
+        if (!DIAG || c >= i0 + r) acc[(i0 + r) * 8 + c] *= s[r][c];
   }
 }
 

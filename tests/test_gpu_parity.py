@@ -27,6 +27,8 @@ def synth(*a, **k):
     (60, 70, 4000, "GP", (0.0, 0.5)),            # nv > 64, not a multiple of 4: multi-block tasks
     (40, 12, 3000, "PL", tuple(round(0.05 * i, 2) for i in range(11))),   # C5-like grid
     (200, 16, 300, "GT", (0.0, 0.5)),            # GT field, low coverage: massive exact ties
+    (24, 256, 6000, "GP", (0.0, 0.3, 0.5)),      # C5-like width: 4 x 4 sample blocks, symmetric and full planes
+    (64, 3, 40, "GP", (0.0, 0.5)),               # tiny: cells with one or two entries, nv not a multiple of 4
 ])
 @pytest.mark.parametrize("fp32", [False, True], ids=["f64pairs", "f32pairs"])
 def test_records_match_oracle(ncells, nv, nsnps, field, alphas, fp32):
