@@ -242,18 +242,20 @@ int launch_gprow(const float* gp_flat, float* gp_rows, int64_t nsnps, int nv, in
 // Two kernels: entq1 (one thread per entry, all distinct values in registers; U <= 8, the common grids) and
 // entq (LPE lanes per entry; lane `sub` owns p values sub, sub+LPE, ...) for long alpha grids.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void entq_emit(const EntqParams& p, int64_t e, double* __restrict__ out) {
+// GETV(slot): value of record slot `slot` (GL, f and Q' are already final when this runs)
+template <class GETV>
+__device__ __forceinline__ void entq_emit(const EntqParams& p, int64_t e, double* __restrict__ out, GETV getv) {
   // per-entry factors of the sample-independent likelihoods (they need only this record and the cohort mean gp0 of
   // the entry's SNP): llk0s (:459) -> head[6], llks00 of a separable plane 0 -> head[7], llks00[n] (:700-709) -> slot 9
   // of each dense plane; then the fp32 copies
   const double* z = reinterpret_cast<const double*>(p.gprow + (int64_t)__ldg(p.ent_snp + e) * p.gp_stride);
   const double z0 = __ldg(z), z1 = __ldg(z + 1), z2 = __ldg(z + 2);
-  const double g0 = __ldcg(out), g1 = __ldcg(out + 1), g2 = __ldcg(out + 2);
+  const double g0 = getv(0), g1 = getv(1), g2 = getv(2);
   double f0 = 0.0, f1 = 0.0, f2 = 0.0;
   const double s0 = fma(g2, z2, fma(g1, z1, g0 * z0));
   double s1 = 1.0;
   if (p.sep0) {
-    f0 = __ldcg(out + 3); f1 = __ldcg(out + 4); f2 = __ldcg(out + 5);
+    f0 = getv(3); f1 = getv(4); f2 = getv(5);
     s1 = fma(f2, z2, fma(f1, z1, f0 * z0)) * ((z0 + z1) + z2);
   }
   out[6] = s0;
@@ -270,7 +272,7 @@ __device__ __forceinline__ void entq_emit(const EntqParams& p, int64_t e, double
     double* q = out + QHEAD + QPLANE * d;
     double Q[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) Q[i] = __ldcg(q + i);
+    for (int i = 0; i < 9; ++i) Q[i] = getv(QHEAD + QPLANE * d + i);
     const double t0 = fma(Q[2], z2, fma(Q[1], z1, Q[0] * z0));
     const double t1 = fma(Q[5], z2, fma(Q[4], z1, Q[3] * z0));
     const double t2 = fma(Q[8], z2, fma(Q[7], z1, Q[6] * z0));
@@ -361,7 +363,7 @@ __global__ void __launch_bounds__(256) entq_kernel(const __grid_constant__ EntqP
     out[2] = __ddiv_rn(G2, sm);
   }
   __syncwarp(gmask);
-  if (sub == 0) entq_emit(p, e, out);
+  if (sub == 0) entq_emit(p, e, out, [&](int slot) { return __ldcg(out + slot); });
 }
 
 // one thread per entry: the U <= UMAX distinct values live in registers (independent chains: the divisions of a read
@@ -402,13 +404,13 @@ __global__ void __launch_bounds__(128) entq1_kernel(const __grid_constant__ Entq
     }
 #pragma unroll
     for (int v = 0; v < UMAX; ++v) P[v] = __ddiv_rn(P[v], mx);              // :632-639
-    G0 = __dmul_rn(G0, pR);                                                 // pass-1 GLs, :437-443
+    // pass-1 GLs, :437-443.  Unlike Q' (which the exact re-scorer consumes bit for bit) the GLs only feed sums of
+    // logs that are compared at 1e-4, so the three quotients by the same sum are one reciprocal and three products
+    G0 = __dmul_rn(G0, pR);
     G1 = __dmul_rn(G1, __dsub_rn(0.5, e3));
     G2 = __dmul_rn(G2, pA);
-    const double sm = __dadd_rn(__dadd_rn(G0, G1), G2);
-    G0 = __ddiv_rn(G0, sm);
-    G1 = __ddiv_rn(G1, sm);
-    G2 = __ddiv_rn(G2, sm);
+    const double rs = __drcp_rn(__dadd_rn(__dadd_rn(G0, G1), G2));
+    G0 *= rs; G1 *= rs; G2 *= rs;
   }
   double mx = 0.0;
 #pragma unroll
@@ -419,23 +421,23 @@ __global__ void __launch_bounds__(128) entq1_kernel(const __grid_constant__ Entq
 #pragma unroll
   for (int v = 0; v < UMAX; ++v) s_val[v][threadIdx.x] = __ddiv_rn(P[v], mx);   // :656-663
   double* out = p.entq + e * p.UQ;
-  {
-    G0 = __dadd_rn(G0, 1e-6);                                                // :446-452
-    G1 = __dadd_rn(G1, 1e-6);
-    G2 = __dadd_rn(G2, 1e-6);
-    const double sm = __dadd_rn(__dadd_rn(G0, G1), G2);
-    out[0] = __ddiv_rn(G0, sm);
-    out[1] = __ddiv_rn(G1, sm);
-    out[2] = __ddiv_rn(G2, sm);
-  }
+  G0 = __dadd_rn(G0, 1e-6);                                                  // :446-452
+  G1 = __dadd_rn(G1, 1e-6);
+  G2 = __dadd_rn(G2, 1e-6);
+  const double rs = __drcp_rn(__dadd_rn(__dadd_rn(G0, G1), G2));
+  G0 *= rs; G1 *= rs; G2 *= rs;
+  out[0] = G0;
+  out[1] = G1;
+  out[2] = G2;
+  const int tid = threadIdx.x;
   if (p.sep0)
-    for (int s = 3; s < 6; ++s) out[s] = s_val[p.slot_u[s]][threadIdx.x];
+    for (int s = 3; s < 6; ++s) out[s] = s_val[p.slot_u[s]][tid];
   for (int d = 0; d < p.nd; ++d)
     for (int i = 0; i < 9; ++i) {
       const int s = QHEAD + QPLANE * d + i;
-      out[s] = s_val[p.slot_u[s]][threadIdx.x];
+      out[s] = s_val[p.slot_u[s]][tid];
     }
-  entq_emit(p, e, out);
+  entq_emit(p, e, out, [&](int slot) { return slot == 0 ? G0 : (slot == 1 ? G1 : (slot == 2 ? G2 : s_val[p.slot_u[slot]][tid])); });
 }
 
 int launch_entq(const EntqParams& p, void* stream) {
