@@ -199,6 +199,15 @@ __device__ __forceinline__ void peelf(float& x, int& esum) {
 __device__ __forceinline__ double unpeelf_log(float x, int esum, int nflush) {
   return (double)(esum - 127 * nflush) * 0.693147180559945309417232121458 + log((double)x);
 }
+// log of a positive double to ~1e-7 absolute: binary exponent exactly, mantissa through the fp32 logf (the fp32 scan's
+// values carry ~1e-6 of product rounding anyway; a double-precision log() costs ~100 dependent FP64 instructions)
+__device__ __forceinline__ double log_pos_fast(double x) {
+  const long long b = __double_as_longlong(x);
+  const int k = (int)(b >> 52) - 1023;
+  if (k <= -1023 || k >= 1024) return log(x);   // zero, denormal, inf / nan: the library's answer
+  const float f = (float)__longlong_as_double((b & 0x000fffffffffffffll) | 0x3ff0000000000000ll);
+  return (double)k * 0.693147180559945309417232121458 + (double)logf(f);
+}
 __device__ __forceinline__ double unpeel_log(double x, int esum, int nflush) {
   return (double)(esum - 1023 * nflush) * 0.693147180559945309417232121458 + log(x);
 }
@@ -1159,7 +1168,7 @@ __device__ __forceinline__ void task_epilogue(const ScanParams& p, const TaskInf
     const int j = vj[i], k = vk[i];
     const double x = v[i];
     if (j != k) {
-      sd += exp(x - m_all);
+      sd += ROW0 ? exp(x - m_all) : (double)expf((float)(x - m_all));   // fp32 scan: 1e-7 relative is plenty here
       if (!noarg && x >= thr) {
         const int cs = atomicAdd(&scr->ncand, 1);
         if (cs < MAX_CAND) scr->cand[cs] = (uint32_t)j | ((uint32_t)k << 12);
@@ -1605,7 +1614,7 @@ __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_f32_kernel(cons
       for (int c = 0; c < 8; ++c) {
         const int j = tt.j0 + bj * 8 + el, k = tt.k0 + bk * 8 + c;
         const bool valid = active && j < p.nv && k < p.nv && (!tri || j <= k);
-        v[c] = valid ? (double)exs * 0.693147180559945309417232121458 + log(d3[c]) : -INFINITY;
+        v[c] = valid ? (double)exs * 0.693147180559945309417232121458 + log_pos_fast(d3[c]) : -INFINITY;
         vj[c] = j;
         vk[c] = k;
         if (valid) vmask |= 1u << c;
@@ -1773,8 +1782,8 @@ int launch_fill_sep_dense(const ScanParams& p, int64_t nactive, void* stream) {
 // (cmd_cram_demuxlet.cpp:671-684: gpAB product, (l,m) row-major sum, log, SNP-ascending accumulation).
 // Two phases, RESC_FAST hypotheses of every cell per pass (the common list is the two orders of the best pair):
 //   rescore_terms_kernel  one block per cell, threads over its entries: log(S) of the listed hypotheses -> terms
-//   rescore_sum_kernel    one thread per (cell, hypothesis): the sequential sum in entry order (the chain of
-//                         dependent adds the reference's accumulation order demands), loads a batch ahead of it
+//   rescore_sum_kernel    one warp per (cell, hypothesis): the sequential sum in entry order (the chain of dependent
+//                         adds the reference's accumulation order demands), coalesced loads a batch ahead of it
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double exact_term(const float* __restrict__ g, const double* __restrict__ q, uint32_t hy,
                                              const int8_t* dense_idx) {
@@ -1826,41 +1835,35 @@ __global__ void __launch_bounds__(256) rescore_terms_kernel(const __grid_constan
   }
 }
 
+// one warp per (cell, hypothesis): lanes fetch 32 consecutive terms at a time (one coalesced request, a batch ahead),
+// lane 0 owns the chain of dependent additions in entry order and receives the terms by shuffle
 __global__ void __launch_bounds__(128) rescore_sum_kernel(const __grid_constant__ RescoreParams p, int64_t nactive,
                                                           int pass) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t aidx = t / RESC_FAST;
-  const int h = (int)(t % RESC_FAST);
-  if (aidx >= nactive) return;
-  const int cell = p.cell_order[aidx];
-  RescList* L = p.lists + cell;
-  if (L->n < 0 || pass * RESC_FAST + h >= L->n) return;
-  const int64_t e0 = p.cell_ptr[cell], n = p.cell_ptr[cell + 1] - e0;
-  const double* x = p.terms + e0 * RESC_FAST + h * n;
-  // the additions form one dependent chain in entry order; the loads run a batch ahead of it and the lines they will
-  // touch are prefetched into L1 eight batches ahead (the terms were written by the previous launch)
-  constexpr int B = 16, PF = 8 * B;
-  double cur[B], nxt[B];
-  for (int64_t i = 0; i < min(n, (int64_t)PF); i += B) asm volatile("prefetch.global.L1 [%0];" ::"l"(x + i));
+  const int lane = threadIdx.x & 31;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wid < nactive * RESC_FAST; wid += nw) {
+    const int64_t aidx = wid / RESC_FAST;
+    const int h = (int)(wid % RESC_FAST);
+    const int cell = p.cell_order[aidx];
+    RescList* L = p.lists + cell;
+    if (L->n < 0 || pass * RESC_FAST + h >= L->n) continue;
+    const int64_t e0 = p.cell_ptr[cell], n = p.cell_ptr[cell + 1] - e0;
+    const double* x = p.terms + e0 * RESC_FAST + h * n;
+    double acc = 0.0;
+    double cur = lane < n ? __ldcg(x + lane) : 0.0;
+    for (int64_t i = 0; i < n; i += 32) {
+      const double nxt = (i + 32 + lane < n) ? __ldcg(x + i + 32 + lane) : 0.0;
+      const int cnt = (int)min((int64_t)32, n - i);
+      if (cnt == 32) {
 #pragma unroll
-  for (int u2 = 0; u2 < B; ++u2) cur[u2] = u2 < n ? x[u2] : 0.0;
-  double acc = 0.0;
-  for (int64_t i = 0; i < n; i += B) {
-    if (i + PF < n) asm volatile("prefetch.global.L1 [%0];" ::"l"(x + i + PF));
-#pragma unroll
-    for (int u2 = 0; u2 < B; ++u2) nxt[u2] = (i + B + u2 < n) ? x[i + B + u2] : 0.0;
-    if (i + B <= n) {
-#pragma unroll
-      for (int u2 = 0; u2 < B; ++u2) acc = __dadd_rn(acc, cur[u2]);
-    } else {
-#pragma unroll
-      for (int u2 = 0; u2 < B; ++u2)
-        if (i + u2 < n) acc = __dadd_rn(acc, cur[u2]);
+        for (int u2 = 0; u2 < 32; ++u2) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, cur, u2));
+      } else {
+        for (int u2 = 0; u2 < cnt; ++u2) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, cur, u2));
+      }
+      cur = nxt;
     }
-#pragma unroll
-    for (int u2 = 0; u2 < B; ++u2) cur[u2] = nxt[u2];
+    if (lane == 0) L->val[pass * RESC_FAST + h] = acc;
   }
-  L->val[pass * RESC_FAST + h] = acc;
 }
 
 int launch_rescore(const RescoreParams& p, int64_t nactive, void* stream) {
@@ -1870,7 +1873,8 @@ int launch_rescore(const RescoreParams& p, int64_t nactive, void* stream) {
   for (int pass = 0; pass * RESC_FAST < RMAX; ++pass) {
     const int64_t grid = pass == 0 ? nactive : (nactive < 1184 ? nactive : 1184);
     rescore_terms_kernel<<<(unsigned)grid, 256, 0, st>>>(p, nactive, pass);
-    rescore_sum_kernel<<<(unsigned)((nactive * RESC_FAST + 127) / 128), 128, 0, st>>>(p, nactive, pass);
+    const int64_t gsum = (nactive * RESC_FAST + 3) / 4;
+    rescore_sum_kernel<<<(unsigned)(pass == 0 ? gsum : (gsum < 1184 ? gsum : 1184)), 128, 0, st>>>(p, nactive, pass);
   }
   return (int)cudaGetLastError();
 }
