@@ -258,7 +258,10 @@ def run_ours(args):
     arrays = [pin(x) for x in (plp.cell_ptr, plp.ent_snp, plp.ent_ptr, plp.reads, plp.totl, plp.npass, plp.uniq)]
 
     fp32 = not args.fp64_pairs
-    d = api.Demuxlet(plp.nv, alphas, device=local_rank, borrow=True, trust_inputs=True, fp32_pairs=fp32)
+    # the ranks of one box share its host cores: each finaliser pool gets its share
+    host_threads = max(1, (os.cpu_count() or 1) // max(1, world))
+    d = api.Demuxlet(plp.nv, alphas, device=local_rank, borrow=True, trust_inputs=True, fp32_pairs=fp32,
+                     host_threads=host_threads)
     d.set_gp(gp)
     d.set_pileup_arrays(*arrays)
 
@@ -371,7 +374,7 @@ def run_ours(args):
         "roofline_fp": fp_roofline(plp, alphas, pair_s, fp32, clocks),
         "breakdown_ms": {"prep": float(np.mean(prep_ms)), "pair_scan": float(np.mean(pair_ms)),
                          "all_kernels": float(np.mean(kern_ms)), "d2h": st["d2h_ms"], "finalise_host": float(np.mean(fin_ms)),
-                         "rescored_hypotheses": int(st["n_rescored"]), "host_threads": os.cpu_count()},
+                         "rescored_hypotheses": int(st["n_rescored"]), "host_threads": host_threads},
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
