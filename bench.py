@@ -362,7 +362,8 @@ def run_ours(args):
                    "exact_ties": True},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(st2["h2d_bytes"]) * world,
                 "d2h_bytes_per_step": int(st2["d2h_bytes"]) * world, "ms_per_step": dt2 / args.steps * 1e3,
-                "h2d_ms": st2["h2d_ms"], "kernel_ms": st2["kernel_ms"], "finalise_ms": st2["finalise_ms"]},
+                "h2d_ms": st2["h2d_ms"], "kernel_ms": st2["kernel_ms"], "finalise_ms": st2["finalise_ms"],
+                "run_ms": st2["total_ms"]},
         "gpu_launches": int(st["gpu_launches"]) * args.steps,
         "roofline": {"bound": "hbm", "kernel": "pair_scan_f32_kernel" if fp32 else "pair_scan_kernel",
                      "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -668,10 +668,20 @@ int dmx_set_pileup(dmx_ctx* c, int64_t ncells, const int64_t* cell_ptr, const in
   // scheduled largest first.  Copies, kernels and the host finaliser of different chunks overlap (run_path).
   int K = (E >= (2 << 20) && ncells >= 256) ? 3 : 1;
   if (const char* ek = getenv("DMX_CHUNKS")) K = std::max(1, std::min(16, atoi(ek)));
+  // one sort of the active cells (largest first, ties by cell id) serves every schedule: a chunked schedule is a
+  // stable partition of it by chunk
+  std::vector<uint64_t> keys(c->order.size());
+  for (size_t i = 0; i < keys.size(); ++i) {
+    const int32_t cell = c->order[i];
+    const uint64_t sz = (uint64_t)std::min<int64_t>(cell_ptr[cell + 1] - cell_ptr[cell], 0xffffffffLL);
+    keys[i] = ((0xffffffffull - sz) << 32) | (uint32_t)cell;
+  }
+  std::sort(keys.begin(), keys.end());
   auto build = [&](int nk, std::vector<int32_t>* ord, std::vector<Chunk>* chunks) {
     chunks->clear();
+    ord->clear();
+    ord->reserve(keys.size());
     int64_t cb = 0;
-    size_t ob = 0;
     for (int k = 0; k < nk; ++k) {
       Chunk ck;
       ck.c0 = cb;
@@ -683,17 +693,16 @@ int dmx_set_pileup(dmx_ctx* c, int64_t ncells, const int64_t* cell_ptr, const in
       else
         while (ce < ncells && (double)cell_ptr[ce] < frac * (double)E) ++ce;
       ck.c1 = ce;
-      ck.o0 = (int64_t)ob;
-      while (ob < ord->size() && (*ord)[ob] < ce) ++ob;   // still in cell-id order here
-      ck.o1 = (int64_t)ob;
-      std::stable_sort(ord->begin() + ck.o0, ord->begin() + ck.o1, [&](int32_t a, int32_t b) {
-        return (cell_ptr[a + 1] - cell_ptr[a]) > (cell_ptr[b + 1] - cell_ptr[b]);
-      });
+      ck.o0 = (int64_t)ord->size();
+      for (const uint64_t key : keys) {
+        const int32_t cell = (int32_t)(uint32_t)key;
+        if (cell >= cb && cell < ce) ord->push_back(cell);
+      }
+      ck.o1 = (int64_t)ord->size();
       chunks->push_back(ck);
       cb = ce;
     }
   };
-  c->order_p = c->order;
   build(1, &c->order, &c->chunks);
   build(K, &c->order_p, &c->chunks_p);
   c->have_plp = true;
