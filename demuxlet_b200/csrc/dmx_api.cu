@@ -688,7 +688,7 @@ int dmx_set_pileup(dmx_ctx* c, int64_t ncells, const int64_t* cell_ptr, const in
       int64_t ce = cb;
       // a small first chunk lets the kernels start early, a small last one shortens the exposed tail (read back
       // and finaliser of the last chunk); three chunks: 15 % / 55 % / 30 % of the entries
-      const double frac = nk == 3 ? (k == 0 ? 0.15 : 0.70) : (double)(k + 1) / nk;
+      const double frac = nk == 3 ? (k == 0 ? 0.15 : 0.70) : (nk == 2 ? 0.2 : (double)(k + 1) / nk);
       if (k == nk - 1) ce = ncells;
       else
         while (ce < ncells && (double)cell_ptr[ce] < frac * (double)E) ++ce;
