@@ -703,7 +703,9 @@ int dmx_set_pileup(dmx_ctx* c, int64_t ncells, const int64_t* cell_ptr, const in
       cb = ce;
     }
   };
-  build(1, &c->order, &c->chunks);
+  // resident inputs: one chunk, unless the host has few threads for the finaliser (several ranks sharing a box):
+  // then chunks let it run under the kernels of the following chunk
+  build((K > 1 && host_threads(c) < 8) ? K : 1, &c->order, &c->chunks);
   build(K, &c->order_p, &c->chunks_p);
   c->have_plp = true;
   c->plp_dirty = true;
@@ -1012,7 +1014,8 @@ int run_path(dmx_ctx* c, bool pipelined) {
       if (r->status != 0) return;
       const CellOut& co = c->r_out.p[cell];
       if (co.ncand > MAX_CAND) { overflow[tid].push_back((int32_t)cell); return; }
-      std::vector<Hyp> cands;
+      thread_local std::vector<Hyp> cands;
+      cands.clear();
       expand_cands(c, co, &cands);
       do_cell(cell, cands, tid);
     });

@@ -169,10 +169,19 @@ void finalise_cell(const HostView& hv, const ExactScorer& sc, int64_t cell, cons
                    const std::vector<Hyp>& cands, double doublet_prior, double eps_rel, double eps_abs, bool exact,
                    const RescList* gl, dmx_best_rec* rec, int32_t* n_from_gpu) {
   const int nv = hv.nv;
-  std::vector<double> vals(g.sing, g.sing + nv);
-  std::vector<uint8_t> is_exact(nv, 0);
-  ExactCache cache;
-  std::vector<Hyp> need;
+  // per-thread scratch, reused from cell to cell (a run finalises tens of thousands of cells per thread)
+  thread_local std::vector<double> vals;
+  thread_local std::vector<uint8_t> is_exact;
+  thread_local ExactCache cache;
+  thread_local std::vector<Hyp> need;
+  thread_local std::vector<double> out, mo;
+  thread_local std::vector<Hyp> miss;
+  thread_local std::vector<size_t> miss_at;
+  vals.assign(g.sing, g.sing + nv);
+  is_exact.assign(nv, 0);
+  cache.h.clear();
+  cache.v.clear();
+  need.clear();
 
   // ---- which singlets are too close to call (:746-758 compares llksAB[j][0][0]) ---------------
   {
@@ -195,11 +204,11 @@ void finalise_cell(const HostView& hv, const ExactScorer& sc, int64_t cell, cons
 
   auto run_batch = [&](std::vector<Hyp>& hs) {
     if (hs.empty()) return;
-    std::vector<double> out(hs.size());
+    out.assign(hs.size(), 0.0);
     // values the device re-scorer already produced (bit-identical to the host arithmetic, verified at
     // dmx_create); the rest is scored here
-    std::vector<Hyp> miss;
-    std::vector<size_t> miss_at;
+    miss.clear();
+    miss_at.clear();
     for (size_t i = 0; i < hs.size(); ++i) {
       bool hit = false;
       if (gl && gl->n > 0) {
@@ -211,7 +220,7 @@ void finalise_cell(const HostView& hv, const ExactScorer& sc, int64_t cell, cons
       else { miss.push_back(hs[i]); miss_at.push_back(i); }
     }
     if (!miss.empty()) {
-      std::vector<double> mo(miss.size());
+      mo.assign(miss.size(), 0.0);
       sc.eval(cell, miss.data(), (int)miss.size(), mo.data());
       for (size_t i = 0; i < miss.size(); ++i) out[miss_at[i]] = mo[i];
     }

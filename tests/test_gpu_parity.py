@@ -200,3 +200,50 @@ def test_cli_reproduces_reference_files(name, tmp_path):
         fa, fb = a.split("\t"), b.split("\t")
         for i in (0, 1, 2, 3, 4, 5, 6, 8, 11, 12, 13):   # identity columns incl. BEST / SNG.1ST / DBL.1ST / DBL.2ND / ALPHA
             assert fa[i] == fb[i], (i, a, b)
+
+
+def test_error_paths_and_context_reuse():
+    """call-order and input errors come back as status codes (never an abort), and one context can be fed several
+    pileups through both entry points (dmx_run: pipelined copies; dmx_upload + dmx_compute: resident inputs)"""
+    from demuxlet_b200.api import Demuxlet, DmxError
+    p = synth(90, 8, 1200, "GP", seed=31)
+    d = Demuxlet(p.nv, (0.0, 0.5), fp32_pairs=True)
+    with pytest.raises(DmxError) as e:
+        d.run()                                   # nothing set yet
+    assert e.value.status == -4
+    d.set_gp(p.gp)
+    bad = p.cell_ptr.copy()
+    bad[5], bad[6] = bad[6], bad[5] + 0           # not monotone
+    if bad[6] < bad[5]:
+        with pytest.raises(DmxError) as e:
+            d.set_pileup_arrays(bad, p.ent_snp, p.ent_ptr, p.reads, p.totl, p.npass, p.uniq)
+        assert e.value.status == -1
+    snp_bad = p.ent_snp.copy()
+    snp_bad[3] = p.nsnps + 7                      # SNP id outside the GP matrix
+    d.set_pileup_arrays(p.cell_ptr, snp_bad, p.ent_ptr, p.reads, p.totl, p.npass, p.uniq)
+    with pytest.raises(DmxError) as e:
+        d.run()
+    assert e.value.status == -1
+    # now the good inputs, three ways; results must be identical
+    d.set_pileup(p)
+    d.run()
+    a = d.best().copy()
+    d.upload()
+    d.compute()
+    b = d.best().copy()
+    q = synth(40, 8, 1200, "GP", seed=32)          # another pileup through the same context
+    d.set_pileup(q)
+    d.run()
+    assert d.best().shape[0] == 40
+    d.set_pileup(p)
+    d.run()
+    c2 = d.best().copy()
+    for f in ("sng1", "sng2", "dbl1", "dbl2", "alpha_idx", "call", "n_snp"):
+        assert np.array_equal(a[f], b[f]) and np.array_equal(a[f], c2[f]), f
+    assert np.array_equal(a["llk12"], b["llk12"]) and np.array_equal(a["llk12"], c2["llk12"])   # re-scored exactly
+    # the singlet / pair-with-sample-0 products are accumulated by whichever transform warp takes a stage: their
+    # fp32 rounding order, not their value, changes from run to run (DESIGN.md 3)
+    for f in ("sng_llk1", "llk10", "llk00", "prb_dbl"):
+        assert np.allclose(a[f], b[f], rtol=0, atol=1e-5) and np.allclose(a[f], c2[f], rtol=0, atol=1e-5), f
+    orc, ref, e2 = run_both(p, (0.0, 0.5), fp32_pairs=True)
+    compare(ref, d, prb_rtol=1e-4)
