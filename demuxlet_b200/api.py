@@ -31,7 +31,7 @@ ABI_SYMBOLS = [
     "dmx_config_default", "dmx_device_count", "dmx_create", "dmx_destroy", "dmx_set_gp", "dmx_set_pileup",
     "dmx_upload", "dmx_compute", "dmx_run", "dmx_get_best", "dmx_get_single", "dmx_get_sing2", "dmx_get_pair",
     "dmx_rescore", "dmx_exact_llk", "dmx_write_outputs", "dmx_get_stats", "dmx_alloc_host", "dmx_free_host", "dmx_strerror",
-    "dmx_last_error", "dmx_abi_version",
+    "dmx_last_error", "dmx_abi_version", "dmx_pack_reads", "dmx_pileup_sizes", "dmx_pileup_copy", "dmx_pileup_free",
 ]
 
 
@@ -135,6 +135,56 @@ def exact_llk(plp: Pileup, alphas: Sequence[float], cell: int, j: int, k: int, n
     if rc != 0:
         raise DmxError(rc, "dmx_exact_llk")
     return out.value
+
+
+def encode_umis(umis: Sequence[str]):
+    """list of UMI strings -> (byte buffer, int64 offsets) as dmx_pack_reads takes them"""
+    enc = [u.encode() for u in umis]
+    off = np.zeros(len(enc) + 1, dtype=np.int64)
+    if enc:
+        off[1:] = np.cumsum([len(b) for b in enc])
+    buf = np.frombuffer(b"".join(enc) + b"\0", dtype=np.uint8).copy()
+    return buf, off
+
+
+def pack_reads(cell, snp, umis, allele, bq, ncells: int, threads: int = 0) -> dict:
+    """Sort-based pileup packer (host only, needs no GPU): reads in arrival order -> the CSR arrays of
+    dmx_set_pileup plus cell_pass_reads / cell_uniq_reads, with the semantics of the reference's add_read
+    (sc_drop_seq.cpp:34-77).  `umis`: list of strings, or an (uint8 buffer, int64 offsets) pair."""
+    lib = load_library()
+    lib.dmx_pack_reads.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]
+    lib.dmx_pileup_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.dmx_pileup_copy.argtypes = [C.c_void_p] * 7
+    lib.dmx_pileup_free.argtypes = [C.c_void_p]
+    lib.dmx_pileup_free.restype = None
+    cell = np.ascontiguousarray(cell, dtype=np.int32)
+    snp = np.ascontiguousarray(snp, dtype=np.int32)
+    allele = np.ascontiguousarray(allele, dtype=np.uint8)
+    bq = np.ascontiguousarray(bq, dtype=np.uint8)
+    buf, off = umis if isinstance(umis, tuple) else encode_umis(umis)
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    n = int(cell.shape[0])
+    assert snp.shape[0] == n and allele.shape[0] == n and bq.shape[0] == n and off.shape[0] == n + 1
+    h = C.c_void_p()
+    rc = lib.dmx_pack_reads(n, cell.ctypes.data, snp.ctypes.data, allele.ctypes.data, bq.ctypes.data, buf.ctypes.data,
+                            off.ctypes.data, int(ncells), int(threads), C.byref(h))
+    if rc != 0:
+        raise DmxError(rc, "dmx_pack_reads")
+    try:
+        nc, E, R = C.c_int64(), C.c_int64(), C.c_int64()
+        lib.dmx_pileup_sizes(h, C.byref(nc), C.byref(E), C.byref(R))
+        out = {"cell_ptr": np.zeros(nc.value + 1, np.int64), "ent_snp": np.zeros(E.value, np.int32),
+               "ent_ptr": np.zeros(E.value + 1, np.int64), "reads": np.zeros(R.value, np.uint16),
+               "npass": np.zeros(nc.value, np.int32), "uniq": np.zeros(nc.value, np.int32)}
+        rc = lib.dmx_pileup_copy(h, out["cell_ptr"].ctypes.data, out["ent_snp"].ctypes.data, out["ent_ptr"].ctypes.data,
+                                 out["reads"].ctypes.data, out["npass"].ctypes.data, out["uniq"].ctypes.data)
+        if rc != 0:
+            raise DmxError(rc, "dmx_pileup_copy")
+    finally:
+        lib.dmx_pileup_free(h)
+    return out
 
 
 def pinned_empty(shape, dtype) -> np.ndarray:

@@ -160,6 +160,22 @@ int dmx_exact_llk(int32_t nv, int32_t n_alpha, const double* alpha, const float*
 
 int dmx_get_stats(dmx_ctx* ctx, dmx_stats* out);
 
+/* ---- pileup packer (host only) -------------------------------------------------------------------
+ * Sort-based replacement of sc_dropseq_lib_t::add_read (sc_drop_seq.cpp:34-77) followed by the flattening of the
+ * container: n reads in arrival order -- cell id (add_cell order, sc_drop_seq.cpp:21-32), SNP id, UMI string
+ * (umi_buf[umi_off[i] .. umi_off[i+1])), allele, base quality -- in; the CSR arrays dmx_set_pileup takes plus
+ * cell_pass_reads / cell_uniq_reads out.  The first read of a (snp, cell, umi) keeps its allele and quality, later
+ * ones only count; SNPs ascending inside a cell, UMIs in std::string order inside an entry. */
+typedef struct dmx_pileup dmx_pileup;
+int dmx_pack_reads(int64_t n, const int32_t* cell, const int32_t* snp, const uint8_t* allele, const uint8_t* bq,
+                   const char* umi_buf, const int64_t* umi_off, int64_t ncells, int32_t n_threads, dmx_pileup** out);
+int dmx_pileup_sizes(const dmx_pileup* p, int64_t* ncells, int64_t* n_entries, int64_t* n_reads);
+/* copies into caller buffers sized from dmx_pileup_sizes: cell_ptr[ncells+1], ent_snp[E], ent_ptr[E+1], reads[R],
+ * pass[ncells], uniq[ncells]; any pointer may be null */
+int dmx_pileup_copy(const dmx_pileup* p, int64_t* cell_ptr, int32_t* ent_snp, int64_t* ent_ptr, uint16_t* reads,
+                    int32_t* pass, int32_t* uniq);
+void dmx_pileup_free(dmx_pileup* p);
+
 /* pinned host memory for DMX_BORROW_INPUTS callers */
 void* dmx_alloc_host(int64_t bytes);
 void dmx_free_host(void* p);
