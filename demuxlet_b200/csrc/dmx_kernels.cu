@@ -546,7 +546,7 @@ constexpr uint32_t F_BLK4_FLT = NB * 12 + 12;                        // 108 floa
 constexpr uint32_t F_SIDE_FLT = (BLK / 4) * F_BLK4_FLT;              // 1728 floats
 constexpr uint32_t F_PROC_SLOT = 2 * F_SIDE_FLT * 4;                 // 13824 B
 static_assert(F_PROC_SLOT % 128 == 0 && NB == 8, "fp32 scan geometry");
-static_assert(2 * 12 + 2 * F_S_PROC <= 64 && 2 * S_RAW + 2 * S_PROC <= 64, "barriers must fit below the scratch area");
+static_assert(2 * 12 + 4 * F_S_PROC <= 64 && 2 * S_RAW + 2 * S_PROC <= 64, "barriers must fit below the scratch area");
 
 constexpr uint32_t SCRATCH_OFF = 512;   // barriers live below
 struct Scratch {                     // at slot offset SCRATCH_OFF
@@ -869,12 +869,12 @@ __device__ __forceinline__ void loader_role_f32(const ScanParams& p, const ScanM
 // floats of its samples' GP rows (3 LDS.128, 48-byte lane stride: conflict free), the entry's fp32 record (5
 // LDS.128, two distinct addresses per warp), and the (a, w) blocks of the processed ring (3 + 3 STS.128, conflict
 // free by the F_BLK4_FLT padding).  w_k[l] = sum_m Q'[l][m] gp_k[m] in fp32.  The per-sample extras (singlet factor
-// of the separable plane, row sums, pass 1, pairs with sample 0) are fp32 running products per lane; a product is
-// peeled into an integer exponent only when it gets small (checked after every stage), and the partial products of a
-// sample (2 lanes x 4 warps) are multiplied together in fp64 at the end of the task: one log per sample and quantity.
+// of the separable plane, row sums, pass 1, pairs with sample 0) leave the transform warps as per-stage products
+// (four entries per lane) in a products ring; the accumulator warp multiplies them up in stage order, so the result
+// does not depend on which transform warp happened to take which stage.
 struct TScratch {
-  double xm[2][F_NTW][4][BLK];       // [task parity][warp][PA, PB, P1, P0][sample]: mantissa products of the warp's slots
-  int xe[2][F_NTW][4][BLK];          // ... and their exponent sums
+  float prod[F_S_PROC][2][4][BLK];   // products ring: [stage slot][entry half][PA, PB, P1, P0][sample], the stage's
+                                     // factors of every per-sample running product (transform -> accumulator warp)
   unsigned next_stage;               // stage counter of the CTA: transform warps take stages as they become free
 };
 constexpr uint32_t F_TS_BYTES = (sizeof(TScratch) + 127) / 128 * 128;
@@ -1004,10 +1004,9 @@ __device__ __forceinline__ void transform_stage_f32(const unsigned char* __restr
 // sub-partition with busier consumers simply takes fewer.  In-flight stages span at most F_NTW consecutive
 // indices, fewer than either ring has slots, so the parity waits below cannot alias.
 template <bool UNROLL>
-__device__ __forceinline__ void transform_role_f32(const ScanParams& p, const Pipe& pp, TScratch* ts, int tw, int lane,
-                                                   int u, int NS) {
+__device__ __forceinline__ void transform_role_f32(const ScanParams& p, const Pipe& pp, TScratch* ts, uint64_t* prod_full,
+                                                   uint64_t* prod_empty, int lane, int u, int NS) {
   const int ebase = lane >> 4, q = lane & 15;
-  const int tl = tw * 32 + lane;
   const uint32_t sraw = (uint32_t)p.f_sraw, rawslot = (uint32_t)p.f_rawslot, off_fh = (uint32_t)p.f_off_fh;
   uint32_t gbase = 0;   // stages of the tasks before this one
   auto grab = [&]() -> uint32_t {
@@ -1025,16 +1024,14 @@ __device__ __forceinline__ void transform_role_f32(const ScanParams& p, const Pi
     const bool kq = same ? jq : (4 * q < tt.nk);
     // pairs with sample 0: on the k side of symmetric tasks, on the j side of the (rectangular) tasks of full planes
     const int row0 = (!(tt.flags & TF_ROW0) || (p.dbg & 16)) ? 0 : ((tt.flags & TF_SYM) ? 1 : (same ? 0 : 2));
-    const bool prods_t = extras_t || row0 != 0;
-    float PA[4], PB[4], P1[4], P0[4];                 // running fp32 products (extras) of this lane's samples
-    int eA[4], e1x[4], e0x[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { PA[i] = PB[i] = P1[i] = P0[i] = 1.0f; eA[i] = e1x[i] = e0x[i] = 0; }
     for (; git < gbase + (uint32_t)ti.nst; git = grab()) {
       const int it = (int)(git - gbase);
       const uint32_t rslot = git % sraw, pslot = git % F_S_PROC;
       const uint32_t rph = (git / sraw) & 1u, pph = (git / F_S_PROC) & 1u;
       const int nvalid = (int)min((int64_t)NB, ti.e1 - (ti.e0 + (int64_t)it * NB));
+      float PA[4], PB[4], P1[4], P0[4];               // this stage's factors of the running products (4 entries each)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) PA[i] = PB[i] = P1[i] = P0[i] = 1.0f;
       mbar_wait(&pp.raw_full[rslot], rph);
       mbar_wait(&pp.proc_empty[pslot], pph ^ 1u);
       const unsigned char* rs = pp.raw_base + (size_t)rslot * rawslot;
@@ -1059,74 +1056,76 @@ __device__ __forceinline__ void transform_role_f32(const ScanParams& p, const Pi
           else transform_stage_f32<false, false, 0, UNROLL>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
         }
       }
-      if (prods_t) {
-        // every factor is >= ~1e-6 (the +1e-6 floors of :446-452 and :643-663), so the four of the next stage keep a
-        // product that is above 2^-46 now inside the fp32 range; exact zeros (padding samples) are left alone
-        float mn = 1.0f;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          mn = fminf(mn, PA[i] > 0.f ? PA[i] : 1.0f);
-          mn = fminf(mn, P1[i] > 0.f ? P1[i] : 1.0f);
-          mn = fminf(mn, P0[i] > 0.f ? P0[i] : 1.0f);
-        }
-        if (__any_sync(0xffffffffu, mn < 0x1p-46f)) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            peelf_unbiased(PA[i], eA[i]); peelf_unbiased(P1[i], e1x[i]); peelf_unbiased(P0[i], e0x[i]);
-          }
-        }
+      // the stage's factors go to the products ring (every factor is >= ~2^-20, four of them cannot underflow)
+      mbar_wait(&prod_empty[pslot], pph ^ 1u);
+      {
+        float4* dst = reinterpret_cast<float4*>(&ts->prod[pslot][ebase][0][4 * q]);
+        dst[0 * (BLK / 4)] = make_float4(PA[0], PA[1], PA[2], PA[3]);
+        dst[1 * (BLK / 4)] = make_float4(PB[0], PB[1], PB[2], PB[3]);
+        dst[2 * (BLK / 4)] = make_float4(P1[0], P1[1], P1[2], P1[3]);
+        dst[3 * (BLK / 4)] = make_float4(P0[0], P0[1], P0[2], P0[3]);
       }
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&pp.proc_full[pslot]);
+        mbar_arrive(&prod_full[pslot]);
         mbar_arrive(&pp.raw_empty[rslot]);
       }
     }
     gbase += (uint32_t)ti.nst;
-    if (!prods_t) continue;   // uniform over the transform warps
-    const int buf = r & 1;
-    // fold the two entry slots of this warp (lanes 16 apart), then the warps through shared memory
+  }
+}
+
+// =============================== accumulator warp =================================================
+// Multiplies the per-stage factors of the products ring into the per-sample running products in stage order (the
+// order the stages were numbered in, not the order the transform warps finished them: the result is reproducible) and
+// writes, at the end of a task, the singlet factor of the separable plane, the row-sum term, the pass-1 likelihoods
+// and the pairs with sample 0.  Lane l owns quantity l / 8 of the samples 8 (l % 8) .. + 7; a product is renormalised
+// into an integer exponent after every factor.
+__device__ __forceinline__ void accumulator_role_f32(const ScanParams& p, const TScratch* ts, uint64_t* prod_full,
+                                                     uint64_t* prod_empty, int lane, int u, int NS) {
+  const int c = lane >> 3, s0 = (lane & 7) * 8;
+  uint32_t git = 0;
+  TaskInfo ti;
+  for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
+    const TaskType tt = p.tt[ti.tti];
+    const bool same = tt.flags & TF_TRI;
+    const bool extras_t = (tt.flags & TF_EXTRAS) != 0 && !(p.dbg & 4);
+    const int row0 = (!(tt.flags & TF_ROW0) || (p.dbg & 16)) ? 0 : ((tt.flags & TF_SYM) ? 1 : (same ? 0 : 2));
+    float acc[8];
+    int ex[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      double ma = (double)PA[i], mb = (double)PB[i], m1 = (double)P1[i], m0 = (double)P0[i];
-      int xa = eA[i], x1 = e1x[i], x0 = e0x[i];
-      ma *= __shfl_xor_sync(0xffffffffu, ma, 16);
-      mb *= __shfl_xor_sync(0xffffffffu, mb, 16);
-      m1 *= __shfl_xor_sync(0xffffffffu, m1, 16);
-      m0 *= __shfl_xor_sync(0xffffffffu, m0, 16);
-      xa += __shfl_xor_sync(0xffffffffu, xa, 16);
-      x1 += __shfl_xor_sync(0xffffffffu, x1, 16);
-      x0 += __shfl_xor_sync(0xffffffffu, x0, 16);
-      if (lane < 16) {
-        const int smp = 4 * q + i;
-        ts->xm[buf][tw][0][smp] = ma; ts->xe[buf][tw][0][smp] = xa;
-        ts->xm[buf][tw][1][smp] = mb; ts->xe[buf][tw][1][smp] = 0;
-        ts->xm[buf][tw][2][smp] = m1; ts->xe[buf][tw][2][smp] = x1;
-        ts->xm[buf][tw][3][smp] = m0; ts->xe[buf][tw][3][smp] = x0;
+    for (int i = 0; i < 8; ++i) { acc[i] = 1.0f; ex[i] = 0; }
+    for (int it = 0; it < ti.nst; ++it, ++git) {
+      const uint32_t slot = git % F_S_PROC, ph = (git / F_S_PROC) & 1u;
+      mbar_wait(&prod_full[slot], ph);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const float4* src = reinterpret_cast<const float4*>(&ts->prod[slot][half][c][s0]);
+        const float4 x = src[0], y = src[1];
+        const float f[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[i] *= f[i];
+          peelf_unbiased(acc[i], ex[i]);     // exact zeros (padding samples) stay zero
+        }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&prod_empty[slot]);
     }
-    asm volatile("bar.sync 2, %0;" ::"n"(F_NTW * 32) : "memory");
-    // 4 x 64 (quantity, sample) results over the transform lanes
-    for (int item = tl; item < 4 * BLK; item += F_NTW * 32) {
-      const int c = item >> 6, smp = item & (BLK - 1);
-      if (c < 3) {
-        if (!extras_t || smp >= tt.nk || tt.k0 + smp >= p.nv) continue;
-        if ((c == 0 && !p.sep0) || (c == 2 && !p.want_single)) continue;
-      } else {
-        if (row0 == 0) continue;
-        if (row0 == 1 ? (smp >= tt.nk || tt.k0 + smp >= p.nv) : (smp >= tt.nj || tt.j0 + smp >= p.nv)) continue;
-      }
-      double m = 1.0;
-      int ex = 0;
+    // results of this task: quantities 0..2 belong to the k-side samples of tasks with TF_EXTRAS, quantity 3 to the
+    // pairs with sample 0
+    const bool want = c == 3 ? row0 != 0 : (extras_t && !(c == 0 && !p.sep0) && !(c == 2 && !p.want_single));
+    if (!want) continue;
 #pragma unroll
-      for (int w = 0; w < F_NTW; ++w) { m *= ts->xm[buf][w][c][smp]; ex += ts->xe[buf][w][c][smp]; }
-      const double v = (double)ex * 0.693147180559945309417232121458 + log(m);
-      if (c < 3) {
-        double* dst = c == 0 ? p.singA : (c == 1 ? p.lb : p.p1);
-        dst[(int64_t)ti.cell * p.nv + tt.k0 + smp] = v;
-      } else {
-        p.row0[((int64_t)ti.cell * p.nA + tt.n) * p.nv + (row0 == 1 ? tt.k0 : tt.j0) + smp] = v;
-      }
+    for (int i = 0; i < 8; ++i) {
+      const int smp = s0 + i;
+      const bool on_j = c == 3 && row0 == 2;
+      const int gs = (on_j ? tt.j0 : tt.k0) + smp;
+      if (smp >= (on_j ? tt.nj : tt.nk) || gs >= p.nv) continue;
+      const double v = (double)ex[i] * 0.693147180559945309417232121458 + (double)logf(acc[i]);
+      if (c == 3) p.row0[((int64_t)ti.cell * p.nA + tt.n) * p.nv + gs] = v;
+      else (c == 0 ? p.singA : (c == 1 ? p.lb : p.p1))[(int64_t)ti.cell * p.nv + gs] = v;
     }
   }
 }
@@ -1426,9 +1425,9 @@ __device__ __forceinline__ void tile_math(const float (&a)[8][3], const float (&
 // ---------------------------------------------------------------------------------------------
 // fp32 pair scan: one task pipeline per CTA, 16 warps in four warpgroups.  SM sub-partition = warp id % 4; roles are
 // placed so that the issue load of the four sub-partitions is even (C = consumer, D = consumer of diagonal tiles:
-// 36 / 64 of the work, T = transform, L = loader):
+// 36 / 64 of the work, T = transform, L = loader, A = accumulator of the per-sample products):
 //   wid   0  1  2  3 |  4  5  6  7 |  8  9 10 11 | 12 13 14 15
-//         D  C  C  C |  D  C  C  C |  C  T  T  T |  T  L  L  T
+//         D  C  C  C |  D  C  C  C |  C  T  T  T |  T  L  L  A
 // The last warpgroup gives registers back (setmaxnreg) so that the consumers' 64 accumulators + 48 operands fit.
 //
 // A consumer thread owns the 8 x 8 tile (bj, bk) of hypotheses for the entries e = lane & 7 of every stage: per
@@ -1442,7 +1441,7 @@ __device__ __forceinline__ void tile_math(const float (&a)[8][3], const float (&
 // multiply their products together (fp64 reduce-scatter: lane e ends up with tile row e).
 // ---------------------------------------------------------------------------------------------
 constexpr int F_LAUNCH_THREADS = 512;
-static_assert(F_S_RAW_RECT % F_NLOAD == 0 && F_S_RAW_TRI % F_NLOAD == 0 && F_NLOAD == 2 && F_NTW <= 5 &&
+static_assert(F_S_RAW_RECT % F_NLOAD == 0 && F_S_RAW_TRI % F_NLOAD == 0 && F_NLOAD == 2 && F_NTW <= 4 &&
               F_NTW < (int)F_S_RAW_RECT && F_NTW < F_S_PROC, "ring ownership");
 constexpr int F_REGS_HI = 136, F_REGS_LO = 104;   // (3 * 136 + 104) * 32 = 16384 registers per sub-partition
 
@@ -1455,6 +1454,8 @@ __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_f32_kernel(cons
   pp.raw_empty = pp.raw_full + F_S_RAW_TRI;
   pp.proc_full = pp.raw_empty + F_S_RAW_TRI;
   pp.proc_empty = pp.proc_full + F_S_PROC;
+  uint64_t* prod_full = pp.proc_empty + F_S_PROC;      // products ring: transform -> accumulator warp
+  uint64_t* prod_empty = prod_full + F_S_PROC;
   Scratch* scr = reinterpret_cast<Scratch*>(smem + SCRATCH_OFF);
   pp.raw_base = smem + SLOT_CTRL;
   pp.proc_base = pp.raw_base + F_RAW_BYTES;
@@ -1468,6 +1469,8 @@ __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_f32_kernel(cons
     for (int s = 0; s < F_S_PROC; ++s) {
       mbar_init(&pp.proc_full[s], 1);
       mbar_init(&pp.proc_empty[s], F_NCW);
+      mbar_init(&prod_full[s], 1);
+      mbar_init(&prod_empty[s], 1);
     }
     scr->ncand = 0;
     ts->next_stage = 0;
@@ -1479,18 +1482,14 @@ __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_f32_kernel(cons
   const int NS = (int)gridDim.x, u = (int)blockIdx.x;
   if (warp >= 12) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(F_REGS_LO));
-    if (warp == 12) { if (F_NTW > 3) transform_role_f32<false>(p, pp, ts, 3, lane, u, NS); }
-    else if (warp == 15) { if (F_NTW > 4) transform_role_f32<false>(p, pp, ts, 4, lane, u, NS); }
+    if (warp == 12) { if (F_NTW > 3) transform_role_f32<false>(p, pp, ts, prod_full, prod_empty, lane, u, NS); }
+    else if (warp == 15) accumulator_role_f32(p, ts, prod_full, prod_empty, lane, u, NS);
     else loader_role_f32(p, tm, pp, lane, u, NS, warp - 13);
     return;
   }
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(F_REGS_HI));
   if (warp >= F_NCW) {
-#ifdef DMX_ROLLED
-    transform_role_f32<false>(p, pp, ts, warp - F_NCW, lane, u, NS);
-#else
-    transform_role_f32<true>(p, pp, ts, warp - F_NCW, lane, u, NS);
-#endif
+    transform_role_f32<true>(p, pp, ts, prod_full, prod_empty, lane, u, NS);
   } else {
     // =============================== consumer warps ============================================
     // logical consumer index: 0..6 own the 28 off-diagonal tile positions of a triangular task, 7 and 8 (physical
