@@ -141,7 +141,6 @@ struct dmx_ctx {
 
   std::vector<dmx_best_rec> best;
   dmx_stats st;
-  DevBuf<long long> d_dbg;
   ScanMaps maps;                    // TMA descriptors of d_gprow / d_entq (encode_maps)
 };
 
@@ -419,10 +418,6 @@ void fill_scan_params(dmx_ctx* c, ScanParams* p) {
   else { p->q_hp = QHEAD * 8; p->q_po = NB * QHEAD * 8; p->q_pp = QPLANE * 8; }
   p->gp_stride = c->nvp * 3 + 8;
   p->dbg = getenv("DMX_DEBUG") ? atoi(getenv("DMX_DEBUG")) : 0;
-  if (p->dbg & 8) {
-    c->d_dbg.reserve(272 * 8);
-    p->dbgbuf = c->d_dbg.p;
-  }
   p->gp = c->d_gprow.p + 8; p->ent_snp = c->d_ent_snp.p; p->entq = c->d_entq.p;
   p->has_rect = 0;
   for (const TaskType& t : c->tt)

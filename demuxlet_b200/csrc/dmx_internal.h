@@ -100,8 +100,8 @@ struct ScanParams {
   int32_t T;                   // task types per cell
   int32_t want_single;         // accumulate pass 1
   int32_t q_hp, q_po, q_pp;    // raw-stage layout of the entry records: head pitch, plane offset, plane pitch (bytes)
-  long long* dbgbuf;           // DMX_DEBUG & 8: [256][8] clock64 stamps of block 0, second task
-  int32_t dbg;                 // DMX_DEBUG: timing experiments (1: skip consumer math, 2: skip transform math)
+  int32_t dbg;                 // DMX_DEBUG: timing experiments of the fp32 scan (1: skip consumer math, 2: skip
+                               // transform math, 4: no per-sample extras, 16: no pairs with sample 0); results are wrong
   int32_t gp_stride;           // floats per GP row in HBM (8 + nvp*3); gp points at the first sample of row 0
   int64_t ntasks;              // nactive * T
   double eps_rel;              // candidate window, relative to max(1, |best|) ...

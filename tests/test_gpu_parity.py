@@ -69,10 +69,13 @@ def test_output_files(tmp_path):
         diff_tsv(tmp_path / ("orc." + ext), tmp_path / ("gpu." + ext), ROW_EXACT)
 
 
-def test_dense_pair_block_matches_oracle():
+@pytest.mark.parametrize("fp32", [False, True], ids=["f64pairs", "f32pairs"])
+def test_dense_pair_block_matches_oracle(fp32):
+    """dmx_get_pair: dense llksAB blocks come from the fp64 scan in both modes (the fp32 scan lets hopeless hypotheses
+    underflow), so they are exact to 1e-8 either way"""
     p = synth(30, 10, 2000, "GP", seed=9)
     alphas = (0.0, 0.3, 0.5)
-    orc, ref, d = run_both(p, alphas)
+    orc, ref, d = run_both(p, alphas, fp32_pairs=fp32)
     AB = d.pair(0, p.ncells)
     gp0 = orc.gp0()
     for c in (0, 7, 29):
