@@ -32,7 +32,17 @@ ABI_SYMBOLS = [
     "dmx_upload", "dmx_compute", "dmx_run", "dmx_get_best", "dmx_get_single", "dmx_get_sing2", "dmx_get_pair",
     "dmx_rescore", "dmx_exact_llk", "dmx_write_outputs", "dmx_get_stats", "dmx_alloc_host", "dmx_free_host", "dmx_strerror",
     "dmx_last_error", "dmx_abi_version", "dmx_pack_reads", "dmx_pileup_sizes", "dmx_pileup_copy", "dmx_pileup_free",
+    "dmx_build_gp", "dmx_build_gp_device", "dmx_set_field",
 ]
+
+DMX_FIELD = {"GT": 0, "GP": 1, "PL": 2}            # --field (cmd_cram_demuxlet.cpp:28, :45)
+_FIELD_DTYPE = {0: np.int8, 1: np.float32, 2: np.int32}
+
+
+class DmxFieldStats(C.Structure):
+    _fields_ = [("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("gpu_launches", C.c_int64),
+                ("algo_bytes", C.c_double)]
 
 
 class DmxConfig(C.Structure):
@@ -106,6 +116,11 @@ def load_library(path: Optional[str] = None):
     lib.dmx_get_stats.argtypes = [C.c_void_p, C.POINTER(DmxStats)]
     lib.dmx_config_default.argtypes = [C.POINTER(DmxConfig)]
     lib.dmx_config_default.restype = None
+    lib.dmx_build_gp.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_double, C.c_void_p,
+                                 C.c_void_p, C.POINTER(DmxFieldStats)]
+    lib.dmx_build_gp_device.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_double, C.c_void_p,
+                                        C.c_int64, C.c_void_p, C.c_void_p]
+    lib.dmx_set_field.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_double]
     if path is None:
         _lib = lib
     return lib
@@ -135,6 +150,38 @@ def exact_llk(plp: Pileup, alphas: Sequence[float], cell: int, j: int, k: int, n
     if rc != 0:
         raise DmxError(rc, "dmx_exact_llk")
     return out.value
+
+
+def _field_array(field, arr):
+    code = DMX_FIELD[field] if isinstance(field, str) else int(field)
+    a = np.ascontiguousarray(arr, dtype=_FIELD_DTYPE[code])
+    if a.ndim != 3 or a.shape[2] != (2 if code == 0 else 3):
+        raise ValueError("field array must be [nsnps][nv][%d]" % (2 if code == 0 else 3))
+    return code, a
+
+
+def build_gp(field, arr, gt_error: float = 0.01, device: int = 0, want_af: bool = False, out=None,
+             want_stats: bool = False):
+    """VCF FORMAT field -> float32[nsnps][nv][3] on the GPU, bit-identical to the reference's
+    BCFFilteredReader::parse_posteriors (/root/reference/bcf_filtered_reader.cpp:360-454).
+    field "GT": int8[nsnps][nv][2] allele indices (< 0 missing); "GP": float32[nsnps][nv][3]; "PL": int32[nsnps][nv][3].
+    No CPU fallback: raises DmxError without an sm_100 device."""
+    lib = load_library()
+    code, a = _field_array(field, arr)
+    nsnps, nv = a.shape[0], a.shape[1]
+    if out is None:
+        out = np.empty((nsnps, nv, 3), np.float32)
+    assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape == (nsnps, nv, 3)
+    af = np.zeros(nsnps, np.float64) if want_af else None
+    st = DmxFieldStats()
+    rc = lib.dmx_build_gp(device, code, nv, nsnps, a.ctypes.data, gt_error, out.ctypes.data,
+                          af.ctypes.data if want_af else None, C.byref(st))
+    if rc != 0:
+        raise DmxError(rc, "dmx_build_gp")
+    res = (out, af) if want_af else out
+    if want_stats:
+        return res, {k: getattr(st, k) for k, _ in DmxFieldStats._fields_}
+    return res
 
 
 def encode_umis(umis: Sequence[str]):
@@ -254,6 +301,12 @@ class Demuxlet:
         assert gp.dtype == np.float32 and gp.flags.c_contiguous and gp.shape[1:] == (self.nv, 3)
         self._gp = gp
         self._chk(self.lib.dmx_set_gp(self._h, gp.ctypes.data, gp.shape[0]), "dmx_set_gp")
+
+    def set_field(self, field, arr, gt_error: float = 0.01):
+        """set_gp from a VCF field (GT / GP / PL arrays as build_gp takes them): the matrix is built on the device"""
+        code, a = _field_array(field, arr)
+        assert a.shape[1] == self.nv
+        self._chk(self.lib.dmx_set_field(self._h, code, a.ctypes.data, a.shape[0], gt_error), "dmx_set_field")
 
     def set_pileup_arrays(self, cell_ptr, ent_snp, ent_ptr, reads, totl, npass, uniq):
         self._keep = [cell_ptr, ent_snp, ent_ptr, reads, totl, npass, uniq]

@@ -1315,4 +1315,217 @@ int dmx_write_outputs(dmx_ctx* c, const char* const* barcodes, const char* const
   return rc;
 }
 
+
+// ---- VCF field -> genotype-probability matrix (kernels in dmx_field.cu) -------------------------------------------
+namespace {
+
+size_t field_in_bytes(int field, int nv) { return field == DMX_FIELD_GT ? (size_t)nv * 2 : (size_t)nv * 12; }
+
+int field_device_ok(int device, int* sm_count) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+    g_last_error = "no CUDA device";
+    return DMX_E_NODEVICE;
+  }
+  int major = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+  if (major != 10) {
+    g_last_error = "device is not compute capability 10.x";
+    return DMX_E_NODEVICE;
+  }
+  CU(cudaSetDevice(device));
+  CU(cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, device));
+  return DMX_OK;
+}
+
+// phred2Prob (PhredHelper.cpp:32) with the host libm's pow(): the table the reference's EM multiplies by
+void field_prob_table(double* t) {
+  for (int i = 0; i <= 255; ++i) t[i] = pow(0.1, i * 0.1);
+}
+
+// scratch shared by the field entry points of one call: the phred table and the error flag
+struct FieldScratch {
+  double* d_prob = nullptr;
+  int* d_flag = nullptr;
+  ~FieldScratch() {
+    if (d_prob) cudaFree(d_prob);
+    if (d_flag) cudaFree(d_flag);
+  }
+  int init(cudaStream_t st) {
+    double t[256];
+    field_prob_table(t);
+    CU(cudaMalloc((void**)&d_prob, sizeof(t)));
+    CU(cudaMalloc((void**)&d_flag, sizeof(int)));
+    CU(cudaMemcpyAsync(d_prob, t, sizeof(t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+    CU(cudaStreamSynchronize(st));   // t lives on this stack frame
+    return DMX_OK;
+  }
+  int check(cudaStream_t st) {       // after the kernels: a GT allele index > 1 is not a biallelic record
+    int flag = 0;
+    CU(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return flag ? DMX_E_INVALID : DMX_OK;
+  }
+};
+
+// per-device cache for dmx_build_gp_device, which must not allocate or synchronise per call
+struct FieldDevCache {
+  double* d_prob = nullptr;
+  int* d_flag = nullptr;
+  int sm_count = 0;
+};
+FieldDevCache g_field_cache[64];
+std::mutex g_field_mu;
+
+}  // namespace
+
+int dmx_build_gp_device(int32_t device, int32_t field, int32_t nv, int64_t nsnps, const void* d_in, double gt_error,
+                        float* d_out, int64_t out_stride, double* d_af, void* stream) {
+  if (field < DMX_FIELD_GT || field > DMX_FIELD_PL || nv < 1 || nv > 4095 || nsnps < 0 || out_stride < (int64_t)nv * 3)
+    return DMX_E_INVALID;
+  if (nsnps > 0 && (!d_in || !d_out)) return DMX_E_INVALID;
+  if (device < 0 || device >= 64) return DMX_E_INVALID;
+  FieldDevCache* fc = &g_field_cache[device];
+  {
+    std::lock_guard<std::mutex> lk(g_field_mu);
+    if (!fc->d_prob) {
+      int smc = 0;
+      RC(field_device_ok(device, &smc));
+      double t[256];
+      field_prob_table(t);
+      CU(cudaMalloc((void**)&fc->d_flag, sizeof(int)));
+      CU(cudaMemset(fc->d_flag, 0, sizeof(int)));
+      double* dp = nullptr;
+      CU(cudaMalloc((void**)&dp, sizeof(t)));
+      CU(cudaMemcpy(dp, t, sizeof(t), cudaMemcpyHostToDevice));
+      fc->sm_count = smc;
+      fc->d_prob = dp;
+    }
+  }
+  CU(cudaSetDevice(device));
+  FieldParams fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.field = field; fp.nv = nv; fp.nsnps = nsnps; fp.in = d_in; fp.out = d_out; fp.out_stride = out_stride;
+  fp.af = d_af; fp.gt_error = gt_error; fp.prob = fc->d_prob; fp.err_flag = fc->d_flag;
+  CU(launch_field(fp, fc->sm_count, stream));
+  return DMX_OK;
+}
+
+int dmx_build_gp(int32_t device, int32_t field, int32_t nv, int64_t nsnps, const void* in, double gt_error,
+                 float* gp_out, double* af_out, dmx_field_stats* stats) {
+  if (field < DMX_FIELD_GT || field > DMX_FIELD_PL || nv < 1 || nv > 4095 || nsnps < 0) return DMX_E_INVALID;
+  if (nsnps > 0 && (!in || !gp_out)) return DMX_E_INVALID;
+  int sm_count = 0;
+  RC(field_device_ok(device, &sm_count));
+  const double t0 = now_ms();
+  const size_t in_row = field_in_bytes(field, nv), out_row = (size_t)nv * 12;
+  // chunks of ~16 MB of output: copies of one chunk overlap the kernel of the other (two streams, two buffer sets)
+  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(nsnps, 1), (16 << 20) / (int64_t)out_row));
+  struct Side {
+    cudaStream_t st = nullptr;
+    void* d_in = nullptr;
+    float* d_out = nullptr;
+    double* d_af = nullptr;
+    ~Side() {
+      if (d_in) cudaFree(d_in);
+      if (d_out) cudaFree(d_out);
+      if (d_af) cudaFree(d_af);
+      if (st) cudaStreamDestroy(st);
+    }
+  } side[2];
+  std::vector<cudaEvent_t> evs;
+  struct EvGuard {
+    std::vector<cudaEvent_t>* v;
+    ~EvGuard() { for (cudaEvent_t e : *v) cudaEventDestroy(e); }
+  } evguard{&evs};
+  const int nside = nsnps > chunk ? 2 : 1;
+  for (int i = 0; i < nside; ++i) {
+    CU(cudaStreamCreateWithFlags(&side[i].st, cudaStreamNonBlocking));
+    CU(cudaMalloc(&side[i].d_in, (size_t)chunk * in_row));
+    CU(cudaMalloc((void**)&side[i].d_out, (size_t)chunk * out_row));
+    if (af_out) CU(cudaMalloc((void**)&side[i].d_af, (size_t)chunk * sizeof(double)));
+  }
+  FieldScratch sc;
+  RC(sc.init(side[0].st));
+  int64_t launches = 0;
+  int k = 0;
+  for (int64_t s0 = 0; s0 < nsnps; s0 += chunk, ++k) {
+    Side& sd = side[k % nside];
+    const int64_t n = std::min(chunk, nsnps - s0);
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); evs.push_back(e0);
+    CU(cudaEventCreate(&e1)); evs.push_back(e1);
+    CU(cudaMemcpyAsync(sd.d_in, (const char*)in + (size_t)s0 * in_row, (size_t)n * in_row, cudaMemcpyHostToDevice, sd.st));
+    FieldParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.field = field; fp.nv = nv; fp.nsnps = n; fp.in = sd.d_in; fp.out = sd.d_out; fp.out_stride = (int64_t)nv * 3;
+    fp.af = af_out ? sd.d_af : nullptr; fp.gt_error = gt_error; fp.prob = sc.d_prob; fp.err_flag = sc.d_flag;
+    CU(cudaEventRecord(e0, sd.st));
+    CU(launch_field(fp, sm_count, sd.st));
+    CU(cudaEventRecord(e1, sd.st));
+    ++launches;
+    CU(cudaMemcpyAsync((char*)gp_out + (size_t)s0 * out_row, sd.d_out, (size_t)n * out_row, cudaMemcpyDeviceToHost, sd.st));
+    if (af_out && field != DMX_FIELD_GP)
+      CU(cudaMemcpyAsync(af_out + s0, sd.d_af, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, sd.st));
+  }
+  for (int i = 0; i < nside; ++i) CU(cudaStreamSynchronize(side[i].st));
+  const int rc = sc.check(side[0].st);
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    for (size_t i = 0; i + 1 < evs.size(); i += 2) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, evs[i], evs[i + 1]);
+      stats->kernel_ms += ms;
+    }
+    stats->total_ms = now_ms() - t0;
+    stats->h2d_bytes = (int64_t)nsnps * (int64_t)in_row;
+    stats->d2h_bytes = (int64_t)nsnps * (int64_t)(out_row + (af_out && field != DMX_FIELD_GP ? 8 : 0));
+    stats->gpu_launches = launches;
+    stats->algo_bytes = (double)nsnps * (double)(in_row + out_row);
+  }
+  if (rc != DMX_OK) g_last_error = "GT allele index > 1: not a biallelic record";
+  return rc;
+}
+
+int dmx_set_field(dmx_ctx* c, int32_t field, const void* in, int64_t nsnps, double gt_error) {
+  if (!c || nsnps < 0 || (nsnps > 0 && !in) || field < DMX_FIELD_GT || field > DMX_FIELD_PL) return DMX_E_INVALID;
+  CU(cudaSetDevice(c->cfg.device));
+  const int nv = c->cfg.nv, nvp = c->nvp;
+  const size_t in_bytes = (size_t)nsnps * field_in_bytes(field, nv), n = (size_t)nsnps * nv * 3;
+  int sm_count = 0;
+  CU(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, c->cfg.device));
+  CU(cudaStreamSynchronize(c->stream));
+  c->nsnps = nsnps;
+  CU(c->d_gp.reserve((size_t)nsnps * nvp * 3 + 4));
+  CU(c->o_gp.reserve(n));
+  DevBuf<unsigned char> d_in;
+  struct Rel { DevBuf<unsigned char>* b; ~Rel() { b->release(); } } rel{&d_in};
+  CU(d_in.reserve(in_bytes));
+  FieldScratch sc;
+  RC(sc.init(c->stream));
+  CU(cudaMemcpyAsync(d_in.p, in, in_bytes, cudaMemcpyHostToDevice, c->stream));
+  if (nvp != nv) CU(cudaMemsetAsync(c->d_gp.p, 0, (size_t)nsnps * nvp * 3 * sizeof(float), c->stream));
+  FieldParams fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.field = field; fp.nv = nv; fp.nsnps = nsnps; fp.in = d_in.p; fp.out = c->d_gp.p; fp.out_stride = (int64_t)nvp * 3;
+  fp.gt_error = gt_error; fp.prob = sc.d_prob; fp.err_flag = sc.d_flag;
+  CU(launch_field(fp, sm_count, c->stream));
+  if (nsnps)
+    CU(cudaMemcpy2DAsync(c->o_gp.p, (size_t)nv * 12, c->d_gp.p, (size_t)nvp * 12, (size_t)nv * 12, (size_t)nsnps,
+                         cudaMemcpyDeviceToHost, c->stream));
+  const int rc = sc.check(c->stream);
+  c->have_gp = false;
+  if (rc != DMX_OK) {
+    g_last_error = "GT allele index > 1: not a biallelic record";
+    return rc;
+  }
+  c->h_gp = c->o_gp.p;
+  c->have_gp = true;
+  c->gp_dirty = false;     // the device copy is already in place: dmx_upload / dmx_run skip the matrix
+  c->uploaded = false;
+  c->computed = false;
+  return DMX_OK;
+}
+
 }  // extern "C"

@@ -209,6 +209,21 @@ struct CellScalarParams {
   double* l00;                     // [ncells][nA]
 };
 
+// VCF field -> genotype probabilities (dmx_field.cu; bcf_filtered_reader.cpp:186-320, :360-454)
+struct FieldParams {
+  int32_t field, nv;           // DMX_FIELD_*
+  int64_t nsnps;
+  const void* in;              // device: GT int8[nsnps][nv][2], GP float[nsnps][nv][3], PL int32[nsnps][nv][3]
+  float* out;                  // device: [nsnps][out_stride], the first nv * 3 floats of a row are written
+  int64_t out_stride;
+  double* af;                  // device [nsnps] or null: get_af(1) (GT / PL)
+  double gt_error;
+  const double* prob;          // device [256]: phred2Prob (PhredHelper.cpp:32), PL only
+  int* err_flag;               // device: set when a GT allele index is > 1
+};
+size_t field_smem_per_warp(int field, int nv);
+int launch_field(const FieldParams& p, int sm_count, void* stream);
+
 // host-callable launchers (dmx_kernels.cu); all return a cudaError_t as int
 int launch_gprow(const float* gp_flat, float* gp_rows, int64_t nsnps, int nv, int nvp, void* stream);
 int launch_entq(const EntqParams& p, void* stream);

@@ -176,6 +176,40 @@ int dmx_pileup_copy(const dmx_pileup* p, int64_t* cell_ptr, int32_t* ent_snp, in
                     int32_t* pass, int32_t* uniq);
 void dmx_pileup_free(dmx_pileup* p);
 
+/* ---- VCF field -> genotype-probability matrix (device) ----------------------------------------------
+ * Replaces, per biallelic diploid VCF record, BCFFilteredReader::parse_posteriors
+ * (bcf_filtered_reader.cpp:360-454) with parse_genotypes (:186-242) for --field GT and the ten-iteration EM of
+ * parse_likelihoods (:244-320) for --field PL, i.e. what cmd_cram_demuxlet.cpp:153,:211 call and :227-231 widen
+ * into scl.snps[i].gps.  The output is bit-identical to the reference's floats.
+ *   DMX_FIELD_GT  in = int8[nsnps][nv][2]   allele indices as bcf_gt_allele() decodes them: 0 ref, 1 alt, < 0 missing
+ *                                           (minDP / minGQ masking, :203-226, applied by the caller)
+ *   DMX_FIELD_GP  in = float[nsnps][nv][3]  the FORMAT floats as bcf_get_format_float returns them
+ *   DMX_FIELD_PL  in = int32[nsnps][nv][3]  the FORMAT integers (missing = INT32_MIN reads as phred 255, PhredHelper.h:40)
+ * gt_error is --geno-error (cmd_cram_demuxlet.cpp:30, :153); PL ignores it, as the reference does.
+ * All nv samples are the selected ones (sm_icols), ploidy 2 (bcf_filtered_reader.cpp:152-153). */
+#define DMX_FIELD_GT 0
+#define DMX_FIELD_GP 1
+#define DMX_FIELD_PL 2
+
+typedef struct {
+  double h2d_ms, kernel_ms, d2h_ms, total_ms;   /* kernel_ms: CUDA events around the field kernel(s) */
+  int64_t h2d_bytes, d2h_bytes, gpu_launches;
+  double algo_bytes;                            /* bytes every launch must move: input + 12 * nv per SNP */
+} dmx_field_stats;
+
+/* host buffers in and out: gp_out[nsnps][nv][3] is what dmx_set_gp takes; af_out[nsnps] (nullable) = get_af(1)
+ * (bcf_filtered_reader.h:177-179; GT and PL).  SNP chunks are copied, transformed and read back on two streams;
+ * pass dmx_alloc_host buffers for overlapped copies.  stats may be null. */
+int dmx_build_gp(int32_t device, int32_t field, int32_t nv, int64_t nsnps, const void* in, double gt_error,
+                 float* gp_out, double* af_out, dmx_field_stats* stats);
+/* the same on DEVICE pointers (input, output rows of out_stride floats, nullable af), enqueued on `stream`
+ * (a cudaStream_t, or null); returns after the launch */
+int dmx_build_gp_device(int32_t device, int32_t field, int32_t nv, int64_t nsnps, const void* d_in, double gt_error,
+                        float* d_out, int64_t out_stride, double* d_af, void* stream);
+/* dmx_set_gp from a VCF field: builds the matrix into the context's device copy (no second upload) and keeps the
+ * read-back on the host for the tie finaliser */
+int dmx_set_field(dmx_ctx* ctx, int32_t field, const void* in, int64_t nsnps, double gt_error);
+
 /* pinned host memory for DMX_BORROW_INPUTS callers */
 void* dmx_alloc_host(int64_t bytes);
 void dmx_free_host(void* p);

@@ -110,6 +110,16 @@ int orc_write_all(const orc_input* in, const char* const* barcodes,
  * llksAB[j][k][n] != llksAB[k][j][n] bitwise in this cell */
 int64_t orc_count_asym(const orc_input* in, const double* llksAB, int32_t n);
 
+/* ---- VCF field -> genotype probabilities (dmx_field_oracle.c) ----
+ * restatement of /root/reference/bcf_filtered_reader.cpp:186-320, :360-454 per biallelic diploid record.
+ * field: 0 GT (in = int8[nsnps][nv][2], htslib-decoded allele indices, -1 missing), 1 GP (float[nsnps][nv][3]),
+ * 2 PL (int32[nsnps][nv][3]); out float[nsnps][nv][3]; af[nsnps] = get_af(1) or NULL (GT / PL only) */
+void orc_field_gt(int32_t nv, const int8_t* al, double gt_error, float* out, double* af);
+void orc_field_pl(int32_t nv, const int32_t* pl, float* out, double* af);
+void orc_field_gp(int32_t nv, const float* raw, double gt_error, float* out);
+int orc_build_gp(int32_t field, int32_t nv, int64_t nsnps, const void* in, double gt_error, float* out, double* af,
+                 int32_t nthreads);
+
 #ifdef __cplusplus
 }
 #endif

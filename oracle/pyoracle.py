@@ -156,3 +156,60 @@ def run_ref(plp, prefix, alphas=None, write_pair=False, doublet_prior=None, min_
         if tmp is not None:
             os.unlink(plp_path)
     return json.loads(out.stdout.decode().strip().splitlines()[-1])
+
+
+# ---- VCF field -> genotype probabilities ----------------------------------------------------------
+REF_FIELD_BIN = os.path.join(HERE, "_ref", "ref_field")
+FIELD_CODE = {"GT": 0, "GP": 1, "PL": 2}
+FIELD_DTYPE = {0: np.int8, 1: np.float32, 2: np.int32}
+
+
+def _field_array(field, arr):
+    code = FIELD_CODE[field] if isinstance(field, str) else int(field)
+    a = np.ascontiguousarray(arr, dtype=FIELD_DTYPE[code])
+    if a.ndim != 3 or a.shape[2] != (2 if code == 0 else 3):
+        raise ValueError("field array must be [nsnps][nv][%d]" % (2 if code == 0 else 3))
+    return code, a
+
+
+def build_gp(field, arr, gt_error: float = 0.01, nthreads: int = 1, want_af: bool = False):
+    """oracle/dmx_field_oracle.c: float32[nsnps][nv][3] (and get_af(1) per SNP) from a GT / GP / PL array."""
+    code, a = _field_array(field, arr)
+    nsnps, nv = a.shape[0], a.shape[1]
+    out = np.empty((nsnps, nv, 3), np.float32)
+    af = np.zeros(nsnps, np.float64)
+    rc = lib().orc_build_gp(C.c_int32(code), C.c_int32(nv), C.c_int64(nsnps), a.ctypes.data_as(C.c_void_p),
+                            C.c_double(gt_error), out.ctypes.data_as(C.c_void_p), af.ctypes.data_as(C.c_void_p),
+                            C.c_int32(nthreads))
+    if rc != 0:
+        raise ValueError("orc_build_gp: %d" % rc)
+    return (out, af) if want_af else out
+
+
+def ref_field_available() -> bool:
+    return os.path.exists(REF_FIELD_BIN) and os.access(REF_FIELD_BIN, os.X_OK)
+
+
+def write_field_file(path, field, arr, gt_error: float):
+    code, a = _field_array(field, arr)
+    with open(path, "wb") as f:
+        f.write(np.array([code, a.shape[1]], np.int32).tobytes())
+        f.write(np.array([a.shape[0]], np.int64).tobytes())
+        f.write(np.array([gt_error], np.float64).tobytes())
+        f.write(a.tobytes())
+    return code, a
+
+
+def run_ref_field(field, arr, gt_error: float = 0.01, want_af: bool = False):
+    """The reference's own parse_posteriors / parse_genotypes / parse_likelihoods (oracle/_ref/ref_field)."""
+    if not ref_field_available():
+        raise FileNotFoundError(REF_FIELD_BIN)
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, "in.fld"), os.path.join(td, "out.gp")
+        code, a = write_field_file(fin, field, arr, gt_error)
+        subprocess.run([REF_FIELD_BIN, fin, fout], check=True)
+        nsnps, nv = a.shape[0], a.shape[1]
+        raw = np.fromfile(fout, np.uint8)
+    gp = raw[: nsnps * nv * 12].view(np.float32).reshape(nsnps, nv, 3).copy()
+    af = raw[nsnps * nv * 12:].view(np.float64).copy()
+    return (gp, af) if want_af else gp
