@@ -220,8 +220,8 @@ struct FieldParams {
   double gt_error;
   const double* prob;          // device [256]: phred2Prob (PhredHelper.cpp:32), PL only
   int* err_flag;               // device: set when a GT allele index is > 1
+  int32_t group, pitch;        // filled by launch_field: SNPs per warp pass, shared-memory row pitch (elements)
 };
-size_t field_smem_per_warp(int field, int nv);
 int launch_field(const FieldParams& p, int sm_count, void* stream);
 
 // host-callable launchers (dmx_kernels.cu); all return a cudaError_t as int
