@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -1195,6 +1196,39 @@ int dmx_get_stats(dmx_ctx* c, dmx_stats* out) {
 }
 
 // ---- writers ---------------------------------------------------------------------------------------
+namespace {
+
+// printf into a growing text buffer (rows carry caller-supplied names of any length)
+void appendf(std::string& out, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
+void appendf(std::string& out, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  const int n = vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (n < 0) return;
+  if ((size_t)n < sizeof(buf)) {
+    out.append(buf, (size_t)n);
+    return;
+  }
+  const size_t at = out.size();
+  out.resize(at + (size_t)n + 1);
+  va_start(ap, fmt);
+  vsnprintf(&out[at], (size_t)n + 1, fmt, ap);
+  va_end(ap);
+  out.resize(at + (size_t)n);
+}
+
+bool write_all(FILE* f, const std::vector<std::string>& bufs) {
+  for (const std::string& b : bufs)
+    if (!b.empty() && fwrite(b.data(), 1, b.size(), f) != b.size()) return false;
+  return true;
+}
+
+}  // namespace
+
+// The rows are formatted by the context's host threads (blocks of cells in output order into per-block text buffers,
+// the reference's printf formats) and written to the files in order by the calling thread.
 int dmx_write_outputs(dmx_ctx* c, const char* const* barcodes, const char* const* samples, const char* prefix,
                       int write_pair) {
   if (!c || !barcodes || !samples || !prefix) return DMX_E_INVALID;
@@ -1202,32 +1236,45 @@ int dmx_write_outputs(dmx_ctx* c, const char* const* barcodes, const char* const
   const int nv = c->cfg.nv, nA = c->cfg.n_alpha;
   const double dp = c->cfg.doublet_prior;
   const int64_t nc = c->ncells;
+  const int nth = host_threads(c);
   // std::map<std::string,int32_t> iteration order (:472, :576)
   std::vector<int32_t> ord(nc);
   for (int64_t i = 0; i < nc; ++i) ord[i] = (int32_t)i;
-  std::sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) { return std::string(barcodes[a]) < std::string(barcodes[b]); });
+  std::sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) { return strcmp(barcodes[a], barcodes[b]) < 0; });
   const std::string pre(prefix);
-  FILE* ws = nullptr;
+  const int64_t CB = 16;                                                  // cells per formatting block
+  const int64_t slab = std::max<int64_t>(CB, (int64_t)nth * CB * 8);      // cells formatted between two writes
+  std::vector<std::string> bufs, bufs2, bufsb;
+  bool io_ok = true;
   if (!(c->cfg.flags & DMX_SKIP_SINGLE)) {
-    ws = fopen((pre + ".single").c_str(), "w");
+    FILE* ws = fopen((pre + ".single").c_str(), "w");
     if (!ws) return DMX_E_IO;                                           // :409
     fprintf(ws, "BARCODE\tSM_ID\tRD.TOTL\tRD.PASS\tRD.UNIQ\tN.SNP\tLLK1\tLLK0\tPOSTPRB\n");   // :470
-    for (int64_t oi = 0; oi < nc; ++oi) {
-      const int32_t i = ord[oi];
-      if (c->status[i] == 1) continue;                                  // :480
-      const double* llks = c->r_p1.p + (size_t)i * nv;
-      double sumLLK = -1e300;                                           // :478-489
-      for (int j = 0; j < nv; ++j) {
-        const double cur = llks[j];
-        if (sumLLK > cur) sumLLK = sumLLK + log(1.0 + exp(cur - sumLLK));
-        else sumLLK = cur + log(1.0 + exp(sumLLK - cur));
-      }
-      const int nsnp = (int)(c->h_cell_ptr[i + 1] - c->h_cell_ptr[i]);
-      for (int j = 0; j < nv; ++j)                                      // :506
-        fprintf(ws, "%s\t%s\t%d\t%d\t%d\t%d\t%.5lf\t%.5lf\t%.3lg\n", barcodes[i], samples[j], c->totl[i],
-                c->npass[i], c->uniq[i], nsnp, llks[j], c->r_p1_0.p[i], exp(llks[j] - sumLLK));
+    for (int64_t o0 = 0; o0 < nc && io_ok; o0 += slab) {
+      const int64_t o1 = std::min(nc, o0 + slab), nblk = (o1 - o0 + CB - 1) / CB;
+      bufs.assign((size_t)nblk, std::string());
+      c->pool->run(nblk, nth, [&](int64_t blk, int) {
+        std::string& out = bufs[(size_t)blk];
+        for (int64_t oi = o0 + blk * CB; oi < std::min(o1, o0 + (blk + 1) * CB); ++oi) {
+          const int32_t i = ord[oi];
+          if (c->status[i] == 1) continue;                              // :480
+          const double* llks = c->r_p1.p + (size_t)i * nv;
+          double sumLLK = -1e300;                                       // :478-489
+          for (int j = 0; j < nv; ++j) {
+            const double cur = llks[j];
+            if (sumLLK > cur) sumLLK = sumLLK + log(1.0 + exp(cur - sumLLK));
+            else sumLLK = cur + log(1.0 + exp(sumLLK - cur));
+          }
+          const int nsnp = (int)(c->h_cell_ptr[i + 1] - c->h_cell_ptr[i]);
+          for (int j = 0; j < nv; ++j)                                  // :506
+            appendf(out, "%s\t%s\t%d\t%d\t%d\t%d\t%.5lf\t%.5lf\t%.3lg\n", barcodes[i], samples[j], c->totl[i],
+                    c->npass[i], c->uniq[i], nsnp, llks[j], c->r_p1_0.p[i], exp(llks[j] - sumLLK));
+        }
+      });
+      io_ok = write_all(ws, bufs);
     }
-    fclose(ws);
+    if (fclose(ws) != 0) io_ok = false;
+    if (!io_ok) return DMX_E_IO;
   }
   FILE* w2 = fopen((pre + ".sing2").c_str(), "w");
   FILE* wb = fopen((pre + ".best").c_str(), "w");
@@ -1243,78 +1290,89 @@ int dmx_write_outputs(dmx_ctx* c, const char* const* barcodes, const char* const
   fprintf(wb,
           "BARCODE\tRD.TOTL\tRD.PASS\tRD.UNIQ\tN.SNP\tBEST\tSNG.1ST\tSNG.LLK1\tSNG.2ND\tSNG.LLK2\tSNG.LLK0\tDBL.1ST\t"
           "DBL.2ND\tALPHA\tLLK12\tLLK1\tLLK2\tLLK10\tLLK20\tLLK00\tPRB.DBL\tPRB.SNG1\n");      // :571
+  // cells with a row, in output order (:581, :592)
+  std::vector<int32_t> live;
+  live.reserve((size_t)nc);
+  for (int64_t oi = 0; oi < nc; ++oi)
+    if (c->status[ord[oi]] == 0) live.push_back(ord[oi]);
+  const int64_t nl = (int64_t)live.size();
   const size_t per = (size_t)nv * nv * nA;
   std::vector<double> dense;
+  // with --write-pair a slab is what one dense re-scan covers (64 MB of llksAB)
   const int64_t pair_batch = std::max<int64_t>(1, ((int64_t)64 << 20) / (int64_t)(per * sizeof(double)));
-  int64_t dense_lo = 0, dense_hi = 0;   // positions in `ord` covered by `dense`
+  const int64_t step = wp ? pair_batch : slab;
+  const int64_t cb = wp ? 1 : CB;
+  std::vector<std::string> bufsp;
   int rc = DMX_OK;
-  for (int64_t oi = 0; oi < nc && rc == DMX_OK; ++oi) {
-    const int32_t i = ord[oi];
-    if (c->status[i] != 0) continue;                                    // :581, :592
-    const dmx_best_rec& b = c->best[i];
-    const double* sing = c->r_sing.p + (size_t)i * nv;
-    const double l00_0 = c->r_l00.p[(size_t)i * nA];
-    // exact values where the finaliser produced them
-    auto sv = [&](int j) {
-      if (j == b.sng1) return b.sng_llk1;
-      if (j == b.sng2) return b.sng_llk2;
-      if (j == b.dbl1) return b.llk1;
-      if (j == b.dbl2) return b.llk2;
-      return sing[j];
-    };
-    for (int j = 0; j < nv; ++j)                                        // :760-769
-      fprintf(w2, "%s\t%s\t%d\t%d\t%d\t%d\t%.4lf\t%.4lf\t%.3lg\n", barcodes[i], samples[j], c->totl[i], c->npass[i],
-              c->uniq[i], b.n_snp, sv(j), l00_0, exp(sv(j) - b.max_llk) * (1. - dp) / nv / b.sum_single);
-    if (wp) {                                                           // :772-797
-      if (oi >= dense_hi) {
-        // next batch of cells in output order
-        std::vector<int32_t> cells;
-        dense_lo = oi;
-        int64_t o2 = oi;
-        for (; o2 < nc && (int64_t)cells.size() < pair_batch; ++o2)
-          if (c->status[ord[o2]] == 0) cells.push_back(ord[o2]);
-        dense_hi = o2;
-        dense.resize(cells.size() * per);
-        rc = dense_scan(c, cells, dense.data());
-        if (rc != DMX_OK) break;
-      }
-      size_t pos = 0;
-      for (int64_t o2 = dense_lo; o2 < oi; ++o2)
-        if (c->status[ord[o2]] == 0) ++pos;
-      const double* AB = dense.data() + pos * per;
-      for (int j = 0; j < nv; ++j) {
-        fprintf(wp, "%s\t%s\t%s\t%.3lf\t%.5lf\t%.5lg\n", barcodes[i], samples[j], samples[j], c->alpha[0], sv(j),
-                exp(sv(j) - b.max_llk) * (1. - dp) / nv / (b.sum_single + b.sum_double));
-        for (int k = 0; k < nv; ++k)
-          for (int n = 0; n < nA; ++n)
-            if (n > 0 && j != k) {
-              if (j > k && c->alpha[n] == 0.5) continue;                // :785
-              double v = AB[((size_t)j * nv + k) * nA + n];
-              if (j == b.dbl1 && k == b.dbl2 && n == b.alpha_idx) v = b.llk12;
-              fprintf(wp, "%s\t%s\t%s\t%.3lf\t%.5lf\t%.5lg\n", barcodes[i], samples[j], samples[k], c->alpha[n], v,
-                      exp(v - b.max_llk) * dp / nv / (nv - 1) / (nA - 1) / (b.sum_single + b.sum_double));
-            }
-      }
+  for (int64_t l0 = 0; l0 < nl && rc == DMX_OK && io_ok; l0 += step) {
+    const int64_t l1 = std::min(nl, l0 + step), nblk = (l1 - l0 + cb - 1) / cb;
+    if (wp) {
+      std::vector<int32_t> cells(live.begin() + l0, live.begin() + l1);
+      dense.resize(cells.size() * per);
+      rc = dense_scan(c, cells, dense.data());
+      if (rc != DMX_OK) break;
+      bufsp.assign((size_t)nblk, std::string());
     }
-    fprintf(wb, "%s\t%d\t%d\t%d\t%d\t", barcodes[i], c->totl[i], c->npass[i], c->uniq[i], b.n_snp);   // :830
-    if (b.call == 0)
-      fprintf(wb, "DBL-%s-%s-%.3lf", samples[b.dbl1], samples[b.dbl2], c->alpha[b.alpha_idx]);       // :838
-    else if (b.call == 1)
-      fprintf(wb, "SNG-%s", samples[b.sng1]);                                                          // :845
-    else
-      fprintf(wb, "AMB-%s-%s-%s/%s", samples[b.sng1], samples[b.sng2], samples[b.dbl1], samples[b.dbl2]);   // :851
-    fprintf(wb, "\t%s\t%.4lf", samples[b.sng1], b.sng_llk1);
-    fprintf(wb, "\t%s\t%.4lf\t%.4lf", samples[b.sng2], b.sng_llk2, b.sng_llk0);
-    fprintf(wb, "\t%s\t%s\t%.3lf\t%.4lf\t%.4lf\t%.4lf\t%.4lf\t%.4lf\t%.4lf\t%.3lg\t%.3lg\n", samples[b.dbl1],
-            samples[b.dbl2], c->alpha[b.alpha_idx], b.llk12, b.llk1, b.llk2, b.llk10, b.llk20, b.llk00, b.prb_dbl,
-            b.prb_sng1);
+    bufs2.assign((size_t)nblk, std::string());
+    bufsb.assign((size_t)nblk, std::string());
+    c->pool->run(nblk, nth, [&](int64_t blk, int) {
+      std::string& o2 = bufs2[(size_t)blk];
+      std::string& ob = bufsb[(size_t)blk];
+      for (int64_t li = l0 + blk * cb; li < std::min(l1, l0 + (blk + 1) * cb); ++li) {
+        const int32_t i = live[(size_t)li];
+        const dmx_best_rec& b = c->best[i];
+        const double* sing = c->r_sing.p + (size_t)i * nv;
+        const double l00_0 = c->r_l00.p[(size_t)i * nA];
+        // exact values where the finaliser produced them
+        auto sv = [&](int j) {
+          if (j == b.sng1) return b.sng_llk1;
+          if (j == b.sng2) return b.sng_llk2;
+          if (j == b.dbl1) return b.llk1;
+          if (j == b.dbl2) return b.llk2;
+          return sing[j];
+        };
+        for (int j = 0; j < nv; ++j)                                      // :760-769
+          appendf(o2, "%s\t%s\t%d\t%d\t%d\t%d\t%.4lf\t%.4lf\t%.3lg\n", barcodes[i], samples[j], c->totl[i], c->npass[i],
+                  c->uniq[i], b.n_snp, sv(j), l00_0, exp(sv(j) - b.max_llk) * (1. - dp) / nv / b.sum_single);
+        if (wp) {                                                         // :772-797
+          std::string& op = bufsp[(size_t)blk];
+          const double* AB = dense.data() + (size_t)(li - l0) * per;
+          for (int j = 0; j < nv; ++j) {
+            appendf(op, "%s\t%s\t%s\t%.3lf\t%.5lf\t%.5lg\n", barcodes[i], samples[j], samples[j], c->alpha[0], sv(j),
+                    exp(sv(j) - b.max_llk) * (1. - dp) / nv / (b.sum_single + b.sum_double));
+            for (int k = 0; k < nv; ++k)
+              for (int n = 0; n < nA; ++n)
+                if (n > 0 && j != k) {
+                  if (j > k && c->alpha[n] == 0.5) continue;              // :785
+                  double v = AB[((size_t)j * nv + k) * nA + n];
+                  if (j == b.dbl1 && k == b.dbl2 && n == b.alpha_idx) v = b.llk12;
+                  appendf(op, "%s\t%s\t%s\t%.3lf\t%.5lf\t%.5lg\n", barcodes[i], samples[j], samples[k], c->alpha[n], v,
+                          exp(v - b.max_llk) * dp / nv / (nv - 1) / (nA - 1) / (b.sum_single + b.sum_double));
+                }
+          }
+        }
+        appendf(ob, "%s\t%d\t%d\t%d\t%d\t", barcodes[i], c->totl[i], c->npass[i], c->uniq[i], b.n_snp);   // :830
+        if (b.call == 0)
+          appendf(ob, "DBL-%s-%s-%.3lf", samples[b.dbl1], samples[b.dbl2], c->alpha[b.alpha_idx]);       // :838
+        else if (b.call == 1)
+          appendf(ob, "SNG-%s", samples[b.sng1]);                                                          // :845
+        else
+          appendf(ob, "AMB-%s-%s-%s/%s", samples[b.sng1], samples[b.sng2], samples[b.dbl1], samples[b.dbl2]);   // :851
+        appendf(ob, "\t%s\t%.4lf", samples[b.sng1], b.sng_llk1);
+        appendf(ob, "\t%s\t%.4lf\t%.4lf", samples[b.sng2], b.sng_llk2, b.sng_llk0);
+        appendf(ob, "\t%s\t%s\t%.3lf\t%.4lf\t%.4lf\t%.4lf\t%.4lf\t%.4lf\t%.4lf\t%.3lg\t%.3lg\n", samples[b.dbl1],
+                samples[b.dbl2], c->alpha[b.alpha_idx], b.llk12, b.llk1, b.llk2, b.llk10, b.llk20, b.llk00, b.prb_dbl,
+                b.prb_sng1);
+      }
+    });
+    io_ok = write_all(w2, bufs2) && write_all(wb, bufsb) && (!wp || write_all(wp, bufsp));
   }
-  fclose(w2);
-  fclose(wb);
-  if (wp) fclose(wp);
-  return rc;
+  if (fclose(w2) != 0) io_ok = false;
+  if (fclose(wb) != 0) io_ok = false;
+  if (wp && fclose(wp) != 0) io_ok = false;
+  if (rc != DMX_OK) return rc;
+  return io_ok ? DMX_OK : DMX_E_IO;
 }
-
 
 // ---- VCF field -> genotype-probability matrix (kernels in dmx_field.cu) -------------------------------------------
 namespace {
