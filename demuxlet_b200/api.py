@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "dmx_upload", "dmx_compute", "dmx_run", "dmx_get_best", "dmx_get_single", "dmx_get_sing2", "dmx_get_pair",
     "dmx_rescore", "dmx_exact_llk", "dmx_write_outputs", "dmx_get_stats", "dmx_alloc_host", "dmx_free_host", "dmx_strerror",
     "dmx_last_error", "dmx_abi_version", "dmx_pack_reads", "dmx_pileup_sizes", "dmx_pileup_copy", "dmx_pileup_free",
-    "dmx_build_gp", "dmx_build_gp_device", "dmx_set_field",
+    "dmx_build_gp", "dmx_build_gp_device", "dmx_set_field", "dmx_site_filter",
 ]
 
 DMX_FIELD = {"GT": 0, "GP": 1, "PL": 2}            # --field (cmd_cram_demuxlet.cpp:28, :45)
@@ -121,6 +121,7 @@ def load_library(path: Optional[str] = None):
     lib.dmx_build_gp_device.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_double, C.c_void_p,
                                         C.c_int64, C.c_void_p, C.c_void_p]
     lib.dmx_set_field.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_double]
+    lib.dmx_site_filter.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_double, C.c_void_p]
     if path is None:
         _lib = lib
     return lib
@@ -182,6 +183,18 @@ def build_gp(field, arr, gt_error: float = 0.01, device: int = 0, want_af: bool 
     if want_stats:
         return res, {k: getattr(st, k) for k, _ in DmxFieldStats._fields_}
     return res
+
+
+def site_filter(gt, min_mac: int = 1, min_callrate: float = 0.5, device: int = 0) -> np.ndarray:
+    """the reference's per-record variant filter (passed_vfilter, /root/reference/bcf_filtered_reader.cpp:540-573)
+    with demuxlet's defaults (cmd_cram_demuxlet.cpp:24-25): bool[nsnps] from int8[nsnps][nv][2] allele indices"""
+    lib = load_library()
+    _, a = _field_array("GT", gt)
+    out = np.zeros(a.shape[0], np.uint8)
+    rc = lib.dmx_site_filter(device, a.shape[1], a.shape[0], a.ctypes.data, min_mac, min_callrate, out.ctypes.data)
+    if rc != 0:
+        raise DmxError(rc, "dmx_site_filter")
+    return out.astype(bool)
 
 
 def encode_umis(umis: Sequence[str]):

@@ -1546,6 +1546,33 @@ int dmx_build_gp(int32_t device, int32_t field, int32_t nv, int64_t nsnps, const
   return rc;
 }
 
+int dmx_site_filter(int32_t device, int32_t nv, int64_t nsnps, const int8_t* gt, int32_t min_mac, double min_callrate,
+                    uint8_t* pass_out) {
+  if (nv < 1 || nv > 4095 || nsnps < 0 || (nsnps > 0 && (!gt || !pass_out))) return DMX_E_INVALID;
+  int sm_count = 0;
+  RC(field_device_ok(device, &sm_count));
+  if (nsnps == 0) return DMX_OK;
+  cudaStream_t st = nullptr;
+  CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  struct StGuard { cudaStream_t s; ~StGuard() { cudaStreamDestroy(s); } } stg{st};
+  DevBuf<unsigned char> d_in, d_pass;
+  struct Rel { DevBuf<unsigned char>*a, *b; ~Rel() { a->release(); b->release(); } } rel{&d_in, &d_pass};
+  CU(d_in.reserve((size_t)nsnps * nv * 2));
+  CU(d_pass.reserve((size_t)nsnps));
+  FieldScratch sc;
+  RC(sc.init(st));
+  CU(cudaMemcpyAsync(d_in.p, gt, (size_t)nsnps * nv * 2, cudaMemcpyHostToDevice, st));
+  FieldParams fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.field = DMX_FIELD_GT; fp.nv = nv; fp.nsnps = nsnps; fp.in = d_in.p; fp.out = nullptr; fp.out_stride = (int64_t)nv * 3;
+  fp.prob = sc.d_prob; fp.err_flag = sc.d_flag; fp.pass = d_pass.p; fp.min_mac = min_mac; fp.min_callrate = min_callrate;
+  CU(launch_field(fp, sm_count, st));
+  CU(cudaMemcpyAsync(pass_out, d_pass.p, (size_t)nsnps, cudaMemcpyDeviceToHost, st));
+  const int rc = sc.check(st);
+  if (rc != DMX_OK) g_last_error = "GT allele index > 1: not a biallelic record";
+  return rc;
+}
+
 int dmx_set_field(dmx_ctx* c, int32_t field, const void* in, int64_t nsnps, double gt_error) {
   if (!c || nsnps < 0 || (nsnps > 0 && !in) || field < DMX_FIELD_GT || field > DMX_FIELD_PL) return DMX_E_INVALID;
   CU(cudaSetDevice(c->cfg.device));

@@ -65,6 +65,13 @@ __global__ void __launch_bounds__(256) field_gt_kernel(const FieldParams p) {
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     const int c0 = cnt & 0x1fff, c1 = (cnt >> 13) & 0x1fff, bad = cnt >> 26;
     if (bad && lane == 0) atomicOr(p.err_flag, 1);
+    if (p.pass && lane == 0) {
+      // passed_vfilter with the thresholds demuxlet exposes (bcf_filtered_reader.cpp:553-561; --min-callrate, --min-mac)
+      const int an = c0 + c1, ac = c1;
+      const bool lowcall = p.min_callrate > __ddiv_rn((double)an, __dmul_rn(2.0, (double)nv));
+      p.pass[s] = (uint8_t)(!lowcall && !(ac < p.min_mac || an - ac < p.min_mac));
+    }
+    if (!p.out) continue;                            // filter only
     // :385: (j == k ? 1.0 : 2.0) * (acs[j] + 1.0 / nalleles) / (an + 1.0) * (acs[k] + 1.0 / nalleles) / (an + 1.0)
     const double a0 = __dadd_rn((double)c0, 0.5), a1 = __dadd_rn((double)c1, 0.5), den = __dadd_rn((double)(c0 + c1), 1.0);
     // lanes 0..2 take one genotype each (two divisions per warp instead of six)

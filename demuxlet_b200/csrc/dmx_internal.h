@@ -220,6 +220,9 @@ struct FieldParams {
   double gt_error;
   const double* prob;          // device [256]: phred2Prob (PhredHelper.cpp:32), PL only
   int* err_flag;               // device: set when a GT allele index is > 1
+  uint8_t* pass;               // device [nsnps] or null (GT only): the reference's site filter, with ...
+  int32_t min_mac;             // ... --min-mac (cmd_cram_demuxlet.cpp:24, :47) and
+  double min_callrate;         // ... --min-callrate (:25, :48)
   int32_t group, pitch;        // filled by launch_field: SNPs per warp pass, shared-memory row pitch (elements)
 };
 int launch_field(const FieldParams& p, int sm_count, void* stream);

@@ -77,6 +77,29 @@ void load_plp(const char* path, Plp* p) {
   p->samples.assign(names.begin() + p->ncells, names.end());
 }
 
+// --field-matrix: the FORMAT values of the VCF records, flat (int32 field code 0 GT / 1 GP / 2 PL, int32 nv, int64 nsnps,
+// double geno_error, then int8[nsnps][nv][2] allele indices, float[nsnps][nv][3] or int32[nsnps][nv][3]); the
+// genotype-probability matrix is then built on the device (dmx_set_field) instead of read from the pileup file
+struct FieldFile {
+  int32_t field = -1, nv = 0;
+  int64_t nsnps = 0;
+  double geno_error = 0.01;
+  std::vector<unsigned char> data;
+};
+
+void load_field(const char* path, FieldFile* ff) {
+  FILE* f = fopen(path, "rb");
+  if (!f) die("Cannot open file %s for reading", path);
+  if (fread(&ff->field, 4, 1, f) != 1 || fread(&ff->nv, 4, 1, f) != 1 || fread(&ff->nsnps, 8, 1, f) != 1 ||
+      fread(&ff->geno_error, 8, 1, f) != 1)
+    die("Truncated field matrix %s", path);
+  if (ff->field < DMX_FIELD_GT || ff->field > DMX_FIELD_PL || ff->nv < 1 || ff->nsnps < 0) die("Corrupt header in %s", path);
+  const size_t n = (size_t)ff->nsnps * ff->nv * (ff->field == DMX_FIELD_GT ? 2 : 12);
+  ff->data.resize(n);
+  if (n && fread(ff->data.data(), 1, n, f) != n) die("Truncated field matrix %s", path);
+  fclose(f);
+}
+
 // --group-list (:68, :131-140): keep only the listed barcodes; cell order is preserved
 void restrict_to_groups(const char* path, Plp* p) {
   FILE* f = fopen(path, "r");
@@ -123,12 +146,16 @@ void usage() {
           "  --write-pair        also write the (huge) PREFIX.pair\n"
           "  --gpu D             CUDA device ordinal (default 0)\n"
           "  --fp64-pairs        pair scan in fp64 (default: fp32 products, exact re-score of the decisive values)\n"
-          "  --sam / --vcf / --field ...   BAM/VCF input needs htslib and is not part of this build\n");
+          "  --field GT|GP|PL --field-matrix FILE [--geno-error E]\n"
+          "                      build the genotype probabilities on the GPU from the flat FORMAT values in FILE\n"
+          "                      (as demuxlet's --field / --geno-error do per VCF record) instead of the matrix in --plp\n"
+          "  --sam / --vcf ...   BAM/VCF input needs htslib and is not part of this build\n");
 }
 }  // namespace
 
 int main(int argc, char** argv) {
-  const char *plp_path = nullptr, *out = nullptr, *groups = nullptr;
+  const char *plp_path = nullptr, *out = nullptr, *groups = nullptr, *field = nullptr, *field_path = nullptr;
+  double geno_error = -1;
   std::vector<double> alpha;
   double prior = 0.5;
   int min_total = 0, min_uniq = 0, min_snp = 0, gpu = 0, write_pair = 0, verbose = 0, fp64 = 0;
@@ -151,7 +178,10 @@ int main(int argc, char** argv) {
     else if (a == "--fp64-pairs") fp64 = 1;
     else if (a == "--verbose") verbose = 1;
     else if (a == "--help" || a == "-h") { usage(); return 0; }
-    else if (a == "--sam" || a == "--vcf" || a == "--field" || a == "--tag-group" || a == "--tag-UMI" || a == "--sm" ||
+    else if (a == "--field") field = val();
+    else if (a == "--field-matrix") field_path = val();
+    else if (a == "--geno-error") geno_error = atof(val());
+    else if (a == "--sam" || a == "--vcf" || a == "--tag-group" || a == "--tag-UMI" || a == "--sm" ||
              a == "--sm-list")
       die("Option %s: BAM/VCF input is read through htslib, which this build does not have; build the pileup with "
           "demuxlet's reader and pass it with --plp (INTEGRATION.md)", argv[i]);
@@ -160,8 +190,18 @@ int main(int argc, char** argv) {
   if (!plp_path || !out) { usage(); die("--plp and --out are required"); }
   if (alpha.empty()) { alpha.push_back(0.0); alpha.push_back(0.5); }   // :78-90
 
+  if (field && !field_path)
+    die("--field %s needs --field-matrix FILE (the FORMAT values as flat arrays; reading them from a VCF needs htslib)", field);
   Plp p;
   load_plp(plp_path, &p);
+  FieldFile ff;
+  if (field_path) {
+    load_field(field_path, &ff);
+    static const char* const names[3] = {"GT", "GP", "PL"};
+    if (field && strcmp(field, names[ff.field]) != 0) die("--field %s does not match the field matrix (%s)", field, names[ff.field]);
+    if (ff.nv != p.nv || ff.nsnps != p.nsnps) die("Field matrix %s does not have the samples / SNPs of the pileup", field_path);
+    if (geno_error >= 0) ff.geno_error = geno_error;   // :46
+  }
   if (groups) restrict_to_groups(groups, &p);
   if (verbose)
     fprintf(stderr, "NOTICE - %lld droplets, %lld SNPs, %lld samples, %lld (droplet, SNP) entries, %lld reads\n",
@@ -178,7 +218,9 @@ int main(int argc, char** argv) {
   if (!fp64) cfg.flags |= DMX_FP32_PAIRS;
   dmx_ctx* ctx = nullptr;
   int rc = dmx_create(&ctx, &cfg);
-  if (rc == DMX_OK) rc = dmx_set_gp(ctx, p.gp.data(), p.nsnps);
+  if (rc == DMX_OK)
+    rc = field_path ? dmx_set_field(ctx, ff.field, ff.data.data(), ff.nsnps, ff.geno_error)
+                    : dmx_set_gp(ctx, p.gp.data(), p.nsnps);
   if (rc == DMX_OK)
     rc = dmx_set_pileup(ctx, p.ncells, p.cell_ptr.data(), p.ent_snp.data(), p.ent_ptr.data(), p.reads.data(),
                         p.totl.data(), p.npass.data(), p.uniq.data());

@@ -210,6 +210,13 @@ int dmx_build_gp_device(int32_t device, int32_t field, int32_t nv, int64_t nsnps
  * read-back on the host for the tie finaliser */
 int dmx_set_field(dmx_ctx* ctx, int32_t field, const void* in, int64_t nsnps, double gt_error);
 
+/* the reference's per-record variant filter on genotype counts (BCFFilteredReader::passed_vfilter,
+ * bcf_filtered_reader.cpp:540-573, which demuxlet always runs on GT: SURVEY Q9) with the two thresholds its command
+ * line exposes, --min-mac (default 1, cmd_cram_demuxlet.cpp:24,:47) and --min-callrate (default 0.5, :25,:48):
+ * pass_out[s] = 1 when an / (2 nv) >= min_callrate and both allele counts are >= min_mac.  gt as DMX_FIELD_GT. */
+int dmx_site_filter(int32_t device, int32_t nv, int64_t nsnps, const int8_t* gt, int32_t min_mac, double min_callrate,
+                    uint8_t* pass_out);
+
 /* pinned host memory for DMX_BORROW_INPUTS callers */
 void* dmx_alloc_host(int64_t bytes);
 void dmx_free_host(void* p);

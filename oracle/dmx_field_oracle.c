@@ -107,6 +107,22 @@ void orc_field_gp(int32_t nv, const float* raw, double gt_error, float* out) {
       out[3 * i + j] = ((1.0 - gt_error) * out[3 * i + j] + gt_error * gp_sums[j]);
 }
 
+/* passed_vfilter's genotype-count block, bcf_filtered_reader.cpp:540-573, with every threshold but --min-mac and
+ * --min-callrate at its default (bcf_filter_arg.h:52-64), where the other comparisons cannot fail */
+void orc_site_filter(int32_t nv, int64_t nsnps, const int8_t* gt, int32_t min_mac, double min_callrate, uint8_t* pass) {
+  for (int64_t s = 0; s < nsnps; ++s) {
+    const int8_t* al = gt + s * nv * 2;
+    double acs[2] = {0.0, 0.0};
+    int32_t an = 0;
+    for (int32_t i = 0; i < nv * 2; ++i)
+      if (al[i] >= 0) { ++an; acs[al[i]] += 1.0; }
+    pass[s] = 1;
+    if (min_callrate > (double)an / (2.0 * (double)nv)) { pass[s] = 0; continue; }   /* :553 */
+    const int32_t ac = an - acs[0];                                                  /* :555 */
+    if ((ac < min_mac) || (an - ac < min_mac)) pass[s] = 0;                          /* :564 */
+  }
+}
+
 /* field: 0 GT (in = int8[nsnps][nv][2]), 1 GP (float[nsnps][nv][3]), 2 PL (int32[nsnps][nv][3]);
  * out float[nsnps][nv][3]; af double[nsnps] or NULL (GT / PL only) */
 int orc_build_gp(int32_t field, int32_t nv, int64_t nsnps, const void* in, double gt_error, float* out, double* af,

@@ -117,6 +117,7 @@ int64_t orc_count_asym(const orc_input* in, const double* llksAB, int32_t n);
 void orc_field_gt(int32_t nv, const int8_t* al, double gt_error, float* out, double* af);
 void orc_field_pl(int32_t nv, const int32_t* pl, float* out, double* af);
 void orc_field_gp(int32_t nv, const float* raw, double gt_error, float* out);
+void orc_site_filter(int32_t nv, int64_t nsnps, const int8_t* gt, int32_t min_mac, double min_callrate, uint8_t* pass);
 int orc_build_gp(int32_t field, int32_t nv, int64_t nsnps, const void* in, double gt_error, float* out, double* af,
                  int32_t nthreads);
 

@@ -213,3 +213,30 @@ def run_ref_field(field, arr, gt_error: float = 0.01, want_af: bool = False):
     gp = raw[: nsnps * nv * 12].view(np.float32).reshape(nsnps, nv, 3).copy()
     af = raw[nsnps * nv * 12:].view(np.float64).copy()
     return (gp, af) if want_af else gp
+
+
+def site_filter(gt, min_mac: int = 1, min_callrate: float = 0.5) -> np.ndarray:
+    """oracle restatement of passed_vfilter's genotype-count tests (bcf_filtered_reader.cpp:540-573)"""
+    _, a = _field_array("GT", gt)
+    out = np.zeros(a.shape[0], np.uint8)
+    lib().orc_site_filter(C.c_int32(a.shape[1]), C.c_int64(a.shape[0]), a.ctypes.data_as(C.c_void_p), C.c_int32(min_mac),
+                          C.c_double(min_callrate), out.ctypes.data_as(C.c_void_p))
+    return out.astype(bool)
+
+
+def run_ref_site_filter(gt, min_mac: int = 1, min_callrate: float = 0.5) -> np.ndarray:
+    """the reference's own lines 540-573 (oracle/_ref/ref_field, mode 3)"""
+    if not ref_field_available():
+        raise FileNotFoundError(REF_FIELD_BIN)
+    _, a = _field_array("GT", gt)
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, "in.fld"), os.path.join(td, "out.pass")
+        with open(fin, "wb") as f:
+            f.write(np.array([3, a.shape[1]], np.int32).tobytes())
+            f.write(np.array([a.shape[0]], np.int64).tobytes())
+            f.write(np.array([0.0], np.float64).tobytes())
+            f.write(np.array([min_mac], np.int32).tobytes())
+            f.write(np.array([min_callrate], np.float64).tobytes())
+            f.write(a.tobytes())
+        subprocess.run([REF_FIELD_BIN, fin, fout], check=True)
+        return np.fromfile(fout, np.uint8).astype(bool)

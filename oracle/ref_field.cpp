@@ -21,6 +21,8 @@
  * double gt_error, then per SNP and sample: GT int8[2] htslib-decoded allele indices (-1 missing),
  * GP float[3], PL int32[3].  Output: float[nsnps][nv][3] (get_posterior_at order), then
  * double[nsnps] get_af(1) (bcf_filtered_reader.h:177-179).
+ * field 3 = the genotype-count tests of passed_vfilter (:540-573) on GT records: the header is followed by
+ * int32 min_mac, double min_callrate; output uint8[nsnps] pass flags.
  */
 #include <limits.h>
 #include <math.h>
@@ -80,6 +82,11 @@ static int bcf_get_format_float(bcf_hdr_t*, bcf1_t*, const char*, float** dst, i
 class BCFFilteredReader {
  public:
   struct { int32_t minDP, minGQ; } gfilt;
+  struct {                                   /* bcf_filter_arg.h:30-47, defaults :52-64 */
+    bool require_GT;
+    int32_t minAC, minMAC, maxAC, maxMAC;
+    double minAF, minMAF, maxAF, maxMAF, minCallRate;
+  } vfilt;
   struct { bcf_hdr_t* hdr; } cdr;
   bcf1_t* cur;
   int32_t* gts; int32_t n_gts;
@@ -91,12 +98,21 @@ class BCFFilteredReader {
   int32_t an;
   std::vector<int32_t> sm_icols;
   BCFFilteredReader() : cur(NULL), gts(NULL), n_gts(0), pls(NULL), n_pls(0), gps(NULL), n_gps(0), flds(NULL),
-                        ploidies(NULL), an(0) { gfilt.minDP = gfilt.minGQ = 0; }
+                        ploidies(NULL), an(0) {
+    gfilt.minDP = gfilt.minGQ = 0;
+    vfilt.require_GT = true;
+    vfilt.minAC = vfilt.minMAC = 0; vfilt.maxAC = vfilt.maxMAC = INT_MAX;
+    vfilt.minAF = vfilt.minMAF = 0; vfilt.maxAF = vfilt.maxMAF = 1.; vfilt.minCallRate = 0;
+  }
   bcf1_t* cursor() { return cur; }
   bool parse_int_fields(const char*, bcf_hdr_t*, bcf1_t*) { return false; }
   bool parse_genotypes(bcf_hdr_t* hdr = NULL, bcf1_t* v = NULL);
   bool parse_likelihoods(bcf_hdr_t* hdr = NULL, bcf1_t* v = NULL, const char* name = "PL");
   bool parse_posteriors(bcf_hdr_t* hdr = NULL, bcf1_t* v = NULL, const char* name = "GP", double gt_error = 1e-4);
+  /* the tail of passed_vfilter (bcf_filtered_reader.cpp:540-573): the genotype-count tests */
+  bool passed_gt_counts(bcf_hdr_t* hdr, bcf1_t* v) {
+#include "_ref/bfr_540_573.inc"
+  }
 #include "_ref/bfr_h_144_149.inc"
   inline float get_posterior_at(int32_t i, int32_t ngenotypes = 3) {   /* bcf_filtered_reader.h:159-161 */
     return gps[sm_icols[i / ngenotypes] * ngenotypes + (i % ngenotypes)];
@@ -117,7 +133,9 @@ int main(int argc, char** argv) {
   int32_t field, nv; int64_t nsnps; double gt_error;
   if (fread(&field, 4, 1, f) != 1 || fread(&nv, 4, 1, f) != 1 || fread(&nsnps, 8, 1, f) != 1 ||
       fread(&gt_error, 8, 1, f) != 1) { fprintf(stderr, "short header\n"); return 2; }
-  const size_t per = field == 0 ? (size_t)nv * 2 : (size_t)nv * 12;
+  int32_t min_mac = 0; double min_callrate = 0;
+  if (field == 3 && (fread(&min_mac, 4, 1, f) != 1 || fread(&min_callrate, 8, 1, f) != 1)) { fprintf(stderr, "short header\n"); return 2; }
+  const size_t per = (field == 0 || field == 3) ? (size_t)nv * 2 : (size_t)nv * 12;
   std::vector<unsigned char> rec(per);
   g_nv = nv;
   bcf_hdr_t hdr; hdr.nsamples = nv;
@@ -129,6 +147,7 @@ int main(int argc, char** argv) {
   memset(vr.ploidies, 2, nv);                       /* bcf_filtered_reader.cpp:152-153 */
   for (int32_t i = 0; i < nv; ++i) vr.sm_icols.push_back(i);
   vr.acs.assign(2, 0.0);
+  vr.vfilt.minMAC = min_mac; vr.vfilt.minCallRate = min_callrate;   /* cmd_cram_demuxlet.cpp:24-25, :47-48 */
   const char* name = field == 0 ? "GT" : (field == 1 ? "GP" : "PL");
   FILE* o = fopen(argv[2], "wb");
   if (!o) { perror(argv[2]); return 2; }
@@ -136,7 +155,12 @@ int main(int argc, char** argv) {
   std::vector<double> afs((size_t)nsnps);
   for (int64_t s = 0; s < nsnps; ++s) {
     if (fread(rec.data(), 1, per, f) != per) { fprintf(stderr, "short record\n"); return 2; }
-    g_rec_gt = field == 0 ? (const int8_t*)rec.data() : NULL;
+    g_rec_gt = (field == 0 || field == 3) ? (const int8_t*)rec.data() : NULL;
+    if (field == 3) {
+      const unsigned char ok = vr.passed_gt_counts(&hdr, &v) ? 1 : 0;
+      fwrite(&ok, 1, 1, o);
+      continue;
+    }
     g_rec_gp = field == 1 ? (const float*)rec.data() : NULL;
     g_rec_pl = field == 2 ? (const int32_t*)rec.data() : NULL;
     v.pos = (int32_t)s;
@@ -145,7 +169,7 @@ int main(int argc, char** argv) {
     fwrite(out.data(), sizeof(float), out.size(), o);
     afs[s] = vr.get_af(1);
   }
-  fwrite(afs.data(), sizeof(double), afs.size(), o);
+  if (field != 3) fwrite(afs.data(), sizeof(double), afs.size(), o);
   fclose(o);
   fclose(f);
   return 0;

@@ -41,7 +41,11 @@ def main():
         po.build()
     for name, (field, arr) in inputs().items():
         gp, af = po.run_ref_field(field, arr, 0.01, want_af=True)
-        np.savez_compressed(os.path.join(HERE, "field_%s.npz" % name), field=field, gt_error=0.01, input=arr, gp=gp, af=af)
+        extra = {}
+        if field == "GT":   # the reference's genotype-count site filter (:540-573) at demuxlet's defaults and a stricter pair
+            extra = {"pass_1_50": po.run_ref_site_filter(arr, 1, 0.5), "pass_2_80": po.run_ref_site_filter(arr, 2, 0.8)}
+        np.savez_compressed(os.path.join(HERE, "field_%s.npz" % name), field=field, gt_error=0.01, input=arr, gp=gp, af=af,
+                            **extra)
         print(name, arr.shape, gp.shape)
 
 

@@ -80,6 +80,18 @@ def test_oracle_against_generator_restatement():
     assert np.abs(po.build_gp("PL", pl, 0.01) - synth.gp_from_pl(np.clip(pl, 0, 255))).max() < 1e-6
 
 
+def test_site_filter_oracle_against_reference():
+    z = np.load(os.path.join(GOLD, "field_gt.npz"))
+    assert np.array_equal(po.site_filter(z["input"], 1, 0.5), z["pass_1_50"])
+    assert np.array_equal(po.site_filter(z["input"], 2, 0.8), z["pass_2_80"])
+    assert 0 < z["pass_1_50"].sum() < len(z["pass_1_50"])
+    if po.ref_field_available():
+        gt = make_field("GT", 500, 9, 13)
+        gt[10:60, :6] = -1
+        for mm, cr in ((1, 0.5), (0, 0.0), (3, 0.9)):
+            assert np.array_equal(po.site_filter(gt, mm, cr), po.run_ref_site_filter(gt, mm, cr))
+
+
 def test_rows_are_distributions():
     for field in FIELDS:
         gp = po.build_gp(field, make_field(field, 300, 9, 7), 0.01)
@@ -95,6 +107,7 @@ def test_abi_argument_checks():
     assert lib.dmx_build_gp(0, 1, 3, 2, None, 0.01, out.ctypes.data, None, None) == -1                # null input
     assert lib.dmx_build_gp_device(0, 1, 3, 2, buf.ctypes.data, 0.01, out.ctypes.data, 8, None, None) == -1   # stride < nv * 3
     assert lib.dmx_set_field(None, 1, buf.ctypes.data, 2, 0.01) == -1
+    assert lib.dmx_site_filter(0, 0, 2, buf.ctypes.data, 1, 0.5, out.ctypes.data) == -1
     if api.device_count() == 0:   # no CPU fallback
         assert lib.dmx_build_gp(0, 1, 3, 2, buf.ctypes.data, 0.01, out.ctypes.data, None, None) == -3
         with pytest.raises(api.DmxError):
@@ -146,6 +159,19 @@ def test_gpu_full_size_chunked(field):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("nsnps,nv", [(48, 5), (5000, 64), (300, 131), (1, 2)])
+def test_gpu_site_filter(nsnps, nv):
+    if (nsnps, nv) == (48, 5):
+        z = np.load(os.path.join(GOLD, "field_gt.npz"))
+        assert np.array_equal(api.site_filter(z["input"], 1, 0.5), z["pass_1_50"])
+        assert np.array_equal(api.site_filter(z["input"], 2, 0.8), z["pass_2_80"])
+    gt = make_field("GT", nsnps, nv, 17)
+    gt[: nsnps // 3, : (2 * nv) // 3] = -1
+    for mm, cr in ((1, 0.5), (0, 0.0), (3, 0.9), (1, 1.0)):
+        assert np.array_equal(api.site_filter(gt, mm, cr), po.site_filter(gt, mm, cr))
+
+
+@pytest.mark.gpu
 def test_gpu_rejects_non_biallelic_gt():
     gt = np.zeros((10, 4, 2), np.int8)
     gt[3, 1, 0] = 2
@@ -176,3 +202,31 @@ def test_set_field_matches_set_gp(field, nv):
         if f not in ("n_rescored", "exact_mask"):
             assert np.array_equal(a[f], b[f]), f
     assert res[1][1] == res[0][1] - gp.nbytes      # the matrix was not uploaded a second time
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("field", FIELDS)
+def test_cli_field_matrix(field, tmp_path):
+    """dmx-demuxlet --field F --field-matrix FILE (matrix built on the GPU from the FORMAT values, like demuxlet's
+    --field / --geno-error per VCF record) writes the files --plp alone writes with the oracle's matrix inside"""
+    import dataclasses
+    import filecmp
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "demuxlet_b200", "dmx-demuxlet")
+    nv, nsnps = 6, 2500
+    p = synth.make_synth(30, nv, nsnps, "GP", seed=4)
+    arr = make_field(field, nsnps, nv, 15)
+    with_gp = dataclasses.replace(p, gp=po.build_gp(field, arr, 0.02))
+    without = dataclasses.replace(p, gp=np.zeros_like(p.gp))
+    with_gp.save(str(tmp_path / "a.dmxp"))
+    without.save(str(tmp_path / "b.dmxp"))
+    po.write_field_file(str(tmp_path / "b.fld"), field, arr, 0.01)
+    ra = subprocess.run([exe, "--plp", str(tmp_path / "a.dmxp"), "--out", str(tmp_path / "a")], capture_output=True, text=True)
+    rb = subprocess.run([exe, "--plp", str(tmp_path / "b.dmxp"), "--out", str(tmp_path / "b"), "--field", field,
+                         "--field-matrix", str(tmp_path / "b.fld"), "--geno-error", "0.02"], capture_output=True, text=True)
+    assert ra.returncode == 0 and rb.returncode == 0, ra.stderr + rb.stderr
+    for ext in ("best", "single", "sing2"):
+        assert filecmp.cmp(str(tmp_path / ("a." + ext)), str(tmp_path / ("b." + ext)), shallow=False), ext
+    bad = subprocess.run([exe, "--plp", str(tmp_path / "b.dmxp"), "--out", str(tmp_path / "c"), "--field",
+                          "GP" if field != "GP" else "PL", "--field-matrix", str(tmp_path / "b.fld")], capture_output=True, text=True)
+    assert bad.returncode == 1 and "does not match" in bad.stderr
