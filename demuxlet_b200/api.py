@@ -33,6 +33,7 @@ ABI_SYMBOLS = [
     "dmx_rescore", "dmx_exact_llk", "dmx_write_outputs", "dmx_get_stats", "dmx_alloc_host", "dmx_free_host", "dmx_strerror",
     "dmx_last_error", "dmx_abi_version", "dmx_pack_reads", "dmx_pileup_sizes", "dmx_pileup_copy", "dmx_pileup_free",
     "dmx_build_gp", "dmx_build_gp_device", "dmx_set_field", "dmx_site_filter",
+    "dmx_vcf_read", "dmx_vcf_sizes", "dmx_vcf_sample", "dmx_vcf_chrom", "dmx_vcf_copy", "dmx_vcf_free", "dmx_vcf_last_error",
 ]
 
 DMX_FIELD = {"GT": 0, "GP": 1, "PL": 2}            # --field (cmd_cram_demuxlet.cpp:28, :45)
@@ -195,6 +196,44 @@ def site_filter(gt, min_mac: int = 1, min_callrate: float = 0.5, device: int = 0
     if rc != 0:
         raise DmxError(rc, "dmx_site_filter")
     return out.astype(bool)
+
+
+def read_vcf(path: str, field: str = "GT") -> dict:
+    """dmx_vcf_read: the biallelic records of a VCF (plain / gzip / bgzip) as the flat arrays site_filter / build_gp
+    take.  Returns samples, chroms, rid, pos (0-based), ref, alt, gt int8[nrec][nv][2], values (GT: gt; GP float32;
+    PL int32 [nrec][nv][3]), n_skipped."""
+    lib = load_library()
+    lib.dmx_vcf_read.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_void_p)]
+    lib.dmx_vcf_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                  C.POINTER(C.c_int32)]
+    lib.dmx_vcf_sample.argtypes = [C.c_void_p, C.c_int32]
+    lib.dmx_vcf_sample.restype = C.c_char_p
+    lib.dmx_vcf_chrom.argtypes = [C.c_void_p, C.c_int32]
+    lib.dmx_vcf_chrom.restype = C.c_char_p
+    lib.dmx_vcf_copy.argtypes = [C.c_void_p] * 7
+    lib.dmx_vcf_free.argtypes = [C.c_void_p]
+    lib.dmx_vcf_free.restype = None
+    lib.dmx_vcf_last_error.restype = C.c_char_p
+    code = DMX_FIELD[field]
+    h = C.c_void_p()
+    rc = lib.dmx_vcf_read(os.fsencode(path), code, C.byref(h))
+    if rc != 0:
+        raise DmxError(rc, "dmx_vcf_read", lib.dmx_vcf_last_error().decode())
+    try:
+        nv, nrec, nskip, nchrom = C.c_int32(), C.c_int64(), C.c_int64(), C.c_int32()
+        lib.dmx_vcf_sizes(h, C.byref(nv), C.byref(nrec), C.byref(nskip), C.byref(nchrom))
+        nv, nrec = nv.value, nrec.value
+        gt = np.zeros((nrec, nv, 2), np.int8)
+        vals = gt if code == 0 else np.zeros((nrec, nv, 3), _FIELD_DTYPE[code])
+        rid, pos = np.zeros(nrec, np.int32), np.zeros(nrec, np.int32)
+        ref, alt = np.zeros(nrec, "S1"), np.zeros(nrec, "S1")
+        lib.dmx_vcf_copy(h, gt.ctypes.data, None if code == 0 else vals.ctypes.data, rid.ctypes.data, pos.ctypes.data,
+                         ref.ctypes.data, alt.ctypes.data)
+        return {"samples": [lib.dmx_vcf_sample(h, i).decode() for i in range(nv)],
+                "chroms": [lib.dmx_vcf_chrom(h, i).decode() for i in range(nchrom.value)],
+                "rid": rid, "pos": pos, "ref": ref, "alt": alt, "gt": gt, "values": vals, "n_skipped": nskip.value}
+    finally:
+        lib.dmx_vcf_free(h)
 
 
 def encode_umis(umis: Sequence[str]):

@@ -1,0 +1,269 @@
+// dmx_vcf.cpp -- htslib-free VCF text reader for the arrays the field kernels take (VCF half; host only).
+//
+// The reference reads VCF / BCF records through htslib (BCFChunkedReader::read, /root/reference/bcf_chunked_reader.cpp:
+// 265-305: bcf_read / vcf_parse1) and asks the record for its FORMAT values with bcf_get_genotypes /
+// bcf_get_format_float / bcf_get_format_int32 (bcf_filtered_reader.cpp:194, :250, :408).  htslib is not in this image,
+// so this file parses the text form itself -- plain, gzip or bgzip (a bgzip file is a series of gzip members, which
+// zlib's gzread walks through) -- and delivers, for every record, what those accessors would:
+//   GT   two allele indices per sample as bcf_gt_allele() decodes them ("." -> -1, a haploid call "1" -> (1, -1):
+//        htslib pads it with bcf_int32_vector_end, which decodes to a negative allele)
+//   GP   three floats per sample, "." or a short vector -> NaN (htslib: bcf_float_missing / vector_end, both NaNs)
+//   PL   three int32 per sample, "." or a short vector -> INT32_MIN (bcf_int32_missing; vector_end = INT32_MIN + 1 reads
+//        the same through PhredHelper.h:40's uint32_t cast: > 255)
+// Records are delivered in file order; records whose allele count is not 2 are skipped and counted (demuxlet sets
+// maxAlleles = 2, cmd_cram_demuxlet.cpp:26; a record without ALT cannot pass --min-mac 1).  All samples are selected
+// (no --sm / --sm-list).  No reference test pins htslib's parse, so the pin of THIS reader is its python restatement
+// (tests/vcfio.py) on generated files: "parity unpinned" against htslib itself.
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/dmx.h"
+
+struct dmx_vcf {
+  int32_t field = DMX_FIELD_GT;
+  std::vector<std::string> samples, chroms;
+  std::vector<int32_t> rid, pos;      // pos 0-based like bcf1_t::pos
+  std::vector<char> ref, alt;         // first base of REF / ALT (what add_snp keeps, cmd_cram_demuxlet.cpp:230)
+  std::vector<int8_t> gt;             // [nrec][nv][2]
+  std::vector<float> gp;              // [nrec][nv][3] (field GP)
+  std::vector<int32_t> pl;            // [nrec][nv][3] (field PL)
+  int64_t n_skipped = 0;              // records with n_allele != 2
+  std::string error;
+};
+
+namespace {
+
+thread_local std::string g_vcf_error;
+
+bool slurp(const char* path, std::string* out) {
+  gzFile f = gzopen(path, "rb");      // transparent for uncompressed files
+  if (!f) return false;
+  gzbuffer(f, 1 << 20);
+  std::vector<char> buf(1 << 22);
+  for (;;) {
+    const int n = gzread(f, buf.data(), (unsigned)buf.size());
+    if (n < 0) { gzclose(f); return false; }
+    if (n == 0) break;
+    out->append(buf.data(), (size_t)n);
+  }
+  gzclose(f);
+  return true;
+}
+
+struct Tok {
+  const char* p;
+  size_t n;
+};
+
+// split [p, e) at `sep`
+void split(const char* p, const char* e, char sep, std::vector<Tok>* out) {
+  out->clear();
+  const char* s = p;
+  for (const char* q = p; q <= e; ++q)
+    if (q == e || *q == sep) {
+      out->push_back(Tok{s, (size_t)(q - s)});
+      s = q + 1;
+    }
+}
+
+const float kNaN = std::numeric_limits<float>::quiet_NaN();
+
+// the idx-th ':'-separated subfield of a sample column, or an empty token
+Tok subfield(const Tok& col, int idx) {
+  const char *p = col.p, *e = col.p + col.n;
+  for (int i = 0; i < idx; ++i) {
+    const char* c = (const char*)memchr(p, ':', (size_t)(e - p));
+    if (!c) return Tok{e, 0};
+    p = c + 1;
+  }
+  const char* c = (const char*)memchr(p, ':', (size_t)(e - p));
+  return Tok{p, (size_t)((c ? c : e) - p)};
+}
+
+void parse_gt(const Tok& t, int8_t* out) {
+  out[0] = out[1] = -1;
+  const char *p = t.p, *e = t.p + t.n;
+  for (int a = 0; a < 2 && p < e; ++a) {
+    if (*p == '.') {
+      ++p;
+    } else {
+      int v = 0;
+      bool any = false;
+      while (p < e && *p >= '0' && *p <= '9') { v = v * 10 + (*p - '0'); ++p; any = true; }
+      if (any) out[a] = (int8_t)(v > 126 ? 126 : v);
+    }
+    if (p < e && (*p == '/' || *p == '|')) ++p;
+    else break;
+  }
+}
+
+template <class T, class F>
+void parse_vec3(const Tok& t, T* out, T missing, F conv) {
+  out[0] = out[1] = out[2] = missing;
+  const char *p = t.p, *e = t.p + t.n;
+  for (int k = 0; k < 3 && p < e; ++k) {
+    const char* c = (const char*)memchr(p, ',', (size_t)(e - p));
+    const char* q = c ? c : e;
+    if (!(q - p == 1 && *p == '.') && q > p) out[k] = conv(p, q);
+    if (!c) break;
+    p = c + 1;
+  }
+}
+
+float conv_float(const char* p, const char* q) {
+  char tmp[64];
+  const size_t n = std::min<size_t>((size_t)(q - p), sizeof(tmp) - 1);
+  memcpy(tmp, p, n);
+  tmp[n] = 0;
+  return strtof(tmp, nullptr);     // htslib parses FORMAT floats with strtod and narrows; the same float for decimal text of
+                                   // <= 9 significant digits, which is what VCF writers emit
+}
+
+int32_t conv_int(const char* p, const char* q) {
+  long v = 0;
+  bool neg = false;
+  if (p < q && *p == '-') { neg = true; ++p; }
+  for (; p < q && *p >= '0' && *p <= '9'; ++p) v = v * 10 + (*p - '0');
+  return (int32_t)(neg ? -v : v);
+}
+
+}  // namespace
+
+extern "C" {
+
+int dmx_vcf_read(const char* path, int32_t field, dmx_vcf** out) {
+  if (!path || !out || field < DMX_FIELD_GT || field > DMX_FIELD_PL) return DMX_E_INVALID;
+  *out = nullptr;
+  std::string text;
+  if (!slurp(path, &text)) {
+    g_vcf_error = std::string("cannot read ") + path;
+    return DMX_E_IO;
+  }
+  dmx_vcf* v = new dmx_vcf();
+  v->field = field;
+  const char* want = field == DMX_FIELD_GP ? "GP" : (field == DMX_FIELD_PL ? "PL" : nullptr);
+  std::vector<Tok> cols, keys, alts;
+  const char *p = text.data(), *end = text.data() + text.size();
+  bool have_header = false;
+  int64_t lineno = 0;
+  auto fail = [&](const std::string& why) {
+    g_vcf_error = std::string(path) + ": line " + std::to_string(lineno) + ": " + why;
+    delete v;
+    return DMX_E_INVALID;
+  };
+  while (p < end) {
+    const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+    const char* e = nl ? nl : end;
+    const char* next = nl ? nl + 1 : end;
+    if (e > p && e[-1] == '\r') --e;
+    ++lineno;
+    if (e == p) { p = next; continue; }
+    if (*p == '#') {
+      if (e - p > 6 && memcmp(p, "#CHROM", 6) == 0) {
+        split(p, e, '\t', &cols);
+        if (cols.size() < 10) return fail("no sample columns");
+        for (size_t i = 9; i < cols.size(); ++i) v->samples.emplace_back(cols[i].p, cols[i].n);
+        have_header = true;
+      }
+      p = next;
+      continue;
+    }
+    if (!have_header) return fail("record before the #CHROM line");
+    split(p, e, '\t', &cols);
+    const size_t nv = v->samples.size();
+    if (cols.size() != 9 + nv) return fail("wrong number of columns");
+    // n_allele = 1 + number of ALT alleles ("." = none)
+    split(cols[4].p, cols[4].p + cols[4].n, ',', &alts);
+    const bool no_alt = cols[4].n == 1 && cols[4].p[0] == '.';
+    if (no_alt || alts.size() != 1) { ++v->n_skipped; p = next; continue; }
+    split(cols[8].p, cols[8].p + cols[8].n, ':', &keys);
+    int i_gt = -1, i_f = -1;
+    for (size_t k = 0; k < keys.size(); ++k) {
+      if (keys[k].n == 2 && memcmp(keys[k].p, "GT", 2) == 0) i_gt = (int)k;
+      if (want && keys[k].n == 2 && memcmp(keys[k].p, want, 2) == 0) i_f = (int)k;
+    }
+    if (i_gt < 0) return fail("no GT in FORMAT (demuxlet's record filter needs it)");
+    if (want && i_f < 0) return fail(std::string("no ") + want + " in FORMAT");
+    const std::string chrom(cols[0].p, cols[0].n);
+    if (v->chroms.empty() || v->chroms.back() != chrom) {
+      size_t r = 0;
+      for (; r < v->chroms.size(); ++r)
+        if (v->chroms[r] == chrom) break;
+      if (r == v->chroms.size()) v->chroms.push_back(chrom);
+      v->rid.push_back((int32_t)r);
+    } else {
+      v->rid.push_back((int32_t)v->chroms.size() - 1);
+    }
+    v->pos.push_back(conv_int(cols[1].p, cols[1].p + cols[1].n) - 1);
+    v->ref.push_back(cols[3].n ? cols[3].p[0] : 'N');
+    v->alt.push_back(cols[4].n ? cols[4].p[0] : 'N');
+    const size_t g0 = v->gt.size();
+    v->gt.resize(g0 + nv * 2);
+    size_t f0 = 0;
+    if (field == DMX_FIELD_GP) { f0 = v->gp.size(); v->gp.resize(f0 + nv * 3); }
+    if (field == DMX_FIELD_PL) { f0 = v->pl.size(); v->pl.resize(f0 + nv * 3); }
+    for (size_t s = 0; s < nv; ++s) {
+      const Tok& col = cols[9 + s];
+      parse_gt(subfield(col, i_gt), &v->gt[g0 + s * 2]);
+      if (field == DMX_FIELD_GP) parse_vec3<float>(subfield(col, i_f), &v->gp[f0 + s * 3], kNaN, conv_float);
+      if (field == DMX_FIELD_PL)
+        parse_vec3<int32_t>(subfield(col, i_f), &v->pl[f0 + s * 3], std::numeric_limits<int32_t>::min(), conv_int);
+    }
+    p = next;
+  }
+  if (!have_header) {
+    lineno = 0;
+    return fail("no #CHROM line");
+  }
+  *out = v;
+  return DMX_OK;
+}
+
+int dmx_vcf_sizes(const dmx_vcf* v, int32_t* nv, int64_t* nrec, int64_t* n_skipped, int32_t* n_chrom) {
+  if (!v) return DMX_E_INVALID;
+  if (nv) *nv = (int32_t)v->samples.size();
+  if (nrec) *nrec = (int64_t)v->pos.size();
+  if (n_skipped) *n_skipped = v->n_skipped;
+  if (n_chrom) *n_chrom = (int32_t)v->chroms.size();
+  return DMX_OK;
+}
+
+const char* dmx_vcf_sample(const dmx_vcf* v, int32_t i) {
+  return (v && i >= 0 && (size_t)i < v->samples.size()) ? v->samples[(size_t)i].c_str() : nullptr;
+}
+
+const char* dmx_vcf_chrom(const dmx_vcf* v, int32_t rid) {
+  return (v && rid >= 0 && (size_t)rid < v->chroms.size()) ? v->chroms[(size_t)rid].c_str() : nullptr;
+}
+
+int dmx_vcf_copy(const dmx_vcf* v, int8_t* gt, void* field_values, int32_t* rid, int32_t* pos, char* ref, char* alt) {
+  if (!v) return DMX_E_INVALID;
+  const size_t n = v->pos.size();
+  if (gt && !v->gt.empty()) memcpy(gt, v->gt.data(), v->gt.size());
+  if (field_values) {
+    if (v->field == DMX_FIELD_GT && !v->gt.empty()) memcpy(field_values, v->gt.data(), v->gt.size());
+    if (v->field == DMX_FIELD_GP && !v->gp.empty()) memcpy(field_values, v->gp.data(), v->gp.size() * sizeof(float));
+    if (v->field == DMX_FIELD_PL && !v->pl.empty()) memcpy(field_values, v->pl.data(), v->pl.size() * sizeof(int32_t));
+  }
+  if (n) {
+    if (rid) memcpy(rid, v->rid.data(), n * sizeof(int32_t));
+    if (pos) memcpy(pos, v->pos.data(), n * sizeof(int32_t));
+    if (ref) memcpy(ref, v->ref.data(), n);
+    if (alt) memcpy(alt, v->alt.data(), n);
+  }
+  return DMX_OK;
+}
+
+void dmx_vcf_free(dmx_vcf* v) { delete v; }
+
+const char* dmx_vcf_last_error(void) { return g_vcf_error.c_str(); }
+
+}  // extern "C"

@@ -217,6 +217,23 @@ int dmx_set_field(dmx_ctx* ctx, int32_t field, const void* in, int64_t nsnps, do
 int dmx_site_filter(int32_t device, int32_t nv, int64_t nsnps, const int8_t* gt, int32_t min_mac, double min_callrate,
                     uint8_t* pass_out);
 
+/* ---- VCF text reader (host only, no htslib; SURVEY 8f N4, VCF half) ---------------------------------------------
+ * Reads a VCF (plain, gzip or bgzip) and delivers per biallelic record what the reference obtains from htslib's
+ * bcf_read / vcf_parse1 (bcf_chunked_reader.cpp:265-305) and bcf_get_genotypes / bcf_get_format_float /
+ * bcf_get_format_int32 (bcf_filtered_reader.cpp:194, :250, :408): the arrays dmx_site_filter and dmx_build_gp take.
+ * Records with an allele count other than 2 are skipped and counted (maxAlleles = 2, cmd_cram_demuxlet.cpp:26).
+ * Missing values: GT -1, GP NaN, PL INT32_MIN.  All samples are selected. */
+typedef struct dmx_vcf dmx_vcf;
+int dmx_vcf_read(const char* path, int32_t field /* DMX_FIELD_*: which FORMAT key besides GT */, dmx_vcf** out);
+int dmx_vcf_sizes(const dmx_vcf* v, int32_t* nv, int64_t* nrec, int64_t* n_skipped, int32_t* n_chrom);
+const char* dmx_vcf_sample(const dmx_vcf* v, int32_t i);        /* sample id of column i (get_sample_id_at)       */
+const char* dmx_vcf_chrom(const dmx_vcf* v, int32_t rid);       /* chromosome name of rid (first-seen order)       */
+/* any pointer may be null: gt int8[nrec][nv][2]; field_values = gt again (GT), float[nrec][nv][3] (GP) or
+ * int32[nrec][nv][3] (PL); rid / pos (0-based) [nrec]; first base of REF / ALT [nrec] (add_snp, :230) */
+int dmx_vcf_copy(const dmx_vcf* v, int8_t* gt, void* field_values, int32_t* rid, int32_t* pos, char* ref, char* alt);
+void dmx_vcf_free(dmx_vcf* v);
+const char* dmx_vcf_last_error(void);
+
 /* pinned host memory for DMX_BORROW_INPUTS callers */
 void* dmx_alloc_host(int64_t bytes);
 void dmx_free_host(void* p);

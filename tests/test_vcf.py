@@ -1,0 +1,72 @@
+"""dmx_vcf_read (htslib-free VCF text reader, SURVEY 8f N4 / VCF half; host only) against the plain-python restatement
+in tests/vcfio.py on generated files: plain, gzip and multi-member (bgzip-like) gzip, the three fields, missing and
+short values, multi-allelic and ALT-less records; then the chain VCF -> dmx_site_filter -> dmx_build_gp on the GPU
+against the oracle chain."""
+import numpy as np
+import pytest
+
+from demuxlet_b200 import api
+from oracle import pyoracle as po
+from tests import vcfio
+
+
+def same(a, b, field):
+    assert a["samples"] == b["samples"] and a["chroms"] == b["chroms"] and a["n_skipped"] == b["n_skipped"]
+    for k in ("rid", "pos", "ref", "alt", "gt"):
+        assert np.array_equal(a[k], b[k]), k
+    if field == "GP":      # missing values are NaNs on both sides; the rest are the same floats
+        assert np.array_equal(np.isnan(a["values"]), np.isnan(b["values"]))
+        assert np.array_equal(np.nan_to_num(a["values"], nan=-1.0), np.nan_to_num(b["values"], nan=-1.0))
+    else:
+        assert np.array_equal(a["values"], b["values"])
+
+
+@pytest.mark.parametrize("field", ["GT", "GP", "PL"])
+@pytest.mark.parametrize("ext,bg", [(".vcf", False), (".vcf.gz", False), (".vcf.gz", True)])
+def test_reader_matches_restatement(field, ext, bg, tmp_path):
+    rng = np.random.default_rng(7)
+    samples = ["S%02d" % i for i in range(9)]
+    recs = vcfio.random_records(rng, 400, len(samples), field)
+    path = str(tmp_path / ("a" + ext))
+    vcfio.write_vcf(path, samples, recs, bgzip_like=bg)
+    got, want = api.read_vcf(path, field), vcfio.parse_vcf(path, field)
+    same(got, want, field)
+    assert got["n_skipped"] > 0 and len(got["pos"]) > 300 and len(got["chroms"]) == 3
+
+
+def test_reader_errors(tmp_path):
+    with pytest.raises(api.DmxError):
+        api.read_vcf(str(tmp_path / "missing.vcf"))
+    p = tmp_path / "nohdr.vcf"
+    p.write_text("chr1\t10\t.\tA\tT\t.\t.\t.\tGT\t0/1\n")
+    with pytest.raises(api.DmxError, match="#CHROM"):
+        api.read_vcf(str(p))
+    p = tmp_path / "nogp.vcf"
+    vcfio.write_vcf(str(p), ["a", "b"], [("1", 5, "A", "C", ["GT"], [{"GT": "0/1"}, {"GT": "1/1"}])])
+    assert len(api.read_vcf(str(p), "GT")["pos"]) == 1
+    with pytest.raises(api.DmxError, match="no GP"):
+        api.read_vcf(str(p), "GP")
+    p = tmp_path / "cols.vcf"
+    p.write_text("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\ta\tb\n1\t5\t.\tA\tC\t.\t.\t.\tGT\t0/1\n")
+    with pytest.raises(api.DmxError, match="columns"):
+        api.read_vcf(str(p))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("field", ["GT", "GP", "PL"])
+def test_vcf_to_matrix_chain(field, tmp_path):
+    """VCF text -> record filter -> genotype-probability matrix, device chain against the oracle chain"""
+    rng = np.random.default_rng(8)
+    samples = ["S%02d" % i for i in range(12)]
+    path = str(tmp_path / "a.vcf.gz")
+    vcfio.write_vcf(path, samples, vcfio.random_records(rng, 600, len(samples), field), bgzip_like=True)
+    v = api.read_vcf(path, field)
+    keep = api.site_filter(v["gt"], 1, 0.5)
+    assert np.array_equal(keep, po.site_filter(v["gt"], 1, 0.5)) and 0 < keep.sum() < len(keep)
+    vals = np.ascontiguousarray(v["values"][keep])
+    if field == "GP":       # a record with a missing GP row yields NaNs: compare the finite records
+        ok = ~np.isnan(vals).any(axis=(1, 2))
+        vals = np.ascontiguousarray(vals[ok])
+    got = api.build_gp(field, vals, 0.01)
+    want = po.build_gp(field, vals, 0.01)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
