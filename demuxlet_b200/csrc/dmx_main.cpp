@@ -149,13 +149,18 @@ void usage() {
           "  --field GT|GP|PL --field-matrix FILE [--geno-error E]\n"
           "                      build the genotype probabilities on the GPU from the flat FORMAT values in FILE\n"
           "                      (as demuxlet's --field / --geno-error do per VCF record) instead of the matrix in --plp\n"
-          "  --sam / --vcf ...   BAM/VCF input needs htslib and is not part of this build\n");
+          "  --vcf FILE [--field F] [--geno-error E] [--min-mac N] [--min-callrate R]\n"
+          "                      the same from a VCF (plain / gzip / bgzip text; F defaults to GP): biallelic records that\n"
+          "                      pass the genotype-count filter must be the SNPs of the pileup, in order\n"
+          "  --sam ...           BAM input needs htslib and is not part of this build\n");
 }
 }  // namespace
 
 int main(int argc, char** argv) {
-  const char *plp_path = nullptr, *out = nullptr, *groups = nullptr, *field = nullptr, *field_path = nullptr;
-  double geno_error = -1;
+  const char *plp_path = nullptr, *out = nullptr, *groups = nullptr, *field = nullptr, *field_path = nullptr,
+             *vcf_path = nullptr;
+  double geno_error = -1, min_callrate = 0.5;     // :25
+  int min_mac = 1;                                // :24
   std::vector<double> alpha;
   double prior = 0.5;
   int min_total = 0, min_uniq = 0, min_snp = 0, gpu = 0, write_pair = 0, verbose = 0, fp64 = 0;
@@ -181,17 +186,21 @@ int main(int argc, char** argv) {
     else if (a == "--field") field = val();
     else if (a == "--field-matrix") field_path = val();
     else if (a == "--geno-error") geno_error = atof(val());
-    else if (a == "--sam" || a == "--vcf" || a == "--tag-group" || a == "--tag-UMI" || a == "--sm" ||
+    else if (a == "--vcf") vcf_path = val();
+    else if (a == "--min-mac") min_mac = atoi(val());              // :47
+    else if (a == "--min-callrate") min_callrate = atof(val());    // :48
+    else if (a == "--sam" || a == "--tag-group" || a == "--tag-UMI" || a == "--sm" ||
              a == "--sm-list")
-      die("Option %s: BAM/VCF input is read through htslib, which this build does not have; build the pileup with "
+      die("Option %s: BAM input is read through htslib, which this build does not have; build the pileup with "
           "demuxlet's reader and pass it with --plp (INTEGRATION.md)", argv[i]);
     else die("Unrecognized option %s", argv[i]);
   }
   if (!plp_path || !out) { usage(); die("--plp and --out are required"); }
   if (alpha.empty()) { alpha.push_back(0.0); alpha.push_back(0.5); }   // :78-90
 
-  if (field && !field_path)
-    die("--field %s needs --field-matrix FILE (the FORMAT values as flat arrays; reading them from a VCF needs htslib)", field);
+  if (field && !field_path && !vcf_path)
+    die("--field %s needs --vcf FILE or --field-matrix FILE (the FORMAT values as flat arrays)", field);
+  if (field_path && vcf_path) die("--vcf and --field-matrix are two sources of the same matrix; give one");
   Plp p;
   load_plp(plp_path, &p);
   FieldFile ff;
@@ -201,6 +210,46 @@ int main(int argc, char** argv) {
     if (field && strcmp(field, names[ff.field]) != 0) die("--field %s does not match the field matrix (%s)", field, names[ff.field]);
     if (ff.nv != p.nv || ff.nsnps != p.nsnps) die("Field matrix %s does not have the samples / SNPs of the pileup", field_path);
     if (geno_error >= 0) ff.geno_error = geno_error;   // :46
+  }
+  if (vcf_path) {
+    // the VCF side of the reference's sweep (:142-231): records in file order, the genotype-count filter
+    // (--min-mac / --min-callrate, always on GT), the survivors are SNP ids 0, 1, ... of the pileup (scl.add_snp)
+    static const char* const names[3] = {"GT", "GP", "PL"};
+    if (!field) field = "GP";                          // :9
+    ff.field = -1;
+    for (int f = 0; f < 3; ++f)
+      if (strcmp(field, names[f]) == 0) ff.field = f;
+    if (ff.field < 0) die("--field %s: only GT, GP and PL are known", field);
+    dmx_vcf* v = nullptr;
+    if (dmx_vcf_read(vcf_path, ff.field, &v) != DMX_OK) die("Cannot read VCF: %s", dmx_vcf_last_error());
+    int32_t vnv = 0;
+    int64_t nrec = 0, nskip = 0;
+    dmx_vcf_sizes(v, &vnv, &nrec, &nskip, nullptr);
+    if (vnv != p.nv) die("VCF %s does not have the samples of the pileup", vcf_path);
+    std::vector<int8_t> gt((size_t)nrec * vnv * 2);
+    const size_t per = (size_t)vnv * (ff.field == DMX_FIELD_GT ? 2 : 12);
+    std::vector<unsigned char> vals((size_t)nrec * per);
+    dmx_vcf_copy(v, gt.data(), vals.data(), nullptr, nullptr, nullptr, nullptr);
+    std::vector<uint8_t> pass((size_t)nrec);
+    const int frc = dmx_site_filter(gpu, vnv, nrec, gt.data(), min_mac, min_callrate, pass.data());
+    if (frc != DMX_OK) die("libdmx: %s", dmx_strerror(frc));
+    int64_t keep = 0;
+    for (int64_t r = 0; r < nrec; ++r)
+      if (pass[(size_t)r]) {
+        if (keep != r) memmove(vals.data() + (size_t)keep * per, vals.data() + (size_t)r * per, per);
+        ++keep;
+      }
+    vals.resize((size_t)keep * per);
+    if (verbose)
+      fprintf(stderr, "NOTICE - VCF: %lld biallelic records, %lld others skipped, %lld pass --min-mac %d --min-callrate %g\n",
+              (long long)nrec, (long long)nskip, (long long)keep, min_mac, min_callrate);
+    if (keep != p.nsnps) die("The records of %s that pass the filters are not the SNPs of the pileup", vcf_path);
+    for (int32_t j = 0; j < vnv; ++j) p.samples[(size_t)j] = dmx_vcf_sample(v, j);   // :506: names from the VCF header
+    dmx_vcf_free(v);
+    ff.nv = vnv; ff.nsnps = keep;
+    ff.geno_error = geno_error >= 0 ? geno_error : 0.01;   // :10
+    ff.data.swap(vals);
+    field_path = vcf_path;
   }
   if (groups) restrict_to_groups(groups, &p);
   if (verbose)

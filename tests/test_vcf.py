@@ -61,8 +61,9 @@ def test_vcf_to_matrix_chain(field, tmp_path):
     path = str(tmp_path / "a.vcf.gz")
     vcfio.write_vcf(path, samples, vcfio.random_records(rng, 600, len(samples), field), bgzip_like=True)
     v = api.read_vcf(path, field)
-    keep = api.site_filter(v["gt"], 1, 0.5)
-    assert np.array_equal(keep, po.site_filter(v["gt"], 1, 0.5)) and 0 < keep.sum() < len(keep)
+    assert np.array_equal(api.site_filter(v["gt"], 1, 0.5), po.site_filter(v["gt"], 1, 0.5))
+    keep = api.site_filter(v["gt"], 4, 0.9)
+    assert np.array_equal(keep, po.site_filter(v["gt"], 4, 0.9)) and 0 < keep.sum() < len(keep)
     vals = np.ascontiguousarray(v["values"][keep])
     if field == "GP":       # a record with a missing GP row yields NaNs: compare the finite records
         ok = ~np.isnan(vals).any(axis=(1, 2))
@@ -70,3 +71,38 @@ def test_vcf_to_matrix_chain(field, tmp_path):
     got = api.build_gp(field, vals, 0.01)
     want = po.build_gp(field, vals, 0.01)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("field", ["GT", "PL"])
+def test_cli_vcf(field, tmp_path):
+    """dmx-demuxlet --plp P --vcf V --field F: VCF text -> record filter -> matrix on the GPU -> the files --plp alone
+    writes when the pileup file carries the oracle's matrix of the same records; sample names come from the VCF"""
+    import dataclasses
+    import filecmp
+    import os
+    import subprocess
+    from demuxlet_b200 import synth
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "demuxlet_b200", "dmx-demuxlet")
+    rng = np.random.default_rng(9)
+    samples = ["donor%d" % i for i in range(6)]
+    path = str(tmp_path / "a.vcf.gz")
+    vcfio.write_vcf(path, samples, vcfio.random_records(rng, 900, len(samples), field), bgzip_like=True)
+    v = vcfio.parse_vcf(path, field)
+    keep = po.site_filter(v["gt"], 2, 0.6)
+    gp = po.build_gp(field, np.ascontiguousarray(v["values"][keep]), 0.03)
+    p = synth.make_synth(25, len(samples), int(keep.sum()), "GP", seed=5)
+    dataclasses.replace(p, gp=gp, samples=samples).save(str(tmp_path / "a.dmxp"))
+    dataclasses.replace(p, gp=np.zeros_like(gp)).save(str(tmp_path / "b.dmxp"))
+    ra = subprocess.run([exe, "--plp", str(tmp_path / "a.dmxp"), "--out", str(tmp_path / "a")], capture_output=True, text=True)
+    rb = subprocess.run([exe, "--plp", str(tmp_path / "b.dmxp"), "--out", str(tmp_path / "b"), "--vcf", path, "--field", field,
+                         "--geno-error", "0.03", "--min-mac", "2", "--min-callrate", "0.6", "--verbose"],
+                        capture_output=True, text=True)
+    assert ra.returncode == 0 and rb.returncode == 0, ra.stderr + rb.stderr
+    assert "pass --min-mac 2" in rb.stderr
+    for ext in ("best", "single", "sing2"):
+        assert filecmp.cmp(str(tmp_path / ("a." + ext)), str(tmp_path / ("b." + ext)), shallow=False), ext
+    assert "donor3" in open(tmp_path / "b.single").read()
+    bad = subprocess.run([exe, "--plp", str(tmp_path / "b.dmxp"), "--out", str(tmp_path / "c"), "--vcf", path, "--field", field],
+                         capture_output=True, text=True)          # default filter keeps another number of records
+    assert bad.returncode == 1 and "not the SNPs of the pileup" in bad.stderr
