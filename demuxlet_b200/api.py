@@ -33,7 +33,8 @@ ABI_SYMBOLS = [
     "dmx_rescore", "dmx_exact_llk", "dmx_write_outputs", "dmx_get_stats", "dmx_alloc_host", "dmx_free_host", "dmx_strerror",
     "dmx_last_error", "dmx_abi_version", "dmx_pack_reads", "dmx_pileup_sizes", "dmx_pileup_copy", "dmx_pileup_free",
     "dmx_build_gp", "dmx_build_gp_device", "dmx_set_field", "dmx_site_filter",
-    "dmx_vcf_read", "dmx_vcf_sizes", "dmx_vcf_sample", "dmx_vcf_chrom", "dmx_vcf_copy", "dmx_vcf_free", "dmx_vcf_last_error",
+    "dmx_sweep_opts_default", "dmx_sweep_bam", "dmx_sweep_sizes", "dmx_sweep_counts", "dmx_sweep_copy", "dmx_sweep_barcode",
+    "dmx_sweep_free", "dmx_sweep_last_error", "dmx_vcf_read", "dmx_vcf_sizes", "dmx_vcf_sample", "dmx_vcf_chrom", "dmx_vcf_copy", "dmx_vcf_free", "dmx_vcf_last_error",
 ]
 
 DMX_FIELD = {"GT": 0, "GP": 1, "PL": 2}            # --field (cmd_cram_demuxlet.cpp:28, :45)
@@ -234,6 +235,67 @@ def read_vcf(path: str, field: str = "GT") -> dict:
                 "rid": rid, "pos": pos, "ref": ref, "alt": alt, "gt": gt, "values": vals, "n_skipped": nskip.value}
     finally:
         lib.dmx_vcf_free(h)
+
+
+class DmxSweepOpts(C.Structure):
+    _fields_ = [("tag_group", C.c_char_p), ("tag_umi", C.c_char_p), ("min_mq", C.c_int32), ("exclude_flag", C.c_uint32),
+                ("min_bq", C.c_int32), ("cap_bq", C.c_int32), ("min_td", C.c_int32), ("n_groups", C.c_int64),
+                ("groups", C.POINTER(C.c_char_p))]
+
+
+def sweep_bam(path: str, chroms: Sequence[str], snp_rid, snp_pos, snp_ref, snp_alt, groups: Optional[Sequence[str]] = None,
+              **opts) -> dict:
+    """dmx_sweep_bam: the reference's BAM sweep (/root/reference/cmd_cram_demuxlet.cpp:186-338) as flat arrays: one
+    (cell, snp, umi, allele, bq) per add_read call in call order, barcodes in add_cell order, RD.TOTL.
+    opts: tag_group, tag_umi, min_mq, exclude_flag, min_bq, cap_bq, min_td."""
+    lib = load_library()
+    lib.dmx_sweep_opts_default.argtypes = [C.POINTER(DmxSweepOpts)]
+    lib.dmx_sweep_opts_default.restype = None
+    lib.dmx_sweep_bam.argtypes = [C.c_char_p, C.POINTER(DmxSweepOpts), C.c_int32, C.POINTER(C.c_char_p), C.c_int64,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.dmx_sweep_sizes.argtypes = [C.c_void_p] + [C.POINTER(C.c_int64)] * 3
+    lib.dmx_sweep_counts.argtypes = [C.c_void_p] + [C.POINTER(C.c_int64)] * 4
+    lib.dmx_sweep_copy.argtypes = [C.c_void_p] * 8
+    lib.dmx_sweep_barcode.argtypes = [C.c_void_p, C.c_int64]
+    lib.dmx_sweep_barcode.restype = C.c_char_p
+    lib.dmx_sweep_free.argtypes = [C.c_void_p]
+    lib.dmx_sweep_free.restype = None
+    lib.dmx_sweep_last_error.restype = C.c_char_p
+    o = DmxSweepOpts()
+    lib.dmx_sweep_opts_default(C.byref(o))
+    for k, v in opts.items():
+        setattr(o, k, v.encode() if isinstance(v, str) else v)
+    keep = [g.encode() for g in (groups or [])]
+    garr = (C.c_char_p * max(len(keep), 1))(*keep)
+    o.n_groups, o.groups = len(keep), garr
+    carr = (C.c_char_p * max(len(chroms), 1))(*[c.encode() for c in chroms])
+    rid = np.ascontiguousarray(snp_rid, np.int32)
+    pos = np.ascontiguousarray(snp_pos, np.int32)
+    ref = np.ascontiguousarray(snp_ref, "S1")
+    alt = np.ascontiguousarray(snp_alt, "S1")
+    h = C.c_void_p()
+    rc = lib.dmx_sweep_bam(os.fsencode(path), C.byref(o), len(chroms), carr, len(pos), rid.ctypes.data, pos.ctypes.data,
+                           ref.ctypes.data, alt.ctypes.data, C.byref(h))
+    if rc != 0:
+        raise DmxError(rc, "dmx_sweep_bam", lib.dmx_sweep_last_error().decode())
+    try:
+        nc, nr, ub = C.c_int64(), C.c_int64(), C.c_int64()
+        lib.dmx_sweep_sizes(h, C.byref(nc), C.byref(nr), C.byref(ub))
+        cnt = [C.c_int64() for _ in range(4)]
+        lib.dmx_sweep_counts(h, *[C.byref(c) for c in cnt])
+        nc, nr, ub = nc.value, nr.value, ub.value
+        cell, snp = np.zeros(nr, np.int32), np.zeros(nr, np.int32)
+        allele, bq = np.zeros(nr, np.uint8), np.zeros(nr, np.uint8)
+        umi_buf, umi_off, totl = np.zeros(max(ub, 1), np.uint8), np.zeros(nr + 1, np.int64), np.zeros(nc, np.int32)
+        lib.dmx_sweep_copy(h, cell.ctypes.data, snp.ctypes.data, allele.ctypes.data, bq.ctypes.data, umi_buf.ctypes.data,
+                           umi_off.ctypes.data, totl.ctypes.data)
+        raw = umi_buf.tobytes()
+        return {"barcodes": [lib.dmx_sweep_barcode(h, i).decode() for i in range(nc)], "totl": totl, "cell": cell,
+                "snp": snp, "allele": allele, "bq": bq,
+                "umis": [raw[umi_off[i]:umi_off[i + 1]].decode() for i in range(nr)],
+                "counts": dict(zip(("records", "filtered", "off_vcf", "skip_bcd"), [c.value for c in cnt]))}
+    finally:
+        lib.dmx_sweep_free(h)
 
 
 def encode_umis(umis: Sequence[str]):

@@ -152,13 +152,17 @@ void usage() {
           "  --vcf FILE [--field F] [--geno-error E] [--min-mac N] [--min-callrate R]\n"
           "                      the same from a VCF (plain / gzip / bgzip text; F defaults to GP): biallelic records that\n"
           "                      pass the genotype-count filter must be the SNPs of the pileup, in order\n"
-          "  --sam ...           BAM input needs htslib and is not part of this build\n");
+          "  --sam FILE --vcf FILE   instead of --plp: pile the reads of a coordinate-sorted BAM up on the VCF's records\n"
+          "                      [--tag-group CB] [--tag-UMI UB] [--min-MQ 20] [--excl-flag 0x0f04] [--min-BQ 13] [--cap-BQ 40]\n"
+          "                      [--min-TD 0]; own BGZF / BAM / VCF-text readers (no htslib; no CRAM / BCF / --sm)\n");
 }
 }  // namespace
 
 int main(int argc, char** argv) {
   const char *plp_path = nullptr, *out = nullptr, *groups = nullptr, *field = nullptr, *field_path = nullptr,
-             *vcf_path = nullptr;
+             *vcf_path = nullptr, *sam_path = nullptr;
+  dmx_sweep_opts so;
+  dmx_sweep_opts_default(&so);
   double geno_error = -1, min_callrate = 0.5;     // :25
   int min_mac = 1;                                // :24
   std::vector<double> alpha;
@@ -189,20 +193,28 @@ int main(int argc, char** argv) {
     else if (a == "--vcf") vcf_path = val();
     else if (a == "--min-mac") min_mac = atoi(val());              // :47
     else if (a == "--min-callrate") min_callrate = atof(val());    // :48
-    else if (a == "--sam" || a == "--tag-group" || a == "--tag-UMI" || a == "--sm" ||
-             a == "--sm-list")
-      die("Option %s: BAM input is read through htslib, which this build does not have; build the pileup with "
-          "demuxlet's reader and pass it with --plp (INTEGRATION.md)", argv[i]);
+    else if (a == "--sam") sam_path = val();                       // :39
+    else if (a == "--tag-group") so.tag_group = val();             // :40
+    else if (a == "--tag-UMI") so.tag_umi = val();                 // :41
+    else if (a == "--cap-BQ") so.cap_bq = atoi(val());             // :60-64
+    else if (a == "--min-BQ") so.min_bq = atoi(val());
+    else if (a == "--min-MQ") so.min_mq = atoi(val());
+    else if (a == "--min-TD") so.min_td = atoi(val());
+    else if (a == "--excl-flag") so.exclude_flag = (uint32_t)strtoul(val(), nullptr, 0);
+    else if (a == "--sm" || a == "--sm-list")
+      die("Option %s: sample subsets are not part of this build (all samples of the VCF are used)", argv[i]);
     else die("Unrecognized option %s", argv[i]);
   }
-  if (!plp_path || !out) { usage(); die("--plp and --out are required"); }
+  if ((!plp_path && !sam_path) || !out) { usage(); die("--plp (or --sam with --vcf) and --out are required"); }
+  if (plp_path && sam_path) die("--plp and --sam are two sources of the same pileup; give one");
+  if (sam_path && !vcf_path) die("--sam needs --vcf (the SNPs the reads are piled up on)");
   if (alpha.empty()) { alpha.push_back(0.0); alpha.push_back(0.5); }   // :78-90
 
   if (field && !field_path && !vcf_path)
     die("--field %s needs --vcf FILE or --field-matrix FILE (the FORMAT values as flat arrays)", field);
   if (field_path && vcf_path) die("--vcf and --field-matrix are two sources of the same matrix; give one");
   Plp p;
-  load_plp(plp_path, &p);
+  if (plp_path) load_plp(plp_path, &p);
   FieldFile ff;
   if (field_path) {
     load_field(field_path, &ff);
@@ -225,7 +237,7 @@ int main(int argc, char** argv) {
     int32_t vnv = 0;
     int64_t nrec = 0, nskip = 0;
     dmx_vcf_sizes(v, &vnv, &nrec, &nskip, nullptr);
-    if (vnv != p.nv) die("VCF %s does not have the samples of the pileup", vcf_path);
+    if (plp_path && vnv != p.nv) die("VCF %s does not have the samples of the pileup", vcf_path);
     std::vector<int8_t> gt((size_t)nrec * vnv * 2);
     const size_t per = (size_t)vnv * (ff.field == DMX_FIELD_GT ? 2 : 12);
     std::vector<unsigned char> vals((size_t)nrec * per);
@@ -243,8 +255,68 @@ int main(int argc, char** argv) {
     if (verbose)
       fprintf(stderr, "NOTICE - VCF: %lld biallelic records, %lld others skipped, %lld pass --min-mac %d --min-callrate %g\n",
               (long long)nrec, (long long)nskip, (long long)keep, min_mac, min_callrate);
-    if (keep != p.nsnps) die("The records of %s that pass the filters are not the SNPs of the pileup", vcf_path);
+    if (plp_path && keep != p.nsnps) die("The records of %s that pass the filters are not the SNPs of the pileup", vcf_path);
+    p.samples.resize((size_t)vnv);
     for (int32_t j = 0; j < vnv; ++j) p.samples[(size_t)j] = dmx_vcf_sample(v, j);   // :506: names from the VCF header
+    if (sam_path) {
+      // the BAM side (:186-338): sweep the reads over the surviving records, then the sort-based pileup packer in
+      // place of scl.add_read; --group-list acts inside the sweep like bcdSet (:131-140, :258)
+      std::vector<int32_t> rid((size_t)nrec), pos((size_t)nrec);
+      std::vector<char> ref((size_t)nrec), alt((size_t)nrec);
+      dmx_vcf_copy(v, nullptr, nullptr, rid.data(), pos.data(), ref.data(), alt.data());
+      int64_t k2 = 0;
+      for (int64_t r = 0; r < nrec; ++r)
+        if (pass[(size_t)r]) { rid[(size_t)k2] = rid[(size_t)r]; pos[(size_t)k2] = pos[(size_t)r]; ref[(size_t)k2] = ref[(size_t)r]; alt[(size_t)k2] = alt[(size_t)r]; ++k2; }
+      int32_t nchrom = 0;
+      dmx_vcf_sizes(v, nullptr, nullptr, nullptr, &nchrom);
+      std::vector<const char*> chroms((size_t)nchrom);
+      for (int32_t c = 0; c < nchrom; ++c) chroms[(size_t)c] = dmx_vcf_chrom(v, c);
+      std::vector<std::string> keep_bcs;
+      std::vector<const char*> keep_ptr;
+      if (groups) {
+        FILE* gf = fopen(groups, "r");
+        if (!gf) die("Cannot open file %s for reading", groups);
+        char line[4096];
+        while (fgets(line, sizeof(line), gf)) {
+          const size_t n = strcspn(line, " \t\r\n");
+          if (n) keep_bcs.emplace_back(line, n);
+        }
+        fclose(gf);
+        for (const std::string& b : keep_bcs) keep_ptr.push_back(b.c_str());
+        so.n_groups = (int64_t)keep_ptr.size();
+        so.groups = keep_ptr.data();
+        groups = nullptr;
+      }
+      dmx_sweep* sw = nullptr;
+      if (dmx_sweep_bam(sam_path, &so, nchrom, chroms.data(), keep, rid.data(), pos.data(), ref.data(), alt.data(), &sw) != DMX_OK)
+        die("Cannot sweep %s: %s", sam_path, dmx_sweep_last_error());
+      int64_t nc = 0, nr = 0, ub = 0, cnt[4] = {0, 0, 0, 0};
+      dmx_sweep_sizes(sw, &nc, &nr, &ub);
+      dmx_sweep_counts(sw, &cnt[0], &cnt[1], &cnt[2], &cnt[3]);
+      std::vector<int32_t> rc_cell((size_t)nr), rc_snp((size_t)nr);
+      std::vector<uint8_t> rc_al((size_t)nr), rc_bq((size_t)nr);
+      std::vector<char> umi_buf((size_t)std::max<int64_t>(ub, 1));
+      std::vector<int64_t> umi_off((size_t)nr + 1);
+      p.totl.resize((size_t)nc);
+      dmx_sweep_copy(sw, rc_cell.data(), rc_snp.data(), rc_al.data(), rc_bq.data(), umi_buf.data(), umi_off.data(), p.totl.data());
+      p.barcodes.resize((size_t)nc);
+      for (int64_t i = 0; i < nc; ++i) p.barcodes[(size_t)i] = dmx_sweep_barcode(sw, i);
+      dmx_sweep_free(sw);
+      dmx_pileup* pk = nullptr;
+      if (dmx_pack_reads(nr, rc_cell.data(), rc_snp.data(), rc_al.data(), rc_bq.data(), umi_buf.data(), umi_off.data(), nc, 0, &pk) != DMX_OK)
+        die("dmx_pack_reads failed", "");
+      dmx_pileup_sizes(pk, &p.ncells, &p.E, &p.R);
+      p.cell_ptr.resize((size_t)p.ncells + 1); p.ent_snp.resize((size_t)p.E); p.ent_ptr.resize((size_t)p.E + 1);
+      p.reads.resize((size_t)p.R); p.npass.resize((size_t)p.ncells); p.uniq.resize((size_t)p.ncells);
+      dmx_pileup_copy(pk, p.cell_ptr.data(), p.ent_snp.data(), p.ent_ptr.data(), p.reads.data(), p.npass.data(), p.uniq.data());
+      dmx_pileup_free(pk);
+      p.nv = vnv; p.nsnps = keep;
+      if (verbose)
+        fprintf(stderr, "NOTICE - BAM: %lld records, %lld fail --min-MQ / --excl-flag, %lld off the VCF's chromosomes, %lld outside "
+                "--group-list; %lld (read, SNP) observations\n", (long long)cnt[0], (long long)cnt[1], (long long)cnt[2],
+                (long long)cnt[3], (long long)nr);
+      if (p.nv < 2) die("demuxlet needs at least two samples in the VCF", "");
+    }
     dmx_vcf_free(v);
     ff.nv = vnv; ff.nsnps = keep;
     ff.geno_error = geno_error >= 0 ? geno_error : 0.01;   // :10

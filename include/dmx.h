@@ -234,6 +234,36 @@ int dmx_vcf_copy(const dmx_vcf* v, int8_t* gt, void* field_values, int32_t* rid,
 void dmx_vcf_free(dmx_vcf* v);
 const char* dmx_vcf_last_error(void);
 
+/* ---- BAM sweep (host only, no htslib; SURVEY 8f N4, BAM half) ----------------------------------------------------
+ * The reference's walk over the position-sorted BAM next to the SNP list (cmd_cram_demuxlet.cpp:186-338): alignment
+ * filter (sam_filtered_reader.cpp:284-296), barcode / UMI tags, RD.TOTL, and per overlapping SNP the base and quality
+ * at the SNP position through the CIGAR (hts_utils.cpp:279-359), thresholds and the allele code (:304-325).  Emits one
+ * tuple per scl.add_read call, in call order -- exactly the arrays dmx_pack_reads takes --, the barcodes in add_cell
+ * order and cell_totl_reads.  SNPs: sorted by (rid, pos), ids = their index (the order of scl.add_snp); chroms[rid] are
+ * the VCF's chromosome names. */
+typedef struct {
+  const char* tag_group;       /* --tag-group, "CB" (:12); "" = one group "." (:241-243)             */
+  const char* tag_umi;         /* --tag-UMI, "UB" (:13); "" (random UMIs, :276) is refused            */
+  int32_t min_mq;              /* --min-MQ 20 (:19)                                                   */
+  uint32_t exclude_flag;       /* --excl-flag 0x0f04 (:18)                                            */
+  int32_t min_bq, cap_bq, min_td;   /* --min-BQ 13, --cap-BQ 40, --min-TD 0 (:14-16)                 */
+  int64_t n_groups;            /* --group-list (:68, :131-140): barcodes to keep, 0 = all             */
+  const char* const* groups;
+} dmx_sweep_opts;
+typedef struct dmx_sweep dmx_sweep;
+void dmx_sweep_opts_default(dmx_sweep_opts* o);
+int dmx_sweep_bam(const char* path, const dmx_sweep_opts* o, int32_t n_chrom, const char* const* chroms, int64_t nsnps,
+                  const int32_t* snp_rid, const int32_t* snp_pos /* 0-based */, const char* snp_ref, const char* snp_alt,
+                  dmx_sweep** out);
+int dmx_sweep_sizes(const dmx_sweep* s, int64_t* ncells, int64_t* nreads, int64_t* umi_bytes);
+int dmx_sweep_counts(const dmx_sweep* s, int64_t* n_records, int64_t* n_filtered, int64_t* n_off_vcf, int64_t* n_skip_bcd);
+/* cell / snp / allele / bq [nreads], umi_buf[umi_bytes], umi_off[nreads+1], totl[ncells]; any pointer may be null */
+int dmx_sweep_copy(const dmx_sweep* s, int32_t* cell, int32_t* snp, uint8_t* allele, uint8_t* bq, char* umi_buf,
+                   int64_t* umi_off, int32_t* totl);
+const char* dmx_sweep_barcode(const dmx_sweep* s, int64_t i);
+void dmx_sweep_free(dmx_sweep* s);
+const char* dmx_sweep_last_error(void);
+
 /* pinned host memory for DMX_BORROW_INPUTS callers */
 void* dmx_alloc_host(int64_t bytes);
 void dmx_free_host(void* p);

@@ -1,0 +1,161 @@
+"""BAM fixtures and a plain-python restatement of demuxlet_b200/csrc/dmx_bam.cpp (the reference's BAM sweep,
+/root/reference/cmd_cram_demuxlet.cpp:186-338 with hts_utils.cpp:279-359 and sam_filtered_reader.cpp:284-296): the
+checker of the C++ sweep.  The BAM writer follows the SAM specification (section 4.2; BGZF = concatenated gzip members).
+htslib is not in this image, so parity with htslib's own decoding is unpinned."""
+import gzip
+import struct
+
+import numpy as np
+
+CIGAR_OPS = "MIDNSHP=X"
+SEQ_CODE = {c: i for i, c in enumerate("=ACMGRSVTWYHKDBN")}
+
+
+def write_bam(path, refs, reads, member=4000):
+    """refs: [(name, length)]; reads: dicts tid, pos, mapq, flag, cigar [(op, len)], seq, qual (list of ints or None),
+    tags [(tag, type, value)] with type in Z, i, A, B (B: list of uint8)"""
+    text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join("@SQ\tSN:%s\tLN:%d\n" % r for r in refs)
+    out = bytearray(b"BAM\1" + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", len(refs)))
+    for name, ln in refs:
+        out += struct.pack("<i", len(name) + 1) + name.encode() + b"\0" + struct.pack("<i", ln)
+    for i, r in enumerate(reads):
+        name = ("r%d" % i).encode() + b"\0"
+        seq = r["seq"]
+        cig = b"".join(struct.pack("<I", (ln << 4) | CIGAR_OPS.index(op)) for op, ln in r["cigar"])
+        sq = bytearray((len(seq) + 1) // 2)
+        for k, c in enumerate(seq):
+            sq[k >> 1] |= SEQ_CODE[c] << (4 if k % 2 == 0 else 0)
+        ql = bytes(r["qual"]) if r["qual"] is not None else b"\xff" * len(seq)
+        aux = b""
+        for tag, typ, val in r["tags"]:
+            if typ == "Z":
+                aux += tag.encode() + b"Z" + val.encode() + b"\0"
+            elif typ == "i":
+                aux += tag.encode() + b"i" + struct.pack("<i", val)
+            elif typ == "A":
+                aux += tag.encode() + b"A" + val.encode()
+            elif typ == "B":
+                aux += tag.encode() + b"BC" + struct.pack("<I", len(val)) + bytes(val)
+        body = struct.pack("<iiBBHHHiiii", r["tid"], r["pos"], len(name), r["mapq"], 0, len(r["cigar"]), r["flag"],
+                           len(seq), -1, -1, 0) + name + cig + bytes(sq) + ql + aux
+        out += struct.pack("<i", len(body)) + body
+    with open(path, "wb") as f:
+        for i in range(0, len(out), member):
+            f.write(gzip.compress(bytes(out[i:i + member])))
+        f.write(gzip.compress(b""))     # BGZF end-of-file marker: an empty member
+
+
+def sweep(refs, reads, chroms, snp_rid, snp_pos, snp_ref, snp_alt, groups=None, tag_group="CB", tag_umi="UB", min_mq=20,
+          exclude_flag=0x0f04, min_bq=13, cap_bq=40, min_td=0):
+    name2rid = {c: i for i, c in enumerate(chroms)}
+    tid2rid = [name2rid.get(n, -1) for n, _ in refs]
+    bc, totl = {}, []
+    out = {"cell": [], "snp": [], "allele": [], "bq": [], "umis": []}
+    cnt = {"records": 0, "filtered": 0, "off_vcf": 0, "skip_bcd": 0}
+    groups = set(groups or [])
+    for r in reads:
+        cnt["records"] += 1
+        if r["mapq"] < min_mq or (r["flag"] & exclude_flag):
+            cnt["filtered"] += 1
+            continue
+        rid = tid2rid[r["tid"]] if 0 <= r["tid"] < len(refs) else -1
+        if rid < 0:
+            cnt["off_vcf"] += 1
+            continue
+        span = sum(ln for op, ln in r["cigar"] if op in "MDN=X")
+        endpos = r["pos"] + (span if span > 0 else 1)
+        tags = {t: v for t, ty, v in r["tags"] if ty == "Z"}
+        sb = tags.get(tag_group, ".") if tag_group else "."
+        if tag_group and groups and sb not in groups:
+            cnt["skip_bcd"] += 1
+            continue
+        if sb not in bc:
+            bc[sb] = len(bc)
+            totl.append(0)
+        ib = bc[sb]
+        umi = tags.get(tag_umi, ".")
+        totl[ib] += 1
+        for i in range(len(snp_pos)):
+            if snp_rid[i] != rid or not (r["pos"] <= snp_pos[i] < endpos):
+                continue
+            if not r["cigar"]:
+                continue
+            cpos, rpos, sp = r["pos"], 0, int(snp_pos[i])
+            for op, ln in r["cigar"]:                      # hts_utils.cpp:296-330
+                if op == "M":
+                    if cpos <= sp <= cpos + ln - 1:
+                        rpos += sp - cpos
+                        break
+                    cpos += ln
+                    rpos += ln
+                elif op in "DN":
+                    if cpos <= sp <= cpos + ln - 1:
+                        rpos = -1
+                        break
+                    cpos += ln
+                elif op in "SI":
+                    rpos += ln
+            if rpos < 0 or rpos >= len(r["seq"]):
+                continue
+            base = r["seq"][rpos]
+            if base == "N":
+                continue
+            raw = 0xff if r["qual"] is None else r["qual"][rpos]
+            q = (raw + 33) & 0xff                          # the reference's signed char qual + 33
+            q = (q - 256 if q >= 128 else q) - 33
+            if q < min_bq or rpos < min_td - 1 or rpos + min_td > len(r["seq"]):
+                continue
+            out["cell"].append(ib)
+            out["snp"].append(i)
+            out["allele"].append(0 if base == snp_ref[i].decode() else (1 if base == snp_alt[i].decode() else 2))
+            out["bq"].append(min(q, cap_bq))
+            out["umis"].append(umi)
+    return {"barcodes": list(bc), "totl": np.array(totl, np.int32), "cell": np.array(out["cell"], np.int32),
+            "snp": np.array(out["snp"], np.int32), "allele": np.array(out["allele"], np.uint8),
+            "bq": np.array(out["bq"], np.uint8), "umis": out["umis"], "counts": cnt}
+
+
+def random_reads(rng, refs, snp_by_tid, n, ncells=12):
+    """position-sorted reads with a mix of CIGARs, flags, qualities and tags; every third read covers a SNP"""
+    barcodes = ["".join(rng.choice(list("ACGT"), 10)) + "-1" for _ in range(ncells)]
+    reads = []
+    for _ in range(n):
+        tid = int(rng.integers(0, len(refs)))
+        snps = snp_by_tid.get(tid, [])
+        if len(snps) and rng.random() < 0.7:
+            pos = max(0, int(snps[rng.integers(0, len(snps))]) - int(rng.integers(0, 60)))
+        else:
+            pos = int(rng.integers(0, refs[tid][1] - 200))
+        kind = rng.random()
+        if kind < 0.4:
+            cigar = [("M", 90)]
+        elif kind < 0.55:
+            cigar = [("S", 7), ("M", 40), ("I", 3), ("M", 40)]
+        elif kind < 0.7:
+            cigar = [("M", 30), ("D", 4), ("M", 60)]
+        elif kind < 0.85:
+            cigar = [("M", 25), ("N", 150), ("M", 65)]
+        elif kind < 0.95:
+            cigar = [("H", 5), ("S", 3), ("M", 50), ("S", 37)]
+        else:
+            cigar = []
+        lseq = sum(ln for op, ln in cigar if op in "MIS=X") or 50
+        seq = "".join(rng.choice(list("ACGTN"), lseq, p=[0.24, 0.24, 0.24, 0.24, 0.04]))
+        if rng.random() < 0.03:
+            qual = None
+        else:
+            qual = [int(x) for x in rng.choice([2, 8, 12, 13, 14, 25, 37, 40, 41, 60, 93, 100], lseq)]
+        flag = int(rng.choice([0, 16, 0x4, 0x100, 0x400, 0x800, 1 | 2 | 64], p=[0.45, 0.3, 0.03, 0.04, 0.04, 0.04, 0.1]))
+        tags = [("NH", "i", 1), ("xf", "B", [1, 2, 3])]
+        u = rng.random()
+        if u < 0.9:
+            tags.append(("CB", "Z", barcodes[rng.integers(0, ncells)]))
+        elif u < 0.95:
+            tags.append(("CB", "A", "x"))                 # wrong type: treated as missing
+        if rng.random() < 0.92:
+            tags.append(("UB", "Z", "".join(rng.choice(list("ACGT"), 3))))
+        tags.append(("RG", "Z", "grp"))
+        reads.append({"tid": tid, "pos": pos, "mapq": int(rng.choice([0, 3, 19, 20, 60, 255])), "flag": flag, "cigar": cigar,
+                      "seq": seq, "qual": qual, "tags": tags})
+    reads.sort(key=lambda r: (r["tid"], r["pos"]))
+    return reads, barcodes

@@ -1,0 +1,135 @@
+"""dmx_sweep_bam (htslib-free BAM reader + the reference's BAM sweep, SURVEY 8f N4 / BAM half; host only) against the
+plain-python restatement in tests/bamio.py on generated BAM files; then the whole command line,
+dmx-demuxlet --sam --vcf --field, against the oracle chain on the GPU."""
+import os
+
+import numpy as np
+import pytest
+
+from demuxlet_b200 import api
+from tests import bamio, vcfio
+
+REFS = [("chrM", 3000), ("chr1", 60000), ("chr2", 50000), ("chrUn", 5000)]
+
+
+def make_snps(rng, n=400):
+    chroms = ["chr1", "chr2"]                 # the VCF has no chrM / chrUn: reads there are skipped (:188-191)
+    rid = np.sort(rng.integers(0, 2, n)).astype(np.int32)
+    pos = np.zeros(n, np.int32)
+    for r in (0, 1):
+        m = rid == r
+        pos[m] = np.sort(rng.choice(np.arange(100, 45000), m.sum(), replace=False))
+    ref = rng.choice(np.array([b"A", b"C", b"G", b"T"]), n).astype("S1")
+    alt = np.array([rng.choice([b for b in (b"A", b"C", b"G", b"T") if b != x]) for x in ref]).astype("S1")
+    return chroms, rid, pos, ref, alt
+
+
+def same(a, b):
+    assert a["barcodes"] == b["barcodes"] and a["counts"] == b["counts"]
+    for k in ("totl", "cell", "snp", "allele", "bq"):
+        assert np.array_equal(a[k], b[k]), k
+    assert a["umis"] == b["umis"]
+
+
+@pytest.mark.parametrize("seed,opts", [(1, {}), (2, {"min_bq": 0, "cap_bq": 30, "min_td": 5}),
+                                       (3, {"min_mq": 0, "exclude_flag": 0x4}), (4, {"tag_group": "", "tag_umi": "RG"})])
+def test_sweep_matches_restatement(seed, opts, tmp_path):
+    rng = np.random.default_rng(seed)
+    chroms, rid, pos, ref, alt = make_snps(rng)
+    by_tid = {1: pos[rid == 0], 2: pos[rid == 1]}
+    reads, barcodes = bamio.random_reads(rng, REFS, by_tid, 3000)
+    path = str(tmp_path / "a.bam")
+    bamio.write_bam(path, REFS, reads)
+    got = api.sweep_bam(path, chroms, rid, pos, ref, alt, **opts)
+    want = bamio.sweep(REFS, reads, chroms, rid, pos, ref, alt, **opts)
+    same(got, want)
+    assert len(got["cell"]) > 300 and got["counts"]["filtered"] > 0 and got["counts"]["off_vcf"] > 0
+    if not opts:
+        assert "." in got["barcodes"] and "." in got["umis"] and set(got["allele"]) == {0, 1, 2}
+        keep = barcodes[:5]
+        same(api.sweep_bam(path, chroms, rid, pos, ref, alt, groups=keep),
+             bamio.sweep(REFS, reads, chroms, rid, pos, ref, alt, groups=keep))
+
+
+def test_sweep_feeds_the_packer(tmp_path):
+    """sweep tuples -> dmx_pack_reads == the python container restatement on the same tuples"""
+    from demuxlet_b200.plp import build_from_reads
+    rng = np.random.default_rng(5)
+    chroms, rid, pos, ref, alt = make_snps(rng)
+    reads, _ = bamio.random_reads(rng, REFS, {1: pos[rid == 0], 2: pos[rid == 1]}, 4000)
+    path = str(tmp_path / "a.bam")
+    bamio.write_bam(path, REFS, reads)
+    s = api.sweep_bam(path, chroms, rid, pos, ref, alt)
+    packed = api.pack_reads(s["cell"], s["snp"], s["umis"], s["allele"], s["bq"], len(s["barcodes"]))
+    gp = np.full((len(pos), 2, 3), 1 / 3, np.float32)
+    want = build_from_reads(gp, s["cell"], s["snp"], s["umis"], s["allele"], s["bq"], s["barcodes"], ["a", "b"], s["totl"])
+    for k in ("cell_ptr", "ent_snp", "ent_ptr", "reads", "npass", "uniq"):
+        assert np.array_equal(packed[k], getattr(want, k)), k
+    assert packed["npass"].sum() == len(s["cell"]) and (s["totl"] >= packed["npass"]).all()
+
+
+def test_sweep_errors(tmp_path):
+    rng = np.random.default_rng(6)
+    chroms, rid, pos, ref, alt = make_snps(rng, 20)
+    with pytest.raises(api.DmxError):
+        api.sweep_bam(str(tmp_path / "none.bam"), chroms, rid, pos, ref, alt)
+    p = tmp_path / "bad.bam"
+    p.write_bytes(b"not a bam")
+    with pytest.raises(api.DmxError, match="not a BAM"):
+        api.sweep_bam(str(p), chroms, rid, pos, ref, alt)
+    path = str(tmp_path / "a.bam")
+    bamio.write_bam(path, REFS, [])
+    with pytest.raises(api.DmxError, match="sorted"):
+        api.sweep_bam(path, chroms, rid[::-1].copy(), pos, ref, alt)
+    with pytest.raises(api.DmxError, match="orderings"):
+        api.sweep_bam(path, chroms[::-1], rid, pos, ref, alt)
+    with pytest.raises(api.DmxError, match="tag-UMI"):
+        api.sweep_bam(path, chroms, rid, pos, ref, alt, tag_umi="")
+    assert api.sweep_bam(path, chroms, rid, pos, ref, alt)["barcodes"] == []
+
+
+def make_case(tmp_path, seed, field, nreads=6000, nv=5):
+    """a consistent VCF + BAM pair: records on chr1 / chr2, reads carrying the alleles of one donor per barcode"""
+    rng = np.random.default_rng(seed)
+    samples = ["donor%d" % i for i in range(nv)]
+    recs = vcfio.random_records(rng, 500, nv, field)
+    recs = [(("chr1" if i < 250 else "chr2"), 200 + 37 * (i % 250), r[2], r[3], r[4], r[5]) for i, r in enumerate(recs)]
+    vcf = str(tmp_path / "a.vcf.gz")
+    vcfio.write_vcf(vcf, samples, recs, bgzip_like=True)
+    v = vcfio.parse_vcf(vcf, field)
+    by_tid = {1: v["pos"][v["rid"] == 0], 2: v["pos"][v["rid"] == 1]}
+    reads, barcodes = bamio.random_reads(rng, REFS, by_tid, nreads, ncells=20)
+    bam = str(tmp_path / "a.bam")
+    bamio.write_bam(bam, REFS, reads)
+    return vcf, bam, v, reads, samples, barcodes
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("field,seed", [("GT", 11), ("PL", 12)])
+def test_cli_sam_vcf_end_to_end(field, seed, tmp_path):
+    """dmx-demuxlet --sam BAM --vcf VCF --field F --out P, demuxlet's own command line, against the oracle chain
+    (python VCF / BAM restatements -> oracle filter and matrix -> python add_read container -> oracle likelihoods and
+    writers): identity columns byte-identical, LLK columns within 1e-4"""
+    import subprocess
+    from demuxlet_b200.plp import build_from_reads
+    from oracle import pyoracle as po
+    from tests.util import diff_tsv
+    from tests.test_gpu_parity import BEST_EXACT, ROW_EXACT
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "demuxlet_b200", "dmx-demuxlet")
+    vcf, bam, v, reads, samples, barcodes = make_case(tmp_path, seed, field)
+    keep = po.site_filter(v["gt"], 1, 0.5)
+    vals = np.ascontiguousarray(v["values"][keep])
+    gp = po.build_gp(field, vals, 0.01)
+    groups = barcodes[:15] + ["."]
+    s = bamio.sweep(REFS, reads, v["chroms"], v["rid"][keep], v["pos"][keep], v["ref"][keep], v["alt"][keep], groups=groups)
+    plp = build_from_reads(gp, s["cell"], s["snp"], s["umis"], s["allele"], s["bq"], s["barcodes"], samples, s["totl"])
+    po.Oracle(plp, (0.0, 0.5)).write_all(str(tmp_path / "orc"))
+    (tmp_path / "groups.txt").write_text("\n".join(groups) + "\n")
+    r = subprocess.run([exe, "--sam", bam, "--vcf", vcf, "--field", field, "--out", str(tmp_path / "cli"), "--fp64-pairs",
+                        "--group-list", str(tmp_path / "groups.txt"), "--verbose"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "observations" in r.stderr
+    diff_tsv(tmp_path / "orc.best", tmp_path / "cli.best", BEST_EXACT)
+    for ext in ("single", "sing2"):
+        diff_tsv(tmp_path / ("orc." + ext), tmp_path / ("cli." + ext), ROW_EXACT)
+    assert len(open(tmp_path / "cli.best").read().splitlines()) > 10
