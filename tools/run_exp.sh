@@ -1,2 +1,4 @@
 cd $GRAFT_REPO_ROOT
-timeout 600 python -m pytest tests/test_bam.py tests/test_vcf.py -m gpu -x -q 2>&1 | tail -12
+mkdir -p gpurun_out
+timeout 300 ./tools/tf32_bench > gpurun_out/r1d_tf32_bench.jsonl 2>&1
+cat gpurun_out/r1d_tf32_bench.jsonl
