@@ -159,3 +159,93 @@ def random_reads(rng, refs, snp_by_tid, n, ncells=12):
                       "seq": seq, "qual": qual, "tags": tags})
     reads.sort(key=lambda r: (r["tid"], r["pos"]))
     return reads, barcodes
+
+
+# ---- the reference's own CIGAR look-up (oracle/_ref/ref_cigar) ---------------------------------------------------
+import os as _os
+import subprocess as _subprocess
+
+REF_CIGAR = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "oracle", "_ref", "ref_cigar")
+
+
+def lookup(read, spos):
+    """python restatement of bam_get_base_and_qual_and_read_and_qual (hts_utils.cpp:279-359): (base, qual char as a
+    signed value, rpos); rpos -1 = BAM_READ_INDEX_NA"""
+    rlen = len(read["seq"])
+    base, qual, rpos = "N", 0, 0
+    if read["cigar"]:
+        cpos = read["pos"]
+        for op, ln in read["cigar"]:
+            if op == "M":
+                if cpos <= spos <= cpos + ln - 1:
+                    rpos += spos - cpos
+                    break
+                cpos += ln
+                rpos += ln
+            elif op in "DN":
+                if cpos <= spos <= cpos + ln - 1:
+                    rpos = -1
+                    break
+                cpos += ln
+            elif op in "SI":
+                rpos += ln
+        if 0 <= rpos <= rlen:
+            base = read["seq"][rpos] if rpos < rlen else "\0"
+            raw = 0 if rpos >= rlen else (0xff if read["qual"] is None else read["qual"][rpos]) + 33
+            raw &= 0xff
+            qual = raw - 256 if raw >= 128 else raw
+        else:
+            rpos = -1
+    if rpos >= rlen:
+        rpos, base = -1, "."
+    return base, qual, rpos
+
+
+def run_ref_cigar(reads, queries, tmpdir):
+    """[(base, qual, rpos)] per read and query position from the reference's function"""
+    fin, fout = _os.path.join(tmpdir, "cases.bin"), _os.path.join(tmpdir, "cases.out")
+    with open(fin, "wb") as f:
+        f.write(struct.pack("<i", len(reads)))
+        for r, qs in zip(reads, queries):
+            f.write(struct.pack("<ii", r["pos"], len(r["cigar"])))
+            for op, ln in r["cigar"]:
+                f.write(struct.pack("<I", (ln << 4) | CIGAR_OPS.index(op)))
+            seq = r["seq"]
+            sq = bytearray((len(seq) + 1) // 2)
+            for k, c in enumerate(seq):
+                sq[k >> 1] |= SEQ_CODE[c] << (4 if k % 2 == 0 else 0)
+            f.write(struct.pack("<i", len(seq)) + bytes(sq))
+            f.write(bytes(r["qual"]) if r["qual"] is not None else b"\xff" * len(seq))
+            f.write(struct.pack("<i", len(qs)) + b"".join(struct.pack("<I", q) for q in qs))
+    _subprocess.run([REF_CIGAR, fin, fout], check=True)
+    raw = open(fout, "rb").read()
+    out, k = [], 0
+    for qs in queries:
+        row = []
+        for _ in qs:
+            b, q, rp = struct.unpack_from("<bbi", raw, k)
+            k += 6
+            row.append((chr(b & 0xff), q, rp))
+        out.append(row)
+    return out
+
+
+def cigar_cases(rng, n=300):
+    """reads with every CIGAR operation, also ones the reference's walk ignores (=, X, H, P), and their query positions"""
+    shapes = [[("M", 40)], [("S", 5), ("M", 20), ("I", 2), ("M", 13)], [("M", 10), ("D", 3), ("M", 30)],
+              [("M", 12), ("N", 40), ("M", 28)], [("H", 4), ("S", 2), ("M", 30), ("S", 8)], [],
+              [("=", 10), ("X", 1), ("M", 29)], [("M", 10), ("P", 2), ("I", 1), ("M", 29)], [("S", 40)], [("M", 1)],
+              [("I", 3), ("M", 37)], [("M", 20), ("D", 1), ("I", 1), ("M", 19)]]
+    reads, queries = [], []
+    for i in range(n):
+        cigar = shapes[i % len(shapes)]
+        lseq = sum(ln for op, ln in cigar if op in "MIS=X") or 20
+        pos = int(rng.integers(0, 500))
+        seq = "".join(rng.choice(list("ACGTN"), lseq, p=[0.24, 0.24, 0.24, 0.24, 0.04]))
+        qual = None if i % 17 == 3 else [int(x) for x in rng.choice([0, 12, 13, 30, 40, 41, 94, 95, 120, 222, 223, 254], lseq)]
+        span = sum(ln for op, ln in cigar if op in "MDN=X")
+        reads.append({"tid": 0, "pos": pos, "mapq": 60, "flag": 0, "cigar": cigar, "seq": seq, "qual": qual,
+                      "tags": [("CB", "Z", "cell%d" % (i % 7)), ("UB", "Z", "u%d" % i)]})
+        queries.append(list(range(max(0, pos - 3), pos + max(span, 1) + 4)))
+    order = sorted(range(n), key=lambda i: reads[i]["pos"])
+    return [reads[i] for i in order], [queries[i] for i in order]

@@ -133,3 +133,61 @@ def test_cli_sam_vcf_end_to_end(field, seed, tmp_path):
     for ext in ("single", "sing2"):
         diff_tsv(tmp_path / ("orc." + ext), tmp_path / ("cli." + ext), ROW_EXACT)
     assert len(open(tmp_path / "cli.best").read().splitlines()) > 10
+
+
+def _reference_lookups(tmp_path):
+    """(reads, queries, results) of the CIGAR look-up cases: results from the committed golden file written by the
+    reference's function, cross-checked against the live function where oracle/_ref/ref_cigar is built"""
+    reads, queries = bamio.cigar_cases(np.random.default_rng(31))
+    flat = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cigar_lookup.npz"))["results"]
+    res, k = [], 0
+    for qs in queries:
+        res.append([(chr(int(b)), int(q), int(rp)) for b, q, rp in flat[k:k + len(qs)]])
+        k += len(qs)
+    assert k == len(flat)
+    if os.path.exists(bamio.REF_CIGAR):
+        assert bamio.run_ref_cigar(reads, queries, str(tmp_path)) == res
+    return reads, queries, res
+
+
+def test_cigar_lookup_restatement_against_reference_function(tmp_path):
+    reads, queries, res = _reference_lookups(tmp_path)
+    n_valid = 0
+    for r, qs, row in zip(reads, queries, res):
+        for q, want in zip(qs, row):
+            got = bamio.lookup(r, q)
+            assert got[2] == want[2], (r["cigar"], r["pos"], q, got, want)
+            if want[2] >= 0:                      # base / qual are only read when the position is found (:304-306)
+                assert got == want, (r["cigar"], r["pos"], q, got, want)
+                n_valid += 1
+    assert n_valid > 5000
+
+
+def test_sweep_lookup_against_reference_function(tmp_path):
+    """dmx_sweep_bam on the same reads with a SNP at every position: the emitted tuples are exactly the reference
+    function's results put through the thresholds of cmd_cram_demuxlet.cpp:304-315"""
+    reads, queries, res = _reference_lookups(tmp_path)
+    L = 700
+    rid, pos = np.zeros(L, np.int32), np.arange(L, dtype=np.int32)
+    ref, alt = np.full(L, b"A", "S1"), np.full(L, b"C", "S1")
+    path = str(tmp_path / "c.bam")
+    bamio.write_bam(path, [("chr1", 5000)], reads)
+    got = api.sweep_bam(path, ["chr1"], rid, pos, ref, alt)
+    want = []
+    cells = {}
+    for r, qs, row in zip(reads, queries, res):
+        cb = dict((t, v) for t, _, v in r["tags"])["CB"]
+        ic = cells.setdefault(cb, len(cells))
+        span = sum(ln for op, ln in r["cigar"] if op in "MDN=X")
+        for q, (base, qual, rpos) in zip(qs, row):
+            if not (r["pos"] <= q < r["pos"] + max(span, 1)):
+                # outside the aligned span the reference finds no base -- except for reads with = / X operations, which
+                # its walk ignores: there it returns the base at the offset the walk ended on for ANY buffered SNP (a
+                # defect the sweep does not reproduce: it only tests SNPs under the read, DESIGN.md 7)
+                assert rpos < 0 or base == "N" or not r["cigar"] or any(op in "=X" for op, _ in r["cigar"])
+                continue
+            if rpos < 0 or base == "N" or qual - 33 < 13:
+                continue
+            want.append((ic, q, 0 if base == "A" else (1 if base == "C" else 2), min(qual - 33, 40)))
+    have = list(zip(got["cell"].tolist(), got["snp"].tolist(), got["allele"].tolist(), got["bq"].tolist()))
+    assert have == want and len(want) > 3000
