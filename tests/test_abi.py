@@ -44,14 +44,16 @@ def test_abi_version_and_strerror(lib):
 
 def test_struct_sizes_match_header(tmp_path):
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "dmx.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(dmx_best_rec), '
-                   'sizeof(dmx_stats), sizeof(dmx_config));return 0;}\n')
+    src.write_text('#include <stdio.h>\n#include "dmx.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(dmx_best_rec), '
+                   'sizeof(dmx_stats), sizeof(dmx_config), sizeof(dmx_field_stats), sizeof(dmx_sweep_opts));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
-    a, b, c = map(int, subprocess.run([str(exe)], check=True, stdout=subprocess.PIPE).stdout.split())
+    a, b, c, d, e = map(int, subprocess.run([str(exe)], check=True, stdout=subprocess.PIPE).stdout.split())
     assert a == api.BEST_DTYPE.itemsize
     assert b == C.sizeof(api.DmxStats)
     assert c == C.sizeof(api.DmxConfig)
+    assert d == C.sizeof(api.DmxFieldStats)
+    assert e == C.sizeof(api.DmxSweepOpts)
 
 
 def test_no_cpu_fallback(lib):
