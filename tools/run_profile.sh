@@ -40,7 +40,7 @@ timeout 600 compute-sanitizer --tool $TOOL --print-limit 20 python /tmp/small_fi
 done
 cat gpurun_out/${T}_field_sanitizer.txt
 # microbenchmarks behind the round-2 plan
-for B in tf32_bench tmem_ld_bench umma_bench; do
+for B in tf32_bench tmem_ld_bench umma_bench umma_pipe_bench; do
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -diag-suppress 128 -o tools/$B tools/$B.cu && timeout 120 ./tools/$B > gpurun_out/${T}_$B.jsonl 2>&1
 tail -3 gpurun_out/${T}_$B.jsonl
 done

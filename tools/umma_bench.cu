@@ -76,13 +76,15 @@ __global__ void __launch_bounds__(128) k(const float* a_in, const float* b_in, f
   const uint64_t da = make_desc(smem_u32(sA)), db = make_desc(smem_u32(sB));
   uint32_t phase = 0;
   bool ok = true;
-  // 1. one MMA, read back
+  // 1. one MMA, read back (and its latency: issue -> commit -> mbarrier phase seen by the waiting threads)
+  const long long t_one = clock64();
   if (tid == 0) {
     mma_tf32(tmem, da, db, idesc, 0);
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&bar)));
   }
   ok = mbar_wait_bounded(smem_u32(&bar), phase);
   phase ^= 1;
+  if (tid == 0) clk_out[blockIdx.x * 2 + 1] = clock64() - t_one;   // (overwritten by the rate part unless nmma == 0)
   asm volatile("tcgen05.fence::after_thread_sync;\n");
   if (ok) {
     for (int c0 = 0; c0 < N; c0 += 16) {
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(128) k(const float* a_in, const float* b_in, f
   const uint32_t idesc_r = (1u << 4) | ((f16 ? 0u : 2u) << 7) | ((f16 ? 0u : 2u) << 10) | ((uint32_t)(n_rate >> 3) << 17) |
                            ((uint32_t)(m_rate >> 4) << 24);
   const uint32_t ntile = 512u / (uint32_t)n_rate;
-  for (int mode = 0; mode < 2 && ok; ++mode) {
+  for (int mode = 0; mode < 2 && ok && nmma > 0; ++mode) {
     long long t0 = 0;
     if (tid == 0) {
       t0 = clock64();
@@ -172,6 +174,12 @@ int main() {
   printf("{\"bench\": \"tcgen05.mma kind::tf32 M64 N64 K8 (SS, no swizzle)\", \"timeout\": %d, \"max_rel_err_rows_in_lanes_0_63\": %.3g, "
          "\"max_rel_err_rows_16_per_subpartition\": %.3g, \"clk_per_mma_dependent\": %.1f, \"clk_per_mma_independent\": %.1f}\n",
          st, err[0], err[1], (double)clk[0] / nmma, (double)clk[1] / nmma);
+  {
+    k<0><<<1, 128>>>(da, db, dd, dclk, 0, dst, 64, 64);
+    cudaDeviceSynchronize();
+    cudaMemcpy(clk, dclk, sizeof(clk), cudaMemcpyDeviceToHost);
+    printf("{\"bench\": \"latency of one tcgen05.mma M64 N64 K8: issue -> commit -> mbarrier observed\", \"clk\": %lld}\n", clk[1]);
+  }
   // all SMs at once, shapes and kinds: does the rate hold chip-wide, what do M = 128, wider N and kind::f16 cost?
   const int shapes[][3] = {{64, 64, 0}, {128, 64, 0}, {64, 128, 0}, {128, 128, 0}, {128, 256, 0},
                            {64, 64, 1}, {128, 64, 1}, {128, 128, 1}, {128, 256, 1}};
