@@ -32,6 +32,15 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
   }
   return false;
 }
+__device__ __forceinline__ bool mbar_poll(uint32_t bar, uint32_t parity) {   // non-blocking test_wait spin (issuer thread)
+  for (int i = 0; i < (1 << 24); ++i) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
 }
@@ -206,6 +215,8 @@ __global__ void __launch_bounds__(32 * 17) k2(float* out, long long* clk_out, in
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem));
 }
 
+// (CHUNKED = 1: the consumer overlaps its loads with its multiplies, 16 columns at a time; CHUNKED = 2: in addition the
+// issuer polls with test_wait instead of try_wait.  Neither changes the result.)
 // Staged variant with both lane halves: a stage is 8 entries -- 4 column tiles x 2 M = 64 accumulators that share the
 // columns (TMEM lanes 0-15 and 16-31 of every sub-partition), so one tcgen05.ld delivers the rows of two entries and all
 // 32 lanes of a consumer warp work.  Otherwise as k2: one wait
@@ -245,7 +256,7 @@ __global__ void __launch_bounds__(32 * 17) k3(float* out, long long* clk_out, in
       for (int s = 0; s < nstage && ok; ++s) {
         const int g = s & 1;
         const uint32_t ph = (uint32_t)(s >> 1) & 1u;
-        if (s >= 2) ok = mbar_wait(smem_u32(&empty[g]), ph ^ 1u);
+        if (s >= 2) ok = CHUNKED == 2 ? mbar_poll(smem_u32(&empty[g]), ph ^ 1u) : mbar_wait(smem_u32(&empty[g]), ph ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;\n");
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -381,6 +392,8 @@ void run(int sms, int m) {
 int main() {
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  run3<1, 2>(sms, 64);
+  run3<2, 2>(sms, 64);
   run3<1, 1>(sms, 64);
   run3<2, 1>(sms, 64);
   run3<1>(sms, 64);
