@@ -18,11 +18,14 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sched.h>
 #include <zlib.h>
 
 #include <algorithm>
 #include <limits>
+#include <functional>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/dmx.h"
@@ -137,61 +140,38 @@ int32_t conv_int(const char* p, const char* q) {
 
 }  // namespace
 
-extern "C" {
+namespace {
 
-int dmx_vcf_read(const char* path, int32_t field, dmx_vcf** out) {
-  if (!path || !out || field < DMX_FIELD_GT || field > DMX_FIELD_PL) return DMX_E_INVALID;
-  *out = nullptr;
-  std::string text;
-  if (!slurp(path, &text)) {
-    g_vcf_error = std::string("cannot read ") + path;
-    return DMX_E_IO;
-  }
-  dmx_vcf* v = new dmx_vcf();
-  v->field = field;
+struct Line { const char *p, *e; int64_t no; };
+
+// records of one contiguous range of lines (one host thread each); rids are local to the part until the merge
+struct Part {
+  dmx_vcf v;
+  std::string error;
+  int64_t err_line = 0;
+};
+
+void parse_range(const std::vector<Line>& lines, size_t lo, size_t hi, int32_t field, size_t nv, Part* part) {
+  dmx_vcf* v = &part->v;
   const char* want = field == DMX_FIELD_GP ? "GP" : (field == DMX_FIELD_PL ? "PL" : nullptr);
   std::vector<Tok> cols, keys, alts;
-  const char *p = text.data(), *end = text.data() + text.size();
-  bool have_header = false;
-  int64_t lineno = 0;
-  auto fail = [&](const std::string& why) {
-    g_vcf_error = std::string(path) + ": line " + std::to_string(lineno) + ": " + why;
-    delete v;
-    return DMX_E_INVALID;
-  };
-  while (p < end) {
-    const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
-    const char* e = nl ? nl : end;
-    const char* next = nl ? nl + 1 : end;
-    if (e > p && e[-1] == '\r') --e;
-    ++lineno;
-    if (e == p) { p = next; continue; }
-    if (*p == '#') {
-      if (e - p > 6 && memcmp(p, "#CHROM", 6) == 0) {
-        split(p, e, '\t', &cols);
-        if (cols.size() < 10) return fail("no sample columns");
-        for (size_t i = 9; i < cols.size(); ++i) v->samples.emplace_back(cols[i].p, cols[i].n);
-        have_header = true;
-      }
-      p = next;
-      continue;
-    }
-    if (!have_header) return fail("record before the #CHROM line");
+  auto fail = [&](int64_t no, const std::string& why) { part->error = why; part->err_line = no; };
+  for (size_t li = lo; li < hi; ++li) {
+    const char *p = lines[li].p, *e = lines[li].e;
     split(p, e, '\t', &cols);
-    const size_t nv = v->samples.size();
-    if (cols.size() != 9 + nv) return fail("wrong number of columns");
+    if (cols.size() != 9 + nv) return fail(lines[li].no, "wrong number of columns");
     // n_allele = 1 + number of ALT alleles ("." = none)
     split(cols[4].p, cols[4].p + cols[4].n, ',', &alts);
     const bool no_alt = cols[4].n == 1 && cols[4].p[0] == '.';
-    if (no_alt || alts.size() != 1) { ++v->n_skipped; p = next; continue; }
+    if (no_alt || alts.size() != 1) { ++v->n_skipped; continue; }
     split(cols[8].p, cols[8].p + cols[8].n, ':', &keys);
     int i_gt = -1, i_f = -1;
     for (size_t k = 0; k < keys.size(); ++k) {
       if (keys[k].n == 2 && memcmp(keys[k].p, "GT", 2) == 0) i_gt = (int)k;
       if (want && keys[k].n == 2 && memcmp(keys[k].p, want, 2) == 0) i_f = (int)k;
     }
-    if (i_gt < 0) return fail("no GT in FORMAT (demuxlet's record filter needs it)");
-    if (want && i_f < 0) return fail(std::string("no ") + want + " in FORMAT");
+    if (i_gt < 0) return fail(lines[li].no, "no GT in FORMAT (demuxlet's record filter needs it)");
+    if (want && i_f < 0) return fail(lines[li].no, std::string("no ") + want + " in FORMAT");
     const std::string chrom(cols[0].p, cols[0].n);
     if (v->chroms.empty() || v->chroms.back() != chrom) {
       size_t r = 0;
@@ -217,11 +197,90 @@ int dmx_vcf_read(const char* path, int32_t field, dmx_vcf** out) {
       if (field == DMX_FIELD_PL)
         parse_vec3<int32_t>(subfield(col, i_f), &v->pl[f0 + s * 3], std::numeric_limits<int32_t>::min(), conv_int);
     }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int dmx_vcf_read(const char* path, int32_t field, dmx_vcf** out) {
+  if (!path || !out || field < DMX_FIELD_GT || field > DMX_FIELD_PL) return DMX_E_INVALID;
+  *out = nullptr;
+  std::string text;
+  if (!slurp(path, &text)) {
+    g_vcf_error = std::string("cannot read ") + path;
+    return DMX_E_IO;
+  }
+  dmx_vcf* v = new dmx_vcf();
+  v->field = field;
+  auto fail = [&](int64_t lineno, const std::string& why) {
+    g_vcf_error = std::string(path) + ": line " + std::to_string(lineno) + ": " + why;
+    delete v;
+    return DMX_E_INVALID;
+  };
+  // pass 1 (one thread): header, line index
+  std::vector<Line> lines;
+  std::vector<Tok> cols;
+  const char *p = text.data(), *end = text.data() + text.size();
+  bool have_header = false;
+  int64_t lineno = 0;
+  while (p < end) {
+    const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+    const char* e = nl ? nl : end;
+    const char* next = nl ? nl + 1 : end;
+    if (e > p && e[-1] == '\r') --e;
+    ++lineno;
+    if (e > p) {
+      if (*p == '#') {
+        if (e - p > 6 && memcmp(p, "#CHROM", 6) == 0) {
+          split(p, e, '\t', &cols);
+          if (cols.size() < 10) return fail(lineno, "no sample columns");
+          for (size_t i = 9; i < cols.size(); ++i) v->samples.emplace_back(cols[i].p, cols[i].n);
+          have_header = true;
+        }
+      } else {
+        if (!have_header) return fail(lineno, "record before the #CHROM line");
+        lines.push_back(Line{p, e, lineno});
+      }
+    }
     p = next;
   }
-  if (!have_header) {
-    lineno = 0;
-    return fail("no #CHROM line");
+  if (!have_header) return fail(0, "no #CHROM line");
+  // pass 2: the records, contiguous line ranges on the host threads, merged in file order
+  const size_t nv = v->samples.size();
+  cpu_set_t cpus;                                   // the CPUs this process may run on (not the machine's)
+  size_t ncpu = std::thread::hardware_concurrency();
+  if (sched_getaffinity(0, sizeof(cpus), &cpus) == 0) ncpu = (size_t)CPU_COUNT(&cpus);
+  size_t nth = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(ncpu, 16), lines.size() / 256 + 1));
+  if (const char* env = getenv("DMX_VCF_THREADS")) nth = std::max<size_t>(1, std::min<size_t>((size_t)atoi(env), 256));
+  std::vector<Part> parts(nth);
+  std::vector<std::thread> th;
+  for (size_t t = 0; t < nth; ++t) {
+    const size_t lo = lines.size() * t / nth, hi = lines.size() * (t + 1) / nth;
+    if (t + 1 < nth) th.emplace_back(parse_range, std::cref(lines), lo, hi, field, nv, &parts[t]);
+    else parse_range(lines, lo, hi, field, nv, &parts[t]);
+  }
+  for (auto& x : th) x.join();
+  for (const Part& pt : parts)
+    if (!pt.error.empty()) return fail(pt.err_line, pt.error);   // the first failing range = the first failing line
+  for (Part& pt : parts) {
+    std::vector<int32_t> remap(pt.v.chroms.size());
+    for (size_t c = 0; c < pt.v.chroms.size(); ++c) {
+      size_t r = 0;
+      for (; r < v->chroms.size(); ++r)
+        if (v->chroms[r] == pt.v.chroms[c]) break;
+      if (r == v->chroms.size()) v->chroms.push_back(pt.v.chroms[c]);
+      remap[c] = (int32_t)r;
+    }
+    for (int32_t r : pt.v.rid) v->rid.push_back(remap[(size_t)r]);
+    v->pos.insert(v->pos.end(), pt.v.pos.begin(), pt.v.pos.end());
+    v->ref.insert(v->ref.end(), pt.v.ref.begin(), pt.v.ref.end());
+    v->alt.insert(v->alt.end(), pt.v.alt.begin(), pt.v.alt.end());
+    v->gt.insert(v->gt.end(), pt.v.gt.begin(), pt.v.gt.end());
+    v->gp.insert(v->gp.end(), pt.v.gp.begin(), pt.v.gp.end());
+    v->pl.insert(v->pl.end(), pt.v.pl.begin(), pt.v.pl.end());
+    v->n_skipped += pt.v.n_skipped;
   }
   *out = v;
   return DMX_OK;

@@ -1,0 +1,55 @@
+"""dmx_vcf_read and dmx_sweep_bam (host only): throughput on generated files -- a VCF of NREC biallelic
+records x 64 samples with GT:GP, a coordinate-sorted BAM of NREADS 90-base reads with CB / UB tags over those records.
+usage: python tools/io_bench.py [NREC=20000] [NREADS=300000]     prints one JSON line (no GPU needed)"""
+import json
+import os
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from demuxlet_b200 import api                   # noqa: E402
+from tests import bamio                         # noqa: E402
+
+nrec = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
+nreads = int(sys.argv[2]) if len(sys.argv) > 2 else 300000
+rng = np.random.default_rng(3)
+nv = 64
+td = tempfile.mkdtemp()
+vcf = os.path.join(td, "a.vcf.gz")
+pos = np.sort(rng.choice(np.arange(1000, 50_000_000), nrec, replace=False))
+g = rng.integers(0, 3, size=(nrec, nv))
+gp = np.eye(3)[g] * 0.97 + 0.01
+import gzip                                     # noqa: E402
+with gzip.open(vcf, "wt", compresslevel=1) as f:
+    f.write("##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join("S%d" % i for i in range(nv)) + "\n")
+    gts = np.array(["0/0", "0/1", "1/1"])
+    for r in range(nrec):
+        cols = [gts[g[r, s]] + ":%.3f,%.3f,%.3f" % tuple(gp[r, s]) for s in range(nv)]
+        f.write("chr1\t%d\t.\tA\tG\t.\tPASS\t.\tGT:GP\t" % pos[r] + "\t".join(cols) + "\n")
+t0 = time.perf_counter()
+v = api.read_vcf(vcf, "GP")
+t_vcf = time.perf_counter() - t0
+text_bytes = sum(len(l) for l in gzip.open(vcf, "rb"))
+starts = np.sort(np.clip(pos[rng.integers(0, nrec, nreads)] - 1 - rng.integers(0, 90, nreads), 0, None))
+cells = ["".join(rng.choice(list("ACGT"), 16)) + "-1" for _ in range(2000)]
+seqs = rng.choice(list("ACGT"), size=(nreads, 90))
+reads = [{"tid": 0, "pos": int(starts[i]), "mapq": 60, "flag": 0, "cigar": [("M", 90)], "seq": "".join(seqs[i]),
+          "qual": [37] * 90, "tags": [("CB", "Z", cells[i % 2000]), ("UB", "Z", "".join(seqs[i][:10]))]} for i in range(nreads)]
+bam = os.path.join(td, "a.bam")
+bamio.write_bam(bam, [("chr1", 60_000_000)], reads, member=60000)
+t0 = time.perf_counter()
+s = api.sweep_bam(bam, v["chroms"], v["rid"], v["pos"], v["ref"], v["alt"])
+t_bam = time.perf_counter() - t0
+t0 = time.perf_counter()
+packed = api.pack_reads(s["cell"], s["snp"], s["umis"], s["allele"], s["bq"], len(s["barcodes"]))
+t_pack = time.perf_counter() - t0
+print(json.dumps({"vcf": {"records": nrec, "samples": nv, "text_mb": round(text_bytes / 1e6, 1), "seconds": round(t_vcf, 3),
+                          "records_per_s": round(nrec / t_vcf), "text_mb_per_s": round(text_bytes / 1e6 / t_vcf, 1)},
+                  "bam": {"reads": nreads, "file_mb": round(os.path.getsize(bam) / 1e6, 1), "seconds": round(t_bam, 3),
+                          "reads_per_s": round(nreads / t_bam), "observations": int(len(s["cell"]))},
+                  "pack": {"seconds_incl_python_umi_encoding": round(t_pack, 3), "entries": int(len(packed["ent_snp"]))},
+                  "threads": 1, "host": "build container"}))
