@@ -52,4 +52,4 @@ print(json.dumps({"vcf": {"records": nrec, "samples": nv, "text_mb": round(text_
                   "bam": {"reads": nreads, "file_mb": round(os.path.getsize(bam) / 1e6, 1), "seconds": round(t_bam, 3),
                           "reads_per_s": round(nreads / t_bam), "observations": int(len(s["cell"]))},
                   "pack": {"seconds_incl_python_umi_encoding": round(t_pack, 3), "entries": int(len(packed["ent_snp"]))},
-                  "threads": 1, "host": "build container"}))
+                  "vcf_threads": len(os.sched_getaffinity(0)), "bam_threads": 1, "host": "build container"}))
