@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "dmx_last_error", "dmx_abi_version", "dmx_pack_reads", "dmx_pileup_sizes", "dmx_pileup_copy", "dmx_pileup_free",
     "dmx_build_gp", "dmx_build_gp_device", "dmx_set_field", "dmx_site_filter",
     "dmx_sweep_opts_default", "dmx_sweep_bam", "dmx_sweep_sizes", "dmx_sweep_counts", "dmx_sweep_copy", "dmx_sweep_barcode",
-    "dmx_sweep_free", "dmx_sweep_last_error", "dmx_vcf_read", "dmx_vcf_sizes", "dmx_vcf_sample", "dmx_vcf_chrom", "dmx_vcf_copy", "dmx_vcf_free", "dmx_vcf_last_error",
+    "dmx_sweep_free", "dmx_sweep_last_error", "dmx_vcf_read", "dmx_vcf_select", "dmx_vcf_sizes", "dmx_vcf_sample", "dmx_vcf_chrom", "dmx_vcf_copy", "dmx_vcf_free", "dmx_vcf_last_error",
 ]
 
 DMX_FIELD = {"GT": 0, "GP": 1, "PL": 2}            # --field (cmd_cram_demuxlet.cpp:28, :45)
@@ -199,7 +199,7 @@ def site_filter(gt, min_mac: int = 1, min_callrate: float = 0.5, device: int = 0
     return out.astype(bool)
 
 
-def read_vcf(path: str, field: str = "GT") -> dict:
+def read_vcf(path: str, field: str = "GT", samples: Optional[Sequence[str]] = None) -> dict:
     """dmx_vcf_read: the biallelic records of a VCF (plain / gzip / bgzip) as the flat arrays site_filter / build_gp
     take.  Returns samples, chroms, rid, pos (0-based), ref, alt, gt int8[nrec][nv][2], values (GT: gt; GP float32;
     PL int32 [nrec][nv][3]), n_skipped."""
@@ -221,6 +221,12 @@ def read_vcf(path: str, field: str = "GT") -> dict:
     if rc != 0:
         raise DmxError(rc, "dmx_vcf_read", lib.dmx_vcf_last_error().decode())
     try:
+        if samples:      # --sm / --sm-list
+            lib.dmx_vcf_select.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p)]
+            arr = (C.c_char_p * len(samples))(*[x.encode() for x in samples])
+            rc = lib.dmx_vcf_select(h, len(samples), arr)
+            if rc != 0:
+                raise DmxError(rc, "dmx_vcf_select", lib.dmx_vcf_last_error().decode())
         nv, nrec, nskip, nchrom = C.c_int32(), C.c_int64(), C.c_int64(), C.c_int32()
         lib.dmx_vcf_sizes(h, C.byref(nv), C.byref(nrec), C.byref(nskip), C.byref(nchrom))
         nv, nrec = nv.value, nrec.value

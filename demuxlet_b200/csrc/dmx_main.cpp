@@ -154,7 +154,7 @@ void usage() {
           "                      pass the genotype-count filter must be the SNPs of the pileup, in order\n"
           "  --sam FILE --vcf FILE   instead of --plp: pile the reads of a coordinate-sorted BAM up on the VCF's records\n"
           "                      [--tag-group CB] [--tag-UMI UB] [--min-MQ 20] [--excl-flag 0x0f04] [--min-BQ 13] [--cap-BQ 40]\n"
-          "                      [--min-TD 0]; own BGZF / BAM / VCF-text readers (no htslib; no CRAM / BCF / --sm)\n");
+          "                      [--min-TD 0] [--sm ID]... [--sm-list FILE]; own BGZF / BAM / VCF-text readers (no htslib; no CRAM / BCF)\n");
 }
 }  // namespace
 
@@ -163,6 +163,8 @@ int main(int argc, char** argv) {
              *vcf_path = nullptr, *sam_path = nullptr;
   dmx_sweep_opts so;
   dmx_sweep_opts_default(&so);
+  std::vector<std::string> sm_ids;
+  const char* sm_list = nullptr;
   double geno_error = -1, min_callrate = 0.5;     // :25
   int min_mac = 1;                                // :24
   std::vector<double> alpha;
@@ -201,13 +203,14 @@ int main(int argc, char** argv) {
     else if (a == "--min-MQ") so.min_mq = atoi(val());
     else if (a == "--min-TD") so.min_td = atoi(val());
     else if (a == "--excl-flag") so.exclude_flag = (uint32_t)strtoul(val(), nullptr, 0);
-    else if (a == "--sm" || a == "--sm-list")
-      die("Option %s: sample subsets are not part of this build (all samples of the VCF are used)", argv[i]);
+    else if (a == "--sm") sm_ids.push_back(val());                 // :50
+    else if (a == "--sm-list") sm_list = val();                    // :51
     else die("Unrecognized option %s", argv[i]);
   }
   if ((!plp_path && !sam_path) || !out) { usage(); die("--plp (or --sam with --vcf) and --out are required"); }
   if (plp_path && sam_path) die("--plp and --sam are two sources of the same pileup; give one");
   if (sam_path && !vcf_path) die("--sam needs --vcf (the SNPs the reads are piled up on)");
+  if ((sm_list || !sm_ids.empty()) && !vcf_path) die("--sm / --sm-list select samples of --vcf", "");
   if (alpha.empty()) { alpha.push_back(0.0); alpha.push_back(0.5); }   // :78-90
 
   if (field && !field_path && !vcf_path)
@@ -234,6 +237,21 @@ int main(int argc, char** argv) {
     if (ff.field < 0) die("--field %s: only GT, GP and PL are known", field);
     dmx_vcf* v = nullptr;
     if (dmx_vcf_read(vcf_path, ff.field, &v) != DMX_OK) die("Cannot read VCF: %s", dmx_vcf_last_error());
+    if (sm_list) {                                     // bcf_filtered_reader.cpp:95-101: first field of every line
+      FILE* sf = fopen(sm_list, "r");
+      if (!sf) die("Cannot open file %s for reading", sm_list);
+      char line[4096];
+      while (fgets(line, sizeof(line), sf)) {
+        const size_t n = strcspn(line, " \t\r\n");
+        if (n) sm_ids.emplace_back(line, n);
+      }
+      fclose(sf);
+    }
+    if (!sm_ids.empty()) {
+      std::vector<const char*> nm;
+      for (const std::string& x : sm_ids) nm.push_back(x.c_str());
+      if (dmx_vcf_select(v, (int32_t)nm.size(), nm.data()) != DMX_OK) die("%s", dmx_vcf_last_error());
+    }
     int32_t vnv = 0;
     int64_t nrec = 0, nskip = 0;
     dmx_vcf_sizes(v, &vnv, &nrec, &nskip, nullptr);

@@ -26,6 +26,7 @@
 #include <functional>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/dmx.h"
@@ -283,6 +284,41 @@ int dmx_vcf_read(const char* path, int32_t field, dmx_vcf** out) {
     v->n_skipped += pt.v.n_skipped;
   }
   *out = v;
+  return DMX_OK;
+}
+
+// --sm / --sm-list (bcf_filtered_reader.cpp:95-121): keep the named samples only.  The reference collects the ids in a
+// std::set<std::string>, so the kept columns come out in byte-lexicographic order of their names, duplicates merged;
+// an id that is not in the header is an error there (:107-108) and here.
+int dmx_vcf_select(dmx_vcf* v, int32_t n, const char* const* names) {
+  if (!v || n < 1 || !names) return DMX_E_INVALID;
+  std::vector<std::string> want(names, names + n);
+  std::sort(want.begin(), want.end());
+  want.erase(std::unique(want.begin(), want.end()), want.end());
+  std::vector<size_t> col;
+  for (const std::string& w : want) {
+    size_t c = 0;
+    for (; c < v->samples.size(); ++c)
+      if (v->samples[c] == w) break;
+    if (c == v->samples.size()) {
+      g_vcf_error = "Cannot find sample ID " + w + " from the VCF file";
+      return DMX_E_INVALID;
+    }
+    col.push_back(c);
+  }
+  const size_t nv0 = v->samples.size(), nv1 = col.size(), nrec = v->pos.size();
+  auto gather = [&](auto& vec, size_t per) {
+    if (vec.empty()) return;
+    typename std::remove_reference<decltype(vec)>::type out(nrec * nv1 * per);
+    for (size_t r = 0; r < nrec; ++r)
+      for (size_t k = 0; k < nv1; ++k)
+        for (size_t x = 0; x < per; ++x) out[(r * nv1 + k) * per + x] = vec[(r * nv0 + col[k]) * per + x];
+    vec.swap(out);
+  };
+  gather(v->gt, 2);
+  gather(v->gp, 3);
+  gather(v->pl, 3);
+  v->samples = want;
   return DMX_OK;
 }
 

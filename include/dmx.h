@@ -225,6 +225,9 @@ int dmx_site_filter(int32_t device, int32_t nv, int64_t nsnps, const int8_t* gt,
  * Missing values: GT -1, GP NaN, PL INT32_MIN.  All samples are selected. */
 typedef struct dmx_vcf dmx_vcf;
 int dmx_vcf_read(const char* path, int32_t field /* DMX_FIELD_*: which FORMAT key besides GT */, dmx_vcf** out);
+/* --sm / --sm-list (bcf_filtered_reader.cpp:95-121): keep only the named samples, in the byte-lexicographic order of
+ * their names (the reference's std::set), duplicates merged; DMX_E_INVALID if a name is not in the header */
+int dmx_vcf_select(dmx_vcf* v, int32_t n, const char* const* names);
 int dmx_vcf_sizes(const dmx_vcf* v, int32_t* nv, int64_t* nrec, int64_t* n_skipped, int32_t* n_chrom);
 const char* dmx_vcf_sample(const dmx_vcf* v, int32_t i);        /* sample id of column i (get_sample_id_at)       */
 const char* dmx_vcf_chrom(const dmx_vcf* v, int32_t rid);       /* chromosome name of rid (first-seen order)       */

@@ -134,7 +134,7 @@ def test_cli_option_handling_without_a_device():
     r = subprocess.run([exe, "--sam", "x.bam", "--out", "o"], capture_output=True, text=True)
     assert r.returncode == 1 and "--sam needs --vcf" in r.stderr
     r = subprocess.run([exe, "--plp", "x.dmxp", "--sm", "a", "--out", "o"], capture_output=True, text=True)
-    assert r.returncode == 1 and "sample subsets" in r.stderr
+    assert r.returncode == 1 and "--sm / --sm-list select samples of --vcf" in r.stderr
     r = subprocess.run([exe, "--plp", "x.dmxp", "--out", "o", "--field", "GT"], capture_output=True, text=True)
     assert r.returncode == 1 and "--field-matrix" in r.stderr
     r = subprocess.run([exe, "--bogus"], capture_output=True, text=True)

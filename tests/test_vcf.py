@@ -34,6 +34,23 @@ def test_reader_matches_restatement(field, ext, bg, tmp_path):
     assert got["n_skipped"] > 0 and len(got["pos"]) > 300 and len(got["chroms"]) == 3
 
 
+def test_sample_subset(tmp_path):
+    """--sm / --sm-list: columns of the named samples in the byte order of their names (the reference's std::set)"""
+    rng = np.random.default_rng(10)
+    samples = ["zeta", "Alpha", "mid", "beta", "S1", "s1"]
+    path = str(tmp_path / "a.vcf")
+    vcfio.write_vcf(path, samples, vcfio.random_records(rng, 120, len(samples), "PL"))
+    full = api.read_vcf(path, "PL")
+    pick = ["mid", "zeta", "Alpha", "mid", "S1"]
+    got = api.read_vcf(path, "PL", samples=pick)
+    order = sorted(set(pick))                       # byte order: "Alpha" < "S1" < "mid" < "zeta"
+    assert got["samples"] == order == ["Alpha", "S1", "mid", "zeta"]
+    cols = [samples.index(x) for x in order]
+    assert np.array_equal(got["gt"], full["gt"][:, cols]) and np.array_equal(got["values"], full["values"][:, cols])
+    with pytest.raises(api.DmxError, match="Cannot find sample ID nobody"):
+        api.read_vcf(path, "PL", samples=["mid", "nobody"])
+
+
 def test_reader_errors(tmp_path):
     with pytest.raises(api.DmxError):
         api.read_vcf(str(tmp_path / "missing.vcf"))
@@ -106,3 +123,35 @@ def test_cli_vcf(field, tmp_path):
     bad = subprocess.run([exe, "--plp", str(tmp_path / "b.dmxp"), "--out", str(tmp_path / "c"), "--vcf", path, "--field", field],
                          capture_output=True, text=True)          # default filter keeps another number of records
     assert bad.returncode == 1 and "not the SNPs of the pileup" in bad.stderr
+
+
+@pytest.mark.gpu
+def test_cli_vcf_sample_subset(tmp_path):
+    """--sm / --sm-list on the command line: the kept samples (name order) are the samples of the whole run"""
+    import dataclasses
+    import filecmp
+    import os
+    import subprocess
+    from demuxlet_b200 import synth
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "demuxlet_b200", "dmx-demuxlet")
+    rng = np.random.default_rng(19)
+    samples = ["d5", "d1", "d4", "d2", "d3", "d0"]
+    path = str(tmp_path / "a.vcf")
+    vcfio.write_vcf(path, samples, vcfio.random_records(rng, 700, len(samples), "PL"))
+    v = vcfio.parse_vcf(path, "PL")
+    pick = ["d4", "d0", "d2", "d5"]
+    order = sorted(pick)
+    cols = [samples.index(x) for x in order]
+    gt, vals = np.ascontiguousarray(v["gt"][:, cols]), np.ascontiguousarray(v["values"][:, cols])
+    keep = po.site_filter(gt, 1, 0.5)
+    gp = po.build_gp("PL", np.ascontiguousarray(vals[keep]), 0.01)
+    p = synth.make_synth(20, len(order), int(keep.sum()), "GP", seed=6)
+    dataclasses.replace(p, gp=gp, samples=order).save(str(tmp_path / "a.dmxp"))
+    dataclasses.replace(p, gp=np.zeros_like(gp)).save(str(tmp_path / "b.dmxp"))
+    (tmp_path / "sm.txt").write_text("d4\textra\nd0\n")
+    ra = subprocess.run([exe, "--plp", str(tmp_path / "a.dmxp"), "--out", str(tmp_path / "a")], capture_output=True, text=True)
+    rb = subprocess.run([exe, "--plp", str(tmp_path / "b.dmxp"), "--out", str(tmp_path / "b"), "--vcf", path, "--field", "PL", "--sm", "d2",
+                         "--sm", "d5", "--sm-list", str(tmp_path / "sm.txt")], capture_output=True, text=True)
+    assert ra.returncode == 0 and rb.returncode == 0, ra.stderr + rb.stderr
+    for ext in ("best", "single", "sing2"):
+        assert filecmp.cmp(str(tmp_path / ("a." + ext)), str(tmp_path / ("b." + ext)), shallow=False), ext
