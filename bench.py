@@ -142,8 +142,11 @@ def cpu_baseline(plp, alphas, budget_s: float = 15.0):
     t_probe = orc.time_cells(probe, nthreads=ncores)
     per_cell = t_probe / len(probe)
     n = int(max(len(probe), min(plp.ncells, budget_s / max(per_cell, 1e-9))))
-    cells = rng.choice(plp.ncells, size=n, replace=False)
-    t = orc.time_cells(cells, nthreads=ncores)
+    if t_probe >= 0.5 * budget_s or n == len(probe):     # expensive barcodes (C5's shape): the probe is the sample
+        n, cells, t = len(probe), probe, t_probe
+    else:
+        cells = rng.choice(plp.ncells, size=n, replace=False)
+        t = orc.time_cells(cells, nthreads=ncores)
     return {"value": n / t, "unit": UNIT, "cores": ncores, "kind": "port",
             "sample": "%d random cells of the workload (%d entries), OpenMP over cells, %.1f s" %
                       (n, int(np.diff(plp.cell_ptr)[cells].sum()), t)}
@@ -161,6 +164,16 @@ def run_reference(args):
     ncores = os.cpu_count() or 1
     use_ref = po.ref_available()
     cells_per_proc = 4 if plp.nv >= 32 else 64
+    # the reference indexes its gpAB table with int32 products (:542, :553, :677): a sample it can run at all
+    # must keep (SNPs of the sample) * nv^2 * 9 below 2^31
+    mean_ent = float(np.diff(plp.cell_ptr).mean())
+    while cells_per_proc > 1 and cells_per_proc * mean_ent * plp.nv * plp.nv * 9 >= 2 ** 31:
+        cells_per_proc //= 2
+    why_port = ""
+    if use_ref and mean_ent * plp.nv * plp.nv * 9 >= 2 ** 31:
+        use_ref = False
+        why_port = ("; the unmodified reference cannot run one barcode of this shape (int32 table index overflow at "
+                    "nsnps*nv^2*9 >= 2^31, cmd_cram_demuxlet.cpp:542)")
     # memory guard: the reference materialises nsnps*nv^2*9 doubles per process (:542)
     try:
         avail = int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) * 1024
@@ -204,7 +217,7 @@ def run_reference(args):
             cells = rng.choice(plp.ncells, size=min(plp.ncells, ncores * cells_per_proc), replace=False)
             t = orc.time_cells(cells, nthreads=ncores)
             v = len(cells) / t
-            sample_desc = "%d random cells per step, oracle port with OpenMP over cells" % len(cells)
+            sample_desc = "%d random cells per step, oracle port with OpenMP over cells%s" % (len(cells), why_port)
         if step >= args.warmup:
             vals.append(v)
             walls.append(time.perf_counter() - t_wall0)
@@ -232,10 +245,125 @@ def workload_name(args):
 
 
 # -------------------------------------------------------------------------------------------------
+def hyps_per_cell(nv, alphas):
+    h = 0
+    for n, a in enumerate(alphas):
+        if n == 0 and a == 0.0:
+            continue
+        h += nv * (nv + 1) // 2 if a == 0.5 else nv * nv
+    return h
+
+
+class Case:
+    """one pileup on this rank's GPU, timed both ways (inputs resident in HBM; host buffers through dmx_run), with
+    the record exchange of the N > 1 path inside both timed regions"""
+
+    def __init__(self, args, plp, alphas, counts, world, rank, local_rank):
+        import torch
+        import torch.distributed as dist
+        from demuxlet_b200 import api
+        from demuxlet_b200.parallel import RecordExchange
+        self.torch, self.dist, self.api = torch, dist, api
+        self.args, self.plp, self.alphas, self.world, self.rank = args, plp, alphas, world, rank
+
+        def pin(a):   # pinned host copies: what a caller that wants full PCIe speed hands to the C ABI
+            out = api.pinned_empty(a.shape, a.dtype)
+            out[...] = a
+            return out
+        self.gp = pin(plp.gp)
+        self.arrays = [pin(x) for x in (plp.cell_ptr, plp.ent_snp, plp.ent_ptr, plp.reads, plp.totl, plp.npass, plp.uniq)]
+        self.fp32 = not args.fp64_pairs
+        # the ranks of one box share its host cores: each finaliser pool gets its share
+        self.host_threads = max(1, (os.cpu_count() or 1) // max(1, world))
+        self.d = api.Demuxlet(plp.nv, alphas, device=local_rank, borrow=True, trust_inputs=True, fp32_pairs=self.fp32,
+                              host_threads=self.host_threads)
+        self.d.set_gp(self.gp)
+        self.d.set_pileup_arrays(*self.arrays)
+        self.ex = RecordExchange(counts, api.BEST_DTYPE.itemsize) if world > 1 else None
+        self.total_cells = int(sum(counts))
+        self.gathered = None
+        self.pair_bytes = 0
+        self.pair_buf = None
+        if args.write_pair:   # --write-pair: the dense llksAB block of every barcode comes back too (:772-797)
+            per = plp.nv * plp.nv * len(alphas)
+            self.pair_slab = max(1, min(plp.ncells, (256 << 20) // (per * 8)))
+            self.pair_buf = np.zeros((self.pair_slab, plp.nv, plp.nv, len(alphas)))
+            self.pair_bytes = plp.ncells * per * 8
+
+    def exchange(self):
+        if self.ex is not None:
+            self.gathered = self.ex(self.d.best())
+
+    def pairs(self):
+        if self.pair_buf is None:
+            return
+        n = self.plp.ncells
+        for lo in range(0, n, self.pair_slab):
+            hi = min(n, lo + self.pair_slab)
+            self.d._chk(self.d.lib.dmx_get_pair(self.d._h, lo, hi, self.pair_buf.ctypes.data), "dmx_get_pair")
+
+    def sync(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps):
+        self.sync()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        self.sync()
+        dt = time.perf_counter() - t0
+        if self.world > 1:
+            t = self.torch.tensor([dt], dtype=self.torch.float64, device="cuda")
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt
+
+    def step_resident(self):
+        self.d.compute()
+        self.pairs()
+        self.exchange()
+
+    def step_e2e(self):
+        d = self.d
+        d._chk(d.lib.dmx_set_gp(d._h, self.gp.ctypes.data, self.gp.shape[0]), "dmx_set_gp")   # marks inputs dirty:
+        d.set_pileup_arrays(*self.arrays)                                                     # every step re-uploads
+        d.run()
+        self.pairs()
+        self.exchange()
+
+    def run(self, sampler=None):
+        args, d = self.args, self.d
+        d.upload()
+        for _ in range(args.warmup):
+            self.step_resident()
+        if sampler is not None:
+            sampler.start()
+        rec = {"kern": [], "pair": [], "fin": [], "prep": []}
+
+        def step_rec():
+            self.step_resident()
+            st = d.stats()
+            rec["kern"].append(st["kernel_ms"]); rec["pair"].append(st["pair_kernel_ms"])
+            rec["fin"].append(st["finalise_ms"]); rec["prep"].append(st["prep_ms"])
+        dt = self.timed(step_rec, args.steps)
+        clocks = sampler.stop() if sampler is not None else None
+        st = d.stats()
+        for _ in range(max(1, args.warmup // 2)):
+            self.step_e2e()
+        dt2 = self.timed(self.step_e2e, args.steps)
+        st2 = d.stats()
+        if self.ex is not None and self.rank == 0:
+            assert self.gathered is not None and self.gathered.shape[0] == self.total_cells
+        return {"dt": dt, "dt2": dt2, "st": st, "st2": st2, "rec": rec, "clocks": clocks}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from demuxlet_b200 import api
+    from demuxlet_b200.parallel import shard_pileup, shard_ranges
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -246,138 +374,116 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    # ---- weak scaling (the line's value): every rank owns one whole workload of the named shape ---------------------
     plp, alphas = make_workload(args.workload, rank, args.scale)
     ncells = plp.ncells
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    weak = None
+    if args.scaling in ("weak", "both") or world == 1:
+        case = Case(args, plp, alphas, [ncells] * world, world, rank, local_rank)
+        weak = case.run(sampler)
+        weak["pair_bytes"], weak["host_threads"] = case.pair_bytes, case.host_threads
+        case.d.close()
+        del case
 
-    # pinned host copies of the inputs: what a caller that wants full PCIe speed hands to the C ABI
-    def pin(a):
-        out = api.pinned_empty(a.shape, a.dtype)
-        out[...] = a
-        return out
-    gp = pin(plp.gp)
-    arrays = [pin(x) for x in (plp.cell_ptr, plp.ent_snp, plp.ent_ptr, plp.reads, plp.totl, plp.npass, plp.uniq)]
-
-    fp32 = not args.fp64_pairs
-    # the ranks of one box share its host cores: each finaliser pool gets its share
-    host_threads = max(1, (os.cpu_count() or 1) // max(1, world))
-    d = api.Demuxlet(plp.nv, alphas, device=local_rank, borrow=True, trust_inputs=True, fp32_pairs=fp32,
-                     host_threads=host_threads)
-    d.set_gp(gp)
-    d.set_pileup_arrays(*arrays)
-
-    rec_bytes = api.BEST_DTYPE.itemsize
-    gather_in = torch.empty(ncells * rec_bytes, dtype=torch.uint8, device="cuda")
-    gather_out = torch.empty(world * ncells * rec_bytes, dtype=torch.uint8, device="cuda") if world > 1 else None
-    host_rec = torch.empty(ncells * rec_bytes, dtype=torch.uint8).pin_memory()
-
-    def exchange():
-        """the one collective of the path: all-gather of the per-barcode best records"""
-        if world == 1:
-            return
-        host_rec.numpy()[:] = d.best().view(np.uint8)
-        gather_in.copy_(host_rec, non_blocking=True)
-        dist.all_gather_into_tensor(gather_out, gather_in)
-
-    def sync():
-        torch.cuda.synchronize()
+    # ---- strong scaling: ONE workload (rank 0's), its barcodes split over the ranks in contiguous ranges balanced by
+    # pileup entries (the reference's --group-list model, cmd_cram_demuxlet.cpp:68), one all-gather of the records -----
+    strong = None
+    if world > 1 and args.scaling in ("strong", "both"):
+        if rank == 0:
+            full = plp
         if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        sync()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            fn()
-        sync()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        return dt
-
-    def step_resident():
-        d.compute()
-        exchange()
-
-    def step_e2e():
-        d._chk(d.lib.dmx_set_gp(d._h, gp.ctypes.data, gp.shape[0]), "dmx_set_gp")   # marks inputs dirty:
-        d.set_pileup_arrays(*arrays)                                                 # every step re-uploads
-        d.run()
-        exchange()
-
-    # ---- value: inputs resident in HBM ---------------------------------------------------------------
-    d.upload()
-    for _ in range(args.warmup):
-        step_resident()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    kern_ms, pair_ms, fin_ms, prep_ms = [], [], [], []
-
-    def step_resident_rec():
-        step_resident()
-        st = d.stats()
-        kern_ms.append(st["kernel_ms"]); pair_ms.append(st["pair_kernel_ms"]); fin_ms.append(st["finalise_ms"])
-        prep_ms.append(st["prep_ms"])
-    dt = timed(step_resident_rec, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
-    st = d.stats()
-    value = world * ncells * args.steps / dt
-    ms_per_step = dt / args.steps * 1e3
-
-    # ---- e2e: host buffers through the C ABI ------------------------------------------------------------
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
-    dt2 = timed(step_e2e, args.steps)
-    st2 = d.stats()
-    e2e_value = world * ncells * args.steps / dt2
+            dist.barrier()                      # rank 0's workload file is in the cache now
+        if rank != 0:
+            full, _ = make_workload(args.workload, 0, args.scale)
+        ranges = shard_ranges(full.cell_ptr, world)
+        counts = [hi - lo for lo, hi in ranges]
+        sub, _ = shard_pileup(full, rank, world)
+        case = Case(args, sub, alphas, counts, world, rank, local_rank)
+        strong = case.run(sampler if weak is None else None)
+        strong["counts"], strong["total"] = counts, full.ncells
+        strong["entries"] = [int(full.cell_ptr[hi] - full.cell_ptr[lo]) for lo, hi in ranges]
+        strong["pair_bytes"], strong["host_threads"] = case.pair_bytes * world, case.host_threads
+        case.d.close()
+        del case
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
+    fp32 = not args.fp64_pairs
+    main, scaling = (weak, "weak") if weak is not None else (strong, "strong")
+    total_cells = world * ncells if scaling == "weak" else strong["total"]
+    st, st2 = main["st"], main["st2"]
+    value = total_cells * args.steps / main["dt"]
+    e2e_value = total_cells * args.steps / main["dt2"]
     peak, peak_src = load_peaks()
-    pair_s = float(np.mean(pair_ms)) * 1e-3
+    pair_s = float(np.mean(main["rec"]["pair"])) * 1e-3
     achieved = st["algo_bytes"] / pair_s / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "pair_scan_traffic.json")
-    if os.path.exists(tpath):
+    kernel = "pair_scan_f32_kernel" if fp32 else "pair_scan_kernel"
+    traffic = None   # DRAM bytes of one launch of this kernel on this workload, from the committed ncu capture
+    tpath = os.path.join(ROOT, "profiles", "traffic_%s_%s.json" % (kernel, args.workload))
+    if os.path.exists(tpath) and args.scale == 1.0 and scaling == "weak":
         try:
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    hyp = hyps_per_cell(plp.nv, alphas)
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC if args.workload == "C3" else "cells/sec (%s) at 1/2/4/8 B200 vs CPU ref" % args.workload,
+        "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": main["dt"] / args.steps * 1e3, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "f32 pair products + f64 logs / exact re-score" if fp32 else "f64", "data": "synthetic (synth-v1, SURVEY 8d)",
         "timing": "host wall clock between device synchronisations (a step ends with the host-side tie finaliser), max "
                   "over ranks; kernel times below from CUDA events on the library's own stream",
         "config": {"workload": workload_name(args), "alpha": list(map(float, alphas)),
-                   "cells_per_gpu": ncells, "entries_per_gpu": int(plp.n_entries), "parallelism": "barcode shards x%d" % world,
+                   "cells_per_gpu": ncells if scaling == "weak" else strong["counts"],
+                   "cells_total": total_cells, "entries_per_gpu": int(plp.n_entries) if scaling == "weak" else strong["entries"],
+                   "hypotheses_per_cell": hyp,
+                   "parallelism": ("every rank one whole workload of this shape (x%d)" % world) if scaling == "weak" else
+                                  "one workload, barcode ranges balanced by entries over %d ranks" % world,
+                   "exchange": "none" if world == 1 else "one NCCL all-gather of the per-barcode records per step",
                    "l2": "no flush: inputs larger than L2 (%.2f GB of CSR + entry tables streamed per step)" %
                          ((plp.n_entries * (8 * 8 * 2 + 4 + 8) + plp.n_reads * 2) / 1e9),
-                   "exact_ties": True},
+                   "write_pair": bool(args.write_pair), "exact_ties": True},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(st2["h2d_bytes"]) * world,
-                "d2h_bytes_per_step": int(st2["d2h_bytes"]) * world, "ms_per_step": dt2 / args.steps * 1e3,
+                "d2h_bytes_per_step": (int(st2["d2h_bytes"]) + main["pair_bytes"]) * world,
+                "ms_per_step": main["dt2"] / args.steps * 1e3,
                 "h2d_ms": st2["h2d_ms"], "kernel_ms": st2["kernel_ms"], "finalise_ms": st2["finalise_ms"],
                 "run_ms": st2["total_ms"]},
         "gpu_launches": int(st["gpu_launches"]) * args.steps,
-        "roofline": {"bound": "hbm", "kernel": "pair_scan_f32_kernel" if fp32 else "pair_scan_kernel",
+        "roofline": {"bound": "hbm", "kernel": kernel,
                      "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algo_bytes_per_launch": st["algo_bytes"], "kernel_ms": pair_s * 1e3,
-                     "note": "gather-model bytes (SURVEY 8d) / CUDA-event time; at nv=64 the kernel is bound by the SM's "
-                             "%s issue rate, not by HBM: the 77 MB GP matrix is L2 resident, DRAM traffic << gather-model "
-                             "bytes (DESIGN.md 6)" % ("FP32" if fp32 else "FP64")},
-        "roofline_fp": fp_roofline(plp, alphas, pair_s, fp32, clocks),
-        "breakdown_ms": {"prep": float(np.mean(prep_ms)), "pair_scan": float(np.mean(pair_ms)),
-                         "all_kernels": float(np.mean(kern_ms)), "d2h": st["d2h_ms"], "finalise_host": float(np.mean(fin_ms)),
-                         "rescored_hypotheses": int(st["n_rescored"]), "host_threads": host_threads},
-        "clocks": clocks,
+                     "note": "gather-model bytes (SURVEY 8d) / CUDA-event time of the scan launches of one step; the GP "
+                             "matrix is re-used out of L2, so DRAM traffic is below the gather model (DESIGN.md 6)"},
+        "roofline_fp": fp_roofline(plp, alphas, pair_s, fp32, main["clocks"]),
+        "breakdown_ms": {"prep": float(np.mean(main["rec"]["prep"])), "pair_scan": float(np.mean(main["rec"]["pair"])),
+                         "all_kernels": float(np.mean(main["rec"]["kern"])), "d2h": st["d2h_ms"],
+                         "finalise_host": float(np.mean(main["rec"]["fin"])),
+                         "rescored_hypotheses": int(st["n_rescored"]), "host_threads": main["host_threads"]},
+        "clocks": main["clocks"],
     }
+    if args.write_pair:
+        line["write_pair"] = {"dense_llk_bytes_per_step": main["pair_bytes"] * (world if scaling == "weak" else 1),
+                              "note": "dmx_get_pair of every barcode inside both timed regions (fp64 scan with dense "
+                                      "stores + read-back); the text of .pair is formatted by dmx_write_outputs, "
+                                      "timed by tools/write_bench.py"}
+    if strong is not None and main is not strong:
+        s1, s2 = strong["st"], strong["st2"]
+        line["strong"] = {
+            "scaling": "strong", "value": strong["total"] * args.steps / strong["dt"], "unit": UNIT,
+            "ms_per_step": strong["dt"] / args.steps * 1e3,
+            "e2e": {"value": strong["total"] * args.steps / strong["dt2"], "unit": UNIT,
+                    "ms_per_step": strong["dt2"] / args.steps * 1e3},
+            "cells_total": strong["total"], "cells_per_gpu": strong["counts"], "entries_per_gpu": strong["entries"],
+            "rank0_ms": {"pair_scan": float(np.mean(strong["rec"]["pair"])), "all_kernels": float(np.mean(strong["rec"]["kern"])),
+                         "finalise_host": float(np.mean(strong["rec"]["fin"])), "e2e_h2d": s2["h2d_ms"]},
+            "gpu_launches": int(s1["gpu_launches"]) * args.steps,
+            "note": "the SAME %d-barcode job as N = 1, split over the ranks; value = barcodes of the job / max-over-ranks "
+                    "step time, all-gather of the records inside the step" % strong["total"]}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(plp, alphas)
     emit(line)
@@ -416,6 +522,11 @@ def main():
                     help="pair scan on the FP64 tensor path (DMMA) instead of fp32 products")
     ap.add_argument("--fp32-pairs", action="store_true", help="(default; kept for old command lines)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="both", choices=["weak", "strong", "both"],
+                    help="N > 1: weak = every rank one whole workload (the line's value); strong = one workload split "
+                         "over the ranks (reported under 'strong'); both by default")
+    ap.add_argument("--write-pair", action="store_true",
+                    help="also fetch the dense llksAB block of every barcode in every step (what --write-pair prints)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

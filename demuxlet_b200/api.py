@@ -29,6 +29,7 @@ DMX_HOST_FINALISE = 0x20
 # every symbol include/dmx.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
     "dmx_config_default", "dmx_device_count", "dmx_create", "dmx_destroy", "dmx_set_gp", "dmx_set_pileup",
+    "dmx_create_sharded", "dmx_shard_count", "dmx_shard_range", "dmx_shard_stats",
     "dmx_upload", "dmx_compute", "dmx_run", "dmx_get_best", "dmx_get_single", "dmx_get_sing2", "dmx_get_pair",
     "dmx_rescore", "dmx_exact_llk", "dmx_write_outputs", "dmx_get_stats", "dmx_alloc_host", "dmx_free_host", "dmx_strerror",
     "dmx_last_error", "dmx_abi_version", "dmx_pack_reads", "dmx_pileup_sizes", "dmx_pileup_copy", "dmx_pileup_free",
@@ -103,6 +104,10 @@ def load_library(path: Optional[str] = None):
     lib.dmx_alloc_host.argtypes = [C.c_int64]
     lib.dmx_free_host.argtypes = [C.c_void_p]
     lib.dmx_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(DmxConfig)]
+    lib.dmx_create_sharded.argtypes = [C.POINTER(C.c_void_p), C.POINTER(DmxConfig), C.c_int32, C.POINTER(C.c_int32)]
+    lib.dmx_shard_count.argtypes = [C.c_void_p]
+    lib.dmx_shard_range.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+    lib.dmx_shard_stats.argtypes = [C.c_void_p, C.c_int32, C.POINTER(DmxStats)]
     lib.dmx_destroy.argtypes = [C.c_void_p]
     lib.dmx_destroy.restype = None
     lib.dmx_set_gp.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
@@ -374,7 +379,8 @@ _PINNED: dict = {}
 
 
 class Demuxlet:
-    """The likelihood scan of one pileup on one GPU.
+    """The likelihood scan of one pileup on one GPU, or -- with `devices=[...]` -- on several GPUs of this host over
+    contiguous barcode ranges balanced by pileup entries (dmx_create_sharded; same results, same files).
 
     alphas        --alpha (multi-valued; default {0, 0.5}, cmd_cram_demuxlet.cpp:78-90)
     doublet_prior --doublet-prior (:56)
@@ -385,7 +391,7 @@ class Demuxlet:
                  min_total: int = 0, min_uniq: int = 0, min_snp: int = 0, device: int = 0,
                  exact_ties: bool = True, borrow: bool = False, fp32_pairs: bool = False,
                  skip_single: bool = False, trust_inputs: bool = False, host_threads: int = 0,
-                 host_finalise: bool = False):
+                 host_finalise: bool = False, devices: Optional[Sequence[int]] = None):
         self.lib = load_library()
         self.nv = int(nv)
         self.alpha = np.ascontiguousarray(alphas, dtype=np.float64)
@@ -396,14 +402,33 @@ class Demuxlet:
         self.cfg = DmxConfig(self.nv, self.nA, self.alpha.ctypes.data_as(C.POINTER(C.c_double)), doublet_prior,
                              min_total, min_uniq, min_snp, device, flags, host_threads)
         self._h = C.c_void_p()
-        self._chk(self.lib.dmx_create(C.byref(self._h), C.byref(self.cfg)), "dmx_create")
+        if devices is None:
+            self._chk(self.lib.dmx_create(C.byref(self._h), C.byref(self.cfg)), "dmx_create")
+        else:
+            dv = (C.c_int32 * len(devices))(*[int(x) for x in devices])
+            self._chk(self.lib.dmx_create_sharded(C.byref(self._h), C.byref(self.cfg), len(devices), dv),
+                      "dmx_create_sharded")
         self._keep = []
         self.ncells = 0
         self.plp: Optional[Pileup] = None
 
     def _chk(self, rc: int, where: str):
         if rc != 0:
-            raise DmxError(rc, where, self.lib.dmx_last_error().decode() if rc == -2 else "")
+            raise DmxError(rc, where, self.lib.dmx_last_error().decode() if rc in (-2, -3) else "")
+
+    def shards(self):
+        """[(cell_lo, cell_hi, device)] of the barcode ranges (one entry for a single-device context)"""
+        out = []
+        for i in range(int(self.lib.dmx_shard_count(self._h))):
+            lo, hi, dev = C.c_int64(), C.c_int64(), C.c_int32()
+            self._chk(self.lib.dmx_shard_range(self._h, i, C.byref(lo), C.byref(hi), C.byref(dev)), "dmx_shard_range")
+            out.append((lo.value, hi.value, dev.value))
+        return out
+
+    def shard_stats(self, i: int) -> dict:
+        st = DmxStats()
+        self._chk(self.lib.dmx_shard_stats(self._h, i, C.byref(st)), "dmx_shard_stats")
+        return st.asdict()
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:

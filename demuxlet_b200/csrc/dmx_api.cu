@@ -55,19 +55,25 @@ template <class T>
 struct PinBuf {
   T* p = nullptr;
   size_t cap = 0;
+  bool view = false;   // p belongs to another buffer (a shard's slice of the sharded context's result arrays)
   cudaError_t reserve(size_t n) {
     if (n <= cap) return cudaSuccess;
-    if (p) cudaFreeHost(p);
-    p = nullptr;
-    cap = 0;
+    release();
     cudaError_t e = cudaMallocHost((void**)&p, std::max<size_t>(n, 1) * sizeof(T));
     if (e == cudaSuccess) cap = n;
     return e;
   }
+  void adopt(T* ptr, size_t n) {
+    release();
+    p = ptr;
+    cap = n;
+    view = true;
+  }
   void release() {
-    if (p) cudaFreeHost(p);
+    if (p && !view) cudaFreeHost(p);
     p = nullptr;
     cap = 0;
+    view = false;
   }
 };
 }  // namespace
@@ -143,6 +149,11 @@ struct dmx_ctx {
   std::vector<dmx_best_rec> best;
   dmx_stats st;
   ScanMaps maps;                    // TMA descriptors of d_gprow / d_entq (encode_maps)
+
+  // sharded context (dmx_create_sharded): one child context per device over the barcode range
+  // [kid_lo[i], kid_lo[i + 1]); the children's per-barcode result arrays are views into this context's
+  std::vector<dmx_ctx*> kids;
+  std::vector<int64_t> kid_lo;
 };
 
 namespace {
@@ -443,10 +454,32 @@ void expand_cands(const dmx_ctx* c, const CellOut& co, std::vector<Hyp>* out) {
   });
 }
 
+int for_each_kid(dmx_ctx* c, const std::function<int(int)>& f);
+
 // dense llksAB for a list of active cells (device order buffer is temporarily replaced)
 int dense_scan(dmx_ctx* c, const std::vector<int32_t>& cells, double* host_out /* [n][nv][nv][nA] */) {
   const int nv = c->cfg.nv, nA = c->cfg.n_alpha;
   const size_t per = (size_t)nv * nv * nA;
+  if (!c->kids.empty()) {
+    // sharded context: every shard scans its own cells of the list (on its own device, in parallel)
+    const int nk = (int)c->kids.size();
+    std::vector<std::vector<int32_t>> mine(nk);
+    std::vector<std::vector<size_t>> at(nk);
+    for (size_t i = 0; i < cells.size(); ++i) {
+      const int k = (int)(std::upper_bound(c->kid_lo.begin(), c->kid_lo.end(), (int64_t)cells[i]) - c->kid_lo.begin()) - 1;
+      mine[k].push_back((int32_t)(cells[i] - c->kid_lo[k]));
+      at[k].push_back(i);
+    }
+    return for_each_kid(c, [&](int k) {
+      if (mine[k].empty()) return (int)DMX_OK;
+      std::vector<double> tmp(mine[k].size() * per);
+      const int rc = dense_scan(c->kids[k], mine[k], tmp.data());
+      if (rc != DMX_OK) return rc;
+      for (size_t i = 0; i < mine[k].size(); ++i) memcpy(host_out + at[k][i] * per, tmp.data() + i * per, per * sizeof(double));
+      return (int)DMX_OK;
+    });
+  }
+  CU(cudaSetDevice(c->cfg.device));
   const size_t max_batch = std::max<size_t>(1, ((size_t)1 << 30) / (per * sizeof(double)));
   DevBuf<int32_t> d_cells;
   DevBuf<Part> d_parts;
@@ -473,6 +506,146 @@ int dense_scan(dmx_ctx* c, const std::vector<int32_t>& cells, double* host_out /
   }
   d_cells.release();
   d_parts.release();
+  return DMX_OK;
+}
+
+
+// ---- sharded contexts -----------------------------------------------------------------------------------------------
+// f(shard index) on one host thread per shard (the caller's thread takes shard 0); first non-zero status wins
+int for_each_kid(dmx_ctx* c, const std::function<int(int)>& f) {
+  const int n = (int)c->kids.size();
+  std::vector<int> rc(n, 0);
+  std::vector<std::string> err(n);
+  std::vector<std::thread> th;
+  for (int i = 1; i < n; ++i)
+    th.emplace_back([&, i]() {
+      rc[i] = f(i);
+      if (rc[i]) err[i] = g_last_error;   // thread-local text of the failing shard
+    });
+  if (n > 0) {
+    rc[0] = f(0);
+    if (rc[0]) err[0] = g_last_error;
+  }
+  for (auto& t : th) t.join();
+  for (int i = 0; i < n; ++i)
+    if (rc[i]) {
+      g_last_error = err[i];
+      return rc[i];
+    }
+  return DMX_OK;
+}
+
+int sharded_set_gp(dmx_ctx* c, const float* gp, int64_t nsnps) {
+  c->nsnps = nsnps;
+  const size_t n = (size_t)nsnps * c->cfg.nv * 3;
+  if (c->cfg.flags & DMX_BORROW_INPUTS) {
+    c->h_gp = gp;
+  } else {
+    CU(c->o_gp.reserve(n));
+    memcpy(c->o_gp.p, gp, n * sizeof(float));
+    c->h_gp = c->o_gp.p;
+  }
+  for (dmx_ctx* k : c->kids) RC(dmx_set_gp(k, c->h_gp, nsnps));   // children borrow: one host copy, n device copies
+  c->have_gp = true;
+  c->computed = false;
+  return DMX_OK;
+}
+
+int sharded_set_pileup(dmx_ctx* c, int64_t ncells, const int64_t* cell_ptr, const int32_t* ent_snp,
+                       const int64_t* ent_ptr, const uint16_t* reads, const int32_t* totl, const int32_t* pass,
+                       const int32_t* uniq) {
+  const int nk = (int)c->kids.size();
+  const int nv = c->cfg.nv, nA = c->cfg.n_alpha;
+  const int64_t E = cell_ptr[ncells], R = ent_ptr[E];
+  c->ncells = ncells; c->E = E; c->R = R;
+  CU(c->o_cell_ptr.reserve(ncells + 1));
+  memcpy(c->o_cell_ptr.p, cell_ptr, (ncells + 1) * sizeof(int64_t));
+  c->h_cell_ptr = c->o_cell_ptr.p;
+  c->totl.assign(totl, totl + ncells);
+  c->npass.assign(pass, pass + ncells);
+  c->uniq.assign(uniq, uniq + ncells);
+  c->status.assign(ncells, 0);
+  for (int64_t i = 0; i < ncells; ++i) {
+    const int64_t ns = cell_ptr[i + 1] - cell_ptr[i];
+    if (totl[i] < c->cfg.min_total || uniq[i] < c->cfg.min_uniq || ns < c->cfg.min_snp) c->status[i] = 1;
+    else if (ns == 0) c->status[i] = 2;
+  }
+  // contiguous barcode ranges with (nearly) equal numbers of pileup entries
+  c->kid_lo.assign(nk + 1, 0);
+  for (int k = 1; k < nk; ++k) {
+    const int64_t target = (int64_t)((double)E * k / nk);
+    int64_t cut = std::lower_bound(cell_ptr, cell_ptr + ncells + 1, target) - cell_ptr;
+    cut = std::min(std::max(cut, c->kid_lo[k - 1]), ncells);
+    c->kid_lo[k] = cut;
+  }
+  c->kid_lo[nk] = ncells;
+  // per-barcode result arrays of the whole job; each shard reads its records back into its own slice
+  CU(c->r_p1.reserve((size_t)ncells * nv + nk + 1)); CU(c->r_p1_0.reserve(ncells + nk + 1));
+  CU(c->r_sing.reserve((size_t)ncells * nv + nk + 1)); CU(c->r_l00.reserve((size_t)ncells * nA + nk + 1));
+  const bool borrow = (c->cfg.flags & DMX_BORROW_INPUTS) != 0;
+  RC(for_each_kid(c, [&](int k) {
+    dmx_ctx* kid = c->kids[k];
+    const int64_t lo = c->kid_lo[k], hi = c->kid_lo[k + 1], n = hi - lo;
+    const int64_t e0 = cell_ptr[lo], e1 = cell_ptr[hi], r0 = ent_ptr[e0], r1 = ent_ptr[e1];
+    CU(cudaSetDevice(kid->cfg.device));
+    CU(kid->o_cell_ptr.reserve(n + 1)); CU(kid->o_ent_ptr.reserve(e1 - e0 + 1));
+    for (int64_t i = 0; i <= n; ++i) kid->o_cell_ptr.p[i] = cell_ptr[lo + i] - e0;
+    for (int64_t i = 0; i <= e1 - e0; ++i) kid->o_ent_ptr.p[i] = ent_ptr[e0 + i] - r0;
+    const int32_t* snp = ent_snp + e0;
+    const uint16_t* rd = reads + r0;
+    if (!borrow) {
+      CU(kid->o_ent_snp.reserve(e1 - e0)); CU(kid->o_reads.reserve(r1 - r0));
+      if (e1 > e0) memcpy(kid->o_ent_snp.p, snp, (e1 - e0) * sizeof(int32_t));
+      if (r1 > r0) memcpy(kid->o_reads.p, rd, (r1 - r0) * sizeof(uint16_t));
+      snp = kid->o_ent_snp.p;
+      rd = kid->o_reads.p;
+    }
+    RC(dmx_set_pileup(kid, n, kid->o_cell_ptr.p, snp, kid->o_ent_ptr.p, rd, totl + lo, pass + lo, uniq + lo));
+    kid->r_p1.adopt(c->r_p1.p + lo * nv, (size_t)n * nv + 1);
+    kid->r_p1_0.adopt(c->r_p1_0.p + lo, (size_t)n + 1);
+    kid->r_sing.adopt(c->r_sing.p + lo * nv, (size_t)n * nv + 1);
+    kid->r_l00.adopt(c->r_l00.p + lo * nA, (size_t)n * nA + 1);
+    return (int)DMX_OK;
+  }));
+  c->have_plp = true;
+  c->computed = false;
+  return DMX_OK;
+}
+
+// mode 0: dmx_run, 1: dmx_upload, 2: dmx_compute
+int sharded_run(dmx_ctx* c, int mode) {
+  if (!c->have_gp || !c->have_plp) return DMX_E_STATE;
+  const double t0 = now_ms();
+  if (mode != 1) c->best.assign((size_t)c->ncells, dmx_best_rec());
+  RC(for_each_kid(c, [&](int k) {
+    dmx_ctx* kid = c->kids[k];
+    const int rc = mode == 0 ? dmx_run(kid) : (mode == 1 ? dmx_upload(kid) : dmx_compute(kid));
+    if (rc != DMX_OK || mode == 1) return rc;
+    if (kid->ncells) memcpy(c->best.data() + c->kid_lo[k], kid->best.data(), kid->ncells * sizeof(dmx_best_rec));
+    return (int)DMX_OK;
+  }));
+  dmx_stats a;
+  memset(&a, 0, sizeof(a));
+  a.gpu_exact = 1;
+  for (const dmx_ctx* kid : c->kids) {
+    const dmx_stats& s = kid->st;
+    a.h2d_ms = std::max(a.h2d_ms, s.h2d_ms); a.prep_ms = std::max(a.prep_ms, s.prep_ms);
+    a.kernel_ms = std::max(a.kernel_ms, s.kernel_ms); a.d2h_ms = std::max(a.d2h_ms, s.d2h_ms);
+    a.finalise_ms = std::max(a.finalise_ms, s.finalise_ms); a.pair_kernel_ms = std::max(a.pair_kernel_ms, s.pair_kernel_ms);
+    a.h2d_bytes += s.h2d_bytes; a.d2h_bytes += s.d2h_bytes; a.n_entries += s.n_entries; a.n_reads += s.n_reads;
+    a.n_tasks += s.n_tasks; a.gpu_launches += s.gpu_launches; a.n_rescored += s.n_rescored; a.n_fullcell += s.n_fullcell;
+    a.n_rescored_gpu += s.n_rescored_gpu; a.algo_bytes += s.algo_bytes;
+    a.gpu_exact = std::min(a.gpu_exact, s.gpu_exact);
+  }
+  a.total_ms = now_ms() - t0;
+  if (mode == 1) {
+    c->st.h2d_ms = a.h2d_ms;
+    c->st.h2d_bytes = a.h2d_bytes;
+    c->uploaded = true;
+  } else {
+    c->st = a;
+    c->computed = true;
+  }
   return DMX_OK;
 }
 
@@ -578,8 +751,81 @@ int dmx_create(dmx_ctx** out, const dmx_config* cfg) {
   return DMX_OK;
 }
 
+int dmx_create_sharded(dmx_ctx** out, const dmx_config* cfg, int32_t n_devices, const int32_t* devices) {
+  if (!out || !cfg || !cfg->alpha || n_devices < 1 || n_devices > 64 || !devices) return DMX_E_INVALID;
+  *out = nullptr;
+  if (cfg->nv < 2 || cfg->nv > 4095 || cfg->n_alpha < 2 || cfg->n_alpha > DMX_MAX_ALPHA) return DMX_E_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    g_last_error = "no CUDA device";
+    return DMX_E_NODEVICE;
+  }
+  for (int i = 0; i < n_devices; ++i)
+    if (devices[i] < 0 || devices[i] >= ndev) {
+      g_last_error = "device ordinal out of range";
+      return DMX_E_NODEVICE;
+    }
+  dmx_ctx* c = new (std::nothrow) dmx_ctx();
+  if (!c) return DMX_E_NOMEM;
+  c->cfg = *cfg;
+  c->cfg.device = devices[0];
+  c->pool = new WorkerPool();
+  c->alpha.assign(cfg->alpha, cfg->alpha + cfg->n_alpha);
+  c->cfg.alpha = c->alpha.data();
+  memset(&c->st, 0, sizeof(c->st));
+  build_pgrid(c->alpha.data(), cfg->n_alpha, &c->pg);
+  c->nvp = (cfg->nv + TILE - 1) / TILE * TILE;
+  c->kids.assign((size_t)n_devices, nullptr);
+  int total = cfg->n_host_threads;
+  if (total <= 0) total = (int)std::thread::hardware_concurrency();
+  const int rc = for_each_kid(c, [&](int k) {
+    dmx_config kc = *cfg;
+    kc.alpha = c->alpha.data();
+    kc.device = devices[k];
+    kc.flags |= DMX_BORROW_INPUTS;                         // the sharded context owns (or borrows) the host inputs
+    kc.n_host_threads = std::max(1, total / n_devices);    // the shards share the host's cores
+    return dmx_create(&c->kids[(size_t)k], &kc);
+  });
+  if (rc != DMX_OK) {
+    const std::string why = g_last_error;
+    dmx_destroy(c);
+    g_last_error = why;
+    return rc;
+  }
+  *out = c;
+  return DMX_OK;
+}
+
+int dmx_shard_count(const dmx_ctx* c) {
+  if (!c) return 0;
+  return c->kids.empty() ? 1 : (int)c->kids.size();
+}
+
+int dmx_shard_range(const dmx_ctx* c, int32_t shard, int64_t* cell_lo, int64_t* cell_hi, int32_t* device) {
+  if (!c || shard < 0 || shard >= dmx_shard_count(c)) return DMX_E_INVALID;
+  if (!c->have_plp) return DMX_E_STATE;
+  if (c->kids.empty()) {
+    if (cell_lo) *cell_lo = 0;
+    if (cell_hi) *cell_hi = c->ncells;
+    if (device) *device = c->cfg.device;
+    return DMX_OK;
+  }
+  if (cell_lo) *cell_lo = c->kid_lo[(size_t)shard];
+  if (cell_hi) *cell_hi = c->kid_lo[(size_t)shard + 1];
+  if (device) *device = c->kids[(size_t)shard]->cfg.device;
+  return DMX_OK;
+}
+
+int dmx_shard_stats(dmx_ctx* c, int32_t shard, dmx_stats* out) {
+  if (!c || !out || shard < 0 || shard >= dmx_shard_count(c)) return DMX_E_INVALID;
+  *out = c->kids.empty() ? c->st : c->kids[(size_t)shard]->st;
+  return DMX_OK;
+}
+
 void dmx_destroy(dmx_ctx* c) {
   if (!c) return;
+  for (dmx_ctx* k : c->kids) dmx_destroy(k);   // their result views point into this context's arrays
+  c->kids.clear();
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   c->d_terms.release(); c->d_ents.release(); c->d_entf_head.release(); c->d_entf_plane.release();
@@ -605,6 +851,7 @@ void dmx_destroy(dmx_ctx* c) {
 int dmx_set_gp(dmx_ctx* c, const float* gp, int64_t nsnps) {
   if (!c || !gp || nsnps < 0) return DMX_E_INVALID;
   CU(cudaSetDevice(c->cfg.device));
+  if (!c->kids.empty()) return sharded_set_gp(c, gp, nsnps);
   c->nsnps = nsnps;
   const size_t n = (size_t)nsnps * c->cfg.nv * 3;
   if (c->cfg.flags & DMX_BORROW_INPUTS) {
@@ -635,6 +882,7 @@ int dmx_set_pileup(dmx_ctx* c, int64_t ncells, const int64_t* cell_ptr, const in
   for (int64_t i = 0; i < ncells; ++i)
     if (cell_ptr[i + 1] < cell_ptr[i]) return DMX_E_INVALID;
   CU(cudaSetDevice(c->cfg.device));
+  if (!c->kids.empty()) return sharded_set_pileup(c, ncells, cell_ptr, ent_snp, ent_ptr, reads, totl, pass, uniq);
   c->ncells = ncells; c->E = E; c->R = R;
   if (c->cfg.flags & DMX_BORROW_INPUTS) {
     c->h_cell_ptr = cell_ptr; c->h_ent_snp = ent_snp; c->h_ent_ptr = ent_ptr; c->h_reads = reads;
@@ -1084,6 +1332,7 @@ int run_path(dmx_ctx* c, bool pipelined) {
 int dmx_upload(dmx_ctx* c) {
   if (!c) return DMX_E_INVALID;
   if (!c->have_gp || !c->have_plp) return DMX_E_STATE;
+  if (!c->kids.empty()) return sharded_run(c, 1);
   CU(cudaSetDevice(c->cfg.device));
   const double t0 = now_ms();
   int64_t bytes = 0;
@@ -1107,6 +1356,7 @@ int dmx_upload(dmx_ctx* c) {
 int dmx_compute(dmx_ctx* c) {
   if (!c) return DMX_E_INVALID;
   if (!c->uploaded) return DMX_E_STATE;
+  if (!c->kids.empty()) return sharded_run(c, 2);
   return run_path(c, false);
 }
 
@@ -1114,6 +1364,7 @@ int dmx_compute(dmx_ctx* c) {
 int dmx_run(dmx_ctx* c) {
   if (!c) return DMX_E_INVALID;
   if (!c->have_gp || !c->have_plp) return DMX_E_STATE;
+  if (!c->kids.empty()) return sharded_run(c, 0);
   if (!c->gp_dirty && !c->plp_dirty && c->uploaded) return run_path(c, false);
   return run_path(c, true);
 }
@@ -1145,7 +1396,6 @@ int dmx_get_sing2(dmx_ctx* c, double* llk_j00, double* llk00) {
 int dmx_get_pair(dmx_ctx* c, int64_t cell_lo, int64_t cell_hi, double* llkAB) {
   if (!c || !llkAB || cell_lo < 0 || cell_hi > c->ncells || cell_lo > cell_hi) return DMX_E_INVALID;
   if (!c->computed) return DMX_E_STATE;
-  CU(cudaSetDevice(c->cfg.device));
   const size_t per = (size_t)c->cfg.nv * c->cfg.nv * c->cfg.n_alpha;
   std::vector<int32_t> cells;
   for (int64_t i = cell_lo; i < cell_hi; ++i)
@@ -1165,6 +1415,10 @@ int dmx_rescore(dmx_ctx* c, int64_t cell, int32_t j, int32_t k, int32_t n, doubl
   if (cell < 0 || cell >= c->ncells || j < 0 || j >= c->cfg.nv || k < 0 || k >= c->cfg.nv || n < 0 ||
       n >= c->cfg.n_alpha)
     return DMX_E_INVALID;
+  if (!c->kids.empty()) {
+    const int s = (int)(std::upper_bound(c->kid_lo.begin(), c->kid_lo.end(), cell) - c->kid_lo.begin()) - 1;
+    return dmx_rescore(c->kids[(size_t)s], cell - c->kid_lo[(size_t)s], j, k, n, out);
+  }
   const HostView hv = host_view(c);
   const ExactScorer scorer(hv, c->err256);
   Hyp h{j, k, n};
@@ -1575,6 +1829,15 @@ int dmx_site_filter(int32_t device, int32_t nv, int64_t nsnps, const int8_t* gt,
 
 int dmx_set_field(dmx_ctx* c, int32_t field, const void* in, int64_t nsnps, double gt_error) {
   if (!c || nsnps < 0 || (nsnps > 0 && !in) || field < DMX_FIELD_GT || field > DMX_FIELD_PL) return DMX_E_INVALID;
+  if (!c->kids.empty()) {
+    // every shard builds the matrix on its own device from the same FORMAT values
+    RC(for_each_kid(c, [&](int k) { return dmx_set_field(c->kids[(size_t)k], field, in, nsnps, gt_error); }));
+    c->nsnps = nsnps;
+    c->h_gp = c->kids[0]->h_gp;
+    c->have_gp = true;
+    c->computed = false;
+    return DMX_OK;
+  }
   CU(cudaSetDevice(c->cfg.device));
   const int nv = c->cfg.nv, nvp = c->nvp;
   const size_t in_bytes = (size_t)nsnps * field_in_bytes(field, nv), n = (size_t)nsnps * nv * 3;

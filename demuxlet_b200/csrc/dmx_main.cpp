@@ -4,11 +4,12 @@
 // (sc_dropseq_lib_t) and then runs lines 386-881.  This driver keeps the option names and the four output files of
 // that program for the part that is in scope: it takes the finished pileup as a flat file (--plp, the .dmxp
 // container of demuxlet_b200/plp.py: GP matrix + CSR pileup + barcodes + sample ids, i.e. exactly what crosses the
-// C ABI) and calls dmx_set_gp / dmx_set_pileup / dmx_run / dmx_write_outputs.  --sam / --vcf are recognised and
-// refused with a clear message: BAM/VCF reading needs htslib, which is not part of this build.
+// C ABI) and calls dmx_set_gp / dmx_set_pileup / dmx_run / dmx_write_outputs.  --sam FILE --vcf FILE run the whole reference
+// command line through the library's own BGZF / BAM / VCF-text readers (no htslib: no CRAM / BCF).
 //
 //   dmx-demuxlet --plp in.dmxp --out prefix [--alpha A]... [--doublet-prior P] [--min-total N] [--min-uniq N]
-//                [--min-snp N] [--group-list FILE] [--write-pair] [--gpu D] [--fp64-pairs] [--verbose]
+//                [--min-snp N] [--group-list FILE] [--write-pair] [--gpu D | --gpus N | --gpu-list a,b,..]
+//                [--fp64-pairs] [--verbose]
 //
 // Options and defaults follow cmd_cram_demuxlet.cpp:29-33,:54-56,:64-71,:78-90 (alpha grid {0, 0.5} when none is
 // given; barcodes restricted to --group-list like :68,:131-140).  Exit status 0 on success, 1 on error with the
@@ -145,6 +146,9 @@ void usage() {
           "  --group-list FILE   only the barcodes listed in FILE\n"
           "  --write-pair        also write the (huge) PREFIX.pair\n"
           "  --gpu D             CUDA device ordinal (default 0)\n"
+          "  --gpus N            shard the barcodes over the first N GPUs of this host (contiguous ranges balanced by\n"
+          "                      pileup entries, the reference's --group-list model); one set of output files\n"
+          "  --gpu-list a,b,..   the same over the listed device ordinals\n"
           "  --fp64-pairs        pair scan in fp64 (default: fp32 products, exact re-score of the decisive values)\n"
           "  --field GT|GP|PL --field-matrix FILE [--geno-error E]\n"
           "                      build the genotype probabilities on the GPU from the flat FORMAT values in FILE\n"
@@ -170,6 +174,7 @@ int main(int argc, char** argv) {
   std::vector<double> alpha;
   double prior = 0.5;
   int min_total = 0, min_uniq = 0, min_snp = 0, gpu = 0, write_pair = 0, verbose = 0, fp64 = 0;
+  std::vector<int32_t> gpu_list;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     auto val = [&]() -> const char* {
@@ -186,6 +191,20 @@ int main(int argc, char** argv) {
     else if (a == "--group-list") groups = val();
     else if (a == "--write-pair") write_pair = 1;
     else if (a == "--gpu") gpu = atoi(val());
+    else if (a == "--gpus") {
+      const int n = atoi(val());
+      if (n < 1) die("--gpus needs a positive count", "");
+      gpu_list.clear();
+      for (int d = 0; d < n; ++d) gpu_list.push_back(d);
+    } else if (a == "--gpu-list") {
+      gpu_list.clear();
+      for (const char* q = val(); *q;) {
+        char* end = nullptr;
+        gpu_list.push_back((int32_t)strtol(q, &end, 10));
+        if (end == q) die("--gpu-list takes device ordinals separated by commas", "");
+        q = *end ? end + 1 : end;
+      }
+    }
     else if (a == "--fp64-pairs") fp64 = 1;
     else if (a == "--verbose") verbose = 1;
     else if (a == "--help" || a == "-h") { usage(); return 0; }
@@ -212,6 +231,7 @@ int main(int argc, char** argv) {
   if (sam_path && !vcf_path) die("--sam needs --vcf (the SNPs the reads are piled up on)");
   if ((sm_list || !sm_ids.empty()) && !vcf_path) die("--sm / --sm-list select samples of --vcf", "");
   if (alpha.empty()) { alpha.push_back(0.0); alpha.push_back(0.5); }   // :78-90
+  if (!gpu_list.empty()) gpu = gpu_list[0];   // the VCF-side device work (site filter) runs on the first one
 
   if (field && !field_path && !vcf_path)
     die("--field %s needs --vcf FILE or --field-matrix FILE (the FORMAT values as flat arrays)", field);
@@ -356,7 +376,8 @@ int main(int argc, char** argv) {
   cfg.device = gpu;
   if (!fp64) cfg.flags |= DMX_FP32_PAIRS;
   dmx_ctx* ctx = nullptr;
-  int rc = dmx_create(&ctx, &cfg);
+  int rc = gpu_list.size() > 1 ? dmx_create_sharded(&ctx, &cfg, (int32_t)gpu_list.size(), gpu_list.data())
+                               : dmx_create(&ctx, &cfg);
   if (rc == DMX_OK)
     rc = field_path ? dmx_set_field(ctx, ff.field, ff.data.data(), ff.nsnps, ff.geno_error)
                     : dmx_set_gp(ctx, p.gp.data(), p.nsnps);
@@ -380,6 +401,15 @@ int main(int argc, char** argv) {
     dmx_get_stats(ctx, &st);
     fprintf(stderr, "NOTICE - %lld kernel launches, copies %.2f ms, kernels %.2f ms (pair scan %.2f ms), finaliser %.2f ms\n",
             (long long)st.gpu_launches, st.h2d_ms, st.kernel_ms, st.pair_kernel_ms, st.finalise_ms);
+    for (int sh = 0; sh < dmx_shard_count(ctx) && dmx_shard_count(ctx) > 1; ++sh) {
+      int64_t lo = 0, hi = 0;
+      int32_t dev = 0;
+      dmx_stats ss;
+      dmx_shard_range(ctx, sh, &lo, &hi, &dev);
+      dmx_shard_stats(ctx, sh, &ss);
+      fprintf(stderr, "NOTICE - shard %d: GPU %d, droplets [%lld, %lld), %lld entries, kernels %.2f ms\n", sh, (int)dev,
+              (long long)lo, (long long)hi, (long long)ss.n_entries, ss.kernel_ms);
+    }
   }
   dmx_destroy(ctx);
   return 0;

@@ -51,3 +51,45 @@ def allgather_records(local: np.ndarray, counts: List[int], device=None) -> np.n
     out = recv.cpu().numpy()
     parts = [out[r * width: r * width + counts[r] * item].view(local.dtype) for r in range(world)]
     return np.concatenate(parts)
+
+
+class RecordExchange:
+    """The path's one collective, with its buffers kept between steps: all-gather of the per-barcode records of every
+    rank's shard (`counts[r]` records of `itemsize` bytes on rank r; shards padded to the largest).  On "nccl" the
+    records go pinned host -> device -> NCCL all-gather over NVLink -> pinned host."""
+
+    def __init__(self, counts: List[int], itemsize: int, device=None):
+        import torch
+        import torch.distributed as dist
+        self.dist, self.torch = dist, torch
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        assert len(counts) == self.world
+        self.counts, self.item = list(counts), int(itemsize)
+        self.width = max(max(counts), 1) * self.item
+        nccl = dist.get_backend() == "nccl"
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if nccl else torch.device("cpu")
+        self.h_send = torch.zeros(self.width, dtype=torch.uint8)
+        self.h_recv = torch.zeros(self.world * self.width, dtype=torch.uint8)
+        if nccl:
+            self.h_send, self.h_recv = self.h_send.pin_memory(), self.h_recv.pin_memory()
+        self.d_send = torch.zeros(self.width, dtype=torch.uint8, device=device)
+        self.d_recv = torch.zeros(self.world * self.width, dtype=torch.uint8, device=device)
+        self.on_device = nccl
+
+    def __call__(self, local: np.ndarray) -> np.ndarray:
+        """returns a view of all ranks' records (rank order) valid until the next call"""
+        n = self.counts[self.rank] * self.item
+        assert local.dtype.itemsize == self.item and local.shape[0] == self.counts[self.rank]
+        self.h_send.numpy()[:n] = local.view(np.uint8).reshape(-1)
+        self.d_send.copy_(self.h_send, non_blocking=True)
+        self.dist.all_gather_into_tensor(self.d_recv, self.d_send)
+        self.h_recv.copy_(self.d_recv, non_blocking=True)
+        if self.on_device:
+            self.torch.cuda.current_stream().synchronize()
+        out = self.h_recv.numpy()
+        if len(set(self.counts)) == 1:
+            return out[: self.world * n].view(local.dtype) if self.width == n else np.concatenate(
+                [out[r * self.width: r * self.width + n] for r in range(self.world)]).view(local.dtype)
+        return np.concatenate([out[r * self.width: r * self.width + self.counts[r] * self.item]
+                               for r in range(self.world)]).view(local.dtype)

@@ -121,7 +121,10 @@ def make_synth(ncells: int, nv: int, nsnps: int, field: str = "GP", seed: int = 
     want = np.clip(want, cover_min, nsnps).astype(np.int64)
     cell_of = np.repeat(np.arange(ncells, dtype=np.int64), want)
     snp_of = rng.integers(0, nsnps, size=cell_of.shape[0], dtype=np.int64)
-    key = np.unique(cell_of * nsnps + snp_of)        # dedupe; sorted by (cell, snp)
+    key = cell_of * nsnps + snp_of                   # dedupe; sorted by (cell, snp)
+    key.sort()
+    if key.shape[0]:
+        key = key[np.concatenate([[True], key[1:] != key[:-1]])]
     cell_of, snp_of = key // nsnps, (key % nsnps).astype(np.int32)
     n_ent = np.bincount(cell_of, minlength=ncells)
     cell_ptr = np.concatenate([[0], np.cumsum(n_ent)]).astype(np.int64)

@@ -12,9 +12,10 @@
  *
  * Conventions: every function returns 0 (DMX_OK) or a negative dmx_status and never throws or
  * aborts; the caller owns all host buffers (the library copies what it keeps unless
- * DMX_BORROW_INPUTS is set); a dmx_ctx is bound to one CUDA device and is not thread-safe;
- * multi-GPU runs use one ctx (one process) per device over disjoint cell ranges -- cells are
- * independent in the reference (:576-875), cf. its --group-list sharding (:68).
+ * DMX_BORROW_INPUTS is set); a dmx_ctx is not thread-safe.  A context made by dmx_create is bound to
+ * one CUDA device; dmx_create_sharded makes one that drives several GPUs of the host over disjoint
+ * barcode ranges -- cells are independent in the reference (:576-875), cf. its --group-list sharding
+ * (:68).  Processes that own one GPU each (torchrun) use one dmx_create context per process instead.
  */
 #ifndef DMX_H
 #define DMX_H
@@ -25,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DMX_ABI_VERSION 1
+#define DMX_ABI_VERSION 2
 #define DMX_MAX_ALPHA 16
 
 typedef enum {
@@ -111,6 +112,20 @@ int dmx_device_count(void);
 
 int dmx_create(dmx_ctx** out, const dmx_config* cfg);
 void dmx_destroy(dmx_ctx* ctx);
+
+/* ---- multi-GPU (the reference's own parallel mode is --group-list over one barcode set, :68, :92-99) ----
+ * One context for n_devices GPUs of this host (cfg->device is ignored; a device may be listed more than once).
+ * dmx_set_pileup splits the barcodes into n_devices contiguous cell-id ranges with (nearly) equal numbers of pileup
+ * entries; every device holds the whole genotype-probability matrix; dmx_run / dmx_upload / dmx_compute drive the
+ * devices from one host thread each (no data-path collective: barcodes are independent), and the per-barcode records
+ * of all shards land in one set of host arrays, so every getter and dmx_write_outputs behave exactly as for a
+ * single-device context and produce the same bytes.  cfg->n_host_threads is the total, shared between the shards. */
+int dmx_create_sharded(dmx_ctx** out, const dmx_config* cfg, int32_t n_devices, const int32_t* devices);
+int dmx_shard_count(const dmx_ctx* ctx);             /* 1 for a dmx_create context */
+/* barcode range [cell_lo, cell_hi) and device of one shard (valid after dmx_set_pileup) */
+int dmx_shard_range(const dmx_ctx* ctx, int32_t shard, int64_t* cell_lo, int64_t* cell_hi, int32_t* device);
+/* dmx_get_stats of one shard (times of that device alone; the context's own stats carry max times / summed counts) */
+int dmx_shard_stats(dmx_ctx* ctx, int32_t shard, dmx_stats* out);
 
 /* gp[nsnps][nv][3], genotype fastest: exactly the floats the reference widens into
  * scl.snps[i].gps (:181-184, :227-231).  Also computes the cohort mean gp0s (:391-401) on device. */

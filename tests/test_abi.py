@@ -37,7 +37,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_abi_version_and_strerror(lib):
-    assert lib.dmx_abi_version() == 1
+    assert lib.dmx_abi_version() == 2
     assert lib.dmx_strerror(0) == b"ok"
     assert b"no CPU fallback" in lib.dmx_strerror(-3)
 

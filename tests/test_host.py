@@ -84,7 +84,7 @@ def test_shard_ranges_balance():
 
 def _worker(rank, world, port, out):
     import torch.distributed as dist
-    from demuxlet_b200.parallel import allgather_records, shard_pileup
+    from demuxlet_b200.parallel import RecordExchange, allgather_records, shard_pileup
     from demuxlet_b200.api import BEST_DTYPE
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -100,6 +100,16 @@ def _worker(rank, world, port, out):
     ok = (full.shape[0] == p.ncells and np.array_equal(full["sng1"], np.arange(p.ncells)) and
           np.array_equal(full["n_snp"], np.diff(p.cell_ptr)) and
           np.array_equal(full["llk12"], -np.arange(p.ncells, dtype=np.float64)))
+    # the buffered exchange bench.py uses every step: uneven shards, then repeated calls on the same buffers
+    ex = RecordExchange(counts, BEST_DTYPE.itemsize)
+    for rep in range(2):
+        rec["llk12"] = -np.arange(lo, hi, dtype=np.float64) - rep
+        full2 = ex(rec)
+        ok = ok and full2.shape[0] == p.ncells and np.array_equal(full2["sng1"], np.arange(p.ncells)) and \
+            np.array_equal(full2["llk12"], -np.arange(p.ncells, dtype=np.float64) - rep)
+    ex3 = RecordExchange([7, 7], 8)
+    ok = ok and np.array_equal(ex3(np.arange(7, dtype=np.int64) + 100 * rank),
+                               np.concatenate([np.arange(7), np.arange(7) + 100]))
     out[rank] = bool(ok)
     dist.destroy_process_group()
 
