@@ -126,7 +126,8 @@ struct dmx_ctx {
   DevBuf<double> d_entq, d_row0, d_singA, d_lb, d_p1, d_p1_0, d_l00, d_sing, d_dense;
   DevBuf<double> d_terms;          // [E][RESC_FAST] log terms of the two-phase exact re-scorer
   DevBuf<double> d_ents;           // [E][2 + nd] per-entry factors of llk0s / llks00 (entq -> cell_scalars)
-  DevBuf<float> d_entf_head, d_entf_plane;   // fp32 copies of the entry records (fp32 pair scan)
+  DevBuf<float> d_entf_head, d_entf_plane;   // fp32 copies of the entry records (fp32 pair scan), class-sorted per cell
+  DevBuf<int32_t> d_perm, d_snp_perm, d_cell_na;   // entry -> position, SNP id by position, affine entries per cell
   double err3_256[256];
   DevBuf<int64_t> d_cell_ptr, d_ent_ptr;
   DevBuf<int32_t> d_ent_snp, d_order;
@@ -435,6 +436,7 @@ void fill_scan_params(dmx_ctx* c, ScanParams* p) {
   for (const TaskType& t : c->tt)
     if (!(t.flags & TF_TRI)) p->has_rect = 1;
   p->entf_head = c->d_entf_head.p; p->entf_plane = c->d_entf_plane.p; p->entf_pstride = (c->E + NB) * FPLANE;
+  p->snp_perm = c->d_snp_perm.p; p->cell_na = c->d_cell_na.p;
   p->cell_ptr = c->d_cell_ptr.p; p->cell_order = c->d_order.p; p->tt = c->d_tt.p; p->parts = c->d_parts.p;
   p->row0 = c->d_row0.p; p->singA = c->d_singA.p; p->lb = c->d_lb.p; p->p1 = c->d_p1.p;
   p->p1_0 = c->d_p1_0.p; p->l00 = c->d_l00.p; p->dense = nullptr;
@@ -829,6 +831,7 @@ void dmx_destroy(dmx_ctx* c) {
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   c->d_terms.release(); c->d_ents.release(); c->d_entf_head.release(); c->d_entf_plane.release();
+  c->d_perm.release(); c->d_snp_perm.release(); c->d_cell_na.release();
   c->d_gp.release(); c->d_gprow.release(); c->d_entq.release(); c->d_row0.release(); c->d_singA.release();
   c->d_lb.release(); c->d_p1.release(); c->d_p1_0.release(); c->d_l00.release(); c->d_sing.release();
   c->d_dense.release(); c->d_cell_ptr.release(); c->d_ent_ptr.release(); c->d_ent_snp.release();
@@ -1038,6 +1041,13 @@ int enqueue_chunk(dmx_ctx* c, const Chunk& ck, const ScanParams& sp0, bool dev_r
   eq.entf_head = fp32 ? c->d_entf_head.p : nullptr;
   eq.entf_plane = fp32 ? c->d_entf_plane.p : nullptr;
   eq.entf_pstride = pstride;
+  eq.perm = fp32 ? c->d_perm.p : nullptr;
+  eq.snp_perm = fp32 ? c->d_snp_perm.p : nullptr;
+  if (fp32 && ck.c1 > ck.c0) {
+    // entry classes of the chunk's cells (affine entries first in the fp32 tables)
+    CU(launch_classify(c->d_cell_ptr.p, c->d_ent_ptr.p, c->d_reads.p, ck.c0, ck.c1, c->d_perm.p, c->d_cell_na.p, c->stream));
+    c->st.gpu_launches += 1;
+  }
   memcpy(eq.pu, c->pg.pu, sizeof(double) * c->pg.U);
   {
     // record layout: GL[3] (written by the kernel), f[3] = Q'[0][l][0] of a separable plane 0, then per dense
@@ -1159,6 +1169,7 @@ int run_path(dmx_ctx* c, bool pipelined) {
   if (fp32) {
     CU(c->d_entf_head.reserve((size_t)(c->E + NB) * FHEAD));
     CU(c->d_entf_plane.reserve((size_t)pstride * std::max(nd, 1)));
+    CU(c->d_perm.reserve((size_t)c->E + 1)); CU(c->d_snp_perm.reserve((size_t)c->E + NB)); CU(c->d_cell_na.reserve((size_t)nc + 1));
   }
   CU(c->d_parts.reserve((size_t)nact * T + 1));
   CU(c->d_row0.reserve((size_t)nc * nA * nv + 1)); CU(c->d_singA.reserve((size_t)nc * nv + 1));

@@ -34,10 +34,22 @@ constexpr int F_NCW = 9;       // consumer warps: 36 tile positions of the 64 x 
 constexpr int F_NTW = DMX_F_NTW;   // transform warps (whole stages, taken dynamically)
 constexpr int F_NLOAD = 2;     // loader warps (stages round-robin); the raw ring sizes are multiples of it, which keeps one
                                // producer and one consumer warp per ring slot (mbarrier parity waits must not alias)
-constexpr int F_S_PROC = 8;    // stages of the processed ring
+#ifndef DMX_S_PROC
+#define DMX_S_PROC 8
+#endif
+constexpr int F_S_PROC = DMX_S_PROC;    // stages of the processed ring
 constexpr int F_PEEL_STAGES = 4;   // underflow check period (stages = entries per thread)
 constexpr int FHEAD = 8;       // floats per entry in the fp32 head table: GL[3], f[3] (separable plane), 2 pad
 constexpr int FPLANE = 12;     // floats per entry and dense plane in the fp32 plane tables: Q'[3][3], 3 pad
+// Entry classes of the fp32 scan.  An entry with at most one informative read (allele 0 or 1) has a read likelihood
+// that is AFFINE in the mixing proportion p(n,l,m) (cmd_cram_demuxlet.cpp:613,:625), hence in (l, m); with the
+// genotype vectors normalised to sum 1 the bilinear form collapses to S'[j][k] = X_j + Y_k, X_j = h + cj * D_j,
+// Y_k = h + ck * D_k, D = expected dosage of the read's allele (all terms positive).  Such "affine" entries (4 in 5 of
+// a droplet pileup) are moved to the front of their cell in the fp32 tables and scanned in stages of their own: one
+// add and one multiply per hypothesis instead of a K = 3 dot product.  Their fp32 records:
+//   head   h1 c1 (pass 1, :455-458)  hs cs (separable plane)  flag (1: ref read, D = ref dosage)  3 pad
+//   plane  h cj ck, 9 pad
+constexpr int A_BLK4_FLT = 36; // floats per 4-sample block of an affine stage in the processed ring: 8 entries x 4 + pad
 constexpr int MAX_CAND = 8;    // near-tie candidates kept per task / per cell
 constexpr int MAX_U = DMX_MAX_ALPHA * 6 + 3;   // distinct mixing proportions p(n,l,m)
 
@@ -77,7 +89,7 @@ static_assert(sizeof(TaskType) == 16, "TaskType layout");
 // partial reduction of one task over its hypotheses
 struct Part {
   double m_all;        // max llk over all hypotheses of the task (incl. j == k)
-  double sd;           // sum_{j != k} exp(llk - m_all) (both orders counted for TF_SYM)
+  double sd;           // sum_{j != k} exp(llk - best_v) (both orders counted for TF_SYM)
   double best_v;       // max llk over j != k
   int32_t ncand;       // hypotheses within eps of best_v (may exceed MAX_CAND: overflow)
   int32_t pad;
@@ -114,6 +126,8 @@ struct ScanParams {
   int64_t entf_pstride;        // floats between consecutive planes
   int32_t has_rect;            // the task list has rectangular tasks (k-side rows needed)
   int32_t f_sraw, f_rawslot, f_off_fh;   // fp32 scan raw ring geometry (filled in by launch_pair_scan)
+  const int32_t* snp_perm;     // [E] SNP id of the entry at each position of the class-sorted fp32 tables
+  const int32_t* cell_na;      // [ncells] affine entries of the cell (they come first in the fp32 tables)
   const int64_t* cell_ptr;     // [ncells+1]
   const int32_t* cell_order;   // [nactive] cell ids, scheduled order
   const TaskType* tt;          // [T]
@@ -191,6 +205,8 @@ struct EntqParams {
   float* entf_head;            // [E][FHEAD] or null
   float* entf_plane;           // [nd][entf_pstride]
   int64_t entf_pstride;
+  const int32_t* perm;         // [E] position of entry e in the class-sorted fp32 tables (classify_kernel)
+  int32_t* snp_perm;           // [E] out: SNP id by position
   double* ents;                // [E][2 + nd]: the entry's factors of llk0s (:459), llks00 of a separable plane 0, and
                                // llks00[n] of every dense plane (:700-709); summed per cell by cell_scalars_kernel
   double pu[MAX_U];            // distinct p values (cmd_cram_demuxlet.cpp:613)
@@ -230,6 +246,10 @@ int launch_field(const FieldParams& p, int sm_count, void* stream);
 // host-callable launchers (dmx_kernels.cu); all return a cudaError_t as int
 int launch_gprow(const float* gp_flat, float* gp_rows, int64_t nsnps, int nv, int nvp, void* stream);
 int launch_entq(const EntqParams& p, void* stream);
+// entry classes of cells [c0, c1): perm[e] = position of entry e inside its cell's block with the affine entries
+// (<= 1 informative read) first, both classes in entry order; cell_na[cell] = number of affine entries
+int launch_classify(const int64_t* cell_ptr, const int64_t* ent_ptr, const uint16_t* reads, int64_t c0, int64_t c1,
+                    int32_t* perm, int32_t* cell_na, void* stream);
 int launch_pair_scan(const ScanParams& p, const ScanMaps& tm, bool fp32, void* stream);
 int launch_cell_scalars(const CellScalarParams& p, int64_t nactive, void* stream);
 int launch_merge(const MergeParams& p, int64_t nactive, void* stream);

@@ -14,9 +14,11 @@
 // w_k[l] = sum_m Q'[l][m] gp_k[m] (3 FMA per hypothesis instead of 9 terms over a precomputed table)
 // and sum-of-logs is replaced by the log of a running product whose exponent is peeled off into an
 // integer every FLUSH_STAGES stages (1 MUL per hypothesis and entry, one log per hypothesis and cell).
-// A CTA is warp specialised: 1 loader warp issues cp.async.bulk (TMA) copies of the gathered GP rows
-// and entry tables into a raw ring; 2 transform warps turn them into (a, w) vectors in a processed ring;
-// 5 consumer warps each own 4 x 4 tiles of hypotheses in registers.  Rings are mbarrier pipelines.
+// A CTA is warp specialised: loader warps issue TMA copies (tile::gather4 of the GP rows, bulk copies of the entry
+// tables) into a raw ring; transform warps turn them into operand blocks in a processed ring; consumer warps own
+// 8 x 8 tiles of hypotheses in registers (fp32 scan: 2 loader, 4 transform, 9 consumer warps and one accumulator
+// warp for the per-sample products; fp64 scan: two pipelines of 1 loader, 2 transform and 5 DMMA consumer warps).
+// Rings are mbarrier pipelines.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -127,19 +129,50 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+#ifndef DMX_WAIT_HINT_NS
+#define DMX_WAIT_HINT_NS 2000
+#endif
+#ifndef DMX_WAIT_SLEEP_NS
+#define DMX_WAIT_SLEEP_NS 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#if DMX_WAIT_HINT_NS > 0
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 2000;\n\t"   // suspend-time hint (ns): fewer retry issues
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"   // suspend-time hint (ns): fewer retry issues
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "n"(DMX_WAIT_HINT_NS)
+      : "memory");
+#else
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
+#if DMX_WAIT_SLEEP_NS > 0
+    __nanosleep(DMX_WAIT_SLEEP_NS);   // a waiting warp must not eat the issue slots of the warps it waits for
+#endif
+  }
+}
+// wait of a role that runs far ahead of its consumers (loaders): sleep between polls instead of competing for the
+// issue slots of the warps that do the work
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+#ifndef DMX_RELAX_NS
+#define DMX_RELAX_NS 256
+#endif
+  while (!mbar_try_wait(bar, parity)) {
+#if DMX_RELAX_NS > 0
+    __nanosleep(DMX_RELAX_NS);
+#endif
   }
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -253,7 +286,8 @@ int launch_gprow(const float* gp_flat, float* gp_rows, int64_t nsnps, int nv, in
 // ---------------------------------------------------------------------------------------------
 // GETV(slot): value of record slot `slot` (GL, f and Q' are already final when this runs)
 template <class GETV>
-__device__ __forceinline__ void entq_emit(const EntqParams& p, int64_t e, double* __restrict__ out, GETV getv) {
+__device__ __forceinline__ void entq_emit(const EntqParams& p, int64_t e, double* __restrict__ out, int nvr, uint32_t al1,
+                                          GETV getv) {
   // per-entry factors of the sample-independent likelihoods (they need only this record and the cohort mean gp0 of
   // the entry's SNP): llk0s (:459) -> head[6], llks00 of a separable plane 0 -> head[7], llks00[n] (:700-709) -> slot 9
   // of each dense plane; then the fp32 copies
@@ -272,10 +306,23 @@ __device__ __forceinline__ void entq_emit(const EntqParams& p, int64_t e, double
   double* sc = p.ents + e * (2 + p.nd);
   sc[0] = s0;
   sc[1] = s1;
+  // fp32 tables of the fp32 scan, class-sorted inside the cell (affine entries first)
+  const bool affine = nvr <= 1;
+  const bool refread = al1 == 0;           // the informative read shows the reference allele: D = ref dosage
+  const int64_t pos = p.perm ? e + (int64_t)__ldg(p.perm + e) : e;
   if (p.entf_head) {
-    float4* fh = reinterpret_cast<float4*>(p.entf_head + e * FHEAD);
-    fh[0] = make_float4((float)g0, (float)g1, (float)g2, (float)f0);
-    fh[1] = make_float4((float)f1, (float)f2, 0.f, 0.f);
+    if (p.snp_perm) p.snp_perm[pos] = __ldg(p.ent_snp + e);
+    float4* fh = reinterpret_cast<float4*>(p.entf_head + pos * FHEAD);
+    if (affine) {
+      // value at the dosage-0 corner and half the difference to the dosage-2 corner (>= 0 by construction)
+      const double h1 = refread ? g2 : g0, c1 = 0.5 * (refread ? g0 - g2 : g2 - g0);
+      const double hs = refread ? f2 : f0, cs = 0.5 * (refread ? f0 - f2 : f2 - f0);
+      fh[0] = make_float4((float)h1, (float)c1, (float)hs, (float)cs);
+      fh[1] = make_float4(refread ? 1.f : 0.f, 0.f, 0.f, 0.f);
+    } else {
+      fh[0] = make_float4((float)g0, (float)g1, (float)g2, (float)f0);
+      fh[1] = make_float4((float)f1, (float)f2, 0.f, 0.f);
+    }
   }
   for (int d = 0; d < p.nd; ++d) {
     double* q = out + QHEAD + QPLANE * d;
@@ -289,10 +336,18 @@ __device__ __forceinline__ void entq_emit(const EntqParams& p, int64_t e, double
     q[9] = s2;
     sc[2 + d] = s2;
     if (p.entf_plane) {
-      float4* fp = reinterpret_cast<float4*>(p.entf_plane + d * p.entf_pstride + e * FPLANE);
-      fp[0] = make_float4((float)Q[0], (float)Q[1], (float)Q[2], (float)Q[3]);
-      fp[1] = make_float4((float)Q[4], (float)Q[5], (float)Q[6], (float)Q[7]);
-      fp[2] = make_float4((float)Q[8], 0.f, 0.f, 0.f);
+      float4* fp = reinterpret_cast<float4*>(p.entf_plane + d * p.entf_pstride + pos * FPLANE);
+      if (affine) {
+        // Q'[l][m] = q + cl * (dosage of l) + cm * (dosage of m) around the corner where the read's allele is absent
+        const double q = refread ? Q[8] : Q[0];
+        const double cl = 0.5 * (refread ? Q[2] - Q[8] : Q[6] - Q[0]);   // along l (j side)
+        const double cm = 0.5 * (refread ? Q[6] - Q[8] : Q[2] - Q[0]);   // along m (k side)
+        fp[0] = make_float4((float)(0.5 * q), (float)cl, (float)cm, 0.f);
+      } else {
+        fp[0] = make_float4((float)Q[0], (float)Q[1], (float)Q[2], (float)Q[3]);
+        fp[1] = make_float4((float)Q[4], (float)Q[5], (float)Q[6], (float)Q[7]);
+        fp[2] = make_float4((float)Q[8], 0.f, 0.f, 0.f);
+      }
     }
   }
 }
@@ -315,11 +370,15 @@ __global__ void __launch_bounds__(256) entq_kernel(const __grid_constant__ EntqP
     P[v] = 1.0;
   }
   double G0 = 1.0, G1 = 1.0, G2 = 1.0;
+  int nvr = 0;
+  uint32_t al1 = 1;
   const int64_t r0 = p.ent_ptr[e], r1 = p.ent_ptr[e + 1];
   for (int64_t r = r0; r < r1; ++r) {
     const uint32_t rd = p.reads[r];
     const uint32_t al = rd >> 8, bq = rd & 0xff;
     if (al == 2) continue;                                                  // :435, :604
+    ++nvr;
+    al1 = al;
     const double err = c_err[bq];
     const double e3 = __ddiv_rn(err, 3.0);
     const double mat = __dsub_rn(1.0, err);
@@ -372,7 +431,7 @@ __global__ void __launch_bounds__(256) entq_kernel(const __grid_constant__ EntqP
     out[2] = __ddiv_rn(G2, sm);
   }
   __syncwarp(gmask);
-  if (sub == 0) entq_emit(p, e, out, [&](int slot) { return __ldcg(out + slot); });
+  if (sub == 0) entq_emit(p, e, out, nvr, al1, [&](int slot) { return __ldcg(out + slot); });
 }
 
 // one thread per entry: the U <= UMAX distinct values live in registers (independent chains: the divisions of a read
@@ -394,11 +453,15 @@ __global__ void __launch_bounds__(128) entq1_kernel(const __grid_constant__ Entq
     P[v] = 1.0;
   }
   double G0 = 1.0, G1 = 1.0, G2 = 1.0;
+  int nvr = 0;
+  uint32_t al1 = 1;
   const int64_t r0 = p.ent_ptr[e], r1 = p.ent_ptr[e + 1];
   for (int64_t r = r0; r < r1; ++r) {
     const uint32_t rd = p.reads[r];
     const uint32_t al = rd >> 8, bq = rd & 0xff;
     if (al == 2) continue;                                                  // :435, :604
+    ++nvr;
+    al1 = al;
     const double err = s_err[bq];
     const double e3 = s_err3[bq];                                           // err / 3 (same rounded quotient)
     const double mat = __dsub_rn(1.0, err);
@@ -446,7 +509,50 @@ __global__ void __launch_bounds__(128) entq1_kernel(const __grid_constant__ Entq
       const int s = QHEAD + QPLANE * d + i;
       out[s] = s_val[p.slot_u[s]][tid];
     }
-  entq_emit(p, e, out, [&](int slot) { return slot == 0 ? G0 : (slot == 1 ? G1 : (slot == 2 ? G2 : s_val[p.slot_u[slot]][tid])); });
+  entq_emit(p, e, out, nvr, al1, [&](int slot) { return slot == 0 ? G0 : (slot == 1 ? G1 : (slot == 2 ? G2 : s_val[p.slot_u[slot]][tid])); });
+}
+
+// entry classes: one warp per cell, two passes over its entries (count the affine ones, then hand out positions)
+__global__ void __launch_bounds__(128) classify_kernel(const int64_t* __restrict__ cell_ptr,
+                                                       const int64_t* __restrict__ ent_ptr,
+                                                       const uint16_t* __restrict__ reads, int64_t c0, int64_t c1,
+                                                       int32_t* __restrict__ perm, int32_t* __restrict__ cell_na) {
+  const int lane = threadIdx.x & 31;
+  const int64_t cell = c0 + (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (cell >= c1) return;
+  const int64_t e0 = cell_ptr[cell], e1 = cell_ptr[cell + 1];
+  auto is_affine = [&](int64_t e) {
+    int nvr = 0;
+    for (int64_t r = ent_ptr[e]; r < ent_ptr[e + 1]; ++r) nvr += (reads[r] >> 8) != 2;
+    return nvr <= 1;
+  };
+  int na = 0;
+  for (int64_t b = e0; b < e1; b += 32) {
+    const int64_t e = b + lane;
+    na += __popc(__ballot_sync(0xffffffffu, e < e1 && is_affine(e)));
+  }
+  int ra = 0, rg = 0;
+  for (int64_t b = e0; b < e1; b += 32) {
+    const int64_t e = b + lane;
+    const bool in = e < e1, aff = in && is_affine(e);
+    const unsigned ma = __ballot_sync(0xffffffffu, aff), mg = __ballot_sync(0xffffffffu, in && !aff);
+    const unsigned lt = (1u << lane) - 1u;
+    if (in) {
+      const int64_t pos = aff ? e0 + ra + __popc(ma & lt) : e0 + na + rg + __popc(mg & lt);
+      perm[e] = (int32_t)(pos - e);
+    }
+    ra += __popc(ma);
+    rg += __popc(mg);
+  }
+  if (lane == 0) cell_na[cell] = na;
+}
+
+int launch_classify(const int64_t* cell_ptr, const int64_t* ent_ptr, const uint16_t* reads, int64_t c0, int64_t c1,
+                    int32_t* perm, int32_t* cell_na, void* stream) {
+  if (c1 <= c0) return 0;
+  classify_kernel<<<(unsigned)((c1 - c0 + 3) / 4), 128, 0, (cudaStream_t)stream>>>(cell_ptr, ent_ptr, reads, c0, c1, perm,
+                                                                                   cell_na);
+  return (int)cudaGetLastError();
 }
 
 int launch_entq(const EntqParams& p, void* stream) {
@@ -792,16 +898,60 @@ __device__ __forceinline__ void transform_role(const ScanParams& p, const Pipe& 
 // The k-side rows exist only when the task list has rectangular tasks (nv > 64 or a non-symmetric plane); without
 // them a stage is 7040 B instead of 10368 B and the same shared memory holds 12 raw stages instead of 8
 // (ScanParams::f_sraw / f_rawslot / f_off_fh, set by launch_pair_scan).
+//
+// The fp32 tables are class-sorted inside a cell (classify_kernel / entq): the na affine entries first, then the
+// general ones; a task walks ceil(na / NB) affine stages and then ceil((n - na) / NB) general stages, every stage
+// holding entries of one class only.
 constexpr uint32_t F_OFF_GPJ = 0;
 constexpr uint32_t F_OFF_GPK = F_OFF_GPJ + NB * GROWJ;
 constexpr uint32_t F_REC_BYTES = NB * (FHEAD + FPLANE) * 4;                    // 640
 constexpr uint32_t F_RAW_SLOT_RECT = F_OFF_GPK + NB * GROWK + F_REC_BYTES;     // 10368 B
 constexpr uint32_t F_RAW_SLOT_TRI = F_OFF_GPK + F_REC_BYTES;                   // 7040 B
-constexpr uint32_t F_S_RAW_RECT = 8, F_S_RAW_TRI = 12;
-constexpr uint32_t F_RAW_BYTES = F_S_RAW_TRI * F_RAW_SLOT_TRI;                 // 84480 B
+#ifndef DMX_S_RAW_TRI
+#define DMX_S_RAW_TRI 12
+#endif
+constexpr uint32_t F_S_RAW_RECT = 8, F_S_RAW_TRI = DMX_S_RAW_TRI;
+constexpr uint32_t F_RAW_BYTES = 12 * F_RAW_SLOT_TRI;                          // 84480 B
 static_assert(F_OFF_GPK % 128 == 0 && F_RAW_SLOT_RECT % 128 == 0 && F_RAW_SLOT_TRI % 128 == 0 &&
               F_S_RAW_RECT * F_RAW_SLOT_RECT <= F_RAW_BYTES && F_S_RAW_TRI <= 12, "raw ring layout");
 constexpr uint32_t F_SMEM_NOTS = SLOT_CTRL + F_RAW_BYTES + F_S_PROC * F_PROC_SLOT;   // + TScratch
+constexpr uint32_t A_SIDE_FLT = (BLK / 4) * A_BLK4_FLT;                        // floats per side of an affine stage (576)
+static_assert(2 * A_SIDE_FLT * 4 <= F_PROC_SLOT, "an affine stage fits a processed-ring slot");
+
+struct TaskInfoF {
+  int64_t aidx;
+  int tti, cell, nst;
+  int64_t e0, e1;
+  int na, nstA;      // affine entries / stages of the cell
+};
+
+__device__ __forceinline__ bool next_task_f32(const ScanParams& p, int r, int u, int NS, TaskInfoF* t) {
+  const int64_t g = (int64_t)r * NS + ((r & 1) ? (NS - 1 - u) : u);   // snake order over size-sorted tasks
+  if (g >= p.ntasks) return false;
+  t->aidx = g / p.T;
+  t->tti = (int)(g - t->aidx * p.T);
+  t->cell = __ldg(p.cell_order + t->aidx);
+  t->e0 = __ldg(p.cell_ptr + t->cell);
+  t->e1 = __ldg(p.cell_ptr + t->cell + 1);
+  t->na = __ldg(p.cell_na + t->cell);
+  t->nstA = (t->na + NB - 1) / NB;
+  t->nst = t->nstA + ((int)(t->e1 - t->e0) - t->na + NB - 1) / NB;
+  return true;
+}
+
+// entries of stage `it`: first position in the class-sorted tables, number of real entries, class
+__device__ __forceinline__ void stage_span(const TaskInfoF& t, int it, int64_t* eb, int* nvalid, bool* affine) {
+  if (it < t.nstA) {
+    *affine = true;
+    *eb = t.e0 + (int64_t)it * NB;
+    *nvalid = min(NB, t.na - it * NB);
+  } else {
+    const int g = it - t.nstA;
+    *affine = false;
+    *eb = t.e0 + t.na + (int64_t)g * NB;
+    *nvalid = min(NB, (int)(t.e1 - t.e0) - t.na - g * NB);
+  }
+}
 
 __device__ __forceinline__ void bulk_g2s_elect(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile(
@@ -820,43 +970,49 @@ __device__ __forceinline__ void loader_role_f32(const ScanParams& p, const ScanM
   const uint32_t raw0 = smem_u32(pp.raw_base), full0 = smem_u32(pp.raw_full);
   const uint32_t sraw = (uint32_t)p.f_sraw, rawslot = (uint32_t)p.f_rawslot, off_fh = (uint32_t)p.f_off_fh;
   uint32_t gbase = 0;   // stages of the tasks before this one
-  TaskInfo ti;
-  for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
+  TaskInfoF ti;
+  for (int r = 0; next_task_f32(p, r, u, NS, &ti); ++r) {
     const TaskType tt = p.tt[ti.tti];
     const bool same = tt.flags & TF_TRI;
     const int colj = tt.j0 * 3, colk = tt.k0 * 3;
     const float* fplane = p.entf_plane + (int64_t)((tt.qoff - QHEAD) / QPLANE) * p.entf_pstride;
-    const uint32_t bytes = (uint32_t)NB * (GROWJ + (same ? 0u : GROWK)) + F_REC_BYTES;
+    const bool nogp = (p.dbg & 32) != 0;   // timing experiment: no GP gathers
+    const uint32_t bytes = (nogp ? 0u : (uint32_t)NB * (GROWJ + (same ? 0u : GROWK))) + F_REC_BYTES;
     int it = (int)((F_NLOAD + lid - gbase % F_NLOAD) % F_NLOAD);   // first stage of this task that is ours
     // SNP ids of a stage are fetched by lanes 0..7 one own stage ahead
-    int snp_nxt = 0;
-    if (it < ti.nst) {
-      const int64_t e = ti.e0 + (int64_t)it * NB + lane;
-      snp_nxt = (lane < NB && e < ti.e1) ? __ldg(p.ent_snp + e) : 0;
-    }
+    auto fetch = [&](int st) -> int {
+      int64_t eb;
+      int nvalid;
+      bool aff;
+      stage_span(ti, st, &eb, &nvalid, &aff);
+      return lane < nvalid ? __ldg(p.snp_perm + eb + lane) : 0;
+    };
+    int snp_nxt = it < ti.nst ? fetch(it) : 0;
     for (; it < ti.nst; it += F_NLOAD) {
       const uint32_t git = gbase + (uint32_t)it;
       const uint32_t rslot = git % sraw;
       const uint32_t ph = (git / sraw) & 1u;
-      const int64_t eb = ti.e0 + (int64_t)it * NB;
+      int64_t eb;
+      int nvalid;
+      bool aff;
+      stage_span(ti, it, &eb, &nvalid, &aff);
       const int snp_cur = snp_nxt;
-      if (it + F_NLOAD < ti.nst) {
-        const int64_t e = eb + (int64_t)F_NLOAD * NB + lane;
-        snp_nxt = (lane < NB && e < ti.e1) ? __ldg(p.ent_snp + e) : 0;
-      }
+      if (it + F_NLOAD < ti.nst) snp_nxt = fetch(it + F_NLOAD);
       int s[NB];
 #pragma unroll
       for (int i = 0; i < NB; ++i) s[i] = __shfl_sync(0xffffffffu, snp_cur, i);
-      mbar_wait(&pp.raw_empty[rslot], ph ^ 1u);
+      mbar_wait_relaxed(&pp.raw_empty[rslot], ph ^ 1u);
       const uint32_t rs = raw0 + rslot * rawslot, bar = full0 + rslot * 8u;
       mbar_expect_tx_elect(bar, bytes);
-      tma_gather4_elect(rs + F_OFF_GPJ, &tm.gpj, colj, s[0], s[1], s[2], s[3], bar);
-      tma_gather4_elect(rs + F_OFF_GPJ + 4 * GROWJ, &tm.gpj, colj, s[4], s[5], s[6], s[7], bar);
-      if (!same) {
-        tma_gather4_elect(rs + F_OFF_GPK, &tm.gpk, colk, s[0], s[1], s[2], s[3], bar);
-        tma_gather4_elect(rs + F_OFF_GPK + 4 * GROWK, &tm.gpk, colk, s[4], s[5], s[6], s[7], bar);
+      if (!nogp) {
+        tma_gather4_elect(rs + F_OFF_GPJ, &tm.gpj, colj, s[0], s[1], s[2], s[3], bar);
+        tma_gather4_elect(rs + F_OFF_GPJ + 4 * GROWJ, &tm.gpj, colj, s[4], s[5], s[6], s[7], bar);
+        if (!same) {
+          tma_gather4_elect(rs + F_OFF_GPK, &tm.gpk, colk, s[0], s[1], s[2], s[3], bar);
+          tma_gather4_elect(rs + F_OFF_GPK + 4 * GROWK, &tm.gpk, colk, s[4], s[5], s[6], s[7], bar);
+        }
       }
-      // entry slots beyond the cell's last entry read the next cell's records (the tables have NB records of slack)
+      // entry slots beyond the stage's last entry read the records that follow (the tables have NB records of slack)
       bulk_g2s_elect(rs + off_fh, p.entf_head + eb * FHEAD, NB * FHEAD * 4, bar);
       bulk_g2s_elect(rs + off_fh + NB * FHEAD * 4, fplane + eb * FPLANE, NB * FPLANE * 4, bar);
     }
@@ -864,17 +1020,25 @@ __device__ __forceinline__ void loader_role_f32(const ScanParams& p, const ScanM
   }
 }
 
-// F_NTW = 4 transform warps, each owning every fourth stage.  A lane serves one 4-sample block q = lane % 16 of each
-// side for the four entries e = lane / 16 + {0, 2, 4, 6} of its stage, so everything moves as 16-byte vectors: the 12
-// floats of its samples' GP rows (3 LDS.128, 48-byte lane stride: conflict free), the entry's fp32 record (5
-// LDS.128, two distinct addresses per warp), and the (a, w) blocks of the processed ring (3 + 3 STS.128, conflict
-// free by the F_BLK4_FLT padding).  w_k[l] = sum_m Q'[l][m] gp_k[m] in fp32.  The per-sample extras (singlet factor
-// of the separable plane, row sums, pass 1, pairs with sample 0) leave the transform warps as per-stage products
-// (four entries per lane) in a products ring; the accumulator warp multiplies them up in stage order, so the result
-// does not depend on which transform warp happened to take which stage.
+// F_NTW = 4 transform warps take whole stages.  A lane serves one 4-sample block q = lane % 16 of each side for the
+// four entries e = lane / 16 + {0, 2, 4, 6} of its stage, so everything moves as 16-byte vectors: the 12 floats of its
+// samples' GP rows (3 LDS.128, 48-byte lane stride: conflict free), the entry's fp32 record, and the operand blocks
+// of the processed ring.  Every genotype vector is normalised to sum 1 here (a_hat = g / s, s = g0 + g1 + g2 ~ 1 up to
+// float rounding), and the product of the sums s is carried as a per-sample quantity of its own (lb); the consumers'
+// S'[j][k] is the likelihood over s_j s_k and the epilogues add lb[j] + lb[k] back.
+//   general stage  (a_hat, w) blocks: w_k[l] = sum_m Q'[l][m] a_hat_k[m]; consumers form S' = a_hat_j . w_k
+//   affine stage   X_j = h + cj D_j, Y_k = h + ck D_k, D = dosage of the read's allele under a_hat; consumers form
+//                  S' = X_j + Y_k
+// The per-sample extras (singlet factor of the separable plane, pass 1, pairs with sample 0) and the sums s leave the
+// transform warps as per-stage products (four entries per lane) in a products ring; the accumulator warp multiplies
+// them up in stage order, so the result does not depend on which transform warp happened to take which stage.
+constexpr int NQ = 5;   // per-sample quantities: PA (separable plane), PB (sums s, k side), P1 (pass 1), P0 (pairs with sample 0),
+                        // PJ (sums s, j side of a rectangular task)
 struct TScratch {
-  float prod[F_S_PROC][2][4][BLK];   // products ring: [stage slot][entry half][PA, PB, P1, P0][sample], the stage's
+  float prod[F_S_PROC][2][NQ][BLK];  // products ring: [stage slot][entry half][quantity][sample], the stage's
                                      // factors of every per-sample running product (transform -> accumulator warp)
+  double lb[2][2][BLK];              // [task parity][j side, k side][sample]: sum log s of the finished task
+                                     // (accumulator -> consumer epilogue)
   unsigned next_stage;               // stage counter of the CTA: transform warps take stages as they become free
 };
 constexpr uint32_t F_TS_BYTES = (sizeof(TScratch) + 127) / 128 * 128;
@@ -886,23 +1050,53 @@ __device__ __forceinline__ void store_neutral_quad(float* dst) {   // four (1, 0
   d[2] = make_float4(0.f, 1.f, 0.f, 0.f);
 }
 
+// 1 / s for a row sum (0 for the all-zero padding samples)
+// (one MUFU.RCP, ~1 ulp; an all-zero padding sample gives 0 * 1e30 = 0 downstream, never inf or NaN)
+__device__ __forceinline__ float rcp_sum(float s) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(s, 1e-30f)));
+  return r;
+}
+
+// normalise the four genotype vectors of a block in place; sums in s[4]
+__device__ __forceinline__ void normalise_quad(float (&g)[12], float (&s)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    s[i] = (g[3 * i] + g[3 * i + 1]) + g[3 * i + 2];
+    const float rs = rcp_sum(s[i]);
+    g[3 * i] *= rs; g[3 * i + 1] *= rs; g[3 * i + 2] *= rs;
+  }
+}
+__device__ __forceinline__ void load_quad(const unsigned char* src, float (&g)[12]) {
+  const float4* p4 = reinterpret_cast<const float4*>(src);
+  const float4 x = p4[0], y = p4[1], z = p4[2];
+  g[0] = x.x; g[1] = x.y; g[2] = x.z; g[3] = x.w; g[4] = y.x; g[5] = y.y; g[6] = y.z; g[7] = y.w;
+  g[8] = z.x; g[9] = z.y; g[10] = z.z; g[11] = z.w;
+}
+__device__ __forceinline__ void store_quad(float* dst, const float (&g)[12]) {
+  float4* d = reinterpret_cast<float4*>(dst);
+  d[0] = make_float4(g[0], g[1], g[2], g[3]);
+  d[1] = make_float4(g[4], g[5], g[6], g[7]);
+  d[2] = make_float4(g[8], g[9], g[10], g[11]);
+}
+
+// per-stage factors of the per-sample running products, four samples per lane
+struct Fac { float PA[4], PB[4], P1[4], P0[4], PJ[4]; };
+
+// ---- general stage ---------------------------------------------------------------------------------------------------
 // ROW0: 0 none, 1 symmetric plane (P0 of k-sample x *= a_0 . w_x), 2 full plane (P0 of j-sample x *= a_x . w_0)
 template <bool SAME, bool EXTRAS, int ROW0>
 __device__ __forceinline__ void transform_quad_f32(const unsigned char* __restrict__ rs, uint32_t off_fh,
-                                                   float* __restrict__ pf, int e, int q, bool jq, bool kq,
-                                                   float (&PA)[4], float (&PB)[4], float (&P1)[4], float (&P0)[4]) {
+                                                   float* __restrict__ pf, int e, int q, bool jq, bool kq, Fac& F) {
   const uint32_t off_fp = off_fh + NB * FHEAD * 4;
   float* af = pf + q * F_BLK4_FLT + e * 12;
   float* wf = af + F_SIDE_FLT;
-  float g[12];
+  float g[12], sk[4];
+  const float4* qp = reinterpret_cast<const float4*>(rs + off_fp + e * (FPLANE * 4));
   if (SAME || q < BLK_RECT_K / 4) {
     if (kq) {
-      const float4* src = reinterpret_cast<const float4*>(
-          rs + (SAME ? F_OFF_GPJ + e * GROWJ : F_OFF_GPK + e * GROWK) + GPFX * 4 + q * 48);
-      const float4 x = src[0], y = src[1], z = src[2];
-      g[0] = x.x; g[1] = x.y; g[2] = x.z; g[3] = x.w; g[4] = y.x; g[5] = y.y; g[6] = y.z; g[7] = y.w;
-      g[8] = z.x; g[9] = z.y; g[10] = z.z; g[11] = z.w;
-      const float4* qp = reinterpret_cast<const float4*>(rs + off_fp + e * (FPLANE * 4));
+      load_quad(rs + (SAME ? F_OFF_GPJ + e * GROWJ : F_OFF_GPK + e * GROWK) + GPFX * 4 + q * 48, g);
+      normalise_quad(g, sk);
       const float4 qa = qp[0], qb = qp[1];       // Q'[l][m] row-major: (00 01 02 10) (11 12 20 21) (22 . . .)
       const float q22 = reinterpret_cast<const float*>(qp + 2)[0];
       float w[12];
@@ -912,6 +1106,7 @@ __device__ __forceinline__ void transform_quad_f32(const unsigned char* __restri
         w[3 * i + 0] = fmaf(qa.z, f2, fmaf(qa.y, f1, qa.x * f0));
         w[3 * i + 1] = fmaf(qb.y, f2, fmaf(qb.x, f1, qa.w * f0));
         w[3 * i + 2] = fmaf(q22, f2, fmaf(qb.w, f1, qb.z * f0));
+        F.PB[i] *= sk[i];
       }
       if (EXTRAS) {
         const float4* hp = reinterpret_cast<const float4*>(rs + off_fh + e * (FHEAD * 4));
@@ -920,53 +1115,114 @@ __device__ __forceinline__ void transform_quad_f32(const unsigned char* __restri
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float f0 = g[3 * i], f1 = g[3 * i + 1], f2 = g[3 * i + 2];
-          PA[i] *= fmaf(h1.y, f2, fmaf(h1.x, f1, h0.w * f0));
-          PB[i] *= (f0 + f1) + f2;
-          P1[i] *= fmaf(h0.z, f2, fmaf(h0.y, f1, h0.x * f0));
+          F.PA[i] *= fmaf(h1.y, f2, fmaf(h1.x, f1, h0.w * f0));
+          F.P1[i] *= fmaf(h0.z, f2, fmaf(h0.y, f1, h0.x * f0));
         }
       }
       if (ROW0 == 1) {   // pairs (0, x): sample 0 is the first sample of the j-side row (j0 == 0)
         const float* a0 = reinterpret_cast<const float*>(rs + F_OFF_GPJ + e * GROWJ + GPFX * 4);
-        const float a00 = a0[0], a01 = a0[1], a02 = a0[2];
+        const float r0 = rcp_sum((a0[0] + a0[1]) + a0[2]);
+        const float a00 = a0[0] * r0, a01 = a0[1] * r0, a02 = a0[2] * r0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) P0[i] *= fmaf(a02, w[3 * i + 2], fmaf(a01, w[3 * i + 1], a00 * w[3 * i]));
+        for (int i = 0; i < 4; ++i) F.P0[i] *= fmaf(a02, w[3 * i + 2], fmaf(a01, w[3 * i + 1], a00 * w[3 * i]));
       }
-      float4* dw = reinterpret_cast<float4*>(wf);
-      dw[0] = make_float4(w[0], w[1], w[2], w[3]);
-      dw[1] = make_float4(w[4], w[5], w[6], w[7]);
-      dw[2] = make_float4(w[8], w[9], w[10], w[11]);
+      store_quad(wf, w);
     } else {
       store_neutral_quad(wf);
     }
   }
   if (jq) {
     if (!SAME) {
-      const float4* src = reinterpret_cast<const float4*>(rs + F_OFF_GPJ + e * GROWJ + GPFX * 4 + q * 48);
-      const float4 x = src[0], y = src[1], z = src[2];
-      float4* da = reinterpret_cast<float4*>(af);
-      da[0] = x; da[1] = y; da[2] = z;
+      float a[12], sj[4];
+      load_quad(rs + F_OFF_GPJ + e * GROWJ + GPFX * 4 + q * 48, a);
+      normalise_quad(a, sj);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) F.PJ[i] *= sj[i];
+      store_quad(af, a);
       if (ROW0 == 2) {   // pairs (x, 0): sample 0 is the first sample of the k-side row (k0 == 0)
         const float* g0p = reinterpret_cast<const float*>(rs + F_OFF_GPK + e * GROWK + GPFX * 4);
-        const float f0 = g0p[0], f1 = g0p[1], f2 = g0p[2];
-        const float4* qp = reinterpret_cast<const float4*>(rs + off_fp + e * (FPLANE * 4));
+        const float r0 = rcp_sum((g0p[0] + g0p[1]) + g0p[2]);
+        const float f0 = g0p[0] * r0, f1 = g0p[1] * r0, f2 = g0p[2] * r0;
         const float4 qa = qp[0], qb = qp[1];
         const float q22 = reinterpret_cast<const float*>(qp + 2)[0];
         const float w0 = fmaf(qa.z, f2, fmaf(qa.y, f1, qa.x * f0));
         const float w1 = fmaf(qb.y, f2, fmaf(qb.x, f1, qa.w * f0));
         const float w2 = fmaf(q22, f2, fmaf(qb.w, f1, qb.z * f0));
-        P0[0] *= fmaf(x.z, w2, fmaf(x.y, w1, x.x * w0));
-        P0[1] *= fmaf(y.y, w2, fmaf(y.x, w1, x.w * w0));
-        P0[2] *= fmaf(z.x, w2, fmaf(y.w, w1, y.z * w0));
-        P0[3] *= fmaf(z.w, w2, fmaf(z.z, w1, z.y * w0));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) F.P0[i] *= fmaf(a[3 * i + 2], w2, fmaf(a[3 * i + 1], w1, a[3 * i] * w0));
       }
     } else {
-      float4* da = reinterpret_cast<float4*>(af);
-      da[0] = make_float4(g[0], g[1], g[2], g[3]);
-      da[1] = make_float4(g[4], g[5], g[6], g[7]);
-      da[2] = make_float4(g[8], g[9], g[10], g[11]);
+      store_quad(af, g);
     }
   } else {
     store_neutral_quad(af);
+  }
+}
+
+// ---- affine stage ----------------------------------------------------------------------------------------------------
+// dosage of the read's allele under the normalised genotype vector: ref read 2 a0 + a1, alt read a1 + 2 a2
+__device__ __forceinline__ float dosage(float g0, float g1, float g2, bool refread, float* s_out) {
+  const float s = (g0 + g1) + g2;
+  *s_out = s;
+  return (refread ? fmaf(2.0f, g0, g1) : fmaf(2.0f, g2, g1)) * rcp_sum(s);
+}
+
+template <bool SAME, bool EXTRAS, int ROW0>
+__device__ __forceinline__ void transform_quad_aff(const unsigned char* __restrict__ rs, uint32_t off_fh,
+                                                   float* __restrict__ pf, int e, int q, bool jq, bool kq, Fac& F) {
+  const uint32_t off_fp = off_fh + NB * FHEAD * 4;
+  const float4* hp = reinterpret_cast<const float4*>(rs + off_fh + e * (FHEAD * 4));
+  const float4 hd = hp[0];                                   // h1 c1 hs cs
+  const bool refread = reinterpret_cast<const float*>(hp + 1)[0] != 0.f;
+  const float4 pl = *reinterpret_cast<const float4*>(rs + off_fp + e * (FPLANE * 4));   // h cj ck
+  float* xf = pf + q * A_BLK4_FLT + e * 4;                   // j side (the only side of a triangular task)
+  float* yf = SAME ? xf : xf + A_SIDE_FLT;
+  if (SAME || q < BLK_RECT_K / 4) {
+    float y[4] = {0.5f, 0.5f, 0.5f, 0.5f};
+    if (kq) {
+      float g[12];
+      load_quad(rs + (SAME ? F_OFF_GPJ + e * GROWJ : F_OFF_GPK + e * GROWK) + GPFX * 4 + q * 48, g);
+      float x0 = 0.f;
+      if (ROW0 == 1) {   // pairs (0, x): sample 0 is the first sample of the j-side row (j0 == 0)
+        const float* a0 = reinterpret_cast<const float*>(rs + F_OFF_GPJ + e * GROWJ + GPFX * 4);
+        float s0;
+        x0 = fmaf(pl.y, dosage(a0[0], a0[1], a0[2], refread, &s0), pl.x);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float s;
+        const float D = dosage(g[3 * i], g[3 * i + 1], g[3 * i + 2], refread, &s);
+        y[i] = fmaf(pl.z, D, pl.x);
+        F.PB[i] *= s;
+        if (EXTRAS) {
+          F.P1[i] *= fmaf(hd.y, D, hd.x);
+          F.PA[i] *= fmaf(hd.w, D, hd.z);
+        }
+        if (ROW0 == 1) F.P0[i] *= x0 + y[i];
+      }
+    }
+    *reinterpret_cast<float4*>(yf) = make_float4(y[0], y[1], y[2], y[3]);
+  }
+  if (!SAME) {
+    float x[4] = {0.5f, 0.5f, 0.5f, 0.5f};
+    if (jq) {
+      float a[12];
+      load_quad(rs + F_OFF_GPJ + e * GROWJ + GPFX * 4 + q * 48, a);
+      float y0 = 0.f;
+      if (ROW0 == 2) {   // pairs (x, 0): sample 0 is the first sample of the k-side row (k0 == 0)
+        const float* g0p = reinterpret_cast<const float*>(rs + F_OFF_GPK + e * GROWK + GPFX * 4);
+        float s0;
+        y0 = fmaf(pl.z, dosage(g0p[0], g0p[1], g0p[2], refread, &s0), pl.x);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float s;
+        x[i] = fmaf(pl.y, dosage(a[3 * i], a[3 * i + 1], a[3 * i + 2], refread, &s), pl.x);
+        F.PJ[i] *= s;
+        if (ROW0 == 2) F.P0[i] *= x[i] + y0;
+      }
+    }
+    *reinterpret_cast<float4*>(xf) = make_float4(x[0], x[1], x[2], x[3]);
   }
 }
 
@@ -979,22 +1235,59 @@ __device__ __forceinline__ void peelf_unbiased(float& x, int& es) {
   }
 }
 
-// all four entries of a lane in one stage: e = ebase + 2 i (independent work, interleaved by the compiler)
-template <bool SAME, bool EXTRAS, int ROW0, bool UNROLL>
+// all four entries of a lane in one stage: e = ebase + 2 i.  Rolled on purpose: the 16 warps of the CTA run five
+// different roles out of a 32 KB instruction cache, and an unrolled transform alone would take a third of it.
+template <bool AFF, bool SAME, bool EXTRAS, int ROW0>
 __device__ __forceinline__ void transform_stage_f32(const unsigned char* __restrict__ rs, uint32_t off_fh,
                                                     float* __restrict__ pf, int ebase, int q, int nvalid, bool jq,
-                                                    bool kq, float (&PA)[4], float (&PB)[4], float (&P1)[4],
-                                                    float (&P0)[4]) {
-  // UNROLL: the four entries' loads and arithmetic interleave (needs ~130 registers); the rolled form is for the
-  // transform warp of the register-poor warpgroup
-#pragma unroll(UNROLL ? NB / 2 : 1)
+                                                    bool kq, Fac& F) {
+#ifndef DMX_T_UNROLL
+#define DMX_T_UNROLL 1
+#endif
+  constexpr int TU = DMX_T_UNROLL;   // entries in flight per lane (instruction-cache footprint against latency hiding)
+#pragma unroll TU
   for (int i = 0; i < NB / 2; ++i) {
     const int e = ebase + 2 * i;
-    if (e < nvalid) {
-      transform_quad_f32<SAME, EXTRAS, ROW0>(rs, off_fh, pf, e, q, jq, kq, PA, PB, P1, P0);
-    } else {   // identity entry: S = 1 for every hypothesis
-      store_neutral_quad(pf + q * F_BLK4_FLT + e * 12);
-      store_neutral_quad(pf + F_SIDE_FLT + q * F_BLK4_FLT + e * 12);
+    if (AFF) {
+      if (e < nvalid) {
+        transform_quad_aff<SAME, EXTRAS, ROW0>(rs, off_fh, pf, e, q, jq, kq, F);
+      } else {   // identity entry: S' = 0.5 + 0.5 for every hypothesis
+        const float4 half4 = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
+        *reinterpret_cast<float4*>(pf + q * A_BLK4_FLT + e * 4) = half4;
+        if (!SAME) *reinterpret_cast<float4*>(pf + A_SIDE_FLT + q * A_BLK4_FLT + e * 4) = half4;
+      }
+    } else {
+      if (e < nvalid) {
+        transform_quad_f32<SAME, EXTRAS, ROW0>(rs, off_fh, pf, e, q, jq, kq, F);
+      } else {   // identity entry: S' = 1 for every hypothesis
+        store_neutral_quad(pf + q * F_BLK4_FLT + e * 12);
+        store_neutral_quad(pf + F_SIDE_FLT + q * F_BLK4_FLT + e * 12);
+      }
+    }
+  }
+}
+
+template <bool AFF>
+__device__ __forceinline__ void transform_dispatch_f32(bool same, bool extras_t, int row0, const unsigned char* rs,
+                                                       uint32_t off_fh, float* pf, int ebase, int q, int nvalid, bool jq,
+                                                       bool kq, Fac& F) {
+  if (same) {
+    if (extras_t) {
+      if (row0) transform_stage_f32<AFF, true, true, 1>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, F);
+      else transform_stage_f32<AFF, true, true, 0>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, F);
+    } else {
+      if (row0) transform_stage_f32<AFF, true, false, 1>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, F);
+      else transform_stage_f32<AFF, true, false, 0>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, F);
+    }
+  } else {
+    if (extras_t) {
+      if (row0 == 2) transform_stage_f32<AFF, false, true, 2>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, F);
+      else if (row0 == 1) transform_stage_f32<AFF, false, true, 1>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, F);
+      else transform_stage_f32<AFF, false, true, 0>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, F);
+    } else {
+      if (row0 == 2) transform_stage_f32<AFF, false, false, 2>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, F);
+      else if (row0 == 1) transform_stage_f32<AFF, false, false, 1>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, F);
+      else transform_stage_f32<AFF, false, false, 0>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, F);
     }
   }
 }
@@ -1003,7 +1296,6 @@ __device__ __forceinline__ void transform_stage_f32(const unsigned char* __restr
 // time (which hides the latency of a stage's dependent load -> FMA -> store chain) and a warp that shares its
 // sub-partition with busier consumers simply takes fewer.  In-flight stages span at most F_NTW consecutive
 // indices, fewer than either ring has slots, so the parity waits below cannot alias.
-template <bool UNROLL>
 __device__ __forceinline__ void transform_role_f32(const ScanParams& p, const Pipe& pp, TScratch* ts, uint64_t* prod_full,
                                                    uint64_t* prod_empty, int lane, int u, int NS) {
   const int ebase = lane >> 4, q = lane & 15;
@@ -1015,8 +1307,8 @@ __device__ __forceinline__ void transform_role_f32(const ScanParams& p, const Pi
     return __shfl_sync(0xffffffffu, g, 0);
   };
   uint32_t git = grab();
-  TaskInfo ti;
-  for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
+  TaskInfoF ti;
+  for (int r = 0; next_task_f32(p, r, u, NS, &ti); ++r) {
     const TaskType tt = p.tt[ti.tti];
     const bool same = tt.flags & TF_TRI;
     const bool extras_t = (tt.flags & TF_EXTRAS) != 0 && !(p.dbg & 4);
@@ -1028,42 +1320,32 @@ __device__ __forceinline__ void transform_role_f32(const ScanParams& p, const Pi
       const int it = (int)(git - gbase);
       const uint32_t rslot = git % sraw, pslot = git % F_S_PROC;
       const uint32_t rph = (git / sraw) & 1u, pph = (git / F_S_PROC) & 1u;
-      const int nvalid = (int)min((int64_t)NB, ti.e1 - (ti.e0 + (int64_t)it * NB));
-      float PA[4], PB[4], P1[4], P0[4];               // this stage's factors of the running products (4 entries each)
+      int64_t eb;
+      int nvalid;
+      bool aff;
+      stage_span(ti, it, &eb, &nvalid, &aff);
+      Fac F;                                          // this stage's factors of the running products (4 entries each)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) PA[i] = PB[i] = P1[i] = P0[i] = 1.0f;
+      for (int i = 0; i < 4; ++i) F.PA[i] = F.PB[i] = F.P1[i] = F.P0[i] = F.PJ[i] = 1.0f;
       mbar_wait(&pp.raw_full[rslot], rph);
       mbar_wait(&pp.proc_empty[pslot], pph ^ 1u);
       const unsigned char* rs = pp.raw_base + (size_t)rslot * rawslot;
       float* pf = reinterpret_cast<float*>(pp.proc_base + (size_t)pslot * F_PROC_SLOT);
       if (p.dbg & 2) {
-      } else if (same) {
-        if (extras_t) {
-          if (row0) transform_stage_f32<true, true, 1, UNROLL>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
-          else transform_stage_f32<true, true, 0, UNROLL>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
-        } else {
-          if (row0) transform_stage_f32<true, false, 1, UNROLL>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
-          else transform_stage_f32<true, false, 0, UNROLL>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
-        }
+      } else if (aff) {
+        transform_dispatch_f32<true>(same, extras_t, row0, rs, off_fh, pf, ebase, q, nvalid, jq, kq, F);
       } else {
-        if (extras_t) {
-          if (row0 == 2) transform_stage_f32<false, true, 2, UNROLL>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
-          else if (row0 == 1) transform_stage_f32<false, true, 1, UNROLL>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
-          else transform_stage_f32<false, true, 0, UNROLL>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
-        } else {
-          if (row0 == 2) transform_stage_f32<false, false, 2, UNROLL>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
-          else if (row0 == 1) transform_stage_f32<false, false, 1, UNROLL>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
-          else transform_stage_f32<false, false, 0, UNROLL>(rs, off_fh, pf, ebase, q, nvalid, jq, kq, PA, PB, P1, P0);
-        }
+        transform_dispatch_f32<false>(same, extras_t, row0, rs, off_fh, pf, ebase, q, nvalid, jq, kq, F);
       }
       // the stage's factors go to the products ring (every factor is >= ~2^-20, four of them cannot underflow)
       mbar_wait(&prod_empty[pslot], pph ^ 1u);
       {
         float4* dst = reinterpret_cast<float4*>(&ts->prod[pslot][ebase][0][4 * q]);
-        dst[0 * (BLK / 4)] = make_float4(PA[0], PA[1], PA[2], PA[3]);
-        dst[1 * (BLK / 4)] = make_float4(PB[0], PB[1], PB[2], PB[3]);
-        dst[2 * (BLK / 4)] = make_float4(P1[0], P1[1], P1[2], P1[3]);
-        dst[3 * (BLK / 4)] = make_float4(P0[0], P0[1], P0[2], P0[3]);
+        dst[0 * (BLK / 4)] = make_float4(F.PA[0], F.PA[1], F.PA[2], F.PA[3]);
+        dst[1 * (BLK / 4)] = make_float4(F.PB[0], F.PB[1], F.PB[2], F.PB[3]);
+        dst[2 * (BLK / 4)] = make_float4(F.P1[0], F.P1[1], F.P1[2], F.P1[3]);
+        dst[3 * (BLK / 4)] = make_float4(F.P0[0], F.P0[1], F.P0[2], F.P0[3]);
+        if (!same) dst[4 * (BLK / 4)] = make_float4(F.PJ[0], F.PJ[1], F.PJ[2], F.PJ[3]);
       }
       __syncwarp();
       if (lane == 0) {
@@ -1078,24 +1360,29 @@ __device__ __forceinline__ void transform_role_f32(const ScanParams& p, const Pi
 
 // =============================== accumulator warp =================================================
 // Multiplies the per-stage factors of the products ring into the per-sample running products in stage order (the
-// order the stages were numbered in, not the order the transform warps finished them: the result is reproducible) and
-// writes, at the end of a task, the singlet factor of the separable plane, the row-sum term, the pass-1 likelihoods
-// and the pairs with sample 0.  Lane l owns quantity l / 8 of the samples 8 (l % 8) .. + 7; a product is renormalised
-// into an integer exponent after every factor.
-__device__ __forceinline__ void accumulator_role_f32(const ScanParams& p, const TScratch* ts, uint64_t* prod_full,
-                                                     uint64_t* prod_empty, int lane, int u, int NS) {
+// order the stages were numbered in, not the order the transform warps finished them: the result is reproducible).
+// Lane l owns quantity l / 8 of the samples 8 (l % 8) .. + 7 (lanes 0..7 also the j-side sums of a rectangular task);
+// a product is renormalised into an integer exponent after every factor.  At the end of a task it hands lb (sum of
+// log s per sample, both sides) to the consumers' epilogue through shared memory and writes the per-sample outputs:
+// singlet factor of the separable plane, row-sum term, pass-1 likelihoods, pairs with sample 0 -- each with the lb
+// terms of its samples added back.
+__device__ __forceinline__ void accumulator_role_f32(const ScanParams& p, TScratch* ts, uint64_t* prod_full,
+                                                     uint64_t* prod_empty, uint64_t* lb_full, uint64_t* lb_empty, int lane,
+                                                     int u, int NS) {
   const int c = lane >> 3, s0 = (lane & 7) * 8;
+  const double LN2 = 0.693147180559945309417232121458;
   uint32_t git = 0;
-  TaskInfo ti;
-  for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
+  TaskInfoF ti;
+  for (int r = 0; next_task_f32(p, r, u, NS, &ti); ++r) {
     const TaskType tt = p.tt[ti.tti];
     const bool same = tt.flags & TF_TRI;
     const bool extras_t = (tt.flags & TF_EXTRAS) != 0 && !(p.dbg & 4);
     const int row0 = (!(tt.flags & TF_ROW0) || (p.dbg & 16)) ? 0 : ((tt.flags & TF_SYM) ? 1 : (same ? 0 : 2));
-    float acc[8];
-    int ex[8];
+    const bool do_j = !same && c == 0;      // lanes 0..7: second set of products for the j-side sums
+    float acc[8], accj[8];
+    int ex[8], exj[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { acc[i] = 1.0f; ex[i] = 0; }
+    for (int i = 0; i < 8; ++i) { acc[i] = accj[i] = 1.0f; ex[i] = exj[i] = 0; }
     for (int it = 0; it < ti.nst; ++it, ++git) {
       const uint32_t slot = git % F_S_PROC, ph = (git / F_S_PROC) & 1u;
       mbar_wait(&prod_full[slot], ph);
@@ -1104,28 +1391,61 @@ __device__ __forceinline__ void accumulator_role_f32(const ScanParams& p, const 
         const float4* src = reinterpret_cast<const float4*>(&ts->prod[slot][half][c][s0]);
         const float4 x = src[0], y = src[1];
         const float f[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+        if (p.dbg & 8) continue;             // timing experiment
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           acc[i] *= f[i];
           peelf_unbiased(acc[i], ex[i]);     // exact zeros (padding samples) stay zero
         }
+        if (do_j) {
+          const float4* sj = reinterpret_cast<const float4*>(&ts->prod[slot][half][4][s0]);
+          const float4 xj = sj[0], yj = sj[1];
+          const float fj[8] = {xj.x, xj.y, xj.z, xj.w, yj.x, yj.y, yj.z, yj.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            accj[i] *= fj[i];
+            peelf_unbiased(accj[i], exj[i]);
+          }
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&prod_empty[slot]);
     }
+    // lb of this task -> shared memory (double buffered by task parity; the consumers release a buffer after reading)
+    const int par = r & 1;
+    mbar_wait(&lb_empty[par], ((uint32_t)(r >> 1) & 1u) ^ 1u);
+    double v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (double)ex[i] * LN2 + (double)logf(acc[i]);
+    if (c == 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        ts->lb[par][1][s0 + i] = v[i];
+        if (same) ts->lb[par][0][s0 + i] = v[i];
+      }
+    }
+    if (do_j) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ts->lb[par][0][s0 + i] = (double)exj[i] * LN2 + (double)logf(accj[i]);
+    }
+    __syncwarp();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // (generic-proxy writes; the fence is cheap insurance)
+    if (lane == 0) mbar_arrive(&lb_full[par]);
     // results of this task: quantities 0..2 belong to the k-side samples of tasks with TF_EXTRAS, quantity 3 to the
     // pairs with sample 0
     const bool want = c == 3 ? row0 != 0 : (extras_t && !(c == 0 && !p.sep0) && !(c == 2 && !p.want_single));
     if (!want) continue;
+    const bool on_j = c == 3 && row0 == 2;
+    const double lb_other = c == 3 ? (row0 == 2 ? ts->lb[par][1][0] : ts->lb[par][0][0]) : 0.0;   // sample 0's share
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int smp = s0 + i;
-      const bool on_j = c == 3 && row0 == 2;
       const int gs = (on_j ? tt.j0 : tt.k0) + smp;
       if (smp >= (on_j ? tt.nj : tt.nk) || gs >= p.nv) continue;
-      const double v = (double)ex[i] * 0.693147180559945309417232121458 + (double)logf(acc[i]);
-      if (c == 3) p.row0[((int64_t)ti.cell * p.nA + tt.n) * p.nv + gs] = v;
-      else (c == 0 ? p.singA : (c == 1 ? p.lb : p.p1))[(int64_t)ti.cell * p.nv + gs] = v;
+      double out = v[i];
+      if (c != 1) out += ts->lb[par][on_j ? 0 : 1][smp] + lb_other;
+      if (c == 3) p.row0[((int64_t)ti.cell * p.nA + tt.n) * p.nv + gs] = out;
+      else (c == 0 ? p.singA : (c == 1 ? p.lb : p.p1))[(int64_t)ti.cell * p.nv + gs] = out;
     }
   }
 }
@@ -1133,8 +1453,8 @@ __device__ __forceinline__ void accumulator_role_f32(const ScanParams& p, const 
 // =============================== per-task reductions (:712-734, :799-814) ==========================
 // Every consumer thread brings NV llk values with their (j, k); the block of NW consumer warps reduces them to
 // the task's Part (max, sum of exp, best pair value, near-tie candidates) and stores row 0 / the dense block.
-template <int NV, int NW, bool ROW0>
-__device__ __forceinline__ void task_epilogue(const ScanParams& p, const TaskInfo& ti, const TaskType& tt, Scratch* scr,
+template <int NV, int NW, bool ROW0, class TI>
+__device__ __forceinline__ void task_epilogue(const ScanParams& p, const TI& ti, const TaskType& tt, Scratch* scr,
                                               int bar_id, int rw, int lane, const double (&v)[NV], const int (&vj)[NV],
                                               const int (&vk)[NV], uint32_t vmask) {
   const bool sym = tt.flags & TF_SYM;
@@ -1167,7 +1487,9 @@ __device__ __forceinline__ void task_epilogue(const ScanParams& p, const TaskInf
     const int j = vj[i], k = vk[i];
     const double x = v[i];
     if (j != k) {
-      sd += ROW0 ? exp(x - m_all) : (double)expf((float)(x - m_all));   // fp32 scan: 1e-7 relative is plenty here
+      // relative to the task's best pair (not to m_all, which may be a singlet-like diagonal value hundreds of nats
+      // above every pair: the sum must keep its leading digits even then)
+      sd += ROW0 ? exp(x - best) : (double)expf((float)(x - best));   // fp32 scan: 1e-7 relative is plenty here
       if (!noarg && x >= thr) {
         const int cs = atomicAdd(&scr->ncand, 1);
         if (cs < MAX_CAND) scr->cand[cs] = (uint32_t)j | ((uint32_t)k << 12);
@@ -1388,10 +1710,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_scan_kernel(const __grid_con
   }
 }
 
-// S[i][c] = a_i . w_c and acc *= S for one 8 x 8 tile and one entry, a few tile rows at a time (independent chains
-// that cover the 4-cycle FMA latency).  A diagonal tile of a triangular task skips the hypotheses below the diagonal.
-template <bool DIAG>
+// S'[i][c] = a_i . w_c and acc *= S' for one 8 x 8 tile and one general entry, a few tile rows at a time (independent
+// chains that cover the 4-cycle FMA latency).  A diagonal tile of a triangular task skips the hypotheses below the
+// diagonal.
 __device__ __forceinline__ void tile_math(const float (&a)[8][3], const float (&w)[8][3], float (&acc)[64]) {
+  constexpr bool DIAG = false;   // diagonal tiles of a triangular task compute all 64 products too: one code path for
+                                 // every consumer warp (the instruction cache is the scarcer resource)
 #ifndef DMX_TILE_ROWS
 #define DMX_TILE_ROWS 2
 #endif
@@ -1422,27 +1746,83 @@ __device__ __forceinline__ void tile_math(const float (&a)[8][3], const float (&
   }
 }
 
+// the same for an affine entry: S'[i][c] = X_i + Y_c, one add and one multiply per hypothesis
+__device__ __forceinline__ void tile_math_aff(const float (&x)[8], const float (&y)[8], float (&acc)[64]) {
+  constexpr bool DIAG = false;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (!DIAG || c >= i) acc[i * 8 + c] *= x[i] + y[c];
+}
+
+// Range of the running products: a thread's 64 products share one integer exponent (block floating point).  A factor
+// is >= ~2^-20 (the 1e-6 floors), so a tile whose largest product is above 2^-46 now keeps it inside the fp32 range
+// for F_PEEL_STAGES more entries; below that every thread of the warp rescales its tile by a power of two.  A diagonal
+// tile looks at (and rescales) only the hypotheses it computes: the products below the diagonal stay 1 and must not
+// pass for the tile's largest.
+__device__ __forceinline__ void range_check(float (&acc)[64], int& ex, bool active) {
+  constexpr bool DIAG = false;
+  float m8[8];   // eight short chains instead of one long one
+#pragma unroll
+  for (int c = 0; c < 8; ++c) m8[c] = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (!DIAG || c >= i) m8[c] = fmaxf(m8[c], acc[i * 8 + c]);
+  const float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+  if (__any_sync(0xffffffffu, active && mx < 0x1p-46f)) {
+    uint32_t eb = __float_as_uint(mx) >> 23;                  // biased exponent of the largest product
+    if (eb == 0u || eb >= 254u) eb = 127u;                    // all-zero tile (padding samples only): leave it alone
+    const float sc = __uint_as_float((254u - eb) << 23);      // 2^(127 - eb): brings it back to [1, 2)
+    ex += (int)eb - 127;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (!DIAG || c >= i) acc[i * 8 + c] *= sc;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // fp32 pair scan: one task pipeline per CTA, 16 warps in four warpgroups.  SM sub-partition = warp id % 4; roles are
 // placed so that the issue load of the four sub-partitions is even (C = consumer, D = consumer of diagonal tiles:
 // 36 / 64 of the work, T = transform, L = loader, A = accumulator of the per-sample products):
 //   wid   0  1  2  3 |  4  5  6  7 |  8  9 10 11 | 12 13 14 15
-//         D  C  C  C |  D  C  C  C |  C  T  T  T |  T  L  L  A
+//         C  C  C  C |  C  C  C  C |  C  T  T  T |  L  T  L  A
 // The last warpgroup gives registers back (setmaxnreg) so that the consumers' 64 accumulators + 48 operands fit.
+// Every role is written for a small instruction footprint (one consumer code path, rolled transform): the warps of a
+// CTA run five different programs out of one 32 KB instruction cache.
 //
-// A consumer thread owns the 8 x 8 tile (bj, bk) of hypotheses for the entries e = lane & 7 of every stage: per
-// entry 12 LDS.128 (two 4-sample blocks of a, two of w), 64 x (FMUL + 2 FFMA) for S[j][k] and 64 FMUL into the
-// running products.  Range: a thread's 64 products share one integer exponent (block floating point): every
-// F_PEEL_STAGES entries the warp checks whether some thread's LARGEST product is about to leave the fp32 range and,
-// if so, every thread rescales its tile by a power of two.  A hypothesis more than ~2^-80 below the best of its own
-// tile underflows to zero (llk = -inf): it cannot be the best pair, a near tie or a visible term of sumDouble.  The
-// pairs with sample 0 that .best prints (LLK10 / LLK20) do not come from here but from the transform warps (TF_ROW0),
-// and dense llksAB blocks (--write-pair) from the fp64 scan.  At the end of a task the eight entry lanes of a tile
-// multiply their products together (fp64 reduce-scatter: lane e ends up with tile row e).
+// A consumer thread owns the 8 x 8 tile (bj, bk) of hypotheses for the entries e = lane & 7 of every stage.  Per
+// general entry: 12 LDS.128 (two 4-sample blocks of a_hat, two of w), 64 x (FMUL + 2 FFMA) for S'[j][k] and 64 FMUL
+// into the running products; per affine entry: 4 LDS.128 (X of its 8 j samples, Y of its 8 k samples), 64 x (FADD +
+// FMUL).  Range: a thread's 64 products share one integer exponent (block floating point): every F_PEEL_STAGES entries
+// the warp checks whether some thread's LARGEST product is about to leave the fp32 range and, if so, every thread
+// rescales its tile by a power of two.  A hypothesis more than ~2^-80 below the best of its own tile underflows to
+// zero (llk = -inf): it cannot be the best pair, a near tie or a visible term of sumDouble.  The pairs with sample 0
+// that .best prints (LLK10 / LLK20) do not come from here but from the transform warps (TF_ROW0), and dense llksAB
+// blocks (--write-pair) from the fp64 scan.  At the end of a task the eight entry lanes of a tile multiply their
+// products together (fp64 reduce-scatter: lane e ends up with tile row e) and add the lb terms of their samples.
 // ---------------------------------------------------------------------------------------------
 constexpr int F_LAUNCH_THREADS = 512;
+// Consumer hand-over: with DMX_CONS_BAR one consumer warp polls the stage's mbarrier and a named hardware barrier
+// releases the other eight (a warp parked in bar.sync costs no issue slots, nine polling warps cost hundreds per
+// stage); the barrier of stage i + 1 also tells that every warp is done with stage i, so the polling warp alone
+// hands the slot back.
+#ifndef DMX_CONS_BAR
+#define DMX_CONS_BAR 0
+#endif
+// Role placement (SM sub-partition = warp id % 4).  DMX_ROLEMAP 1: the four transform warps own sub-partition 3, the
+// nine consumers sit three to a sub-partition on 0..2 with a loader or the accumulator as fourth warp.
+#ifndef DMX_ROLEMAP
+#define DMX_ROLEMAP 0
+#endif
+#define DMX_CONS_POLLERS (DMX_CONS_BAR ? 1 : F_NCW)
 static_assert(F_S_RAW_RECT % F_NLOAD == 0 && F_S_RAW_TRI % F_NLOAD == 0 && F_NLOAD == 2 && F_NTW <= 4 &&
               F_NTW < (int)F_S_RAW_RECT && F_NTW < F_S_PROC, "ring ownership");
+static_assert(2 * 12 + 4 * F_S_PROC + 4 <= 64, "barriers must fit below the scratch area");
 constexpr int F_REGS_HI = 136, F_REGS_LO = 104;   // (3 * 136 + 104) * 32 = 16384 registers per sub-partition
 
 __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_f32_kernel(const __grid_constant__ ScanParams p,
@@ -1456,6 +1836,8 @@ __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_f32_kernel(cons
   pp.proc_empty = pp.proc_full + F_S_PROC;
   uint64_t* prod_full = pp.proc_empty + F_S_PROC;      // products ring: transform -> accumulator warp
   uint64_t* prod_empty = prod_full + F_S_PROC;
+  uint64_t* lb_full = prod_empty + F_S_PROC;           // lb of a finished task: accumulator -> consumers
+  uint64_t* lb_empty = lb_full + 2;
   Scratch* scr = reinterpret_cast<Scratch*>(smem + SCRATCH_OFF);
   pp.raw_base = smem + SLOT_CTRL;
   pp.proc_base = pp.raw_base + F_RAW_BYTES;
@@ -1468,9 +1850,13 @@ __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_f32_kernel(cons
     }
     for (int s = 0; s < F_S_PROC; ++s) {
       mbar_init(&pp.proc_full[s], 1);
-      mbar_init(&pp.proc_empty[s], F_NCW);
+      mbar_init(&pp.proc_empty[s], DMX_CONS_POLLERS);
       mbar_init(&prod_full[s], 1);
       mbar_init(&prod_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&lb_full[s], 1);
+      mbar_init(&lb_empty[s], F_NCW);
     }
     scr->ncand = 0;
     ts->next_stage = 0;
@@ -1480,26 +1866,39 @@ __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_f32_kernel(cons
   __syncthreads();
 
   const int NS = (int)gridDim.x, u = (int)blockIdx.x;
+#if DMX_ROLEMAP == 1
+  const bool is_cons = warp < 12 && (warp & 3) != 3;
+  const bool is_tr = (warp & 3) == 3;
+  const bool is_acc = warp == 14;
+  const int lid = warp - 12;                       // loaders: warps 12, 13
+  const int rw_map = (warp >> 2) * 3 + (warp & 3); // consumer index 0..8
+#else
+  const bool is_cons = warp < F_NCW;
+  const bool is_tr = (warp >= F_NCW && warp < 12) || warp == 13;
+  const bool is_acc = warp == 15;
+  const int lid = (warp - 12) >> 1;                // loaders: warps 12, 14
+  const int rw_map = warp;
+#endif
   if (warp >= 12) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(F_REGS_LO));
-    if (warp == 12) { if (F_NTW > 3) transform_role_f32<false>(p, pp, ts, prod_full, prod_empty, lane, u, NS); }
-    else if (warp == 15) accumulator_role_f32(p, ts, prod_full, prod_empty, lane, u, NS);
-    else loader_role_f32(p, tm, pp, lane, u, NS, warp - 13);
+    if (is_tr) { if (F_NTW > 3) transform_role_f32(p, pp, ts, prod_full, prod_empty, lane, u, NS); }
+    else if (is_acc) accumulator_role_f32(p, ts, prod_full, prod_empty, lb_full, lb_empty, lane, u, NS);
+    else loader_role_f32(p, tm, pp, lane, u, NS, lid);
     return;
   }
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(F_REGS_HI));
-  if (warp >= F_NCW) {
-    transform_role_f32<true>(p, pp, ts, prod_full, prod_empty, lane, u, NS);
-  } else {
+  if (is_tr) {
+    transform_role_f32(p, pp, ts, prod_full, prod_empty, lane, u, NS);
+  } else if (is_cons) {
     // =============================== consumer warps ============================================
-    // logical consumer index: 0..6 own the 28 off-diagonal tile positions of a triangular task, 7 and 8 (physical
-    // warps 0 and 4) the 8 diagonal ones
-    const int rw = warp == 0 ? 7 : (warp == 4 ? 8 : (warp < 4 ? warp - 1 : warp - 2));
+    // consumer warp rw owns tile positions 4 rw .. 4 rw + 3: 0..27 the off-diagonal tiles of a triangular task, 28..35
+    // the diagonal ones
+    const int rw = rw_map;
     const int el = lane & 7;
     const int pos = rw * 4 + (lane >> 3);
     uint32_t git = 0;
-    TaskInfo ti;
-    for (int r = 0; next_task(p, r, u, NS, &ti); ++r) {
+    TaskInfoF ti;
+    for (int r = 0; next_task_f32(p, r, u, NS, &ti); ++r) {
       const TaskType tt = p.tt[ti.tti];
       const bool tri = tt.flags & TF_TRI;
       const int nbj = (tt.nj + 7) >> 3, nbk = (tt.nk + 7) >> 3;   // 8-sample blocks on each side
@@ -1523,6 +1922,9 @@ __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_f32_kernel(cons
       const bool active = (tri || pos < 32) && bj < nbj && bk < nbk;
       const uint32_t aoff = (uint32_t)(2 * bj) * F_BLK4_FLT + (uint32_t)el * 12u;                 // floats
       const uint32_t woff = F_SIDE_FLT + (uint32_t)(2 * bk) * F_BLK4_FLT + (uint32_t)el * 12u;
+      // affine stages: X blocks of the j side, Y blocks of the k side (one shared side in a triangular task)
+      const uint32_t xoff = (uint32_t)(2 * bj) * A_BLK4_FLT + (uint32_t)el * 4u;
+      const uint32_t yoff = (tri ? 0u : A_SIDE_FLT) + (uint32_t)(2 * bk) * A_BLK4_FLT + (uint32_t)el * 4u;
       float acc[64];
 #pragma unroll
       for (int h = 0; h < 64; ++h) acc[h] = 1.0f;
@@ -1530,9 +1932,24 @@ __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_f32_kernel(cons
       for (int it = 0; it < ti.nst; ++it, ++git) {
         const int pslot = git % F_S_PROC;
         const uint32_t pph = (git / F_S_PROC) & 1u;
+#if DMX_CONS_BAR
+        if (rw == 0) mbar_wait(&pp.proc_full[pslot], pph);
+        consumer_bar_sync<F_NCW * 32>(1);
+        if (rw == 0 && lane == 0 && it > 0) mbar_arrive(&pp.proc_empty[(git - 1) % F_S_PROC]);
+#else
         mbar_wait(&pp.proc_full[pslot], pph);
-        if (active && !(p.dbg & 1)) {
-          const float* pf = reinterpret_cast<const float*>(pp.proc_base + (size_t)pslot * F_PROC_SLOT);
+#endif
+        const float* pf = reinterpret_cast<const float*>(pp.proc_base + (size_t)pslot * F_PROC_SLOT);
+        if (!active || (p.dbg & 1)) {
+        } else if (it < ti.nstA) {
+          const float4 x0 = *reinterpret_cast<const float4*>(pf + xoff);
+          const float4 x1 = *reinterpret_cast<const float4*>(pf + xoff + A_BLK4_FLT);
+          const float4 y0 = *reinterpret_cast<const float4*>(pf + yoff);
+          const float4 y1 = *reinterpret_cast<const float4*>(pf + yoff + A_BLK4_FLT);
+          const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+          const float y[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+          tile_math_aff(x, y, acc);
+        } else {
           float a[8][3], w[8][3];
           float4 ld[12];   // issue order: first w block, the two a blocks, second w block
 #pragma unroll
@@ -1553,26 +1970,20 @@ __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_f32_kernel(cons
               w[(q / 3) * 4 + f / 3][f % 3] = ys[c];
             }
           }
-          if (diag) tile_math<true>(a, w, acc);     // warp-uniform (logical warps 7 and 8)
-          else tile_math<false>(a, w, acc);
+          tile_math(a, w, acc);
         }
-        if ((it % F_PEEL_STAGES) == F_PEEL_STAGES - 1) {
-          // a factor is >= ~2^-20 (the 1e-6 floors), so a tile whose largest product is above 2^-46 now keeps it
-          // inside the fp32 range for F_PEEL_STAGES more entries
-          float mx = 0.0f;
-#pragma unroll
-          for (int h = 0; h < 64; h += 2) mx = fmaxf(mx, fmaxf(acc[h], acc[h + 1]));
-          if (__any_sync(0xffffffffu, active && mx < 0x1p-46f)) {
-            const uint32_t eb = __float_as_uint(mx) >> 23;            // biased exponent of the largest product
-            const float sc = __uint_as_float((254u - eb) << 23);      // 2^(127 - eb): brings it back to [1, 2)
-            ex += (int)eb - 127;
-#pragma unroll
-            for (int h = 0; h < 64; ++h) acc[h] *= sc;
-          }
+        if ((it % F_PEEL_STAGES) == F_PEEL_STAGES - 1 && !(p.dbg & 64)) {
+          range_check(acc, ex, active);
         }
+#if !DMX_CONS_BAR
         __syncwarp();
         if (lane == 0) mbar_arrive(&pp.proc_empty[pslot]);
+#endif
       }
+#if DMX_CONS_BAR
+      consumer_bar_sync<F_NCW * 32>(1);          // every warp is done with the task's last stage
+      if (rw == 0 && lane == 0 && ti.nst > 0) mbar_arrive(&pp.proc_empty[(git - 1) % F_S_PROC]);
+#endif
       // ---- fold the eight entry lanes of each tile (reduce-scatter over lane bits 2, 1, 0): lane e ends up with the
       // products of tile row e.  Values of different lanes are multiplied in fp64 (no range problem).
       double d3[8];
@@ -1606,6 +2017,10 @@ __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_f32_kernel(cons
       exs += __shfl_xor_sync(0xffffffffu, exs, 4);
       exs += __shfl_xor_sync(0xffffffffu, exs, 2);
       exs += __shfl_xor_sync(0xffffffffu, exs, 1);
+      // the sums s the transform divided out come back as lb[j] + lb[k] (from the accumulator warp)
+      const int par = r & 1;
+      mbar_wait(&lb_full[par], (uint32_t)(r >> 1) & 1u);
+      const double lbj = ts->lb[par][0][bj * 8 + el];
       double v[8];
       int vj[8], vk[8];
       uint32_t vmask = 0;
@@ -1613,11 +2028,14 @@ __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_f32_kernel(cons
       for (int c = 0; c < 8; ++c) {
         const int j = tt.j0 + bj * 8 + el, k = tt.k0 + bk * 8 + c;
         const bool valid = active && j < p.nv && k < p.nv && (!tri || j <= k);
-        v[c] = valid ? (double)exs * 0.693147180559945309417232121458 + log_pos_fast(d3[c]) : -INFINITY;
+        v[c] = valid ? (double)exs * 0.693147180559945309417232121458 + log_pos_fast(d3[c]) + (lbj + ts->lb[par][1][bk * 8 + c])
+                     : -INFINITY;
         vj[c] = j;
         vk[c] = k;
         if (valid) vmask |= 1u << c;
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&lb_empty[par]);
       task_epilogue<8, F_NCW, false>(p, ti, tt, scr, 0, rw, lane, v, vj, vk, vmask);
     }
   }
@@ -1702,7 +2120,7 @@ __global__ void merge_kernel(const __grid_constant__ MergeParams p, int64_t nact
   for (int t = 0; t < p.T; ++t) {
     const TaskType& tt = p.tt[t];
     if (tt.flags & TF_NOARG) continue;
-    sdb += parts[t].sd * exp(parts[t].m_all - mx) * p.w_double[tt.n];
+    if (parts[t].best_v > -INFINITY) sdb += parts[t].sd * exp(parts[t].best_v - mx) * p.w_double[tt.n];
     if (parts[t].best_v >= thr) {
       const int nc = parts[t].ncand;
       for (int c = 0; c < nc && c < MAX_CAND; ++c)
