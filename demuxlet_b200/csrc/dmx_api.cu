@@ -128,6 +128,12 @@ struct dmx_ctx {
   DevBuf<double> d_ents;           // [E][2 + nd] per-entry factors of llk0s / llks00 (entq -> cell_scalars)
   DevBuf<float> d_entf_head, d_entf_plane;   // fp32 copies of the entry records (fp32 pair scan), class-sorted per cell
   DevBuf<int32_t> d_perm, d_snp_perm, d_cell_na;   // entry -> position, SNP id by position, affine entries per cell
+  DevBuf<double> d_memo_q;         // memo tables of the affine entries (build_memo)
+  DevBuf<float> d_memo_fh, d_memo_fp;
+  DevBuf<uint16_t> d_ecode;        // memo row per entry (0xffff: general entry with its own fp64 record)
+  DevBuf<int32_t> d_glist;         // entry by class-sorted position (sign bit: general entry)
+  bool memo_ready = false;
+  bool entq_full = false;          // the fp64 entry table holds every entry (fp32 mode: only after ensure_entq_full)
   double err3_256[256];
   DevBuf<int64_t> d_cell_ptr, d_ent_ptr;
   DevBuf<int32_t> d_ent_snp, d_order;
@@ -457,6 +463,7 @@ void expand_cands(const dmx_ctx* c, const CellOut& co, std::vector<Hyp>* out) {
 }
 
 int for_each_kid(dmx_ctx* c, const std::function<int(int)>& f);
+int ensure_entq_full(dmx_ctx* c);
 
 // dense llksAB for a list of active cells (device order buffer is temporarily replaced)
 int dense_scan(dmx_ctx* c, const std::vector<int32_t>& cells, double* host_out /* [n][nv][nv][nA] */) {
@@ -482,6 +489,7 @@ int dense_scan(dmx_ctx* c, const std::vector<int32_t>& cells, double* host_out /
     });
   }
   CU(cudaSetDevice(c->cfg.device));
+  RC(ensure_entq_full(c));
   const size_t max_batch = std::max<size_t>(1, ((size_t)1 << 30) / (per * sizeof(double)));
   DevBuf<int32_t> d_cells;
   DevBuf<Part> d_parts;
@@ -832,6 +840,8 @@ void dmx_destroy(dmx_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   c->d_terms.release(); c->d_ents.release(); c->d_entf_head.release(); c->d_entf_plane.release();
   c->d_perm.release(); c->d_snp_perm.release(); c->d_cell_na.release();
+  c->d_memo_q.release(); c->d_memo_fh.release(); c->d_memo_fp.release(); c->d_ecode.release();
+  c->d_glist.release();
   c->d_gp.release(); c->d_gprow.release(); c->d_entq.release(); c->d_row0.release(); c->d_singA.release();
   c->d_lb.release(); c->d_p1.release(); c->d_p1_0.release(); c->d_l00.release(); c->d_sing.release();
   c->d_dense.release(); c->d_cell_ptr.release(); c->d_ent_ptr.release(); c->d_ent_snp.release();
@@ -1022,49 +1032,115 @@ int upload_chunk(dmx_ctx* c, const Chunk& ck, cudaStream_t st, int64_t* bytes) {
   return DMX_OK;
 }
 
-// ---- the kernels of one chunk (a contiguous cell-id range; its active cells are order[o0, o1)) ----------------------
-int enqueue_chunk(dmx_ctx* c, const Chunk& ck, const ScanParams& sp0, bool dev_rescore, cudaEvent_t* ev /* [5] */) {
-  const int nv = c->cfg.nv, nA = c->cfg.n_alpha;
-  const int T = (int)c->tt.size();
+extern "C++" {
+// parameters of the entry-table kernels (everything but the entry range)
+void fill_entq_params(dmx_ctx* c, EntqParams* eqp, bool fp32) {
+  EntqParams& eq = *eqp;
+  memset(&eq, 0, sizeof(eq));
+  const int nA = c->cfg.n_alpha;
   const int nd = (c->UQ - QHEAD) / QPLANE;
-  const bool fp32 = (c->cfg.flags & DMX_FP32_PAIRS) != 0;
-  const int64_t pstride = (c->E + NB) * FPLANE;
-  const int64_t e0 = c->h_cell_ptr[ck.c0], e1 = c->h_cell_ptr[ck.c1];
-  const int64_t nact = ck.o1 - ck.o0;
-  CU(cudaEventRecord(ev[0], c->stream));
-  EntqParams eq;
-  eq.U = c->pg.U; eq.UQ = c->UQ; eq.E0 = e0; eq.E = e1;
+  eq.U = c->pg.U; eq.UQ = c->UQ;
   eq.nd = nd; eq.sep0 = c->pg.sep0; eq.gp_stride = c->nvp * 3 + 8; eq.gprow = c->d_gprow.p;
   eq.ent_snp = c->d_ent_snp.p; eq.ent_ptr = c->d_ent_ptr.p; eq.reads = c->d_reads.p;
   eq.entq = c->d_entq.p;
   eq.ents = c->d_ents.p;
   eq.entf_head = fp32 ? c->d_entf_head.p : nullptr;
   eq.entf_plane = fp32 ? c->d_entf_plane.p : nullptr;
-  eq.entf_pstride = pstride;
+  eq.entf_pstride = (c->E + NB) * FPLANE;
   eq.perm = fp32 ? c->d_perm.p : nullptr;
   eq.snp_perm = fp32 ? c->d_snp_perm.p : nullptr;
-  if (fp32 && ck.c1 > ck.c0) {
-    // entry classes of the chunk's cells (affine entries first in the fp32 tables)
-    CU(launch_classify(c->d_cell_ptr.p, c->d_ent_ptr.p, c->d_reads.p, ck.c0, ck.c1, c->d_perm.p, c->d_cell_na.p, c->stream));
-    c->st.gpu_launches += 1;
-  }
+  eq.ecode = fp32 ? c->d_ecode.p : nullptr;
+  eq.memo_q = c->d_memo_q.p; eq.memo_fh = c->d_memo_fh.p; eq.memo_fp = c->d_memo_fp.p;
   memcpy(eq.pu, c->pg.pu, sizeof(double) * c->pg.U);
-  {
-    // record layout: GL[3] (written by the kernel), f[3] = Q'[0][l][0] of a separable plane 0, then per dense
-    // plane 9 values Q'[n][l][m] (+1 pad); oslot lists, per distinct p value, the record slots it feeds
-    std::vector<std::vector<int>> slots(c->pg.U);
-    if (c->pg.sep0)
-      for (int l = 0; l < 3; ++l) slots[c->pg.umap[l * 3]].push_back(3 + l);
-    for (int n = 0; n < nA; ++n)
-      if (c->dense_idx[n] >= 0)
-        for (int i = 0; i < 9; ++i) slots[c->pg.umap[n * 9 + i]].push_back(QHEAD + QPLANE * c->dense_idx[n] + i);
-    int o = 0;
-    memset(eq.slot_u, 0, sizeof(eq.slot_u));
-    for (int u2 = 0; u2 < c->pg.U; ++u2) {
-      eq.oslot_ptr[u2] = (uint8_t)o;
-      for (int sl : slots[u2]) { eq.oslot[o++] = (uint8_t)sl; eq.slot_u[sl] = (uint8_t)u2; }
-    }
-    eq.oslot_ptr[c->pg.U] = (uint8_t)o;
+  // record layout: GL[3] (written by the kernel), f[3] = Q'[0][l][0] of a separable plane 0, then per dense
+  // plane 9 values Q'[n][l][m] (+1 pad); oslot lists, per distinct p value, the record slots it feeds
+  std::vector<std::vector<int>> slots(c->pg.U);
+  if (c->pg.sep0)
+    for (int l = 0; l < 3; ++l) slots[c->pg.umap[l * 3]].push_back(3 + l);
+  for (int n = 0; n < nA; ++n)
+    if (c->dense_idx[n] >= 0)
+      for (int i = 0; i < 9; ++i) slots[c->pg.umap[n * 9 + i]].push_back(QHEAD + QPLANE * c->dense_idx[n] + i);
+  int o = 0;
+  for (int u2 = 0; u2 < c->pg.U; ++u2) {
+    eq.oslot_ptr[u2] = (uint8_t)o;
+    for (int sl : slots[u2]) { eq.oslot[o++] = (uint8_t)sl; eq.slot_u[sl] = (uint8_t)u2; }
+  }
+  eq.oslot_ptr[c->pg.U] = (uint8_t)o;
+}
+
+// Memo tables of the affine entries (fp32 scan): the entry-table kernels themselves run once on a synthetic pileup of
+// MEMO_ROWS entries -- one read of allele a and quality q in row a * 256 + q, no informative read in the last row --
+// so a memo record is bit for bit what the kernels would write for such an entry.  (The SNP-dependent factors of a
+// record are not memo material: entq_aff_kernel recomputes them.)  Needs the GP rows of SNP 0 to exist.
+int build_memo(dmx_ctx* c) {
+  const int nd = (c->UQ - QHEAD) / QPLANE;
+  std::vector<int64_t> ptr(MEMO_ROWS + 1);
+  std::vector<uint16_t> rd(MEMO_ROWS, 0);
+  for (int i = 0; i < MEMO_ROWS - 1; ++i) { ptr[i] = i; rd[i] = (uint16_t)i; }   // allele << 8 | quality
+  ptr[MEMO_ROWS - 1] = MEMO_ROWS - 1;
+  ptr[MEMO_ROWS] = MEMO_ROWS - 1;          // the last row has no read at all
+  DevBuf<int64_t> d_ptr;
+  DevBuf<uint16_t> d_rd;
+  DevBuf<int32_t> d_snp;
+  DevBuf<double> d_ents;
+  struct Rel { DevBuf<int64_t>* a; DevBuf<uint16_t>* b; DevBuf<int32_t>* s; DevBuf<double>* e;
+               ~Rel() { a->release(); b->release(); s->release(); e->release(); } } rel{&d_ptr, &d_rd, &d_snp, &d_ents};
+  CU(d_ptr.reserve(MEMO_ROWS + 1)); CU(d_rd.reserve(MEMO_ROWS)); CU(d_snp.reserve(MEMO_ROWS));
+  CU(d_ents.reserve((size_t)MEMO_ROWS * (2 + nd)));
+  CU(c->d_memo_q.reserve((size_t)MEMO_ROWS * c->UQ)); CU(c->d_memo_fh.reserve((size_t)MEMO_ROWS * FHEAD));
+  CU(c->d_memo_fp.reserve((size_t)std::max(nd, 1) * MEMO_ROWS * FPLANE));
+  CU(cudaMemcpyAsync(d_ptr.p, ptr.data(), ptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(d_rd.p, rd.data(), rd.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemsetAsync(d_snp.p, 0, MEMO_ROWS * sizeof(int32_t), c->stream));
+  EntqParams eq;
+  fill_entq_params(c, &eq, true);
+  eq.E0 = 0; eq.E = MEMO_ROWS;
+  eq.ent_snp = d_snp.p; eq.ent_ptr = d_ptr.p; eq.reads = d_rd.p;
+  eq.entq = c->d_memo_q.p; eq.ents = d_ents.p;
+  eq.entf_head = c->d_memo_fh.p; eq.entf_plane = c->d_memo_fp.p; eq.entf_pstride = (int64_t)MEMO_ROWS * FPLANE;
+  eq.perm = nullptr; eq.snp_perm = nullptr; eq.ecode = nullptr;
+  CU(launch_entq(eq, c->stream));
+  CU(cudaStreamSynchronize(c->stream));     // the staging vectors live on this stack frame
+  c->st.gpu_launches += 1;
+  c->memo_ready = true;
+  return DMX_OK;
+}
+
+// the full fp64 entry table (every entry through the general kernels): what the fp64 scan streams.  In fp32 mode
+// only the general entries have their records there after a run; dense llksAB blocks (dmx_get_pair, --write-pair,
+// candidate-list overflow) come from the fp64 scan and fill the rest in first.
+int ensure_entq_full(dmx_ctx* c) {
+  if (c->entq_full || !(c->cfg.flags & DMX_FP32_PAIRS) || c->E == 0) return DMX_OK;
+  EntqParams eq;
+  fill_entq_params(c, &eq, false);
+  eq.E0 = 0; eq.E = c->E;
+  CU(launch_entq(eq, c->stream));
+  c->st.gpu_launches += 1;
+  c->entq_full = true;
+  return DMX_OK;
+}
+}  // extern "C++"
+
+// ---- the kernels of one chunk (a contiguous cell-id range; its active cells are order[o0, o1)) ----------------------
+int enqueue_chunk(dmx_ctx* c, const Chunk& ck, const ScanParams& sp0, bool dev_rescore, cudaEvent_t* ev /* [5] */) {
+  const int nv = c->cfg.nv, nA = c->cfg.n_alpha;
+  const int T = (int)c->tt.size();
+  const int nd = (c->UQ - QHEAD) / QPLANE;
+  const bool fp32 = (c->cfg.flags & DMX_FP32_PAIRS) != 0;
+  const int64_t e0 = c->h_cell_ptr[ck.c0], e1 = c->h_cell_ptr[ck.c1];
+  const int64_t nact = ck.o1 - ck.o0;
+  CU(cudaEventRecord(ev[0], c->stream));
+  EntqParams eq;
+  fill_entq_params(c, &eq, fp32);
+  eq.E0 = e0; eq.E = e1;
+  if (fp32 && e1 > e0) {
+    // entry classes of the chunk's cells (affine entries first in the fp32 tables), then the affine entries from the
+    // memo tables and the general ones (the listed fifth or so) through the full computation
+    CU(launch_classify(c->d_cell_ptr.p, c->d_ent_ptr.p, c->d_reads.p, ck.c0, ck.c1, c->d_perm.p, c->d_cell_na.p,
+                       c->d_glist.p, c->stream));
+    CU(launch_entq_aff(eq, c->stream));
+    eq.glist = c->d_glist.p;
+    c->st.gpu_launches += 2;
   }
   CU(launch_entq(eq, c->stream));
   if (e1 > e0) c->st.gpu_launches += 1;
@@ -1126,6 +1202,7 @@ int enqueue_chunk(dmx_ctx* c, const Chunk& ck, const ScanParams& sp0, bool dev_r
     for (int n2 = 0; n2 < nA; ++n2) rp.dense_idx[n2] = (int8_t)c->dense_idx[n2];
     rp.gp = c->d_gprow.p + 8; rp.ent_snp = c->d_ent_snp.p; rp.entq = c->d_entq.p; rp.cell_ptr = c->d_cell_ptr.p;
     rp.cell_order = sp.cell_order; rp.lists = c->d_lists.p;
+    rp.ecode = fp32 ? c->d_ecode.p : nullptr; rp.memo_q = c->d_memo_q.p;
     rp.terms = c->d_terms.p;
     CU(launch_rescore(rp, nact, c->stream));
     if (nact) c->st.gpu_launches += 2 * (RMAX / RESC_FAST);
@@ -1170,6 +1247,7 @@ int run_path(dmx_ctx* c, bool pipelined) {
     CU(c->d_entf_head.reserve((size_t)(c->E + NB) * FHEAD));
     CU(c->d_entf_plane.reserve((size_t)pstride * std::max(nd, 1)));
     CU(c->d_perm.reserve((size_t)c->E + 1)); CU(c->d_snp_perm.reserve((size_t)c->E + NB)); CU(c->d_cell_na.reserve((size_t)nc + 1));
+    CU(c->d_ecode.reserve((size_t)c->E + 1)); CU(c->d_glist.reserve((size_t)c->E + 1));
   }
   CU(c->d_parts.reserve((size_t)nact * T + 1));
   CU(c->d_row0.reserve((size_t)nc * nA * nv + 1)); CU(c->d_singA.reserve((size_t)nc * nv + 1));
@@ -1220,6 +1298,8 @@ int run_path(dmx_ctx* c, bool pipelined) {
   if (pipelined) CU(cudaStreamWaitEvent(c->stream, ev_up[1], 0));
   CU(launch_gprow(c->d_gp.p, c->d_gprow.p, c->nsnps, nv, c->nvp, c->stream));
   if (c->nsnps) c->st.gpu_launches += 1;
+  c->entq_full = !fp32;
+  if (fp32 && !c->memo_ready && c->nsnps > 0 && c->E > 0) RC(build_memo(c));
   ScanParams sp;
   fill_scan_params(c, &sp);
   {

@@ -49,6 +49,7 @@ constexpr int FPLANE = 12;     // floats per entry and dense plane in the fp32 p
 // add and one multiply per hypothesis instead of a K = 3 dot product.  Their fp32 records:
 //   head   h1 c1 (pass 1, :455-458)  hs cs (separable plane)  flag (1: ref read, D = ref dosage)  3 pad
 //   plane  h cj ck, 9 pad
+constexpr int MEMO_ROWS = 513; // rows of the affine-entry memo tables
 constexpr int A_BLK4_FLT = 36; // floats per 4-sample block of an affine stage in the processed ring: 8 entries x 4 + pad
 constexpr int MAX_CAND = 8;    // near-tie candidates kept per task / per cell
 constexpr int MAX_U = DMX_MAX_ALPHA * 6 + 3;   // distinct mixing proportions p(n,l,m)
@@ -168,6 +169,8 @@ struct RescoreParams {
   const float* gp;
   const int32_t* ent_snp;
   const double* entq;
+  const uint16_t* ecode;       // fp32 scan: memo row per entry (0xffff: the entry has its own record in entq), or null
+  const double* memo_q;
   const int64_t* cell_ptr;
   const int32_t* cell_order;
   RescList* lists;             // [ncells]
@@ -207,6 +210,16 @@ struct EntqParams {
   int64_t entf_pstride;
   const int32_t* perm;         // [E] position of entry e in the class-sorted fp32 tables (classify_kernel)
   int32_t* snp_perm;           // [E] out: SNP id by position
+  // fp32 scan: affine entries (<= 1 informative read) take their records from a 513-row memo table -- every record
+  // value depends only on (allele, quality) of that read -- built once per context by the same kernels on a synthetic
+  // pileup (rows allele * 256 + quality, row 512 = no informative read); entq_aff_kernel handles them and the general
+  // kernels run over the list of the remaining entries
+  uint16_t* ecode;             // [E] out: memo row of an affine entry, 0xffff for a general entry
+  const double* memo_q;        // [MEMO_ROWS][UQ]
+  const float* memo_fh;        // [MEMO_ROWS][FHEAD]
+  const float* memo_fp;        // [nd][MEMO_ROWS][FPLANE]
+  const int32_t* glist;        // [E] entry at each class-sorted position, sign bit set for a general entry
+                               // (classify_kernel): the general kernels then run by position; null: all entries
   double* ents;                // [E][2 + nd]: the entry's factors of llk0s (:459), llks00 of a separable plane 0, and
                                // llks00[n] of every dense plane (:700-709); summed per cell by cell_scalars_kernel
   double pu[MAX_U];            // distinct p values (cmd_cram_demuxlet.cpp:613)
@@ -249,7 +262,8 @@ int launch_entq(const EntqParams& p, void* stream);
 // entry classes of cells [c0, c1): perm[e] = position of entry e inside its cell's block with the affine entries
 // (<= 1 informative read) first, both classes in entry order; cell_na[cell] = number of affine entries
 int launch_classify(const int64_t* cell_ptr, const int64_t* ent_ptr, const uint16_t* reads, int64_t c0, int64_t c1,
-                    int32_t* perm, int32_t* cell_na, void* stream);
+                    int32_t* perm, int32_t* cell_na, int32_t* glist, void* stream);
+int launch_entq_aff(const EntqParams& p, void* stream);
 int launch_pair_scan(const ScanParams& p, const ScanMaps& tm, bool fp32, void* stream);
 int launch_cell_scalars(const CellScalarParams& p, int64_t nactive, void* stream);
 int launch_merge(const MergeParams& p, int64_t nactive, void* stream);

@@ -357,8 +357,13 @@ __global__ void __launch_bounds__(256) entq_kernel(const __grid_constant__ EntqP
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPE;
   const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t e = p.E0 + gw * (32 / LPE) + lane / LPE;
+  int64_t e = p.E0 + gw * (32 / LPE) + lane / LPE;
   if (e >= p.E) return;   // whole groups leave together
+  if (p.glist) {            // fp32 scan: by position, general entries only
+    const int32_t v = __ldg(p.glist + e);
+    if (v >= 0) return;
+    e = (int64_t)(v & 0x7fffffff);
+  }
   const unsigned gmask = (LPE == 32) ? 0xffffffffu : (((1u << LPE) - 1u) << (lane - sub));
   double P[VPL], pu[VPL];
   bool ok[VPL];
@@ -442,8 +447,13 @@ __global__ void __launch_bounds__(128) entq1_kernel(const __grid_constant__ Entq
   __shared__ double s_val[UMAX][128];
   for (int i = threadIdx.x; i < 256; i += 128) { s_err[i] = c_err[i]; s_err3[i] = c_err3[i]; }
   __syncthreads();
-  const int64_t e = p.E0 + (int64_t)blockIdx.x * 128 + threadIdx.x;
+  int64_t e = p.E0 + (int64_t)blockIdx.x * 128 + threadIdx.x;
   if (e >= p.E) return;
+  if (p.glist) {            // fp32 scan: by position, general entries only
+    const int32_t v = __ldg(p.glist + e);
+    if (v >= 0) return;
+    e = (int64_t)(v & 0x7fffffff);
+  }
   const int nu = p.U;
   double P[UMAX], pu[UMAX], qu[UMAX];
 #pragma unroll
@@ -512,46 +522,102 @@ __global__ void __launch_bounds__(128) entq1_kernel(const __grid_constant__ Entq
   entq_emit(p, e, out, nvr, al1, [&](int slot) { return slot == 0 ? G0 : (slot == 1 ? G1 : (slot == 2 ? G2 : s_val[p.slot_u[slot]][tid])); });
 }
 
-// entry classes: one warp per cell, two passes over its entries (count the affine ones, then hand out positions)
+// entry classes: one warp per cell, one pass over its entries.  The affine entries take the front positions of the
+// cell's block in entry order, the general ones the back positions in reverse entry order (any fixed order serves: the
+// products commute and the exact re-scorer walks the original order).  glist[pos] = entry at that position, sign bit
+// set for a general entry: the general entry-table kernels run over positions and skip the others.
 __global__ void __launch_bounds__(128) classify_kernel(const int64_t* __restrict__ cell_ptr,
                                                        const int64_t* __restrict__ ent_ptr,
                                                        const uint16_t* __restrict__ reads, int64_t c0, int64_t c1,
-                                                       int32_t* __restrict__ perm, int32_t* __restrict__ cell_na) {
+                                                       int32_t* __restrict__ perm, int32_t* __restrict__ cell_na,
+                                                       int32_t* __restrict__ glist) {
   const int lane = threadIdx.x & 31;
   const int64_t cell = c0 + (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   if (cell >= c1) return;
   const int64_t e0 = cell_ptr[cell], e1 = cell_ptr[cell + 1];
-  auto is_affine = [&](int64_t e) {
-    int nvr = 0;
-    for (int64_t r = ent_ptr[e]; r < ent_ptr[e + 1]; ++r) nvr += (reads[r] >> 8) != 2;
-    return nvr <= 1;
-  };
-  int na = 0;
-  for (int64_t b = e0; b < e1; b += 32) {
-    const int64_t e = b + lane;
-    na += __popc(__ballot_sync(0xffffffffu, e < e1 && is_affine(e)));
-  }
   int ra = 0, rg = 0;
+  const unsigned lt = (1u << lane) - 1u;
   for (int64_t b = e0; b < e1; b += 32) {
     const int64_t e = b + lane;
-    const bool in = e < e1, aff = in && is_affine(e);
-    const unsigned ma = __ballot_sync(0xffffffffu, aff), mg = __ballot_sync(0xffffffffu, in && !aff);
-    const unsigned lt = (1u << lane) - 1u;
+    const bool in = e < e1;
+    bool aff = false;
     if (in) {
-      const int64_t pos = aff ? e0 + ra + __popc(ma & lt) : e0 + na + rg + __popc(mg & lt);
+      int nvr = 0;
+      for (int64_t r = ent_ptr[e]; r < ent_ptr[e + 1]; ++r) nvr += (reads[r] >> 8) != 2;
+      aff = nvr <= 1;
+    }
+    const unsigned ma = __ballot_sync(0xffffffffu, aff), mg = __ballot_sync(0xffffffffu, in && !aff);
+    if (in) {
+      const int64_t pos = aff ? e0 + ra + __popc(ma & lt) : e1 - 1 - (rg + __popc(mg & lt));
       perm[e] = (int32_t)(pos - e);
+      glist[pos] = (int32_t)e | (aff ? 0 : (int32_t)0x80000000);
     }
     ra += __popc(ma);
     rg += __popc(mg);
   }
-  if (lane == 0) cell_na[cell] = na;
+  if (lane == 0) cell_na[cell] = ra;
 }
 
 int launch_classify(const int64_t* cell_ptr, const int64_t* ent_ptr, const uint16_t* reads, int64_t c0, int64_t c1,
-                    int32_t* perm, int32_t* cell_na, void* stream) {
+                    int32_t* perm, int32_t* cell_na, int32_t* glist, void* stream) {
   if (c1 <= c0) return 0;
   classify_kernel<<<(unsigned)((c1 - c0 + 3) / 4), 128, 0, (cudaStream_t)stream>>>(cell_ptr, ent_ptr, reads, c0, c1, perm,
-                                                                                   cell_na);
+                                                                                   cell_na, glist);
+  return (int)cudaGetLastError();
+}
+
+// affine entries of the fp32 scan: records from the memo tables, the SNP-dependent factors computed here
+__global__ void __launch_bounds__(256) entq_aff_kernel(const __grid_constant__ EntqParams p) {
+  const int64_t e = p.E0 + (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (e >= p.E) return;
+  int nvr = 0;
+  uint32_t rd1 = 0;
+  for (int64_t r = p.ent_ptr[e]; r < p.ent_ptr[e + 1]; ++r) {
+    const uint32_t rd = p.reads[r];
+    if ((rd >> 8) != 2) { ++nvr; rd1 = rd; }
+  }
+  if (nvr > 1) {
+    p.ecode[e] = 0xffffu;
+    return;
+  }
+  const int idx = nvr == 0 ? MEMO_ROWS - 1 : (int)rd1;      // allele * 256 + quality
+  p.ecode[e] = (uint16_t)idx;
+  const double* mq = p.memo_q + (int64_t)idx * p.UQ;
+  const int snp = __ldg(p.ent_snp + e);
+  const double* z = reinterpret_cast<const double*>(p.gprow + (int64_t)snp * p.gp_stride);
+  const double z0 = __ldg(z), z1 = __ldg(z + 1), z2 = __ldg(z + 2);
+  // the same expressions as entq_emit
+  const double g0 = __ldg(mq), g1 = __ldg(mq + 1), g2 = __ldg(mq + 2);
+  const double s0 = fma(g2, z2, fma(g1, z1, g0 * z0));
+  double s1 = 1.0;
+  if (p.sep0) {
+    const double f0 = __ldg(mq + 3), f1 = __ldg(mq + 4), f2 = __ldg(mq + 5);
+    s1 = fma(f2, z2, fma(f1, z1, f0 * z0)) * ((z0 + z1) + z2);
+  }
+  double* sc = p.ents + e * (2 + p.nd);
+  sc[0] = s0;
+  sc[1] = s1;
+  const int64_t pos = e + (int64_t)__ldg(p.perm + e);
+  p.snp_perm[pos] = snp;
+  const float4* mh = reinterpret_cast<const float4*>(p.memo_fh + (int64_t)idx * FHEAD);
+  float4* fh = reinterpret_cast<float4*>(p.entf_head + pos * FHEAD);
+  fh[0] = __ldg(mh);
+  fh[1] = __ldg(mh + 1);
+  for (int d = 0; d < p.nd; ++d) {
+    const double* Q = mq + QHEAD + QPLANE * d;
+    const double t0 = fma(__ldg(Q + 2), z2, fma(__ldg(Q + 1), z1, __ldg(Q + 0) * z0));
+    const double t1 = fma(__ldg(Q + 5), z2, fma(__ldg(Q + 4), z1, __ldg(Q + 3) * z0));
+    const double t2 = fma(__ldg(Q + 8), z2, fma(__ldg(Q + 7), z1, __ldg(Q + 6) * z0));
+    sc[2 + d] = fma(z2, t2, fma(z1, t1, z0 * t0));
+    *reinterpret_cast<float4*>(p.entf_plane + d * p.entf_pstride + pos * FPLANE) =
+        __ldg(reinterpret_cast<const float4*>(p.memo_fp + ((int64_t)d * MEMO_ROWS + idx) * FPLANE));
+  }
+}
+
+int launch_entq_aff(const EntqParams& p, void* stream) {
+  const int64_t n = p.E - p.E0;
+  if (n <= 0) return 0;
+  entq_aff_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p);
   return (int)cudaGetLastError();
 }
 
@@ -2245,6 +2311,10 @@ __global__ void __launch_bounds__(256) rescore_terms_kernel(const __grid_constan
       const int64_t e = e0 + i;
       const float* g = p.gp + (int64_t)__ldg(p.ent_snp + e) * p.gp_stride;
       const double* q = p.entq + e * p.UQ;
+      if (p.ecode) {
+        const uint32_t code = __ldg(p.ecode + e);
+        if (code != 0xffffu) q = p.memo_q + (int64_t)code * p.UQ;
+      }
 #pragma unroll
       for (int h = 0; h < RESC_FAST; ++h)
         if (h < H) out[h * n + i] = exact_term(g, q, hyp[h], p.dense_idx);
