@@ -286,7 +286,7 @@ class Case:
         self.pair_buf = None
         if args.write_pair:   # --write-pair: the dense llksAB block of every barcode comes back too (:772-797)
             per = plp.nv * plp.nv * len(alphas)
-            self.pair_slab = max(1, min(plp.ncells, (256 << 20) // (per * 8)))
+            self.pair_slab = max(1, min(plp.ncells, (8 << 30) // (per * 8)))     # whole job if it fits 8 GB of host memory
             self.pair_buf = np.zeros((self.pair_slab, plp.nv, plp.nv, len(alphas)))
             self.pair_bytes = plp.ncells * per * 8
 

@@ -123,7 +123,7 @@ struct dmx_ctx {
   // device
   DevBuf<float> d_gp;              // uploaded [nsnps][nvp*3]
   DevBuf<float> d_gprow;           // [nsnps][8 + nvp*3]: gp0 | samples (gprow_kernel)
-  DevBuf<double> d_entq, d_row0, d_singA, d_lb, d_p1, d_p1_0, d_l00, d_sing, d_dense;
+  DevBuf<double> d_entq, d_row0, d_singA, d_lb, d_p1, d_p1_0, d_l00, d_sing, d_dense, d_dense2;
   DevBuf<double> d_terms;          // [E][RESC_FAST] log terms of the two-phase exact re-scorer
   DevBuf<double> d_ents;           // [E][2 + nd] per-entry factors of llk0s / llks00 (entq -> cell_scalars)
   DevBuf<float> d_entf_head, d_entf_plane;   // fp32 copies of the entry records (fp32 pair scan), class-sorted per cell
@@ -151,7 +151,7 @@ struct dmx_ctx {
 
   // read-back (pinned)
   PinBuf<CellOut> r_out;
-  PinBuf<double> r_sing, r_row0, r_l00, r_p1, r_p1_0, r_dense;
+  PinBuf<double> r_sing, r_row0, r_l00, r_p1, r_p1_0, r_dense, r_dense2;
 
   std::vector<dmx_best_rec> best;
   dmx_stats st;
@@ -466,56 +466,87 @@ int for_each_kid(dmx_ctx* c, const std::function<int(int)>& f);
 int ensure_entq_full(dmx_ctx* c);
 
 // dense llksAB for a list of active cells (device order buffer is temporarily replaced)
-int dense_scan(dmx_ctx* c, const std::vector<int32_t>& cells, double* host_out /* [n][nv][nv][nA] */) {
+// Dense llksAB of a list of active cells: block i of the list lands at host_out + dest[i] * nv * nv * nA (dest null:
+// i).  Two batches in flight: the fp64 scan of batch b runs while batch b - 1 comes back into pinned memory and the
+// host threads move batch b - 2 ... b - 1 to its (usually pageable) destination.
+int dense_scan(dmx_ctx* c, const std::vector<int32_t>& cells, double* host_out, const int64_t* dest = nullptr) {
   const int nv = c->cfg.nv, nA = c->cfg.n_alpha;
   const size_t per = (size_t)nv * nv * nA;
+  if (cells.empty()) return DMX_OK;
   if (!c->kids.empty()) {
     // sharded context: every shard scans its own cells of the list (on its own device, in parallel)
     const int nk = (int)c->kids.size();
     std::vector<std::vector<int32_t>> mine(nk);
-    std::vector<std::vector<size_t>> at(nk);
+    std::vector<std::vector<int64_t>> at(nk);
     for (size_t i = 0; i < cells.size(); ++i) {
       const int k = (int)(std::upper_bound(c->kid_lo.begin(), c->kid_lo.end(), (int64_t)cells[i]) - c->kid_lo.begin()) - 1;
       mine[k].push_back((int32_t)(cells[i] - c->kid_lo[k]));
-      at[k].push_back(i);
+      at[k].push_back(dest ? dest[i] : (int64_t)i);
     }
-    return for_each_kid(c, [&](int k) {
-      if (mine[k].empty()) return (int)DMX_OK;
-      std::vector<double> tmp(mine[k].size() * per);
-      const int rc = dense_scan(c->kids[k], mine[k], tmp.data());
-      if (rc != DMX_OK) return rc;
-      for (size_t i = 0; i < mine[k].size(); ++i) memcpy(host_out + at[k][i] * per, tmp.data() + i * per, per * sizeof(double));
-      return (int)DMX_OK;
-    });
+    return for_each_kid(c, [&](int k) { return dense_scan(c->kids[k], mine[k], host_out, at[k].data()); });
   }
   CU(cudaSetDevice(c->cfg.device));
   RC(ensure_entq_full(c));
-  const size_t max_batch = std::max<size_t>(1, ((size_t)1 << 30) / (per * sizeof(double)));
-  DevBuf<int32_t> d_cells;
+  const size_t batch = std::min(cells.size(), std::max<size_t>(1, ((size_t)256 << 20) / (per * sizeof(double))));
+  const size_t nb = (cells.size() + batch - 1) / batch;
+  const int depth = nb > 1 ? 2 : 1;
+  DevBuf<int32_t> d_cells[2];
   DevBuf<Part> d_parts;
-  CU(d_cells.reserve(std::min(cells.size(), max_batch)));
-  CU(d_parts.reserve(std::min(cells.size(), max_batch) * c->tt.size()));
-  CU(c->d_dense.reserve(std::min(cells.size(), max_batch) * per));
-  for (size_t lo = 0; lo < cells.size(); lo += max_batch) {
-    const size_t n = std::min(max_batch, cells.size() - lo);
-    CU(cudaMemcpyAsync(d_cells.p, cells.data() + lo, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  DevBuf<double>& d_dense2 = c->d_dense2;   // second device / pinned buffers (kept by the context between calls)
+  PinBuf<double>& pin2 = c->r_dense2;
+  cudaEvent_t ev_scan[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
+  struct Rel {
+    DevBuf<int32_t>* a; DevBuf<Part>* b; cudaEvent_t* e1; cudaEvent_t* e2;
+    ~Rel() {
+      a[0].release(); a[1].release(); b->release();
+      for (int i = 0; i < 2; ++i) { if (e1[i]) cudaEventDestroy(e1[i]); if (e2[i]) cudaEventDestroy(e2[i]); }
+    }
+  } rel{d_cells, &d_parts, ev_scan, ev_copy};
+  CU(d_parts.reserve(batch * c->tt.size()));
+  CU(c->d_dense.reserve(batch * per)); CU(c->r_dense.reserve(batch * per));
+  if (depth == 2) { CU(d_dense2.reserve(batch * per)); CU(pin2.reserve(batch * per)); }
+  for (int i = 0; i < depth; ++i) {
+    CU(d_cells[i].reserve(batch));
+    CU(cudaEventCreateWithFlags(&ev_scan[i], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ev_copy[i], cudaEventDisableTiming));
+  }
+  double* dbuf[2] = {c->d_dense.p, d_dense2.p};
+  double* pbuf[2] = {c->r_dense.p, pin2.p};
+  const int nth = host_threads(c);
+  auto scatter = [&](size_t b) -> int {      // batch b: pinned buffer -> destination blocks
+    CU(cudaEventSynchronize(ev_copy[b % depth]));
+    const size_t lo = b * batch, n = std::min(batch, cells.size() - lo);
+    const double* src = pbuf[b % depth];
+    c->pool->run((int64_t)n, nth, [&](int64_t i, int) {
+      const int64_t d = dest ? dest[lo + (size_t)i] : (int64_t)(lo + (size_t)i);
+      memcpy(host_out + (size_t)d * per, src + (size_t)i * per, per * sizeof(double));
+    });
+    return DMX_OK;
+  };
+  for (size_t b = 0; b < nb; ++b) {
+    const int s = (int)(b % depth);
+    const size_t lo = b * batch, n = std::min(batch, cells.size() - lo);
+    if (b >= (size_t)depth) CU(cudaStreamWaitEvent(c->stream, ev_copy[s], 0));   // its device buffer has been read back
+    CU(cudaMemcpyAsync(d_cells[s].p, cells.data() + lo, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     ScanParams p;
     fill_scan_params(c, &p);
-    p.cell_order = d_cells.p;
+    p.cell_order = d_cells[s].p;
     p.parts = d_parts.p;
-    p.dense = c->d_dense.p;
+    p.dense = dbuf[s];
     p.ntasks = (int64_t)n * p.T;
     // dense blocks always come from the fp64 scan: every hypothesis keeps its own exponent there, whereas the fp32
     // scan lets hypotheses that are hopeless against the best of their tile underflow
     CU(launch_pair_scan(p, c->maps, false, c->stream));
     CU(launch_fill_sep_dense(p, (int64_t)n, c->stream));
     c->st.gpu_launches += 1 + (p.sep0 ? 1 : 0);
-    CU(cudaMemcpyAsync(host_out + lo * per, c->d_dense.p, n * per * sizeof(double), cudaMemcpyDeviceToHost,
-                       c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaEventRecord(ev_scan[s], c->stream));
+    if (b >= 1) RC(scatter(b - 1));            // frees the pinned buffer batch b + 1 will use; overlaps scan b
+    CU(cudaStreamWaitEvent(c->stream3, ev_scan[s], 0));
+    CU(cudaMemcpyAsync(pbuf[s], dbuf[s], n * per * sizeof(double), cudaMemcpyDeviceToHost, c->stream3));
+    CU(cudaEventRecord(ev_copy[s], c->stream3));
   }
-  d_cells.release();
-  d_parts.release();
+  RC(scatter(nb - 1));
+  CU(cudaStreamSynchronize(c->stream));
   return DMX_OK;
 }
 
@@ -849,7 +880,7 @@ void dmx_destroy(dmx_ctx* c) {
   c->d_lists.release(); c->r_lists.release();
   c->o_gp.release(); c->o_cell_ptr.release(); c->o_ent_ptr.release(); c->o_ent_snp.release(); c->o_reads.release();
   c->r_out.release(); c->r_sing.release(); c->r_row0.release(); c->r_l00.release(); c->r_p1.release();
-  c->r_p1_0.release(); c->r_dense.release();
+  c->r_p1_0.release(); c->r_dense.release(); c->r_dense2.release(); c->d_dense2.release();
   for (int i = 0; i < 6; ++i)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   delete c->pool;
@@ -1381,16 +1412,16 @@ int run_path(dmx_ctx* c, bool pipelined) {
     // candidates from a dense llksAB scan of just those cells
     const size_t per = (size_t)nv * nv * nA;
     const size_t batch = std::max<size_t>(1, ((size_t)256 << 20) / (per * sizeof(double)));
-    CU(c->r_dense.reserve(std::min(batch, ov.size()) * per));
+    std::vector<double> dense_host(std::min(batch, ov.size()) * per);
     for (size_t lo = 0; lo < ov.size(); lo += batch) {
       const size_t n = std::min(batch, ov.size() - lo);
       std::vector<int32_t> cells(ov.begin() + lo, ov.begin() + lo + n);
-      int rc = dense_scan(c, cells, c->r_dense.p);
+      int rc = dense_scan(c, cells, dense_host.data());
       if (rc != DMX_OK) return rc;
       c->pool->run((int64_t)n, nth, [&](int64_t i, int tid) {
         std::vector<Hyp> cands;
         const int64_t cl = cells[i];
-        candidates_from_dense(c->r_dense.p + (size_t)i * per, nv, nA, 1, sp.eps_rel,
+        candidates_from_dense(dense_host.data() + (size_t)i * per, nv, nA, 1, sp.eps_rel,
                               sp.eps_ent * (double)(c->h_cell_ptr[cl + 1] - c->h_cell_ptr[cl]), &cands);
         do_cell(cells[i], cands, tid);
         c->best[cells[i]].exact_mask |= DMX_X_FULLCELL;
@@ -1489,16 +1520,16 @@ int dmx_get_pair(dmx_ctx* c, int64_t cell_lo, int64_t cell_hi, double* llkAB) {
   if (!c->computed) return DMX_E_STATE;
   const size_t per = (size_t)c->cfg.nv * c->cfg.nv * c->cfg.n_alpha;
   std::vector<int32_t> cells;
-  for (int64_t i = cell_lo; i < cell_hi; ++i)
-    if (c->status[i] == 0) cells.push_back((int32_t)i);
-  memset(llkAB, 0, (size_t)(cell_hi - cell_lo) * per * sizeof(double));
-  if (cells.empty()) return DMX_OK;
-  std::vector<double> tmp(cells.size() * per);
-  int rc = dense_scan(c, cells, tmp.data());
-  if (rc != DMX_OK) return rc;
-  for (size_t i = 0; i < cells.size(); ++i)
-    memcpy(llkAB + (size_t)(cells[i] - cell_lo) * per, tmp.data() + i * per, per * sizeof(double));
-  return DMX_OK;
+  std::vector<int64_t> dst;
+  for (int64_t i = cell_lo; i < cell_hi; ++i) {
+    if (c->status[i] == 0) {
+      cells.push_back((int32_t)i);
+      dst.push_back(i - cell_lo);
+    } else {
+      memset(llkAB + (size_t)(i - cell_lo) * per, 0, per * sizeof(double));   // no row in the output files
+    }
+  }
+  return dense_scan(c, cells, llkAB, dst.data());
 }
 
 int dmx_rescore(dmx_ctx* c, int64_t cell, int32_t j, int32_t k, int32_t n, double* out) {

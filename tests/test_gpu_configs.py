@@ -191,3 +191,36 @@ def test_sharded_cli_and_field(tmp_path):
     many.set_pileup_arrays(p.cell_ptr, p.ent_snp, p.ent_ptr, p.reads, p.totl, p.npass, p.uniq)
     many.run()
     assert one.best().tobytes() == many.best().tobytes()
+
+
+# ---- the documented call site, compiled against the reference's real container --------
+def _golden():
+    import json
+    here = os.path.dirname(os.path.abspath(__file__))
+    return sorted(json.load(open(os.path.join(here, "golden", "manifest.json"))).items())
+
+
+@pytest.mark.parametrize("name,m", _golden())
+def test_reference_side_binding(name, m, tmp_path):
+    """oracle/_ref/ref_bind = the reference's sc_dropseq_lib_t (its own add_snp / add_cell / add_read) + the flattening
+    block of INTEGRATION.md + libdmx: its four files against the ones the reference's lines 386-881 wrote for the same
+    pileup (tests/golden)"""
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = os.path.join(os.path.dirname(here), "oracle", "_ref", "ref_bind")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_bind is built only where /root/reference exists (it travels with the snapshot)")
+    gold = os.path.join(here, "golden", name)
+    cmd = [exe, gold + ".dmxp", str(tmp_path / "b"), "--write-pair"]
+    for a in m["alphas"]:
+        cmd += ["--alpha", repr(float(a))]
+    for opt, key in (("--doublet-prior", "doublet_prior"), ("--min-total", "min_total"), ("--min-uniq", "min_uniq"),
+                     ("--min-snp", "min_snp")):
+        if key in m:
+            cmd += [opt, str(m[key])]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    from tests.test_gpu_parity import BEST_EXACT, ROW_EXACT
+    diff_tsv(gold + ".best", tmp_path / "b.best", BEST_EXACT)
+    for ext in ("single", "sing2", "pair"):
+        diff_tsv(gold + "." + ext, tmp_path / ("b." + ext), ROW_EXACT)

@@ -153,3 +153,13 @@ def test_cli_option_handling_without_a_device():
     assert r.returncode == 1 and "--plp" in r.stderr
     r = subprocess.run([exe, "--plp", "/nonexistent.dmxp", "--out", "o"], capture_output=True, text=True)
     assert r.returncode == 1 and "Cannot open" in r.stderr
+
+
+def test_integration_doc_block_is_the_compiled_one():
+    """INTEGRATION.md section 2 shows the call site a maintainer adds to cmd_cram_demuxlet.cpp; oracle/ref_bind.cpp
+    compiles oracle/integration_block.inc around the reference's real sc_dropseq_lib_t.  The two texts must be the
+    same, so the documented boundary is the tested one."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md = open(os.path.join(root, "INTEGRATION.md")).read()
+    blk = open(os.path.join(root, "oracle", "integration_block.inc")).read()
+    assert blk.strip() and blk in md
