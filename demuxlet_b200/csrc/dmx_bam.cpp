@@ -16,7 +16,7 @@
 // outside the aligned span yields no base, so testing exactly the SNPs with read start <= pos < read end on the read's
 // chromosome, in VCF order, gives the same tuples.  BAM decoding (BGZF = a series of gzip members, which zlib's gzread
 // walks through; record layout of the SAM specification section 4.2) replaces htslib's sam_read1 / bam_aux_get.
-// Not handled: CRAM, SAM text, --tag-UMI "" (the reference then draws rand() UMIs).  Parity: the checker is
+// Not handled: CRAM, SAM text.  --tag-UMI "" reproduces the reference's unseeded rand() UMIs.  Parity: the checker is
 // the python restatement in tests/bamio.py on generated BAM files -- "parity unpinned" against htslib itself.
 #include <stdint.h>
 #include <stdio.h>
@@ -123,8 +123,8 @@ int dmx_sweep_bam(const char* path, const dmx_sweep_opts* o, int32_t n_chrom, co
       (n_chrom > 0 && !chroms))
     return DMX_E_INVALID;
   *out = nullptr;
-  if (!o->tag_umi || !o->tag_umi[0]) {
-    g_bam_error = "--tag-UMI \"\" (random UMIs, cmd_cram_demuxlet.cpp:276) is not supported";
+  if (!o->tag_umi) {
+    g_bam_error = "tag_umi is null";
     return DMX_E_UNSUPPORTED;
   }
   for (int64_t i = 1; i < nsnps; ++i)
@@ -170,6 +170,10 @@ int dmx_sweep_bam(const char* path, const dmx_sweep_opts* o, int32_t n_chrom, co
   std::unordered_set<std::string> groups;
   for (int64_t i = 0; i < o->n_groups; ++i) groups.insert(o->groups[i]);
   const bool use_group = o->tag_group && o->tag_group[0];
+  struct random_data rnd_buf;                 // glibc's rand() of an unseeded process: TYPE_3 state, seed 1
+  char rnd_state[128];
+  memset(&rnd_buf, 0, sizeof(rnd_buf));
+  initstate_r(1u, rnd_state, sizeof(rnd_state), &rnd_buf);
 
   dmx_sweep* sw = new dmx_sweep();
   sw->umi_off.push_back(0);
@@ -226,9 +230,17 @@ int dmx_sweep_bam(const char* path, const dmx_sweep_opts* o, int32_t n_chrom, co
         ibcd = it->second;
       }
     }
-    // UMI (:272-293): a missing tag leaves "."
+    // UMI (:272-293): a missing tag leaves "."; --tag-UMI "" draws "." + hex(rand()) per read (:274-276).  The
+    // reference never seeds rand(), so its UMIs are glibc's default sequence (TYPE_3 generator, seed 1): the same
+    // numbers come from a private random_r state here, whatever else the process does with rand().
     const char* sumi = ".";
-    {
+    char rnd_umi[16];
+    if (!o->tag_umi[0]) {
+      int32_t rv = 0;
+      random_r(&rnd_buf, &rv);
+      snprintf(rnd_umi, sizeof(rnd_umi), ".%x", (unsigned)rv);
+      sumi = rnd_umi;
+    } else {
       const char* z = aux_get_z(aux, end, o->tag_umi);
       if (z) sumi = z;
     }

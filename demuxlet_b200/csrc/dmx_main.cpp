@@ -231,6 +231,11 @@ int main(int argc, char** argv) {
   if (sam_path && !vcf_path) die("--sam needs --vcf (the SNPs the reads are piled up on)");
   if ((sm_list || !sm_ids.empty()) && !vcf_path) die("--sm / --sm-list select samples of --vcf", "");
   if (alpha.empty()) { alpha.push_back(0.0); alpha.push_back(0.5); }   // :78-90
+  // :121-139: a tag is empty or exactly two characters
+  if (so.tag_group && so.tag_group[0] && strlen(so.tag_group) != 2)
+    die("Cannot recognize group tag %s. It is suppose to be a length 2 string", so.tag_group);
+  if (so.tag_umi && so.tag_umi[0] && strlen(so.tag_umi) != 2)
+    die("Cannot recognize UMI tag %s. It is suppose to be a length 2 string", so.tag_umi);
   if (!gpu_list.empty()) gpu = gpu_list[0];   // the VCF-side device work (site filter) runs on the first one
 
   if (field && !field_path && !vcf_path)
@@ -331,6 +336,8 @@ int main(int argc, char** argv) {
       int64_t nc = 0, nr = 0, ub = 0, cnt[4] = {0, 0, 0, 0};
       dmx_sweep_sizes(sw, &nc, &nr, &ub);
       dmx_sweep_counts(sw, &cnt[0], &cnt[1], &cnt[2], &cnt[3]);
+      if (cnt[0] > 0 && cnt[2] + cnt[1] == cnt[0] && cnt[2] > 0)   // :176-178
+        die("Your VCF/BCF files and SAM/BAM/CRAM files does not have any matching chromosomes%s", "");
       std::vector<int32_t> rc_cell((size_t)nr), rc_snp((size_t)nr);
       std::vector<uint8_t> rc_al((size_t)nr), rc_bq((size_t)nr);
       std::vector<char> umi_buf((size_t)std::max<int64_t>(ub, 1));
@@ -366,6 +373,25 @@ int main(int argc, char** argv) {
     fprintf(stderr, "NOTICE - %lld droplets, %lld SNPs, %lld samples, %lld (droplet, SNP) entries, %lld reads\n",
             (long long)p.ncells, (long long)p.nsnps, (long long)p.nv, (long long)p.E, (long long)p.R);
 
+  if (p.ncells == 0) {
+    // no droplet at all (empty BAM, --group-list matching nothing): the reference's loops run over an empty bc_map and
+    // leave the header lines (:470, :533, :570-571)
+    const std::string pre(out);
+    struct { const char* ext; const char* hdr; } files[4] = {
+        {".single", "BARCODE\tSM_ID\tRD.TOTL\tRD.PASS\tRD.UNIQ\tN.SNP\tLLK1\tLLK0\tPOSTPRB\n"},
+        {".sing2", "BARCODE\tSM_ID\tRD.TOTL\tRD.PASS\tRD.UNIQ\tN.SNP\tLLK1\tLLK0\tPOSTPRB\n"},
+        {".best", "BARCODE\tRD.TOTL\tRD.PASS\tRD.UNIQ\tN.SNP\tBEST\tSNG.1ST\tSNG.LLK1\tSNG.2ND\tSNG.LLK2\tSNG.LLK0\tDBL.1ST\t"
+                  "DBL.2ND\tALPHA\tLLK12\tLLK1\tLLK2\tLLK10\tLLK20\tLLK00\tPRB.DBL\tPRB.SNG1\n"},
+        {".pair", "BARCODE\tSM1.ID\tSM2.ID\tLLK12\tPOSTPRB\n"}};
+    for (int f = 0; f < (write_pair ? 4 : 3); ++f) {
+      FILE* w = fopen((pre + files[f].ext).c_str(), "w");
+      if (!w) die("Cannot open file %s for writing", (pre + files[f].ext).c_str());
+      fputs(files[f].hdr, w);
+      fclose(w);
+    }
+    fprintf(stderr, "NOTICE - no droplet to score: header-only output files written\n");
+    return 0;
+  }
   dmx_config cfg;
   dmx_config_default(&cfg);
   cfg.nv = (int32_t)p.nv;

@@ -12,7 +12,8 @@
 //        the same through PhredHelper.h:40's uint32_t cast: > 255)
 // Records are delivered in file order; records whose allele count is not 2 are skipped and counted (demuxlet sets
 // maxAlleles = 2, cmd_cram_demuxlet.cpp:26; a record without ALT cannot pass --min-mac 1).  All samples are selected
-// (no --sm / --sm-list).  No reference test pins htslib's parse, so the pin of THIS reader is its python restatement
+// (dmx_vcf_select applies --sm / --sm-list afterwards).  The chromosome ids follow the header's ##contig lines, then first
+// appearance in the records (htslib's dictionary: bcf_hdr_name2id, cmd_cram_demuxlet.cpp:197-199).  No reference test pins htslib's parse, so the pin of THIS reader is its python restatement
 // (tests/vcfio.py) on generated files: "parity unpinned" against htslib itself.
 #include <stdint.h>
 #include <stdio.h>
@@ -164,6 +165,14 @@ void parse_range(const std::vector<Line>& lines, size_t lo, size_t hi, int32_t f
     // n_allele = 1 + number of ALT alleles ("." = none)
     split(cols[4].p, cols[4].p + cols[4].n, ',', &alts);
     const bool no_alt = cols[4].n == 1 && cols[4].p[0] == '.';
+    const std::string chrom(cols[0].p, cols[0].n);
+    size_t chrom_id = v->chroms.size();
+    if (!v->chroms.empty() && v->chroms.back() == chrom) chrom_id = v->chroms.size() - 1;
+    else {
+      for (chrom_id = 0; chrom_id < v->chroms.size(); ++chrom_id)
+        if (v->chroms[chrom_id] == chrom) break;
+      if (chrom_id == v->chroms.size()) v->chroms.push_back(chrom);   // htslib adds an undeclared contig on sight
+    }
     if (no_alt || alts.size() != 1) { ++v->n_skipped; continue; }
     split(cols[8].p, cols[8].p + cols[8].n, ':', &keys);
     int i_gt = -1, i_f = -1;
@@ -173,16 +182,7 @@ void parse_range(const std::vector<Line>& lines, size_t lo, size_t hi, int32_t f
     }
     if (i_gt < 0) return fail(lines[li].no, "no GT in FORMAT (demuxlet's record filter needs it)");
     if (want && i_f < 0) return fail(lines[li].no, std::string("no ") + want + " in FORMAT");
-    const std::string chrom(cols[0].p, cols[0].n);
-    if (v->chroms.empty() || v->chroms.back() != chrom) {
-      size_t r = 0;
-      for (; r < v->chroms.size(); ++r)
-        if (v->chroms[r] == chrom) break;
-      if (r == v->chroms.size()) v->chroms.push_back(chrom);
-      v->rid.push_back((int32_t)r);
-    } else {
-      v->rid.push_back((int32_t)v->chroms.size() - 1);
-    }
+    v->rid.push_back((int32_t)chrom_id);
     v->pos.push_back(conv_int(cols[1].p, cols[1].p + cols[1].n) - 1);
     v->ref.push_back(cols[3].n ? cols[3].p[0] : 'N');
     v->alt.push_back(cols[4].n ? cols[4].p[0] : 'N');
@@ -234,7 +234,26 @@ int dmx_vcf_read(const char* path, int32_t field, dmx_vcf** out) {
     ++lineno;
     if (e > p) {
       if (*p == '#') {
-        if (e - p > 6 && memcmp(p, "#CHROM", 6) == 0) {
+        if (e - p > 13 && memcmp(p, "##contig=<", 10) == 0) {
+          // the header's contig dictionary defines the chromosome ids (bcf_hdr_name2id, cmd_cram_demuxlet.cpp:197-199):
+          // a read on a declared contig counts for its droplet even when no record of the file lies there
+          const char* q = p + 10;
+          while (q < e) {
+            const char* key = q;
+            while (q < e && *q != '=' && *q != ',' && *q != '>') ++q;
+            const bool is_id = q - key == 2 && key[0] == 'I' && key[1] == 'D';
+            if (q < e && *q == '=') ++q;
+            const char* val = q;
+            if (q < e && *q == '"') { ++q; while (q < e && *q != '"') ++q; if (q < e) ++q; }
+            else while (q < e && *q != ',' && *q != '>') ++q;
+            if (is_id && q > val) {
+              const std::string id(val, (size_t)(q - val));
+              if (std::find(v->chroms.begin(), v->chroms.end(), id) == v->chroms.end()) v->chroms.push_back(id);
+            }
+            if (q < e && (*q == ',' || *q == '>')) ++q;
+            if (q[-1] == '>') break;
+          }
+        } else if (e - p > 6 && memcmp(p, "#CHROM", 6) == 0) {
           split(p, e, '\t', &cols);
           if (cols.size() < 10) return fail(lineno, "no sample columns");
           for (size_t i = 9; i < cols.size(); ++i) v->samples.emplace_back(cols[i].p, cols[i].n);
@@ -254,7 +273,7 @@ int dmx_vcf_read(const char* path, int32_t field, dmx_vcf** out) {
   size_t ncpu = std::thread::hardware_concurrency();
   if (sched_getaffinity(0, sizeof(cpus), &cpus) == 0) ncpu = (size_t)CPU_COUNT(&cpus);
   size_t nth = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(ncpu, 16), lines.size() / 256 + 1));
-  if (const char* env = getenv("DMX_VCF_THREADS")) nth = std::max<size_t>(1, std::min<size_t>((size_t)atoi(env), 256));
+  if (const char* env = getenv("DMX_VCF_THREADS")) nth = (size_t)std::max(1, std::min(atoi(env), 256));
   std::vector<Part> parts(nth);
   std::vector<std::thread> th;
   for (size_t t = 0; t < nth; ++t) {

@@ -261,7 +261,8 @@ const char* dmx_vcf_last_error(void);
  * the VCF's chromosome names. */
 typedef struct {
   const char* tag_group;       /* --tag-group, "CB" (:12); "" = one group "." (:241-243)             */
-  const char* tag_umi;         /* --tag-UMI, "UB" (:13); "" (random UMIs, :276) is refused            */
+  const char* tag_umi;         /* --tag-UMI, "UB" (:13); "": "." + hex(rand()) per read like :274-276 (the reference
+                                  never seeds rand(): glibc's default sequence, reproduced from a private state) */
   int32_t min_mq;              /* --min-MQ 20 (:19)                                                   */
   uint32_t exclude_flag;       /* --excl-flag 0x0f04 (:18)                                            */
   int32_t min_bq, cap_bq, min_td;   /* --min-BQ 13, --cap-BQ 40, --min-TD 0 (:14-16)                 */

@@ -45,8 +45,35 @@ def write_bam(path, refs, reads, member=4000):
         f.write(gzip.compress(b""))     # BGZF end-of-file marker: an empty member
 
 
+class GlibcRand:
+    """glibc's rand() / random() of a process that never calls srand(): the TYPE_3 additive feedback generator
+    (r[i] = r[i-3] + r[i-31], 310 values discarded) seeded with 1 -- what the reference's `rand()` at
+    cmd_cram_demuxlet.cpp:276 returns"""
+
+    def __init__(self, seed=1):
+        r = [0] * 34
+        r[0] = seed
+        for i in range(1, 31):
+            r[i] = (16807 * r[i - 1]) % 2147483647
+        for i in range(31, 34):
+            r[i] = r[i - 31]
+        self.r = r
+        for _ in range(310):
+            self._step()
+
+    def _step(self):
+        v = (self.r[-31] + self.r[-3]) & 0xffffffff
+        self.r.append(v)
+        self.r.pop(0)
+        return v
+
+    def __call__(self):
+        return self._step() >> 1
+
+
 def sweep(refs, reads, chroms, snp_rid, snp_pos, snp_ref, snp_alt, groups=None, tag_group="CB", tag_umi="UB", min_mq=20,
           exclude_flag=0x0f04, min_bq=13, cap_bq=40, min_td=0):
+    rnd = GlibcRand()
     name2rid = {c: i for i, c in enumerate(chroms)}
     tid2rid = [name2rid.get(n, -1) for n, _ in refs]
     bc, totl = {}, []
@@ -73,7 +100,7 @@ def sweep(refs, reads, chroms, snp_rid, snp_pos, snp_ref, snp_alt, groups=None, 
             bc[sb] = len(bc)
             totl.append(0)
         ib = bc[sb]
-        umi = tags.get(tag_umi, ".")
+        umi = (".%x" % rnd()) if tag_umi == "" else tags.get(tag_umi, ".")     # :274-276
         totl[ib] += 1
         for i in range(len(snp_pos)):
             if snp_rid[i] != rid or not (r["pos"] <= snp_pos[i] < endpos):

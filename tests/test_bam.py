@@ -32,7 +32,8 @@ def same(a, b):
 
 
 @pytest.mark.parametrize("seed,opts", [(1, {}), (2, {"min_bq": 0, "cap_bq": 30, "min_td": 5}),
-                                       (3, {"min_mq": 0, "exclude_flag": 0x4}), (4, {"tag_group": "", "tag_umi": "RG"})])
+                                       (3, {"min_mq": 0, "exclude_flag": 0x4}), (4, {"tag_group": "", "tag_umi": "RG"}),
+                                       (5, {"tag_umi": ""})])
 def test_sweep_matches_restatement(seed, opts, tmp_path):
     rng = np.random.default_rng(seed)
     chroms, rid, pos, ref, alt = make_snps(rng)
@@ -83,8 +84,6 @@ def test_sweep_errors(tmp_path):
         api.sweep_bam(path, chroms, rid[::-1].copy(), pos, ref, alt)
     with pytest.raises(api.DmxError, match="orderings"):
         api.sweep_bam(path, chroms[::-1], rid, pos, ref, alt)
-    with pytest.raises(api.DmxError, match="tag-UMI"):
-        api.sweep_bam(path, chroms, rid, pos, ref, alt, tag_umi="")
     assert api.sweep_bam(path, chroms, rid, pos, ref, alt)["barcodes"] == []
 
 
@@ -95,9 +94,12 @@ def make_case(tmp_path, seed, field, nreads=6000, nv=5):
     recs = vcfio.random_records(rng, 500, nv, field)
     recs = [(("chr1" if i < 250 else "chr2"), 200 + 37 * (i % 250), r[2], r[3], r[4], r[5]) for i, r in enumerate(recs)]
     vcf = str(tmp_path / "a.vcf.gz")
-    vcfio.write_vcf(vcf, samples, recs, bgzip_like=True)
+    # chrM is declared in the VCF header but carries no record: its reads still count for RD.TOTL (the reference maps
+    # read chromosomes through the header dictionary, cmd_cram_demuxlet.cpp:197-199, :295); chrUn is not declared at all
+    vcfio.write_vcf(vcf, samples, recs, bgzip_like=True, contigs=["chrM", "chr1", "chr2"])
     v = vcfio.parse_vcf(vcf, field)
-    by_tid = {1: v["pos"][v["rid"] == 0], 2: v["pos"][v["rid"] == 1]}
+    assert v["chroms"] == ["chrM", "chr1", "chr2"]
+    by_tid = {1: v["pos"][v["rid"] == 1], 2: v["pos"][v["rid"] == 2]}
     reads, barcodes = bamio.random_reads(rng, REFS, by_tid, nreads, ncells=20)
     bam = str(tmp_path / "a.bam")
     bamio.write_bam(bam, REFS, reads)
@@ -133,6 +135,10 @@ def test_cli_sam_vcf_end_to_end(field, seed, tmp_path):
     for ext in ("single", "sing2"):
         diff_tsv(tmp_path / ("orc." + ext), tmp_path / ("cli." + ext), ROW_EXACT)
     assert len(open(tmp_path / "cli.best").read().splitlines()) > 10
+    # reads on the declared, record-free contig are in RD.TOTL; without the ##contig dictionary they would be dropped
+    no_m = bamio.sweep(REFS, reads, ["chr1", "chr2"], v["rid"][keep] - 1, v["pos"][keep], v["ref"][keep], v["alt"][keep],
+                       groups=groups)
+    assert s["counts"]["off_vcf"] < no_m["counts"]["off_vcf"] and int(np.sum(s["totl"])) > int(np.sum(no_m["totl"]))
 
 
 def _reference_lookups(tmp_path):
@@ -191,3 +197,14 @@ def test_sweep_lookup_against_reference_function(tmp_path):
             want.append((ic, q, 0 if base == "A" else (1 if base == "C" else 2), min(qual - 33, 40)))
     have = list(zip(got["cell"].tolist(), got["snp"].tolist(), got["allele"].tolist(), got["bq"].tolist()))
     assert have == want and len(want) > 3000
+
+
+def test_random_umis_are_glibc_rand():
+    """--tag-UMI "": the reference appends hex(rand()) to "." per read and never seeds rand() (cmd_cram_demuxlet.cpp:276):
+    the python restatement of glibc's generator gives the numbers the C library gives after srand(1)"""
+    import ctypes
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(1)
+    want = [libc.rand() for _ in range(2000)]
+    rnd = bamio.GlibcRand()
+    assert [rnd() for _ in range(2000)] == want and want[0] == 1804289383

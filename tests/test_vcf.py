@@ -155,3 +155,65 @@ def test_cli_vcf_sample_subset(tmp_path):
     assert ra.returncode == 0 and rb.returncode == 0, ra.stderr + rb.stderr
     for ext in ("best", "single", "sing2"):
         assert filecmp.cmp(str(tmp_path / ("a." + ext)), str(tmp_path / ("b." + ext)), shallow=False), ext
+
+
+def test_contig_dictionary_defines_the_chromosome_ids(tmp_path):
+    """##contig lines come first (header order), then chromosomes in order of first appearance in ANY record, also a
+    skipped multi-allelic one (htslib's dictionary; the BAM sweep maps read chromosomes through it,
+    cmd_cram_demuxlet.cpp:197-199)"""
+    rng = np.random.default_rng(3)
+    samples = ["a", "b", "c"]
+    recs = vcfio.random_records(rng, 60, 3, "GT")                      # chr1..chr3
+    recs.insert(0, ("chrZ", 5, "A", "T,G", ["GT"], [{"GT": "0/1"}] * 3))   # skipped record on an undeclared chromosome
+    path = str(tmp_path / "c.vcf")
+    vcfio.write_vcf(path, samples, recs, contigs=["chrM", "chr2", "chr1", "chrEmpty"])
+    got, want = api.read_vcf(path, "GT"), vcfio.parse_vcf(path, "GT")
+    same(got, want, "GT")
+    assert got["chroms"] == ["chrM", "chr2", "chr1", "chrEmpty", "chrZ", "chr3"]
+    assert got["n_skipped"] >= 1 and set(np.unique(got["rid"])) == {1, 2, 5}
+
+
+def test_tutorial_vcf_pin():
+    """the one VCF the reference holds (tutorial/jurkat_293T_exons_only.vcf.gz: 54 424 records x 2 samples, plain gzip,
+    chromosome order 1, 10, 11, ...): dmx_vcf_read against an independent python parse, live where /root/reference
+    exists, and against the summary committed by tests/golden/make_tutorial_golden.py"""
+    import hashlib
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    gold = json.load(open(os.path.join(here, "golden", "tutorial_vcf.json")))
+    assert gold["n_records"] == 54424 and gold["n_skipped"] == 308 and gold["n_biallelic"] == 54116
+    assert gold["samples"] == ["jurkat", "293T_RTG"] and gold["record_chroms"][:3] == ["1", "10", "11"]
+    src = gold["source"]
+    if not os.path.exists(src):
+        pytest.skip("the tutorial VCF lives in /root/reference (build container only)")
+    got = api.read_vcf(src, "GT")
+
+    def digest(a):
+        return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+    assert got["samples"] == gold["samples"] and got["chroms"] == gold["chroms"]
+    assert got["n_skipped"] == gold["n_skipped"] and len(got["pos"]) == gold["n_biallelic"]
+    assert digest(got["rid"]) == gold["sha_rid"] and digest(got["pos"]) == gold["sha_pos"]
+    assert digest(got["gt"]) == gold["sha_gt"]
+    assert hashlib.sha256(got["ref"].tobytes()).hexdigest()[:16] == gold["sha_ref"]
+    assert hashlib.sha256(got["alt"].tobytes()).hexdigest()[:16] == gold["sha_alt"]
+    # and live against the independent parse itself
+    from tests.golden.make_tutorial_golden import independent_parse
+    ind = independent_parse(src)
+    assert np.array_equal(ind["gt"], got["gt"]) and np.array_equal(ind["pos"], got["pos"]) and np.array_equal(ind["rid"], got["rid"])
+    npz = np.load(os.path.join(here, "golden", "tutorial_gt.npz"))
+    assert np.array_equal(npz["gt"], got["gt"])
+
+
+@pytest.mark.gpu
+def test_tutorial_gt_chain_on_gpu():
+    """the tutorial VCF's genotype calls (committed tests/golden/tutorial_gt.npz) through dmx_site_filter and the
+    --field GT matrix on the device, against the oracle (pinned on the reference's own passed_vfilter / parse_posteriors)"""
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    gt = np.load(os.path.join(here, "golden", "tutorial_gt.npz"))["gt"]
+    assert gt.shape == (54116, 2, 2)
+    keep = api.site_filter(gt)
+    assert np.array_equal(keep, po.site_filter(gt)) and 0 < keep.sum() < len(keep)
+    g = api.build_gp("GT", gt[keep], 0.01)
+    assert np.array_equal(g.view(np.uint32), po.build_gp("GT", gt[keep], 0.01).view(np.uint32))

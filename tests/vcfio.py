@@ -10,10 +10,13 @@ import numpy as np
 INT_MISSING = np.iinfo(np.int32).min
 
 
-def write_vcf(path, samples, records, bgzip_like=False):
-    """records: list of (chrom, pos1, ref, alt, fmt_keys, [per-sample dict key -> text])"""
-    lines = ["##fileformat=VCFv4.2", "##source=dmx-b200 tests",
-             "\t".join(["#CHROM", "POS", "ID", "REF", "ALT", "QUAL", "FILTER", "INFO", "FORMAT"] + list(samples))]
+def write_vcf(path, samples, records, bgzip_like=False, contigs=()):
+    """records: list of (chrom, pos1, ref, alt, fmt_keys, [per-sample dict key -> text]); contigs: ##contig header lines"""
+    lines = ["##fileformat=VCFv4.2", "##source=dmx-b200 tests"]
+    for i, c in enumerate(contigs):
+        lines.append(("##contig=<ID=%s,length=%d>" % (c, 1000000 + i)) if i % 2 == 0 else
+                     ('##contig=<length=%d,assembly="a,b",ID=%s>' % (1000000 + i, c)))
+    lines.append("\t".join(["#CHROM", "POS", "ID", "REF", "ALT", "QUAL", "FILTER", "INFO", "FORMAT"] + list(samples)))
     for chrom, pos1, ref, alt, keys, cols in records:
         lines.append("\t".join([chrom, str(pos1), ".", ref, alt, ".", "PASS", ".", ":".join(keys)] +
                                [":".join(c[k] for k in keys if k in c) for c in cols]))
@@ -44,14 +47,19 @@ def parse_vcf(path, field="GT"):
             if line.startswith("#"):
                 if line.startswith("#CHROM"):
                     samples = line.split("\t")[9:]
+                elif line.startswith("##contig=<"):      # the header's contig dictionary comes first, in header order
+                    import re
+                    m = re.search(r"[<,]ID=([^,>]+)", line)
+                    if m and m.group(1) not in chroms:
+                        chroms.append(m.group(1))
                 continue
             c = line.split("\t")
+            if c[0] not in chroms:                       # every record's chromosome, also of the skipped ones
+                chroms.append(c[0])
             if c[4] == "." or len(c[4].split(",")) != 1:
                 nskip += 1
                 continue
             keys = c[8].split(":")
-            if c[0] not in chroms:
-                chroms.append(c[0])
             rid.append(chroms.index(c[0]))
             pos.append(int(c[1]) - 1)
             ref.append(c[3][0].encode())
