@@ -25,7 +25,10 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
+#include <future>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -46,19 +49,152 @@ namespace {
 
 thread_local std::string g_bam_error;
 
-struct Gz {
-  gzFile f = nullptr;
-  ~Gz() { if (f) gzclose(f); }
+// Byte stream over a BAM file.  A BGZF file (gzip members of <= 64 KB with the 'BC' extra field that gives each
+// block's compressed size, SAM spec 4.1) is inflated block-parallel: the compressed file is indexed by walking the block
+// headers, batches of blocks are inflated on the host threads into one buffer at their prefix-sum offsets (one batch
+// ahead of the record walk), and the records are then read in file order -- htslib's bgzf_mt idea.  Any other gzip file
+// (or a plain one) goes through zlib's gzread.
+class ByteStream {
+ public:
+  ~ByteStream() {
+    if (next_.valid()) next_.wait();
+    if (gz_) gzclose(gz_);
+  }
+  bool open(const char* path) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return false;
+    uint8_t h[18];
+    const size_t got = fread(h, 1, 18, f);
+    const bool bgzf = got == 18 && h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && (h[3] & 4) && h[10] == 6 && h[11] == 0 &&
+                      h[12] == 'B' && h[13] == 'C' && h[14] == 2 && h[15] == 0;
+    if (!bgzf) {
+      fclose(f);
+      gz_ = gzopen(path, "rb");
+      if (gz_) gzbuffer(gz_, 1 << 20);
+      return gz_ != nullptr;
+    }
+    fseek(f, 0, SEEK_END);
+    const long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    comp_.resize((size_t)std::max(0L, sz));
+    const bool ok = fread(comp_.data(), 1, comp_.size(), f) == comp_.size();
+    fclose(f);
+    if (!ok) return false;
+    // index: every block starts with the 18-byte header checked above; BSIZE = total block size - 1
+    for (size_t off = 0; off + 28 <= comp_.size();) {
+      const uint8_t* b = comp_.data() + off;
+      if (!(b[0] == 0x1f && b[1] == 0x8b && b[12] == 'B' && b[13] == 'C')) { bad_ = true; break; }
+      const size_t bsize = (size_t)(b[16] | (b[17] << 8)) + 1;
+      if (bsize < 26 || off + bsize > comp_.size()) { bad_ = true; break; }
+      uint32_t isize;
+      memcpy(&isize, b + bsize - 4, 4);
+      blocks_.push_back(Blk{off, bsize, isize});
+      off += bsize;
+    }
+    nth_ = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (const char* env = getenv("DMX_BAM_THREADS")) nth_ = std::max(1, std::min(atoi(env), 256));
+    parallel_ = true;
+    schedule();
+    return true;
+  }
+  int threads() const { return parallel_ ? nth_ : 1; }
+  // n bytes or fail; read_some-style EOF probe through `at_eof`
   bool read(void* dst, size_t n) {
+    if (!parallel_) {
+      char* p = (char*)dst;
+      while (n) {
+        const int k = gzread(gz_, p, (unsigned)std::min<size_t>(n, 1u << 30));
+        if (k <= 0) return false;
+        p += k;
+        n -= (size_t)k;
+      }
+      return true;
+    }
     char* p = (char*)dst;
     while (n) {
-      const int k = gzread(f, p, (unsigned)std::min<size_t>(n, 1u << 30));
-      if (k <= 0) return false;
+      if (pos_ == cur_.size() && !advance()) return false;
+      const size_t k = std::min(n, cur_.size() - pos_);
+      memcpy(p, cur_.data() + pos_, k);
+      pos_ += k;
       p += k;
-      n -= (size_t)k;
+      n -= k;
     }
     return true;
   }
+  // 1: four bytes read, 0: clean end of file, -1: truncated
+  int read4(uint8_t* dst) {
+    if (!parallel_) {
+      const int k = gzread(gz_, dst, 4);
+      return k == 4 ? 1 : (k == 0 ? 0 : -1);
+    }
+    if (pos_ == cur_.size() && !advance()) return bad_ ? -1 : 0;
+    if (cur_.size() - pos_ >= 4) {
+      memcpy(dst, cur_.data() + pos_, 4);
+      pos_ += 4;
+      return 1;
+    }
+    return read(dst, 4) ? 1 : -1;
+  }
+
+ private:
+  struct Blk { size_t off, size; uint32_t isize; };
+  static constexpr size_t kBatch = 1024;    // blocks per batch (<= 64 MB of BAM)
+  bool inflate_batch(size_t b0, size_t b1, std::vector<uint8_t>* out) {
+    std::vector<size_t> at(b1 - b0 + 1, 0);
+    for (size_t i = b0; i < b1; ++i) at[i - b0 + 1] = at[i - b0] + blocks_[i].isize;
+    out->resize(at.back());
+    std::atomic<size_t> nextb{b0};
+    std::atomic<bool> ok{true};
+    auto work = [&]() {
+      z_stream zs;
+      for (;;) {
+        const size_t i = nextb.fetch_add(1);
+        if (i >= b1) break;
+        const Blk& bl = blocks_[i];
+        if (bl.isize == 0) continue;
+        memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, -15) != Z_OK) { ok = false; break; }
+        zs.next_in = comp_.data() + bl.off + 18;
+        zs.avail_in = (uInt)(bl.size - 26);
+        zs.next_out = out->data() + at[i - b0];
+        zs.avail_out = bl.isize;
+        const int rc = inflate(&zs, Z_FINISH);
+        inflateEnd(&zs);
+        uint32_t crc;
+        memcpy(&crc, comp_.data() + bl.off + bl.size - 8, 4);
+        if (rc != Z_STREAM_END || zs.avail_out != 0 ||
+            (uint32_t)crc32(crc32(0L, Z_NULL, 0), out->data() + at[i - b0], bl.isize) != crc)
+          ok = false;
+      }
+    };
+    const int nt = (int)std::min<size_t>((size_t)nth_, b1 - b0);
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work);
+    work();
+    for (auto& x : th) x.join();
+    return ok;
+  }
+  void schedule() {      // start inflating the next batch in the background
+    if (next_blk_ >= blocks_.size()) return;
+    const size_t b0 = next_blk_, b1 = std::min(blocks_.size(), b0 + kBatch);
+    next_blk_ = b1;
+    next_ = std::async(std::launch::async, [this, b0, b1]() { return inflate_batch(b0, b1, &ahead_); });
+  }
+  bool advance() {       // the batch that was inflated ahead becomes the current one
+    if (!next_.valid()) return false;
+    if (!next_.get()) { bad_ = true; return false; }
+    cur_.swap(ahead_);
+    pos_ = 0;
+    schedule();
+    return !cur_.empty() || advance();
+  }
+  gzFile gz_ = nullptr;
+  bool parallel_ = false, bad_ = false;
+  int nth_ = 1;
+  std::vector<uint8_t> comp_, cur_, ahead_;
+  std::vector<Blk> blocks_;
+  size_t next_blk_ = 0, pos_ = 0;
+  std::future<bool> next_;
 };
 
 int32_t rd_i32(const uint8_t* p) { int32_t v; memcpy(&v, p, 4); return v; }
@@ -132,13 +268,11 @@ int dmx_sweep_bam(const char* path, const dmx_sweep_opts* o, int32_t n_chrom, co
       g_bam_error = "SNPs are not sorted by chromosome and position";
       return DMX_E_INVALID;
     }
-  Gz gz;
-  gz.f = gzopen(path, "rb");
-  if (!gz.f) {
+  ByteStream gz;
+  if (!gz.open(path)) {
     g_bam_error = std::string("cannot open ") + path;
     return DMX_E_IO;
   }
-  gzbuffer(gz.f, 1 << 20);
   uint8_t hdr[12];
   if (!gz.read(hdr, 8) || memcmp(hdr, "BAM\1", 4) != 0) {
     g_bam_error = std::string(path) + " is not a BAM file";
@@ -182,9 +316,9 @@ int dmx_sweep_bam(const char* path, const dmx_sweep_opts* o, int32_t n_chrom, co
   static const char kBase[] = "=ACMGRSVTWYHKDBN";
   for (;;) {
     uint8_t bs[4];
-    const int k = gzread(gz.f, bs, 4);
+    const int k = gz.read4(bs);
     if (k == 0) break;                    // end of file
-    if (k != 4) { g_bam_error = "truncated BAM record"; delete sw; return DMX_E_INVALID; }
+    if (k != 1) { g_bam_error = "truncated BAM record"; delete sw; return DMX_E_INVALID; }
     const int32_t block = rd_i32(bs);
     if (block < 32) { g_bam_error = "corrupt BAM record"; delete sw; return DMX_E_INVALID; }
     buf.resize((size_t)block);

@@ -52,6 +52,28 @@ def test_sweep_matches_restatement(seed, opts, tmp_path):
              bamio.sweep(REFS, reads, chroms, rid, pos, ref, alt, groups=keep))
 
 
+@pytest.mark.parametrize("threads", ["1", "3", "16"])
+def test_bgzf_blocks_inflate_in_parallel(threads, tmp_path, monkeypatch):
+    """a real BGZF file (blocks with the BC size field) is inflated block-parallel, in batches, records walked in file
+    order: same tuples as the gzread path on the same records, for any thread count; a corrupt block is an error"""
+    monkeypatch.setenv("DMX_BAM_THREADS", threads)
+    rng = np.random.default_rng(8)
+    chroms, rid, pos, ref, alt = make_snps(rng)
+    by_tid = {1: pos[rid == 0], 2: pos[rid == 1]}
+    reads, _ = bamio.random_reads(rng, REFS, by_tid, 9000)
+    a, b = str(tmp_path / "plain.bam"), str(tmp_path / "bgzf.bam")
+    bamio.write_bam(a, REFS, reads)
+    bamio.write_bam(b, REFS, reads, member=700, bgzf=True)       # ~1500 blocks: more than one batch of 1024
+    want = bamio.sweep(REFS, reads, chroms, rid, pos, ref, alt)
+    same(api.sweep_bam(a, chroms, rid, pos, ref, alt), want)
+    same(api.sweep_bam(b, chroms, rid, pos, ref, alt), want)
+    raw = bytearray(open(b, "rb").read())
+    raw[len(raw) // 2] ^= 0x55
+    (tmp_path / "bad.bam").write_bytes(bytes(raw))
+    with pytest.raises(api.DmxError):
+        api.sweep_bam(str(tmp_path / "bad.bam"), chroms, rid, pos, ref, alt)
+
+
 def test_sweep_feeds_the_packer(tmp_path):
     """sweep tuples -> dmx_pack_reads == the python container restatement on the same tuples"""
     from demuxlet_b200.plp import build_from_reads
