@@ -175,6 +175,23 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
 #endif
   }
 }
+// DMX_PROF (experiment builds only, tools/build_variant.sh): cycles every warp role of the fp32 scan spends inside its
+// mbarrier waits, summed over warps and CTAs; launch_pair_scan prints and clears the table after every launch.
+// role 0 loader, 1 transform, 2 accumulator, 3 consumer; counter 0 = role total, 7 = warps, 1..6 = waits (see roles)
+#ifndef DMX_PROF
+#define DMX_PROF 0
+#endif
+#if DMX_PROF
+__device__ unsigned long long g_prof[4][8];
+#define PROF_DECL long long prof_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long prof_t0_ = clock64();
+#define PROF_WAIT(i, stmt) { const long long t0_ = clock64(); stmt; prof_[i] += clock64() - t0_; }
+#define PROF_END(role, lane) if ((lane) == 0) { prof_[0] = clock64() - prof_t0_; prof_[7] = 1; \
+    for (int i_ = 0; i_ < 8; ++i_) atomicAdd(&g_prof[role][i_], (unsigned long long)prof_[i_]); }
+#else
+#define PROF_DECL
+#define PROF_WAIT(i, stmt) { stmt; }
+#define PROF_END(role, lane)
+#endif
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -1037,6 +1054,7 @@ __device__ __forceinline__ void loader_role_f32(const ScanParams& p, const ScanM
   const uint32_t sraw = (uint32_t)p.f_sraw, rawslot = (uint32_t)p.f_rawslot, off_fh = (uint32_t)p.f_off_fh;
   uint32_t gbase = 0;   // stages of the tasks before this one
   TaskInfoF ti;
+  PROF_DECL
   for (int r = 0; next_task_f32(p, r, u, NS, &ti); ++r) {
     const TaskType tt = p.tt[ti.tti];
     const bool same = tt.flags & TF_TRI;
@@ -1067,7 +1085,7 @@ __device__ __forceinline__ void loader_role_f32(const ScanParams& p, const ScanM
       int s[NB];
 #pragma unroll
       for (int i = 0; i < NB; ++i) s[i] = __shfl_sync(0xffffffffu, snp_cur, i);
-      mbar_wait_relaxed(&pp.raw_empty[rslot], ph ^ 1u);
+      PROF_WAIT(1, mbar_wait_relaxed(&pp.raw_empty[rslot], ph ^ 1u));
       const uint32_t rs = raw0 + rslot * rawslot, bar = full0 + rslot * 8u;
       mbar_expect_tx_elect(bar, bytes);
       if (!nogp) {
@@ -1084,6 +1102,7 @@ __device__ __forceinline__ void loader_role_f32(const ScanParams& p, const ScanM
     }
     gbase += (uint32_t)ti.nst;
   }
+  PROF_END(0, lane)
 }
 
 // F_NTW = 4 transform warps take whole stages.  A lane serves one 4-sample block q = lane % 16 of each side for the
@@ -1372,6 +1391,7 @@ __device__ __forceinline__ void transform_role_f32(const ScanParams& p, const Pi
     if (lane == 0) g = atomicAdd(&ts->next_stage, 1u);
     return __shfl_sync(0xffffffffu, g, 0);
   };
+  PROF_DECL
   uint32_t git = grab();
   TaskInfoF ti;
   for (int r = 0; next_task_f32(p, r, u, NS, &ti); ++r) {
@@ -1382,7 +1402,7 @@ __device__ __forceinline__ void transform_role_f32(const ScanParams& p, const Pi
     const bool kq = same ? jq : (4 * q < tt.nk);
     // pairs with sample 0: on the k side of symmetric tasks, on the j side of the (rectangular) tasks of full planes
     const int row0 = (!(tt.flags & TF_ROW0) || (p.dbg & 16)) ? 0 : ((tt.flags & TF_SYM) ? 1 : (same ? 0 : 2));
-    for (; git < gbase + (uint32_t)ti.nst; git = grab()) {
+    for (; git < gbase + (uint32_t)ti.nst;) {
       const int it = (int)(git - gbase);
       const uint32_t rslot = git % sraw, pslot = git % F_S_PROC;
       const uint32_t rph = (git / sraw) & 1u, pph = (git / F_S_PROC) & 1u;
@@ -1393,18 +1413,18 @@ __device__ __forceinline__ void transform_role_f32(const ScanParams& p, const Pi
       Fac F;                                          // this stage's factors of the running products (4 entries each)
 #pragma unroll
       for (int i = 0; i < 4; ++i) F.PA[i] = F.PB[i] = F.P1[i] = F.P0[i] = F.PJ[i] = 1.0f;
-      mbar_wait(&pp.raw_full[rslot], rph);
-      mbar_wait(&pp.proc_empty[pslot], pph ^ 1u);
+      PROF_WAIT(1, mbar_wait(&pp.raw_full[rslot], rph));
+      PROF_WAIT(2, mbar_wait(&pp.proc_empty[pslot], pph ^ 1u));
       const unsigned char* rs = pp.raw_base + (size_t)rslot * rawslot;
       float* pf = reinterpret_cast<float*>(pp.proc_base + (size_t)pslot * F_PROC_SLOT);
       if (p.dbg & 2) {
       } else if (aff) {
-        transform_dispatch_f32<true>(same, extras_t, row0, rs, off_fh, pf, ebase, q, nvalid, jq, kq, F);
+        PROF_WAIT(5, transform_dispatch_f32<true>(same, extras_t, row0, rs, off_fh, pf, ebase, q, nvalid, jq, kq, F));
       } else {
-        transform_dispatch_f32<false>(same, extras_t, row0, rs, off_fh, pf, ebase, q, nvalid, jq, kq, F);
+        PROF_WAIT(6, transform_dispatch_f32<false>(same, extras_t, row0, rs, off_fh, pf, ebase, q, nvalid, jq, kq, F));
       }
       // the stage's factors go to the products ring (every factor is >= ~2^-20, four of them cannot underflow)
-      mbar_wait(&prod_empty[pslot], pph ^ 1u);
+      PROF_WAIT(3, mbar_wait(&prod_empty[pslot], pph ^ 1u));
       {
         float4* dst = reinterpret_cast<float4*>(&ts->prod[pslot][ebase][0][4 * q]);
         dst[0 * (BLK / 4)] = make_float4(F.PA[0], F.PA[1], F.PA[2], F.PA[3]);
@@ -1419,9 +1439,11 @@ __device__ __forceinline__ void transform_role_f32(const ScanParams& p, const Pi
         mbar_arrive(&prod_full[pslot]);
         mbar_arrive(&pp.raw_empty[rslot]);
       }
+      PROF_WAIT(4, git = grab());
     }
     gbase += (uint32_t)ti.nst;
   }
+  PROF_END(1, lane)
 }
 
 // =============================== accumulator warp =================================================
@@ -1439,6 +1461,7 @@ __device__ __forceinline__ void accumulator_role_f32(const ScanParams& p, TScrat
   const double LN2 = 0.693147180559945309417232121458;
   uint32_t git = 0;
   TaskInfoF ti;
+  PROF_DECL
   for (int r = 0; next_task_f32(p, r, u, NS, &ti); ++r) {
     const TaskType tt = p.tt[ti.tti];
     const bool same = tt.flags & TF_TRI;
@@ -1451,7 +1474,7 @@ __device__ __forceinline__ void accumulator_role_f32(const ScanParams& p, TScrat
     for (int i = 0; i < 8; ++i) { acc[i] = accj[i] = 1.0f; ex[i] = exj[i] = 0; }
     for (int it = 0; it < ti.nst; ++it, ++git) {
       const uint32_t slot = git % F_S_PROC, ph = (git / F_S_PROC) & 1u;
-      mbar_wait(&prod_full[slot], ph);
+      PROF_WAIT(1, mbar_wait(&prod_full[slot], ph));
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const float4* src = reinterpret_cast<const float4*>(&ts->prod[slot][half][c][s0]);
@@ -1479,7 +1502,7 @@ __device__ __forceinline__ void accumulator_role_f32(const ScanParams& p, TScrat
     }
     // lb of this task -> shared memory (double buffered by task parity; the consumers release a buffer after reading)
     const int par = r & 1;
-    mbar_wait(&lb_empty[par], ((uint32_t)(r >> 1) & 1u) ^ 1u);
+    PROF_WAIT(2, mbar_wait(&lb_empty[par], ((uint32_t)(r >> 1) & 1u) ^ 1u));
     double v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = (double)ex[i] * LN2 + (double)logf(acc[i]);
@@ -1514,6 +1537,7 @@ __device__ __forceinline__ void accumulator_role_f32(const ScanParams& p, TScrat
       else (c == 0 ? p.singA : (c == 1 ? p.lb : p.p1))[(int64_t)ti.cell * p.nv + gs] = out;
     }
   }
+  PROF_END(2, lane)
 }
 
 // =============================== per-task reductions (:712-734, :799-814) ==========================
@@ -1964,6 +1988,7 @@ __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_f32_kernel(cons
     const int pos = rw * 4 + (lane >> 3);
     uint32_t git = 0;
     TaskInfoF ti;
+    PROF_DECL
     for (int r = 0; next_task_f32(p, r, u, NS, &ti); ++r) {
       const TaskType tt = p.tt[ti.tti];
       const bool tri = tt.flags & TF_TRI;
@@ -2003,7 +2028,7 @@ __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_f32_kernel(cons
         consumer_bar_sync<F_NCW * 32>(1);
         if (rw == 0 && lane == 0 && it > 0) mbar_arrive(&pp.proc_empty[(git - 1) % F_S_PROC]);
 #else
-        mbar_wait(&pp.proc_full[pslot], pph);
+        PROF_WAIT(1, mbar_wait(&pp.proc_full[pslot], pph));
 #endif
         const float* pf = reinterpret_cast<const float*>(pp.proc_base + (size_t)pslot * F_PROC_SLOT);
         if (!active || (p.dbg & 1)) {
@@ -2085,7 +2110,7 @@ __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_f32_kernel(cons
       exs += __shfl_xor_sync(0xffffffffu, exs, 1);
       // the sums s the transform divided out come back as lb[j] + lb[k] (from the accumulator warp)
       const int par = r & 1;
-      mbar_wait(&lb_full[par], (uint32_t)(r >> 1) & 1u);
+      PROF_WAIT(2, mbar_wait(&lb_full[par], (uint32_t)(r >> 1) & 1u));
       const double lbj = ts->lb[par][0][bj * 8 + el];
       double v[8];
       int vj[8], vk[8];
@@ -2102,8 +2127,9 @@ __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_f32_kernel(cons
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&lb_empty[par]);
-      task_epilogue<8, F_NCW, false>(p, ti, tt, scr, 0, rw, lane, v, vj, vk, vmask);
+      PROF_WAIT(3, (task_epilogue<8, F_NCW, false>(p, ti, tt, scr, 0, rw, lane, v, vj, vk, vmask)));
     }
+    PROF_END(3, lane)
   }
 }
 
@@ -2138,6 +2164,22 @@ int launch_pair_scan(const ScanParams& p, const ScanMaps& tm, bool fp32, void* s
     q.f_rawslot = p.has_rect ? F_RAW_SLOT_RECT : F_RAW_SLOT_TRI;
     q.f_off_fh = q.f_rawslot - F_REC_BYTES;
     pair_scan_f32_kernel<<<(unsigned)grid, F_LAUNCH_THREADS, smem, (cudaStream_t)stream>>>(q, tm);
+#if DMX_PROF
+    {
+      unsigned long long h[4][8];
+      cudaStreamSynchronize((cudaStream_t)stream);
+      cudaMemcpyFromSymbol(h, g_prof, sizeof(h));
+      static const char* role[4] = {"loader", "transform", "accumulator", "consumer"};
+      for (int r = 0; r < 4; ++r) {
+        const double w = h[r][7] ? (double)h[r][7] : 1.0;
+        fprintf(stderr, "prof %-11s warps %4llu  total %.0f kclk/warp  waits(kclk/warp):", role[r], h[r][7], h[r][0] / w / 1e3);
+        for (int i = 1; i < 7; ++i) fprintf(stderr, " %.0f", h[r][i] / w / 1e3);
+        fprintf(stderr, "\n");
+      }
+      memset(h, 0, sizeof(h));
+      cudaMemcpyToSymbol(g_prof, h, sizeof(h));
+    }
+#endif
   } else {
     int64_t grid = (p.ntasks + NSLOT - 1) / NSLOT;
     if (grid > g_num_sms) grid = g_num_sms;

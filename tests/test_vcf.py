@@ -213,7 +213,11 @@ def test_tutorial_gt_chain_on_gpu():
     here = os.path.dirname(os.path.abspath(__file__))
     gt = np.load(os.path.join(here, "golden", "tutorial_gt.npz"))["gt"]
     assert gt.shape == (54116, 2, 2)
+    # demuxlet's defaults (--min-mac 1 --min-callrate 0.5) and a setting that drops records of this two-sample file
+    for mac, cr in ((1, 0.5), (2, 1.0)):
+        assert np.array_equal(api.site_filter(gt, mac, cr), po.site_filter(gt, mac, cr))
+    strict = po.site_filter(gt, 2, 1.0)
+    assert 0 < strict.sum() < len(strict)
     keep = api.site_filter(gt)
-    assert np.array_equal(keep, po.site_filter(gt)) and 0 < keep.sum() < len(keep)
     g = api.build_gp("GT", gt[keep], 0.01)
     assert np.array_equal(g.view(np.uint32), po.build_gp("GT", gt[keep], 0.01).view(np.uint32))

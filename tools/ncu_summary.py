@@ -1,4 +1,6 @@
-"""summary of an `ncu --set full` report for profiles/: usage ncu_summary.py in.ncu-rep out.csv
+"""summary of an `ncu --set full` report for profiles/: usage ncu_summary.py in.ncu-rep out.csv [kernel workload traffic.json]
+with the last three arguments also writes the measured DRAM bytes of that launch as profiles/traffic_<kernel>_<workload>.json,
+the file bench.py reads for `roofline.traffic`
 (first kernel of the report; the metrics DESIGN.md quotes: time, DRAM bytes, occupancy, issue / pipe utilisation,
 shared-memory conflicts, stall reasons per issued instruction)"""
 import csv
@@ -25,3 +27,18 @@ with open(sys.argv[2], "w", newline="") as f:
     for h, u, v in sorted(zip(hdr, units, first)):
         if KEEP.match(h):
             w.writerow([h, u, v])
+if len(sys.argv) > 5:
+    import json
+    d = dict(zip(hdr, first))
+    u = dict(zip(hdr, units))
+
+    def nbytes(k):
+        v = float(d[k].replace(",", ""))
+        return v * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u[k]]
+    tot = nbytes("dram__bytes_read.sum") + nbytes("dram__bytes_write.sum")
+    json.dump({"kernel": sys.argv[3], "workload": sys.argv[4], "dram_bytes_per_launch": tot,
+               "dram_bytes_read": nbytes("dram__bytes_read.sum"), "dram_bytes_write": nbytes("dram__bytes_write.sum"),
+               "l2_hit_rate_pct": float(d.get("lts__t_sector_hit_rate.pct", "nan")),
+               "gpu_time_ns": d.get("gpu__time_duration.sum"),
+               "source": "ncu --set full --clock-control none, one launch of %s (%s) under bench.py; tools/run_profile.sh" %
+                         (sys.argv[3], sys.argv[1])}, open(sys.argv[5], "w"), indent=1)
