@@ -123,6 +123,9 @@ struct dmx_ctx {
   // device
   DevBuf<float> d_gp;              // uploaded [nsnps][nvp*3]
   DevBuf<float> d_gprow;           // [nsnps][8 + nvp*3]: gp0 | samples (gprow_kernel)
+  DevBuf<float> d_drow, d_srow;    // second-generation fp32 scan: dosage rows [2 nsnps][nvp + 8], row sums [nsnps][nvp + 8]
+  DevBuf<double> d_lm;             // [ncells][nA] sum of log M over the affine entries (cell_scalars_kernel)
+  int scan_gen = 2;                // fp32 scan generation (DMX_SCAN_GEN=1 selects pair_scan_f32_kernel)
   DevBuf<double> d_entq, d_row0, d_singA, d_lb, d_p1, d_p1_0, d_l00, d_sing, d_dense, d_dense2;
   DevBuf<double> d_terms;          // [E][RESC_FAST] log terms of the two-phase exact re-scorer
   DevBuf<double> d_ents;           // [E][2 + nd] per-entry factors of llk0s / llks00 (entq -> cell_scalars)
@@ -290,6 +293,13 @@ int encode_maps(dmx_ctx* c) {
   if (rc == DMX_OK)
     rc = encode_2d(&c->maps.qp, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, c->d_entq.p, (uint64_t)c->UQ, (uint64_t)c->E,
                    QPLANE, NB);
+  if (c->d_drow.p && c->d_srow.p) {
+    const uint64_t dp = (uint64_t)c->nvp + 8;
+    if (rc == DMX_OK) rc = encode_2d(&c->maps.dj, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c->d_drow.p, dp, 2 * (uint64_t)c->nsnps, BLK + 8, 1);
+    if (rc == DMX_OK) rc = encode_2d(&c->maps.dk, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c->d_drow.p, dp, 2 * (uint64_t)c->nsnps, BLK_RECT_K + 8, 1);
+    if (rc == DMX_OK) rc = encode_2d(&c->maps.sj, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c->d_srow.p, dp, (uint64_t)c->nsnps, BLK + 8, 1);
+    if (rc == DMX_OK) rc = encode_2d(&c->maps.sk, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c->d_srow.p, dp, (uint64_t)c->nsnps, BLK_RECT_K + 8, 1);
+  }
   return rc;
 }
 
@@ -446,6 +456,7 @@ void fill_scan_params(dmx_ctx* c, ScanParams* p) {
   p->cell_ptr = c->d_cell_ptr.p; p->cell_order = c->d_order.p; p->tt = c->d_tt.p; p->parts = c->d_parts.p;
   p->row0 = c->d_row0.p; p->singA = c->d_singA.p; p->lb = c->d_lb.p; p->p1 = c->d_p1.p;
   p->p1_0 = c->d_p1_0.p; p->l00 = c->d_l00.p; p->dense = nullptr;
+  p->lm = c->d_lm.p;
 }
 
 // candidate list of a cell -> ordered hypotheses in (j,k,n) lexicographic order
@@ -536,7 +547,7 @@ int dense_scan(dmx_ctx* c, const std::vector<int32_t>& cells, double* host_out, 
     p.ntasks = (int64_t)n * p.T;
     // dense blocks always come from the fp64 scan: every hypothesis keeps its own exponent there, whereas the fp32
     // scan lets hypotheses that are hopeless against the best of their tile underflow
-    CU(launch_pair_scan(p, c->maps, false, c->stream));
+    CU(launch_pair_scan(p, c->maps, 0, c->stream));
     CU(launch_fill_sep_dense(p, (int64_t)n, c->stream));
     c->st.gpu_launches += 1 + (p.sep0 ? 1 : 0);
     CU(cudaEventRecord(ev_scan[s], c->stream));
@@ -873,6 +884,7 @@ void dmx_destroy(dmx_ctx* c) {
   c->d_perm.release(); c->d_snp_perm.release(); c->d_cell_na.release();
   c->d_memo_q.release(); c->d_memo_fh.release(); c->d_memo_fp.release(); c->d_ecode.release();
   c->d_glist.release();
+  c->d_drow.release(); c->d_srow.release(); c->d_lm.release();
   c->d_gp.release(); c->d_gprow.release(); c->d_entq.release(); c->d_row0.release(); c->d_singA.release();
   c->d_lb.release(); c->d_p1.release(); c->d_p1_0.release(); c->d_l00.release(); c->d_sing.release();
   c->d_dense.release(); c->d_cell_ptr.release(); c->d_ent_ptr.release(); c->d_ent_snp.release();
@@ -1117,7 +1129,7 @@ int build_memo(dmx_ctx* c) {
   struct Rel { DevBuf<int64_t>* a; DevBuf<uint16_t>* b; DevBuf<int32_t>* s; DevBuf<double>* e;
                ~Rel() { a->release(); b->release(); s->release(); e->release(); } } rel{&d_ptr, &d_rd, &d_snp, &d_ents};
   CU(d_ptr.reserve(MEMO_ROWS + 1)); CU(d_rd.reserve(MEMO_ROWS)); CU(d_snp.reserve(MEMO_ROWS));
-  CU(d_ents.reserve((size_t)MEMO_ROWS * (2 + nd)));
+  CU(d_ents.reserve((size_t)MEMO_ROWS * (2 + 2 * nd)));
   CU(c->d_memo_q.reserve((size_t)MEMO_ROWS * c->UQ)); CU(c->d_memo_fh.reserve((size_t)MEMO_ROWS * FHEAD));
   CU(c->d_memo_fp.reserve((size_t)std::max(nd, 1) * MEMO_ROWS * FPLANE));
   CU(cudaMemcpyAsync(d_ptr.p, ptr.data(), ptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
@@ -1183,7 +1195,7 @@ int enqueue_chunk(dmx_ctx* c, const Chunk& ck, const ScanParams& sp0, bool dev_r
     for (int n = 0; n < nA; ++n)
       if (c->dense_idx[n] >= 0) cs.plane_n[c->dense_idx[n]] = (int8_t)n;
     cs.ents = c->d_ents.p; cs.cell_ptr = c->d_cell_ptr.p; cs.cell_order = c->d_order.p + ck.o0;
-    cs.p1_0 = c->d_p1_0.p; cs.l00 = c->d_l00.p;
+    cs.p1_0 = c->d_p1_0.p; cs.l00 = c->d_l00.p; cs.lm = c->scan_gen == 2 ? c->d_lm.p : nullptr;
     CU(launch_cell_scalars(cs, nact, c->stream));
     c->st.gpu_launches += 1;
   }
@@ -1192,7 +1204,7 @@ int enqueue_chunk(dmx_ctx* c, const Chunk& ck, const ScanParams& sp0, bool dev_r
   sp.cell_order = c->d_order.p + ck.o0;
   sp.parts = c->d_parts.p + ck.o0 * T;
   sp.ntasks = nact * T;
-  CU(launch_pair_scan(sp, c->maps, fp32, c->stream));
+  CU(launch_pair_scan(sp, c->maps, fp32 ? c->scan_gen : 0, c->stream));
   CU(cudaEventRecord(ev[2], c->stream));
   MergeParams mp;
   memset(&mp, 0, sizeof(mp));
@@ -1273,7 +1285,7 @@ int run_path(dmx_ctx* c, bool pipelined) {
     RC(reserve_inputs(c));
   }
   CU(c->d_entq.reserve((size_t)c->E * c->UQ + (size_t)NB * c->UQ + 2));   // slack: a stage always reads NB records
-  CU(c->d_ents.reserve((size_t)c->E * (2 + nd) + 2));
+  CU(c->d_ents.reserve((size_t)c->E * (2 + 2 * nd) + 2));
   if (fp32) {
     CU(c->d_entf_head.reserve((size_t)(c->E + NB) * FHEAD));
     CU(c->d_entf_plane.reserve((size_t)pstride * std::max(nd, 1)));
@@ -1284,6 +1296,15 @@ int run_path(dmx_ctx* c, bool pipelined) {
   CU(c->d_row0.reserve((size_t)nc * nA * nv + 1)); CU(c->d_singA.reserve((size_t)nc * nv + 1));
   CU(c->d_lb.reserve((size_t)nc * nv + 1)); CU(c->d_p1.reserve((size_t)nc * nv + 1));
   CU(c->d_p1_0.reserve(nc + 1)); CU(c->d_l00.reserve((size_t)nc * nA + 1));
+  {
+    const char* g = getenv("DMX_SCAN_GEN");
+    c->scan_gen = (g && atoi(g) == 1) ? 1 : 2;
+  }
+  if (fp32 && c->scan_gen == 2) {
+    CU(c->d_lm.reserve((size_t)nc * nA + 1));
+    CU(c->d_drow.reserve((size_t)2 * c->nsnps * (c->nvp + 8) + 256));
+    CU(c->d_srow.reserve((size_t)c->nsnps * (c->nvp + 8) + 256));
+  }
   CU(c->d_sing.reserve((size_t)nc * nv + 1)); CU(c->d_out.reserve(nc + 1));
   CU(c->r_out.reserve(nc + 1)); CU(c->r_sing.reserve((size_t)nc * nv + 1));
   CU(c->r_row0.reserve((size_t)nc * nA * nv + 1)); CU(c->r_l00.reserve((size_t)nc * nA + 1));
@@ -1329,6 +1350,11 @@ int run_path(dmx_ctx* c, bool pipelined) {
   if (pipelined) CU(cudaStreamWaitEvent(c->stream, ev_up[1], 0));
   CU(launch_gprow(c->d_gp.p, c->d_gprow.p, c->nsnps, nv, c->nvp, c->stream));
   if (c->nsnps) c->st.gpu_launches += 1;
+  if (fp32 && c->scan_gen == 2 && c->nsnps) {
+    CU(launch_dtab(c->d_gprow.p, c->d_drow.p, c->d_srow.p, c->nsnps, c->nvp, c->stream));
+    c->st.gpu_launches += 1;
+    CU(cudaMemsetAsync(c->d_lm.p, 0, (size_t)nc * nA * sizeof(double), c->stream));
+  }
   c->entq_full = !fp32;
   if (fp32 && !c->memo_ready && c->nsnps > 0 && c->E > 0) RC(build_memo(c));
   ScanParams sp;

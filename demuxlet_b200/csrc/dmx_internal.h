@@ -127,7 +127,10 @@ struct ScanParams {
   int64_t entf_pstride;        // floats between consecutive planes
   int32_t has_rect;            // the task list has rectangular tasks (k-side rows needed)
   int32_t f_sraw, f_rawslot, f_off_fh;   // fp32 scan raw ring geometry (filled in by launch_pair_scan)
-  const int32_t* snp_perm;     // [E] SNP id of the entry at each position of the class-sorted fp32 tables
+  const int32_t* snp_perm;     // [E] row index of the entry at each position of the class-sorted fp32 tables: SNP id
+                               // of a general entry, SNP * 2 + (alt read) of an affine entry (row of the dosage table)
+  const double* lm;            // [ncells][nA] sum over the cell's affine entries of log M (scale of the affine form)
+  int32_t v_nslot, v_slot;     // second-generation fp32 scan: ring slots and bytes per slot (launch_pair_scan)
   const int32_t* cell_na;      // [ncells] affine entries of the cell (they come first in the fp32 tables)
   const int64_t* cell_ptr;     // [ncells+1]
   const int32_t* cell_order;   // [nactive] cell ids, scheduled order
@@ -150,6 +153,9 @@ struct ScanMaps {
   CUtensorMap q;     // float64 [E][UQ], box {16, NB}: whole records (single dense plane)
   CUtensorMap qh;    // float64 [E][UQ], box {QHEAD, NB}:  record heads of NB consecutive entries
   CUtensorMap qp;    // float64 [E][UQ], box {QPLANE, NB}: one plane of NB consecutive entries
+  // second-generation fp32 scan (dmx_scan2.cuh): dosage rows [2 nsnps][nvp + 8] and row sums [nsnps][nvp + 8]
+  // (dtab_kernel; sample j at column 4 + j), gather4 boxes of {72, 1} (64 samples) and {40, 1} (32 samples, k side)
+  CUtensorMap dj, dk, sj, sk;
 };
 
 // exact re-scoring requests of one cell (built by merge_kernel, filled by rescore_kernel)
@@ -220,8 +226,9 @@ struct EntqParams {
   const float* memo_fp;        // [nd][MEMO_ROWS][FPLANE]
   const int32_t* glist;        // [E] entry at each class-sorted position, sign bit set for a general entry
                                // (classify_kernel): the general kernels then run by position; null: all entries
-  double* ents;                // [E][2 + nd]: the entry's factors of llk0s (:459), llks00 of a separable plane 0, and
-                               // llks00[n] of every dense plane (:700-709); summed per cell by cell_scalars_kernel
+  double* ents;                // [E][2 + 2 nd]: the entry's factors of llk0s (:459), llks00 of a separable plane 0,
+                               // llks00[n] of every dense plane (:700-709), and the scale M of its affine form per
+                               // dense plane (1 for a general entry); their logs are summed per cell by cell_scalars_kernel
   double pu[MAX_U];            // distinct p values (cmd_cram_demuxlet.cpp:613)
   uint8_t oslot_ptr[MAX_U + 1];   // CSR: record slots fed by distinct value u
   uint8_t oslot[QHEAD + QPLANE * DMX_MAX_ALPHA];
@@ -231,7 +238,8 @@ struct EntqParams {
 struct CellScalarParams {
   int32_t nd, nA, sep0, want_single;
   int8_t plane_n[DMX_MAX_ALPHA];   // alpha index of dense plane d
-  const double* ents;              // [E][2 + nd]
+  const double* ents;              // [E][2 + 2 nd]
+  double* lm;                      // [ncells][nA] sum of log M over the affine entries, per dense plane
   const int64_t* cell_ptr;
   const int32_t* cell_order;
   double* p1_0;                    // [ncells]
@@ -258,13 +266,16 @@ int launch_field(const FieldParams& p, int sm_count, void* stream);
 
 // host-callable launchers (dmx_kernels.cu); all return a cudaError_t as int
 int launch_gprow(const float* gp_flat, float* gp_rows, int64_t nsnps, int nv, int nvp, void* stream);
+// dosage / row-sum tables of the second-generation fp32 scan from the GP rows: drow [2 nsnps][nvp + 8], srow [nsnps][nvp + 8]
+int launch_dtab(const float* gp_rows, float* drow, float* srow, int64_t nsnps, int nvp, void* stream);
 int launch_entq(const EntqParams& p, void* stream);
 // entry classes of cells [c0, c1): perm[e] = position of entry e inside its cell's block with the affine entries
 // (<= 1 informative read) first, both classes in entry order; cell_na[cell] = number of affine entries
 int launch_classify(const int64_t* cell_ptr, const int64_t* ent_ptr, const uint16_t* reads, int64_t c0, int64_t c1,
                     int32_t* perm, int32_t* cell_na, int32_t* glist, void* stream);
 int launch_entq_aff(const EntqParams& p, void* stream);
-int launch_pair_scan(const ScanParams& p, const ScanMaps& tm, bool fp32, void* stream);
+int launch_pair_scan(const ScanParams& p, const ScanMaps& tm, int fp32, void* stream);   // fp32: 0 fp64 scan, 1 first-,
+                                                                                           // 2 second-generation fp32 scan
 int launch_cell_scalars(const CellScalarParams& p, int64_t nactive, void* stream);
 int launch_merge(const MergeParams& p, int64_t nactive, void* stream);
 int launch_fill_sep_dense(const ScanParams& p, int64_t nactive, void* stream);
@@ -273,6 +284,6 @@ int set_err_table(const double* err256, const double* err3_256);
 int set_log_table(const double* tab274);          // glibc __log_data: ln2hi, ln2lo, A[5], B[11], tab[128][2]
 int launch_logtest(const double* x, double* y, int64_t n, void* stream);
 int pair_scan_init();          // func attributes (max dynamic smem)
-size_t pair_scan_smem_bytes(const ScanParams& p, bool fp32);
+size_t pair_scan_smem_bytes(const ScanParams& p, int fp32);
 
 }  // namespace dmx

@@ -23,6 +23,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <math.h>
+#include <type_traits>
 
 #include "dmx_internal.h"
 
@@ -291,6 +292,41 @@ int launch_gprow(const float* gp_flat, float* gp_rows, int64_t nsnps, int nv, in
   return (int)cudaGetLastError();
 }
 
+// dtab: the tables the second-generation fp32 scan gathers for affine entries (dmx_scan2.cuh), from the GP rows:
+//   drow[2 snp + a][4 + j]  expected dosage of allele a under sample j's genotype vector normalised to sum 1
+//                           (a = 0: 2 g0 + g1, a = 1: g1 + 2 g2, over s = (g0 + g1) + g2)
+//   srow[snp][4 + j]        s (its logs come back as the lb term of the scan's epilogue)
+// Rows are nvp + 8 floats: four floats of padding on either side of the samples, so that a gather4 box may start four
+// floats to the left of the block it fetches.  Padding samples (all-zero GP) get D = 0, s = 0.
+__global__ void __launch_bounds__(256) dtab_kernel(const float* __restrict__ rows, float* __restrict__ drow,
+                                                   float* __restrict__ srow, int64_t nsnps, int nvp) {
+  const int pitch = nvp + 8;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nsnps * pitch) return;
+  const int64_t snp = i / pitch;
+  const int c = (int)(i - snp * pitch), j = c - 4;
+  float d0 = 0.f, d1 = 0.f, s = 0.f;
+  if (j >= 0 && j < nvp) {
+    const float* g = rows + snp * (int64_t)(nvp * 3 + 8) + 8 + 3 * j;
+    const float g0 = g[0], g1 = g[1], g2 = g[2];
+    s = (g0 + g1) + g2;
+    if (s > 0.f) {
+      d0 = __fdiv_rn(fmaf(2.0f, g0, g1), s);
+      d1 = __fdiv_rn(fmaf(2.0f, g2, g1), s);
+    }
+  }
+  drow[(2 * snp) * pitch + c] = d0;
+  drow[(2 * snp + 1) * pitch + c] = d1;
+  srow[i] = s;
+}
+
+int launch_dtab(const float* gp_rows, float* drow, float* srow, int64_t nsnps, int nvp, void* stream) {
+  if (nsnps == 0) return 0;
+  const int64_t n = nsnps * (nvp + 8);
+  dtab_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(gp_rows, drow, srow, nsnps, nvp);
+  return (int)cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------
 // entq: per-entry read likelihood on the distinct p values (:597-663) and pass-1 GLs (:424-452), in the
 // reference's arithmetic (separately rounded mul/add/div, per-read max normalisation).  Outputs per entry:
@@ -320,7 +356,7 @@ __device__ __forceinline__ void entq_emit(const EntqParams& p, int64_t e, double
   }
   out[6] = s0;
   out[7] = s1;
-  double* sc = p.ents + e * (2 + p.nd);
+  double* sc = p.ents + e * (2 + 2 * p.nd);
   sc[0] = s0;
   sc[1] = s1;
   // fp32 tables of the fp32 scan, class-sorted inside the cell (affine entries first)
@@ -328,7 +364,7 @@ __device__ __forceinline__ void entq_emit(const EntqParams& p, int64_t e, double
   const bool refread = al1 == 0;           // the informative read shows the reference allele: D = ref dosage
   const int64_t pos = p.perm ? e + (int64_t)__ldg(p.perm + e) : e;
   if (p.entf_head) {
-    if (p.snp_perm) p.snp_perm[pos] = __ldg(p.ent_snp + e);
+    if (p.snp_perm) p.snp_perm[pos] = affine ? 2 * __ldg(p.ent_snp + e) + (refread ? 0 : 1) : __ldg(p.ent_snp + e);
     float4* fh = reinterpret_cast<float4*>(p.entf_head + pos * FHEAD);
     if (affine) {
       // value at the dosage-0 corner and half the difference to the dosage-2 corner (>= 0 by construction)
@@ -352,6 +388,7 @@ __device__ __forceinline__ void entq_emit(const EntqParams& p, int64_t e, double
     const double s2 = fma(z2, t2, fma(z1, t1, z0 * t0));
     q[9] = s2;
     sc[2 + d] = s2;
+    sc[2 + p.nd + d] = 1.0;
     if (p.entf_plane) {
       float4* fp = reinterpret_cast<float4*>(p.entf_plane + d * p.entf_pstride + pos * FPLANE);
       if (affine) {
@@ -360,6 +397,12 @@ __device__ __forceinline__ void entq_emit(const EntqParams& p, int64_t e, double
         const double cl = 0.5 * (refread ? Q[2] - Q[8] : Q[6] - Q[0]);   // along l (j side)
         const double cm = 0.5 * (refread ? Q[6] - Q[8] : Q[2] - Q[0]);   // along m (k side)
         fp[0] = make_float4((float)(0.5 * q), (float)cl, (float)cm, 0.f);
+        // second-generation scan: Q' / M with M = the largest corner value of Q' (both genotypes with two copies of the
+        // read's allele, unless the base error is above 3/4 and a slope negative): alpha + bl * (dosage of l) +
+        // bm * (dosage of m) in (0, 1]
+        const double M = q + 2.0 * (fmax(cl, 0.0) + fmax(cm, 0.0));
+        fp[1] = make_float4((float)(q / M), (float)(cl / M), (float)(cm / M), 0.f);
+        if (affine) sc[2 + p.nd + d] = M;
       } else {
         fp[0] = make_float4((float)Q[0], (float)Q[1], (float)Q[2], (float)Q[3]);
         fp[1] = make_float4((float)Q[4], (float)Q[5], (float)Q[6], (float)Q[7]);
@@ -611,11 +654,12 @@ __global__ void __launch_bounds__(256) entq_aff_kernel(const __grid_constant__ E
     const double f0 = __ldg(mq + 3), f1 = __ldg(mq + 4), f2 = __ldg(mq + 5);
     s1 = fma(f2, z2, fma(f1, z1, f0 * z0)) * ((z0 + z1) + z2);
   }
-  double* sc = p.ents + e * (2 + p.nd);
+  double* sc = p.ents + e * (2 + 2 * p.nd);
   sc[0] = s0;
   sc[1] = s1;
   const int64_t pos = e + (int64_t)__ldg(p.perm + e);
-  p.snp_perm[pos] = snp;
+  const bool refread = nvr == 1 && (rd1 >> 8) == 0;
+  p.snp_perm[pos] = 2 * snp + (refread ? 0 : 1);          // row of the dosage table
   const float4* mh = reinterpret_cast<const float4*>(p.memo_fh + (int64_t)idx * FHEAD);
   float4* fh = reinterpret_cast<float4*>(p.entf_head + pos * FHEAD);
   fh[0] = __ldg(mh);
@@ -626,8 +670,16 @@ __global__ void __launch_bounds__(256) entq_aff_kernel(const __grid_constant__ E
     const double t1 = fma(__ldg(Q + 5), z2, fma(__ldg(Q + 4), z1, __ldg(Q + 3) * z0));
     const double t2 = fma(__ldg(Q + 8), z2, fma(__ldg(Q + 7), z1, __ldg(Q + 6) * z0));
     sc[2 + d] = fma(z2, t2, fma(z1, t1, z0 * t0));
-    *reinterpret_cast<float4*>(p.entf_plane + d * p.entf_pstride + pos * FPLANE) =
-        __ldg(reinterpret_cast<const float4*>(p.memo_fp + ((int64_t)d * MEMO_ROWS + idx) * FPLANE));
+    {   // the scale of the affine form, the same expression as entq_emit
+      const double q = refread ? __ldg(Q + 8) : __ldg(Q + 0);
+      const double cl = 0.5 * (refread ? __ldg(Q + 2) - __ldg(Q + 8) : __ldg(Q + 6) - __ldg(Q + 0));
+      const double cm = 0.5 * (refread ? __ldg(Q + 6) - __ldg(Q + 8) : __ldg(Q + 2) - __ldg(Q + 0));
+      sc[2 + p.nd + d] = q + 2.0 * (fmax(cl, 0.0) + fmax(cm, 0.0));
+    }
+    const float4* mp = reinterpret_cast<const float4*>(p.memo_fp + ((int64_t)d * MEMO_ROWS + idx) * FPLANE);
+    float4* fp = reinterpret_cast<float4*>(p.entf_plane + d * p.entf_pstride + pos * FPLANE);
+    fp[0] = __ldg(mp);
+    fp[1] = __ldg(mp + 1);
   }
 }
 
@@ -670,9 +722,9 @@ __global__ void __launch_bounds__(128) cell_scalars_kernel(const __grid_constant
   if (aidx >= nactive) return;
   const int cell = p.cell_order[aidx];
   const int64_t e0 = p.cell_ptr[cell], e1 = p.cell_ptr[cell + 1];
-  const int ns = 2 + p.nd;
+  const int ns = 2 + 2 * p.nd;
   for (int s = 0; s < ns; ++s) {
-    if ((s == 0 && !p.want_single) || (s == 1 && !p.sep0)) continue;
+    if ((s == 0 && !p.want_single) || (s == 1 && !p.sep0) || (s >= 2 + p.nd && !p.lm)) continue;
     double prod = 1.0;
     int es = 0, nfl = 0, cnt = 0;
     for (int64_t e = e0 + lane; e < e1; e += 32) {
@@ -685,7 +737,8 @@ __global__ void __launch_bounds__(128) cell_scalars_kernel(const __grid_constant
     if (lane == 0) {
       if (s == 0) p.p1_0[cell] = v;
       else if (s == 1) p.l00[(int64_t)cell * p.nA] = v;
-      else p.l00[(int64_t)cell * p.nA + p.plane_n[s - 2]] = v;
+      else if (s < 2 + p.nd) p.l00[(int64_t)cell * p.nA + p.plane_n[s - 2]] = v;
+      else p.lm[(int64_t)cell * p.nA + p.plane_n[s - 2 - p.nd]] = v;
     }
   }
 }
@@ -1080,7 +1133,7 @@ __device__ __forceinline__ void loader_role_f32(const ScanParams& p, const ScanM
       int nvalid;
       bool aff;
       stage_span(ti, it, &eb, &nvalid, &aff);
-      const int snp_cur = snp_nxt;
+      const int snp_cur = aff ? snp_nxt >> 1 : snp_nxt;   // affine entries carry the row of the dosage table
       if (it + F_NLOAD < ti.nst) snp_nxt = fetch(it + F_NLOAD);
       int s[NB];
 #pragma unroll
@@ -2133,7 +2186,10 @@ __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_f32_kernel(cons
   }
 }
 
-size_t pair_scan_smem_bytes(const ScanParams& /*p*/, bool fp32) {
+#include "dmx_scan2.cuh"
+
+size_t pair_scan_smem_bytes(const ScanParams& p, int fp32) {
+  if (fp32 == 2) return p.has_rect ? (size_t)V_SMEM_RECT : (size_t)V_SMEM_TRI;
   return fp32 ? (size_t)(F_SMEM_NOTS + F_TS_BYTES) : (size_t)NSLOT * SLOT_BYTES;
 }
 
@@ -2146,17 +2202,43 @@ int pair_scan_init() {
     e = cudaFuncSetAttribute(pair_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NSLOT * SLOT_BYTES);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(pair_scan_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_NOTS + F_TS_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(pair_scan_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             V_SMEM_TRI > V_SMEM_RECT ? V_SMEM_TRI : V_SMEM_RECT);
   return (int)e;
 }
 
-int launch_pair_scan(const ScanParams& p, const ScanMaps& tm, bool fp32, void* stream) {
+int launch_pair_scan(const ScanParams& p, const ScanMaps& tm, int fp32, void* stream) {
   if (p.ntasks == 0) return 0;
   if (g_num_sms == 0) {
     int rc = pair_scan_init();
     if (rc) return rc;
   }
   const size_t smem = pair_scan_smem_bytes(p, fp32);
-  if (fp32) {
+  if (fp32 == 2) {
+    int64_t grid = p.ntasks;
+    if (grid > g_num_sms) grid = g_num_sms;
+    ScanParams q = p;
+    q.v_nslot = p.has_rect ? V_NSLOT_RECT : V_NSLOT_TRI;
+    q.v_slot = p.has_rect ? V_SLOT_RECT : V_SLOT_TRI;
+    pair_scan_v2_kernel<<<(unsigned)grid, F_LAUNCH_THREADS, smem, (cudaStream_t)stream>>>(q, tm);
+#if DMX_PROF
+    {
+      unsigned long long h[4][8];
+      cudaStreamSynchronize((cudaStream_t)stream);
+      cudaMemcpyFromSymbol(h, g_prof, sizeof(h));
+      static const char* role[4] = {"loader", "singles", "-", "consumer"};
+      for (int r = 0; r < 4; ++r) {
+        const double w = h[r][7] ? (double)h[r][7] : 1.0;
+        fprintf(stderr, "prof2 %-9s warps %4llu  total %.0f kclk/warp  waits(kclk/warp):", role[r], h[r][7], h[r][0] / w / 1e3);
+        for (int i = 1; i < 7; ++i) fprintf(stderr, " %.0f", h[r][i] / w / 1e3);
+        fprintf(stderr, "\n");
+      }
+      memset(h, 0, sizeof(h));
+      cudaMemcpyToSymbol(g_prof, h, sizeof(h));
+    }
+#endif
+  } else if (fp32) {
     int64_t grid = p.ntasks;
     if (grid > g_num_sms) grid = g_num_sms;
     ScanParams q = p;

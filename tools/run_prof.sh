@@ -1,8 +1,9 @@
-# pair-scan profile: debug-switch timings, then one ncu --set full capture with source counters
+# wait-cycle profile of the fp32 scan roles (tools/build_variant.sh prof "-DDMX_PROF=1"): usage run_prof.sh TAG SCALE DBG...
 cd $GRAFT_REPO_ROOT
-T=${1:-prof}
+T=${1:-prof}; S=${2:-0.25}; shift; shift
 mkdir -p gpurun_out
-python tools/scan_probe.py 1.0 0 1 2 3 4 2>&1 | tail -8 | tee gpurun_out/${T}_probe.txt
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:pair_scan_f32 -s 3 -c 1 -o gpurun_out/${T}_pair_scan_f32 -f python tools/scan_probe.py 1.0 0 > gpurun_out/ncu_full.log 2>&1
-tail -2 gpurun_out/ncu_full.log
-ls -la gpurun_out/${T}_pair_scan_f32.ncu-rep
+for L in tools/libdmx_prof*.so; do
+echo "== $L" >> gpurun_out/${T}_prof.txt
+DMX_LIB=$PWD/$L python tools/scan_probe.py $S "$@" >> gpurun_out/${T}_prof.txt 2>&1
+done
+tail -120 gpurun_out/${T}_prof.txt

@@ -1,17 +1,9 @@
-# quick GPU check: parity tests (optionally a -k filter), then one short C3 bench line
+# quick GPU check of a kernel change: smoke, the parity tests, a timing probe (C3 at SCALE), the wait profile
 cd $GRAFT_REPO_ROOT
-T=${1:-quick}
-K=${2:-}
+T=${1:-q}; S=${2:-0.25}; TESTS=${3:-tests/test_gpu_parity.py tests/test_gpu_configs.py}
 mkdir -p gpurun_out
-if [ -n "$K" ]; then
-timeout 1500 python -m pytest tests -m gpu -x -q -k "$K" 2>&1 | tail -15
-else
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
-fi
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; tail -3 gpurun_out/${T}_bench.err
-python - <<PY
-import json
-d=json.load(open("gpurun_out/${T}_bench.json"))
-print("value %.0f e2e %.0f ms/step %.2f pair %.3f frac %.3f" % (d["value"], d["e2e"]["value"], d["ms_per_step"], d["roofline"]["kernel_ms"], d["roofline"]["frac"]))
-print(d["breakdown_ms"])
-PY
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2
+timeout 900 python -m pytest $TESTS -x -q 2>&1 | tail -15
+timeout 300 python tools/scan_probe.py $S 0 1 2>&1 | tail -2
+DMX_SCAN_GEN=1 timeout 300 python tools/scan_probe.py $S 0 2>&1 | tail -1
+if [ -f tools/libdmx_prof.so ]; then DMX_LIB=$PWD/tools/libdmx_prof.so timeout 300 python tools/scan_probe.py $S 0 2>&1 | tail -5; fi
