@@ -117,8 +117,10 @@ __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
 // (~600 cycles) at the price of two instructions.
 __device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity, const int32_t* probe, unsigned& sink) {
   while (!mbar_try_a(bar, parity)) {
-    unsigned v;
-    asm volatile("ld.global.cv.u32 %0, [%1];" : "=r"(v) : "l"(probe) : "memory");
+    unsigned v = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)   // three dependent round trips (the address of each load depends on the previous value)
+      asm volatile("ld.global.cv.u32 %0, [%1];" : "=r"(v) : "l"(probe + (v & 1u)) : "memory");
     sink += v;
   }
 }
