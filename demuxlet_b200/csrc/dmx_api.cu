@@ -146,6 +146,9 @@ struct dmx_ctx {
   DevBuf<CellOut> d_out;
   DevBuf<RescList> d_lists;
   PinBuf<RescList> r_lists;
+  DevBuf<dmx_best_rec> d_best;      // finalise_kernel: records of the cells it could decide ...
+  DevBuf<uint8_t> d_flag;           // ... and 1 for the cells left to the host finaliser
+  PinBuf<uint8_t> r_flag;
   bool gpu_exact = false;          // device log() verified bit-identical to the host libm
 
   // schedule
@@ -156,7 +159,7 @@ struct dmx_ctx {
   PinBuf<CellOut> r_out;
   PinBuf<double> r_sing, r_row0, r_l00, r_p1, r_p1_0, r_dense, r_dense2;
 
-  std::vector<dmx_best_rec> best;
+  PinBuf<dmx_best_rec> best;        // [ncells] the records (pinned: finalise_kernel's records are copied straight into it)
   dmx_stats st;
   ScanMaps maps;                    // TMA descriptors of d_gprow / d_entq (encode_maps)
 
@@ -668,12 +671,15 @@ int sharded_set_pileup(dmx_ctx* c, int64_t ncells, const int64_t* cell_ptr, cons
 int sharded_run(dmx_ctx* c, int mode) {
   if (!c->have_gp || !c->have_plp) return DMX_E_STATE;
   const double t0 = now_ms();
-  if (mode != 1) c->best.assign((size_t)c->ncells, dmx_best_rec());
+  if (mode != 1) {
+    CU(c->best.reserve((size_t)c->ncells + 1));
+    if (c->ncells) memset(c->best.p, 0, (size_t)c->ncells * sizeof(dmx_best_rec));
+  }
   RC(for_each_kid(c, [&](int k) {
     dmx_ctx* kid = c->kids[k];
     const int rc = mode == 0 ? dmx_run(kid) : (mode == 1 ? dmx_upload(kid) : dmx_compute(kid));
     if (rc != DMX_OK || mode == 1) return rc;
-    if (kid->ncells) memcpy(c->best.data() + c->kid_lo[k], kid->best.data(), kid->ncells * sizeof(dmx_best_rec));
+    if (kid->ncells) memcpy(c->best.p + c->kid_lo[k], kid->best.p, kid->ncells * sizeof(dmx_best_rec));
     return (int)DMX_OK;
   }));
   dmx_stats a;
@@ -890,6 +896,7 @@ void dmx_destroy(dmx_ctx* c) {
   c->d_dense.release(); c->d_cell_ptr.release(); c->d_ent_ptr.release(); c->d_ent_snp.release();
   c->d_order.release(); c->d_reads.release(); c->d_tt.release(); c->d_parts.release(); c->d_out.release();
   c->d_lists.release(); c->r_lists.release();
+  c->d_best.release(); c->d_flag.release(); c->best.release(); c->r_flag.release();
   c->o_gp.release(); c->o_cell_ptr.release(); c->o_ent_ptr.release(); c->o_ent_snp.release(); c->o_reads.release();
   c->r_out.release(); c->r_sing.release(); c->r_row0.release(); c->r_l00.release(); c->r_p1.release();
   c->r_p1_0.release(); c->r_dense.release(); c->r_dense2.release(); c->d_dense2.release();
@@ -1249,11 +1256,22 @@ int enqueue_chunk(dmx_ctx* c, const Chunk& ck, const ScanParams& sp0, bool dev_r
     rp.terms = c->d_terms.p;
     CU(launch_rescore(rp, nact, c->stream));
     if (nact) c->st.gpu_launches += 2 * (RMAX / RESC_FAST);
+    // the decision logic on the device; the cells it cannot decide (flag 1) go through the host finaliser below
+    FinaliseParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.nv = nv; fp.nA = nA; fp.eps_rel = sp.eps_rel; fp.eps_ent = sp.eps_ent; fp.w_single = (1. - c->cfg.doublet_prior) / nv;
+    for (int n2 = 0; n2 < nA; ++n2) fp.mode[n2] = c->pg.mode[n2];
+    fp.cell_ptr = c->d_cell_ptr.p; fp.cell_order = sp.cell_order; fp.sing = c->d_sing.p; fp.row0 = c->d_row0.p;
+    fp.l00 = c->d_l00.p; fp.out = c->d_out.p; fp.lists = c->d_lists.p; fp.best = c->d_best.p; fp.flag = c->d_flag.p;
+    CU(launch_finalise(fp, nact, c->stream));
+    if (nact) c->st.gpu_launches += 1;
   }
   CU(cudaEventRecord(ev[3], c->stream));
   if (n > 0 && dev_rescore) {
     CU(cudaStreamWaitEvent(c->stream3, ev[3], 0));
-    CU(cudaMemcpyAsync(c->r_lists.p + c0, c->d_lists.p + c0, n * sizeof(RescList), cudaMemcpyDeviceToHost, c->stream3));
+    CU(cudaMemcpyAsync(c->best.p + c0, c->d_best.p + c0, n * sizeof(dmx_best_rec), cudaMemcpyDeviceToHost, c->stream3));
+    CU(cudaMemcpyAsync(c->r_flag.p + c0, c->d_flag.p + c0, n * sizeof(uint8_t), cudaMemcpyDeviceToHost, c->stream3));
+    // (the re-score lists stay on the device: run_path fetches them for the cells the host finaliser takes)
   }
   return DMX_OK;
 }
@@ -1306,6 +1324,7 @@ int run_path(dmx_ctx* c, bool pipelined) {
     CU(c->d_srow.reserve((size_t)c->nsnps * (c->nvp + 8) + 256));
   }
   CU(c->d_sing.reserve((size_t)nc * nv + 1)); CU(c->d_out.reserve(nc + 1));
+  CU(c->best.reserve(nc + 1));
   CU(c->r_out.reserve(nc + 1)); CU(c->r_sing.reserve((size_t)nc * nv + 1));
   CU(c->r_row0.reserve((size_t)nc * nA * nv + 1)); CU(c->r_l00.reserve((size_t)nc * nA + 1));
   CU(c->r_p1.reserve((size_t)nc * nv + 1)); CU(c->r_p1_0.reserve(nc + 1));
@@ -1313,6 +1332,8 @@ int run_path(dmx_ctx* c, bool pipelined) {
     CU(c->d_lists.reserve(nc + 1));
     CU(c->r_lists.reserve(nc + 1));
     CU(c->d_terms.reserve((size_t)c->E * RESC_FAST + 1));
+    CU(c->d_best.reserve(nc + 1));
+    CU(c->d_flag.reserve(nc + 1)); CU(c->r_flag.reserve(nc + 1));
   }
   if ((int)c->cev.size() < 7 * K + 4) {
     const size_t old = c->cev.size();
@@ -1347,6 +1368,10 @@ int run_path(dmx_ctx* c, bool pipelined) {
   CU(cudaMemsetAsync(c->d_l00.p, 0, (size_t)nc * nA * sizeof(double), c->stream));
   CU(cudaMemsetAsync(c->d_row0.p, 0, (size_t)nc * nA * nv * sizeof(double), c->stream));
   CU(cudaMemsetAsync(c->d_out.p, 0, (size_t)nc * sizeof(CellOut), c->stream));
+  if (dev_rescore) {
+    CU(cudaMemsetAsync(c->d_flag.p, 1, (size_t)nc, c->stream));
+    CU(cudaMemsetAsync(c->d_best.p, 0, (size_t)nc * sizeof(dmx_best_rec), c->stream));
+  }
   if (pipelined) CU(cudaStreamWaitEvent(c->stream, ev_up[1], 0));
   CU(launch_gprow(c->d_gp.p, c->d_gprow.p, c->nsnps, nv, c->nvp, c->stream));
   if (c->nsnps) c->st.gpu_launches += 1;
@@ -1372,14 +1397,14 @@ int run_path(dmx_ctx* c, bool pipelined) {
   CU(cudaEventRecord(ev_last, c->stream));
 
   // ---- finalise, chunk by chunk as the records arrive ---------------------------------------------------------
-  c->best.assign(nc, dmx_best_rec());
+  if (!dev_rescore && nc) memset(c->best.p, 0, (size_t)nc * sizeof(dmx_best_rec));   // else every record comes from the device
   const HostView hv = host_view(c);
   const ExactScorer scorer(hv, c->err256);
   const int nth = host_threads(c);
   std::vector<std::vector<int32_t>> overflow(nth);
   std::vector<int64_t> resc(nth, 0), resc_gpu(nth, 0);
   auto do_cell = [&](int64_t cell, const std::vector<Hyp>& cands, int tid) {
-    dmx_best_rec* r = &c->best[cell];
+    dmx_best_rec* r = &c->best.p[cell];
     CellGpu g;
     g.co = &c->r_out.p[cell];
     g.sing = c->r_sing.p + (size_t)cell * nv;
@@ -1393,13 +1418,13 @@ int run_path(dmx_ctx* c, bool pipelined) {
     resc_gpu[tid] += from_gpu;
   };
   double fin_ms = 0.0;
+  const bool getenv_host_fin = getenv("DMX_HOST_DECIDE") != nullptr;   // debugging: every cell through the host logic
   for (int k = 0; k < K; ++k) {
     CU(cudaEventSynchronize(ev_done[k]));
     const double tf0 = now_ms();
     const int64_t c0 = chunks[k].c0, n = chunks[k].c1 - c0;
-    c->pool->run(n, nth, [&](int64_t i, int tid) {
-      const int64_t cell = c0 + i;
-      dmx_best_rec* r = &c->best[cell];
+    auto host_cell = [&](int64_t cell, int tid) {
+      dmx_best_rec* r = &c->best.p[cell];
       memset(r, 0, sizeof(*r));
       r->status = c->status[cell];
       r->n_snp = (int32_t)(c->h_cell_ptr[cell + 1] - c->h_cell_ptr[cell]);
@@ -1410,13 +1435,40 @@ int run_path(dmx_ctx* c, bool pipelined) {
       cands.clear();
       expand_cands(c, co, &cands);
       do_cell(cell, cands, tid);
-    });
+    };
+    if (dev_rescore && !getenv_host_fin) {
+      // the records of this chunk came back complete; only the cells finalise_kernel left alone (flag 1: not
+      // scheduled, or undecidable on the device) go through the host logic
+      thread_local std::vector<int64_t> todo;
+      todo.clear();
+      for (int64_t i = 0; i < n; ++i) {
+        if (c->r_flag.p[c0 + i]) todo.push_back(c0 + i);
+        else { resc[0] += c->best.p[c0 + i].n_rescored; resc_gpu[0] += c->best.p[c0 + i].n_rescored; }
+      }
+      // their re-score lists: a few single copies, or the chunk's slice
+      int64_t nlist = 0;
+      for (const int64_t cell : todo) nlist += c->status[cell] == 0;
+      // (synchronous copies: the chunk's lists are final, and the streams -- non-blocking ones -- carry later chunks)
+      if (nlist > 0 && nlist < 32) {
+        for (const int64_t cell : todo)
+          if (c->status[cell] == 0)
+            CU(cudaMemcpy(c->r_lists.p + cell, c->d_lists.p + cell, sizeof(RescList), cudaMemcpyDeviceToHost));
+      } else if (nlist > 0) {
+        CU(cudaMemcpy(c->r_lists.p + c0, c->d_lists.p + c0, n * sizeof(RescList), cudaMemcpyDeviceToHost));
+      }
+      if (todo.size() < 64) for (const int64_t cell : todo) host_cell(cell, 0);
+      else c->pool->run((int64_t)todo.size(), nth, [&](int64_t i, int tid) { host_cell(todo[i], tid); });
+    } else {
+      if (dev_rescore && n > 0)
+        CU(cudaMemcpy(c->r_lists.p + c0, c->d_lists.p + c0, n * sizeof(RescList), cudaMemcpyDeviceToHost));
+      c->pool->run(n, nth, [&](int64_t i, int tid) { host_cell(c0 + i, tid); });
+    }
     fin_ms += now_ms() - tf0;
   }
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaStreamSynchronize(c->stream3));
   if (pipelined) CU(cudaStreamSynchronize(c->stream2));
-  c->st.d2h_bytes = nc * (int64_t)(sizeof(CellOut) + (dev_rescore ? sizeof(RescList) : 0)) + (int64_t)nc * nv * 8 * (1 + nA + (sp.want_single ? 1 : 0)) +
+  c->st.d2h_bytes = nc * (int64_t)(sizeof(CellOut) + (dev_rescore ? sizeof(dmx_best_rec) + 1 : 0)) + (int64_t)nc * nv * 8 * (1 + nA + (sp.want_single ? 1 : 0)) +
                     nc * nA * 8 + (sp.want_single ? nc * 8 : 0);
   float ms = 0;
   c->st.prep_ms = 0; c->st.pair_kernel_ms = 0; c->st.d2h_ms = 0;
@@ -1450,7 +1502,7 @@ int run_path(dmx_ctx* c, bool pipelined) {
         candidates_from_dense(dense_host.data() + (size_t)i * per, nv, nA, 1, sp.eps_rel,
                               sp.eps_ent * (double)(c->h_cell_ptr[cl + 1] - c->h_cell_ptr[cl]), &cands);
         do_cell(cells[i], cands, tid);
-        c->best[cells[i]].exact_mask |= DMX_X_FULLCELL;
+        c->best.p[cells[i]].exact_mask |= DMX_X_FULLCELL;
       });
     }
     c->st.n_fullcell = (int64_t)ov.size();
@@ -1458,6 +1510,12 @@ int run_path(dmx_ctx* c, bool pipelined) {
   fin_ms += now_ms() - tf1;
   c->st.n_rescored_gpu = 0;
   for (int t = 0; t < nth; ++t) { c->st.n_rescored += resc[t]; c->st.n_rescored_gpu += resc_gpu[t]; }
+  if (getenv("DMX_FIN_DEBUG") && dev_rescore) {
+    int64_t nh = 0;
+    for (int64_t i = 0; i < nc; ++i) nh += c->status[i] == 0 && c->r_flag.p[i] != 0;
+    fprintf(stderr, "dmx: %lld of %lld cells finalised on the host, finaliser %.3f ms on %d threads\n", (long long)nh,
+            (long long)nact, fin_ms, nth);
+  }
   c->st.gpu_exact = c->gpu_exact ? 1 : 0;
   c->st.finalise_ms = fin_ms;
   c->st.n_entries = c->E;
@@ -1520,7 +1578,7 @@ int dmx_run(dmx_ctx* c) {
 int dmx_get_best(dmx_ctx* c, dmx_best_rec* out) {
   if (!c || !out) return DMX_E_INVALID;
   if (!c->computed) return DMX_E_STATE;
-  if (c->ncells) memcpy(out, c->best.data(), c->ncells * sizeof(dmx_best_rec));
+  if (c->ncells) memcpy(out, c->best.p, c->ncells * sizeof(dmx_best_rec));
   return DMX_OK;
 }
 
@@ -1722,7 +1780,7 @@ int dmx_write_outputs(dmx_ctx* c, const char* const* barcodes, const char* const
       std::string& ob = bufsb[(size_t)blk];
       for (int64_t li = l0 + blk * cb; li < std::min(l1, l0 + (blk + 1) * cb); ++li) {
         const int32_t i = live[(size_t)li];
-        const dmx_best_rec& b = c->best[i];
+        const dmx_best_rec& b = c->best.p[i];
         const double* sing = c->r_sing.p + (size_t)i * nv;
         const double l00_0 = c->r_l00.p[(size_t)i * nA];
         // exact values where the finaliser produced them

@@ -201,6 +201,26 @@ struct MergeParams {
   uint8_t mode[DMX_MAX_ALPHA]; // PM_* per alpha index
 };
 
+// device half of the decision logic (finalise_kernel): the reference's comparisons (:746-758, :799-814, :837, :844)
+// on the values of merge_kernel with the re-scored ones of the RescList in place; a cell whose decision needs a value
+// that is neither exact nor clear of its window is left to the host finaliser (flag = 1)
+struct FinaliseParams {
+  int32_t nv, nA;
+  double eps_rel, eps_ent;
+  double w_single;             // (1 - doublet_prior) / nv
+  uint8_t mode[DMX_MAX_ALPHA];
+  const int64_t* cell_ptr;
+  const int32_t* cell_order;
+  const double* sing;          // [ncells][nv]
+  const double* row0;          // [ncells][nA][nv]
+  const double* l00;           // [ncells][nA]
+  const CellOut* out;          // [ncells]
+  const RescList* lists;       // [ncells]
+  dmx_best_rec* best;          // [ncells] out: the whole record (PRB.SNG1 with the device's exp())
+  uint8_t* flag;               // [ncells] out: 1 = the host finaliser takes the cell
+};
+int launch_finalise(const FinaliseParams& p, int64_t nactive, void* stream);
+
 struct EntqParams {
   int32_t U, UQ;
   int32_t nd, sep0;            // dense planes; alpha[0] == 0

@@ -2355,6 +2355,37 @@ __global__ void merge_kernel(const __grid_constant__ MergeParams p, int64_t nact
           if (n < RMAX) L->hyp[n] = (uint32_t)j;   // (j, 0, 0)
           ++n;
         }
+    // decision thresholds (:837, :844) that fall inside their window want their operands exact as well: listing them
+    // here lets finalise_kernel decide the cell on the device (same tests as the host finaliser, on the scanned values)
+    if (!over && n <= RMAX && o.ncand >= 1) {
+      auto add = [&](uint32_t h) {
+        for (int q = 0; q < n && q < RMAX; ++q)
+          if (L->hyp[q] == h) return;
+        if (n < RMAX) L->hyp[n] = h;
+        ++n;
+      };
+      auto nearw = [&](double a, double b) {
+        return fabs(a - b) <= p.eps_rel * (fmax(1.0, fabs(a)) + fmax(1.0, fabs(b))) + 2.0 * eps_abs;
+      };
+      int i2 = -1;
+      for (int j = 0; j < nv; ++j)
+        if (j != i1 && (i2 < 0 || sing[j] > sing[i2])) i2 = j;
+      const double s1 = sing[i1], s2 = i2 >= 0 ? sing[i2] : -INFINITY;
+      bool want_pairs = false;
+      if (nearw(best, s1 + 2.0)) { add((uint32_t)i1); want_pairs = true; }
+      if (i2 >= 0 && nearw(s1, s2 + 2.0)) { add((uint32_t)i1); add((uint32_t)i2); }
+      for (int c = 0; c < o.ncand; ++c) {
+        const int j = o.cand[c] & 0xfff, k = (o.cand[c] >> 12) & 0xfff;
+        if (nearw(best, sing[j])) { add((uint32_t)j); want_pairs = true; }
+        if (nearw(best, sing[k])) { add((uint32_t)k); want_pairs = true; }
+      }
+      if (want_pairs)
+        for (int c = 0; c < o.ncand; ++c) {
+          const uint32_t h = o.cand[c];
+          add(h);
+          if (p.mode[h >> 24] == PM_SYM) add(((h >> 12) & 0xfffu) | ((h & 0xfffu) << 12) | (h & 0xff000000u));
+        }
+    }
     L->n = (over || n > RMAX) ? -1 : n;
   }
 }
@@ -2362,6 +2393,146 @@ __global__ void merge_kernel(const __grid_constant__ MergeParams p, int64_t nact
 int launch_merge(const MergeParams& p, int64_t nactive, void* stream) {
   if (nactive == 0) return 0;
   merge_kernel<<<(unsigned)((nactive + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p, nactive);
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalise: one thread per active cell applies the reference's comparisons to the values of merge_kernel, with the
+// re-scored (reference-exact) values of the cell's RescList in place of the scanned ones -- the logic of
+// dmx_finalise.cpp:finalise_cell for the case that every value it wants exact is on the list.  Anything else
+// (candidate overflow, a list that did not fit, a decision threshold inside its window that needs one more exact
+// value) is flagged for the host finaliser, which re-derives the cell from the same arrays.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool fin_near(double a, double b, double eps_rel, double eps_abs) {
+  return fabs(a - b) <= eps_rel * (fmax(1.0, fabs(a)) + fmax(1.0, fabs(b))) + 2.0 * eps_abs;
+}
+
+__global__ void __launch_bounds__(128) finalise_kernel(const __grid_constant__ FinaliseParams p, int64_t nactive) {
+  const int64_t aidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (aidx >= nactive) return;
+  const int cell = p.cell_order[aidx];
+  const int nv = p.nv;
+  const CellOut co = p.out[cell];
+  const RescList* L = p.lists + cell;
+  const int ln = L->n;
+  if (co.ncand > MAX_CAND || co.ncand < 1 || ln < 0) { p.flag[cell] = 1; return; }
+  const double* sing = p.sing + (int64_t)cell * nv;
+  const double eps_abs = p.eps_ent * (double)(p.cell_ptr[cell + 1] - p.cell_ptr[cell]);
+  // the listed singlets (j, 0, 0) carry exact values
+  auto sval = [&](int j, bool* exact) -> double {
+    for (int q = 0; q < ln; ++q)
+      if (L->hyp[q] == (uint32_t)j) { *exact = true; return L->val[q]; }
+    *exact = false;
+    return sing[j];
+  };
+  bool any_sing = false;
+  for (int q = 0; q < ln; ++q) any_sing |= L->hyp[q] < 0x1000u;
+  // ---- were the singlets too close to call?  then merge_kernel listed every one inside the window (same test)
+  {
+    int i1 = 0;
+    for (int j = 1; j < nv; ++j)
+      if (sing[j] > sing[i1]) i1 = j;
+    double m2 = -INFINITY;
+    for (int j = 0; j < nv; ++j)
+      if (j != i1) m2 = fmax(m2, sing[j]);
+    const double w = 2.0 * (p.eps_rel * fmax(1.0, fabs(m2)) + eps_abs);
+    int close2 = 0;
+    for (int j = 0; j < nv; ++j)
+      if (j != i1 && sing[j] >= m2 - w) ++close2;
+    if (sing[i1] - m2 <= w || close2 >= 2) {
+      for (int j = 0; j < nv; ++j)
+        if (sing[j] >= m2 - w) {
+          bool ex;
+          sval(j, &ex);
+          if (!ex) { p.flag[cell] = 1; return; }
+        }
+    }
+  }
+  // ---- top-2 singlets, :746-758
+  int iS1 = -1, iS2 = -1;
+  double max1 = -1e300, max2 = -1e300;
+  bool x1 = false, x2 = false;
+  for (int j = 0; j < nv; ++j) {
+    bool ex = false;
+    const double v = any_sing ? sval(j, &ex) : sing[j];
+    if (max1 < v) { max2 = max1; iS2 = iS1; x2 = x1; iS1 = j; max1 = v; x1 = ex; }
+    else if (max2 < v) { iS2 = j; max2 = v; x2 = ex; }
+  }
+  // ---- best pair, :799-814: the candidates in (j, k, n) lexicographic order, both orders of a symmetric plane
+  uint32_t ch[2 * MAX_CAND];
+  int nc = 0;
+  for (int c = 0; c < co.ncand; ++c) {
+    const uint32_t h = co.cand[c];
+    ch[nc++] = h;
+    if (p.mode[h >> 24] == PM_SYM) ch[nc++] = ((h >> 12) & 0xfffu) | ((h & 0xfffu) << 12) | (h & 0xff000000u);
+  }
+  auto key = [](uint32_t h) { return ((uint64_t)(h & 0xfffu) << 24) | ((uint64_t)((h >> 12) & 0xfffu) << 12) | (uint64_t)(h >> 24); };
+  for (int a = 1; a < nc; ++a) {
+    const uint32_t h = ch[a];
+    int b = a - 1;
+    while (b >= 0 && key(ch[b]) > key(h)) { ch[b + 1] = ch[b]; --b; }
+    ch[b + 1] = h;
+  }
+  int jB = -1, kB = -1, nB = -1;
+  double llk12 = co.best_v;
+  bool llk12_exact = false;
+  if (nc == 1) {
+    jB = ch[0] & 0xfff; kB = (ch[0] >> 12) & 0xfff; nB = ch[0] >> 24;
+    for (int q = 0; q < ln; ++q)   // listed by merge_kernel when a decision threshold is close
+      if (L->hyp[q] == ch[0]) { llk12 = L->val[q]; llk12_exact = true; break; }
+  } else {
+    double mx = -1e300;
+    for (int a = 0; a < nc; ++a) {
+      double v = 0.0;
+      bool have = false;
+      for (int q = 0; q < ln; ++q)
+        if (L->hyp[q] == ch[a]) { v = L->val[q]; have = true; break; }
+      if (!have) { p.flag[cell] = 1; return; }
+      if (mx < v) { mx = v; jB = ch[a] & 0xfff; kB = (ch[a] >> 12) & 0xfff; nB = ch[a] >> 24; llk12_exact = true; }
+    }
+    llk12 = mx;
+  }
+  if (iS1 < 0 || iS2 < 0 || jB < 0) { p.flag[cell] = 1; return; }   // NaN inputs: the host keeps the indices valid
+  // ---- decision thresholds :837, :844: every comparison clear of its window, or between exact values
+  bool xj = false, xk = false;
+  const double l1 = any_sing ? sval(jB, &xj) : sing[jB], l2 = any_sing ? sval(kB, &xk) : sing[kB];
+  {
+    bool bad = false;
+    if (fin_near(llk12, l1, p.eps_rel, eps_abs)) bad |= !(llk12_exact && xj);
+    if (fin_near(llk12, l2, p.eps_rel, eps_abs)) bad |= !(llk12_exact && xk);
+    if (fin_near(llk12, max1 + 2, p.eps_rel, eps_abs)) bad |= !(llk12_exact && x1);
+    if (fin_near(max1, max2 + 2, p.eps_rel, eps_abs)) bad |= !(x1 && x2);
+    if (bad) { p.flag[cell] = 1; return; }
+  }
+  dmx_best_rec r;
+  r.status = 0; r.n_snp = (int32_t)(p.cell_ptr[cell + 1] - p.cell_ptr[cell]);
+  r.sng1 = iS1; r.sng2 = iS2; r.dbl1 = jB; r.dbl2 = kB; r.alpha_idx = nB;
+  r.sng_llk1 = max1; r.sng_llk2 = max2;
+  r.sng_llk0 = p.l00[(int64_t)cell * p.nA];
+  r.llk12 = llk12; r.llk1 = l1; r.llk2 = l2;
+  r.llk10 = p.row0[((int64_t)cell * p.nA + nB) * nv + jB];   // :824 (nB >= 1: always a dense plane)
+  r.llk20 = p.row0[((int64_t)cell * p.nA + nB) * nv + kB];   // :825
+  r.llk00 = p.l00[(int64_t)cell * p.nA + nB];
+  r.max_llk = co.max_llk; r.sum_single = co.sum_single; r.sum_double = co.sum_double;
+  r.prb_dbl = __ddiv_rn(co.sum_double, __dadd_rn(co.sum_single, co.sum_double));   // :827
+  r.prb_sng1 = exp(max1 - co.max_llk) * p.w_single / co.sum_single;                 // :828
+  r.n_rescored = ln;
+  r.exact_mask = 0;
+  if (x1) r.exact_mask |= DMX_X_SNG1 | (jB == iS1 ? DMX_X_LLK1 : 0) | (kB == iS1 ? DMX_X_LLK2 : 0);
+  if (x2) r.exact_mask |= DMX_X_SNG2;
+  if (xj) r.exact_mask |= DMX_X_LLK1;
+  if (xk) r.exact_mask |= DMX_X_LLK2;
+  if (llk12_exact) r.exact_mask |= DMX_X_LLK12;
+  if ((r.llk12 > r.llk1) && (r.llk12 > r.llk2) && (r.llk12 > r.sng_llk1 + 2)) r.call = 0;   // :837
+  else if (r.sng_llk1 > r.sng_llk2 + 2) r.call = 1;                                           // :844
+  else r.call = 2;
+  p.best[cell] = r;
+  p.flag[cell] = 0;
+}
+
+int launch_finalise(const FinaliseParams& p, int64_t nactive, void* stream) {
+  if (nactive == 0) return 0;
+  finalise_kernel<<<(unsigned)((nactive + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p, nactive);
   return (int)cudaGetLastError();
 }
 
