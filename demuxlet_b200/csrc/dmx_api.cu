@@ -119,6 +119,8 @@ struct dmx_ctx {
   PinBuf<uint16_t> o_reads;
   std::vector<int32_t> totl, npass, uniq;
   bool have_gp = false, have_plp = false, gp_dirty = true, plp_dirty = true, uploaded = false, computed = false;
+  std::vector<int64_t> sched_cell_ptr;   // cell_ptr the current schedule was built for
+  int gptab_state = 0;              // tables derived from the device GP matrix: 0 stale, 1 GP rows, 2 + dosage / row-sum tables
 
   // device
   DevBuf<float> d_gp;              // uploaded [nsnps][nvp*3]
@@ -926,6 +928,7 @@ int dmx_set_gp(dmx_ctx* c, const float* gp, int64_t nsnps) {
   }
   c->have_gp = true;
   c->gp_dirty = true;
+  c->gptab_state = 0;
   c->uploaded = false;
   c->computed = false;
   return DMX_OK;
@@ -959,10 +962,23 @@ int dmx_set_pileup(dmx_ctx* c, int64_t ncells, const int64_t* cell_ptr, const in
     c->h_cell_ptr = c->o_cell_ptr.p; c->h_ent_snp = c->o_ent_snp.p; c->h_ent_ptr = c->o_ent_ptr.p;
     c->h_reads = c->o_reads.p;
   }
-  c->totl.assign(totl, totl + ncells);
+  // schedule: drop filtered (:581) and empty (:592) cells, largest cells first.  It depends on the cell sizes and the
+  // read counts only: a caller that hands in the same droplets again (new reads, new qualities) keeps it
+  const bool same_sched = c->have_plp && (int64_t)c->sched_cell_ptr.size() == ncells + 1 &&
+                          (int64_t)c->totl.size() == ncells && (int64_t)c->uniq.size() == ncells &&
+                          memcmp(c->sched_cell_ptr.data(), cell_ptr, (ncells + 1) * sizeof(int64_t)) == 0 &&
+                          memcmp(c->totl.data(), totl, ncells * sizeof(int32_t)) == 0 &&
+                          memcmp(c->uniq.data(), uniq, ncells * sizeof(int32_t)) == 0;
   c->npass.assign(pass, pass + ncells);
+  if (same_sched) {
+    c->plp_dirty = true;
+    c->uploaded = false;
+    c->computed = false;
+    return DMX_OK;
+  }
+  c->totl.assign(totl, totl + ncells);
   c->uniq.assign(uniq, uniq + ncells);
-  // schedule: drop filtered (:581) and empty (:592) cells, largest cells first
+  c->sched_cell_ptr.assign(cell_ptr, cell_ptr + ncells + 1);
   c->status.assign(ncells, 0);
   c->order.clear();
   for (int64_t i = 0; i < ncells; ++i) {
@@ -973,7 +989,7 @@ int dmx_set_pileup(dmx_ctx* c, int64_t ncells, const int64_t* cell_ptr, const in
   }
   // chunks: contiguous cell-id ranges with about the same number of entries; inside a chunk the active cells are
   // scheduled largest first.  Copies, kernels and the host finaliser of different chunks overlap (run_path).
-  int K = (E >= (2 << 20) && ncells >= 256) ? 3 : 1;
+  int K = (E >= (2 << 20) && ncells >= 256) ? 2 : 1;
   if (const char* ek = getenv("DMX_CHUNKS")) K = std::max(1, std::min(16, atoi(ek)));
   // one sort of the active cells (largest first, ties by cell id) serves every schedule: a chunked schedule is a
   // stable partition of it by chunk
@@ -993,9 +1009,10 @@ int dmx_set_pileup(dmx_ctx* c, int64_t ncells, const int64_t* cell_ptr, const in
       Chunk ck;
       ck.c0 = cb;
       int64_t ce = cb;
-      // a small first chunk lets the kernels start early, a small last one shortens the exposed tail (read back
-      // and finaliser of the last chunk); three chunks: 15 % / 55 % / 30 % of the entries
-      const double frac = nk == 3 ? (k == 0 ? 0.15 : 0.70) : (nk == 2 ? 0.2 : (double)(k + 1) / nk);
+      // a small first chunk lets the kernels start early (two chunks by default: 24 % / 76 % of the entries)
+      double f2 = 0.24;   // two chunks: the first one's kernels should end about when the second one's copies do
+      if (const char* ef = getenv("DMX_CHUNK_F0")) f2 = std::min(0.9, std::max(0.02, atof(ef)));
+      const double frac = nk == 3 ? (k == 0 ? 0.15 : 0.70) : (nk == 2 ? f2 : (double)(k + 1) / nk);
       if (k == nk - 1) ce = ncells;
       else
         while (ce < ncells && (double)cell_ptr[ce] < frac * (double)E) ++ce;
@@ -1010,9 +1027,9 @@ int dmx_set_pileup(dmx_ctx* c, int64_t ncells, const int64_t* cell_ptr, const in
       cb = ce;
     }
   };
-  // resident inputs: one chunk, unless the host has few threads for the finaliser (several ranks sharing a box):
-  // then chunks let it run under the kernels of the following chunk
-  build((K > 1 && host_threads(c) < 8) ? K : 1, &c->order, &c->chunks);
+  // resident inputs: one chunk (every chunk costs ~0.3 ms of latency-bound per-cell kernels and a pipeline fill of the
+  // scan; the decision logic runs on the device, so the host has nothing to overlap)
+  build(1, &c->order, &c->chunks);
   build(K, &c->order_p, &c->chunks_p);
   c->have_plp = true;
   c->plp_dirty = true;
@@ -1373,13 +1390,19 @@ int run_path(dmx_ctx* c, bool pipelined) {
     CU(cudaMemsetAsync(c->d_best.p, 0, (size_t)nc * sizeof(dmx_best_rec), c->stream));
   }
   if (pipelined) CU(cudaStreamWaitEvent(c->stream, ev_up[1], 0));
-  CU(launch_gprow(c->d_gp.p, c->d_gprow.p, c->nsnps, nv, c->nvp, c->stream));
-  if (c->nsnps) c->st.gpu_launches += 1;
-  if (fp32 && c->scan_gen == 2 && c->nsnps) {
+  // tables derived from the GP matrix: once per matrix (a run with the inputs resident finds them in place)
+  const int want_tab = (fp32 && c->scan_gen == 2) ? 2 : 1;
+  if (pipelined) c->gptab_state = 0;
+  if (c->gptab_state < 1) {
+    CU(launch_gprow(c->d_gp.p, c->d_gprow.p, c->nsnps, nv, c->nvp, c->stream));
+    if (c->nsnps) c->st.gpu_launches += 1;
+  }
+  if (want_tab == 2 && c->gptab_state < 2 && c->nsnps) {
     CU(launch_dtab(c->d_gprow.p, c->d_drow.p, c->d_srow.p, c->nsnps, c->nvp, c->stream));
     c->st.gpu_launches += 1;
-    CU(cudaMemsetAsync(c->d_lm.p, 0, (size_t)nc * nA * sizeof(double), c->stream));
   }
+  c->gptab_state = std::max(c->gptab_state, want_tab);
+  if (want_tab == 2) CU(cudaMemsetAsync(c->d_lm.p, 0, (size_t)nc * nA * sizeof(double), c->stream));
   c->entq_full = !fp32;
   if (fp32 && !c->memo_ready && c->nsnps > 0 && c->E > 0) RC(build_memo(c));
   ScanParams sp;
@@ -2077,6 +2100,7 @@ int dmx_set_field(dmx_ctx* c, int32_t field, const void* in, int64_t nsnps, doub
   c->h_gp = c->o_gp.p;
   c->have_gp = true;
   c->gp_dirty = false;     // the device copy is already in place: dmx_upload / dmx_run skip the matrix
+  c->gptab_state = 0;
   c->uploaded = false;
   c->computed = false;
   return DMX_OK;

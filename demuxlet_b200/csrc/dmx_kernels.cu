@@ -591,38 +591,51 @@ __global__ void __launch_bounds__(128) classify_kernel(const int64_t* __restrict
                                                        const uint16_t* __restrict__ reads, int64_t c0, int64_t c1,
                                                        int32_t* __restrict__ perm, int32_t* __restrict__ cell_na,
                                                        int32_t* __restrict__ glist) {
-  const int lane = threadIdx.x & 31;
-  const int64_t cell = c0 + (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  // one block per cell (a warp per cell left the kernel waiting for the few largest cells): 128 entries per round,
+  // positions from the warps' ballots and a prefix over the four warps
+  __shared__ int wa[4], wg[4];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t cell = c0 + (int64_t)blockIdx.x;
   if (cell >= c1) return;
   const int64_t e0 = cell_ptr[cell], e1 = cell_ptr[cell + 1];
   int ra = 0, rg = 0;
   const unsigned lt = (1u << lane) - 1u;
-  for (int64_t b = e0; b < e1; b += 32) {
-    const int64_t e = b + lane;
+  for (int64_t b = e0; b < e1; b += 128) {
+    const int64_t e = b + threadIdx.x;
     const bool in = e < e1;
     bool aff = false;
     if (in) {
       int nvr = 0;
-      for (int64_t r = ent_ptr[e]; r < ent_ptr[e + 1]; ++r) nvr += (reads[r] >> 8) != 2;
+      const int64_t r1 = ent_ptr[e + 1];
+      for (int64_t r = ent_ptr[e]; r < r1; ++r) nvr += (reads[r] >> 8) != 2;
       aff = nvr <= 1;
     }
     const unsigned ma = __ballot_sync(0xffffffffu, aff), mg = __ballot_sync(0xffffffffu, in && !aff);
+    if (lane == 0) { wa[w] = __popc(ma); wg[w] = __popc(mg); }
+    __syncthreads();
+    int pa = 0, pg = 0, ta = 0, tg = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (q < w) { pa += wa[q]; pg += wg[q]; }
+      ta += wa[q]; tg += wg[q];
+    }
     if (in) {
-      const int64_t pos = aff ? e0 + ra + __popc(ma & lt) : e1 - 1 - (rg + __popc(mg & lt));
+      const int64_t pos = aff ? e0 + ra + pa + __popc(ma & lt) : e1 - 1 - (rg + pg + __popc(mg & lt));
       perm[e] = (int32_t)(pos - e);
       glist[pos] = (int32_t)e | (aff ? 0 : (int32_t)0x80000000);
     }
-    ra += __popc(ma);
-    rg += __popc(mg);
+    ra += ta;
+    rg += tg;
+    __syncthreads();
   }
-  if (lane == 0) cell_na[cell] = ra;
+  if (threadIdx.x == 0) cell_na[cell] = ra;
 }
 
 int launch_classify(const int64_t* cell_ptr, const int64_t* ent_ptr, const uint16_t* reads, int64_t c0, int64_t c1,
                     int32_t* perm, int32_t* cell_na, int32_t* glist, void* stream) {
   if (c1 <= c0) return 0;
-  classify_kernel<<<(unsigned)((c1 - c0 + 3) / 4), 128, 0, (cudaStream_t)stream>>>(cell_ptr, ent_ptr, reads, c0, c1, perm,
-                                                                                   cell_na, glist);
+  classify_kernel<<<(unsigned)(c1 - c0), 128, 0, (cudaStream_t)stream>>>(cell_ptr, ent_ptr, reads, c0, c1, perm, cell_na,
+                                                                         glist);
   return (int)cudaGetLastError();
 }
 
@@ -722,23 +735,35 @@ __global__ void __launch_bounds__(128) cell_scalars_kernel(const __grid_constant
   if (aidx >= nactive) return;
   const int cell = p.cell_order[aidx];
   const int64_t e0 = p.cell_ptr[cell], e1 = p.cell_ptr[cell + 1];
-  const int ns = 2 + 2 * p.nd;
-  for (int s = 0; s < ns; ++s) {
-    if ((s == 0 && !p.want_single) || (s == 1 && !p.sep0) || (s >= 2 + p.nd && !p.lm)) continue;
-    double prod = 1.0;
-    int es = 0, nfl = 0, cnt = 0;
+  const int ns = 2 + 2 * p.nd;             // even: the rows are read as double2 pairs, four columns (32 B) per pass
+  for (int s0 = 0; s0 < ns; s0 += 4) {
+    const bool two = s0 + 2 < ns;          // the last pass of a row with ns % 4 == 2 has one pair only
+    double prod[4] = {1.0, 1.0, 1.0, 1.0};
+    int es[4] = {0, 0, 0, 0}, nfl = 0, cnt = 0;
+#pragma unroll 4
     for (int64_t e = e0 + lane; e < e1; e += 32) {
-      prod *= __ldg(p.ents + e * ns + s);
-      if (++cnt == 16) { peel(prod, es); ++nfl; cnt = 0; }
-    }
-    double v = unpeel_log(prod, es, nfl);
+      const double2* row = reinterpret_cast<const double2*>(p.ents + e * ns + s0);
+      const double2 a = __ldg(row);
+      const double2 b = two ? __ldg(row + 1) : make_double2(1.0, 1.0);
+      prod[0] *= a.x; prod[1] *= a.y; prod[2] *= b.x; prod[3] *= b.y;
+      if (++cnt == 16) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) {
-      if (s == 0) p.p1_0[cell] = v;
-      else if (s == 1) p.l00[(int64_t)cell * p.nA] = v;
+        for (int i = 0; i < 4; ++i) peel(prod[i], es[i]);
+        ++nfl;
+        cnt = 0;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int s = s0 + i;
+      double v = unpeel_log(prod[i], es[i], nfl);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane != 0 || s >= ns) continue;
+      if (s == 0) { if (p.want_single) p.p1_0[cell] = v; }
+      else if (s == 1) { if (p.sep0) p.l00[(int64_t)cell * p.nA] = v; }
       else if (s < 2 + p.nd) p.l00[(int64_t)cell * p.nA + p.plane_n[s - 2]] = v;
-      else p.lm[(int64_t)cell * p.nA + p.plane_n[s - 2 - p.nd]] = v;
+      else if (p.lm) p.lm[(int64_t)cell * p.nA + p.plane_n[s - 2 - p.nd]] = v;
     }
   }
 }
@@ -2617,35 +2642,46 @@ __global__ void __launch_bounds__(256) rescore_terms_kernel(const __grid_constan
   }
 }
 
-// one warp per (cell, hypothesis): lanes fetch 32 consecutive terms at a time (one coalesced request, a batch ahead),
-// lane 0 owns the chain of dependent additions in entry order and receives the terms by shuffle
+// one warp per cell: the lanes fetch 32 consecutive terms of each listed hypothesis at a time (coalesced, a batch
+// ahead) and stage them in shared memory; lane h owns the chain of dependent additions of hypothesis h, in entry order
+// as the reference's accumulation demands.  (Handing the terms to one lane by shuffle cost 148 M warp instructions for
+// 20 k chains; a thread per chain with its own loads was latency bound at 1 ms.)
 __global__ void __launch_bounds__(128) rescore_sum_kernel(const __grid_constant__ RescoreParams p, int64_t nactive,
                                                           int pass) {
-  const int lane = threadIdx.x & 31;
-  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wid < nactive * RESC_FAST; wid += nw) {
-    const int64_t aidx = wid / RESC_FAST;
-    const int h = (int)(wid % RESC_FAST);
-    const int cell = p.cell_order[aidx];
-    RescList* L = p.lists + cell;
-    if (L->n < 0 || pass * RESC_FAST + h >= L->n) continue;
-    const int64_t e0 = p.cell_ptr[cell], n = p.cell_ptr[cell + 1] - e0;
-    const double* x = p.terms + e0 * RESC_FAST + h * n;
-    double acc = 0.0;
-    double cur = lane < n ? __ldcg(x + lane) : 0.0;
-    for (int64_t i = 0; i < n; i += 32) {
-      const double nxt = (i + 32 + lane < n) ? __ldcg(x + i + 32 + lane) : 0.0;
-      const int cnt = (int)min((int64_t)32, n - i);
+  __shared__ double buf[4][RESC_FAST][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t aidx = (int64_t)blockIdx.x * 4 + w;
+  if (aidx >= nactive) return;
+  const int cell = p.cell_order[aidx];
+  RescList* L = p.lists + cell;
+  const int H = min(L->n - pass * RESC_FAST, RESC_FAST);   // hypotheses of this pass
+  if (H <= 0) return;
+  const int64_t e0 = p.cell_ptr[cell], n = p.cell_ptr[cell + 1] - e0;
+  const double* x = p.terms + e0 * RESC_FAST;               // this cell's block: [h][entry]
+  double cur[RESC_FAST];
+#pragma unroll
+  for (int h = 0; h < RESC_FAST; ++h) cur[h] = (h < H && lane < n) ? __ldcg(x + h * n + lane) : 0.0;
+  double acc = 0.0;
+  for (int64_t i = 0; i < n; i += 32) {
+#pragma unroll
+    for (int h = 0; h < RESC_FAST; ++h)
+      if (h < H) buf[w][h][lane] = cur[h];
+#pragma unroll
+    for (int h = 0; h < RESC_FAST; ++h)
+      if (h < H) cur[h] = (i + 32 + lane < n) ? __ldcg(x + h * n + i + 32 + lane) : 0.0;
+    __syncwarp();
+    const int cnt = (int)min((int64_t)32, n - i);
+    if (lane < H) {
       if (cnt == 32) {
 #pragma unroll
-        for (int u2 = 0; u2 < 32; ++u2) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, cur, u2));
+        for (int u2 = 0; u2 < 32; ++u2) acc = __dadd_rn(acc, buf[w][lane][u2]);
       } else {
-        for (int u2 = 0; u2 < cnt; ++u2) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, cur, u2));
+        for (int u2 = 0; u2 < cnt; ++u2) acc = __dadd_rn(acc, buf[w][lane][u2]);
       }
-      cur = nxt;
     }
-    if (lane == 0) L->val[pass * RESC_FAST + h] = acc;
+    __syncwarp();
   }
+  if (lane < H) L->val[pass * RESC_FAST + lane] = acc;
 }
 
 int launch_rescore(const RescoreParams& p, int64_t nactive, void* stream) {
@@ -2655,8 +2691,7 @@ int launch_rescore(const RescoreParams& p, int64_t nactive, void* stream) {
   for (int pass = 0; pass * RESC_FAST < RMAX; ++pass) {
     const int64_t grid = pass == 0 ? nactive : (nactive < 1184 ? nactive : 1184);
     rescore_terms_kernel<<<(unsigned)grid, 256, 0, st>>>(p, nactive, pass);
-    const int64_t gsum = (nactive * RESC_FAST + 3) / 4;
-    rescore_sum_kernel<<<(unsigned)(pass == 0 ? gsum : (gsum < 1184 ? gsum : 1184)), 128, 0, st>>>(p, nactive, pass);
+    rescore_sum_kernel<<<(unsigned)((nactive + 3) / 4), 128, 0, st>>>(p, nactive, pass);
   }
   return (int)cudaGetLastError();
 }
