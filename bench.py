@@ -4,7 +4,7 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C3]
 
 A "step" is one pass of the hot path (cmd_cram_demuxlet.cpp:386-875 equivalent: entry tables, pair scan,
-reductions, read-back, exact tie finaliser) over one batch of synthetic pileups of the headline shape
+reductions, exact re-scoring of near ties, decision logic, read-back) over one batch of synthetic pileups of the headline shape
 (10k barcodes x 64 samples x 100k SNPs, alpha {0, 0.5}; SURVEY 8d "synth-v1").  One process per GPU;
 with N > 1 every rank owns its own 10k-barcode shard (weak scaling: barcodes are independent) and the
 ranks exchange the per-barcode best records with one NCCL all-gather inside the timed region.
@@ -129,7 +129,8 @@ def fp_roofline(plp, alphas, pair_s, fp32, clocks):
     ach = flop / pair_s / 1e12
     return {"bound": "fp32 pipe" if fp32 else "fp64 pipe", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
             "frac": ach / peak, "flop_per_launch": flop,
-            "note": "7 flop per hypothesis and pileup entry (4 issue slots); peak = 148 SMs x lanes x 2 x SM clock"}
+            "note": "7 flop per hypothesis and pileup entry (the K = 3 form; entries with one informative read are "
+                    "evaluated in an equivalent 2-flop form); peak = 148 SMs x lanes x 2 x SM clock"}
 
 
 def cpu_baseline(plp, alphas, budget_s: float = 15.0):
@@ -421,7 +422,7 @@ def run_ours(args):
     peak, peak_src = load_peaks()
     pair_s = float(np.mean(main["rec"]["pair"])) * 1e-3
     achieved = st["algo_bytes"] / pair_s / 1e9
-    kernel = "pair_scan_f32_kernel" if fp32 else "pair_scan_kernel"
+    kernel = ("pair_scan_f32_kernel" if os.environ.get("DMX_SCAN_GEN") == "1" else "pair_scan_v2_kernel") if fp32 else "pair_scan_kernel"
     traffic = None   # DRAM bytes of one launch of this kernel on this workload, from the committed ncu capture
     tpath = os.path.join(ROOT, "profiles", "traffic_%s_%s.json" % (kernel, args.workload))
     if os.path.exists(tpath) and args.scale == 1.0 and scaling == "weak":
@@ -435,7 +436,7 @@ def run_ours(args):
         "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": main["dt"] / args.steps * 1e3, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "f32 pair products + f64 logs / exact re-score" if fp32 else "f64", "data": "synthetic (synth-v1, SURVEY 8d)",
-        "timing": "host wall clock between device synchronisations (a step ends with the host-side tie finaliser), max "
+        "timing": "host wall clock between device synchronisations (a step ends with the records in host memory), max "
                   "over ranks; kernel times below from CUDA events on the library's own stream",
         "config": {"workload": workload_name(args), "alpha": list(map(float, alphas)),
                    "cells_per_gpu": ncells if scaling == "weak" else strong["counts"],

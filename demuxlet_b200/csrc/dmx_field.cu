@@ -166,6 +166,13 @@ __global__ void __launch_bounds__(256) field_gp_kernel(const FieldParams p) {
   }
 }
 
+// RN(a / s) given r = RN(1 / s), for normal operands far from the exponent limits (here: 1e-60 < a <= s <= 3)
+__device__ __forceinline__ double div_shared(double a, double s, double r) {
+  const double q = __dmul_rn(a, r);
+  const double rem = __fma_rn(-q, s, a);
+  return __fma_rn(rem, r, q);
+}
+
 template <int NV>
 __global__ void __launch_bounds__(256) field_pl_kernel(const FieldParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -202,9 +209,14 @@ __global__ void __launch_bounds__(256) field_pl_kernel(const FieldParams p) {
           const double g1 = __dmul_rn(q1, __ldg(p.prob + pg[3 * i + 1]));
           const double g2 = __dmul_rn(q2, __ldg(p.prob + pg[3 * i + 2]));
           const double sum = __dadd_rn(__dadd_rn(__dadd_rn(0.0, g0), g1), g2);
-          og[3 * i] = __ddiv_rn(g0, sum);
-          og[3 * i + 1] = __ddiv_rn(g1, sum);
-          og[3 * i + 2] = __ddiv_rn(g2, sum);
+          // the three IEEE quotients by the same sum (:276-287) from ONE correctly rounded reciprocal: q = a * r,
+          // residual a - q * sum exact in an FMA, q' = q + residual * r -- Markstein's correction step, the tail of the
+          // hardware division sequence itself; checked bit for bit against __ddiv_rn over all 256^3 phred triples and
+          // 2^30 random operands by tools/pl_div_check.cu (profiles/)
+          const double rs = __drcp_rn(sum);
+          og[3 * i] = div_shared(g0, sum, rs);
+          og[3 * i + 1] = div_shared(g1, sum, rs);
+          og[3 * i + 2] = div_shared(g2, sum, rs);
         }
       }
       __syncwarp();

@@ -3,7 +3,7 @@
 // What is computed (reference: /root/reference/cmd_cram_demuxlet.cpp):
 //   entq_kernel       :424-452 + :597-663  per (cell, snp) entry: read likelihood table Q'(p) on the
 //                     distinct mixing proportions p(n,l,m) (:613) and the pass-1 GLs
-//   gp0_kernel        :391-401  cohort mean genotype probability per SNP
+//   gprow_kernel      :391-401  cohort mean genotype probability per SNP (gp0) in front of every GP row
 //   pair_scan_kernel  :455-459 + :665-710  per cell: sum over its entries of log(sum_{l,m} gp_j[l] gp_k[m]
 //                     Q'[n][l][m]) for every sample pair (j,k) of every dense alpha plane, the
 //                     separable alpha = 0 plane factors, llks00, and the pass-1 singlet llks;
@@ -11,14 +11,18 @@
 //   merge_kernel      combines the tasks of a cell (:712-734, :799-814)
 //
 // Design: the bilinear form is factored as S[j][k] = sum_l a_j[l] * w_k[l] with
-// w_k[l] = sum_m Q'[l][m] gp_k[m] (3 FMA per hypothesis instead of 9 terms over a precomputed table)
-// and sum-of-logs is replaced by the log of a running product whose exponent is peeled off into an
-// integer every FLUSH_STAGES stages (1 MUL per hypothesis and entry, one log per hypothesis and cell).
-// A CTA is warp specialised: loader warps issue TMA copies (tile::gather4 of the GP rows, bulk copies of the entry
-// tables) into a raw ring; transform warps turn them into operand blocks in a processed ring; consumer warps own
-// 8 x 8 tiles of hypotheses in registers (fp32 scan: 2 loader, 4 transform, 9 consumer warps and one accumulator
-// warp for the per-sample products; fp64 scan: two pipelines of 1 loader, 2 transform and 5 DMMA consumer warps).
-// Rings are mbarrier pipelines.
+// w_k[l] = sum_m Q'[l][m] gp_k[m] (3 FMA per hypothesis instead of 9 terms over a precomputed table); entries with at
+// most one informative read collapse further to S' = X_j + Y_k (one add, one multiply); sum-of-logs is replaced by
+// the log of a running product with the exponent kept in an integer (one log per hypothesis and cell).
+// Three persistent, warp-specialised scan kernels, all mbarrier pipelines fed by TMA (tile::gather4 of table rows by
+// SNP id + bulk copies of the entry records):
+//   pair_scan_v2_kernel   (dmx_scan2.cuh) default fp32 scan: the gathers deliver ready-to-use operands (dosage rows,
+//                         row sums, raw GP rows): 3 loader, 3 "singles" (per-sample products) and 9 consumer warps,
+//                         a thread owns an 8 x 8 tile of hypotheses for one of the 8 entries of a stage
+//   pair_scan_f32_kernel  first-generation fp32 scan (DMX_SCAN_GEN=1): 2 loader, 4 transform, 9 consumer warps and an
+//                         accumulator warp; operands pass through a processed ring
+//   pair_scan_kernel      fp64 scan on the FP64 tensor path (DMMA): two pipelines of 1 loader, 2 transform and 5
+//                         consumer warps; dense llksAB blocks (--write-pair) and the DMX_FP32_PAIRS-off mode
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>

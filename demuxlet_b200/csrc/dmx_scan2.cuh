@@ -108,6 +108,12 @@ __device__ __forceinline__ bool mbar_test_a(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// DMX_ARRIVE_ALL (sanitizer builds): every lane arrives instead of one lane after __syncwarp, so that racecheck sees an
+// arrival by each thread whose accesses the barrier orders (tools/run_profile.sh part s)
+#ifndef DMX_ARRIVE_ALL
+#define DMX_ARRIVE_ALL 0
+#endif
+constexpr uint32_t V_ARR = DMX_ARRIVE_ALL ? 32u : 1u;   // arrivals per warp
 __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -434,7 +440,7 @@ __device__ __forceinline__ void v2_singles(const ScanParams& p, unsigned char* r
       // a stage multiplies <= 4 entry factors, each >= ~2^-21, into a mantissa in [1, 2): no underflow before the peel
       PROF_WAIT(5, v2_singles_dispatch(same, extras_t, row0, ring + (size_t)slot * slotb, aff, eh, q, nvalid, jq, kq, R));
       __syncwarp();
-      if (lane == 0) mbar_arrive_a(empty0 + slot * 8u);
+      if (DMX_ARRIVE_ALL || lane == 0) mbar_arrive_a(empty0 + slot * 8u);
 #pragma unroll
       for (int a = 0; a < VQ; ++a) {
         if ((a == 4 && !row0) || (a == 5 && same) || ((a == 0 || a == 3) && !extras_t)) continue;   // factors are all 1
@@ -484,7 +490,7 @@ __device__ __forceinline__ void v2_singles(const ScanParams& p, unsigned char* r
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&lb_full[par]);
+      if (DMX_ARRIVE_ALL || lane == 0) mbar_arrive(&lb_full[par]);
       if (eh == 0) {
         // per-sample results: the k-side samples of tasks with TF_EXTRAS; pairs with sample 0 where the task holds them
         const double lb0 = row0 == 2 ? ts->lb[par][1][0] : ts->lb[par][0][0];   // sample 0's share of a pair with it
@@ -529,11 +535,11 @@ __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_v2_kernel(const
   if (threadIdx.x == 0) {
     for (int s = 0; s < nslot; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], V_NCW + 1);
+      mbar_init(&empty[s], (V_NCW + 1) * V_ARR);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&lb_full[s], 1);
-      mbar_init(&lb_empty[s], V_NCW);
+      mbar_init(&lb_full[s], V_ARR);
+      mbar_init(&lb_empty[s], V_NCW * V_ARR);
     }
     scr->ncand = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -610,7 +616,7 @@ __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_v2_kernel(const
     };
     auto end_stage = [&]() {
       __syncwarp();
-      if (lane == 0) mbar_arrive_a(empty0 + slot * 8u);
+      if (DMX_ARRIVE_ALL || lane == 0) mbar_arrive_a(empty0 + slot * 8u);
       slot = slot2;
       ph = ph2;
     };
@@ -717,7 +723,7 @@ __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_v2_kernel(const
       if (valid) vmask |= 1u << c;
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&lb_empty[par]);
+    if (DMX_ARRIVE_ALL || lane == 0) mbar_arrive(&lb_empty[par]);
     PROF_WAIT(3, (task_epilogue<8, V_NCW, false>(p, ti, tt, scr, 0, rw, lane, v, vj, vk, vmask)));
   }
   PROF_END(3, lane)

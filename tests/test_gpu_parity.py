@@ -110,6 +110,28 @@ def test_device_rescorer_matches_host_libm():
     assert np.array_equal(a["llk12"], ref["best"]["pair_llk12"])   # ... and equal to the oracle's bits
 
 
+def test_host_scorer_fallback_when_libm_table_is_missing(monkeypatch):
+    """a host whose libm does not carry glibc's log table (DMX_NO_LIBM_TABLE simulates it) disables the device
+    re-scorer at dmx_create; the host scorer then decides the same records, bit for bit in every exact field"""
+    from demuxlet_b200.api import Demuxlet
+    p = synth(120, 16, 2500, "GP", seed=77)
+    d = Demuxlet(p.nv, (0.0, 0.5))
+    d.set_pileup(p)
+    d.run()
+    assert d.stats()["gpu_exact"] == 1
+    monkeypatch.setenv("DMX_NO_LIBM_TABLE", "1")
+    h = Demuxlet(p.nv, (0.0, 0.5))
+    monkeypatch.delenv("DMX_NO_LIBM_TABLE")
+    h.set_pileup(p)
+    h.run()
+    st = h.stats()
+    assert st["gpu_exact"] == 0 and st["n_rescored_gpu"] == 0 and st["n_rescored"] >= 2 * 120
+    a, b = d.best(), h.best()
+    for f in ("sng1", "sng2", "dbl1", "dbl2", "alpha_idx", "call", "n_snp"):
+        assert np.array_equal(a[f], b[f]), f
+    assert np.array_equal(a["llk12"], b["llk12"])          # the same exact bits from either scorer
+
+
 def _golden_cases():
     import json
     here = os.path.dirname(os.path.abspath(__file__))
@@ -241,6 +263,17 @@ def test_error_paths_and_context_reuse():
     d.set_pileup(p)
     d.run()
     c2 = d.best().copy()
+    d.set_pileup(p)                                # the same droplets again: the schedule is kept, the data re-uploaded
+    d.run()
+    assert d.best().tobytes() == c2.tobytes()
+    r2 = p.reads.copy()
+    r2[::7] = (r2[::7] & 0xff00) | 20              # same droplets, other qualities: not a cached result
+    d.set_pileup_arrays(p.cell_ptr, p.ent_snp, p.ent_ptr, r2, p.totl, p.npass, p.uniq)
+    d.run()
+    assert d.best().tobytes() != c2.tobytes()
+    d.set_pileup(p)
+    d.run()
+    assert d.best().tobytes() == c2.tobytes()
     for f in ("sng1", "sng2", "dbl1", "dbl2", "alpha_idx", "call", "n_snp"):
         assert np.array_equal(a[f], b[f]) and np.array_equal(a[f], c2[f]), f
     # runs are reproducible bit for bit: the per-sample products are accumulated in stage order by one warp, whichever

@@ -21,10 +21,10 @@ cat gpurun_out/${T}_bench_ref.json
 fi
 if has n; then
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_b.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:pair_scan_f32 -s 3 -c 1 -o gpurun_out/${T}_pair_scan_f32 -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:pair_scan_v2 -s 3 -c 1 -o gpurun_out/${T}_pair_scan_v2 -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
-python tools/ncu_summary.py gpurun_out/${T}_pair_scan_f32.ncu-rep gpurun_out/${T}_pair_scan_f32_ncu.csv pair_scan_f32_kernel C3 gpurun_out/traffic_pair_scan_f32_kernel_C3.json
-cat gpurun_out/traffic_pair_scan_f32_kernel_C3.json
+python tools/ncu_summary.py gpurun_out/${T}_pair_scan_v2.ncu-rep gpurun_out/${T}_pair_scan_v2_ncu.csv pair_scan_v2_kernel C3 gpurun_out/traffic_pair_scan_v2_kernel_C3.json
+cat gpurun_out/traffic_pair_scan_v2_kernel_C3.json
 timeout 900 ncu --set full --clock-control none -k regex:"pair_scan_kernel" -s 1 -c 1 -o gpurun_out/${T}_pair_scan_f64 -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --fp64-pairs > gpurun_out/ncu_full64.log 2>&1
 python tools/ncu_summary.py gpurun_out/${T}_pair_scan_f64.ncu-rep gpurun_out/${T}_pair_scan_f64_ncu.csv pair_scan_kernel C3 gpurun_out/traffic_pair_scan_kernel_C3.json
 rm -f gpurun_out/${T}_pair_scan_f64.ncu-rep
@@ -38,6 +38,11 @@ timeout 1200 python bench.py --workload C5 --scale 0.0005 --steps 2 --warmup 3 >
 tail -c 300 gpurun_out/${T}_bench_C5.json
 fi
 if has s; then
+# racecheck also on the build in which every lane arrives on the ring barriers (tools/build_variant.sh arrall -DDMX_ARRIVE_ALL=1)
+if [ -f tools/libdmx_arrall.so ]; then
+echo "== DMX_ARRIVE_ALL build: compute-sanitizer --tool racecheck python tools/sanitize_scan.py" >> gpurun_out/${T}_scan_sanitizer.txt
+DMX_LIB=$PWD/tools/libdmx_arrall.so timeout 900 compute-sanitizer --tool racecheck --print-limit 8 python tools/sanitize_scan.py 2>&1 | cut -c1-400 | tail -30 >> gpurun_out/${T}_scan_sanitizer.txt
+fi
 for TOOL in racecheck synccheck memcheck; do
 echo "== compute-sanitizer --tool $TOOL python tools/sanitize_scan.py" >> gpurun_out/${T}_scan_sanitizer.txt
 timeout 900 compute-sanitizer --tool $TOOL --print-limit 8 python tools/sanitize_scan.py 2>&1 | cut -c1-400 | tail -40 >> gpurun_out/${T}_scan_sanitizer.txt
