@@ -283,6 +283,7 @@ class Case:
         self.ex = RecordExchange(counts, api.BEST_DTYPE.itemsize) if world > 1 else None
         self.total_cells = int(sum(counts))
         self.gathered = None
+        self.t_exchange, self.n_exchange = 0.0, 0
         self.pair_bytes = 0
         self.pair_buf = None
         if args.write_pair:   # --write-pair: the dense llksAB block of every barcode comes back too (:772-797)
@@ -293,7 +294,11 @@ class Case:
 
     def exchange(self):
         if self.ex is not None:
-            self.gathered = self.ex(self.d.best())
+            t0 = time.perf_counter()
+            mine = self.d.best(out=self.ex.send_view(self.api.BEST_DTYPE))   # records straight into the pinned send buffer
+            self.gathered = self.ex(mine)
+            self.t_exchange += time.perf_counter() - t0
+            self.n_exchange += 1
 
     def pairs(self):
         if self.pair_buf is None:
@@ -358,7 +363,8 @@ class Case:
         st2 = d.stats()
         if self.ex is not None and self.rank == 0:
             assert self.gathered is not None and self.gathered.shape[0] == self.total_cells
-        return {"dt": dt, "dt2": dt2, "st": st, "st2": st2, "rec": rec, "clocks": clocks}
+        return {"dt": dt, "dt2": dt2, "st": st, "st2": st2, "rec": rec, "clocks": clocks,
+                "exchange_ms": self.t_exchange / max(self.n_exchange, 1) * 1e3}
 
 
 def run_ours(args):
@@ -464,7 +470,8 @@ def run_ours(args):
         "breakdown_ms": {"prep": float(np.mean(main["rec"]["prep"])), "pair_scan": float(np.mean(main["rec"]["pair"])),
                          "all_kernels": float(np.mean(main["rec"]["kern"])), "d2h": st["d2h_ms"],
                          "finalise_host": float(np.mean(main["rec"]["fin"])),
-                         "rescored_hypotheses": int(st["n_rescored"]), "host_threads": main["host_threads"]},
+                         "rescored_hypotheses": int(st["n_rescored"]), "host_threads": main["host_threads"],
+                         "record_exchange": main["exchange_ms"]},
         "clocks": main["clocks"],
     }
     if args.write_pair:

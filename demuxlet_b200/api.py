@@ -477,8 +477,12 @@ class Demuxlet:
         self._chk(self.lib.dmx_run(self._h), "dmx_run")
 
     # ---- results ----------------------------------------------------------------------------------
-    def best(self) -> np.ndarray:
-        out = np.zeros(self.ncells, dtype=BEST_DTYPE)
+    def best(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """the per-barcode records; `out`: a caller-owned BEST_DTYPE array of ncells records to fill (e.g. a pinned
+        staging buffer of the record exchange) instead of a new one"""
+        if out is None:
+            out = np.zeros(self.ncells, dtype=BEST_DTYPE)
+        assert out.dtype == BEST_DTYPE and out.shape[0] == self.ncells and out.flags["C_CONTIGUOUS"]
         self._chk(self.lib.dmx_get_best(self._h, out.ctypes.data), "dmx_get_best")
         return out
 

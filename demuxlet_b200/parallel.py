@@ -77,11 +77,19 @@ class RecordExchange:
         self.d_recv = torch.zeros(self.world * self.width, dtype=torch.uint8, device=device)
         self.on_device = nccl
 
+    def send_view(self, dtype) -> np.ndarray:
+        """this rank's slot of the pinned send buffer as `dtype` records: fill it in place (Demuxlet.best(out=...)) and
+        call the exchange with that very array to skip one copy"""
+        n = self.counts[self.rank] * self.item
+        return self.h_send.numpy()[:n].view(dtype)
+
     def __call__(self, local: np.ndarray) -> np.ndarray:
         """returns a view of all ranks' records (rank order) valid until the next call"""
         n = self.counts[self.rank] * self.item
         assert local.dtype.itemsize == self.item and local.shape[0] == self.counts[self.rank]
-        self.h_send.numpy()[:n] = local.view(np.uint8).reshape(-1)
+        mine = self.h_send.numpy()[:n]
+        if local.ctypes.data != mine.ctypes.data:
+            mine[:] = local.view(np.uint8).reshape(-1)
         self.d_send.copy_(self.h_send, non_blocking=True)
         self.dist.all_gather_into_tensor(self.d_recv, self.d_send)
         self.h_recv.copy_(self.d_recv, non_blocking=True)
