@@ -85,6 +85,8 @@ class WorkerPool;
 struct Chunk {
   int64_t c0, c1;   // cell ids [c0, c1)
   int64_t o0, o1;   // its active cells, largest first: order[o0, o1)
+  bool packed = false;   // this run sent the chunk's read counts (1 B per entry) instead of ent_ptr (8 B): the kernels of
+                         // the chunk start with entptr_kernel
 };
 
 struct dmx_ctx {
@@ -126,6 +128,10 @@ struct dmx_ctx {
   DevBuf<float> d_gp;              // uploaded [nsnps][nvp*3]
   DevBuf<float> d_gprow;           // [nsnps][8 + nvp*3]: gp0 | samples (gprow_kernel)
   DevBuf<float> d_drow, d_srow;    // second-generation fp32 scan: dosage rows [2 nsnps][nvp + 8], row sums [nsnps][nvp + 8]
+  PinBuf<uint8_t> h_cnt;           // reads per entry, staged by dmx_run for the upload (pack_chunk)
+  PinBuf<int64_t> h_cell_r;        // ent_ptr at the first entry of every cell
+  DevBuf<uint8_t> d_cnt;
+  DevBuf<int64_t> d_cell_r;
   DevBuf<double> d_lm;             // [ncells][nA] sum of log M over the affine entries (cell_scalars_kernel)
   int scan_gen = 2;                // fp32 scan generation (DMX_SCAN_GEN=1 selects pair_scan_f32_kernel)
   DevBuf<double> d_entq, d_row0, d_singA, d_lb, d_p1, d_p1_0, d_l00, d_sing, d_dense, d_dense2;
@@ -893,6 +899,7 @@ void dmx_destroy(dmx_ctx* c) {
   c->d_memo_q.release(); c->d_memo_fh.release(); c->d_memo_fp.release(); c->d_ecode.release();
   c->d_glist.release();
   c->d_drow.release(); c->d_srow.release(); c->d_lm.release();
+  c->h_cnt.release(); c->h_cell_r.release(); c->d_cnt.release(); c->d_cell_r.release();
   c->d_gp.release(); c->d_gprow.release(); c->d_entq.release(); c->d_row0.release(); c->d_singA.release();
   c->d_lb.release(); c->d_p1.release(); c->d_p1_0.release(); c->d_l00.release(); c->d_sing.release();
   c->d_dense.release(); c->d_cell_ptr.release(); c->d_ent_ptr.release(); c->d_ent_snp.release();
@@ -1009,8 +1016,10 @@ int dmx_set_pileup(dmx_ctx* c, int64_t ncells, const int64_t* cell_ptr, const in
       Chunk ck;
       ck.c0 = cb;
       int64_t ce = cb;
-      // a small first chunk lets the kernels start early (two chunks by default: 24 % / 76 % of the entries)
-      double f2 = 0.24;   // two chunks: the first one's kernels should end about when the second one's copies do
+      // a small first chunk lets the kernels start early (two chunks by default: 14 % / 86 % of the entries)
+      // two chunks: the first one's kernels should end about when the second one's copies do -- sooner when the offsets
+      // travel as one-byte read counts (pack_chunk; an entry of a droplet pileup has a handful of reads)
+      double f2 = (R <= 8 * E) ? 0.14 : 0.24;
       if (const char* ef = getenv("DMX_CHUNK_F0")) f2 = std::min(0.9, std::max(0.02, atof(ef)));
       const double frac = nk == 3 ? (k == 0 ? 0.15 : 0.70) : (nk == 2 ? f2 : (double)(k + 1) / nk);
       if (k == nk - 1) ce = ncells;
@@ -1086,16 +1095,55 @@ int upload_common(dmx_ctx* c, cudaStream_t st, int64_t* bytes, const std::vector
   return DMX_OK;
 }
 
-int upload_chunk(dmx_ctx* c, const Chunk& ck, cudaStream_t st, int64_t* bytes) {
+// Host side of the packed upload: ent_ptr is 8 bytes per entry, a third of everything dmx_run sends, yet an entry has a
+// handful of reads.  The pool writes the counts of the chunk's entries (1 byte each) and the first offset of every cell
+// into pinned staging buffers while earlier copies are in flight; entptr_kernel rebuilds the offsets on the device.
+// Returns false (chunk goes unpacked) when an entry has more than 255 reads.
+bool pack_chunk(dmx_ctx* c, const Chunk& ck) {
+  const int64_t e0 = c->h_cell_ptr[ck.c0], e1 = c->h_cell_ptr[ck.c1];
+  if (e1 - e0 < (1 << 16) || getenv("DMX_NO_PTR_PACK")) return false;
+  if (c->h_cnt.reserve((size_t)c->E + 1) != cudaSuccess || c->h_cell_r.reserve((size_t)c->ncells + 2) != cudaSuccess ||
+      c->d_cnt.reserve((size_t)c->E + 1) != cudaSuccess || c->d_cell_r.reserve((size_t)c->ncells + 2) != cudaSuccess)
+    return false;
+  const int nth = host_threads(c);
+  const int64_t n = e1 - e0, blk = 1 << 15, nb = (n + blk - 1) / blk;
+  std::atomic<int> big{0};
+  const int64_t* ep = c->h_ent_ptr;
+  uint8_t* cnt = c->h_cnt.p;
+  c->pool->run(nb, nth, [&](int64_t b, int) {
+    const int64_t lo = e0 + b * blk, hi = std::min(e1, lo + blk);
+    int64_t mx = 0;
+    for (int64_t e = lo; e < hi; ++e) {
+      const int64_t d = ep[e + 1] - ep[e];
+      mx = std::max(mx, d);
+      cnt[e] = (uint8_t)d;
+    }
+    if (mx > 255) big.store(1);
+  });
+  if (big.load()) return false;
+  for (int64_t cl = ck.c0; cl <= ck.c1; ++cl) c->h_cell_r.p[cl] = ep[c->h_cell_ptr[cl]];
+  return true;
+}
+
+int upload_chunk(dmx_ctx* c, Chunk& ck, cudaStream_t st, int64_t* bytes, bool may_pack) {
   if (!c->plp_dirty) return DMX_OK;
   const int64_t e0 = c->h_cell_ptr[ck.c0], e1 = c->h_cell_ptr[ck.c1];
   const int64_t r0 = c->h_ent_ptr[e0], r1 = c->h_ent_ptr[e1];
+  ck.packed = may_pack && pack_chunk(c, ck);
   if (e1 > e0)
     CU(cudaMemcpyAsync(c->d_ent_snp.p + e0, c->h_ent_snp + e0, (e1 - e0) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(c->d_ent_ptr.p + e0, c->h_ent_ptr + e0, (e1 - e0 + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  if (ck.packed) {
+    CU(cudaMemcpyAsync(c->d_cnt.p + e0, c->h_cnt.p + e0, (size_t)(e1 - e0), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->d_cell_r.p + ck.c0, c->h_cell_r.p + ck.c0, (size_t)(ck.c1 - ck.c0 + 1) * sizeof(int64_t),
+                       cudaMemcpyHostToDevice, st));
+    *bytes += (e1 - e0) + (ck.c1 - ck.c0 + 1) * 8;
+  } else {
+    CU(cudaMemcpyAsync(c->d_ent_ptr.p + e0, c->h_ent_ptr + e0, (e1 - e0 + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    *bytes += (e1 - e0 + 1) * 8;
+  }
   if (r1 > r0)
     CU(cudaMemcpyAsync(c->d_reads.p + r0, c->h_reads + r0, (r1 - r0) * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
-  *bytes += (e1 - e0) * 4 + (e1 - e0 + 1) * 8 + (r1 - r0) * 2;
+  *bytes += (e1 - e0) * 4 + (r1 - r0) * 2;
   return DMX_OK;
 }
 
@@ -1197,6 +1245,10 @@ int enqueue_chunk(dmx_ctx* c, const Chunk& ck, const ScanParams& sp0, bool dev_r
   const int64_t e0 = c->h_cell_ptr[ck.c0], e1 = c->h_cell_ptr[ck.c1];
   const int64_t nact = ck.o1 - ck.o0;
   CU(cudaEventRecord(ev[0], c->stream));
+  if (ck.packed) {   // the offsets of this chunk came as read counts
+    CU(launch_entptr(c->d_cell_ptr.p, c->d_cell_r.p, c->d_cnt.p, ck.c0, ck.c1, c->d_ent_ptr.p, c->stream));
+    c->st.gpu_launches += 1;
+  }
   EntqParams eq;
   fill_entq_params(c, &eq, fp32);
   eq.E0 = e0; eq.E = e1;
@@ -1367,13 +1419,8 @@ int run_path(dmx_ctx* c, bool pipelined) {
     CU(cudaEventRecord(ev_up[0], c->stream2));
     RC(upload_common(c, c->stream2, &h2d_bytes, order));
     CU(cudaEventRecord(ev_up[1], c->stream2));
-    for (int k = 0; k < K; ++k) {
-      RC(upload_chunk(c, chunks[k], c->stream2, &h2d_bytes));
-      CU(cudaEventRecord(ev_up[2 + k], c->stream2));
-    }
-    c->gp_dirty = false;
-    c->plp_dirty = false;
-    c->uploaded = true;
+    // (the chunks' copies are enqueued one by one below, each right before its kernels: packing chunk k + 1 on the host
+    // then runs under the copies and kernels of chunk k)
   }
   if (!pipelined && !order.empty())   // dmx_run may have left its own schedule there
     CU(cudaMemcpyAsync(c->d_order.p, order.data(), order.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
@@ -1412,12 +1459,21 @@ int run_path(dmx_ctx* c, bool pipelined) {
     if (rc != DMX_OK) return rc;
   }
   for (int k = 0; k < K; ++k) {
-    if (pipelined) CU(cudaStreamWaitEvent(c->stream, ev_up[2 + k], 0));
+    if (pipelined) {
+      RC(upload_chunk(c, c->chunks_p[k], c->stream2, &h2d_bytes, true));
+      CU(cudaEventRecord(ev_up[2 + k], c->stream2));
+      CU(cudaStreamWaitEvent(c->stream, ev_up[2 + k], 0));
+    }
     const int rc = enqueue_chunk(c, chunks[k], sp, dev_rescore, ev_k + 5 * k);
     if (rc != DMX_OK) return rc;
     CU(cudaEventRecord(ev_done[k], c->stream3));
   }
   CU(cudaEventRecord(ev_last, c->stream));
+  if (pipelined) {
+    c->gp_dirty = false;
+    c->plp_dirty = false;
+    c->uploaded = true;
+  }
 
   // ---- finalise, chunk by chunk as the records arrive ---------------------------------------------------------
   if (!dev_rescore && nc) memset(c->best.p, 0, (size_t)nc * sizeof(dmx_best_rec));   // else every record comes from the device
@@ -1571,7 +1627,7 @@ int dmx_upload(dmx_ctx* c) {
   }
   RC(reserve_inputs(c));
   RC(upload_common(c, c->stream, &bytes, c->order));
-  for (const Chunk& ck : c->chunks) RC(upload_chunk(c, ck, c->stream, &bytes));
+  for (Chunk& ck : c->chunks) RC(upload_chunk(c, ck, c->stream, &bytes, false));
   c->gp_dirty = false;
   c->plp_dirty = false;
   CU(cudaStreamSynchronize(c->stream));

@@ -291,6 +291,10 @@ int launch_dtab(const float* gp_rows, float* drow, float* srow, int64_t nsnps, i
 int launch_entq(const EntqParams& p, void* stream);
 // entry classes of cells [c0, c1): perm[e] = position of entry e inside its cell's block with the affine entries
 // (<= 1 informative read) first, both classes in entry order; cell_na[cell] = number of affine entries
+// ent_ptr[e] of cells [c0, c1) from the per-entry read counts (what dmx_run sends instead of the 8-byte offsets):
+// ent_ptr[e] = cell_r[cell] + sum of cnt over the cell's entries before e; also the end of every cell
+int launch_entptr(const int64_t* cell_ptr, const int64_t* cell_r, const uint8_t* cnt, int64_t c0, int64_t c1,
+                  int64_t* ent_ptr, void* stream);
 int launch_classify(const int64_t* cell_ptr, const int64_t* ent_ptr, const uint16_t* reads, int64_t c0, int64_t c1,
                     int32_t* perm, int32_t* cell_na, int32_t* glist, void* stream);
 int launch_entq_aff(const EntqParams& p, void* stream);

@@ -586,6 +586,47 @@ __global__ void __launch_bounds__(128) entq1_kernel(const __grid_constant__ Entq
   entq_emit(p, e, out, nvr, al1, [&](int slot) { return slot == 0 ? G0 : (slot == 1 ? G1 : (slot == 2 ? G2 : s_val[p.slot_u[slot]][tid])); });
 }
 
+// ent_ptr from read counts: one block per cell, block-wide exclusive scan of the counts in rounds of 128 entries
+__global__ void __launch_bounds__(128) entptr_kernel(const int64_t* __restrict__ cell_ptr, const int64_t* __restrict__ cell_r,
+                                                     const uint8_t* __restrict__ cnt, int64_t c0, int64_t c1,
+                                                     int64_t* __restrict__ ent_ptr) {
+  __shared__ int ws[4];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t cell = c0 + (int64_t)blockIdx.x;
+  if (cell >= c1) return;
+  const int64_t e0 = cell_ptr[cell], e1 = cell_ptr[cell + 1];
+  int64_t run = cell_r[cell];
+  for (int64_t b = e0; b < e1; b += 128) {
+    const int64_t e = b + threadIdx.x;
+    const int v = e < e1 ? (int)cnt[e] : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) ws[w] = inc;
+    __syncthreads();
+    int pre = 0, tot = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (q < w) pre += ws[q];
+      tot += ws[q];
+    }
+    if (e < e1) ent_ptr[e] = run + pre + inc - v;
+    run += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) ent_ptr[e1] = run;   // == cell_r[cell + 1]: the next cell's first offset, written by both
+}
+
+int launch_entptr(const int64_t* cell_ptr, const int64_t* cell_r, const uint8_t* cnt, int64_t c0, int64_t c1,
+                  int64_t* ent_ptr, void* stream) {
+  if (c1 <= c0) return 0;
+  entptr_kernel<<<(unsigned)(c1 - c0), 128, 0, (cudaStream_t)stream>>>(cell_ptr, cell_r, cnt, c0, c1, ent_ptr);
+  return (int)cudaGetLastError();
+}
+
 // entry classes: one warp per cell, one pass over its entries.  The affine entries take the front positions of the
 // cell's block in entry order, the general ones the back positions in reverse entry order (any fixed order serves: the
 // products commute and the exact re-scorer walks the original order).  glist[pos] = entry at that position, sign bit
