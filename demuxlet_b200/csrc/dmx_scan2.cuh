@@ -125,7 +125,7 @@ __device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity, 
   while (!mbar_try_a(bar, parity)) {
     unsigned v = 0;
 #pragma unroll
-    for (int i = 0; i < 3; ++i)   // three dependent round trips (the address of each load depends on the previous value)
+    for (int i = 0; i < 6; ++i)   // six dependent round trips (the address of each load depends on the previous value)
       asm volatile("ld.global.cv.u32 %0, [%1];" : "=r"(v) : "l"(probe + (v & 1u)) : "memory");
     sink += v;
   }
@@ -201,6 +201,16 @@ __device__ __forceinline__ void v2_range_check(float (&acc)[64], int& ex, bool a
         if (!DIAG || c >= i) acc[i * 8 + c] = (acc[i * 8 + c] * s1) * s2;
   }
 }
+
+// 16-byte shared-memory load from a shared-window address (volatile: stays behind the barrier wait it follows)
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+// keeps a loop-invariant value in its register (at the register limit ptxas otherwise re-derives thread-id arithmetic
+// and the shared window base in every iteration of the stage loop)
+#define V_KEEP(x) asm volatile("" : "+r"(x))
 
 struct VFac { float q[VQ][4]; };
 }  // namespace
@@ -563,7 +573,9 @@ __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_v2_kernel(const
   const uint32_t el = (uint32_t)lane & 7u;
   const int pos = rw * 4 + (lane >> 3);
   const uint32_t slotb = (uint32_t)p.v_slot;
-  const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
+  uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty), ring_a = smem_u32(ring);
+  int lane_k = lane;
+  V_KEEP(full0); V_KEEP(empty0); V_KEEP(ring_a); V_KEEP(lane_k);
   uint32_t slot = 0, ph = 0;       // ring position of the next stage (continues across tasks)
   bool ready = false;              // the next stage's barrier has been seen complete
   TaskInfoF ti;
@@ -616,23 +628,31 @@ __global__ void __launch_bounds__(F_LAUNCH_THREADS, 1) pair_scan_v2_kernel(const
     };
     auto end_stage = [&]() {
       __syncwarp();
-      if (DMX_ARRIVE_ALL || lane == 0) mbar_arrive_a(empty0 + slot * 8u);
+      if (DMX_ARRIVE_ALL || lane_k == 0) mbar_arrive_a(empty0 + slot * 8u);
       slot = slot2;
       ph = ph2;
     };
     auto affine_stages = [&](auto diag_c) {
       constexpr bool DIAG = decltype(diag_c)::value;
+      // shared-window addresses of this thread's operands inside slot 0, pinned to registers
+      uint32_t ax = ring_a + xoff, ay = ring_a + yoff, ap = ring_a + poff + 16u;
+      int nlive = act ? ((int)el < nvA ? 2 : ((int)el < NB ? 1 : 0)) : 0;   // 2: live in every stage, 1: not in the last one
+      V_KEEP(ax); V_KEEP(ay); V_KEEP(ap); V_KEEP(nlive);
       for (int it = 0; it < ti.nstA;) {
         const int lim = min(ti.nstA, it + V_PEEL);
 #pragma unroll 1
         for (; it < lim; ++it) {
-          begin_stage();
-          const bool live = act && (int)el < (it == lastA ? nvA : NB);
-          float4 pl = *reinterpret_cast<const float4*>(rs + poff + 16);   // alpha bl bm
+          if (!ready) { PROF_WAIT(1, mbar_wait_a(full0 + slot * 8u, ph)); }
+          const uint32_t so = slot * slotb;
+          slot2 = slot + 1; ph2 = ph;
+          if (slot2 == (uint32_t)nslot) { slot2 = 0; ph2 ^= 1u; }
+          ready = mbar_test_a(full0 + slot2 * 8u, ph2);
+          const bool live = nlive > (it == lastA ? 1 : 0);
+          float4 pl = lds128(ap + so);   // alpha bl bm
+          const float4 x0 = lds128(ax + so), x1 = lds128(ax + so + 16u), y0 = lds128(ay + so), y1 = lds128(ay + so + 16u);
           pl.x = live ? pl.x : 1.0f; pl.y = live ? pl.y : 0.0f; pl.z = live ? pl.z : 0.0f;
-          float x[8], y[8];
-          ld8(rs + xoff, x);
-          ld8(rs + yoff, y);
+          float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+          float y[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
 #pragma unroll
           for (int i = 0; i < 8; ++i) { x[i] = fmaf(pl.y, x[i], pl.x); y[i] = pl.z * y[i]; }
           v2_tile_aff<DIAG>(x, y, acc);
