@@ -85,6 +85,7 @@ class WorkerPool;
 struct Chunk {
   int64_t c0, c1;   // cell ids [c0, c1)
   int64_t o0, o1;   // its active cells, largest first: order[o0, o1)
+  int idx = 0;           // position in its schedule
   bool packed = false;   // this run sent the chunk's read counts (1 B per entry) instead of ent_ptr (8 B): the kernels of
                          // the chunk start with entptr_kernel
 };
@@ -156,6 +157,7 @@ struct dmx_ctx {
   PinBuf<RescList> r_lists;
   DevBuf<dmx_best_rec> d_best;      // finalise_kernel: records of the cells it could decide ...
   DevBuf<uint8_t> d_flag;           // ... and 1 for the cells left to the host finaliser
+  DevBuf<int32_t> d_any_long;       // per chunk: some re-score list is longer than one pass
   PinBuf<uint8_t> r_flag;
   bool gpu_exact = false;          // device log() verified bit-identical to the host libm
 
@@ -905,7 +907,7 @@ void dmx_destroy(dmx_ctx* c) {
   c->d_dense.release(); c->d_cell_ptr.release(); c->d_ent_ptr.release(); c->d_ent_snp.release();
   c->d_order.release(); c->d_reads.release(); c->d_tt.release(); c->d_parts.release(); c->d_out.release();
   c->d_lists.release(); c->r_lists.release();
-  c->d_best.release(); c->d_flag.release(); c->best.release(); c->r_flag.release();
+  c->d_best.release(); c->d_flag.release(); c->best.release(); c->r_flag.release(); c->d_any_long.release();
   c->o_gp.release(); c->o_cell_ptr.release(); c->o_ent_ptr.release(); c->o_ent_snp.release(); c->o_reads.release();
   c->r_out.release(); c->r_sing.release(); c->r_row0.release(); c->r_l00.release(); c->r_p1.release();
   c->r_p1_0.release(); c->r_dense.release(); c->r_dense2.release(); c->d_dense2.release();
@@ -1032,6 +1034,7 @@ int dmx_set_pileup(dmx_ctx* c, int64_t ncells, const int64_t* cell_ptr, const in
         if (cell >= cb && cell < ce) ord->push_back(cell);
       }
       ck.o1 = (int64_t)ord->size();
+      ck.idx = k;
       chunks->push_back(ck);
       cb = ce;
     }
@@ -1293,6 +1296,7 @@ int enqueue_chunk(dmx_ctx* c, const Chunk& ck, const ScanParams& sp0, bool dev_r
   if (dev_rescore) {
     mp.lists = c->d_lists.p;
     for (int n = 0; n < nA; ++n) mp.mode[n] = c->pg.mode[n];
+    mp.any_long = c->d_any_long.p + ck.idx;
   }
   // read back on the third stream as soon as each array is final (all per-cell arrays are indexed by cell id: one
   // contiguous slice per chunk): the scan's outputs while merge and the re-scorer run, the rest after them
@@ -1323,6 +1327,7 @@ int enqueue_chunk(dmx_ctx* c, const Chunk& ck, const ScanParams& sp0, bool dev_r
     rp.cell_order = sp.cell_order; rp.lists = c->d_lists.p;
     rp.ecode = fp32 ? c->d_ecode.p : nullptr; rp.memo_q = c->d_memo_q.p;
     rp.terms = c->d_terms.p;
+    rp.any_long = c->d_any_long.p + ck.idx;
     CU(launch_rescore(rp, nact, c->stream));
     if (nact) c->st.gpu_launches += 2 * (RMAX / RESC_FAST);
     // the decision logic on the device; the cells it cannot decide (flag 1) go through the host finaliser below
@@ -1403,6 +1408,7 @@ int run_path(dmx_ctx* c, bool pipelined) {
     CU(c->d_terms.reserve((size_t)c->E * RESC_FAST + 1));
     CU(c->d_best.reserve(nc + 1));
     CU(c->d_flag.reserve(nc + 1)); CU(c->r_flag.reserve(nc + 1));
+    CU(c->d_any_long.reserve(64));
   }
   if ((int)c->cev.size() < 7 * K + 4) {
     const size_t old = c->cev.size();
@@ -1434,6 +1440,7 @@ int run_path(dmx_ctx* c, bool pipelined) {
   CU(cudaMemsetAsync(c->d_out.p, 0, (size_t)nc * sizeof(CellOut), c->stream));
   if (dev_rescore) {
     CU(cudaMemsetAsync(c->d_flag.p, 1, (size_t)nc, c->stream));
+    CU(cudaMemsetAsync(c->d_any_long.p, 0, 64 * sizeof(int32_t), c->stream));
     CU(cudaMemsetAsync(c->d_best.p, 0, (size_t)nc * sizeof(dmx_best_rec), c->stream));
   }
   if (pipelined) CU(cudaStreamWaitEvent(c->stream, ev_up[1], 0));

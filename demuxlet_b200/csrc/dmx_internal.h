@@ -181,6 +181,8 @@ struct RescoreParams {
   const int32_t* cell_order;
   RescList* lists;             // [ncells]
   double* terms;               // per cell [RESC_FAST][entries] log(S) terms, cell block at e0 * RESC_FAST
+  const int32_t* any_long;     // != 0: some list of this launch set is longer than RESC_FAST (merge_kernel); the passes
+                               // after the first return at once otherwise
 };
 
 struct MergeParams {
@@ -198,6 +200,7 @@ struct MergeParams {
   double* sing;                // [ncells][nv] out: llksAB[j][0][0]
   CellOut* out;                // [ncells]
   RescList* lists;             // [ncells] or null: exact re-scoring requests
+  int32_t* any_long;           // set when a list is longer than RESC_FAST hypotheses
   uint8_t mode[DMX_MAX_ALPHA]; // PM_* per alpha index
 };
 

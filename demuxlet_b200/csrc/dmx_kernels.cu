@@ -235,6 +235,15 @@ __device__ __forceinline__ void mbar_expect_tx_elect(uint32_t bar, uint32_t byte
       : "memory");
 }
 
+// RN(a / s) given r = RN(1 / s) (__drcp_rn): q = a * r, the residual a - q * s exact in an FMA, q' = q + residual * r --
+// Markstein's correction step, the tail of the hardware's own division sequence.  For normal operands far from the
+// exponent limits; checked bit for bit against __ddiv_rn by tools/pl_div_check.cu (3.5 G + 2^30 quotients, 0 mismatches).
+__device__ __forceinline__ double div_shared(double a, double s, double r) {
+  const double q = __dmul_rn(a, r);
+  const double rem = __fma_rn(-q, s, a);
+  return __fma_rn(rem, r, q);
+}
+
 // peel the binary exponent of a positive double into an integer accumulator; mantissa stays in [1,2)
 __device__ __forceinline__ void peel(double& x, int& esum) {
   int hi = __double2hiint(x);
@@ -548,8 +557,11 @@ __global__ void __launch_bounds__(128) entq1_kernel(const __grid_constant__ Entq
       P[v] = __dmul_rn(P[v], t);
       if (v < nu) mx = fmax(mx, P[v]);
     }
+    {   // :632-639: the quotients by the same maximum from one correctly rounded reciprocal (bit-identical)
+      const double rmx = __drcp_rn(mx);
 #pragma unroll
-    for (int v = 0; v < UMAX; ++v) P[v] = __ddiv_rn(P[v], mx);              // :632-639
+      for (int v = 0; v < UMAX; ++v) P[v] = div_shared(P[v], mx, rmx);
+    }
     // pass-1 GLs, :437-443.  Unlike Q' (which the exact re-scorer consumes bit for bit) the GLs only feed sums of
     // logs that are compared at 1e-4, so the three quotients by the same sum are one reciprocal and three products
     G0 = __dmul_rn(G0, pR);
@@ -564,8 +576,11 @@ __global__ void __launch_bounds__(128) entq1_kernel(const __grid_constant__ Entq
     P[v] = __dadd_rn(P[v], 1e-6);                                           // :643-654
     if (v < nu) mx = fmax(mx, P[v]);
   }
+  {
+    const double rmx = __drcp_rn(mx);
 #pragma unroll
-  for (int v = 0; v < UMAX; ++v) s_val[v][threadIdx.x] = __ddiv_rn(P[v], mx);   // :656-663
+    for (int v = 0; v < UMAX; ++v) s_val[v][threadIdx.x] = div_shared(P[v], mx, rmx);   // :656-663
+  }
   double* out = p.entq + e * p.UQ;
   G0 = __dadd_rn(G0, 1e-6);                                                  // :446-452
   G1 = __dadd_rn(G1, 1e-6);
@@ -2457,6 +2472,7 @@ __global__ void merge_kernel(const __grid_constant__ MergeParams p, int64_t nact
         }
     }
     L->n = (over || n > RMAX) ? -1 : n;
+    if (n > RESC_FAST && n <= RMAX && !over && p.any_long) *p.any_long = 1;   // (benign race: everybody writes 1)
   }
 }
 
@@ -2660,8 +2676,26 @@ __device__ __forceinline__ double exact_term(const float* __restrict__ g, const 
   return glibc_log_fma(s);
 }
 
+template <int HM>
+__device__ __forceinline__ void rescore_terms_cell(const RescoreParams& p, const uint32_t (&hyp)[RESC_FAST], int H, int64_t e0,
+                                                   int64_t n, double* __restrict__ out) {
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const int64_t e = e0 + i;
+    const float* g = p.gp + (int64_t)__ldg(p.ent_snp + e) * p.gp_stride;
+    const double* q = p.entq + e * p.UQ;
+    if (p.ecode) {
+      const uint32_t code = __ldg(p.ecode + e);
+      if (code != 0xffffu) q = p.memo_q + (int64_t)code * p.UQ;
+    }
+#pragma unroll
+    for (int h = 0; h < HM; ++h)
+      if (h < H) out[h * n + i] = exact_term(g, q, hyp[h], p.dense_idx);
+  }
+}
+
 __global__ void __launch_bounds__(256) rescore_terms_kernel(const __grid_constant__ RescoreParams p, int64_t nactive,
                                                             int pass) {
+  if (pass > 0 && p.any_long && !*p.any_long) return;        // no list of this launch set needs a further pass
   for (int64_t aidx = blockIdx.x; aidx < nactive; aidx += gridDim.x) {
     const int cell = p.cell_order[aidx];
     const RescList* L = p.lists + cell;
@@ -2672,18 +2706,9 @@ __global__ void __launch_bounds__(256) rescore_terms_kernel(const __grid_constan
     for (int h = 0; h < RESC_FAST; ++h) hyp[h] = h < H ? L->hyp[pass * RESC_FAST + h] : 0u;
     const int64_t e0 = p.cell_ptr[cell], n = p.cell_ptr[cell + 1] - e0;
     double* out = p.terms + e0 * RESC_FAST;                  // this cell's block: [h][entry]
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-      const int64_t e = e0 + i;
-      const float* g = p.gp + (int64_t)__ldg(p.ent_snp + e) * p.gp_stride;
-      const double* q = p.entq + e * p.UQ;
-      if (p.ecode) {
-        const uint32_t code = __ldg(p.ecode + e);
-        if (code != 0xffffu) q = p.memo_q + (int64_t)code * p.UQ;
-      }
-#pragma unroll
-      for (int h = 0; h < RESC_FAST; ++h)
-        if (h < H) out[h * n + i] = exact_term(g, q, hyp[h], p.dense_idx);
-    }
+    // the common list is the two orders of the best pair: a body with two hypotheses inlined instead of eight
+    if (H <= 2) rescore_terms_cell<2>(p, hyp, H, e0, n, out);
+    else rescore_terms_cell<RESC_FAST>(p, hyp, H, e0, n, out);
   }
 }
 
@@ -2695,6 +2720,7 @@ __global__ void __launch_bounds__(128) rescore_sum_kernel(const __grid_constant_
                                                           int pass) {
   __shared__ double buf[4][RESC_FAST][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (pass > 0 && p.any_long && !*p.any_long) return;
   const int64_t aidx = (int64_t)blockIdx.x * 4 + w;
   if (aidx >= nactive) return;
   const int cell = p.cell_order[aidx];

@@ -117,6 +117,19 @@ constexpr uint32_t V_ARR = DMX_ARRIVE_ALL ? 32u : 1u;   // arrivals per warp
 __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// bulk copy of streamed data (the entry records: read once per launch) with an L2 evict-first policy, so that the
+// stream does not push the table rows the gathers re-use out of the 126 MB L2
+__device__ __forceinline__ void bulk_g2s_stream_elect(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
+                                                      uint64_t policy) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n\t}" ::
+          "r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+
 // A loader runs ten stages ahead of the consumers, so its ring slot is practically never free when it first looks.
 // nanosleep returns within tens of cycles here, and every poll costs issue slots of the SM sub-partition the loader
 // shares with two consumer warps; a dependent uncached load parks the warp on the scoreboard for an L2 round trip
@@ -222,6 +235,8 @@ __device__ __forceinline__ void v2_loader(const ScanParams& p, const ScanMaps& t
   const uint32_t nslot = (uint32_t)p.v_nslot, slotb = (uint32_t)p.v_slot;
   uint32_t gbase = 0;
   unsigned sink = 0;
+  uint64_t pol_stream;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
   TaskInfoF ti;
   PROF_DECL
   for (int r = 0; next_task_f32(p, r, u, NS, &ti); ++r) {
@@ -274,8 +289,8 @@ __device__ __forceinline__ void v2_loader(const ScanParams& p, const ScanMaps& t
         }
       }
       // entry slots beyond the stage's last entry read the records that follow (the tables have NB records of slack)
-      bulk_g2s_elect(rs + V_OFF_HEAD, p.entf_head + eb * FHEAD, NB * FHEAD * 4, bar);
-      bulk_g2s_elect(rs + V_OFF_PLANE, fplane + eb * FPLANE, NB * FPLANE * 4, bar);
+      bulk_g2s_stream_elect(rs + V_OFF_HEAD, p.entf_head + eb * FHEAD, NB * FHEAD * 4, bar, pol_stream);
+      bulk_g2s_stream_elect(rs + V_OFF_PLANE, fplane + eb * FPLANE, NB * FPLANE * 4, bar, pol_stream);
     }
     gbase += (uint32_t)ti.nst;
   }
