@@ -1021,7 +1021,7 @@ int dmx_set_pileup(dmx_ctx* c, int64_t ncells, const int64_t* cell_ptr, const in
       // a small first chunk lets the kernels start early (two chunks by default: 14 % / 86 % of the entries)
       // two chunks: the first one's kernels should end about when the second one's copies do -- sooner when the offsets
       // travel as one-byte read counts (pack_chunk; an entry of a droplet pileup has a handful of reads)
-      double f2 = (R <= 8 * E) ? 0.14 : 0.24;
+      double f2 = (R <= 8 * E && E >= (4 << 20)) ? 0.14 : 0.24;
       if (const char* ef = getenv("DMX_CHUNK_F0")) f2 = std::min(0.9, std::max(0.02, atof(ef)));
       const double frac = nk == 3 ? (k == 0 ? 0.15 : 0.70) : (nk == 2 ? f2 : (double)(k + 1) / nk);
       if (k == nk - 1) ce = ncells;
@@ -1104,7 +1104,11 @@ int upload_common(dmx_ctx* c, cudaStream_t st, int64_t* bytes, const std::vector
 // Returns false (chunk goes unpacked) when an entry has more than 255 reads.
 bool pack_chunk(dmx_ctx* c, const Chunk& ck) {
   const int64_t e0 = c->h_cell_ptr[ck.c0], e1 = c->h_cell_ptr[ck.c1];
-  if (e1 - e0 < (1 << 16) || getenv("DMX_NO_PTR_PACK")) return false;
+  // worth it when the copies saved (7 bytes per entry over PCIe) outweigh the host pass, and when there is a GP upload to
+  // hide that pass under: large pileups only (C3: 11.3 M entries; C2's 2.3 M are faster unpacked)
+  int64_t min_entries = 4 << 20;
+  if (const char* em = getenv("DMX_PTR_PACK_MIN")) min_entries = atoll(em);
+  if (c->E < min_entries || e1 - e0 < (1 << 16) || getenv("DMX_NO_PTR_PACK")) return false;
   if (c->h_cnt.reserve((size_t)c->E + 1) != cudaSuccess || c->h_cell_r.reserve((size_t)c->ncells + 2) != cudaSuccess ||
       c->d_cnt.reserve((size_t)c->E + 1) != cudaSuccess || c->d_cell_r.reserve((size_t)c->ncells + 2) != cudaSuccess)
     return false;

@@ -224,3 +224,45 @@ def test_reference_side_binding(name, m, tmp_path):
     diff_tsv(gold + ".best", tmp_path / "b.best", BEST_EXACT)
     for ext in ("single", "sing2", "pair"):
         diff_tsv(gold + "." + ext, tmp_path / ("b." + ext), ROW_EXACT)
+
+
+def test_packed_offsets_upload(monkeypatch):
+    """dmx_run sends one-byte read counts instead of ent_ptr and rebuilds the offsets on the device (pack_chunk /
+    entptr_kernel): same records as the plain upload, as dmx_upload + dmx_compute (never packed), and a pileup with an
+    entry of more than 255 reads (which cannot be packed) still runs"""
+    from demuxlet_b200.api import Demuxlet
+    from demuxlet_b200.synth import make_synth
+    p = make_synth(700, 8, 20000, "GP", seed=91)
+    assert p.n_entries > (1 << 16)                     # large enough for the packed path ...
+    monkeypatch.setenv("DMX_PTR_PACK_MIN", "1")        # ... once the "large pileups only" rule is out of the way
+    d = Demuxlet(p.nv, (0.0, 0.5))
+    d.set_pileup(p)
+    d.run()
+    a = d.best().copy()
+    assert d.stats()["h2d_bytes"] < p.gp.nbytes + p.n_entries * 8     # the 8-byte offsets did not travel
+    d.upload()
+    d.compute()
+    assert d.best().tobytes() == a.tobytes()
+    monkeypatch.setenv("DMX_NO_PTR_PACK", "1")
+    e = Demuxlet(p.nv, (0.0, 0.5))
+    e.set_pileup(p)
+    e.run()
+    monkeypatch.delenv("DMX_NO_PTR_PACK")
+    assert e.best().tobytes() == a.tobytes()
+    assert e.stats()["h2d_bytes"] > p.gp.nbytes + p.n_entries * 8
+    # one entry with 300 reads: its count does not fit a byte, the chunk goes unpacked
+    k = int(p.ent_ptr[5])
+    reads = np.concatenate([p.reads[:k], np.full(300, (1 << 8) | 30, np.uint16), p.reads[k:]])
+    ent_ptr = p.ent_ptr.copy()
+    ent_ptr[6:] += 300
+    f = Demuxlet(p.nv, (0.0, 0.5))
+    f.set_gp(p.gp)
+    f.set_pileup_arrays(p.cell_ptr, p.ent_snp, ent_ptr, reads, p.totl, p.npass, p.uniq)
+    f.run()
+    g = Demuxlet(p.nv, (0.0, 0.5))
+    g.set_gp(p.gp)
+    g.set_pileup_arrays(p.cell_ptr, p.ent_snp, ent_ptr, reads, p.totl, p.npass, p.uniq)
+    g.upload()
+    g.compute()
+    assert f.best().tobytes() == g.best().tobytes()
+    assert not np.array_equal(f.best()["llk12"][:1], a["llk12"][:1])     # the extra reads changed barcode 0
