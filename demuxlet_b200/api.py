@@ -255,10 +255,11 @@ class DmxSweepOpts(C.Structure):
 
 
 def sweep_bam(path: str, chroms: Sequence[str], snp_rid, snp_pos, snp_ref, snp_alt, groups: Optional[Sequence[str]] = None,
-              **opts) -> dict:
+              raw_umis: bool = False, **opts) -> dict:
     """dmx_sweep_bam: the reference's BAM sweep (/root/reference/cmd_cram_demuxlet.cpp:186-338) as flat arrays: one
     (cell, snp, umi, allele, bq) per add_read call in call order, barcodes in add_cell order, RD.TOTL.
-    opts: tag_group, tag_umi, min_mq, exclude_flag, min_bq, cap_bq, min_td."""
+    opts: tag_group, tag_umi, min_mq, exclude_flag, min_bq, cap_bq, min_td.  raw_umis: "umis" as the (uint8 buffer,
+    int64 offsets) pair pack_reads takes instead of a list of strings (no per-read python object)."""
     lib = load_library()
     lib.dmx_sweep_opts_default.argtypes = [C.POINTER(DmxSweepOpts)]
     lib.dmx_sweep_opts_default.restype = None
@@ -303,7 +304,7 @@ def sweep_bam(path: str, chroms: Sequence[str], snp_rid, snp_pos, snp_ref, snp_a
         raw = umi_buf.tobytes()
         return {"barcodes": [lib.dmx_sweep_barcode(h, i).decode() for i in range(nc)], "totl": totl, "cell": cell,
                 "snp": snp, "allele": allele, "bq": bq,
-                "umis": [raw[umi_off[i]:umi_off[i + 1]].decode() for i in range(nr)],
+                "umis": (umi_buf, umi_off) if raw_umis else [raw[umi_off[i]:umi_off[i + 1]].decode() for i in range(nr)],
                 "counts": dict(zip(("records", "filtered", "off_vcf", "skip_bcd"), [c.value for c in cnt]))}
     finally:
         lib.dmx_sweep_free(h)

@@ -12,22 +12,47 @@
 // flat arrays dmx_pack_reads takes (the packer reproduces add_read's first-seen semantics), the barcodes in first-seen
 // order (add_cell, sc_drop_seq.cpp:21-32) and cell_totl_reads.
 //
-// The SNP buffer of the reference (clear_buffer_before / read-ahead, :197-232) only bounds which SNPs are *tested*; a SNP
-// outside the aligned span yields no base, so testing exactly the SNPs with read start <= pos < read end on the read's
-// chromosome, in VCF order, gives the same tuples.  BAM decoding (BGZF = a series of gzip members, which zlib's gzread
-// walks through; record layout of the SAM specification section 4.2) replaces htslib's sam_read1 / bam_aux_get.
-// Not handled: CRAM, SAM text.  --tag-UMI "" reproduces the reference's unseeded rand() UMIs.  Parity: the checker is
-// the python restatement in tests/bamio.py on generated BAM files -- "parity unpinned" against htslib itself.
+// Which SNPs a read is tested against is the reference's SNP buffer, restated exactly (:197-232, :306-308,
+// bcf_filtered_reader.cpp:649-669): before a read is tested the buffer drops its leading SNPs that lie on an earlier
+// chromosome or more than one base before the read start, then reads ahead until the newest SNP is at or behind the
+// read end (or on a later chromosome); the read is tested against everything buffered BY POSITION ALONE.  For a read
+// whose CIGAR accounts for all its bases with M / S / I that is the SNPs under its aligned span -- plus, rarely, a
+// SNP of another chromosome that sits in the buffer at the same coordinate (the look-ahead SNP of the next chromosome,
+// or the tail of the previous one right after a chromosome change); for a read with '=' / 'X' operations (which the
+// reference's walk ignores) every buffered SNP outside its M / D / N segments yields the base at the offset where the
+// walk ended.  Both are reproduced: the buffer state [s, hi] is a pair of running maxima over the reads in file order.
+//
+// Execution: the file is mapped, BGZF blocks (gzip members of <= 64 KB with the 'BC' extra field, SAM spec 4.1) are
+// inflated on all host threads one batch ahead, and the records of a batch are walked on all host threads in contiguous
+// chunks.  A chunk is walked under the assumption that only the SNPs under the aligned span can give a base; a cheap
+// serial pass then runs the buffer recurrence over the chunk's reads and, where a read could see more than that (the
+// cases above), the chunk is walked again with the exact buffer state.  Barcode ids are assigned per chunk and merged in
+// file order, so that ids, tuples and counts do not depend on the number of threads.  Any other gzip file (or a plain
+// one) is read through zlib's gzread and walked the same way.
+// Not handled: CRAM, SAM text.  --tag-UMI "" reproduces the reference's unseeded rand() UMIs (one walking
+// thread).  The BAM must be coordinate-sorted, as for the reference.  Parity: the checker is the python restatement in
+// tests/bamio.py (a literal transcription of the buffer loop) on generated BAM files; the CIGAR look-up is pinned on
+// the reference's own function (oracle/ref_cigar) -- BGZF / BAM decoding itself is "parity unpinned" against htslib.
+#include <fcntl.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
 #include <atomic>
+#include <deque>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <future>
+#include <memory>
 #include <string>
+#include <string_view>
 #include <thread>
 #include <unordered_map>
 #include <unordered_set>
@@ -49,151 +74,222 @@ namespace {
 
 thread_local std::string g_bam_error;
 
-// Byte stream over a BAM file.  A BGZF file (gzip members of <= 64 KB with the 'BC' extra field that gives each
-// block's compressed size, SAM spec 4.1) is inflated block-parallel: the compressed file is indexed by walking the block
-// headers, batches of blocks are inflated on the host threads into one buffer at their prefix-sum offsets (one batch
-// ahead of the record walk), and the records are then read in file order -- htslib's bgzf_mt idea.  Any other gzip file
-// (or a plain one) goes through zlib's gzread.
+int env_threads() {
+  int n = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) n = std::max(1, std::min(n, CPU_COUNT(&set)));
+  if (const char* env = getenv("DMX_BAM_THREADS")) n = std::max(1, std::min(atoi(env), 256));
+  return n;
+}
+
+// Host threads that live as long as one sweep: run(nt, f) calls f(t) for t in [0, nt), t = 0 on the calling thread.
+class Pool {
+ public:
+  explicit Pool(int n) : n_(std::max(1, n)) {
+    for (int t = 1; t < n_; ++t) th_.emplace_back([this, t]() { loop(t); });
+  }
+  ~Pool() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+      ++gen_;
+    }
+    cv_.notify_all();
+    for (auto& x : th_) x.join();
+  }
+  int size() const { return n_; }
+  void run(int nt, const std::function<void(int)>& f) {
+    nt = std::min(nt, n_);
+    if (nt <= 1) { f(0); return; }
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      fn_ = &f;
+      nt_ = nt;
+      pending_ = nt - 1;
+      ++gen_;
+    }
+    cv_.notify_all();
+    f(0);
+    std::unique_lock<std::mutex> lk(m_);
+    done_.wait(lk, [this]() { return pending_ == 0; });
+  }
+
+ private:
+  void loop(int t) {
+    uint64_t seen = 0;
+    std::unique_lock<std::mutex> lk(m_);
+    for (;;) {
+      cv_.wait(lk, [&]() { return gen_ != seen; });
+      seen = gen_;
+      if (stop_) return;
+      if (t >= nt_) continue;
+      const std::function<void(int)>* f = fn_;
+      lk.unlock();
+      (*f)(t);
+      lk.lock();
+      if (--pending_ == 0) done_.notify_one();
+    }
+  }
+  int n_, nt_ = 0, pending_ = 0;
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+  const std::function<void(int)>* fn_ = nullptr;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  std::vector<std::thread> th_;
+};
+
+// Decoded BAM bytes as a sliding window.  more(keep_from) drops the bytes before keep_from, appends the next batch and
+// returns false when there is nothing left (the window then holds only the kept tail).
 class ByteStream {
  public:
   ~ByteStream() {
     if (next_.valid()) next_.wait();
     if (gz_) gzclose(gz_);
+    if (map_ && map_ != MAP_FAILED) munmap((void*)map_, map_size_);
   }
-  bool open(const char* path) {
-    FILE* f = fopen(path, "rb");
-    if (!f) return false;
+  bool open(const char* path, int nth) {
+    pool_.reset(new Pool(nth));
+    const int fd = ::open(path, O_RDONLY);
+    if (fd < 0) return false;
     uint8_t h[18];
-    const size_t got = fread(h, 1, 18, f);
+    const ssize_t got = pread(fd, h, 18, 0);
     const bool bgzf = got == 18 && h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && (h[3] & 4) && h[10] == 6 && h[11] == 0 &&
                       h[12] == 'B' && h[13] == 'C' && h[14] == 2 && h[15] == 0;
-    if (!bgzf) {
-      fclose(f);
+    struct stat st;
+    if (!bgzf || fstat(fd, &st) != 0 || st.st_size <= 0) {
+      ::close(fd);
       gz_ = gzopen(path, "rb");
       if (gz_) gzbuffer(gz_, 1 << 20);
       return gz_ != nullptr;
     }
-    fseek(f, 0, SEEK_END);
-    const long sz = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    comp_.resize((size_t)std::max(0L, sz));
-    const bool ok = fread(comp_.data(), 1, comp_.size(), f) == comp_.size();
-    fclose(f);
-    if (!ok) return false;
-    // index: every block starts with the 18-byte header checked above; BSIZE = total block size - 1
-    for (size_t off = 0; off + 28 <= comp_.size();) {
-      const uint8_t* b = comp_.data() + off;
-      if (!(b[0] == 0x1f && b[1] == 0x8b && b[12] == 'B' && b[13] == 'C')) { bad_ = true; break; }
-      const size_t bsize = (size_t)(b[16] | (b[17] << 8)) + 1;
-      if (bsize < 26 || off + bsize > comp_.size()) { bad_ = true; break; }
-      uint32_t isize;
-      memcpy(&isize, b + bsize - 4, 4);
-      blocks_.push_back(Blk{off, bsize, isize});
-      off += bsize;
-    }
-    nth_ = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    if (const char* env = getenv("DMX_BAM_THREADS")) nth_ = std::max(1, std::min(atoi(env), 256));
+    map_size_ = (size_t)st.st_size;
+    map_ = (const uint8_t*)mmap(nullptr, map_size_, PROT_READ, MAP_PRIVATE, fd, 0);
+    ::close(fd);
+    if (map_ == MAP_FAILED) { map_ = nullptr; return false; }
+    madvise((void*)map_, map_size_, MADV_SEQUENTIAL);
     parallel_ = true;
     schedule();
     return true;
   }
-  int threads() const { return parallel_ ? nth_ : 1; }
-  // n bytes or fail; read_some-style EOF probe through `at_eof`
-  bool read(void* dst, size_t n) {
+  const uint8_t* data() const { return win_.data() + beg_; }
+  size_t size() const { return win_.size() - beg_; }
+  bool bad() const { return bad_; }
+  // share of the compressed file whose bytes have been handed out or are being inflated (0: unknown)
+  double decoded_share() const { return map_size_ ? (double)sched_off_ / (double)map_size_ : 0.0; }
+  bool more(size_t keep_from) {
+    const size_t keep = size() - keep_from;
+    static const uint8_t kNone = 0;
+    const uint8_t* tail = keep ? data() + keep_from : &kNone;
     if (!parallel_) {
-      char* p = (char*)dst;
-      while (n) {
-        const int k = gzread(gz_, p, (unsigned)std::min<size_t>(n, 1u << 30));
-        if (k <= 0) return false;
-        p += k;
-        n -= (size_t)k;
+      if (gz_eof_) { memmove(win_.data(), tail, keep); win_.resize(keep); beg_ = 0; return false; }
+      std::vector<uint8_t> nw(keep + kGzChunk);
+      memcpy(nw.data(), tail, keep);
+      size_t got = 0;
+      while (got < kGzChunk) {
+        const int k = gzread(gz_, nw.data() + keep + got, (unsigned)(kGzChunk - got));
+        if (k < 0) { bad_ = true; break; }
+        if (k == 0) { gz_eof_ = true; break; }
+        got += (size_t)k;
       }
-      return true;
+      nw.resize(keep + got);
+      win_.swap(nw);
+      beg_ = 0;
+      return got > 0 && !bad_;
     }
-    char* p = (char*)dst;
-    while (n) {
-      if (pos_ == cur_.size() && !advance()) return false;
-      const size_t k = std::min(n, cur_.size() - pos_);
-      memcpy(p, cur_.data() + pos_, k);
-      pos_ += k;
-      p += k;
-      n -= k;
+    for (;;) {
+      if (!next_.valid()) { memmove(win_.data(), tail, keep); win_.resize(keep); beg_ = 0; return false; }
+      if (!next_.get()) { bad_ = true; return false; }
+      // ahead_ was inflated behind kSlack spare bytes: the kept tail goes in front of it without moving the batch
+      if (keep <= kSlack) {
+        memcpy(ahead_.data() + kSlack - keep, tail, keep);
+        win_.swap(ahead_);
+        beg_ = kSlack - keep;
+      } else {
+        std::vector<uint8_t> nw(keep + ahead_.size() - kSlack);
+        memcpy(nw.data(), tail, keep);
+        memcpy(nw.data() + keep, ahead_.data() + kSlack, ahead_.size() - kSlack);
+        win_.swap(nw);
+        beg_ = 0;
+      }
+      const bool grew = size() > keep;
+      schedule();
+      if (grew) return true;
+      // a batch of empty blocks (the end-of-file marker): keep going
+      return more(0);
     }
-    return true;
-  }
-  // 1: four bytes read, 0: clean end of file, -1: truncated
-  int read4(uint8_t* dst) {
-    if (!parallel_) {
-      const int k = gzread(gz_, dst, 4);
-      return k == 4 ? 1 : (k == 0 ? 0 : -1);
-    }
-    if (pos_ == cur_.size() && !advance()) return bad_ ? -1 : 0;
-    if (cur_.size() - pos_ >= 4) {
-      memcpy(dst, cur_.data() + pos_, 4);
-      pos_ += 4;
-      return 1;
-    }
-    return read(dst, 4) ? 1 : -1;
   }
 
  private:
   struct Blk { size_t off, size; uint32_t isize; };
-  static constexpr size_t kBatch = 1024;    // blocks per batch (<= 64 MB of BAM)
-  bool inflate_batch(size_t b0, size_t b1, std::vector<uint8_t>* out) {
-    std::vector<size_t> at(b1 - b0 + 1, 0);
-    for (size_t i = b0; i < b1; ++i) at[i - b0 + 1] = at[i - b0] + blocks_[i].isize;
+  static constexpr size_t kBatch = 256;         // blocks per batch (<= 16 MB of BAM)
+  static constexpr size_t kSlack = 1 << 16;     // room in front of a batch for the unconsumed tail of the last one
+  static constexpr size_t kGzChunk = 32u << 20;
+  // every block starts with the 18-byte header checked in open(); BSIZE = total block size - 1
+  bool index_batch(std::vector<Blk>* blocks) {
+    while (blocks->size() < kBatch && file_off_ < map_size_) {
+      if (file_off_ + 28 > map_size_) return false;
+      const uint8_t* b = map_ + file_off_;
+      if (!(b[0] == 0x1f && b[1] == 0x8b && b[12] == 'B' && b[13] == 'C')) return false;
+      const size_t bsize = (size_t)(b[16] | (b[17] << 8)) + 1;
+      if (bsize < 26 || file_off_ + bsize > map_size_) return false;
+      uint32_t isize;
+      memcpy(&isize, b + bsize - 4, 4);
+      blocks->push_back(Blk{file_off_, bsize, isize});
+      file_off_ += bsize;
+    }
+    return true;
+  }
+  bool inflate_batch(const std::vector<Blk>& blocks, std::vector<uint8_t>* out) {
+    const size_t nb = blocks.size();
+    std::vector<size_t> at(nb + 1, kSlack);
+    for (size_t i = 0; i < nb; ++i) at[i + 1] = at[i] + blocks[i].isize;
     out->resize(at.back());
-    std::atomic<size_t> nextb{b0};
+    std::atomic<size_t> nextb{0};
     std::atomic<bool> ok{true};
-    auto work = [&]() {
+    auto work = [&](int) {
       z_stream zs;
+      memset(&zs, 0, sizeof(zs));
+      if (inflateInit2(&zs, -15) != Z_OK) { ok = false; return; }
       for (;;) {
         const size_t i = nextb.fetch_add(1);
-        if (i >= b1) break;
-        const Blk& bl = blocks_[i];
+        if (i >= nb) break;
+        const Blk& bl = blocks[i];
         if (bl.isize == 0) continue;
-        memset(&zs, 0, sizeof(zs));
-        if (inflateInit2(&zs, -15) != Z_OK) { ok = false; break; }
-        zs.next_in = comp_.data() + bl.off + 18;
+        inflateReset(&zs);
+        zs.next_in = const_cast<Bytef*>(map_ + bl.off + 18);
         zs.avail_in = (uInt)(bl.size - 26);
-        zs.next_out = out->data() + at[i - b0];
+        zs.next_out = out->data() + at[i];
         zs.avail_out = bl.isize;
         const int rc = inflate(&zs, Z_FINISH);
-        inflateEnd(&zs);
         uint32_t crc;
-        memcpy(&crc, comp_.data() + bl.off + bl.size - 8, 4);
+        memcpy(&crc, map_ + bl.off + bl.size - 8, 4);
         if (rc != Z_STREAM_END || zs.avail_out != 0 ||
-            (uint32_t)crc32(crc32(0L, Z_NULL, 0), out->data() + at[i - b0], bl.isize) != crc)
+            (uint32_t)crc32(crc32(0L, Z_NULL, 0), out->data() + at[i], bl.isize) != crc)
           ok = false;
       }
+      inflateEnd(&zs);
     };
-    const int nt = (int)std::min<size_t>((size_t)nth_, b1 - b0);
-    std::vector<std::thread> th;
-    for (int t = 1; t < nt; ++t) th.emplace_back(work);
-    work();
-    for (auto& x : th) x.join();
+    pool_->run((int)std::min<size_t>((size_t)pool_->size(), std::max<size_t>(nb, 1)), work);
     return ok;
   }
   void schedule() {      // start inflating the next batch in the background
-    if (next_blk_ >= blocks_.size()) return;
-    const size_t b0 = next_blk_, b1 = std::min(blocks_.size(), b0 + kBatch);
-    next_blk_ = b1;
-    next_ = std::async(std::launch::async, [this, b0, b1]() { return inflate_batch(b0, b1, &ahead_); });
-  }
-  bool advance() {       // the batch that was inflated ahead becomes the current one
-    if (!next_.valid()) return false;
-    if (!next_.get()) { bad_ = true; return false; }
-    cur_.swap(ahead_);
-    pos_ = 0;
-    schedule();
-    return !cur_.empty() || advance();
+    sched_off_ = file_off_;
+    if (file_off_ >= map_size_ || index_bad_) return;
+    next_ = std::async(std::launch::async, [this]() {
+      std::vector<Blk> blocks;
+      blocks.reserve(kBatch);
+      if (!index_batch(&blocks)) { index_bad_ = true; return false; }
+      return inflate_batch(blocks, &ahead_);
+    });
   }
   gzFile gz_ = nullptr;
-  bool parallel_ = false, bad_ = false;
-  int nth_ = 1;
-  std::vector<uint8_t> comp_, cur_, ahead_;
-  std::vector<Blk> blocks_;
-  size_t next_blk_ = 0, pos_ = 0;
+  bool parallel_ = false, bad_ = false, gz_eof_ = false, index_bad_ = false;
+  std::unique_ptr<Pool> pool_;
+  const uint8_t* map_ = nullptr;
+  size_t map_size_ = 0, file_off_ = 0, sched_off_ = 0;
+  std::vector<uint8_t> win_, ahead_;
+  size_t beg_ = 0;
   std::future<bool> next_;
 };
 
@@ -236,6 +332,199 @@ const char* aux_get_z(const uint8_t* p, const uint8_t* e, const char* tag) {
   return nullptr;
 }
 
+// The SNP list and the options one sweep works with.
+struct Sweep {
+  const dmx_sweep_opts* o;
+  int64_t nsnps;
+  const int32_t *snp_rid, *snp_pos;
+  const char *snp_ref, *snp_alt;
+  int32_t n_ref;
+  std::vector<int32_t> tid2rid;
+  std::vector<int64_t> rid_end;                         // rid -> index behind the last SNP with that or a smaller rid
+  std::unordered_set<std::string_view> groups;
+  bool use_group, random_umi;
+  // first SNP index i >= from with (rid, pos)[i] >= (c, p); the SNPs are sorted, reads mostly too: gallop, then bisect
+  int64_t lower(int32_t c, int64_t p, int64_t from) const {
+    auto less = [&](int64_t i) { return snp_rid[i] < c || (snp_rid[i] == c && (int64_t)snp_pos[i] < p); };
+    if (from < 0 || from > nsnps || (from > 0 && !less(from - 1))) from = 0;
+    int64_t lo = from, step = 1;
+    while (lo + step <= nsnps && less(lo + step - 1)) { lo += step; step <<= 1; }
+    int64_t hi = std::min(nsnps, lo + step);           // answer in [lo, hi]
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (less(mid)) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+  }
+};
+
+// The reference's SNP buffer = SNPs [s, hi] (empty when s == hi + 1); cmd_cram_demuxlet.cpp:150,:202-237
+struct BufState { int64_t s, hi; };
+
+// What the buffer recurrence needs to know of one read that reached :202
+struct ReadKey {
+  int32_t c, pos;
+  int64_t endpos, lo, la;     // lo: first SNP not cleared by clear_buffer_before; la: where the read-ahead stops
+  bool plain;                 // M + S + I cover the read: no base outside [pos, endpos)
+};
+
+inline void advance_buffer(const Sweep& S, const ReadKey& k, BufState* b) {
+  b->s = std::max(b->s, std::min(k.lo, b->hi + 1));          // bcf_filtered_reader.cpp:660-667
+  b->hi = std::max(b->hi, std::min(k.la, S.nsnps - 1));      // :209-237 (vr.read() fails at the end: nothing is added)
+}
+
+// True when read k, tested against the buffer b (already advanced), can see a SNP outside the ones under its aligned
+// span on its own chromosome: then the fast walk of its chunk is not the reference's.
+inline bool needs_exact(const Sweep& S, const ReadKey& k, const BufState& b) {
+  if (!k.plain) return true;
+  for (int64_t i = b.s; i <= b.hi && i < k.lo && S.snp_rid[i] < k.c; ++i)       // tail of earlier chromosomes
+    if (S.snp_pos[i] >= k.pos && S.snp_pos[i] < k.endpos) return true;
+  const int64_t x = S.rid_end[(size_t)k.c];                                     // look-ahead SNP of a later chromosome
+  return x < S.nsnps && x <= b.hi && S.snp_pos[x] >= k.pos && S.snp_pos[x] < k.endpos;
+}
+
+struct ChunkOut {
+  std::vector<int32_t> lcell, snp;         // tuples with chunk-local barcode ids
+  std::vector<uint8_t> allele, bq;
+  std::vector<char> umi;
+  std::vector<int64_t> umi_end;
+  std::vector<std::string_view> bcs;       // chunk-local barcode id -> string (inside the window)
+  std::vector<int32_t> bc_totl;
+  std::vector<ReadKey> keys;
+  std::unordered_map<std::string_view, int32_t> bc_map;
+  int64_t n_filtered = 0, n_off_vcf = 0, n_skip_bcd = 0;
+  bool corrupt = false;
+  void clear() {
+    lcell.clear(); snp.clear(); allele.clear(); bq.clear(); umi.clear(); umi_end.clear();
+    bcs.clear(); bc_totl.clear(); keys.clear(); bc_map.clear();
+    n_filtered = n_off_vcf = n_skip_bcd = 0;
+    corrupt = false;
+  }
+};
+
+// Walks records [r0, r1) of the window.  exact == nullptr: every read is tested against the SNPs under its aligned
+// span (and its ReadKey is recorded); otherwise against the reference's buffer, whose state *exact carries along.
+void walk_chunk(const Sweep& S, const uint8_t* win, const size_t* offs, size_t r0, size_t r1, BufState* exact,
+                struct random_data* rnd, ChunkOut* out) {
+  static const char kBase[] = "=ACMGRSVTWYHKDBN";
+  const dmx_sweep_opts* o = S.o;
+  out->clear();
+  int64_t hint_lo = 0;
+  for (size_t r = r0; r < r1; ++r) {
+    const uint8_t* b = win + offs[r] + 4;
+    const int32_t block = rd_i32(b - 4);
+    const int32_t tid = rd_i32(b), pos = rd_i32(b + 4);
+    const uint32_t l_name = b[8], mapq = b[9], n_cigar = rd_u16(b + 12), flag = rd_u16(b + 14);
+    const int32_t l_seq = rd_i32(b + 16);
+    const uint8_t* cigar = b + 32 + l_name;
+    const uint8_t* seq = cigar + 4 * (size_t)n_cigar;
+    const uint8_t* qual = seq + ((size_t)std::max(l_seq, 0) + 1) / 2;
+    const uint8_t* aux = qual + (size_t)std::max(l_seq, 0);
+    const uint8_t* end = b + block;
+    if (l_seq < 0 || aux > end) { out->corrupt = true; return; }
+    // sam_filtered_reader.cpp:284-296
+    if ((int32_t)mapq < o->min_mq || (o->exclude_flag & flag)) { ++out->n_filtered; continue; }
+    const int32_t rid = (tid >= 0 && tid < S.n_ref) ? S.tid2rid[(size_t)tid] : -1;
+    if (rid < 0) { ++out->n_off_vcf; continue; }                                      // :197-200
+    // bam_endpos: start + reference span of the CIGAR (M, D, N, =, X), at least one base
+    int64_t span = 0, covered = 0;
+    for (uint32_t c = 0; c < n_cigar; ++c) {
+      const uint32_t v = rd_u32(cigar + 4 * c), op = v & 15u;
+      if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += v >> 4;
+      if (op == 0 || op == 1 || op == 4) covered += v >> 4;
+    }
+    ReadKey k;
+    k.c = rid;
+    k.pos = pos;
+    k.endpos = (int64_t)pos + (span > 0 ? span : 1);
+    k.plain = n_cigar == 0 || covered >= l_seq;
+    k.lo = hint_lo = S.lower(rid, (int64_t)pos - 1, hint_lo);
+    k.la = S.lower(rid, k.endpos, k.lo);
+    int64_t i0, i1;              // SNPs to test: [i0, i1)
+    if (exact) {
+      advance_buffer(S, k, exact);                                                   // :202-237
+      i0 = exact->s;
+      i1 = exact->hi + 1;
+    } else {
+      out->keys.push_back(k);
+      i0 = k.lo;
+      i1 = k.la;
+    }
+    // barcode (:239-268)
+    std::string_view sbcd(".");
+    if (S.use_group) {
+      const char* z = aux_get_z(aux, end, o->tag_group);
+      if (z) sbcd = std::string_view(z);
+      if (!S.groups.empty() && S.groups.find(sbcd) == S.groups.end()) { ++out->n_skip_bcd; continue; }
+    }
+    int32_t ibcd;
+    {
+      auto it = out->bc_map.find(sbcd);
+      if (it == out->bc_map.end()) {
+        ibcd = (int32_t)out->bcs.size();
+        out->bc_map.emplace(sbcd, ibcd);
+        out->bcs.push_back(sbcd);
+        out->bc_totl.push_back(0);
+      } else {
+        ibcd = it->second;
+      }
+    }
+    // UMI (:272-293): a missing tag leaves "."; --tag-UMI "" draws "." + hex(rand()) per read (:274-276).  The
+    // reference never seeds rand(), so its UMIs are glibc's default sequence (TYPE_3 generator, seed 1): the same
+    // numbers come from a private random_r state here, whatever else the process does with rand().
+    const char* sumi = ".";
+    char rnd_umi[16];
+    if (S.random_umi) {
+      int32_t rv = 0;
+      random_r(rnd, &rv);
+      snprintf(rnd_umi, sizeof(rnd_umi), ".%x", (unsigned)rv);
+      sumi = rnd_umi;
+    } else {
+      const char* z = aux_get_z(aux, end, o->tag_umi);
+      if (z) sumi = z;
+    }
+    ++out->bc_totl[(size_t)ibcd];                                                    // :295
+    if (!n_cigar) continue;            // no walk: base 'N' (hts_utils.cpp:285-288)
+    const size_t umi_len = strlen(sumi);
+    for (int64_t i = i0; i < i1; ++i) {
+      const int64_t sp = S.snp_pos[i];
+      if (k.plain && (sp < pos || sp >= k.endpos)) continue;     // the walk ends at rpos >= l_seq: no base
+      // hts_utils.cpp:279-359, by position alone
+      const uint32_t spos = (uint32_t)sp;
+      uint32_t cpos = (uint32_t)pos;
+      int32_t rpos = 0;
+      for (uint32_t c = 0; c < n_cigar; ++c) {
+        const uint32_t v = rd_u32(cigar + 4 * c), op = v & 15u, len = v >> 4;
+        if (op == 0) {                            // M
+          if (spos >= cpos && spos <= cpos + len - 1) { rpos += (int32_t)(spos - cpos); break; }
+          cpos += len;
+          rpos += (int32_t)len;
+        } else if (op == 2 || op == 3) {          // D, N
+          if (spos >= cpos && spos <= cpos + len - 1) { rpos = -1; break; }
+          cpos += len;
+        } else if (op == 4 || op == 1) {          // S, I
+          rpos += (int32_t)len;
+        }
+      }
+      if (rpos < 0 || rpos >= l_seq) continue;    // BAM_READ_INDEX_NA
+      const char base = kBase[(seq[rpos >> 1] >> ((~rpos & 1) << 2)) & 15];
+      if (base == 'N') continue;                                                      // :314
+      // the reference carries the quality as a (signed) char qual + 33 and subtracts 33 again (:318, :323): values
+      // >= 95, and the 0xff of a record without qualities, wrap to negative numbers and are dropped by --min-BQ
+      const int32_t q = (int32_t)(int8_t)(uint8_t)(qual[rpos] + 33) - 33;
+      if (q < o->min_bq) continue;                                                   // :318
+      if (rpos < o->min_td - 1) continue;                                            // :319
+      if (rpos + o->min_td > l_seq) continue;                                        // :320
+      out->lcell.push_back(ibcd);
+      out->snp.push_back((int32_t)i);
+      out->allele.push_back((uint8_t)(base == S.snp_ref[i] ? 0 : (base == S.snp_alt[i] ? 1 : 2)));   // :322
+      out->bq.push_back((uint8_t)(q > o->cap_bq ? o->cap_bq : q));                   // :323
+      out->umi.insert(out->umi.end(), sumi, sumi + umi_len);
+      out->umi_end.push_back((int64_t)out->umi.size());
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -263,47 +552,83 @@ int dmx_sweep_bam(const char* path, const dmx_sweep_opts* o, int32_t n_chrom, co
     g_bam_error = "tag_umi is null";
     return DMX_E_UNSUPPORTED;
   }
-  for (int64_t i = 1; i < nsnps; ++i)
-    if (snp_rid[i] < snp_rid[i - 1] || (snp_rid[i] == snp_rid[i - 1] && snp_pos[i] < snp_pos[i - 1])) {
+  for (int64_t i = 0; i < nsnps; ++i) {
+    if (snp_rid[i] < 0 || snp_rid[i] >= n_chrom) {
+      g_bam_error = "SNP on a chromosome that is not in the list";
+      return DMX_E_INVALID;
+    }
+    if (i > 0 && (snp_rid[i] < snp_rid[i - 1] || (snp_rid[i] == snp_rid[i - 1] && snp_pos[i] < snp_pos[i - 1]))) {
       g_bam_error = "SNPs are not sorted by chromosome and position";
       return DMX_E_INVALID;
     }
+  }
+  Sweep S;
+  S.o = o;
+  S.nsnps = nsnps;
+  S.snp_rid = snp_rid;
+  S.snp_pos = snp_pos;
+  S.snp_ref = snp_ref;
+  S.snp_alt = snp_alt;
+  S.use_group = o->tag_group && o->tag_group[0];
+  S.random_umi = !o->tag_umi[0];
+  S.rid_end.assign((size_t)n_chrom, 0);
+  {
+    int64_t i = 0;
+    for (int32_t c = 0; c < n_chrom; ++c) {
+      while (i < nsnps && snp_rid[i] <= c) ++i;
+      S.rid_end[(size_t)c] = i;
+    }
+  }
+  for (int64_t i = 0; i < o->n_groups; ++i) S.groups.insert(std::string_view(o->groups[i]));
+  const int nth = S.random_umi ? 1 : env_threads();    // the rand() sequence is drawn in file order
+  size_t min_chunk = 2048;                              // records per walking thread, at least
+  if (const char* env = getenv("DMX_BAM_MIN_CHUNK")) min_chunk = (size_t)std::max(1, atoi(env));
+
   ByteStream gz;
-  if (!gz.open(path)) {
+  if (!gz.open(path, env_threads())) {
     g_bam_error = std::string("cannot open ") + path;
     return DMX_E_IO;
   }
-  uint8_t hdr[12];
-  if (!gz.read(hdr, 8) || memcmp(hdr, "BAM\1", 4) != 0) {
+  size_t cur = 0;             // read position inside the window
+  auto need = [&](size_t n) {
+    while (gz.size() - cur < n) {
+      const bool got = gz.more(cur);
+      cur = 0;
+      if (!got) return gz.size() >= n;
+    }
+    return true;
+  };
+  if (!need(8) || memcmp(gz.data() + cur, "BAM\1", 4) != 0) {
     g_bam_error = std::string(path) + " is not a BAM file";
     return DMX_E_INVALID;
   }
-  std::vector<uint8_t> buf((size_t)std::max(0, rd_i32(hdr + 4)));
-  if (!buf.empty() && !gz.read(buf.data(), buf.size())) { g_bam_error = "truncated BAM header"; return DMX_E_INVALID; }
-  if (!gz.read(hdr, 4)) { g_bam_error = "truncated BAM header"; return DMX_E_INVALID; }
-  const int32_t n_ref = rd_i32(hdr);
-  // BAM tid -> VCF rid by name (bcf_hdr_name2id, :188); the reference insists on the same chromosome order (:160-176)
+  const size_t l_text = (size_t)std::max(0, rd_i32(gz.data() + cur + 4));
+  cur += 8;
+  if (!need(l_text + 4)) { g_bam_error = "truncated BAM header"; return DMX_E_INVALID; }
+  cur += l_text;
+  S.n_ref = rd_i32(gz.data() + cur);
+  cur += 4;
+  // BAM tid -> VCF rid by name (bcf_hdr_name2id, :197); the reference insists on the same chromosome order (:160-176)
   std::unordered_map<std::string, int32_t> name2rid;
   for (int32_t r = 0; r < n_chrom; ++r) name2rid[chroms[r]] = r;
-  std::vector<int32_t> tid2rid((size_t)std::max(0, n_ref), -1);
+  S.tid2rid.assign((size_t)std::max(0, S.n_ref), -1);
   int32_t prev = -1;
-  for (int32_t t = 0; t < n_ref; ++t) {
-    if (!gz.read(hdr, 4)) { g_bam_error = "truncated BAM header"; return DMX_E_INVALID; }
-    const int32_t l = rd_i32(hdr);
-    std::vector<char> nm((size_t)std::max(0, l) + 4);
-    if (l < 1 || !gz.read(nm.data(), (size_t)l + 4)) { g_bam_error = "truncated BAM header"; return DMX_E_INVALID; }
-    auto it = name2rid.find(std::string(nm.data()));
+  for (int32_t t = 0; t < S.n_ref; ++t) {
+    if (!need(4)) { g_bam_error = "truncated BAM header"; return DMX_E_INVALID; }
+    const int32_t l = rd_i32(gz.data() + cur);
+    cur += 4;
+    if (l < 1 || !need((size_t)l + 4)) { g_bam_error = "truncated BAM header"; return DMX_E_INVALID; }
+    const std::string nm((const char*)gz.data() + cur, strnlen((const char*)gz.data() + cur, (size_t)l));
+    cur += (size_t)l + 4;
+    auto it = name2rid.find(nm);
     if (it != name2rid.end()) {
       if (prev >= it->second) {
-        g_bam_error = "VCF and BAM have different orderings of chromosomes";   // :169-171
+        g_bam_error = "VCF and BAM have different orderings of chromosomes";   // :166-169
         return DMX_E_INVALID;
       }
-      tid2rid[(size_t)t] = prev = it->second;
+      S.tid2rid[(size_t)t] = prev = it->second;
     }
   }
-  std::unordered_set<std::string> groups;
-  for (int64_t i = 0; i < o->n_groups; ++i) groups.insert(o->groups[i]);
-  const bool use_group = o->tag_group && o->tag_group[0];
   struct random_data rnd_buf;                 // glibc's rand() of an unseeded process: TYPE_3 state, seed 1
   char rnd_state[128];
   memset(&rnd_buf, 0, sizeof(rnd_buf));
@@ -311,113 +636,119 @@ int dmx_sweep_bam(const char* path, const dmx_sweep_opts* o, int32_t n_chrom, co
 
   dmx_sweep* sw = new dmx_sweep();
   sw->umi_off.push_back(0);
-  std::unordered_map<std::string, int32_t> bc_map;
-  int64_t ibeg = 0;                       // first SNP that can still overlap a read (reads are position-sorted)
-  static const char kBase[] = "=ACMGRSVTWYHKDBN";
+  std::deque<std::string> bc_store;                        // stable storage for the keys of bc_map
+  std::unordered_map<std::string_view, int32_t> bc_map;
+  BufState buf{0, nsnps > 0 ? 0 : -1};        // the first SNP is read before the loop (:150)
+  std::vector<size_t> offs;
+  Pool pool(nth);
+  std::vector<ChunkOut> chunks((size_t)nth);
+  std::vector<std::vector<int32_t>> l2g((size_t)nth);
+  auto fail = [&](const char* msg) {
+    g_bam_error = msg;
+    delete sw;
+    return DMX_E_INVALID;
+  };
   for (;;) {
-    uint8_t bs[4];
-    const int k = gz.read4(bs);
-    if (k == 0) break;                    // end of file
-    if (k != 1) { g_bam_error = "truncated BAM record"; delete sw; return DMX_E_INVALID; }
-    const int32_t block = rd_i32(bs);
-    if (block < 32) { g_bam_error = "corrupt BAM record"; delete sw; return DMX_E_INVALID; }
-    buf.resize((size_t)block);
-    if (!gz.read(buf.data(), buf.size())) { g_bam_error = "truncated BAM record"; delete sw; return DMX_E_INVALID; }
-    ++sw->n_records;
-    const uint8_t* b = buf.data();
-    const int32_t tid = rd_i32(b), pos = rd_i32(b + 4);
-    const uint32_t l_name = b[8], mapq = b[9], n_cigar = rd_u16(b + 12), flag = rd_u16(b + 14);
-    const int32_t l_seq = rd_i32(b + 16);
-    const uint8_t* cigar = b + 32 + l_name;
-    const uint8_t* seq = cigar + 4 * (size_t)n_cigar;
-    const uint8_t* qual = seq + ((size_t)l_seq + 1) / 2;
-    const uint8_t* aux = qual + (size_t)l_seq;
-    const uint8_t* end = b + block;
-    if (l_seq < 0 || aux > end) { g_bam_error = "corrupt BAM record"; delete sw; return DMX_E_INVALID; }
-    // sam_filtered_reader.cpp:284-296
-    if ((int32_t)mapq < o->min_mq || (o->exclude_flag & flag)) { ++sw->n_filtered; continue; }
-    const int32_t rid = (tid >= 0 && tid < n_ref) ? tid2rid[(size_t)tid] : -1;
-    if (rid < 0) { ++sw->n_off_vcf; continue; }                                      // :188-191
-    // bam_endpos: start + reference span of the CIGAR (M, D, N, =, X), at least one base
-    int64_t span = 0;
-    for (uint32_t c = 0; c < n_cigar; ++c) {
-      const uint32_t v = rd_u32(cigar + 4 * c), op = v & 15u;
-      if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += v >> 4;
+    // complete records of the window
+    offs.clear();
+    const uint8_t* win = gz.data();
+    const size_t wsize = gz.size();
+    size_t p = cur;
+    while (p + 4 <= wsize) {
+      const int32_t block = rd_i32(win + p);
+      if (block < 32) return fail("corrupt BAM record");
+      if (p + 4 + (size_t)block > wsize) break;
+      offs.push_back(p);
+      p += 4 + (size_t)block;
     }
-    const int64_t endpos = (int64_t)pos + (span > 0 ? span : 1);
-    // barcode (:239-268)
-    int32_t ibcd = 0;
-    const char* sbcd = ".";
-    if (use_group) {
-      const char* z = aux_get_z(aux, end, o->tag_group);
-      if (z) sbcd = z;
-      if (!groups.empty() && groups.find(sbcd) == groups.end()) { ++sw->n_skip_bcd; continue; }
-    }
-    {
-      auto it = bc_map.find(sbcd);
-      if (it == bc_map.end()) {
-        ibcd = (int32_t)sw->barcodes.size();
-        bc_map.emplace(sbcd, ibcd);
-        sw->barcodes.emplace_back(sbcd);
-        sw->totl.push_back(0);
-      } else {
-        ibcd = it->second;
-      }
-    }
-    // UMI (:272-293): a missing tag leaves "."; --tag-UMI "" draws "." + hex(rand()) per read (:274-276).  The
-    // reference never seeds rand(), so its UMIs are glibc's default sequence (TYPE_3 generator, seed 1): the same
-    // numbers come from a private random_r state here, whatever else the process does with rand().
-    const char* sumi = ".";
-    char rnd_umi[16];
-    if (!o->tag_umi[0]) {
-      int32_t rv = 0;
-      random_r(&rnd_buf, &rv);
-      snprintf(rnd_umi, sizeof(rnd_umi), ".%x", (unsigned)rv);
-      sumi = rnd_umi;
+    const size_t nrec = offs.size();
+    sw->n_records += (int64_t)nrec;
+    const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)nth, nrec / min_chunk));
+    auto lo_of = [&](int t) { return nrec * (size_t)t / (size_t)nt; };
+    if (S.random_umi) {
+      walk_chunk(S, win, offs.data(), 0, nrec, &buf, &rnd_buf, &chunks[0]);
     } else {
-      const char* z = aux_get_z(aux, end, o->tag_umi);
-      if (z) sumi = z;
+      pool.run(nt, [&](int t) { walk_chunk(S, win, offs.data(), lo_of(t), lo_of(t + 1), nullptr, nullptr, &chunks[(size_t)t]); });
     }
-    ++sw->totl[(size_t)ibcd];                                                        // :295
-    // SNPs of this chromosome from the read start on
-    while (ibeg < nsnps && (snp_rid[ibeg] < rid || (snp_rid[ibeg] == rid && snp_pos[ibeg] < pos))) ++ibeg;
-    const size_t umi_len = strlen(sumi);
-    for (int64_t i = ibeg; i < nsnps && snp_rid[i] == rid && snp_pos[i] < endpos; ++i) {
-      // hts_utils.cpp:279-359
-      const uint32_t spos = (uint32_t)snp_pos[i];
-      uint32_t cpos = (uint32_t)pos;
-      int32_t rpos = 0;
-      if (!n_cigar) continue;
-      for (uint32_t c = 0; c < n_cigar; ++c) {
-        const uint32_t v = rd_u32(cigar + 4 * c), op = v & 15u, len = v >> 4;
-        if (op == 0) {                            // M
-          if (spos >= cpos && spos <= cpos + len - 1) { rpos += (int32_t)(spos - cpos); break; }
-          cpos += len;
-          rpos += (int32_t)len;
-        } else if (op == 2 || op == 3) {          // D, N
-          if (spos >= cpos && spos <= cpos + len - 1) { rpos = -1; break; }
-          cpos += len;
-        } else if (op == 4 || op == 1) {          // S, I
-          rpos += (int32_t)len;
+    // in file order: buffer recurrence (exact second walk where a read sees more than its own span), barcode ids
+    size_t total = sw->cell.size(), umi_total = sw->umi_buf.size();
+    std::vector<size_t> at((size_t)nt + 1), umi_at((size_t)nt + 1);
+    for (int t = 0; t < nt; ++t) {
+      ChunkOut& c = chunks[(size_t)t];
+      if (c.corrupt) return fail("corrupt BAM record");
+      if (!S.random_umi) {
+        BufState b = buf;
+        bool redo = false;
+        for (const ReadKey& k : c.keys) {
+          advance_buffer(S, k, &b);
+          if (needs_exact(S, k, b)) { redo = true; break; }
+        }
+        if (redo) {
+          walk_chunk(S, win, offs.data(), lo_of(t), lo_of(t + 1), &buf, nullptr, &c);
+        } else {
+          buf = b;
         }
       }
-      if (rpos < 0 || rpos >= l_seq) continue;    // BAM_READ_INDEX_NA
-      const char base = kBase[(seq[rpos >> 1] >> ((~rpos & 1) << 2)) & 15];
-      if (base == 'N') continue;                                                      // :306
-      // the reference carries the quality as a (signed) char qual + 33 and subtracts 33 again (:310, :315): values
-      // >= 95, and the 0xff of a record without qualities, wrap to negative numbers and are dropped by --min-BQ
-      const int32_t q = (int32_t)(int8_t)(uint8_t)(qual[rpos] + 33) - 33;
-      if (q < o->min_bq) continue;                                                   // :310
-      if (rpos < o->min_td - 1) continue;                                            // :311
-      if (rpos + o->min_td > l_seq) continue;                                        // :312
-      sw->cell.push_back(ibcd);
-      sw->snp.push_back((int32_t)i);
-      sw->allele.push_back((uint8_t)(base == snp_ref[i] ? 0 : (base == snp_alt[i] ? 1 : 2)));   // :314
-      sw->bq.push_back((uint8_t)(q > o->cap_bq ? o->cap_bq : q));                    // :315
-      sw->umi_buf.insert(sw->umi_buf.end(), sumi, sumi + umi_len);
-      sw->umi_off.push_back((int64_t)sw->umi_buf.size());
+      std::vector<int32_t>& map = l2g[(size_t)t];
+      map.resize(c.bcs.size());
+      for (size_t i = 0; i < c.bcs.size(); ++i) {
+        auto it = bc_map.find(c.bcs[i]);
+        if (it == bc_map.end()) {
+          bc_store.emplace_back(c.bcs[i]);
+          it = bc_map.emplace(std::string_view(bc_store.back()), (int32_t)bc_store.size() - 1).first;
+          sw->totl.push_back(0);
+        }
+        map[i] = it->second;
+        sw->totl[(size_t)it->second] += c.bc_totl[i];
+      }
+      sw->n_filtered += c.n_filtered;
+      sw->n_off_vcf += c.n_off_vcf;
+      sw->n_skip_bcd += c.n_skip_bcd;
+      at[(size_t)t] = total;
+      umi_at[(size_t)t] = umi_total;
+      total += c.lcell.size();
+      umi_total += c.umi.size();
+    }
+    at[(size_t)nt] = total;
+    if (total > sw->cell.capacity()) {          // grow once to the size the decoded share of the file suggests
+      const double frac = gz.decoded_share();
+      const size_t want = frac > 0 ? (size_t)((double)total / frac * 1.05) + 4096 : 0;
+      const size_t umi_want = frac > 0 ? (size_t)((double)umi_total / frac * 1.05) + 65536 : 0;
+      sw->cell.reserve(std::max(want, total));
+      sw->snp.reserve(std::max(want, total));
+      sw->allele.reserve(std::max(want, total));
+      sw->bq.reserve(std::max(want, total));
+      sw->umi_off.reserve(std::max(want, total) + 1);
+      sw->umi_buf.reserve(std::max(umi_want, umi_total));
+    }
+    sw->cell.resize(total);
+    sw->snp.resize(total);
+    sw->allele.resize(total);
+    sw->bq.resize(total);
+    sw->umi_buf.resize(umi_total);
+    sw->umi_off.resize(total + 1);
+    pool.run(nt, [&](int t) {
+      const ChunkOut& c = chunks[(size_t)t];
+      const size_t a = at[(size_t)t], n = c.lcell.size();
+      const std::vector<int32_t>& map = l2g[(size_t)t];
+      for (size_t i = 0; i < n; ++i) sw->cell[a + i] = map[(size_t)c.lcell[i]];
+      if (n) {
+        memcpy(sw->snp.data() + a, c.snp.data(), n * 4);
+        memcpy(sw->allele.data() + a, c.allele.data(), n);
+        memcpy(sw->bq.data() + a, c.bq.data(), n);
+        memcpy(sw->umi_buf.data() + umi_at[(size_t)t], c.umi.data(), c.umi.size());
+      }
+      for (size_t i = 0; i < n; ++i) sw->umi_off[a + i + 1] = (int64_t)umi_at[(size_t)t] + c.umi_end[i];
+    });
+    // next window
+    const bool got = gz.more(p);
+    cur = 0;
+    if (!got) {
+      if (gz.bad() || gz.size() > 0) return fail("truncated BAM record");
+      break;
     }
   }
+  sw->barcodes.assign(bc_store.begin(), bc_store.end());
   *out = sw;
   return DMX_OK;
 }

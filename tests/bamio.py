@@ -87,6 +87,9 @@ class GlibcRand:
 
 def sweep(refs, reads, chroms, snp_rid, snp_pos, snp_ref, snp_alt, groups=None, tag_group="CB", tag_umi="UB", min_mq=20,
           exclude_flag=0x0f04, min_bq=13, cap_bq=40, min_td=0):
+    """cmd_cram_demuxlet.cpp:186-338 read by read, with the reference's SNP buffer transcribed literally: `ibeg` / `nbuf`
+    are its variables (buffer = SNPs [ibeg, ibeg + nbuf), the newest one is the VCF cursor), clear_buffer_before is
+    bcf_filtered_reader.cpp:649-669, and a read is tested against every buffered SNP by position alone (:306-308)."""
     rnd = GlibcRand()
     name2rid = {c: i for i, c in enumerate(chroms)}
     tid2rid = [name2rid.get(n, -1) for n, _ in refs]
@@ -94,6 +97,8 @@ def sweep(refs, reads, chroms, snp_rid, snp_pos, snp_ref, snp_alt, groups=None, 
     out = {"cell": [], "snp": [], "allele": [], "bq": [], "umis": []}
     cnt = {"records": 0, "filtered": 0, "off_vcf": 0, "skip_bcd": 0}
     groups = set(groups or [])
+    nsnps = len(snp_pos)
+    ibeg, nbuf, eof = 0, (1 if nsnps else 0), nsnps == 0     # :150 reads the first SNP before the loop
     for r in reads:
         cnt["records"] += 1
         if r["mapq"] < min_mq or (r["flag"] & exclude_flag):
@@ -105,6 +110,22 @@ def sweep(refs, reads, chroms, snp_rid, snp_pos, snp_ref, snp_alt, groups=None, 
             continue
         span = sum(ln for op, ln in r["cigar"] if op in "MDN=X")
         endpos = r["pos"] + (span if span > 0 else 1)
+        n_rm = 0                                           # clear_buffer_before(chrom, read start), rlen = 1
+        for i in range(ibeg, ibeg + nbuf):
+            if snp_rid[i] < rid or (snp_rid[i] == rid and snp_pos[i] + 1 < r["pos"]):
+                n_rm += 1
+            else:
+                break
+        nbuf -= n_rm
+        ibeg += n_rm                                       # :206
+        while not eof:                                     # :209: the cursor is the newest SNP
+            cur = ibeg + nbuf - 1 if nbuf else ibeg - 1
+            if not (snp_rid[cur] < rid or (snp_rid[cur] == rid and snp_pos[cur] < endpos)):
+                break
+            if cur + 1 < nsnps:
+                nbuf += 1
+            else:
+                eof = True
         tags = {t: v for t, ty, v in r["tags"] if ty == "Z"}
         sb = tags.get(tag_group, ".") if tag_group else "."
         if tag_group and groups and sb not in groups:
@@ -116,9 +137,7 @@ def sweep(refs, reads, chroms, snp_rid, snp_pos, snp_ref, snp_alt, groups=None, 
         ib = bc[sb]
         umi = (".%x" % rnd()) if tag_umi == "" else tags.get(tag_umi, ".")     # :274-276
         totl[ib] += 1
-        for i in range(len(snp_pos)):
-            if snp_rid[i] != rid or not (r["pos"] <= snp_pos[i] < endpos):
-                continue
+        for i in range(ibeg, ibeg + nbuf):                 # :306
             if not r["cigar"]:
                 continue
             cpos, rpos, sp = r["pos"], 0, int(snp_pos[i])

@@ -74,6 +74,67 @@ def test_bgzf_blocks_inflate_in_parallel(threads, tmp_path, monkeypatch):
         api.sweep_bam(str(tmp_path / "bad.bam"), chroms, rid, pos, ref, alt)
 
 
+def _read(tid, pos, cigar, cb="c1-1", umi="u", base="C"):
+    lseq = sum(ln for op, ln in cigar if op in "MIS=X")
+    return {"tid": tid, "pos": pos, "mapq": 60, "flag": 0, "cigar": cigar, "seq": base * lseq, "qual": [30] * lseq,
+            "tags": [("CB", "Z", cb), ("UB", "Z", umi)]}
+
+
+def test_sweep_buffer_tests_by_position_alone(tmp_path):
+    """the reference tests a read against every SNP in its buffer by position only (cmd_cram_demuxlet.cpp:306-308,
+    hts_utils.cpp:279-359 has no chromosome): the look-ahead SNP of the next chromosome and, right after a chromosome
+    change, the not yet dropped tail of the previous one give add_read calls for reads at the same coordinate of another
+    chromosome; reads with = / X operations find a base for any buffered SNP outside their M / D / N segments"""
+    chroms = ["chrM", "chr1", "chr2"]
+    #           chrM: none   chr1: 1000, 5000, 5050          chr2: 1020, 5040
+    rid = np.array([1, 1, 1, 2, 2], np.int32)
+    pos = np.array([1000, 5000, 5050, 1020, 5040], np.int32)
+    ref, alt = np.full(5, b"A", "S1"), np.full(5, b"C", "S1")
+    reads = [
+        _read(0, 990, [("M", 50)], umi="m"),       # chrM (declared, no SNPs): the buffer holds SNP 0 = chr1:1000 -> hit
+        _read(1, 980, [("M", 50)], umi="a"),       # chr1:1000 itself
+        _read(1, 5030, [("M", 50)], umi="b"),      # chr1:5050, and the look-ahead chr2:1020 is not under it
+        _read(1, 5060, [("M", 10)], umi="x"),      # behind the last chr1 SNP: look-ahead = chr2:1020, no overlap
+        _read(2, 1010, [("M", 50)], umi="c"),      # chr2:1020
+        _read(2, 5035, [("=", 10), ("M", 20)], umi="d"),   # = ignored: chr2:5040 is outside the M walk -> base at offset 20
+    ]
+    path = str(tmp_path / "q.bam")
+    bamio.write_bam(path, [("chrM", 16000), ("chr1", 60000), ("chr2", 50000)], reads)
+    got = api.sweep_bam(path, chroms, rid, pos, ref, alt)
+    want = bamio.sweep([("chrM", 16000), ("chr1", 60000), ("chr2", 50000)], reads, chroms, rid, pos, ref, alt)
+    same(got, want)
+    assert list(zip(got["umis"], got["snp"].tolist())) == [("m", 0), ("a", 0), ("b", 2), ("c", 3), ("d", 4)]
+    # the tail of the previous chromosome: after a chr1 read far in front of chr1's last SNPs, the first chr2 read drops
+    # what was buffered (chr1:1000, chr1:5000), reads ahead through chr1:5050 and is tested against it
+    reads2 = [_read(1, 980, [("M", 50)], umi="a"), _read(2, 4990, [("M", 80)], umi="t")]
+    bamio.write_bam(path, [("chrM", 16000), ("chr1", 60000), ("chr2", 50000)], reads2)
+    got = api.sweep_bam(path, chroms, rid, pos, ref, alt)
+    same(got, bamio.sweep([("chrM", 16000), ("chr1", 60000), ("chr2", 50000)], reads2, chroms, rid, pos, ref, alt))
+    assert list(zip(got["umis"], got["snp"].tolist())) == [("a", 0), ("t", 2), ("t", 4)]
+
+
+@pytest.mark.parametrize("threads,chunk", [("1", "1"), ("2", "40"), ("5", "7"), ("16", "300")])
+def test_sweep_is_independent_of_the_thread_count(threads, chunk, tmp_path, monkeypatch):
+    """records are walked in chunks on all host threads and merged in file order: same tuples, barcode ids and counts
+    for any number of threads and any chunk size, on chromosomes whose coordinates overlap (so that chunks hit the
+    exact second walk) and with = / X reads in between"""
+    monkeypatch.setenv("DMX_BAM_THREADS", threads)
+    monkeypatch.setenv("DMX_BAM_MIN_CHUNK", chunk)
+    rng = np.random.default_rng(21)
+    chroms, rid, pos, ref, alt = make_snps(rng, 1500)
+    reads, barcodes = bamio.random_reads(rng, REFS, {1: pos[rid == 0], 2: pos[rid == 1]}, 7000, ncells=40)
+    for r in reads[::97]:
+        if r["cigar"] == [("M", 90)]:
+            r["cigar"] = [("M", 30), ("X", 1), ("=", 19), ("M", 40)]
+    path = str(tmp_path / "t.bam")
+    bamio.write_bam(path, REFS, reads, member=900, bgzf=True)
+    want = bamio.sweep(REFS, reads, chroms, rid, pos, ref, alt)
+    same(api.sweep_bam(path, chroms, rid, pos, ref, alt), want)
+    keep = barcodes[::3]
+    same(api.sweep_bam(path, chroms, rid, pos, ref, alt, groups=keep),
+         bamio.sweep(REFS, reads, chroms, rid, pos, ref, alt, groups=keep))
+
+
 def test_sweep_feeds_the_packer(tmp_path):
     """sweep tuples -> dmx_pack_reads == the python container restatement on the same tuples"""
     from demuxlet_b200.plp import build_from_reads
@@ -193,7 +254,9 @@ def test_cigar_lookup_restatement_against_reference_function(tmp_path):
 
 def test_sweep_lookup_against_reference_function(tmp_path):
     """dmx_sweep_bam on the same reads with a SNP at every position: the emitted tuples are exactly the reference
-    function's results put through the thresholds of cmd_cram_demuxlet.cpp:304-315"""
+    function's results put through the thresholds of cmd_cram_demuxlet.cpp:304-325, for every SNP the reference's buffer
+    holds when the read is tested (:202-237: from one base before the read start to the furthest read end so far) --
+    which, for reads with = / X operations (ignored by the reference's walk), includes bases "found" outside the read"""
     reads, queries, res = _reference_lookups(tmp_path)
     L = 700
     rid, pos = np.zeros(L, np.int32), np.arange(L, dtype=np.int32)
@@ -203,22 +266,26 @@ def test_sweep_lookup_against_reference_function(tmp_path):
     got = api.sweep_bam(path, ["chr1"], rid, pos, ref, alt)
     want = []
     cells = {}
+    s, hi, outside = 0, 0, 0
     for r, qs, row in zip(reads, queries, res):
         cb = dict((t, v) for t, _, v in r["tags"])["CB"]
         ic = cells.setdefault(cb, len(cells))
         span = sum(ln for op, ln in r["cigar"] if op in "MDN=X")
-        for q, (base, qual, rpos) in zip(qs, row):
-            if not (r["pos"] <= q < r["pos"] + max(span, 1)):
-                # outside the aligned span the reference finds no base -- except for reads with = / X operations, which
-                # its walk ignores: there it returns the base at the offset the walk ended on for ANY buffered SNP (a
-                # defect the sweep does not reproduce: it only tests SNPs under the read)
-                assert rpos < 0 or base == "N" or not r["cigar"] or any(op in "=X" for op, _ in r["cigar"])
-                continue
+        s = max(s, min(max(r["pos"] - 1, 0), hi + 1))            # SNP index == position here
+        hi = max(hi, min(r["pos"] + max(span, 1), L - 1))
+        by_q = dict(zip(qs, row))
+        for q in range(s, hi + 1):
+            # beyond the positions the reference function was asked about, its restatement (checked against it above)
+            base, qual, rpos = by_q[q] if q in by_q else bamio.lookup(r, q)
             if rpos < 0 or base == "N" or qual - 33 < 13:
                 continue
+            if not (r["pos"] <= q < r["pos"] + max(span, 1)):
+                assert any(op in "=X" for op, _ in r["cigar"])
+                outside += 1
             want.append((ic, q, 0 if base == "A" else (1 if base == "C" else 2), min(qual - 33, 40)))
     have = list(zip(got["cell"].tolist(), got["snp"].tolist(), got["allele"].tolist(), got["bq"].tolist()))
-    assert have == want and len(want) > 3000
+    assert have == want and len(want) > 3000 and outside > 100
+    assert same(got, bamio.sweep([("chr1", 5000)], reads, ["chr1"], rid, pos, ref, alt)) is None
 
 
 def test_random_umis_are_glibc_rand():
