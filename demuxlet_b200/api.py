@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "dmx_last_error", "dmx_abi_version", "dmx_pack_reads", "dmx_pileup_sizes", "dmx_pileup_copy", "dmx_pileup_free",
     "dmx_build_gp", "dmx_build_gp_device", "dmx_set_field", "dmx_site_filter",
     "dmx_sweep_opts_default", "dmx_sweep_bam", "dmx_sweep_sizes", "dmx_sweep_counts", "dmx_sweep_copy", "dmx_sweep_barcode",
-    "dmx_sweep_free", "dmx_sweep_last_error", "dmx_vcf_read", "dmx_vcf_select", "dmx_vcf_sizes", "dmx_vcf_sample", "dmx_vcf_chrom", "dmx_vcf_copy", "dmx_vcf_free", "dmx_vcf_last_error",
+    "dmx_sweep_free", "dmx_sweep_last_error", "dmx_vcf_read", "dmx_vcf_select", "dmx_vcf_sizes", "dmx_vcf_sample", "dmx_vcf_chrom", "dmx_vcf_copy", "dmx_vcf_no_field", "dmx_vcf_free", "dmx_vcf_last_error",
 ]
 
 DMX_FIELD = {"GT": 0, "GP": 1, "PL": 2}            # --field (cmd_cram_demuxlet.cpp:28, :45)
@@ -207,7 +207,8 @@ def site_filter(gt, min_mac: int = 1, min_callrate: float = 0.5, device: int = 0
 def read_vcf(path: str, field: str = "GT", samples: Optional[Sequence[str]] = None) -> dict:
     """dmx_vcf_read: the biallelic records of a VCF (plain / gzip / bgzip) as the flat arrays site_filter / build_gp
     take.  Returns samples, chroms, rid, pos (0-based), ref, alt, gt int8[nrec][nv][2], values (GT: gt; GP float32;
-    PL int32 [nrec][nv][3]), n_skipped."""
+    PL int32 [nrec][nv][3]), n_skipped, no_field (uint8[nrec]: the record's FORMAT lacks `field`; an error for the
+    reference only if the record passes site_filter, /root/reference/cmd_cram_demuxlet.cpp:153,:211)."""
     lib = load_library()
     lib.dmx_vcf_read.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_void_p)]
     lib.dmx_vcf_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
@@ -217,6 +218,7 @@ def read_vcf(path: str, field: str = "GT", samples: Optional[Sequence[str]] = No
     lib.dmx_vcf_chrom.argtypes = [C.c_void_p, C.c_int32]
     lib.dmx_vcf_chrom.restype = C.c_char_p
     lib.dmx_vcf_copy.argtypes = [C.c_void_p] * 7
+    lib.dmx_vcf_no_field.argtypes = [C.c_void_p] * 2
     lib.dmx_vcf_free.argtypes = [C.c_void_p]
     lib.dmx_vcf_free.restype = None
     lib.dmx_vcf_last_error.restype = C.c_char_p
@@ -241,7 +243,9 @@ def read_vcf(path: str, field: str = "GT", samples: Optional[Sequence[str]] = No
         ref, alt = np.zeros(nrec, "S1"), np.zeros(nrec, "S1")
         lib.dmx_vcf_copy(h, gt.ctypes.data, None if code == 0 else vals.ctypes.data, rid.ctypes.data, pos.ctypes.data,
                          ref.ctypes.data, alt.ctypes.data)
-        return {"samples": [lib.dmx_vcf_sample(h, i).decode() for i in range(nv)],
+        no_field = np.zeros(nrec, np.uint8)
+        lib.dmx_vcf_no_field(h, no_field.ctypes.data)
+        return {"samples": [lib.dmx_vcf_sample(h, i).decode() for i in range(nv)], "no_field": no_field,
                 "chroms": [lib.dmx_vcf_chrom(h, i).decode() for i in range(nchrom.value)],
                 "rid": rid, "pos": pos, "ref": ref, "alt": alt, "gt": gt, "values": vals, "n_skipped": nskip.value}
     finally:

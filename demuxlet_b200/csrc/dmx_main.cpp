@@ -288,6 +288,17 @@ int main(int argc, char** argv) {
     std::vector<uint8_t> pass((size_t)nrec);
     const int frc = dmx_site_filter(gpu, vnv, nrec, gt.data(), min_mac, min_callrate, pass.data());
     if (frc != DMX_OK) die("libdmx: %s", dmx_strerror(frc));
+    {
+      // a record without the requested FORMAT key stops the reference only when it has passed the filter (:153,:211-212)
+      std::vector<uint8_t> no_field((size_t)nrec);
+      std::vector<int32_t> rid((size_t)nrec), pos((size_t)nrec);
+      dmx_vcf_no_field(v, no_field.data());
+      dmx_vcf_copy(v, nullptr, nullptr, rid.data(), pos.data(), nullptr, nullptr);
+      for (int64_t r = 0; r < nrec; ++r)
+        if (pass[(size_t)r] && no_field[(size_t)r])
+          die("Cannot parse posterior probability at %s:%s", dmx_vcf_chrom(v, rid[(size_t)r]),
+              std::to_string(pos[(size_t)r] + 1).c_str());
+    }
     int64_t keep = 0;
     for (int64_t r = 0; r < nrec; ++r)
       if (pass[(size_t)r]) {

@@ -10,6 +10,8 @@
 //   GP   three floats per sample, "." or a short vector -> NaN (htslib: bcf_float_missing / vector_end, both NaNs)
 //   PL   three int32 per sample, "." or a short vector -> INT32_MIN (bcf_int32_missing; vector_end = INT32_MIN + 1 reads
 //        the same through PhredHelper.h:40's uint32_t cast: > 255)
+// A record whose FORMAT lacks the requested key is delivered with all values missing and flagged (dmx_vcf_no_field): the
+// reference fails on it only if it passes the genotype filter (parse_posteriors, cmd_cram_demuxlet.cpp:153,:211).
 // Records are delivered in file order; records whose allele count is not 2 are skipped and counted (demuxlet sets
 // maxAlleles = 2, cmd_cram_demuxlet.cpp:26; a record without ALT cannot pass --min-mac 1).  All samples are selected
 // (dmx_vcf_select applies --sm / --sm-list afterwards).  The chromosome ids follow the header's ##contig lines, then first
@@ -40,6 +42,7 @@ struct dmx_vcf {
   std::vector<int8_t> gt;             // [nrec][nv][2]
   std::vector<float> gp;              // [nrec][nv][3] (field GP)
   std::vector<int32_t> pl;            // [nrec][nv][3] (field PL)
+  std::vector<uint8_t> no_field;      // [nrec] 1: the record's FORMAT lacks the requested key (values all missing)
   int64_t n_skipped = 0;              // records with n_allele != 2
   std::string error;
 };
@@ -181,7 +184,9 @@ void parse_range(const std::vector<Line>& lines, size_t lo, size_t hi, int32_t f
       if (want && keys[k].n == 2 && memcmp(keys[k].p, want, 2) == 0) i_f = (int)k;
     }
     if (i_gt < 0) return fail(lines[li].no, "no GT in FORMAT (demuxlet's record filter needs it)");
-    if (want && i_f < 0) return fail(lines[li].no, std::string("no ") + want + " in FORMAT");
+    // a record without the requested key is an error in the reference only if it gets as far as parse_posteriors,
+    // i.e. passes the genotype filter (cmd_cram_demuxlet.cpp:153,:211): flag it, the caller decides after the filter
+    v->no_field.push_back((uint8_t)(want && i_f < 0));
     v->rid.push_back((int32_t)chrom_id);
     v->pos.push_back(conv_int(cols[1].p, cols[1].p + cols[1].n) - 1);
     v->ref.push_back(cols[3].n ? cols[3].p[0] : 'N');
@@ -194,9 +199,9 @@ void parse_range(const std::vector<Line>& lines, size_t lo, size_t hi, int32_t f
     for (size_t s = 0; s < nv; ++s) {
       const Tok& col = cols[9 + s];
       parse_gt(subfield(col, i_gt), &v->gt[g0 + s * 2]);
-      if (field == DMX_FIELD_GP) parse_vec3<float>(subfield(col, i_f), &v->gp[f0 + s * 3], kNaN, conv_float);
-      if (field == DMX_FIELD_PL)
-        parse_vec3<int32_t>(subfield(col, i_f), &v->pl[f0 + s * 3], std::numeric_limits<int32_t>::min(), conv_int);
+      const Tok fcol = i_f >= 0 ? subfield(col, i_f) : Tok{col.p, 0};
+      if (field == DMX_FIELD_GP) parse_vec3<float>(fcol, &v->gp[f0 + s * 3], kNaN, conv_float);
+      if (field == DMX_FIELD_PL) parse_vec3<int32_t>(fcol, &v->pl[f0 + s * 3], std::numeric_limits<int32_t>::min(), conv_int);
     }
   }
 }
@@ -297,6 +302,7 @@ int dmx_vcf_read(const char* path, int32_t field, dmx_vcf** out) {
     v->pos.insert(v->pos.end(), pt.v.pos.begin(), pt.v.pos.end());
     v->ref.insert(v->ref.end(), pt.v.ref.begin(), pt.v.ref.end());
     v->alt.insert(v->alt.end(), pt.v.alt.begin(), pt.v.alt.end());
+    v->no_field.insert(v->no_field.end(), pt.v.no_field.begin(), pt.v.no_field.end());
     v->gt.insert(v->gt.end(), pt.v.gt.begin(), pt.v.gt.end());
     v->gp.insert(v->gp.end(), pt.v.gp.begin(), pt.v.gp.end());
     v->pl.insert(v->pl.end(), pt.v.pl.begin(), pt.v.pl.end());
@@ -373,6 +379,12 @@ int dmx_vcf_copy(const dmx_vcf* v, int8_t* gt, void* field_values, int32_t* rid,
     if (ref) memcpy(ref, v->ref.data(), n);
     if (alt) memcpy(alt, v->alt.data(), n);
   }
+  return DMX_OK;
+}
+
+int dmx_vcf_no_field(const dmx_vcf* v, uint8_t* flags) {
+  if (!v) return DMX_E_INVALID;
+  if (flags && !v->no_field.empty()) memcpy(flags, v->no_field.data(), v->no_field.size());
   return DMX_OK;
 }
 

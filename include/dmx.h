@@ -249,6 +249,10 @@ const char* dmx_vcf_chrom(const dmx_vcf* v, int32_t rid);       /* chromosome na
 /* any pointer may be null: gt int8[nrec][nv][2]; field_values = gt again (GT), float[nrec][nv][3] (GP) or
  * int32[nrec][nv][3] (PL); rid / pos (0-based) [nrec]; first base of REF / ALT [nrec] (add_snp, :230) */
 int dmx_vcf_copy(const dmx_vcf* v, int8_t* gt, void* field_values, int32_t* rid, int32_t* pos, char* ref, char* alt);
+/* flags[nrec]: 1 where the record's FORMAT does not have the requested key (its values are all missing).  The reference
+ * fails on such a record only when it reaches parse_posteriors, i.e. after the genotype filter and inside the span of
+ * the BAM (cmd_cram_demuxlet.cpp:153,:211-212): check the records that survive dmx_site_filter */
+int dmx_vcf_no_field(const dmx_vcf* v, uint8_t* flags);
 void dmx_vcf_free(dmx_vcf* v);
 const char* dmx_vcf_last_error(void);
 

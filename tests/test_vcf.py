@@ -61,8 +61,14 @@ def test_reader_errors(tmp_path):
     p = tmp_path / "nogp.vcf"
     vcfio.write_vcf(str(p), ["a", "b"], [("1", 5, "A", "C", ["GT"], [{"GT": "0/1"}, {"GT": "1/1"}])])
     assert len(api.read_vcf(str(p), "GT")["pos"]) == 1
-    with pytest.raises(api.DmxError, match="no GP"):
-        api.read_vcf(str(p), "GP")
+    # a record without the requested key is flagged, not refused: the reference fails on it only if it passes the
+    # genotype filter (parse_posteriors comes after passed_vfilter, cmd_cram_demuxlet.cpp:153,:211)
+    vcfio.write_vcf(str(p), ["a", "b"], [("1", 5, "A", "C", ["GT"], [{"GT": "0/0"}, {"GT": "0/0"}]),
+                                         ("1", 9, "A", "C", ["GT", "GP"], [{"GT": "0/1", "GP": "0,1,0"}, {"GT": "1/1", "GP": "0,0,1"}]),
+                                         ("1", 12, "A", "C", ["GT"], [{"GT": "0/1"}, {"GT": "1/1"}])])
+    v = api.read_vcf(str(p), "GP")
+    assert v["no_field"].tolist() == [1, 0, 1] and np.isnan(v["values"][[0, 2]]).all() and not np.isnan(v["values"][1]).any()
+    assert api.read_vcf(str(p), "GT")["no_field"].tolist() == [0, 0, 0]
     p = tmp_path / "cols.vcf"
     p.write_text("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\ta\tb\n1\t5\t.\tA\tC\t.\t.\t.\tGT\t0/1\n")
     with pytest.raises(api.DmxError, match="columns"):
@@ -123,6 +129,34 @@ def test_cli_vcf(field, tmp_path):
     bad = subprocess.run([exe, "--plp", str(tmp_path / "b.dmxp"), "--out", str(tmp_path / "c"), "--vcf", path, "--field", field],
                          capture_output=True, text=True)          # default filter keeps another number of records
     assert bad.returncode == 1 and "not the SNPs of the pileup" in bad.stderr
+
+
+@pytest.mark.gpu
+def test_cli_vcf_missing_field_only_matters_after_the_filter(tmp_path):
+    """a record whose FORMAT lacks --field stops the reference only when it passes the genotype filter
+    (parse_posteriors follows passed_vfilter, cmd_cram_demuxlet.cpp:153,:211-212): a monomorphic record without PL is
+    dropped silently, a polymorphic one is the reference's error"""
+    import os
+    import subprocess
+    from demuxlet_b200 import synth
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "demuxlet_b200", "dmx-demuxlet")
+    rng = np.random.default_rng(10)
+    samples = ["d%d" % i for i in range(4)]
+    recs = vcfio.random_records(rng, 300, len(samples), "PL")
+    mono = ("1", 1, "A", "C", ["GT"], [{"GT": "0/0"}] * 4)
+    poly = ("1", 2, "A", "C", ["GT"], [{"GT": "0/1"}, {"GT": "1/1"}, {"GT": "0/0"}, {"GT": "0/1"}])
+    ok_path, bad_path = str(tmp_path / "ok.vcf"), str(tmp_path / "bad.vcf")
+    vcfio.write_vcf(ok_path, samples, [mono] + recs)
+    vcfio.write_vcf(bad_path, samples, [mono, poly] + recs)
+    v = vcfio.parse_vcf(ok_path, "GT")
+    keep = int(po.site_filter(v["gt"], 1, 0.5).sum())
+    synth.make_synth(10, len(samples), keep, "GP", seed=6).save(str(tmp_path / "a.dmxp"))
+    r = subprocess.run([exe, "--plp", str(tmp_path / "a.dmxp"), "--out", str(tmp_path / "a"), "--vcf", ok_path, "--field", "PL"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, "--plp", str(tmp_path / "a.dmxp"), "--out", str(tmp_path / "b"), "--vcf", bad_path, "--field", "PL"],
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "Cannot parse posterior probability at 1:2" in r.stderr
 
 
 @pytest.mark.gpu
