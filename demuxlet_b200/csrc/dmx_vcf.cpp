@@ -33,6 +33,7 @@
 #include <vector>
 
 #include "../../include/dmx.h"
+#include "dmx_bgzf.h"
 
 struct dmx_vcf {
   int32_t field = DMX_FIELD_GT;
@@ -51,19 +52,12 @@ namespace {
 
 thread_local std::string g_vcf_error;
 
-bool slurp(const char* path, std::string* out) {
-  gzFile f = gzopen(path, "rb");      // transparent for uncompressed files
-  if (!f) return false;
-  gzbuffer(f, 1 << 20);
-  std::vector<char> buf(1 << 22);
-  for (;;) {
-    const int n = gzread(f, buf.data(), (unsigned)buf.size());
-    if (n < 0) { gzclose(f); return false; }
-    if (n == 0) break;
-    out->append(buf.data(), (size_t)n);
-  }
-  gzclose(f);
-  return true;
+// the whole decompressed text (BGZF blocks inflated on all host threads, dmx_bgzf.h)
+bool slurp(const char* path, int nth, std::string* out) {
+  dmx_io::ByteStream in;
+  if (!in.open(path, nth)) return false;
+  while (in.more(in.size())) out->append((const char*)in.data(), in.size());
+  return !in.bad();
 }
 
 struct Tok {
@@ -126,13 +120,45 @@ void parse_vec3(const Tok& t, T* out, T missing, F conv) {
   }
 }
 
+// htslib parses a FORMAT float with strtod and stores it in a float (vcf.c, vcf_parse_format): (float)strtod(text).
+// Plain decimal text -- [-+]digits[.digits][e[-+]digits] with a mantissa below 2^53 and a decimal exponent within
+// +-22 -- is converted exactly as strtod does by ONE correctly rounded double operation on two exactly representable
+// numbers (Clinger's fast path); everything else (inf, nan, hex, long mantissas, big exponents) goes to strtod itself.
 float conv_float(const char* p, const char* q) {
-  char tmp[64];
+  static const double kPow10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                                    1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+  const char* s = p;
+  bool neg = false;
+  if (s < q && (*s == '-' || *s == '+')) neg = *s++ == '-';
+  uint64_t m = 0;
+  int digits = 0, frac = 0;
+  bool any = false, ok = true;
+  for (; s < q && *s >= '0' && *s <= '9'; ++s) { m = m * 10 + (uint64_t)(*s - '0'); any = true; if (m) ++digits; }
+  if (s < q && *s == '.') {
+    ++s;
+    for (; s < q && *s >= '0' && *s <= '9'; ++s) { m = m * 10 + (uint64_t)(*s - '0'); any = true; ++frac; if (m) ++digits; }
+  }
+  int ex = 0;
+  if (any && s < q && (*s == 'e' || *s == 'E')) {
+    const char* t = s + 1;
+    bool eneg = false;
+    if (t < q && (*t == '-' || *t == '+')) eneg = *t++ == '-';
+    if (t < q && *t >= '0' && *t <= '9') {
+      for (; t < q && *t >= '0' && *t <= '9'; ++t) { ex = ex * 10 + (*t - '0'); if (ex > 9999) ok = false; }
+      if (eneg) ex = -ex;
+      s = t;
+    }
+  }
+  const int k = ex - frac;
+  if (any && ok && s == q && digits <= 15 && k >= -22 && k <= 22) {
+    const double d = k < 0 ? (double)m / kPow10[-k] : (double)m * kPow10[k];
+    return (float)(neg ? -d : d);
+  }
+  char tmp[128];
   const size_t n = std::min<size_t>((size_t)(q - p), sizeof(tmp) - 1);
   memcpy(tmp, p, n);
   tmp[n] = 0;
-  return strtof(tmp, nullptr);     // htslib parses FORMAT floats with strtod and narrows; the same float for decimal text of
-                                   // <= 9 significant digits, which is what VCF writers emit
+  return (float)strtod(tmp, nullptr);
 }
 
 int32_t conv_int(const char* p, const char* q) {
@@ -149,18 +175,22 @@ namespace {
 
 struct Line { const char *p, *e; int64_t no; };
 
-// records of one contiguous range of lines (one host thread each); rids are local to the part until the merge
+// Records of one contiguous range of lines [lo, hi), parsed by one host thread straight into the arrays of the whole
+// file at record slots lo, lo + 1, ... (a skipped record leaves its slot to the next one; the ranges are closed up
+// afterwards).  Chromosome ids are local to the part until the merge.
 struct Part {
-  dmx_vcf v;
+  std::vector<std::string> chroms;
+  size_t n = 0;                      // records delivered into slots [lo, lo + n)
+  int64_t n_skipped = 0;
   std::string error;
   int64_t err_line = 0;
 };
 
-void parse_range(const std::vector<Line>& lines, size_t lo, size_t hi, int32_t field, size_t nv, Part* part) {
-  dmx_vcf* v = &part->v;
+void parse_range(const std::vector<Line>& lines, size_t lo, size_t hi, int32_t field, size_t nv, dmx_vcf* v, Part* part) {
   const char* want = field == DMX_FIELD_GP ? "GP" : (field == DMX_FIELD_PL ? "PL" : nullptr);
   std::vector<Tok> cols, keys, alts;
   auto fail = [&](int64_t no, const std::string& why) { part->error = why; part->err_line = no; };
+  size_t slot = lo;
   for (size_t li = lo; li < hi; ++li) {
     const char *p = lines[li].p, *e = lines[li].e;
     split(p, e, '\t', &cols);
@@ -168,15 +198,15 @@ void parse_range(const std::vector<Line>& lines, size_t lo, size_t hi, int32_t f
     // n_allele = 1 + number of ALT alleles ("." = none)
     split(cols[4].p, cols[4].p + cols[4].n, ',', &alts);
     const bool no_alt = cols[4].n == 1 && cols[4].p[0] == '.';
-    const std::string chrom(cols[0].p, cols[0].n);
-    size_t chrom_id = v->chroms.size();
-    if (!v->chroms.empty() && v->chroms.back() == chrom) chrom_id = v->chroms.size() - 1;
+    size_t chrom_id = part->chroms.size();
+    auto is_chrom = [&](size_t c) { return part->chroms[c].size() == cols[0].n && memcmp(part->chroms[c].data(), cols[0].p, cols[0].n) == 0; };
+    if (!part->chroms.empty() && is_chrom(part->chroms.size() - 1)) chrom_id = part->chroms.size() - 1;
     else {
-      for (chrom_id = 0; chrom_id < v->chroms.size(); ++chrom_id)
-        if (v->chroms[chrom_id] == chrom) break;
-      if (chrom_id == v->chroms.size()) v->chroms.push_back(chrom);   // htslib adds an undeclared contig on sight
+      for (chrom_id = 0; chrom_id < part->chroms.size(); ++chrom_id)
+        if (is_chrom(chrom_id)) break;
+      if (chrom_id == part->chroms.size()) part->chroms.emplace_back(cols[0].p, cols[0].n);   // htslib adds an undeclared contig on sight
     }
-    if (no_alt || alts.size() != 1) { ++v->n_skipped; continue; }
+    if (no_alt || alts.size() != 1) { ++part->n_skipped; continue; }
     split(cols[8].p, cols[8].p + cols[8].n, ':', &keys);
     int i_gt = -1, i_f = -1;
     for (size_t k = 0; k < keys.size(); ++k) {
@@ -186,24 +216,24 @@ void parse_range(const std::vector<Line>& lines, size_t lo, size_t hi, int32_t f
     if (i_gt < 0) return fail(lines[li].no, "no GT in FORMAT (demuxlet's record filter needs it)");
     // a record without the requested key is an error in the reference only if it gets as far as parse_posteriors,
     // i.e. passes the genotype filter (cmd_cram_demuxlet.cpp:153,:211): flag it, the caller decides after the filter
-    v->no_field.push_back((uint8_t)(want && i_f < 0));
-    v->rid.push_back((int32_t)chrom_id);
-    v->pos.push_back(conv_int(cols[1].p, cols[1].p + cols[1].n) - 1);
-    v->ref.push_back(cols[3].n ? cols[3].p[0] : 'N');
-    v->alt.push_back(cols[4].n ? cols[4].p[0] : 'N');
-    const size_t g0 = v->gt.size();
-    v->gt.resize(g0 + nv * 2);
-    size_t f0 = 0;
-    if (field == DMX_FIELD_GP) { f0 = v->gp.size(); v->gp.resize(f0 + nv * 3); }
-    if (field == DMX_FIELD_PL) { f0 = v->pl.size(); v->pl.resize(f0 + nv * 3); }
+    v->no_field[slot] = (uint8_t)(want && i_f < 0);
+    v->rid[slot] = (int32_t)chrom_id;
+    v->pos[slot] = conv_int(cols[1].p, cols[1].p + cols[1].n) - 1;
+    v->ref[slot] = cols[3].n ? cols[3].p[0] : 'N';
+    v->alt[slot] = cols[4].n ? cols[4].p[0] : 'N';
+    int8_t* gt = &v->gt[slot * nv * 2];
+    float* gp = field == DMX_FIELD_GP ? &v->gp[slot * nv * 3] : nullptr;
+    int32_t* pl = field == DMX_FIELD_PL ? &v->pl[slot * nv * 3] : nullptr;
     for (size_t s = 0; s < nv; ++s) {
       const Tok& col = cols[9 + s];
-      parse_gt(subfield(col, i_gt), &v->gt[g0 + s * 2]);
+      parse_gt(subfield(col, i_gt), gt + s * 2);
       const Tok fcol = i_f >= 0 ? subfield(col, i_f) : Tok{col.p, 0};
-      if (field == DMX_FIELD_GP) parse_vec3<float>(fcol, &v->gp[f0 + s * 3], kNaN, conv_float);
-      if (field == DMX_FIELD_PL) parse_vec3<int32_t>(fcol, &v->pl[f0 + s * 3], std::numeric_limits<int32_t>::min(), conv_int);
+      if (gp) parse_vec3<float>(fcol, gp + s * 3, kNaN, conv_float);
+      if (pl) parse_vec3<int32_t>(fcol, pl + s * 3, std::numeric_limits<int32_t>::min(), conv_int);
     }
+    ++slot;
   }
+  part->n = slot - lo;
 }
 
 }  // namespace
@@ -213,8 +243,9 @@ extern "C" {
 int dmx_vcf_read(const char* path, int32_t field, dmx_vcf** out) {
   if (!path || !out || field < DMX_FIELD_GT || field > DMX_FIELD_PL) return DMX_E_INVALID;
   *out = nullptr;
+  const int nthreads = dmx_io::host_threads("DMX_VCF_THREADS");
   std::string text;
-  if (!slurp(path, &text)) {
+  if (!slurp(path, nthreads, &text)) {
     g_vcf_error = std::string("cannot read ") + path;
     return DMX_E_IO;
   }
@@ -272,42 +303,57 @@ int dmx_vcf_read(const char* path, int32_t field, dmx_vcf** out) {
     p = next;
   }
   if (!have_header) return fail(0, "no #CHROM line");
-  // pass 2: the records, contiguous line ranges on the host threads, merged in file order
-  const size_t nv = v->samples.size();
-  cpu_set_t cpus;                                   // the CPUs this process may run on (not the machine's)
-  size_t ncpu = std::thread::hardware_concurrency();
-  if (sched_getaffinity(0, sizeof(cpus), &cpus) == 0) ncpu = (size_t)CPU_COUNT(&cpus);
-  size_t nth = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(ncpu, 16), lines.size() / 256 + 1));
-  if (const char* env = getenv("DMX_VCF_THREADS")) nth = (size_t)std::max(1, std::min(atoi(env), 256));
+  // pass 2: the records, contiguous line ranges on the host threads, each range into its own slots of the arrays
+  const size_t nv = v->samples.size(), nl = lines.size();
+  const size_t nth = std::max<size_t>(1, std::min<size_t>((size_t)nthreads, nl / 256 + 1));
+  v->rid.resize(nl);
+  v->pos.resize(nl);
+  v->ref.resize(nl);
+  v->alt.resize(nl);
+  v->no_field.resize(nl);
+  v->gt.resize(nl * nv * 2);
+  if (field == DMX_FIELD_GP) v->gp.resize(nl * nv * 3);
+  if (field == DMX_FIELD_PL) v->pl.resize(nl * nv * 3);
   std::vector<Part> parts(nth);
-  std::vector<std::thread> th;
-  for (size_t t = 0; t < nth; ++t) {
-    const size_t lo = lines.size() * t / nth, hi = lines.size() * (t + 1) / nth;
-    if (t + 1 < nth) th.emplace_back(parse_range, std::cref(lines), lo, hi, field, nv, &parts[t]);
-    else parse_range(lines, lo, hi, field, nv, &parts[t]);
+  auto lo_of = [&](size_t t) { return nl * t / nth; };
+  {
+    dmx_io::Pool pool((int)nth);
+    pool.run((int)nth, [&](int t) { parse_range(lines, lo_of((size_t)t), lo_of((size_t)t + 1), field, nv, v, &parts[(size_t)t]); });
   }
-  for (auto& x : th) x.join();
   for (const Part& pt : parts)
     if (!pt.error.empty()) return fail(pt.err_line, pt.error);   // the first failing range = the first failing line
-  for (Part& pt : parts) {
-    std::vector<int32_t> remap(pt.v.chroms.size());
-    for (size_t c = 0; c < pt.v.chroms.size(); ++c) {
+  // merge in file order: chromosome ids by first appearance, ranges closed up over the slots of skipped records
+  size_t nrec = 0;
+  for (size_t t = 0; t < nth; ++t) {
+    const Part& pt = parts[t];
+    const size_t lo = lo_of(t);
+    std::vector<int32_t> remap(pt.chroms.size());
+    for (size_t c = 0; c < pt.chroms.size(); ++c) {
       size_t r = 0;
       for (; r < v->chroms.size(); ++r)
-        if (v->chroms[r] == pt.v.chroms[c]) break;
-      if (r == v->chroms.size()) v->chroms.push_back(pt.v.chroms[c]);
+        if (v->chroms[r] == pt.chroms[c]) break;
+      if (r == v->chroms.size()) v->chroms.push_back(pt.chroms[c]);
       remap[c] = (int32_t)r;
     }
-    for (int32_t r : pt.v.rid) v->rid.push_back(remap[(size_t)r]);
-    v->pos.insert(v->pos.end(), pt.v.pos.begin(), pt.v.pos.end());
-    v->ref.insert(v->ref.end(), pt.v.ref.begin(), pt.v.ref.end());
-    v->alt.insert(v->alt.end(), pt.v.alt.begin(), pt.v.alt.end());
-    v->no_field.insert(v->no_field.end(), pt.v.no_field.begin(), pt.v.no_field.end());
-    v->gt.insert(v->gt.end(), pt.v.gt.begin(), pt.v.gt.end());
-    v->gp.insert(v->gp.end(), pt.v.gp.begin(), pt.v.gp.end());
-    v->pl.insert(v->pl.end(), pt.v.pl.begin(), pt.v.pl.end());
-    v->n_skipped += pt.v.n_skipped;
+    for (size_t i = 0; i < pt.n; ++i) v->rid[lo + i] = remap[(size_t)v->rid[lo + i]];
+    if (nrec != lo && pt.n) {
+      auto close_up = [&](auto& vec, size_t per) {
+        if (!vec.empty()) memmove(vec.data() + nrec * per, vec.data() + lo * per, pt.n * per * sizeof(vec[0]));
+      };
+      close_up(v->rid, 1); close_up(v->pos, 1); close_up(v->ref, 1); close_up(v->alt, 1); close_up(v->no_field, 1);
+      close_up(v->gt, nv * 2); close_up(v->gp, nv * 3); close_up(v->pl, nv * 3);
+    }
+    nrec += pt.n;
+    v->n_skipped += pt.n_skipped;
   }
+  v->rid.resize(nrec);
+  v->pos.resize(nrec);
+  v->ref.resize(nrec);
+  v->alt.resize(nrec);
+  v->no_field.resize(nrec);
+  v->gt.resize(nrec * nv * 2);
+  if (field == DMX_FIELD_GP) v->gp.resize(nrec * nv * 3);
+  if (field == DMX_FIELD_PL) v->pl.resize(nrec * nv * 3);
   *out = v;
   return DMX_OK;
 }

@@ -34,6 +34,60 @@ def test_reader_matches_restatement(field, ext, bg, tmp_path):
     assert got["n_skipped"] > 0 and len(got["pos"]) > 300 and len(got["chroms"]) == 3
 
 
+@pytest.mark.parametrize("threads", ["1", "3", "16"])
+def test_bgzf_vcf_any_thread_count(threads, tmp_path, monkeypatch):
+    """a bgzipped VCF (BGZF blocks with the BC size field) is inflated block-parallel and its lines are parsed in
+    contiguous ranges on the host threads, straight into the arrays of the whole file: same records for any thread
+    count, skipped records closed up, chromosome ids by first appearance; python's gzip module reads the same text"""
+    monkeypatch.setenv("DMX_VCF_THREADS", threads)
+    rng = np.random.default_rng(17)
+    samples = ["S%02d" % i for i in range(5)]
+    recs = vcfio.random_records(rng, 1500, len(samples), "GP")
+    path = str(tmp_path / "a.vcf.gz")
+    vcfio.write_vcf(path, samples, recs, bgzf=True, contigs=("chrM", "chr2"))
+    got, want = api.read_vcf(path, "GP"), vcfio.parse_vcf(path, "GP")
+    same(got, want, "GP")
+    assert got["chroms"] == ["chrM", "chr2", "chr1", "chr3"] and got["n_skipped"] > 50
+    raw = bytearray(open(path, "rb").read())
+    raw[len(raw) // 2] ^= 0x55
+    (tmp_path / "bad.vcf.gz").write_bytes(bytes(raw))
+    with pytest.raises(api.DmxError):
+        api.read_vcf(str(tmp_path / "bad.vcf.gz"), "GP")
+
+
+def test_format_floats_are_strtod_narrowed(tmp_path):
+    """GP text -> float as htslib does it, (float)strtod(text): the reader's one-operation conversion of plain decimals
+    (mantissa < 2^53, |decimal exponent| <= 22) and its strtod fall-back give that bit pattern for every spelling"""
+    rng = np.random.default_rng(12)
+    texts = ["0", "-0", "1", "0.1", "0.3", ".5", "5.", "1e-3", "1E5", "2.5e+3", "1e22", "1e23", "1e-22", "1e-23", "1e-45", "3e-46",
+             "1e39", "-1e39", "inf", "-inf", "nan", "0.30000000000000004", "0.1234567890123456789", "123456789012345678",
+             "999999999999999", "9999999999999999", "16777217", "16777216.5", "0.000001", "1e", "1.5e+", "+4.25",
+             "3.4028235e38", "3.4028236e38", "1.17549435e-38", "7.006492321624085e-46", "8.5e-46", "1.00000006", "1.00000005960464"]
+    for _ in range(3000):
+        kind = rng.integers(0, 4)
+        if kind == 0:
+            texts.append("%.*f" % (int(rng.integers(0, 12)), rng.random() * 10 ** int(rng.integers(-3, 6))))
+        elif kind == 1:
+            texts.append("%.*g" % (int(rng.integers(1, 20)), rng.random() * 10.0 ** int(rng.integers(-30, 30))))
+        elif kind == 2:
+            texts.append("%.*e" % (int(rng.integers(0, 18)), rng.standard_normal() * 10.0 ** int(rng.integers(-45, 39))))
+        else:       # halfway cases of the float grid written with many digits
+            f = np.float32(rng.random() * 10.0 ** int(rng.integers(-10, 10)))
+            mid = (float(f) + float(np.nextafter(f, np.float32(np.inf)))) / 2
+            texts.append(repr(mid))
+    while len(texts) % 3:
+        texts.append("0.25")
+    recs = [("1", 10 + i, "A", "C", ["GT", "GP"], [{"GT": "0/1", "GP": ",".join(texts[3 * i:3 * i + 3])}])
+            for i in range(len(texts) // 3)]
+    path = str(tmp_path / "f.vcf")
+    vcfio.write_vcf(path, ["s"], recs)
+    got = api.read_vcf(path, "GP")["values"].reshape(-1)
+    with np.errstate(over="ignore"):
+        want = np.array([np.float32(float(t)) if t not in ("1e", "1.5e+") else np.float32(float(t.split("e")[0])) for t in texts], np.float32)
+    bad = [(t, g, w) for t, g, w in zip(texts, got, want) if g.view(np.uint32) != w.view(np.uint32) and not (np.isnan(g) and np.isnan(w))]
+    assert not bad, bad[:5]
+
+
 def test_sample_subset(tmp_path):
     """--sm / --sm-list: columns of the named samples in the byte order of their names (the reference's std::set)"""
     rng = np.random.default_rng(10)

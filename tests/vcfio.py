@@ -10,7 +10,7 @@ import numpy as np
 INT_MISSING = np.iinfo(np.int32).min
 
 
-def write_vcf(path, samples, records, bgzip_like=False, contigs=()):
+def write_vcf(path, samples, records, bgzip_like=False, contigs=(), bgzf=False):
     """records: list of (chrom, pos1, ref, alt, fmt_keys, [per-sample dict key -> text]); contigs: ##contig header lines"""
     lines = ["##fileformat=VCFv4.2", "##source=dmx-b200 tests"]
     for i, c in enumerate(contigs):
@@ -22,7 +22,13 @@ def write_vcf(path, samples, records, bgzip_like=False, contigs=()):
                                [":".join(c[k] for k in keys if k in c) for c in cols]))
     text = ("\n".join(lines) + "\n").encode()
     if path.endswith(".gz"):
-        if bgzip_like:      # several gzip members back to back, as bgzip writes them
+        if bgzf:            # real BGZF: blocks with the BC size field and the empty end-of-file block (SAM spec 4.1)
+            from tests.bamio import bgzf_block
+            with open(path, "wb") as f:
+                for i in range(0, len(text), 900):
+                    f.write(bgzf_block(text[i:i + 900]))
+                f.write(bgzf_block(b""))
+        elif bgzip_like:      # several gzip members back to back, as bgzip writes them
             with open(path, "wb") as f:
                 for i in range(0, len(text), 1500):
                     f.write(gzip.compress(text[i:i + 1500]))
@@ -76,7 +82,7 @@ def parse_vcf(path, field="GT"):
                     t = sub[i] if i < len(sub) else ""
                     parts = t.split(",")[:3] if t else []
                     if field == "GP":
-                        x = [np.float32(p) if p not in (".", "") else np.float32("nan") for p in parts]
+                        x = [np.float32(float(p)) if p not in (".", "") else np.float32("nan") for p in parts]   # (float)strtod, as htslib
                         x += [np.float32("nan")] * (3 - len(x))
                     else:
                         x = [int(p) if p not in (".", "") else INT_MISSING for p in parts]
