@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "dmx_last_error", "dmx_abi_version", "dmx_pack_reads", "dmx_pileup_sizes", "dmx_pileup_copy", "dmx_pileup_free",
     "dmx_build_gp", "dmx_build_gp_device", "dmx_set_field", "dmx_site_filter",
     "dmx_sweep_opts_default", "dmx_sweep_bam", "dmx_sweep_sizes", "dmx_sweep_counts", "dmx_sweep_copy", "dmx_sweep_barcode",
-    "dmx_sweep_free", "dmx_sweep_last_error", "dmx_vcf_read", "dmx_vcf_select", "dmx_vcf_sizes", "dmx_vcf_sample", "dmx_vcf_chrom", "dmx_vcf_copy", "dmx_vcf_no_field", "dmx_vcf_free", "dmx_vcf_last_error",
+    "dmx_sweep_free", "dmx_sweep_last_error", "dmx_vcf_read", "dmx_vcf_read_key", "dmx_vcf_select", "dmx_vcf_sizes", "dmx_vcf_sample", "dmx_vcf_chrom", "dmx_vcf_copy", "dmx_vcf_no_field", "dmx_vcf_free", "dmx_vcf_last_error",
 ]
 
 DMX_FIELD = {"GT": 0, "GP": 1, "PL": 2}            # --field (cmd_cram_demuxlet.cpp:28, :45)
@@ -204,13 +204,14 @@ def site_filter(gt, min_mac: int = 1, min_callrate: float = 0.5, device: int = 0
     return out.astype(bool)
 
 
-def read_vcf(path: str, field: str = "GT", samples: Optional[Sequence[str]] = None) -> dict:
+def read_vcf(path: str, field: str = "GT", samples: Optional[Sequence[str]] = None, key: Optional[str] = None) -> dict:
     """dmx_vcf_read: the biallelic records of a VCF (plain / gzip / bgzip) as the flat arrays site_filter / build_gp
     take.  Returns samples, chroms, rid, pos (0-based), ref, alt, gt int8[nrec][nv][2], values (GT: gt; GP float32;
     PL int32 [nrec][nv][3]), n_skipped, no_field (uint8[nrec]: the record's FORMAT lacks `field`; an error for the
-    reference only if the record passes site_filter, /root/reference/cmd_cram_demuxlet.cpp:153,:211)."""
+    reference only if the record passes site_filter, /root/reference/cmd_cram_demuxlet.cpp:153,:211).
+    key: FORMAT key to read as `field` (the reference treats any --field but GT / PL as posteriors like GP)."""
     lib = load_library()
-    lib.dmx_vcf_read.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_void_p)]
+    lib.dmx_vcf_read_key.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.POINTER(C.c_void_p)]
     lib.dmx_vcf_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                   C.POINTER(C.c_int32)]
     lib.dmx_vcf_sample.argtypes = [C.c_void_p, C.c_int32]
@@ -224,7 +225,7 @@ def read_vcf(path: str, field: str = "GT", samples: Optional[Sequence[str]] = No
     lib.dmx_vcf_last_error.restype = C.c_char_p
     code = DMX_FIELD[field]
     h = C.c_void_p()
-    rc = lib.dmx_vcf_read(os.fsencode(path), code, C.byref(h))
+    rc = lib.dmx_vcf_read_key(os.fsencode(path), code, key.encode() if key else None, C.byref(h))
     if rc != 0:
         raise DmxError(rc, "dmx_vcf_read", lib.dmx_vcf_last_error().decode())
     try:

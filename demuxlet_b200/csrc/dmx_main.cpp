@@ -154,6 +154,7 @@ void usage() {
           "                      build the genotype probabilities on the GPU from the flat FORMAT values in FILE\n"
           "                      (as demuxlet's --field / --geno-error do per VCF record) instead of the matrix in --plp\n"
           "  --vcf FILE [--field F] [--geno-error E] [--min-mac N] [--min-callrate R]\n"
+          "                      (F: GT, PL, or the name of a float FORMAT field with genotype posteriors, GP by default)\n"
           "                      the same from a VCF (plain / gzip / bgzip text; F defaults to GP): biallelic records that\n"
           "                      pass the genotype-count filter must be the SNPs of the pileup, in order\n"
           "  --sam FILE --vcf FILE   instead of --plp: pile the reads of a coordinate-sorted BAM up on the VCF's records\n"
@@ -247,21 +248,13 @@ int main(int argc, char** argv) {
   if (field_path) {
     load_field(field_path, &ff);
     static const char* const names[3] = {"GT", "GP", "PL"};
-    if (field && strcmp(field, names[ff.field]) != 0) die("--field %s does not match the field matrix (%s)", field, names[ff.field]);
-    if (ff.nv != p.nv || ff.nsnps != p.nsnps) die("Field matrix %s does not have the samples / SNPs of the pileup", field_path);
-    if (geno_error >= 0) ff.geno_error = geno_error;   // :46
-  }
-  if (vcf_path) {
-    // the VCF side of the reference's sweep (:142-231): records in file order, the genotype-count filter
-    // (--min-mac / --min-callrate, always on GT), the survivors are SNP ids 0, 1, ... of the pileup (scl.add_snp)
-    static const char* const names[3] = {"GT", "GP", "PL"};
     if (!field) field = "GP";                          // :9
-    ff.field = -1;
-    for (int f = 0; f < 3; ++f)
+    ff.field = DMX_FIELD_GP;                           // any other name is read as posteriors like GP
+    for (int f = 0; f < 3; ++f)                        // (parse_posteriors' last branch, bcf_filtered_reader.cpp:408)
       if (strcmp(field, names[f]) == 0) ff.field = f;
-    if (ff.field < 0) die("--field %s: only GT, GP and PL are known", field);
     dmx_vcf* v = nullptr;
-    if (dmx_vcf_read(vcf_path, ff.field, &v) != DMX_OK) die("Cannot read VCF: %s", dmx_vcf_last_error());
+    if (dmx_vcf_read_key(vcf_path, ff.field, ff.field == DMX_FIELD_GP ? field : nullptr, &v) != DMX_OK)
+      die("Cannot read VCF: %s", dmx_vcf_last_error());
     if (sm_list) {                                     // bcf_filtered_reader.cpp:95-101: first field of every line
       FILE* sf = fopen(sm_list, "r");
       if (!sf) die("Cannot open file %s for reading", sm_list);

@@ -186,8 +186,10 @@ struct Part {
   int64_t err_line = 0;
 };
 
-void parse_range(const std::vector<Line>& lines, size_t lo, size_t hi, int32_t field, size_t nv, dmx_vcf* v, Part* part) {
-  const char* want = field == DMX_FIELD_GP ? "GP" : (field == DMX_FIELD_PL ? "PL" : nullptr);
+void parse_range(const std::vector<Line>& lines, size_t lo, size_t hi, int32_t field, const char* key, size_t nv, dmx_vcf* v,
+                 Part* part) {
+  const char* want = field == DMX_FIELD_GT ? nullptr : key;
+  const size_t want_n = want ? strlen(want) : 0;
   std::vector<Tok> cols, keys, alts;
   auto fail = [&](int64_t no, const std::string& why) { part->error = why; part->err_line = no; };
   size_t slot = lo;
@@ -211,7 +213,7 @@ void parse_range(const std::vector<Line>& lines, size_t lo, size_t hi, int32_t f
     int i_gt = -1, i_f = -1;
     for (size_t k = 0; k < keys.size(); ++k) {
       if (keys[k].n == 2 && memcmp(keys[k].p, "GT", 2) == 0) i_gt = (int)k;
-      if (want && keys[k].n == 2 && memcmp(keys[k].p, want, 2) == 0) i_f = (int)k;
+      if (want && keys[k].n == want_n && memcmp(keys[k].p, want, want_n) == 0) i_f = (int)k;
     }
     if (i_gt < 0) return fail(lines[li].no, "no GT in FORMAT (demuxlet's record filter needs it)");
     // a record without the requested key is an error in the reference only if it gets as far as parse_posteriors,
@@ -241,7 +243,12 @@ void parse_range(const std::vector<Line>& lines, size_t lo, size_t hi, int32_t f
 extern "C" {
 
 int dmx_vcf_read(const char* path, int32_t field, dmx_vcf** out) {
+  return dmx_vcf_read_key(path, field, nullptr, out);
+}
+
+int dmx_vcf_read_key(const char* path, int32_t field, const char* key, dmx_vcf** out) {
   if (!path || !out || field < DMX_FIELD_GT || field > DMX_FIELD_PL) return DMX_E_INVALID;
+  if (!key || !key[0]) key = field == DMX_FIELD_PL ? "PL" : "GP";
   *out = nullptr;
   const int nthreads = dmx_io::host_threads("DMX_VCF_THREADS");
   std::string text;
@@ -318,7 +325,7 @@ int dmx_vcf_read(const char* path, int32_t field, dmx_vcf** out) {
   auto lo_of = [&](size_t t) { return nl * t / nth; };
   {
     dmx_io::Pool pool((int)nth);
-    pool.run((int)nth, [&](int t) { parse_range(lines, lo_of((size_t)t), lo_of((size_t)t + 1), field, nv, v, &parts[(size_t)t]); });
+    pool.run((int)nth, [&](int t) { parse_range(lines, lo_of((size_t)t), lo_of((size_t)t + 1), field, key, nv, v, &parts[(size_t)t]); });
   }
   for (const Part& pt : parts)
     if (!pt.error.empty()) return fail(pt.err_line, pt.error);   // the first failing range = the first failing line

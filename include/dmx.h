@@ -240,6 +240,9 @@ int dmx_site_filter(int32_t device, int32_t nv, int64_t nsnps, const int8_t* gt,
  * Missing values: GT -1, GP NaN, PL INT32_MIN.  All samples are selected. */
 typedef struct dmx_vcf dmx_vcf;
 int dmx_vcf_read(const char* path, int32_t field /* DMX_FIELD_*: which FORMAT key besides GT */, dmx_vcf** out);
+/* the same with the FORMAT key named: the reference reads ANY --field other than GT and PL as genotype posteriors
+ * like GP (parse_posteriors' last branch, bcf_filtered_reader.cpp:408-452): field = DMX_FIELD_GP, key = that name */
+int dmx_vcf_read_key(const char* path, int32_t field, const char* key /* null: "GP" / "PL" */, dmx_vcf** out);
 /* --sm / --sm-list (bcf_filtered_reader.cpp:95-121): keep only the named samples, in the byte-lexicographic order of
  * their names (the reference's std::set), duplicates merged; DMX_E_INVALID if a name is not in the header */
 int dmx_vcf_select(dmx_vcf* v, int32_t n, const char* const* names);

@@ -55,6 +55,22 @@ def test_bgzf_vcf_any_thread_count(threads, tmp_path, monkeypatch):
         api.read_vcf(str(tmp_path / "bad.vcf.gz"), "GP")
 
 
+def test_any_other_field_name_is_read_like_gp(tmp_path):
+    """the reference reads any --field other than GT and PL as posteriors like GP (parse_posteriors' last branch,
+    bcf_filtered_reader.cpp:408): dmx_vcf_read_key with the key named"""
+    rng = np.random.default_rng(23)
+    samples = ["a", "b", "c"]
+    recs = vcfio.random_records(rng, 200, len(samples), "GP")
+    renamed = [(c, p, r, a, [("POST" if k == "GP" else k) for k in keys], [{("POST" if k == "GP" else k): x for k, x in col.items()} for col in cols])
+               for c, p, r, a, keys, cols in recs]
+    pa, pb = str(tmp_path / "a.vcf"), str(tmp_path / "b.vcf")
+    vcfio.write_vcf(pa, samples, recs)
+    vcfio.write_vcf(pb, samples, renamed)
+    a, b = api.read_vcf(pa, "GP"), api.read_vcf(pb, "GP", key="POST")
+    assert np.array_equal(a["values"].view(np.uint32), b["values"].view(np.uint32)) and not b["no_field"].any()
+    assert api.read_vcf(pb, "GP")["no_field"].all()
+
+
 def test_format_floats_are_strtod_narrowed(tmp_path):
     """GP text -> float as htslib does it, (float)strtod(text): the reader's one-operation conversion of plain decimals
     (mantissa < 2^53, |decimal exponent| <= 22) and its strtod fall-back give that bit pattern for every spelling"""
