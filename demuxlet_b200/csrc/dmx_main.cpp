@@ -248,6 +248,14 @@ int main(int argc, char** argv) {
   if (field_path) {
     load_field(field_path, &ff);
     static const char* const names[3] = {"GT", "GP", "PL"};
+    if (field && strcmp(field, names[ff.field]) != 0) die("--field %s does not match the field matrix (%s)", field, names[ff.field]);
+    if (ff.nv != p.nv || ff.nsnps != p.nsnps) die("Field matrix %s does not have the samples / SNPs of the pileup", field_path);
+    if (geno_error >= 0) ff.geno_error = geno_error;   // :46
+  }
+  if (vcf_path) {
+    // the VCF side of the reference's sweep (:142-231): records in file order, the genotype-count filter
+    // (--min-mac / --min-callrate, always on GT), the survivors are SNP ids 0, 1, ... of the pileup (scl.add_snp)
+    static const char* const names[3] = {"GT", "GP", "PL"};
     if (!field) field = "GP";                          // :9
     ff.field = DMX_FIELD_GP;                           // any other name is read as posteriors like GP
     for (int f = 0; f < 3; ++f)                        // (parse_posteriors' last branch, bcf_filtered_reader.cpp:408)
