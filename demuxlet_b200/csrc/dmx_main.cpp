@@ -5,7 +5,7 @@
 // that program for the part that is in scope: it takes the finished pileup as a flat file (--plp, the .dmxp
 // container of demuxlet_b200/plp.py: GP matrix + CSR pileup + barcodes + sample ids, i.e. exactly what crosses the
 // C ABI) and calls dmx_set_gp / dmx_set_pileup / dmx_run / dmx_write_outputs.  --sam FILE --vcf FILE run the whole reference
-// command line through the library's own BGZF / BAM / VCF-text readers (no htslib: no CRAM / BCF).
+// command line through the library's own BGZF / BAM / VCF / BCF readers (no htslib: no CRAM).
 //
 //   dmx-demuxlet --plp in.dmxp --out prefix [--alpha A]... [--doublet-prior P] [--min-total N] [--min-uniq N]
 //                [--min-snp N] [--group-list FILE] [--write-pair] [--gpu D | --gpus N | --gpu-list a,b,..]
@@ -155,11 +155,11 @@ void usage() {
           "                      (as demuxlet's --field / --geno-error do per VCF record) instead of the matrix in --plp\n"
           "  --vcf FILE [--field F] [--geno-error E] [--min-mac N] [--min-callrate R]\n"
           "                      (F: GT, PL, or the name of a float FORMAT field with genotype posteriors, GP by default)\n"
-          "                      the same from a VCF (plain / gzip / bgzip text; F defaults to GP): biallelic records that\n"
+          "                      the same from a VCF (plain / gzip / bgzip text) or BCF (F defaults to GP): biallelic records that\n"
           "                      pass the genotype-count filter must be the SNPs of the pileup, in order\n"
           "  --sam FILE --vcf FILE   instead of --plp: pile the reads of a coordinate-sorted BAM up on the VCF's records\n"
           "                      [--tag-group CB] [--tag-UMI UB] [--min-MQ 20] [--excl-flag 0x0f04] [--min-BQ 13] [--cap-BQ 40]\n"
-          "                      [--min-TD 0] [--sm ID]... [--sm-list FILE]; own BGZF / BAM / VCF-text readers (no htslib; no CRAM / BCF)\n");
+          "                      [--min-TD 0] [--sm ID]... [--sm-list FILE]; own BGZF / BAM / VCF / BCF readers (no htslib; no CRAM)\n");
 }
 }  // namespace
 

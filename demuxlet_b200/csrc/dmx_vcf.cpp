@@ -3,8 +3,8 @@
 // The reference reads VCF / BCF records through htslib (BCFChunkedReader::read, /root/reference/bcf_chunked_reader.cpp:
 // 265-305: bcf_read / vcf_parse1) and asks the record for its FORMAT values with bcf_get_genotypes /
 // bcf_get_format_float / bcf_get_format_int32 (bcf_filtered_reader.cpp:194, :250, :408).  htslib is not in this image,
-// so this file parses the text form itself -- plain, gzip or bgzip (a bgzip file is a series of gzip members, which
-// zlib's gzread walks through) -- and delivers, for every record, what those accessors would:
+// so this file parses the text form itself -- plain, gzip or bgzip -- and the binary form, BCF2 (recognised by its magic
+// after decompression; section "BCF2" below), and delivers, for every record, what those accessors would:
 //   GT   two allele indices per sample as bcf_gt_allele() decodes them ("." -> -1, a haploid call "1" -> (1, -1):
 //        htslib pads it with bcf_int32_vector_end, which decodes to a negative allele)
 //   GP   three floats per sample, "." or a short vector -> NaN (htslib: bcf_float_missing / vector_end, both NaNs)
@@ -238,6 +238,164 @@ void parse_range(const std::vector<Line>& lines, size_t lo, size_t hi, int32_t f
   part->n = slot - lo;
 }
 
+
+// ---- BCF2 (the binary form of VCF, BGZF-compressed; VCF specification 6.3) ------------------------------------------
+// Header: "BCF\2\2", uint32 l_text, the VCF header text.  Strings are numbered by the header's dictionaries: FILTER /
+// INFO / FORMAT ids in order of appearance behind PASS = 0 (or their IDX=), contigs in order (or IDX=).  Record: uint32
+// l_shared, l_indiv; shared = CHROM, POS (0-based), rlen, QUAL, n_allele << 16 | n_info, n_fmt << 24 | n_sample, ID,
+// alleles, FILTER, INFO; indiv = per FORMAT key: typed int (dictionary index), type byte, n_sample x length values.
+// A typed value starts with a byte (length << 4 | type; length 15 = a typed int follows), types 1 / 2 / 3 = int8 / 16 /
+// 32, 5 = float, 7 = char; the smallest value of an int type is "missing", the next one "end of vector", as are the
+// float bit patterns 0x7F800001 / 0x7F800002.  What bcf_get_genotypes / bcf_get_format_float / bcf_get_format_int32
+// hand to the reference: alleles (x >> 1) - 1 (missing and padding negative), floats (missing / padding NaN), int32
+// (missing / padding INT32_MIN); a field stored with the wrong type is an error there (-2) -> flagged like a missing key.
+struct BcfRec { const uint8_t* p; int64_t no; };
+
+int bcf_type_size(int t) { return t == 1 ? 1 : (t == 2 ? 2 : (t == 3 || t == 5 ? 4 : (t == 7 ? 1 : 0))); }
+
+bool bcf_int(const uint8_t*& p, const uint8_t* e, int t, int64_t* out) {
+  const int sz = bcf_type_size(t);
+  if ((t != 1 && t != 2 && t != 3) || p + sz > e) return false;
+  if (t == 1) *out = (int8_t)p[0];
+  else if (t == 2) { int16_t x; memcpy(&x, p, 2); *out = x; }
+  else { int32_t x; memcpy(&x, p, 4); *out = x; }
+  p += sz;
+  return true;
+}
+
+bool bcf_typed(const uint8_t*& p, const uint8_t* e, int* type, int64_t* len) {
+  if (p >= e) return false;
+  const uint8_t b = *p++;
+  *type = b & 15;
+  *len = b >> 4;
+  if (*len == 15) {
+    if (p >= e) return false;
+    const int t2 = *p++ & 15;
+    if (!bcf_int(p, e, t2, len) || *len < 0) return false;
+  }
+  return true;
+}
+
+// one int of a vector of type t at q; missing / end of vector -> INT32_MIN
+inline int32_t bcf_vec_int(const uint8_t* q, int t) {
+  if (t == 1) { const int8_t x = (int8_t)q[0]; return x <= INT8_MIN + 1 ? INT32_MIN : x; }
+  if (t == 2) { int16_t x; memcpy(&x, q, 2); return x <= INT16_MIN + 1 ? INT32_MIN : x; }
+  int32_t x; memcpy(&x, q, 4); return x <= INT32_MIN + 1 ? INT32_MIN : x;
+}
+
+void parse_range_bcf(const std::vector<BcfRec>& recs, size_t lo, size_t hi, int32_t field, int64_t id_gt, int64_t id_key,
+                     size_t nv, size_t n_contig, dmx_vcf* v, Part* part) {
+  auto fail = [&](int64_t no, const std::string& why) { part->error = why; part->err_line = no; };
+  size_t slot = lo;
+  for (size_t ri = lo; ri < hi; ++ri) {
+    const uint8_t* r = recs[ri].p;
+    uint32_t l_shared, l_indiv;
+    memcpy(&l_shared, r, 4);
+    memcpy(&l_indiv, r + 4, 4);
+    const uint8_t *p = r + 8, *se = r + 8 + l_shared, *ie = se + l_indiv;
+    if (l_shared < 24) return fail(recs[ri].no, "corrupt BCF record");
+    int32_t chrom, pos;
+    uint32_t n_allele_info, n_fmt_sample;
+    memcpy(&chrom, p, 4);
+    memcpy(&pos, p + 4, 4);
+    memcpy(&n_allele_info, p + 16, 4);
+    memcpy(&n_fmt_sample, p + 20, 4);
+    p += 24;
+    const uint32_t n_allele = n_allele_info >> 16, n_fmt = n_fmt_sample >> 24, n_sample = n_fmt_sample & 0xffffffu;
+    if (chrom < 0 || (size_t)chrom >= n_contig) return fail(recs[ri].no, "CHROM is not in the header's contig dictionary");
+    if (n_allele != 2) { ++part->n_skipped; continue; }
+    if (n_sample != nv) return fail(recs[ri].no, "wrong number of samples");
+    int type;
+    int64_t len;
+    if (!bcf_typed(p, se, &type, &len) || p + len > se) return fail(recs[ri].no, "corrupt BCF record");   // ID
+    p += len;
+    char a0[2] = {'N', 'N'};
+    for (int a = 0; a < 2; ++a) {
+      if (!bcf_typed(p, se, &type, &len) || type != 7 || p + len > se) return fail(recs[ri].no, "corrupt BCF record");
+      if (len > 0) a0[a] = (char)p[0];
+      p += len;
+    }
+    // FORMAT fields
+    const uint8_t *gt_p = nullptr, *f_p = nullptr;
+    int gt_t = 0, f_t = 0;
+    int64_t gt_n = 0, f_n = 0;
+    p = se;
+    for (uint32_t f = 0; f < n_fmt; ++f) {
+      int kt;
+      int64_t kl, key;
+      if (!bcf_typed(p, ie, &kt, &kl) || kl != 1 || !bcf_int(p, ie, kt, &key)) return fail(recs[ri].no, "corrupt BCF record");
+      if (!bcf_typed(p, ie, &type, &len)) return fail(recs[ri].no, "corrupt BCF record");
+      const int64_t bytes = (int64_t)bcf_type_size(type) * len * (int64_t)nv;
+      if (p + bytes > ie) return fail(recs[ri].no, "corrupt BCF record");
+      if (key == id_gt) { gt_p = p; gt_t = type; gt_n = len; }
+      if (field != DMX_FIELD_GT && key == id_key) { f_p = p; f_t = type; f_n = len; }
+      p += bytes;
+    }
+    if (!gt_p || gt_t < 1 || gt_t > 3) return fail(recs[ri].no, "no GT in FORMAT (demuxlet's record filter needs it)");
+    const bool f_ok = field == DMX_FIELD_GT || (f_p && (field == DMX_FIELD_GP ? f_t == 5 : (f_t >= 1 && f_t <= 3)));
+    v->no_field[slot] = (uint8_t)!f_ok;
+    v->rid[slot] = chrom;
+    v->pos[slot] = pos;
+    v->ref[slot] = a0[0];
+    v->alt[slot] = a0[1];
+    int8_t* gt = &v->gt[slot * nv * 2];
+    float* gp = field == DMX_FIELD_GP ? &v->gp[slot * nv * 3] : nullptr;
+    int32_t* pl = field == DMX_FIELD_PL ? &v->pl[slot * nv * 3] : nullptr;
+    const int gsz = bcf_type_size(gt_t), fsz = bcf_type_size(f_t);
+    for (size_t s = 0; s < nv; ++s) {
+      for (int a = 0; a < 2; ++a) {
+        int32_t x = INT32_MIN;
+        if (a < gt_n) x = bcf_vec_int(gt_p + ((int64_t)s * gt_n + a) * gsz, gt_t);
+        const int32_t al = x == INT32_MIN ? -1 : (x >> 1) - 1;            // bcf_gt_allele
+        gt[s * 2 + a] = (int8_t)(al > 126 ? 126 : (al < -1 ? -1 : al));
+      }
+      if (gp)
+        for (int k = 0; k < 3; ++k) {
+          float x = kNaN;
+          if (f_ok && k < f_n) {
+            uint32_t bits;
+            memcpy(&bits, f_p + ((int64_t)s * f_n + k) * fsz, 4);
+            if (bits != 0x7F800001u && bits != 0x7F800002u) memcpy(&x, &bits, 4);
+          }
+          gp[s * 3 + k] = x;
+        }
+      if (pl)
+        for (int k = 0; k < 3; ++k)
+          pl[s * 3 + k] = (f_ok && k < f_n) ? bcf_vec_int(f_p + ((int64_t)s * f_n + k) * fsz, f_t) : INT32_MIN;
+    }
+    ++slot;
+  }
+  part->n = slot - lo;
+}
+
+// value of `key` inside the <...> of a header line (quoted values may hold commas)
+bool meta_value(const char* q, const char* e, const char* key, std::string* out) {
+  const size_t kn = strlen(key);
+  while (q < e) {
+    const char* k = q;
+    while (q < e && *q != '=' && *q != ',' && *q != '>') ++q;
+    const bool hit = (size_t)(q - k) == kn && memcmp(k, key, kn) == 0;
+    if (q < e && *q == '=') ++q;
+    const char* val = q;
+    if (q < e && *q == '"') { ++q; while (q < e && *q != '"') ++q; if (q < e) ++q; }
+    else while (q < e && *q != ',' && *q != '>') ++q;
+    if (hit && q > val) { out->assign(val, (size_t)(q - val)); return true; }
+    if (q < e && *q == '>') break;
+    if (q < e) ++q;
+  }
+  return false;
+}
+
+// registers `id` in a dictionary (header order, or at IDX=): htslib's bcf_hdr_register_hrec
+void dict_add(std::vector<std::string>* dict, const std::string& id, const char* q, const char* e) {
+  if (std::find(dict->begin(), dict->end(), id) != dict->end()) return;
+  std::string idx;
+  size_t at = dict->size();
+  if (meta_value(q, e, "IDX", &idx)) at = (size_t)std::max(0, atoi(idx.c_str()));
+  if (at >= dict->size()) dict->resize(at + 1);
+  (*dict)[at] = id;
+}
+
 }  // namespace
 
 extern "C" {
@@ -263,10 +421,21 @@ int dmx_vcf_read_key(const char* path, int32_t field, const char* key, dmx_vcf**
     delete v;
     return DMX_E_INVALID;
   };
-  // pass 1 (one thread): header, line index
+  // pass 1 (one thread): header (of the text, or the text inside a BCF file), line index
+  const bool is_bcf = text.size() >= 9 && memcmp(text.data(), "BCF\2\2", 5) == 0;
   std::vector<Line> lines;
+  std::vector<BcfRec> recs;
+  std::vector<std::string> ids(1, "PASS");            // BCF: the FILTER / INFO / FORMAT string dictionary
   std::vector<Tok> cols;
   const char *p = text.data(), *end = text.data() + text.size();
+  if (is_bcf) {
+    uint32_t l_text;
+    memcpy(&l_text, text.data() + 5, 4);
+    if ((size_t)l_text + 9 > text.size()) return fail(0, "truncated BCF header");
+    p = text.data() + 9;
+    end = p + l_text;
+    while (end > p && end[-1] == 0) --end;
+  }
   bool have_header = false;
   int64_t lineno = 0;
   while (p < end) {
@@ -277,25 +446,15 @@ int dmx_vcf_read_key(const char* path, int32_t field, const char* key, dmx_vcf**
     ++lineno;
     if (e > p) {
       if (*p == '#') {
+        std::string id;
         if (e - p > 13 && memcmp(p, "##contig=<", 10) == 0) {
           // the header's contig dictionary defines the chromosome ids (bcf_hdr_name2id, cmd_cram_demuxlet.cpp:197-199):
           // a read on a declared contig counts for its droplet even when no record of the file lies there
-          const char* q = p + 10;
-          while (q < e) {
-            const char* key = q;
-            while (q < e && *q != '=' && *q != ',' && *q != '>') ++q;
-            const bool is_id = q - key == 2 && key[0] == 'I' && key[1] == 'D';
-            if (q < e && *q == '=') ++q;
-            const char* val = q;
-            if (q < e && *q == '"') { ++q; while (q < e && *q != '"') ++q; if (q < e) ++q; }
-            else while (q < e && *q != ',' && *q != '>') ++q;
-            if (is_id && q > val) {
-              const std::string id(val, (size_t)(q - val));
-              if (std::find(v->chroms.begin(), v->chroms.end(), id) == v->chroms.end()) v->chroms.push_back(id);
-            }
-            if (q < e && (*q == ',' || *q == '>')) ++q;
-            if (q[-1] == '>') break;
-          }
+          if (meta_value(p + 10, e, "ID", &id)) dict_add(&v->chroms, id, p + 10, e);
+        } else if (is_bcf && ((e - p > 11 && memcmp(p, "##FORMAT=<", 10) == 0) || (e - p > 9 && memcmp(p, "##INFO=<", 8) == 0) ||
+                              (e - p > 11 && memcmp(p, "##FILTER=<", 10) == 0))) {
+          const char* q = (const char*)memchr(p, '<', (size_t)(e - p)) + 1;
+          if (meta_value(q, e, "ID", &id)) dict_add(&ids, id, q, e);
         } else if (e - p > 6 && memcmp(p, "#CHROM", 6) == 0) {
           split(p, e, '\t', &cols);
           if (cols.size() < 10) return fail(lineno, "no sample columns");
@@ -310,8 +469,29 @@ int dmx_vcf_read_key(const char* path, int32_t field, const char* key, dmx_vcf**
     p = next;
   }
   if (!have_header) return fail(0, "no #CHROM line");
+  int64_t id_gt = -1, id_key = -1;
+  if (is_bcf) {
+    if (!lines.empty()) return fail(0, "text records inside a BCF header");
+    for (size_t i = 0; i < ids.size(); ++i) {
+      if (ids[i] == "GT") id_gt = (int64_t)i;
+      if (ids[i] == key) id_key = (int64_t)i;
+    }
+    uint32_t l_text;
+    memcpy(&l_text, text.data() + 5, 4);
+    const uint8_t *q = (const uint8_t*)text.data() + 9 + l_text, *qe = (const uint8_t*)text.data() + text.size();
+    int64_t no = 0;
+    while (q < qe) {
+      uint32_t l_shared, l_indiv;
+      if (q + 8 > qe) return fail(no + 1, "truncated BCF record");
+      memcpy(&l_shared, q, 4);
+      memcpy(&l_indiv, q + 4, 4);
+      if ((uint64_t)l_shared + l_indiv + 8 > (uint64_t)(qe - q)) return fail(no + 1, "truncated BCF record");
+      recs.push_back(BcfRec{q, ++no});
+      q += 8 + (size_t)l_shared + l_indiv;
+    }
+  }
   // pass 2: the records, contiguous line ranges on the host threads, each range into its own slots of the arrays
-  const size_t nv = v->samples.size(), nl = lines.size();
+  const size_t nv = v->samples.size(), nl = is_bcf ? recs.size() : lines.size();
   const size_t nth = std::max<size_t>(1, std::min<size_t>((size_t)nthreads, nl / 256 + 1));
   v->rid.resize(nl);
   v->pos.resize(nl);
@@ -325,7 +505,11 @@ int dmx_vcf_read_key(const char* path, int32_t field, const char* key, dmx_vcf**
   auto lo_of = [&](size_t t) { return nl * t / nth; };
   {
     dmx_io::Pool pool((int)nth);
-    pool.run((int)nth, [&](int t) { parse_range(lines, lo_of((size_t)t), lo_of((size_t)t + 1), field, key, nv, v, &parts[(size_t)t]); });
+    const size_t n_contig = v->chroms.size();
+    pool.run((int)nth, [&](int t) {
+      if (is_bcf) parse_range_bcf(recs, lo_of((size_t)t), lo_of((size_t)t + 1), field, id_gt, id_key, nv, n_contig, v, &parts[(size_t)t]);
+      else parse_range(lines, lo_of((size_t)t), lo_of((size_t)t + 1), field, key, nv, v, &parts[(size_t)t]);
+    });
   }
   for (const Part& pt : parts)
     if (!pt.error.empty()) return fail(pt.err_line, pt.error);   // the first failing range = the first failing line
@@ -342,7 +526,8 @@ int dmx_vcf_read_key(const char* path, int32_t field, const char* key, dmx_vcf**
       if (r == v->chroms.size()) v->chroms.push_back(pt.chroms[c]);
       remap[c] = (int32_t)r;
     }
-    for (size_t i = 0; i < pt.n; ++i) v->rid[lo + i] = remap[(size_t)v->rid[lo + i]];
+    if (!is_bcf)       // a BCF record carries the index into the header's contig dictionary itself
+      for (size_t i = 0; i < pt.n; ++i) v->rid[lo + i] = remap[(size_t)v->rid[lo + i]];
     if (nrec != lo && pt.n) {
       auto close_up = [&](auto& vec, size_t per) {
         if (!vec.empty()) memmove(vec.data() + nrec * per, vec.data() + lo * per, pt.n * per * sizeof(vec[0]));

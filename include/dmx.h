@@ -232,8 +232,8 @@ int dmx_set_field(dmx_ctx* ctx, int32_t field, const void* in, int64_t nsnps, do
 int dmx_site_filter(int32_t device, int32_t nv, int64_t nsnps, const int8_t* gt, int32_t min_mac, double min_callrate,
                     uint8_t* pass_out);
 
-/* ---- VCF text reader (host only, no htslib; SURVEY 8f N4, VCF half) ---------------------------------------------
- * Reads a VCF (plain, gzip or bgzip) and delivers per biallelic record what the reference obtains from htslib's
+/* ---- VCF / BCF reader (host only, no htslib; SURVEY 8f N4, VCF half) --------------------------------------------
+ * Reads a VCF (plain, gzip or bgzip text) or a BCF2 file and delivers per biallelic record what the reference obtains from htslib's
  * bcf_read / vcf_parse1 (bcf_chunked_reader.cpp:265-305) and bcf_get_genotypes / bcf_get_format_float /
  * bcf_get_format_int32 (bcf_filtered_reader.cpp:194, :250, :408): the arrays dmx_site_filter and dmx_build_gp take.
  * Records with an allele count other than 2 are skipped and counted (maxAlleles = 2, cmd_cram_demuxlet.cpp:26).

@@ -71,6 +71,35 @@ def test_any_other_field_name_is_read_like_gp(tmp_path):
     assert api.read_vcf(pb, "GP")["no_field"].all()
 
 
+@pytest.mark.parametrize("field", ["GT", "GP", "PL"])
+@pytest.mark.parametrize("int_type,idx", [(0, False), (3, True)])
+def test_bcf_gives_the_arrays_of_its_vcf_text(field, int_type, idx, tmp_path):
+    """--vcf takes VCF or BCF in the reference (htslib opens either): the BCF2 reader delivers, record by record, the
+    arrays the text reader delivers for the same records -- GT with missing / haploid / phased calls, GP / PL with
+    missing values and short vectors, int8 / int16 / int32 vectors, multi-allelic and ALT-less records skipped,
+    dictionary numbering by appearance or by IDX=.  (The writer is tests/vcfio.py:write_bcf, from the specification:
+    unpinned against htslib, like the text reader.)"""
+    rng = np.random.default_rng(29)
+    samples = ["S%02d" % i for i in range(7)]
+    recs = vcfio.random_records(rng, 700, len(samples), field)
+    contigs = ["chrM", "chr1", "chr2", "chr3"]
+    pt, pb = str(tmp_path / "a.vcf"), str(tmp_path / "a.bcf")
+    vcfio.write_vcf(pt, samples, recs, contigs=contigs)
+    vcfio.write_bcf(pb, samples, recs, contigs, int_type=int_type, idx=idx)
+    a, b = api.read_vcf(pt, field), api.read_vcf(pb, field)
+    same(b, a, field)
+    assert a["chroms"] == b["chroms"] == contigs and b["n_skipped"] == a["n_skipped"] > 0 and len(b["pos"]) > 500
+    assert not b["no_field"].any()
+    if field != "GT":      # the other field is not in these records: flagged, values missing
+        other = "PL" if field == "GP" else "GP"
+        c = api.read_vcf(pb, other)
+        assert c["no_field"].all() and np.array_equal(c["gt"], a["gt"])
+    raw = open(pb, "rb").read()
+    (tmp_path / "cut.bcf").write_bytes(raw[:len(raw) // 2])
+    with pytest.raises(api.DmxError):
+        api.read_vcf(str(tmp_path / "cut.bcf"), field)
+
+
 def test_format_floats_are_strtod_narrowed(tmp_path):
     """GP text -> float as htslib does it, (float)strtod(text): the reader's one-operation conversion of plain decimals
     (mantissa < 2^53, |decimal exponent| <= 22) and its strtod fall-back give that bit pattern for every spelling"""

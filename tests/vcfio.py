@@ -143,3 +143,110 @@ def random_records(rng, nrec, nv, field):
             cols.append(c)
         recs.append((chrom, 1000 + 17 * r, "ACGT"[r % 4] + ("A" if r % 50 == 7 else ""), alt, keys, cols))
     return recs
+
+
+# ---- BCF2 writer (VCF specification 6.3), for the reader's tests ----------------------------------------------------
+import struct as _struct
+
+_INT_MISSING = {1: -128, 2: -32768, 3: -2147483648}
+_FLOAT_MISSING, _FLOAT_END = 0x7F800001, 0x7F800002
+
+
+def _typed_header(t, n):
+    if n < 15:
+        return bytes([(n << 4) | t])
+    return bytes([0xF0 | t]) + _typed_int(n)
+
+
+def _int_type(vals):
+    lo, hi = (min(vals), max(vals)) if vals else (0, 0)
+    if lo >= -120 and hi <= 127:
+        return 1
+    if lo >= -32760 and hi <= 32767:
+        return 2
+    return 3
+
+
+def _typed_int(x):
+    t = _int_type([x])
+    return bytes([0x10 | t]) + _struct.pack("<" + "bhi"[t - 1], x)
+
+
+def _typed_str(txt):
+    b = txt.encode()
+    return _typed_header(7, len(b)) + b
+
+
+def write_bcf(path, samples, records, contigs, int_type=0, idx=False):
+    """the records of write_vcf as a BCF2 file (BGZF blocks).  contigs: every chromosome, in dictionary order (BCF needs
+    them declared).  int_type 1 / 2 / 3 forces the width of the PL / DP vectors (0: smallest that fits, like htslib);
+    idx=True writes IDX= into the header lines, in an order different from their appearance."""
+    from tests.bamio import bgzf_block
+    fmt_ids = ["GT", "DP", "GP", "PL"]
+    ids = ["PASS"] + fmt_ids
+    order = list(range(len(fmt_ids)))
+    if idx:
+        order = order[::-1]                      # header lines in reverse, IDX keeps the numbering
+    lines = ["##fileformat=VCFv4.2", '##FILTER=<ID=PASS,Description="All filters passed"%s>' % (",IDX=0" if idx else "")]
+    for i, c in enumerate(contigs):
+        lines.append("##contig=<ID=%s,length=%d%s>" % (c, 1000000 + i, (",IDX=%d" % i) if idx else ""))
+    types = {"GT": ("1", "String"), "DP": ("1", "Integer"), "GP": ("G", "Float"), "PL": ("G", "Integer")}
+    for k in order:
+        f = fmt_ids[k]
+        lines.append('##FORMAT=<ID=%s,Number=%s,Type=%s,Description="x, y"%s>' % (f, types[f][0], types[f][1],
+                                                                                    (",IDX=%d" % (k + 1)) if idx else ""))
+    lines.append("\t".join(["#CHROM", "POS", "ID", "REF", "ALT", "QUAL", "FILTER", "INFO", "FORMAT"] + list(samples)))
+    text = ("\n".join(lines) + "\n").encode() + b"\0"
+    out = bytearray(b"BCF\2\2" + _struct.pack("<I", len(text)) + text)
+    for chrom, pos1, ref, alt, keys, cols in records:
+        alleles = [ref] + ([] if alt == "." else alt.split(","))
+        shared = bytearray(_struct.pack("<iiifII", contigs.index(chrom), pos1 - 1, len(ref), float("nan"),
+                                        (len(alleles) << 16) | 0, (len(keys) << 24) | len(samples)))
+        _struct.pack_into("<I", shared, 12, 0x7F800001)          # QUAL missing
+        shared += _typed_str(".")                                 # ID
+        for a in alleles:
+            shared += _typed_str(a)
+        shared += _typed_header(1, 1) + _struct.pack("<b", 0)     # FILTER = PASS
+        indiv = bytearray()
+        for k in keys:
+            indiv += _typed_int(ids.index(k))
+            if k == "GT":
+                rows = []
+                for c in cols:
+                    t = c["GT"]
+                    vals, phased = [], 0
+                    for ch in t.replace("|", "/|").split("/"):      # keeps the separator in front of a phased allele
+                        ph = ch.startswith("|")
+                        a = ch.lstrip("|")
+                        vals.append((0 if a in (".", "") else (int(a) + 1) << 1) | (1 if ph else 0))
+                    rows.append(vals[:2])
+                width = max(len(r) for r in rows)
+                indiv += _typed_header(1, width)
+                for r in rows:
+                    indiv += _struct.pack("<%db" % width, *(r + [-127] * (width - len(r))))
+            elif k == "GP":
+                rows = []
+                for c in cols:
+                    parts = [] if c["GP"] == "." else c["GP"].split(",")
+                    vals = [_FLOAT_MISSING if x == "." else _struct.unpack("<I", _struct.pack("<f", float(x)))[0] for x in parts]
+                    rows.append(vals or [_FLOAT_MISSING])
+                width = max(len(r) for r in rows)
+                indiv += _typed_header(5, width)
+                for r in rows:
+                    indiv += _struct.pack("<%dI" % width, *(r + [_FLOAT_END] * (width - len(r))))
+            else:                                                  # DP, PL
+                rows = []
+                for c in cols:
+                    parts = [] if c[k] == "." else c[k].split(",")
+                    rows.append([None if x == "." else int(x) for x in parts] or [None])
+                width = max(len(r) for r in rows)
+                t = int_type or _int_type([x for r in rows for x in r if x is not None])
+                indiv += _typed_header(t, width)
+                for r in rows:
+                    vals = [(_INT_MISSING[t] if x is None else x) for x in r] + [_INT_MISSING[t] + 1] * (width - len(r))
+                    indiv += _struct.pack("<%d%s" % (width, "bhi"[t - 1]), *vals)
+        out += _struct.pack("<II", len(shared), len(indiv)) + shared + indiv
+    with open(path, "wb") as f:
+        for i in range(0, len(out), 60000):
+            f.write(bgzf_block(bytes(out[i:i + 60000])))
+        f.write(bgzf_block(b""))
