@@ -29,7 +29,8 @@
 // cases above), the chunk is walked again with the exact buffer state.  Barcode ids are assigned per chunk and merged in
 // file order, so that ids, tuples and counts do not depend on the number of threads.  Any other gzip file (or a plain
 // one) is read through zlib's gzread and walked the same way.
-// Not handled: CRAM, SAM text.  --tag-UMI "" reproduces the reference's unseeded rand() UMIs (one walking
+// SAM text (with its @SQ header; plain, gzip or bgzip) is read too: every line becomes the BAM record sam_parse1 would
+// build of it, on the walking threads.  Not handled: CRAM.  --tag-UMI "" reproduces the reference's unseeded rand() UMIs (one walking
 // thread).  The BAM must be coordinate-sorted, as for the reference.  Parity: the checker is the python restatement in
 // tests/bamio.py (a literal transcription of the buffer loop) on generated BAM files; the CIGAR look-up is pinned on
 // the reference's own function (oracle/ref_cigar) -- BGZF / BAM decoding itself is "parity unpinned" against htslib.
@@ -312,6 +313,129 @@ void walk_chunk(const Sweep& S, const uint8_t* win, const size_t* offs, size_t r
   }
 }
 
+
+// One SAM text line as the BAM record htslib's sam_parse1 would build of it (SAM spec 1.4 -> 4.2), appended to *out with
+// its block_size in front: the walker then reads text and binary input alike.  Mate fields are not needed (-1 / 0).
+bool sam_to_bam(const char* p, const char* e, const std::unordered_map<std::string_view, int32_t>& name2tid,
+                std::vector<uint8_t>* out) {
+  static const char kOps[] = "MIDNSHP=X";
+  const char* f[12];
+  size_t n[12];
+  int nf = 0;
+  const char* s = p;
+  for (const char* q = p; q <= e && nf < 11; ++q)
+    if (q == e || *q == '\t') { f[nf] = s; n[nf] = (size_t)(q - s); ++nf; s = q + 1; }
+  if (nf < 11) return false;
+  const char* tags = s <= e ? s : e;            // behind the 11th field
+  auto num = [](const char* a, size_t len) {
+    long v = 0;
+    size_t i = (len && a[0] == '-') ? 1 : 0;
+    for (; i < len && a[i] >= '0' && a[i] <= '9'; ++i) v = v * 10 + (a[i] - '0');
+    return (len && a[0] == '-') ? -v : v;
+  };
+  if (n[0] == 0 || n[0] > 254) return false;
+  int32_t tid = -1;
+  if (!(n[2] == 1 && f[2][0] == '*')) {
+    auto it = name2tid.find(std::string_view(f[2], n[2]));
+    if (it != name2tid.end()) tid = it->second;
+  }
+  const size_t at = out->size();
+  out->resize(at + 36 + n[0] + 1);
+  uint8_t* b = out->data() + at + 4;
+  const int32_t pos = (int32_t)num(f[3], n[3]) - 1, l_seq = (n[9] == 1 && f[9][0] == '*') ? 0 : (int32_t)n[9];
+  const int32_t m1 = -1, zero = 0;
+  memcpy(b, &tid, 4);
+  memcpy(b + 4, &pos, 4);
+  b[8] = (uint8_t)(n[0] + 1);
+  b[9] = (uint8_t)num(f[4], n[4]);
+  b[10] = b[11] = 0;                              // bin: not used
+  const uint16_t flag = (uint16_t)num(f[1], n[1]);
+  memcpy(b + 14, &flag, 2);
+  memcpy(b + 16, &l_seq, 4);
+  memcpy(b + 20, &m1, 4);
+  memcpy(b + 24, &m1, 4);
+  memcpy(b + 28, &zero, 4);
+  memcpy(b + 32, f[0], n[0]);
+  b[32 + n[0]] = 0;
+  uint32_t n_cigar = 0;
+  if (!(n[5] == 1 && f[5][0] == '*')) {
+    const char *c = f[5], *ce = f[5] + n[5];
+    while (c < ce) {
+      uint32_t len = 0;
+      bool any = false;
+      while (c < ce && *c >= '0' && *c <= '9') { len = len * 10 + (uint32_t)(*c - '0'); ++c; any = true; }
+      const char* op = c < ce ? strchr(kOps, *c) : nullptr;
+      if (!any || !op || !*c) return false;
+      const uint32_t v = (len << 4) | (uint32_t)(op - kOps);
+      out->insert(out->end(), (const uint8_t*)&v, (const uint8_t*)&v + 4);
+      ++n_cigar;
+      ++c;
+    }
+    if (n_cigar > 65535) return false;
+  }
+  {
+    const uint16_t nc = (uint16_t)n_cigar;
+    memcpy(out->data() + at + 4 + 12, &nc, 2);
+  }
+  // sequence (4 bits per base) and qualities
+  const size_t sq = out->size();
+  out->resize(sq + ((size_t)l_seq + 1) / 2 + (size_t)l_seq);
+  uint8_t* q4 = out->data() + sq;
+  memset(q4, 0, ((size_t)l_seq + 1) / 2);
+  for (int32_t i = 0; i < l_seq; ++i) {
+    static const char kBase[] = "=ACMGRSVTWYHKDBN";
+    const char ch = f[9][i] >= 'a' && f[9][i] <= 'z' ? (char)(f[9][i] - 32) : f[9][i];
+    const char* w = strchr(kBase, ch);
+    const uint8_t code = (w && ch) ? (uint8_t)(w - kBase) : 15;
+    q4[i >> 1] |= (uint8_t)(code << ((~i & 1) << 2));
+  }
+  uint8_t* ql = q4 + ((size_t)l_seq + 1) / 2;
+  if (n[10] == 1 && f[10][0] == '*') memset(ql, 0xff, (size_t)l_seq);
+  else {
+    if ((int32_t)n[10] != l_seq) return false;
+    for (int32_t i = 0; i < l_seq; ++i) ql[i] = (uint8_t)(f[10][i] - 33);
+  }
+  // tags TAG:TYPE:VALUE
+  for (const char* t = tags; t < e;) {
+    const char* te = (const char*)memchr(t, '\t', (size_t)(e - t));
+    if (!te) te = e;
+    if (te - t >= 5 && t[2] == ':' && t[4] == ':') {
+      const char ty = t[3];
+      const char *val = t + 5;
+      const size_t vl = (size_t)(te - val);
+      out->push_back((uint8_t)t[0]);
+      out->push_back((uint8_t)t[1]);
+      if (ty == 'A') { out->push_back('A'); out->push_back(vl ? (uint8_t)val[0] : 0); }
+      else if (ty == 'i') { const int32_t v = (int32_t)num(val, vl); out->push_back('i'); out->insert(out->end(), (const uint8_t*)&v, (const uint8_t*)&v + 4); }
+      else if (ty == 'f') { const float v = strtof(std::string(val, vl).c_str(), nullptr); out->push_back('f'); out->insert(out->end(), (const uint8_t*)&v, (const uint8_t*)&v + 4); }
+      else if (ty == 'Z' || ty == 'H') { out->push_back((uint8_t)ty); out->insert(out->end(), val, val + vl); out->push_back(0); }
+      else if (ty == 'B' && vl >= 1) {
+        const char st = val[0];
+        const size_t es = (st == 'c' || st == 'C') ? 1 : ((st == 's' || st == 'S') ? 2 : 4);
+        out->push_back('B');
+        out->push_back((uint8_t)st);
+        const size_t cnt_at = out->size();
+        out->resize(cnt_at + 4);
+        uint32_t cnt = 0;
+        for (const char* c = val + 1; c < te;) {
+          if (*c == ',') ++c;
+          const char* ce = (const char*)memchr(c, ',', (size_t)(te - c));
+          if (!ce) ce = te;
+          if (st == 'f') { const float v = strtof(std::string(c, (size_t)(ce - c)).c_str(), nullptr); out->insert(out->end(), (const uint8_t*)&v, (const uint8_t*)&v + 4); }
+          else { const int32_t v = (int32_t)num(c, (size_t)(ce - c)); out->insert(out->end(), (const uint8_t*)&v, (const uint8_t*)&v + es); }
+          ++cnt;
+          c = ce;
+        }
+        memcpy(out->data() + cnt_at, &cnt, 4);
+      } else return false;
+    } else if (te > t) return false;
+    t = te + 1;
+  }
+  const int32_t block = (int32_t)(out->size() - at - 4);
+  memcpy(out->data() + at, &block, 4);
+  return true;
+}
+
 }  // namespace
 
 extern "C" {
@@ -385,29 +509,65 @@ int dmx_sweep_bam(const char* path, const dmx_sweep_opts* o, int32_t n_chrom, co
     }
     return true;
   };
-  if (!need(8) || memcmp(gz.data() + cur, "BAM\1", 4) != 0) {
+  // BAM, or SAM text with its header (recognised by the leading '@')
+  const bool is_sam = need(1) && gz.data()[cur] == '@';
+  if (!is_sam && (!need(8) || memcmp(gz.data() + cur, "BAM\1", 4) != 0)) {
     g_bam_error = std::string(path) + " is not a BAM file";
     return DMX_E_INVALID;
   }
-  const size_t l_text = (size_t)std::max(0, rd_i32(gz.data() + cur + 4));
-  cur += 8;
-  if (!need(l_text + 4)) { g_bam_error = "truncated BAM header"; return DMX_E_INVALID; }
-  cur += l_text;
-  S.n_ref = rd_i32(gz.data() + cur);
-  cur += 4;
-  // BAM tid -> VCF rid by name (bcf_hdr_name2id, :197); the reference insists on the same chromosome order (:160-176)
+  std::vector<std::string> ref_names;
+  if (is_sam) {
+    // header lines: @SQ SN:name in order are the reference ids (sam_hdr_parse)
+    for (;;) {
+      while (!memchr(gz.data() + cur, '\n', gz.size() - cur)) {
+        const bool got = gz.more(cur);
+        cur = 0;
+        if (!got) break;
+      }
+      if (gz.size() == cur || gz.data()[cur] != '@') break;
+      const char* lp = (const char*)gz.data() + cur;
+      const char* nl = (const char*)memchr(lp, '\n', gz.size() - cur);
+      const char* le = nl ? nl : (const char*)gz.data() + gz.size();
+      if (le - lp > 4 && memcmp(lp, "@SQ\t", 4) == 0) {
+        for (const char* q = lp + 4; q < le;) {
+          const char* qe = (const char*)memchr(q, '\t', (size_t)(le - q));
+          if (!qe) qe = le;
+          if (qe - q > 3 && memcmp(q, "SN:", 3) == 0) {
+            const char* ve = qe;
+            while (ve > q + 3 && (ve[-1] == '\r')) --ve;
+            ref_names.emplace_back(q + 3, (size_t)(ve - q - 3));
+          }
+          q = qe + 1;
+        }
+      }
+      cur = (size_t)(le - (const char*)gz.data()) + (nl ? 1 : 0);
+    }
+    S.n_ref = (int32_t)ref_names.size();
+  } else {
+    const size_t l_text = (size_t)std::max(0, rd_i32(gz.data() + cur + 4));
+    cur += 8;
+    if (!need(l_text + 4)) { g_bam_error = "truncated BAM header"; return DMX_E_INVALID; }
+    cur += l_text;
+    S.n_ref = rd_i32(gz.data() + cur);
+    cur += 4;
+    for (int32_t t = 0; t < S.n_ref; ++t) {
+      if (!need(4)) { g_bam_error = "truncated BAM header"; return DMX_E_INVALID; }
+      const int32_t l = rd_i32(gz.data() + cur);
+      cur += 4;
+      if (l < 1 || !need((size_t)l + 4)) { g_bam_error = "truncated BAM header"; return DMX_E_INVALID; }
+      ref_names.emplace_back((const char*)gz.data() + cur, strnlen((const char*)gz.data() + cur, (size_t)l));
+      cur += (size_t)l + 4;
+    }
+  }
+  // tid -> VCF rid by name (bcf_hdr_name2id, :197); the reference insists on the same chromosome order (:160-176)
   std::unordered_map<std::string, int32_t> name2rid;
   for (int32_t r = 0; r < n_chrom; ++r) name2rid[chroms[r]] = r;
   S.tid2rid.assign((size_t)std::max(0, S.n_ref), -1);
+  std::unordered_map<std::string_view, int32_t> name2tid;       // SAM text: RNAME -> tid
   int32_t prev = -1;
   for (int32_t t = 0; t < S.n_ref; ++t) {
-    if (!need(4)) { g_bam_error = "truncated BAM header"; return DMX_E_INVALID; }
-    const int32_t l = rd_i32(gz.data() + cur);
-    cur += 4;
-    if (l < 1 || !need((size_t)l + 4)) { g_bam_error = "truncated BAM header"; return DMX_E_INVALID; }
-    const std::string nm((const char*)gz.data() + cur, strnlen((const char*)gz.data() + cur, (size_t)l));
-    cur += (size_t)l + 4;
-    auto it = name2rid.find(nm);
+    name2tid.emplace(std::string_view(ref_names[(size_t)t]), t);
+    auto it = name2rid.find(ref_names[(size_t)t]);
     if (it != name2rid.end()) {
       if (prev >= it->second) {
         g_bam_error = "VCF and BAM have different orderings of chromosomes";   // :166-169
@@ -435,34 +595,24 @@ int dmx_sweep_bam(const char* path, const dmx_sweep_opts* o, int32_t n_chrom, co
     delete sw;
     return DMX_E_INVALID;
   };
-  for (;;) {
-    // complete records of the window
-    offs.clear();
-    const uint8_t* win = gz.data();
-    const size_t wsize = gz.size();
-    size_t p = cur;
-    while (p + 4 <= wsize) {
-      const int32_t block = rd_i32(win + p);
-      if (block < 32) return fail("corrupt BAM record");
-      if (p + 4 + (size_t)block > wsize) break;
-      offs.push_back(p);
-      p += 4 + (size_t)block;
-    }
-    const size_t nrec = offs.size();
+  // One batch of records: walked in contiguous chunks on the host threads (walk(lo, hi, exact, out) walks records
+  // [lo, hi) of the batch), merged in file order, scattered into the output arrays.
+  using WalkFn = std::function<void(int, size_t, size_t, BufState*, ChunkOut*)>;
+  auto run_batch = [&](size_t nrec, const WalkFn& walk) -> bool {
     sw->n_records += (int64_t)nrec;
     const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)nth, nrec / min_chunk));
     auto lo_of = [&](int t) { return nrec * (size_t)t / (size_t)nt; };
     if (S.random_umi) {
-      walk_chunk(S, win, offs.data(), 0, nrec, &buf, &rnd_buf, &chunks[0]);
+      walk(0, 0, nrec, &buf, &chunks[0]);
     } else {
-      pool.run(nt, [&](int t) { walk_chunk(S, win, offs.data(), lo_of(t), lo_of(t + 1), nullptr, nullptr, &chunks[(size_t)t]); });
+      pool.run(nt, [&](int t) { walk(t, lo_of(t), lo_of(t + 1), nullptr, &chunks[(size_t)t]); });
     }
     // in file order: buffer recurrence (exact second walk where a read sees more than its own span), barcode ids
     size_t total = sw->cell.size(), umi_total = sw->umi_buf.size();
     std::vector<size_t> at((size_t)nt + 1), umi_at((size_t)nt + 1);
     for (int t = 0; t < nt; ++t) {
       ChunkOut& c = chunks[(size_t)t];
-      if (c.corrupt) return fail("corrupt BAM record");
+      if (c.corrupt) return false;
       if (!S.random_umi) {
         BufState b = buf;
         bool redo = false;
@@ -471,7 +621,7 @@ int dmx_sweep_bam(const char* path, const dmx_sweep_opts* o, int32_t n_chrom, co
           if (needs_exact(S, k, b)) { redo = true; break; }
         }
         if (redo) {
-          walk_chunk(S, win, offs.data(), lo_of(t), lo_of(t + 1), &buf, nullptr, &c);
+          walk(t, lo_of(t), lo_of(t + 1), &buf, &c);
         } else {
           buf = b;
         }
@@ -527,12 +677,79 @@ int dmx_sweep_bam(const char* path, const dmx_sweep_opts* o, int32_t n_chrom, co
       }
       for (size_t i = 0; i < n; ++i) sw->umi_off[a + i + 1] = (int64_t)umi_at[(size_t)t] + c.umi_end[i];
     });
-    // next window
-    const bool got = gz.more(p);
-    cur = 0;
-    if (!got) {
-      if (gz.bad() || gz.size() > 0) return fail("truncated BAM record");
-      break;
+    return true;
+  };
+  if (is_sam) {
+    // text: the complete lines of the window; every walking thread first turns its lines into BAM records
+    struct TLine { const char *p, *e; };
+    std::vector<TLine> tl;
+    std::vector<std::vector<uint8_t>> rec_buf((size_t)nth);
+    std::vector<std::vector<size_t>> rec_off((size_t)nth);
+    for (bool last = false; !last;) {
+      tl.clear();
+      const char* w = (const char*)gz.data();
+      const size_t wsize = gz.size();
+      size_t p = cur;
+      while (p < wsize) {
+        const char* nl = (const char*)memchr(w + p, '\n', wsize - p);
+        if (!nl) break;
+        const char* le = nl;
+        if (le > w + p && le[-1] == '\r') --le;
+        if (le > w + p) tl.push_back(TLine{w + p, le});
+        p = (size_t)(nl - w) + 1;
+      }
+      const WalkFn walk = [&](int t, size_t lo, size_t hi, BufState* exact, ChunkOut* out) {
+        std::vector<uint8_t>& rb = rec_buf[(size_t)t];
+        std::vector<size_t>& ro = rec_off[(size_t)t];
+        if (!exact || S.random_umi) {           // a second, exact walk finds the records already built
+          rb.clear();
+          ro.clear();
+          for (size_t i = lo; i < hi; ++i) {
+            ro.push_back(rb.size());
+            if (!sam_to_bam(tl[i].p, tl[i].e, name2tid, &rb)) { out->clear(); out->corrupt = true; return; }
+          }
+        }
+        walk_chunk(S, rb.data(), ro.data(), 0, ro.size(), exact, &rnd_buf, out);
+      };
+      if (!run_batch(tl.size(), walk)) return fail("malformed SAM record");
+      const bool got = gz.more(p);
+      cur = 0;
+      if (!got) {
+        if (gz.bad()) return fail("truncated SAM file");
+        last = true;
+        if (gz.size() > 0) {                     // a last line without a newline
+          tl.clear();
+          const char* lp = (const char*)gz.data();
+          tl.push_back(TLine{lp, lp + gz.size()});
+          if (!run_batch(1, walk)) return fail("malformed SAM record");
+        }
+      }
+    }
+  } else {
+    for (;;) {
+      // complete records of the window
+      offs.clear();
+      const uint8_t* win = gz.data();
+      const size_t wsize = gz.size();
+      size_t p = cur;
+      while (p + 4 <= wsize) {
+        const int32_t block = rd_i32(win + p);
+        if (block < 32) return fail("corrupt BAM record");
+        if (p + 4 + (size_t)block > wsize) break;
+        offs.push_back(p);
+        p += 4 + (size_t)block;
+      }
+      const WalkFn walk = [&](int, size_t lo, size_t hi, BufState* exact, ChunkOut* out) {
+        walk_chunk(S, win, offs.data(), lo, hi, exact, &rnd_buf, out);
+      };
+      if (!run_batch(offs.size(), walk)) return fail("corrupt BAM record");
+      // next window
+      const bool got = gz.more(p);
+      cur = 0;
+      if (!got) {
+        if (gz.bad() || gz.size() > 0) return fail("truncated BAM record");
+        break;
+      }
     }
   }
   sw->barcodes.assign(bc_store.begin(), bc_store.end());

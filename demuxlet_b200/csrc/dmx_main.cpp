@@ -157,7 +157,7 @@ void usage() {
           "                      (F: GT, PL, or the name of a float FORMAT field with genotype posteriors, GP by default)\n"
           "                      the same from a VCF (plain / gzip / bgzip text) or BCF (F defaults to GP): biallelic records that\n"
           "                      pass the genotype-count filter must be the SNPs of the pileup, in order\n"
-          "  --sam FILE --vcf FILE   instead of --plp: pile the reads of a coordinate-sorted BAM up on the VCF's records\n"
+          "  --sam FILE --vcf FILE   instead of --plp: pile the reads of a coordinate-sorted BAM (or SAM text) up on the VCF's records\n"
           "                      [--tag-group CB] [--tag-UMI UB] [--min-MQ 20] [--excl-flag 0x0f04] [--min-BQ 13] [--cap-BQ 40]\n"
           "                      [--min-TD 0] [--sm ID]... [--sm-list FILE]; own BGZF / BAM / VCF / BCF readers (no htslib; no CRAM)\n");
 }

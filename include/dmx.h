@@ -259,7 +259,7 @@ int dmx_vcf_no_field(const dmx_vcf* v, uint8_t* flags);
 void dmx_vcf_free(dmx_vcf* v);
 const char* dmx_vcf_last_error(void);
 
-/* ---- BAM sweep (host only, no htslib; SURVEY 8f N4, BAM half) ----------------------------------------------------
+/* ---- BAM sweep (host only, no htslib; SURVEY 8f N4, BAM half; `path` may also be SAM text with its header) --------
  * The reference's walk over the position-sorted BAM next to the SNP list (cmd_cram_demuxlet.cpp:186-338): alignment
  * filter (sam_filtered_reader.cpp:284-296), barcode / UMI tags, RD.TOTL, and per overlapping SNP the base and quality
  * at the SNP position through the CIGAR (hts_utils.cpp:279-359), thresholds and the allele code (:304-325).  Emits one

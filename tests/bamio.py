@@ -59,6 +59,30 @@ def write_bam(path, refs, reads, member=4000, bgzf=False):
         f.write(gzip.compress(b""))     # BGZF end-of-file marker: an empty member
 
 
+def write_sam(path, refs, reads, gz=False, final_newline=True):
+    """the same reads as SAM text (SAM spec 1.4) with an @HD / @SQ header"""
+    lines = ["@HD\tVN:1.6\tSO:coordinate"] + ["@SQ\tSN:%s\tLN:%d" % (n, ln) for n, ln in refs] + ["@PG\tID:tests\tPN:bamio"]
+    for i, r in enumerate(reads):
+        tags = []
+        for t, ty, v in r["tags"]:
+            if ty == "B":
+                tags.append("%s:B:i,%s" % (t, ",".join(str(x) for x in v)))
+            else:
+                tags.append("%s:%s:%s" % (t, ty, v))
+        qual = "*" if r["qual"] is None else "".join(chr(min(q, 93) + 33) for q in r["qual"])
+        lines.append("\t".join(["r%d" % i, str(r["flag"]), refs[r["tid"]][0] if r["tid"] >= 0 else "*", str(r["pos"] + 1),
+                                 str(r["mapq"]), "".join("%d%s" % (ln, op) for op, ln in r["cigar"]) or "*", "*", "0", "0",
+                                 r["seq"] or "*", qual] + tags))
+    text = ("\n".join(lines) + ("\n" if final_newline else "")).encode()
+    if gz:
+        import gzip
+        with gzip.open(path, "wb") as f:
+            f.write(text)
+    else:
+        with open(path, "wb") as f:
+            f.write(text)
+
+
 class GlibcRand:
     """glibc's rand() / random() of a process that never calls srand(): the TYPE_3 additive feedback generator
     (r[i] = r[i-3] + r[i-31], 310 values discarded) seeded with 1 -- what the reference's `rand()` at

@@ -135,6 +135,33 @@ def test_sweep_is_independent_of_the_thread_count(threads, chunk, tmp_path, monk
          bamio.sweep(REFS, reads, chroms, rid, pos, ref, alt, groups=keep))
 
 
+@pytest.mark.parametrize("gz,threads", [(False, "1"), (True, "4")])
+def test_sam_text_gives_the_tuples_of_its_bam(gz, threads, tmp_path, monkeypatch):
+    """--sam takes SAM text as well in the reference (htslib opens either): every line is turned into the BAM record
+    sam_parse1 would build and goes through the same walk -- same tuples, barcodes and counts as the BAM of the reads
+    (qualities above 93 cannot be written as text and are capped in both files)"""
+    monkeypatch.setenv("DMX_BAM_THREADS", threads)
+    monkeypatch.setenv("DMX_BAM_MIN_CHUNK", "100")
+    rng = np.random.default_rng(33)
+    chroms, rid, pos, ref, alt = make_snps(rng)
+    reads, barcodes = bamio.random_reads(rng, REFS, {1: pos[rid == 0], 2: pos[rid == 1]}, 3000)
+    for r in reads:
+        if r["qual"] is not None:
+            r["qual"] = [min(q, 93) for q in r["qual"]]
+    pb, ps = str(tmp_path / "a.bam"), str(tmp_path / ("a.sam.gz" if gz else "a.sam"))
+    bamio.write_bam(pb, REFS, reads, bgzf=True)
+    bamio.write_sam(ps, REFS, reads, gz=gz, final_newline=not gz)
+    want = api.sweep_bam(pb, chroms, rid, pos, ref, alt)
+    same(api.sweep_bam(ps, chroms, rid, pos, ref, alt), want)
+    same(want, bamio.sweep(REFS, reads, chroms, rid, pos, ref, alt))
+    keep = barcodes[:4]
+    same(api.sweep_bam(ps, chroms, rid, pos, ref, alt, groups=keep, tag_umi=""),
+         bamio.sweep(REFS, reads, chroms, rid, pos, ref, alt, groups=keep, tag_umi=""))
+    (tmp_path / "bad.sam").write_text("@SQ\tSN:chr1\tLN:100\nr0\t0\tchr1\t5\t60\t3Q\t*\t0\t0\tACG\tIII\n")
+    with pytest.raises(api.DmxError, match="malformed SAM"):
+        api.sweep_bam(str(tmp_path / "bad.sam"), chroms, rid, pos, ref, alt)
+
+
 def test_sweep_feeds_the_packer(tmp_path):
     """sweep tuples -> dmx_pack_reads == the python container restatement on the same tuples"""
     from demuxlet_b200.plp import build_from_reads
