@@ -316,6 +316,7 @@ class Case:
 
     def timed(self, fn, steps):
         self.sync()
+        self.t_exchange, self.n_exchange = 0.0, 0      # of this timed region only (the warm-up holds NCCL's set-up)
         t0 = time.perf_counter()
         for _ in range(steps):
             fn()
@@ -355,6 +356,7 @@ class Case:
             rec["kern"].append(st["kernel_ms"]); rec["pair"].append(st["pair_kernel_ms"])
             rec["fin"].append(st["finalise_ms"]); rec["prep"].append(st["prep_ms"])
         dt = self.timed(step_rec, args.steps)
+        exchange_ms = self.t_exchange / max(self.n_exchange, 1) * 1e3
         clocks = sampler.stop() if sampler is not None else None
         st = d.stats()
         for _ in range(max(1, args.warmup // 2)):
@@ -364,7 +366,7 @@ class Case:
         if self.ex is not None and self.rank == 0:
             assert self.gathered is not None and self.gathered.shape[0] == self.total_cells
         return {"dt": dt, "dt2": dt2, "st": st, "st2": st2, "rec": rec, "clocks": clocks,
-                "exchange_ms": self.t_exchange / max(self.n_exchange, 1) * 1e3}
+                "exchange_ms": exchange_ms}
 
 
 def run_ours(args):
