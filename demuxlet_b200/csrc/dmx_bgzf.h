@@ -105,6 +105,9 @@ class ByteStream {
   }
   bool open(const char* path, int nth) {
     pool_.reset(new Pool(nth));
+    // test knobs: small windows exercise the carry-over of incomplete records / lines
+    if (const char* env = getenv("DMX_IO_BATCH_BLOCKS")) batch_blocks_ = (size_t)std::max(1, atoi(env));
+    if (const char* env = getenv("DMX_IO_CHUNK_BYTES")) gz_chunk_ = (size_t)std::max(1, atoi(env));
     const int fd = ::open(path, O_RDONLY);
     if (fd < 0) return false;
     uint8_t h[18];
@@ -138,11 +141,11 @@ class ByteStream {
     const uint8_t* tail = keep ? data() + keep_from : &kNone;
     if (!parallel_) {
       if (gz_eof_) { memmove(win_.data(), tail, keep); win_.resize(keep); beg_ = 0; return false; }
-      std::vector<uint8_t> nw(keep + kGzChunk);
+      std::vector<uint8_t> nw(keep + gz_chunk_);
       memcpy(nw.data(), tail, keep);
       size_t got = 0;
-      while (got < kGzChunk) {
-        const int k = gzread(gz_, nw.data() + keep + got, (unsigned)(kGzChunk - got));
+      while (got < gz_chunk_) {
+        const int k = gzread(gz_, nw.data() + keep + got, (unsigned)(gz_chunk_ - got));
         if (k < 0) { bad_ = true; break; }
         if (k == 0) { gz_eof_ = true; break; }
         got += (size_t)k;
@@ -182,7 +185,7 @@ class ByteStream {
   static constexpr size_t kGzChunk = 32u << 20;
   // every block starts with the 18-byte header checked in open(); BSIZE = total block size - 1
   bool index_batch(std::vector<Blk>* blocks) {
-    while (blocks->size() < kBatch && file_off_ < map_size_) {
+    while (blocks->size() < batch_blocks_ && file_off_ < map_size_) {
       if (file_off_ + 28 > map_size_) return false;
       const uint8_t* b = map_ + file_off_;
       if (!(b[0] == 0x1f && b[1] == 0x8b && b[12] == 'B' && b[13] == 'C')) return false;
@@ -242,7 +245,7 @@ class ByteStream {
   bool parallel_ = false, bad_ = false, gz_eof_ = false, index_bad_ = false;
   std::unique_ptr<Pool> pool_;
   const uint8_t* map_ = nullptr;
-  size_t map_size_ = 0, file_off_ = 0, sched_off_ = 0;
+  size_t map_size_ = 0, file_off_ = 0, sched_off_ = 0, batch_blocks_ = kBatch, gz_chunk_ = kGzChunk;
   std::vector<uint8_t> win_, ahead_;
   size_t beg_ = 0;
   std::future<bool> next_;

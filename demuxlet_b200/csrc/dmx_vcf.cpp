@@ -52,14 +52,6 @@ namespace {
 
 thread_local std::string g_vcf_error;
 
-// the whole decompressed text (BGZF blocks inflated on all host threads, dmx_bgzf.h)
-bool slurp(const char* path, int nth, std::string* out) {
-  dmx_io::ByteStream in;
-  if (!in.open(path, nth)) return false;
-  while (in.more(in.size())) out->append((const char*)in.data(), in.size());
-  return !in.bad();
-}
-
 struct Tok {
   const char* p;
   size_t n;
@@ -176,8 +168,8 @@ namespace {
 struct Line { const char *p, *e; int64_t no; };
 
 // Records of one contiguous range of lines [lo, hi), parsed by one host thread straight into the arrays of the whole
-// file at record slots lo, lo + 1, ... (a skipped record leaves its slot to the next one; the ranges are closed up
-// afterwards).  Chromosome ids are local to the part until the merge.
+// file at record slots base + lo, base + lo + 1, ... behind the `base` records read so far (a skipped record leaves its
+// slot to the next one; the ranges are closed up afterwards).  Chromosome ids are local to the part until the merge.
 struct Part {
   std::vector<std::string> chroms;
   size_t n = 0;                      // records delivered into slots [lo, lo + n)
@@ -186,13 +178,13 @@ struct Part {
   int64_t err_line = 0;
 };
 
-void parse_range(const std::vector<Line>& lines, size_t lo, size_t hi, int32_t field, const char* key, size_t nv, dmx_vcf* v,
-                 Part* part) {
+void parse_range(const std::vector<Line>& lines, size_t lo, size_t hi, size_t base, int32_t field, const char* key, size_t nv,
+                 dmx_vcf* v, Part* part) {
   const char* want = field == DMX_FIELD_GT ? nullptr : key;
   const size_t want_n = want ? strlen(want) : 0;
   std::vector<Tok> cols, keys, alts;
   auto fail = [&](int64_t no, const std::string& why) { part->error = why; part->err_line = no; };
-  size_t slot = lo;
+  size_t slot = base + lo;
   for (size_t li = lo; li < hi; ++li) {
     const char *p = lines[li].p, *e = lines[li].e;
     split(p, e, '\t', &cols);
@@ -235,7 +227,7 @@ void parse_range(const std::vector<Line>& lines, size_t lo, size_t hi, int32_t f
     }
     ++slot;
   }
-  part->n = slot - lo;
+  part->n = slot - base - lo;
 }
 
 
@@ -283,10 +275,10 @@ inline int32_t bcf_vec_int(const uint8_t* q, int t) {
   int32_t x; memcpy(&x, q, 4); return x <= INT32_MIN + 1 ? INT32_MIN : x;
 }
 
-void parse_range_bcf(const std::vector<BcfRec>& recs, size_t lo, size_t hi, int32_t field, int64_t id_gt, int64_t id_key,
-                     size_t nv, size_t n_contig, dmx_vcf* v, Part* part) {
+void parse_range_bcf(const std::vector<BcfRec>& recs, size_t lo, size_t hi, size_t base, int32_t field, int64_t id_gt,
+                     int64_t id_key, size_t nv, size_t n_contig, dmx_vcf* v, Part* part) {
   auto fail = [&](int64_t no, const std::string& why) { part->error = why; part->err_line = no; };
-  size_t slot = lo;
+  size_t slot = base + lo;
   for (size_t ri = lo; ri < hi; ++ri) {
     const uint8_t* r = recs[ri].p;
     uint32_t l_shared, l_indiv;
@@ -365,7 +357,7 @@ void parse_range_bcf(const std::vector<BcfRec>& recs, size_t lo, size_t hi, int3
     }
     ++slot;
   }
-  part->n = slot - lo;
+  part->n = slot - base - lo;
 }
 
 // value of `key` inside the <...> of a header line (quoted values may hold commas)
@@ -409,8 +401,10 @@ int dmx_vcf_read_key(const char* path, int32_t field, const char* key, dmx_vcf**
   if (!key || !key[0]) key = field == DMX_FIELD_PL ? "PL" : "GP";
   *out = nullptr;
   const int nthreads = dmx_io::host_threads("DMX_VCF_THREADS");
-  std::string text;
-  if (!slurp(path, nthreads, &text)) {
+  // The file is read window by window (a batch of inflated BGZF blocks, or 32 MB of any other stream, behind the
+  // unconsumed tail of the last one): memory is the window plus the arrays, and inflating runs ahead of the parsing.
+  dmx_io::ByteStream in;
+  if (!in.open(path, nthreads)) {
     g_vcf_error = std::string("cannot read ") + path;
     return DMX_E_IO;
   }
@@ -421,131 +415,203 @@ int dmx_vcf_read_key(const char* path, int32_t field, const char* key, dmx_vcf**
     delete v;
     return DMX_E_INVALID;
   };
-  // pass 1 (one thread): header (of the text, or the text inside a BCF file), line index
-  const bool is_bcf = text.size() >= 9 && memcmp(text.data(), "BCF\2\2", 5) == 0;
-  std::vector<Line> lines;
-  std::vector<BcfRec> recs;
+  auto fail_io = [&]() {
+    g_vcf_error = std::string("cannot read ") + path;
+    delete v;
+    return DMX_E_IO;
+  };
+  size_t cur = 0;                                     // read position inside the window
+  auto need = [&](size_t n) {                         // at least n bytes from cur on, if the file has them
+    while (in.size() - cur < n) {
+      const bool got = in.more(cur);
+      cur = 0;
+      if (!got) return in.size() >= n;
+    }
+    return true;
+  };
+  need(9);
+  if (in.bad()) return fail_io();
+  const bool is_bcf = in.size() >= 9 && memcmp(in.data(), "BCF\2\2", 5) == 0;
   std::vector<std::string> ids(1, "PASS");            // BCF: the FILTER / INFO / FORMAT string dictionary
   std::vector<Tok> cols;
-  const char *p = text.data(), *end = text.data() + text.size();
-  if (is_bcf) {
-    uint32_t l_text;
-    memcpy(&l_text, text.data() + 5, 4);
-    if ((size_t)l_text + 9 > text.size()) return fail(0, "truncated BCF header");
-    p = text.data() + 9;
-    end = p + l_text;
-    while (end > p && end[-1] == 0) --end;
-  }
   bool have_header = false;
   int64_t lineno = 0;
-  while (p < end) {
-    const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
-    const char* e = nl ? nl : end;
-    const char* next = nl ? nl + 1 : end;
-    if (e > p && e[-1] == '\r') --e;
-    ++lineno;
-    if (e > p) {
-      if (*p == '#') {
-        std::string id;
-        if (e - p > 13 && memcmp(p, "##contig=<", 10) == 0) {
-          // the header's contig dictionary defines the chromosome ids (bcf_hdr_name2id, cmd_cram_demuxlet.cpp:197-199):
-          // a read on a declared contig counts for its droplet even when no record of the file lies there
-          if (meta_value(p + 10, e, "ID", &id)) dict_add(&v->chroms, id, p + 10, e);
-        } else if (is_bcf && ((e - p > 11 && memcmp(p, "##FORMAT=<", 10) == 0) || (e - p > 9 && memcmp(p, "##INFO=<", 8) == 0) ||
-                              (e - p > 11 && memcmp(p, "##FILTER=<", 10) == 0))) {
-          const char* q = (const char*)memchr(p, '<', (size_t)(e - p)) + 1;
-          if (meta_value(q, e, "ID", &id)) dict_add(&ids, id, q, e);
-        } else if (e - p > 6 && memcmp(p, "#CHROM", 6) == 0) {
-          split(p, e, '\t', &cols);
-          if (cols.size() < 10) return fail(lineno, "no sample columns");
-          for (size_t i = 9; i < cols.size(); ++i) v->samples.emplace_back(cols[i].p, cols[i].n);
-          have_header = true;
-        }
-      } else {
-        if (!have_header) return fail(lineno, "record before the #CHROM line");
-        lines.push_back(Line{p, e, lineno});
-      }
+  // one header line: contig and (BCF) string dictionaries, sample names
+  auto header_line = [&](const char* p, const char* e) -> bool {
+    std::string id;
+    if (e - p > 13 && memcmp(p, "##contig=<", 10) == 0) {
+      // the header's contig dictionary defines the chromosome ids (bcf_hdr_name2id, cmd_cram_demuxlet.cpp:197-199):
+      // a read on a declared contig counts for its droplet even when no record of the file lies there
+      if (meta_value(p + 10, e, "ID", &id)) dict_add(&v->chroms, id, p + 10, e);
+    } else if (is_bcf && ((e - p > 11 && memcmp(p, "##FORMAT=<", 10) == 0) || (e - p > 9 && memcmp(p, "##INFO=<", 8) == 0) ||
+                          (e - p > 11 && memcmp(p, "##FILTER=<", 10) == 0))) {
+      const char* q = (const char*)memchr(p, '<', (size_t)(e - p)) + 1;
+      if (meta_value(q, e, "ID", &id)) dict_add(&ids, id, q, e);
+    } else if (e - p > 6 && memcmp(p, "#CHROM", 6) == 0) {
+      split(p, e, '\t', &cols);
+      if (cols.size() < 10) return false;
+      for (size_t i = 9; i < cols.size(); ++i) v->samples.emplace_back(cols[i].p, cols[i].n);
+      have_header = true;
     }
-    p = next;
-  }
-  if (!have_header) return fail(0, "no #CHROM line");
+    return true;
+  };
+  // one batch of records (lines of text, or BCF records, all inside the window): contiguous ranges on the host
+  // threads, each range into its own slots behind the records read so far; then, in file order, chromosome ids by
+  // first appearance and the ranges closed up over the slots of skipped records
+  std::vector<Line> lines;
+  std::vector<BcfRec> recs;
   int64_t id_gt = -1, id_key = -1;
+  dmx_io::Pool pool(nthreads);
+  std::vector<Part> parts;
+  auto run_batch = [&]() -> int64_t {                 // 0, or the failing line / record number
+    const size_t nv = v->samples.size(), nl = is_bcf ? recs.size() : lines.size(), base = v->rid.size();
+    if (nl == 0) return 0;
+    const size_t nth = std::max<size_t>(1, std::min<size_t>((size_t)nthreads, nl / 256 + 1));
+    v->rid.resize(base + nl);
+    v->pos.resize(base + nl);
+    v->ref.resize(base + nl);
+    v->alt.resize(base + nl);
+    v->no_field.resize(base + nl);
+    v->gt.resize((base + nl) * nv * 2);
+    if (field == DMX_FIELD_GP) v->gp.resize((base + nl) * nv * 3);
+    if (field == DMX_FIELD_PL) v->pl.resize((base + nl) * nv * 3);
+    parts.assign(nth, Part());
+    auto lo_of = [&](size_t t) { return nl * t / nth; };
+    const size_t n_contig = v->chroms.size();
+    pool.run((int)nth, [&](int t) {
+      if (is_bcf) parse_range_bcf(recs, lo_of((size_t)t), lo_of((size_t)t + 1), base, field, id_gt, id_key, nv, n_contig, v, &parts[(size_t)t]);
+      else parse_range(lines, lo_of((size_t)t), lo_of((size_t)t + 1), base, field, key, nv, v, &parts[(size_t)t]);
+    });
+    for (const Part& pt : parts)
+      if (!pt.error.empty()) { g_vcf_error = pt.error; return pt.err_line; }   // the first failing range = the first failing line
+    size_t nrec = base;
+    for (size_t t = 0; t < nth; ++t) {
+      const Part& pt = parts[t];
+      const size_t lo = base + lo_of(t);
+      if (!is_bcf) {       // (a BCF record carries the index into the header's contig dictionary itself)
+        std::vector<int32_t> remap(pt.chroms.size());
+        for (size_t c = 0; c < pt.chroms.size(); ++c) {
+          size_t r = 0;
+          for (; r < v->chroms.size(); ++r)
+            if (v->chroms[r] == pt.chroms[c]) break;
+          if (r == v->chroms.size()) v->chroms.push_back(pt.chroms[c]);
+          remap[c] = (int32_t)r;
+        }
+        for (size_t i = 0; i < pt.n; ++i) v->rid[lo + i] = remap[(size_t)v->rid[lo + i]];
+      }
+      if (nrec != lo && pt.n) {
+        auto close_up = [&](auto& vec, size_t per) {
+          if (!vec.empty()) memmove(vec.data() + nrec * per, vec.data() + lo * per, pt.n * per * sizeof(vec[0]));
+        };
+        close_up(v->rid, 1); close_up(v->pos, 1); close_up(v->ref, 1); close_up(v->alt, 1); close_up(v->no_field, 1);
+        close_up(v->gt, nv * 2); close_up(v->gp, nv * 3); close_up(v->pl, nv * 3);
+      }
+      nrec += pt.n;
+      v->n_skipped += pt.n_skipped;
+    }
+    v->rid.resize(nrec);
+    v->pos.resize(nrec);
+    v->ref.resize(nrec);
+    v->alt.resize(nrec);
+    v->no_field.resize(nrec);
+    v->gt.resize(nrec * nv * 2);
+    if (field == DMX_FIELD_GP) v->gp.resize(nrec * nv * 3);
+    if (field == DMX_FIELD_PL) v->pl.resize(nrec * nv * 3);
+    return 0;
+  };
+
   if (is_bcf) {
-    if (!lines.empty()) return fail(0, "text records inside a BCF header");
+    uint32_t l_text;
+    memcpy(&l_text, in.data() + 5, 4);
+    if (!need((size_t)l_text + 9)) return in.bad() ? fail_io() : fail(0, "truncated BCF header");
+    const char *p = (const char*)in.data() + 9, *end = p + l_text;
+    while (end > p && end[-1] == 0) --end;
+    while (p < end) {
+      const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+      const char* e = nl ? nl : end;
+      ++lineno;
+      if (e > p && e[-1] == '\r') --e;
+      if (e > p) {
+        if (*p != '#') return fail(lineno, "text records inside a BCF header");
+        if (!header_line(p, e)) return fail(lineno, "no sample columns");
+      }
+      p = nl ? nl + 1 : end;
+    }
+    if (!have_header) return fail(0, "no #CHROM line");
     for (size_t i = 0; i < ids.size(); ++i) {
       if (ids[i] == "GT") id_gt = (int64_t)i;
       if (ids[i] == key) id_key = (int64_t)i;
     }
-    uint32_t l_text;
-    memcpy(&l_text, text.data() + 5, 4);
-    const uint8_t *q = (const uint8_t*)text.data() + 9 + l_text, *qe = (const uint8_t*)text.data() + text.size();
+    cur = 9 + (size_t)l_text;
     int64_t no = 0;
-    while (q < qe) {
-      uint32_t l_shared, l_indiv;
-      if (q + 8 > qe) return fail(no + 1, "truncated BCF record");
-      memcpy(&l_shared, q, 4);
-      memcpy(&l_indiv, q + 4, 4);
-      if ((uint64_t)l_shared + l_indiv + 8 > (uint64_t)(qe - q)) return fail(no + 1, "truncated BCF record");
-      recs.push_back(BcfRec{q, ++no});
-      q += 8 + (size_t)l_shared + l_indiv;
+    for (;;) {
+      recs.clear();
+      const uint8_t* w = in.data();
+      const size_t wsize = in.size();
+      size_t q = cur;
+      while (q + 8 <= wsize) {
+        uint32_t l_shared, l_indiv;
+        memcpy(&l_shared, w + q, 4);
+        memcpy(&l_indiv, w + q + 4, 4);
+        if ((uint64_t)l_shared + l_indiv + 8 > (uint64_t)(wsize - q)) break;
+        recs.push_back(BcfRec{w + q, ++no});
+        q += 8 + (size_t)l_shared + l_indiv;
+      }
+      const int64_t bad = run_batch();
+      if (bad) return fail(bad, g_vcf_error);
+      const bool got = in.more(q);
+      cur = 0;
+      if (!got) {
+        if (in.bad()) return fail_io();
+        if (in.size() > 0) return fail(no + 1, "truncated BCF record");
+        break;
+      }
     }
-  }
-  // pass 2: the records, contiguous line ranges on the host threads, each range into its own slots of the arrays
-  const size_t nv = v->samples.size(), nl = is_bcf ? recs.size() : lines.size();
-  const size_t nth = std::max<size_t>(1, std::min<size_t>((size_t)nthreads, nl / 256 + 1));
-  v->rid.resize(nl);
-  v->pos.resize(nl);
-  v->ref.resize(nl);
-  v->alt.resize(nl);
-  v->no_field.resize(nl);
-  v->gt.resize(nl * nv * 2);
-  if (field == DMX_FIELD_GP) v->gp.resize(nl * nv * 3);
-  if (field == DMX_FIELD_PL) v->pl.resize(nl * nv * 3);
-  std::vector<Part> parts(nth);
-  auto lo_of = [&](size_t t) { return nl * t / nth; };
-  {
-    dmx_io::Pool pool((int)nth);
-    const size_t n_contig = v->chroms.size();
-    pool.run((int)nth, [&](int t) {
-      if (is_bcf) parse_range_bcf(recs, lo_of((size_t)t), lo_of((size_t)t + 1), field, id_gt, id_key, nv, n_contig, v, &parts[(size_t)t]);
-      else parse_range(lines, lo_of((size_t)t), lo_of((size_t)t + 1), field, key, nv, v, &parts[(size_t)t]);
-    });
-  }
-  for (const Part& pt : parts)
-    if (!pt.error.empty()) return fail(pt.err_line, pt.error);   // the first failing range = the first failing line
-  // merge in file order: chromosome ids by first appearance, ranges closed up over the slots of skipped records
-  size_t nrec = 0;
-  for (size_t t = 0; t < nth; ++t) {
-    const Part& pt = parts[t];
-    const size_t lo = lo_of(t);
-    std::vector<int32_t> remap(pt.chroms.size());
-    for (size_t c = 0; c < pt.chroms.size(); ++c) {
-      size_t r = 0;
-      for (; r < v->chroms.size(); ++r)
-        if (v->chroms[r] == pt.chroms[c]) break;
-      if (r == v->chroms.size()) v->chroms.push_back(pt.chroms[c]);
-      remap[c] = (int32_t)r;
-    }
-    if (!is_bcf)       // a BCF record carries the index into the header's contig dictionary itself
-      for (size_t i = 0; i < pt.n; ++i) v->rid[lo + i] = remap[(size_t)v->rid[lo + i]];
-    if (nrec != lo && pt.n) {
-      auto close_up = [&](auto& vec, size_t per) {
-        if (!vec.empty()) memmove(vec.data() + nrec * per, vec.data() + lo * per, pt.n * per * sizeof(vec[0]));
+  } else {
+    for (bool last = false; !last;) {
+      lines.clear();
+      const char* w = (const char*)in.data();
+      const size_t wsize = in.size();
+      size_t q = cur;
+      auto take = [&](const char* p, const char* e) -> int {     // 0 ok, else an error code for the messages below
+        if (e > p && e[-1] == '\r') --e;
+        ++lineno;
+        if (e <= p) return 0;
+        if (*p == '#') return header_line(p, e) ? 0 : 1;
+        if (!have_header) return 2;
+        lines.push_back(Line{p, e, lineno});
+        return 0;
       };
-      close_up(v->rid, 1); close_up(v->pos, 1); close_up(v->ref, 1); close_up(v->alt, 1); close_up(v->no_field, 1);
-      close_up(v->gt, nv * 2); close_up(v->gp, nv * 3); close_up(v->pl, nv * 3);
+      int err = 0;
+      while (q < wsize && !err) {
+        const char* nl = (const char*)memchr(w + q, '\n', wsize - q);
+        if (!nl) break;
+        err = take(w + q, nl);
+        q = (size_t)(nl - w) + 1;
+      }
+      if (!err) {
+        // the rest of the window is an incomplete line -- or, at the end of the file, a last line without a newline
+        const int64_t bad = run_batch();
+        if (bad) return fail(bad, g_vcf_error);
+        const bool got = in.more(q);
+        cur = 0;
+        if (!got) {
+          if (in.bad()) return fail_io();
+          last = true;
+          if (in.size() > 0) {
+            lines.clear();
+            err = take((const char*)in.data(), (const char*)in.data() + in.size());
+            if (!err) {
+              const int64_t bad2 = run_batch();
+              if (bad2) return fail(bad2, g_vcf_error);
+            }
+          }
+        }
+      }
+      if (err) return fail(lineno, err == 1 ? "no sample columns" : "record before the #CHROM line");
     }
-    nrec += pt.n;
-    v->n_skipped += pt.n_skipped;
+    if (!have_header) return fail(0, "no #CHROM line");
   }
-  v->rid.resize(nrec);
-  v->pos.resize(nrec);
-  v->ref.resize(nrec);
-  v->alt.resize(nrec);
-  v->no_field.resize(nrec);
-  v->gt.resize(nrec * nv * 2);
-  if (field == DMX_FIELD_GP) v->gp.resize(nrec * nv * 3);
-  if (field == DMX_FIELD_PL) v->pl.resize(nrec * nv * 3);
   *out = v;
   return DMX_OK;
 }

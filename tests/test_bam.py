@@ -162,6 +162,27 @@ def test_sam_text_gives_the_tuples_of_its_bam(gz, threads, tmp_path, monkeypatch
         api.sweep_bam(str(tmp_path / "bad.sam"), chroms, rid, pos, ref, alt)
 
 
+@pytest.mark.parametrize("blocks,chunk", [("1", "7"), ("2", "5000")])
+def test_sweep_streams_window_by_window(blocks, chunk, tmp_path, monkeypatch):
+    """windows of a few bytes (every header field and record straddles several): same tuples from the gzip, BGZF and
+    SAM-text form of the reads"""
+    rng = np.random.default_rng(43)
+    chroms, rid, pos, ref, alt = make_snps(rng)
+    reads, _ = bamio.random_reads(rng, REFS, {1: pos[rid == 0], 2: pos[rid == 1]}, 400)
+    for r in reads:
+        if r["qual"] is not None:
+            r["qual"] = [min(q, 93) for q in r["qual"]]
+    pa, pb, ps = str(tmp_path / "a.bam"), str(tmp_path / "b.bam"), str(tmp_path / "c.sam")
+    bamio.write_bam(pa, REFS, reads)
+    bamio.write_bam(pb, REFS, reads, member=300, bgzf=True)
+    bamio.write_sam(ps, REFS, reads)
+    want = bamio.sweep(REFS, reads, chroms, rid, pos, ref, alt)
+    monkeypatch.setenv("DMX_IO_BATCH_BLOCKS", blocks)
+    monkeypatch.setenv("DMX_IO_CHUNK_BYTES", chunk)
+    for p in (pa, pb, ps):
+        same(api.sweep_bam(p, chroms, rid, pos, ref, alt), want)
+
+
 def test_sweep_feeds_the_packer(tmp_path):
     """sweep tuples -> dmx_pack_reads == the python container restatement on the same tuples"""
     from demuxlet_b200.plp import build_from_reads

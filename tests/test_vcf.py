@@ -100,6 +100,28 @@ def test_bcf_gives_the_arrays_of_its_vcf_text(field, int_type, idx, tmp_path):
         api.read_vcf(str(tmp_path / "cut.bcf"), field)
 
 
+@pytest.mark.parametrize("blocks,chunk", [("1", "7"), ("3", "1000")])
+def test_reader_streams_window_by_window(blocks, chunk, tmp_path, monkeypatch):
+    """the file is read window by window (a batch of BGZF blocks / a chunk of any other stream behind the unconsumed tail
+    of the last one) and parsed as it comes: windows of a few bytes -- every line, BCF header and BCF record straddles
+    several -- give the records of the one-window read, in text, gzip, BGZF and BCF form"""
+    rng = np.random.default_rng(41)
+    samples = ["S%d" % i for i in range(4)]
+    recs = vcfio.random_records(rng, 150, len(samples), "PL")
+    contigs = ["chr1", "chr2", "chr3"]
+    paths = [str(tmp_path / n) for n in ("a.vcf", "b.vcf.gz", "c.vcf.gz", "d.bcf")]
+    vcfio.write_vcf(paths[0], samples, recs, contigs=contigs)
+    vcfio.write_vcf(paths[1], samples, recs, contigs=contigs)
+    vcfio.write_vcf(paths[2], samples, recs, contigs=contigs, bgzf=True)
+    vcfio.write_bcf(paths[3], samples, recs, contigs)
+    want = [api.read_vcf(p, "PL") for p in paths]
+    monkeypatch.setenv("DMX_IO_BATCH_BLOCKS", blocks)
+    monkeypatch.setenv("DMX_IO_CHUNK_BYTES", chunk)
+    for p, w in zip(paths, want):
+        same(api.read_vcf(p, "PL"), w, "PL")
+        same(w, want[0], "PL")
+
+
 def test_format_floats_are_strtod_narrowed(tmp_path):
     """GP text -> float as htslib does it, (float)strtod(text): the reader's one-operation conversion of plain decimals
     (mantissa < 2^53, |decimal exponent| <= 22) and its strtod fall-back give that bit pattern for every spelling"""
