@@ -456,7 +456,7 @@ int dmx_sweep_bam(const char* path, const dmx_sweep_opts* o, int32_t n_chrom, co
                   const int32_t* snp_rid, const int32_t* snp_pos, const char* snp_ref, const char* snp_alt,
                   dmx_sweep** out) {
   if (!path || !o || !out || n_chrom < 0 || nsnps < 0 || (nsnps > 0 && (!snp_rid || !snp_pos || !snp_ref || !snp_alt)) ||
-      (n_chrom > 0 && !chroms))
+      (n_chrom > 0 && !chroms) || o->n_groups < 0 || (o->n_groups > 0 && !o->groups))
     return DMX_E_INVALID;
   *out = nullptr;
   if (!o->tag_umi) {
