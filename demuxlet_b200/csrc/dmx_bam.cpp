@@ -214,18 +214,22 @@ void walk_chunk(const Sweep& S, const uint8_t* win, const size_t* offs, size_t r
     if ((int32_t)mapq < o->min_mq || (o->exclude_flag & flag)) { ++out->n_filtered; continue; }
     const int32_t rid = (tid >= 0 && tid < S.n_ref) ? S.tid2rid[(size_t)tid] : -1;
     if (rid < 0) { ++out->n_off_vcf; continue; }                                      // :197-200
-    // bam_endpos: start + reference span of the CIGAR (M, D, N, =, X), at least one base
+    // bam_endpos (htslib >= 1.10): start + reference span of the CIGAR (M, D, N, =, X), at least one base
     int64_t span = 0, covered = 0;
     for (uint32_t c = 0; c < n_cigar; ++c) {
       const uint32_t v = rd_u32(cigar + 4 * c), op = v & 15u;
       if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += v >> 4;
       if (op == 0 || op == 1 || op == 4) covered += v >> 4;
     }
+    // (htslib: a read flagged unmapped ends one base behind its start whatever its CIGAR says -- it is still walked
+    // through that CIGAR below, so for it the aligned span does not bound where a base can be found)
+    const bool unmapped_cigar = (flag & 4u) && n_cigar > 0;
+    if (unmapped_cigar) span = 0;
     ReadKey k;
     k.c = rid;
     k.pos = pos;
     k.endpos = (int64_t)pos + (span > 0 ? span : 1);
-    k.plain = n_cigar == 0 || covered >= l_seq;
+    k.plain = n_cigar == 0 || (covered >= l_seq && !unmapped_cigar);
     k.lo = hint_lo = S.lower(rid, (int64_t)pos - 1, hint_lo);
     k.la = S.lower(rid, k.endpos, k.lo);
     int64_t i0, i1;              // SNPs to test: [i0, i1)

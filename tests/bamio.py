@@ -133,6 +133,8 @@ def sweep(refs, reads, chroms, snp_rid, snp_pos, snp_ref, snp_alt, groups=None, 
             cnt["off_vcf"] += 1
             continue
         span = sum(ln for op, ln in r["cigar"] if op in "MDN=X")
+        if r["flag"] & 4:                                  # bam_endpos: an unmapped read ends one base behind its start
+            span = 0
         endpos = r["pos"] + (span if span > 0 else 1)
         n_rm = 0                                           # clear_buffer_before(chrom, read start), rlen = 1
         for i in range(ibeg, ibeg + nbuf):

@@ -33,7 +33,7 @@ def same(a, b):
 
 @pytest.mark.parametrize("seed,opts", [(1, {}), (2, {"min_bq": 0, "cap_bq": 30, "min_td": 5}),
                                        (3, {"min_mq": 0, "exclude_flag": 0x4}), (4, {"tag_group": "", "tag_umi": "RG"}),
-                                       (5, {"tag_umi": ""})])
+                                       (5, {"tag_umi": ""}), (6, {"exclude_flag": 0, "min_mq": 0})])
 def test_sweep_matches_restatement(seed, opts, tmp_path):
     rng = np.random.default_rng(seed)
     chroms, rid, pos, ref, alt = make_snps(rng)
@@ -44,7 +44,8 @@ def test_sweep_matches_restatement(seed, opts, tmp_path):
     got = api.sweep_bam(path, chroms, rid, pos, ref, alt, **opts)
     want = bamio.sweep(REFS, reads, chroms, rid, pos, ref, alt, **opts)
     same(got, want)
-    assert len(got["cell"]) > 300 and got["counts"]["filtered"] > 0 and got["counts"]["off_vcf"] > 0
+    assert len(got["cell"]) > 300 and got["counts"]["off_vcf"] > 0
+    assert (got["counts"]["filtered"] > 0) == (opts.get("exclude_flag") != 0)    # seed 6: unmapped reads with CIGARs go through
     if not opts:
         assert "." in got["barcodes"] and "." in got["umis"] and set(got["allele"]) == {0, 1, 2}
         keep = barcodes[:5]

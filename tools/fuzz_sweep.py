@@ -38,6 +38,7 @@ for seed in range(int(sys.argv[1]), int(sys.argv[2])):
     if rng.random() < 0.3: opts["min_td"] = int(rng.integers(0, 10))
     if rng.random() < 0.2: opts["tag_umi"] = ""
     if rng.random() < 0.2: opts["tag_group"] = ""
+    if rng.random() < 0.3: opts.update(exclude_flag=int(rng.choice([0, 0x100, 0x0f00])), min_mq=0)   # unmapped reads go through
     groups = barcodes[::2] if rng.random() < 0.3 else None
     os.environ["DMX_BAM_THREADS"] = str(int(rng.choice([1, 2, 3, 8])))
     os.environ["DMX_BAM_MIN_CHUNK"] = str(int(rng.choice([1, 5, 50, 2048])))
