@@ -184,6 +184,61 @@ def test_sweep_streams_window_by_window(blocks, chunk, tmp_path, monkeypatch):
         same(api.sweep_bam(p, chroms, rid, pos, ref, alt), want)
 
 
+def test_sam_specification_example(tmp_path):
+    """the example alignment of the SAM specification (section 1.1; qualities added, its QUAL column is '*'): a SNP at
+    every reference position must find the base the specification's picture shows there --
+
+        Coor     12345678901234  5678901234567890123456789012345
+        ref      AGCATGTTAGATAA**GATAGCTGTGCTAGTAGGCAGTCAGCGCCAT
+        +r001/1        TTAGATAAAGGATA*CTG
+        +r002         aaaAGATAA*GGATA
+        +r003       gcctaAGCTAA
+        +r004                     ATAGCT..............TCAGC
+        -r003                            ttagctTAGGC          (supplementary: dropped by --excl-flag 0x0f04)
+        -r001/2                                        CAGCGGCAT
+
+    -- through M / I / D / N / S / H / P operations, from the SAM text and from the BAM of the same reads"""
+    ref = "AGCATGTTAGATAAGATAGCTGTGCTAGTAGGCAGTCAGCGCCAT"
+    sam = ("@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:ref\tLN:45\n"
+           "r001\t99\tref\t7\t30\t8M2I4M1D3M\t=\t37\t39\tTTAGATAAAGGATACTG\t" + "I" * 17 + "\n"
+           "r002\t0\tref\t9\t30\t3S6M1P1I4M\t*\t0\t0\tAAAAGATAAGGATA\t" + "I" * 14 + "\n"
+           "r003\t0\tref\t9\t30\t5S6M\t*\t0\t0\tGCCTAAGCTAA\t" + "I" * 11 + "\tSA:Z:ref,29,-,6H5M,17,0;\n"
+           "r004\t0\tref\t16\t30\t6M14N5M\t*\t0\t0\tATAGCTTCAGC\t" + "I" * 11 + "\n"
+           "r003\t2064\tref\t29\t17\t6H5M\t*\t0\t0\tTAGGC\t" + "I" * 5 + "\tSA:Z:ref,9,+,5S6M,30,1;\n"
+           "r001\t147\tref\t37\t30\t9M\t=\t7\t-39\tCAGCGGCAT\t" + "I" * 9 + "\tNM:i:1\n")
+    ps = tmp_path / "spec.sam"
+    ps.write_text(sam)
+    n = len(ref)
+    rid, pos = np.zeros(n, np.int32), np.arange(n, dtype=np.int32)
+    snp_ref = np.array([c.encode() for c in ref], "S1")
+    snp_alt = np.array([b"C" if c != "C" else b"G" for c in ref], "S1")      # ref 11 A>C (r003), ref 42 C>G (r001/2)
+    # what the picture shows: (read, 1-based reference positions of its aligned bases, those bases)
+    shown = [("r001/1", list(range(7, 15)) + list(range(15, 19)) + list(range(20, 23)), "TTAGATAA" "GATA" "CTG"),
+             ("r002", list(range(9, 15)) + list(range(15, 19)), "AGATAA" "GATA"),
+             ("r003", list(range(9, 15)), "AGCTAA"),
+             ("r004", list(range(16, 22)) + list(range(36, 41)), "ATAGCT" "TCAGC"),
+             ("r001/2", list(range(37, 46)), "CAGCGGCAT")]
+    want = []
+    for _, where, bases in shown:
+        for p1, b in zip(where, bases):
+            want.append((p1 - 1, 0 if b == ref[p1 - 1] else (1 if b.encode() == snp_alt[p1 - 1] else 2), 40))
+    assert sum(a for _, a, _ in want) == 2                 # the two mismatches of the example
+    got = api.sweep_bam(str(ps), ["ref"], rid, pos, snp_ref, snp_alt)
+    assert list(zip(got["snp"].tolist(), got["allele"].tolist(), got["bq"].tolist())) == want
+    assert got["barcodes"] == ["."] and got["totl"].tolist() == [5] and got["counts"] == {
+        "records": 6, "filtered": 1, "off_vcf": 0, "skip_bcd": 0} and set(got["umis"]) == {"."}
+    # the same reads as BAM
+    ops = {"r001/1": [("M", 8), ("I", 2), ("M", 4), ("D", 1), ("M", 3)], "r002": [("S", 3), ("M", 6), ("P", 1), ("I", 1), ("M", 4)],
+           "r003": [("S", 5), ("M", 6)], "r004": [("M", 6), ("N", 14), ("M", 5)], "r003s": [("H", 6), ("M", 5)], "r001/2": [("M", 9)]}
+    rows = [("r001/1", 99, 6, 30, "TTAGATAAAGGATACTG"), ("r002", 0, 8, 30, "AAAAGATAAGGATA"), ("r003", 0, 8, 30, "GCCTAAGCTAA"),
+            ("r004", 0, 15, 30, "ATAGCTTCAGC"), ("r003s", 2064, 28, 17, "TAGGC"), ("r001/2", 147, 36, 30, "CAGCGGCAT")]
+    reads = [{"tid": 0, "pos": p0, "mapq": mq, "flag": fl, "cigar": ops[nm], "seq": sq, "qual": [40] * len(sq), "tags": []}
+             for nm, fl, p0, mq, sq in rows]
+    pb = str(tmp_path / "spec.bam")
+    bamio.write_bam(pb, [("ref", 45)], reads, bgzf=True)
+    same(api.sweep_bam(pb, ["ref"], rid, pos, snp_ref, snp_alt), got)
+
+
 def test_sweep_feeds_the_packer(tmp_path):
     """sweep tuples -> dmx_pack_reads == the python container restatement on the same tuples"""
     from demuxlet_b200.plp import build_from_reads

@@ -122,6 +122,50 @@ def test_reader_streams_window_by_window(blocks, chunk, tmp_path, monkeypatch):
         same(w, want[0], "PL")
 
 
+def test_vcf_specification_example(tmp_path):
+    """the example file of the VCF specification (section 1.1): two biallelic records are kept, the two multi-allelic
+    ones and the monomorphic one are skipped; genotypes, phased or not, positions and alleles as printed there; a
+    sample column that drops its trailing subfields (NA00003 of the second record) reads as missing"""
+    text = """##fileformat=VCFv4.3
+##fileDate=20090805
+##source=myImputationProgramV3.1
+##reference=file:///seq/references/1000GenomesPilot-NCBI36.fasta
+##contig=<ID=20,length=62435964,assembly=B36,md5=f126cdf8a6e0c7f379d618ff66beb2da,species="Homo sapiens",taxonomy=x>
+##phasing=partial
+##INFO=<ID=NS,Number=1,Type=Integer,Description="Number of Samples With Data">
+##INFO=<ID=DP,Number=1,Type=Integer,Description="Total Depth">
+##INFO=<ID=AF,Number=A,Type=Float,Description="Allele Frequency">
+##INFO=<ID=AA,Number=1,Type=String,Description="Ancestral Allele">
+##INFO=<ID=DB,Number=0,Type=Flag,Description="dbSNP membership, build 129">
+##INFO=<ID=H2,Number=0,Type=Flag,Description="HapMap2 membership">
+##FILTER=<ID=q10,Description="Quality below 10">
+##FILTER=<ID=s50,Description="Less than 50% of samples have data">
+##FORMAT=<ID=GT,Number=1,Type=String,Description="Genotype">
+##FORMAT=<ID=GQ,Number=1,Type=Integer,Description="Genotype Quality">
+##FORMAT=<ID=DP,Number=1,Type=Integer,Description="Read Depth">
+##FORMAT=<ID=HQ,Number=2,Type=Integer,Description="Haplotype Quality">
+#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tNA00001\tNA00002\tNA00003
+20\t14370\trs6054257\tG\tA\t29\tPASS\tNS=3;DP=14;AF=0.5;DB;H2\tGT:GQ:DP:HQ\t0|0:48:1:51,51\t1|0:48:8:51,51\t1/1:43:5:.,.
+20\t17330\t.\tT\tA\t3\tq10\tNS=3;DP=11;AF=0.017\tGT:GQ:DP:HQ\t0|0:49:3:58,50\t0|1:3:5:65,3\t0/0:41:3
+20\t1110696\trs6040355\tA\tG,T\t67\tPASS\tNS=2;DP=10;AF=0.333,0.667;AA=T;DB\tGT:GQ:DP:HQ\t1|2:21:6:23,27\t2|1:2:0:18,2\t2/2:35:4
+20\t1230237\t.\tT\t.\t47\tPASS\tNS=3;DP=13;AA=T\tGT:GQ:DP:HQ\t0|0:54:7:56,60\t0|0:48:4:51,51\t0/0:61:2
+20\t1234567\tmicrosat1\tGTC\tG,GTCT\t50\tPASS\tNS=3;DP=9;AA=G\tGT:GQ:DP\t0/1:35:4\t0/2:17:2\t1/1:40:3
+"""
+    p = tmp_path / "spec.vcf"
+    p.write_text(text)
+    v = api.read_vcf(str(p), "GT")
+    assert v["samples"] == ["NA00001", "NA00002", "NA00003"] and v["chroms"] == ["20"] and v["n_skipped"] == 3
+    assert v["pos"].tolist() == [14369, 17329] and v["ref"].tolist() == [b"G", b"T"] and v["alt"].tolist() == [b"A", b"A"]
+    assert v["gt"].tolist() == [[[0, 0], [1, 0], [1, 1]], [[0, 0], [0, 1], [0, 0]]]
+    # HQ read the way the reference reads any other --field: float posteriors (two values and a missing third)
+    h = api.read_vcf(str(p), "GP", key="HQ")
+    nan = float("nan")
+    want = np.array([[[51, 51, nan], [51, 51, nan], [nan, nan, nan]], [[58, 50, nan], [65, 3, nan], [nan, nan, nan]]], np.float32)
+    assert not h["no_field"].any() and np.array_equal(np.nan_to_num(h["values"], nan=-1), np.nan_to_num(want, nan=-1))
+    # the reference's filter on these genotypes (an = 6; record 1: ac = 3, record 2: ac = 1): --min-mac 1 keeps both, 2 only the first
+    assert po.site_filter(v["gt"], 1, 0.5).tolist() == [True, True] and po.site_filter(v["gt"], 2, 0.5).tolist() == [True, False]
+
+
 def test_format_floats_are_strtod_narrowed(tmp_path):
     """GP text -> float as htslib does it, (float)strtod(text): the reader's one-operation conversion of plain decimals
     (mantissa < 2^53, |decimal exponent| <= 22) and its strtod fall-back give that bit pattern for every spelling"""
