@@ -239,6 +239,13 @@ def test_sam_specification_example(tmp_path):
     same(api.sweep_bam(pb, ["ref"], rid, pos, snp_ref, snp_alt), got)
 
 
+def test_bgzf_framing_matches_the_specification_constant():
+    """the empty BGZF block the test writer emits is, byte for byte, the end-of-file marker printed in the SAM
+    specification (section 4.1.2) -- the one fixed BGZF byte string there is: header fields, BC subfield, BSIZE, CRC, ISIZE"""
+    eof = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+    assert bamio.bgzf_block(b"") == eof and len(eof) == 28
+
+
 def test_sweep_feeds_the_packer(tmp_path):
     """sweep tuples -> dmx_pack_reads == the python container restatement on the same tuples"""
     from demuxlet_b200.plp import build_from_reads
