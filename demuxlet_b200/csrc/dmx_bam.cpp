@@ -702,7 +702,7 @@ int dmx_sweep_bam(const char* path, const dmx_sweep_opts* o, int32_t n_chrom, co
         if (le > w + p) tl.push_back(TLine{w + p, le});
         p = (size_t)(nl - w) + 1;
       }
-      const WalkFn walk = [&](int t, size_t lo, size_t hi, BufState* exact, ChunkOut* out) {
+      const WalkFn walk = [&](int t, size_t lo, size_t hi, BufState* exact, ChunkOut* co) {
         std::vector<uint8_t>& rb = rec_buf[(size_t)t];
         std::vector<size_t>& ro = rec_off[(size_t)t];
         if (!exact || S.random_umi) {           // a second, exact walk finds the records already built
@@ -710,10 +710,10 @@ int dmx_sweep_bam(const char* path, const dmx_sweep_opts* o, int32_t n_chrom, co
           ro.clear();
           for (size_t i = lo; i < hi; ++i) {
             ro.push_back(rb.size());
-            if (!sam_to_bam(tl[i].p, tl[i].e, name2tid, &rb)) { out->clear(); out->corrupt = true; return; }
+            if (!sam_to_bam(tl[i].p, tl[i].e, name2tid, &rb)) { co->clear(); co->corrupt = true; return; }
           }
         }
-        walk_chunk(S, rb.data(), ro.data(), 0, ro.size(), exact, &rnd_buf, out);
+        walk_chunk(S, rb.data(), ro.data(), 0, ro.size(), exact, &rnd_buf, co);
       };
       if (!run_batch(tl.size(), walk)) return fail("malformed SAM record");
       const bool got = gz.more(p);
@@ -743,8 +743,8 @@ int dmx_sweep_bam(const char* path, const dmx_sweep_opts* o, int32_t n_chrom, co
         offs.push_back(p);
         p += 4 + (size_t)block;
       }
-      const WalkFn walk = [&](int, size_t lo, size_t hi, BufState* exact, ChunkOut* out) {
-        walk_chunk(S, win, offs.data(), lo, hi, exact, &rnd_buf, out);
+      const WalkFn walk = [&](int, size_t lo, size_t hi, BufState* exact, ChunkOut* co) {
+        walk_chunk(S, win, offs.data(), lo, hi, exact, &rnd_buf, co);
       };
       if (!run_batch(offs.size(), walk)) return fail("corrupt BAM record");
       // next window
