@@ -140,9 +140,9 @@ class ByteStream {
     static const uint8_t kNone = 0;
     const uint8_t* tail = keep ? data() + keep_from : &kNone;
     if (!parallel_) {
-      if (gz_eof_) { memmove(win_.data(), tail, keep); win_.resize(keep); beg_ = 0; return false; }
+      if (gz_eof_) { if (keep) memmove(win_.data(), tail, keep); win_.resize(keep); beg_ = 0; return false; }
       std::vector<uint8_t> nw(keep + gz_chunk_);
-      memcpy(nw.data(), tail, keep);
+      if (keep) memcpy(nw.data(), tail, keep);
       size_t got = 0;
       while (got < gz_chunk_) {
         const int k = gzread(gz_, nw.data() + keep + got, (unsigned)(gz_chunk_ - got));
@@ -156,11 +156,11 @@ class ByteStream {
       return got > 0 && !bad_;
     }
     for (;;) {
-      if (!next_.valid()) { memmove(win_.data(), tail, keep); win_.resize(keep); beg_ = 0; return false; }
+      if (!next_.valid()) { if (keep) memmove(win_.data(), tail, keep); win_.resize(keep); beg_ = 0; return false; }
       if (!next_.get()) { bad_ = true; return false; }
       // ahead_ was inflated behind kSlack spare bytes: the kept tail goes in front of it without moving the batch
       if (keep <= kSlack) {
-        memcpy(ahead_.data() + kSlack - keep, tail, keep);
+        if (keep) memcpy(ahead_.data() + kSlack - keep, tail, keep);
         win_.swap(ahead_);
         beg_ = kSlack - keep;
       } else {
