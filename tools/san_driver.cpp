@@ -37,7 +37,16 @@ int main(int argc, char** argv) {
     int64_t nc = 0, nr = 0, ub = 0;
     if (rc == 0) { dmx_sweep_sizes(sw, &nc, &nr, &ub);
       std::vector<int32_t> cell(nr + 1), snp(nr + 1), totl(nc + 1); std::vector<uint8_t> al(nr + 1), bq(nr + 1); std::vector<char> ubuf(ub + 1); std::vector<int64_t> uo(nr + 2);
-      dmx_sweep_copy(sw, cell.data(), snp.data(), al.data(), bq.data(), ubuf.data(), uo.data(), totl.data()); }
+      dmx_sweep_copy(sw, cell.data(), snp.data(), al.data(), bq.data(), ubuf.data(), uo.data(), totl.data());
+      // ... and through the packer (N1), on several threads
+      dmx_pileup* pl = nullptr;
+      const int prc = dmx_pack_reads(nr, cell.data(), snp.data(), al.data(), bq.data(), ubuf.data(), uo.data(), nc, 4, &pl);
+      int64_t pc = 0, pe = 0, pr = 0;
+      if (prc == 0) { dmx_pileup_sizes(pl, &pc, &pe, &pr);
+        std::vector<int64_t> cp(pc + 1), ep(pe + 1); std::vector<int32_t> es(pe + 1), pa(pc + 1), un(pc + 1); std::vector<uint16_t> rd(pr + 1);
+        dmx_pileup_copy(pl, cp.data(), es.data(), ep.data(), rd.data(), pa.data(), un.data()); }
+      printf("pack rc %d cells %lld entries %lld reads %lld\n", prc, (long long)pc, (long long)pe, (long long)pr);
+      dmx_pileup_free(pl); }
     printf("bam mode %d rc %d cells %lld tuples %lld %s\n", mode, rc, (long long)nc, (long long)nr, rc ? dmx_sweep_last_error() : "");
     dmx_sweep_free(sw);
   }
