@@ -108,6 +108,11 @@ class ByteStream {
     // test knobs: small windows exercise the carry-over of incomplete records / lines
     if (const char* env = getenv("DMX_IO_BATCH_BLOCKS")) batch_blocks_ = (size_t)std::max(1, atoi(env));
     if (const char* env = getenv("DMX_IO_CHUNK_BYTES")) gz_chunk_ = (size_t)std::max(1, atoi(env));
+    if (!strcmp(path, "-")) {          // standard input, as htslib reads it
+      gz_ = gzdopen(dup(0), "rb");
+      if (gz_) gzbuffer(gz_, 1 << 20);
+      return gz_ != nullptr;
+    }
     const int fd = ::open(path, O_RDONLY);
     if (fd < 0) return false;
     uint8_t h[18];

@@ -246,6 +246,27 @@ def test_bgzf_framing_matches_the_specification_constant():
     assert bamio.bgzf_block(b"") == eof and len(eof) == 28
 
 
+def test_sweep_reads_standard_input(tmp_path):
+    """--sam - (htslib's name for standard input): a BAM piped in gives the tuples of the file"""
+    import subprocess
+    import sys
+    rng = np.random.default_rng(47)
+    chroms, rid, pos, ref, alt = make_snps(rng, 100)
+    reads, _ = bamio.random_reads(rng, REFS, {1: pos[rid == 0], 2: pos[rid == 1]}, 500)
+    path = str(tmp_path / "a.bam")
+    bamio.write_bam(path, REFS, reads, bgzf=True)
+    np.savez(str(tmp_path / "snps.npz"), rid=rid, pos=pos, ref=ref, alt=alt)
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); from demuxlet_b200 import api; z = np.load(%r); "
+            "s = api.sweep_bam('-', %r, z['rid'], z['pos'], z['ref'], z['alt']); "
+            "print(len(s['cell']), int(s['snp'].sum()), int(s['totl'].sum()), len(s['barcodes']))"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(tmp_path / "snps.npz"), chroms))
+    with open(path, "rb") as f:
+        r = subprocess.run([sys.executable, "-c", code], stdin=f, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    w = api.sweep_bam(path, chroms, rid, pos, ref, alt)
+    assert r.stdout.split() == [str(len(w["cell"])), str(int(w["snp"].sum())), str(int(w["totl"].sum())), str(len(w["barcodes"]))]
+
+
 def test_sweep_feeds_the_packer(tmp_path):
     """sweep tuples -> dmx_pack_reads == the python container restatement on the same tuples"""
     from demuxlet_b200.plp import build_from_reads
