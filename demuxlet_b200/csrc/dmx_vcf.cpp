@@ -1,4 +1,4 @@
-// dmx_vcf.cpp -- htslib-free VCF text reader for the arrays the field kernels take (VCF half; host only).
+// dmx_vcf.cpp -- htslib-free VCF / BCF reader for the arrays the field kernels take (VCF half; host only).
 //
 // The reference reads VCF / BCF records through htslib (BCFChunkedReader::read, /root/reference/bcf_chunked_reader.cpp:
 // 265-305: bcf_read / vcf_parse1) and asks the record for its FORMAT values with bcf_get_genotypes /
@@ -15,8 +15,12 @@
 // Records are delivered in file order; records whose allele count is not 2 are skipped and counted (demuxlet sets
 // maxAlleles = 2, cmd_cram_demuxlet.cpp:26; a record without ALT cannot pass --min-mac 1).  All samples are selected
 // (dmx_vcf_select applies --sm / --sm-list afterwards).  The chromosome ids follow the header's ##contig lines, then first
-// appearance in the records (htslib's dictionary: bcf_hdr_name2id, cmd_cram_demuxlet.cpp:197-199).  No reference test pins htslib's parse, so the pin of THIS reader is its python restatement
-// (tests/vcfio.py) on generated files: "parity unpinned" against htslib itself.
+// appearance in the records (htslib's dictionary: bcf_hdr_name2id, cmd_cram_demuxlet.cpp:197-199).
+// The file is streamed window by window (dmx_bgzf.h): a window's lines / records are parsed in contiguous ranges on the
+// host threads straight into the arrays; memory is one window plus the arrays.
+// Pins: the reference's tutorial VCF against an independent parse and the example file of the VCF specification
+// (tests/test_vcf.py); beyond those the python restatement (tests/vcfio.py) on generated files -- "parity unpinned"
+// against htslib itself.
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
