@@ -13,7 +13,7 @@ REFS = [("chrM", 3000), ("chr1", 60000), ("chr2", 50000), ("chrUn", 5000)]
 
 
 def make_snps(rng, n=400):
-    chroms = ["chr1", "chr2"]                 # the VCF has no chrM / chrUn: reads there are skipped (:188-191)
+    chroms = ["chr1", "chr2"]                 # the VCF has no chrM / chrUn: reads there are skipped (:197-200)
     rid = np.sort(rng.integers(0, 2, n)).astype(np.int32)
     pos = np.zeros(n, np.int32)
     for r in (0, 1):
