@@ -261,8 +261,9 @@ const char* dmx_vcf_last_error(void);
 
 /* ---- BAM sweep (host only, no htslib; SURVEY 8f N4, BAM half; `path` may also be SAM text with its header) --------
  * The reference's walk over the position-sorted BAM next to the SNP list (cmd_cram_demuxlet.cpp:186-338): alignment
- * filter (sam_filtered_reader.cpp:284-296), barcode / UMI tags, RD.TOTL, and per overlapping SNP the base and quality
- * at the SNP position through the CIGAR (hts_utils.cpp:279-359), thresholds and the allele code (:304-325).  Emits one
+ * filter (sam_filtered_reader.cpp:284-296), barcode / UMI tags, RD.TOTL, and per SNP of the reference's SNP buffer
+ * (:202-237, restated exactly: in practice the SNPs under the read) the base and quality at the SNP position through
+ * the CIGAR (hts_utils.cpp:279-359), thresholds and the allele code (:304-325).  Emits one
  * tuple per scl.add_read call, in call order -- exactly the arrays dmx_pack_reads takes --, the barcodes in add_cell
  * order and cell_totl_reads.  SNPs: sorted by (rid, pos), ids = their index (the order of scl.add_snp); chroms[rid] are
  * the VCF's chromosome names. */
