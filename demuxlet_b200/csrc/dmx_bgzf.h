@@ -26,6 +26,8 @@
 #include <thread>
 #include <vector>
 
+#include "dmx_inflate.h"
+
 namespace dmx_io {
 
 // host threads to use: the CPUs this process may run on (<= 32), or the value of the environment variable `env_name`
@@ -210,7 +212,11 @@ class ByteStream {
     out->resize(at.back());
     std::atomic<size_t> nextb{0};
     std::atomic<bool> ok{true};
+    const bool zlib_only = getenv("DMX_IO_ZLIB") != nullptr;      // A / B switch: every block through zlib
     auto work = [&](int) {
+      // every block first through the block decoder of dmx_inflate.h; whatever it cannot vouch for -- wrong length, no
+      // clean end of stream, CRC-32 mismatch -- goes through zlib, whose verdict (with the same CRC check) stands
+      std::unique_ptr<FastInflate> fast(zlib_only ? nullptr : new FastInflate());
       z_stream zs;
       memset(&zs, 0, sizeof(zs));
       if (inflateInit2(&zs, -15) != Z_OK) { ok = false; return; }
@@ -219,17 +225,19 @@ class ByteStream {
         if (i >= nb) break;
         const Blk& bl = blocks[i];
         if (bl.isize == 0) continue;
+        uint32_t crc;
+        memcpy(&crc, map_ + bl.off + bl.size - 8, 4);
+        uint8_t* dst = out->data() + at[i];
+        if (fast && fast->run(map_ + bl.off + 18, bl.size - 26, dst, bl.isize) &&
+            (uint32_t)crc32(crc32(0L, Z_NULL, 0), dst, bl.isize) == crc)
+          continue;
         inflateReset(&zs);
         zs.next_in = const_cast<Bytef*>(map_ + bl.off + 18);
         zs.avail_in = (uInt)(bl.size - 26);
-        zs.next_out = out->data() + at[i];
+        zs.next_out = dst;
         zs.avail_out = bl.isize;
         const int rc = inflate(&zs, Z_FINISH);
-        uint32_t crc;
-        memcpy(&crc, map_ + bl.off + bl.size - 8, 4);
-        if (rc != Z_STREAM_END || zs.avail_out != 0 ||
-            (uint32_t)crc32(crc32(0L, Z_NULL, 0), out->data() + at[i], bl.isize) != crc)
-          ok = false;
+        if (rc != Z_STREAM_END || zs.avail_out != 0 || (uint32_t)crc32(crc32(0L, Z_NULL, 0), dst, bl.isize) != crc) ok = false;
       }
       inflateEnd(&zs);
     };

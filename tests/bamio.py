@@ -11,16 +11,16 @@ CIGAR_OPS = "MIDNSHP=X"
 SEQ_CODE = {c: i for i, c in enumerate("=ACMGRSVTWYHKDBN")}
 
 
-def bgzf_block(data: bytes) -> bytes:
+def bgzf_block(data: bytes, level: int = 6) -> bytes:
     """one BGZF block (SAM spec 4.1): gzip member with the BC extra subfield = total block size - 1"""
     import zlib
-    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    co = zlib.compressobj(level, zlib.DEFLATED, -15)
     c = co.compress(data) + co.flush()
     return (b"\x1f\x8b\x08\x04\0\0\0\0\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, len(c) + 25) + c +
             struct.pack("<II", zlib.crc32(data) & 0xffffffff, len(data)))
 
 
-def write_bam(path, refs, reads, member=4000, bgzf=False):
+def write_bam(path, refs, reads, member=4000, bgzf=False, level=6):
     """refs: [(name, length)]; reads: dicts tid, pos, mapq, flag, cigar [(op, len)], seq, qual (list of ints or None),
     tags [(tag, type, value)] with type in Z, i, A, B (B: list of uint8)"""
     text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join("@SQ\tSN:%s\tLN:%d\n" % r for r in refs)
@@ -51,7 +51,7 @@ def write_bam(path, refs, reads, member=4000, bgzf=False):
     with open(path, "wb") as f:
         if bgzf:                        # real BGZF blocks: the reader inflates them block-parallel
             for i in range(0, len(out), member):
-                f.write(bgzf_block(bytes(out[i:i + member])))
+                f.write(bgzf_block(bytes(out[i:i + member]), level))
             f.write(bgzf_block(b""))
             return
         for i in range(0, len(out), member):

@@ -267,6 +267,22 @@ def test_sweep_reads_standard_input(tmp_path):
     assert r.stdout.split() == [str(len(w["cell"])), str(int(w["snp"].sum())), str(int(w["totl"].sum())), str(len(w["barcodes"]))]
 
 
+@pytest.mark.parametrize("level,member", [(0, 5000), (1, 60000), (9, 60000), (6, 40)])
+def test_block_decoder_on_every_kind_of_deflate_block(level, member, tmp_path, monkeypatch):
+    """BGZF blocks go through the block decoder of csrc/dmx_inflate.h first and through zlib when it cannot vouch for
+    its output (length, end of stream, CRC-32): stored blocks (level 0), fixed-Huffman blocks (tiny payloads), dynamic
+    ones at the fastest and the best setting -- the same tuples with the decoder and with zlib alone (DMX_IO_ZLIB)"""
+    rng = np.random.default_rng(51)
+    chroms, rid, pos, ref, alt = make_snps(rng)
+    reads, _ = bamio.random_reads(rng, REFS, {1: pos[rid == 0], 2: pos[rid == 1]}, 1500)
+    path = str(tmp_path / "a.bam")
+    bamio.write_bam(path, REFS, reads, member=member, bgzf=True, level=level)
+    want = bamio.sweep(REFS, reads, chroms, rid, pos, ref, alt)
+    same(api.sweep_bam(path, chroms, rid, pos, ref, alt), want)
+    monkeypatch.setenv("DMX_IO_ZLIB", "1")
+    same(api.sweep_bam(path, chroms, rid, pos, ref, alt), want)
+
+
 def test_sweep_feeds_the_packer(tmp_path):
     """sweep tuples -> dmx_pack_reads == the python container restatement on the same tuples"""
     from demuxlet_b200.plp import build_from_reads
